@@ -1,0 +1,101 @@
+"""ctypes binding of libdrs_b200.so (include/drs_b200.h).
+
+There is no CPU fallback: if the library is missing or a call fails, an
+exception is raised.  Status codes map to the exceptions the reference's igraph
+calls would raise (ValueError for bad vertices / arguments).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdrs_b200.so")
+
+MODE_F32 = 0
+MODE_I32 = 1
+FW_TILE = 128
+I32_INF = 0x3FFFFFFF
+
+ERR_ARG, ERR_CUDA, ERR_STATE, ERR_NOMEM, ERR_RANGE, ERR_CAPACITY = -1, -2, -3, -4, -5, -6
+
+
+class DrsError(RuntimeError):
+    """A libdrs_b200 call failed for a reason that is not the caller's argument."""
+
+
+_lib = None
+
+_i32p = C.POINTER(C.c_int32)
+_f64p = C.POINTER(C.c_double)
+_vp = C.c_void_p
+
+# name -> (restype, argtypes); kept in one table so tests can check that every
+# symbol declared in include/drs_b200.h is exported and bound.
+SIGNATURES = {
+    "drs_last_error": (C.c_char_p, []),
+    "drs_version": (C.c_int, []),
+    "drs_graph_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _i32p, _i32p, _f64p, _f64p, C.POINTER(_vp)]),
+    "drs_graph_set_weights": (C.c_int, [_vp, _f64p]),
+    "drs_graph_destroy": (C.c_int, [_vp]),
+    "drs_graph_info": (C.c_int, [_vp, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p]),
+    "drs_apsp_build": (C.c_int, [_vp, C.c_int32]),
+    "drs_apsp_matrices": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_int64)]),
+    "drs_apsp_adopt": (C.c_int, [_vp, C.c_int32, _vp, _vp, C.c_int64]),
+    "drs_apsp_rows_to_host": (C.c_int, [_vp, C.c_int32, C.c_int32, _f64p]),
+    "drs_fw_init": (C.c_int, [_vp, C.c_int32, _vp, C.c_int64, C.c_int32, C.c_int32, _vp]),
+    "drs_fw_pivot_row": (C.c_int, [C.c_int32, _vp, C.c_int64, C.c_int32, _vp]),
+    "drs_fw_update": (C.c_int, [C.c_int32, _vp, C.c_int64, C.c_int32, _vp, C.c_int32, C.c_int32, C.c_int32,
+                                C.c_int32, _vp]),
+    "drs_pred_build": (C.c_int, [_vp, C.c_int32, _vp, C.c_int64, C.c_int32, C.c_int32, _vp, _vp]),
+    "drs_query_pairs": (C.c_int, [_vp, C.c_int32, _i32p, _i32p, _f64p, _f64p, _i32p]),
+    "drs_query_matrix": (C.c_int, [_vp, C.c_int32, _i32p, _i32p, _f64p]),
+    "drs_path": (C.c_int, [_vp, C.c_int32, C.c_int32, _i32p, _i32p, _i32p]),
+    "drs_alu_peak": (C.c_int, [C.c_int32, C.c_int32, _f64p]),
+}
+
+
+def load():
+    """Load the shared library, binding every entry point.  Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DrsError(
+            "libdrs_b200.so is not built (%s). Run `python -m drs_abm_b200.build`; "
+            "there is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, lib=None):
+    if rc == 0:
+        return
+    lib = lib or load()
+    msg = lib.drs_last_error().decode("utf-8", "replace")
+    if rc in (ERR_ARG, ERR_RANGE, ERR_CAPACITY):
+        raise ValueError(msg)
+    if rc == ERR_NOMEM:
+        raise MemoryError(msg)
+    raise DrsError("libdrs_b200 error %d: %s" % (rc, msg))
+
+
+def as_i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def as_f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def ptr_i32(a):
+    return a.ctypes.data_as(_i32p)
+
+
+def ptr_f64(a):
+    return a.ctypes.data_as(_f64p)

@@ -1,0 +1,83 @@
+// Internal definitions shared by the translation units of libdrs_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <cstdarg>
+#include <cstdio>
+#include <vector>
+
+#include "drs_b200.h"
+
+void drs_set_error(const char* fmt, ...);
+
+#define DRS_CUDA(call)                                                                      \
+  do {                                                                                      \
+    cudaError_t e_ = (call);                                                                \
+    if (e_ != cudaSuccess) {                                                                \
+      drs_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__,       \
+                    __LINE__);                                                              \
+      return DRS_ERR_CUDA;                                                                  \
+    }                                                                                       \
+  } while (0)
+
+#define DRS_REQUIRE(cond, code, ...)    \
+  do {                                  \
+    if (!(cond)) {                      \
+      drs_set_error(__VA_ARGS__);       \
+      return (code);                    \
+    }                                   \
+  } while (0)
+
+// Host-side graph handle.  Device arrays live on `device`.
+struct drs_graph {
+  int device = 0;
+  int n = 0, m = 0, directed = 0;
+  int npad = 0;  // n rounded up to DRS_FW_TILE
+  int narcs = 0; // directed arcs in the CSR (m or 2m)
+
+  // host copies of the edge list (edge id = position)
+  std::vector<int32_t> h_src, h_dst;
+  std::vector<double> h_tt, h_len;
+
+  // per-edge attributes on device, indexed by edge id
+  int32_t* d_esrc = nullptr;
+  int32_t* d_edst = nullptr;
+  double* d_tt64 = nullptr;
+  double* d_len64 = nullptr;
+
+  // out-adjacency CSR (arc u -> col[a]) and in-adjacency CSR (arc in_src[a] -> v)
+  int32_t* d_out_ptr = nullptr;
+  int32_t* d_out_col = nullptr;
+  int32_t* d_out_eid = nullptr;
+  float* d_out_w = nullptr;
+  int32_t* d_in_ptr = nullptr;
+  int32_t* d_in_src = nullptr;
+  int32_t* d_in_eid = nullptr;
+  float* d_in_w = nullptr;
+
+  // resident matrices
+  int mode = DRS_MODE_F32;
+  bool apsp_valid = false;
+  bool owns_matrices = false;
+  void* d_dist = nullptr;
+  int32_t* d_pred = nullptr;
+  int64_t ld = 0;
+
+  cudaStream_t stream = nullptr;
+};
+
+int drs_graph_upload_weights(drs_graph* g);
+
+// RAII device guard
+struct DrsDeviceGuard {
+  int prev = -1;
+  explicit DrsDeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DrsDeviceGuard() {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (cur != prev && prev >= 0) cudaSetDevice(prev);
+  }
+};

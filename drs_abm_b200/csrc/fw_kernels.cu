@@ -1,0 +1,389 @@
+// Blocked min-plus Floyd-Warshall for sm_100a (K1 in SURVEY.md section 2).
+//
+// Replaces the per-query Dijkstra of the reference (lib/RoutingEngine.py:87,199,212;
+// lib/optimUtils.py:528,531,659) by one all-pairs travel-time matrix.
+//
+// Layout: row-major matrix, leading dimension ld (multiple of 128), element type
+// float (DRS_MODE_F32) or int32 (DRS_MODE_I32).  Round kb of the blocked
+// algorithm touches
+//   phase 1  the diagonal tile (kb,kb): closed in shared memory by one CTA;
+//   phase 2  the pivot row panel  C[kb,j] = D* (x) C[kb,j]  and the pivot column
+//            panel C[i,kb] = C[i,kb] (x) D*  (D* = closed diagonal tile);
+//   phase 3  every other tile    C[i,j] = min(C[i,j], C[i,kb] (x) C[kb,j]).
+// Phases 2 and 3 are the same kernel: a 128x128x128 min-plus tile product whose
+// accumulators start from the C tile.  Per CTA: 256 threads, an 8x8 register
+// tile per thread, A/B streamed through a 3-stage cp.async ring in 32-wide k
+// chunks.  The work is ALU-bound (one add + one min per relaxation, two issue
+// slots); HBM traffic per round is one read + one write of the matrix, a factor
+// ~5 below the ALU time at tile width 128 (kernel K1).
+#include "drs_common.cuh"
+
+namespace {
+
+constexpr int TILE = DRS_FW_TILE;  // 128
+constexpr int KC = 32;             // k chunk streamed per pipeline stage
+constexpr int STAGES = 3;
+constexpr int APAD = KC + 4;       // padded row of the A chunk (keeps 16 B alignment)
+constexpr int NTHREADS = 256;
+
+template <typename T> struct Semiring;
+template <> struct Semiring<float> {
+  static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
+  // acc = min(acc, a0+b0, a1+b1): two FADD + one 3-input FMNMX3 (sm_100+)
+  static __device__ __forceinline__ float relax2(float acc, float a0, float b0, float a1, float b1) {
+    float d;
+    float s0 = a0 + b0, s1 = a1 + b1;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(acc), "f"(s0), "f"(s1));
+    return d;
+  }
+  static __device__ __forceinline__ float relax1(float acc, float a, float b) { return fminf(acc, a + b); }
+};
+template <> struct Semiring<int> {
+  static __device__ __forceinline__ int inf() { return DRS_I32_INF; }
+  // VIADDMNMX: add and min in one DPX instruction
+  static __device__ __forceinline__ int relax2(int acc, int a0, int b0, int a1, int b1) {
+    return __viaddmin_s32(a1, b1, __viaddmin_s32(a0, b0, acc));
+  }
+  static __device__ __forceinline__ int relax1(int acc, int a, int b) { return __viaddmin_s32(a, b, acc); }
+};
+
+template <typename T> struct Vec4;
+template <> struct Vec4<float> { using type = float4; };
+template <> struct Vec4<int> { using type = int4; };
+template <typename T> struct Vec2;
+template <> struct Vec2<float> { using type = float2; };
+template <> struct Vec2<int> { using type = int2; };
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N));
+}
+
+// Tile operands are addressed as base + i*si + j*sj (element strides), i = blockIdx.y
+// (+ i_off), j = blockIdx.x.
+template <typename T> struct TileArgs {
+  const T* A; int64_t a_si, a_sj, lda;
+  const T* B; int64_t b_si, b_sj, ldb;
+  T* C;       int64_t c_si, c_sj, ldc;
+  int i_off;   // first block-row index handled by blockIdx.y == 0
+  int skip_i;  // block-row to skip (-1: none), compared against i_off + blockIdx.y
+  int skip_j;  // block-column to skip (-1: none)
+};
+
+template <typename T>
+__global__ void __launch_bounds__(NTHREADS, 2) fw_minplus_tile_kernel(TileArgs<T> p) {
+  using V4 = typename Vec4<T>::type;
+  using V2 = typename Vec2<T>::type;
+  const int bi = p.i_off + blockIdx.y, bj = blockIdx.x;
+  if (bi == p.skip_i || bj == p.skip_j) return;
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T(*As)[TILE][APAD] = reinterpret_cast<T(*)[TILE][APAD]>(smem_raw);
+  T(*Bs)[KC][TILE] = reinterpret_cast<T(*)[KC][TILE]>(smem_raw + sizeof(T) * STAGES * TILE * APAD);
+
+  const T* __restrict__ A = p.A + bi * p.a_si + bj * p.a_sj;
+  const T* __restrict__ B = p.B + bi * p.b_si + bj * p.b_sj;
+  T* __restrict__ C = p.C + bi * p.c_si + bj * p.c_sj;
+
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+
+  auto load_chunk = [&](int kc, int stage) {
+    const int k0 = kc * KC;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {   // A chunk: 128 rows x 32 k
+      const int v = tid + NTHREADS * q;
+      const int row = v >> 3, cv = v & 7;
+      cp_async16(&As[stage][row][cv * 4], A + (int64_t)row * p.lda + k0 + cv * 4);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {   // B chunk: 32 k x 128 columns
+      const int v = tid + NTHREADS * q;
+      const int row = v >> 5, cv = v & 31;
+      cp_async16(&Bs[stage][row][cv * 4], B + (int64_t)(k0 + row) * p.ldb + cv * 4);
+    }
+  };
+
+  constexpr int NCHUNK = TILE / KC;
+  load_chunk(0, 0);
+  cp_async_commit();
+  load_chunk(1, 1);
+  cp_async_commit();
+
+  // accumulators start from the C tile: rows ty+16r, columns tx*4.. and 64+tx*4..
+  T acc[8][8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const T* crow = C + (int64_t)(ty + 16 * r) * p.ldc;
+    V4 lo = *reinterpret_cast<const V4*>(crow + tx * 4);
+    V4 hi = *reinterpret_cast<const V4*>(crow + 64 + tx * 4);
+    acc[r][0] = lo.x; acc[r][1] = lo.y; acc[r][2] = lo.z; acc[r][3] = lo.w;
+    acc[r][4] = hi.x; acc[r][5] = hi.y; acc[r][6] = hi.z; acc[r][7] = hi.w;
+  }
+
+#pragma unroll 1
+  for (int kc = 0; kc < NCHUNK; ++kc) {
+    const int stage = kc % STAGES;
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    if (kc + STAGES - 1 < NCHUNK) load_chunk(kc + STAGES - 1, (kc + STAGES - 1) % STAGES);
+    cp_async_commit();
+
+#pragma unroll
+    for (int kk = 0; kk < KC; kk += 2) {   // two k per step: acc = min3(acc, a0+b0, a1+b1)
+      V2 a[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) a[r] = *reinterpret_cast<const V2*>(&As[stage][ty + 16 * r][kk]);
+      const V4 b0l = *reinterpret_cast<const V4*>(&Bs[stage][kk][tx * 4]);
+      const V4 b0h = *reinterpret_cast<const V4*>(&Bs[stage][kk][64 + tx * 4]);
+      const V4 b1l = *reinterpret_cast<const V4*>(&Bs[stage][kk + 1][tx * 4]);
+      const V4 b1h = *reinterpret_cast<const V4*>(&Bs[stage][kk + 1][64 + tx * 4]);
+      const T b0[8] = {b0l.x, b0l.y, b0l.z, b0l.w, b0h.x, b0h.y, b0h.z, b0h.w};
+      const T b1[8] = {b1l.x, b1l.y, b1l.z, b1l.w, b1h.x, b1h.y, b1h.z, b1h.w};
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[r][c] = Semiring<T>::relax2(acc[r][c], a[r].x, b0[c], a[r].y, b1[c]);
+    }
+  }
+  cp_async_wait<0>();
+
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    T* crow = C + (int64_t)(ty + 16 * r) * p.ldc;
+    V4 lo, hi;
+    lo.x = acc[r][0]; lo.y = acc[r][1]; lo.z = acc[r][2]; lo.w = acc[r][3];
+    hi.x = acc[r][4]; hi.y = acc[r][5]; hi.z = acc[r][6]; hi.w = acc[r][7];
+    *reinterpret_cast<V4*>(crow + tx * 4) = lo;
+    *reinterpret_cast<V4*>(crow + 64 + tx * 4) = hi;
+  }
+}
+
+constexpr size_t kTileSmemBytes = sizeof(float) * STAGES * (TILE * APAD + KC * TILE);
+
+// Phase 1: close the 128x128 diagonal tile in shared memory (classic FW, one CTA).
+constexpr int P1PAD = TILE + 4;
+template <typename T>
+__global__ void __launch_bounds__(1024, 1) fw_diag_kernel(T* D, int64_t ld) {
+  using V4 = typename Vec4<T>::type;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T(*s)[P1PAD] = reinterpret_cast<T(*)[P1PAD]>(smem_raw);
+  const int tid = threadIdx.x;
+  const int tx = tid & 31, ty = tid >> 5;  // thread owns rows ty*4..+3, columns tx*4..+3
+  V4 c[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    c[r] = *reinterpret_cast<const V4*>(D + (int64_t)(ty * 4 + r) * ld + tx * 4);
+    *reinterpret_cast<V4*>(&s[ty * 4 + r][tx * 4]) = c[r];
+  }
+  __syncthreads();
+  for (int k = 0; k < TILE; ++k) {
+    const V4 bk = *reinterpret_cast<const V4*>(&s[k][tx * 4]);
+    T a[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) a[r] = s[ty * 4 + r][k];
+    __syncthreads();   // all reads of iteration k done before anyone overwrites
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      c[r].x = Semiring<T>::relax1(c[r].x, a[r], bk.x);
+      c[r].y = Semiring<T>::relax1(c[r].y, a[r], bk.y);
+      c[r].z = Semiring<T>::relax1(c[r].z, a[r], bk.z);
+      c[r].w = Semiring<T>::relax1(c[r].w, a[r], bk.w);
+      *reinterpret_cast<V4*>(&s[ty * 4 + r][tx * 4]) = c[r];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) *reinterpret_cast<V4*>(D + (int64_t)(ty * 4 + r) * ld + tx * 4) = c[r];
+}
+constexpr size_t kDiagSmemBytes = sizeof(float) * TILE * P1PAD;
+
+// dist[i][j] = (row0+i == j) ? 0 : inf
+template <typename T>
+__global__ void fw_fill_kernel(T* local, int64_t ld, int row0, int nrows) {
+  const int64_t total = (int64_t)nrows * ld;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / ld), j = (int)(idx % ld);
+    local[idx] = (row0 + i == j) ? (T)0 : Semiring<T>::inf();
+  }
+}
+
+// scatter arcs u->v (out CSR) into the rows owned by this shard; multi-edges keep the minimum
+template <typename T>
+__global__ void fw_scatter_kernel(T* local, int64_t ld, int row0, int nrows, const int32_t* out_ptr,
+                                  const int32_t* out_col, const float* out_w) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrows) return;
+  const int u = row0 + i;
+  for (int a = out_ptr[u]; a < out_ptr[u + 1]; ++a) {
+    const int v = out_col[a];
+    if (v == u) continue;
+    T w = (T)out_w[a];
+    T* cell = local + (int64_t)i * ld + v;
+    if (w < *cell) *cell = w;   // one thread per row: no race
+  }
+}
+
+// Canonical predecessor edge: among in-arcs (u->t, w, eid) minimise
+// (dist[s,u] + w, dist[s,u], eid) lexicographically.
+template <typename T>
+__global__ void pred_kernel(const T* __restrict__ local, int64_t ld, int row0, int nrows, int n,
+                            const int32_t* __restrict__ in_ptr, const int32_t* __restrict__ in_src,
+                            const int32_t* __restrict__ in_eid, const float* __restrict__ in_w,
+                            int32_t* __restrict__ pred) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ls = blockIdx.y;
+  if (t >= ld || ls >= nrows) return;
+  const int s = row0 + ls;
+  const T* row = local + (int64_t)ls * ld;
+  int best_e = -1;
+  if (t < n && s < n && t != s && row[t] < Semiring<T>::inf()) {
+    T best_c = Semiring<T>::inf(), best_du = Semiring<T>::inf();
+    const int a1 = in_ptr[t + 1];
+    for (int a = in_ptr[t]; a < a1; ++a) {
+      const int u = in_src[a];
+      const T du = row[u];
+      if (!(du < Semiring<T>::inf())) continue;
+      const T cand = du + (T)in_w[a];
+      const int e = in_eid[a];
+      if (cand < best_c || (cand == best_c && (du < best_du || (du == best_du && e < best_e)))) {
+        best_c = cand; best_du = du; best_e = e;
+      }
+    }
+  }
+  pred[(int64_t)ls * ld + t] = best_e;
+}
+
+template <typename T>
+int launch_tile(const TileArgs<T>& p, dim3 grid, cudaStream_t st) {
+  static bool configured[64] = {};   // per device: opt in to >48 KB dynamic shared memory once
+  int dev = 0;
+  DRS_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    DRS_CUDA(cudaFuncSetAttribute(fw_minplus_tile_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)kTileSmemBytes));
+    DRS_CUDA(cudaFuncSetAttribute(fw_diag_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)kDiagSmemBytes));
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
+  if (grid.x == 0 || grid.y == 0) return DRS_OK;
+  fw_minplus_tile_kernel<T><<<grid, NTHREADS, kTileSmemBytes, st>>>(p);
+  DRS_CUDA(cudaGetLastError());
+  return DRS_OK;
+}
+
+template <typename T>
+int pivot_row_impl(T* panel, int64_t ld, int kb, cudaStream_t st) {
+  const int nb = (int)(ld / TILE);
+  T* diag = panel + (int64_t)kb * TILE;
+  TileArgs<T> p{};
+  // make sure attributes are configured before the first diag launch
+  p.A = diag; p.a_si = 0; p.a_sj = 0; p.lda = ld;
+  p.B = panel; p.b_si = 0; p.b_sj = TILE; p.ldb = ld;
+  p.C = panel; p.c_si = 0; p.c_sj = TILE; p.ldc = ld;
+  p.i_off = 0; p.skip_i = -1; p.skip_j = kb;
+  int rc = launch_tile<T>(p, dim3(0, 0), st);   // configure only
+  if (rc) return rc;
+  fw_diag_kernel<T><<<1, 1024, kDiagSmemBytes, st>>>(diag, ld);
+  DRS_CUDA(cudaGetLastError());
+  return launch_tile<T>(p, dim3(nb, 1), st);
+}
+
+template <typename T>
+int update_impl(T* local, int64_t ld, int nrows, const T* panel, int kb, int skip_local, int blo,
+                int bhi, cudaStream_t st) {
+  const int nb = (int)(ld / TILE);
+  if (bhi <= blo) return DRS_OK;
+  const T* diag = panel + (int64_t)kb * TILE;
+  // phase 2, column part: C[i,kb] = C[i,kb] (x) D*
+  TileArgs<T> q{};
+  q.A = local + (int64_t)kb * TILE; q.a_si = (int64_t)TILE * ld; q.a_sj = 0; q.lda = ld;
+  q.B = diag; q.b_si = 0; q.b_sj = 0; q.ldb = ld;
+  q.C = local + (int64_t)kb * TILE; q.c_si = (int64_t)TILE * ld; q.c_sj = 0; q.ldc = ld;
+  q.i_off = blo; q.skip_i = skip_local; q.skip_j = -1;
+  int rc = launch_tile<T>(q, dim3(1, bhi - blo), st);
+  if (rc) return rc;
+  // phase 3: C[i,j] = min(C[i,j], C[i,kb] (x) panel[kb,j])
+  TileArgs<T> p{};
+  p.A = local + (int64_t)kb * TILE; p.a_si = (int64_t)TILE * ld; p.a_sj = 0; p.lda = ld;
+  p.B = panel; p.b_si = 0; p.b_sj = TILE; p.ldb = ld;
+  p.C = local; p.c_si = (int64_t)TILE * ld; p.c_sj = TILE; p.ldc = ld;
+  p.i_off = blo; p.skip_i = skip_local; p.skip_j = kb;
+  return launch_tile<T>(p, dim3(nb, bhi - blo), st);
+}
+
+}  // namespace
+
+extern "C" int drs_fw_init(const drs_graph* g, int32_t mode, void* local_dev, int64_t ld, int32_t row0,
+                           int32_t nrows, void* stream) {
+  DRS_REQUIRE(g && local_dev, DRS_ERR_ARG, "drs_fw_init: null argument");
+  DRS_REQUIRE(ld == g->npad && row0 >= 0 && nrows >= 0 && row0 + nrows <= g->npad, DRS_ERR_ARG,
+              "drs_fw_init: bad shard (ld=%lld row0=%d nrows=%d npad=%d)", (long long)ld, row0, nrows, g->npad);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (nrows == 0) return DRS_OK;
+  const int nreal = max(0, min(nrows, g->n - row0));   // rows that are real vertices
+  if (mode == DRS_MODE_F32) {
+    fw_fill_kernel<float><<<148 * 8, 256, 0, st>>>((float*)local_dev, ld, row0, nrows);
+    if (nreal > 0)
+      fw_scatter_kernel<float><<<(nreal + 127) / 128, 128, 0, st>>>((float*)local_dev, ld, row0, nreal,
+                                                                     g->d_out_ptr, g->d_out_col, g->d_out_w);
+  } else if (mode == DRS_MODE_I32) {
+    fw_fill_kernel<int><<<148 * 8, 256, 0, st>>>((int*)local_dev, ld, row0, nrows);
+    if (nreal > 0)
+      fw_scatter_kernel<int><<<(nreal + 127) / 128, 128, 0, st>>>((int*)local_dev, ld, row0, nreal,
+                                                                   g->d_out_ptr, g->d_out_col, g->d_out_w);
+  } else {
+    DRS_REQUIRE(false, DRS_ERR_ARG, "drs_fw_init: unknown mode %d", mode);
+  }
+  DRS_CUDA(cudaGetLastError());
+  return DRS_OK;
+}
+
+extern "C" int drs_fw_pivot_row(int32_t mode, void* panel_dev, int64_t ld, int32_t kb, void* stream) {
+  DRS_REQUIRE(panel_dev && ld > 0 && ld % TILE == 0 && kb >= 0 && kb < ld / TILE, DRS_ERR_ARG,
+              "drs_fw_pivot_row: bad argument (ld=%lld kb=%d)", (long long)ld, kb);
+  if (mode == DRS_MODE_F32) return pivot_row_impl<float>((float*)panel_dev, ld, kb, (cudaStream_t)stream);
+  if (mode == DRS_MODE_I32) return pivot_row_impl<int>((int*)panel_dev, ld, kb, (cudaStream_t)stream);
+  DRS_REQUIRE(false, DRS_ERR_ARG, "drs_fw_pivot_row: unknown mode %d", mode);
+}
+
+extern "C" int drs_fw_update(int32_t mode, void* local_dev, int64_t ld, int32_t nrows, const void* panel_dev,
+                             int32_t kb, int32_t skip_local_block, int32_t block_lo, int32_t block_hi,
+                             void* stream) {
+  DRS_REQUIRE(local_dev && panel_dev && ld > 0 && ld % TILE == 0 && nrows % TILE == 0 && kb >= 0 &&
+                  kb < ld / TILE && block_lo >= 0 && block_hi <= nrows / TILE,
+              DRS_ERR_ARG, "drs_fw_update: bad argument (ld=%lld nrows=%d kb=%d blocks=[%d,%d))",
+              (long long)ld, nrows, kb, block_lo, block_hi);
+  if (mode == DRS_MODE_F32)
+    return update_impl<float>((float*)local_dev, ld, nrows, (const float*)panel_dev, kb, skip_local_block,
+                              block_lo, block_hi, (cudaStream_t)stream);
+  if (mode == DRS_MODE_I32)
+    return update_impl<int>((int*)local_dev, ld, nrows, (const int*)panel_dev, kb, skip_local_block,
+                            block_lo, block_hi, (cudaStream_t)stream);
+  DRS_REQUIRE(false, DRS_ERR_ARG, "drs_fw_update: unknown mode %d", mode);
+}
+
+extern "C" int drs_pred_build(const drs_graph* g, int32_t mode, const void* local_dev, int64_t ld,
+                              int32_t row0, int32_t nrows, int32_t* pred_local_dev, void* stream) {
+  DRS_REQUIRE(g && local_dev && pred_local_dev, DRS_ERR_ARG, "drs_pred_build: null argument");
+  DRS_REQUIRE(ld == g->npad && row0 >= 0 && nrows >= 0 && row0 + nrows <= g->npad, DRS_ERR_ARG,
+              "drs_pred_build: bad shard");
+  if (nrows == 0) return DRS_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((unsigned)((ld + 255) / 256), (unsigned)nrows);
+  if (mode == DRS_MODE_F32)
+    pred_kernel<float><<<grid, 256, 0, st>>>((const float*)local_dev, ld, row0, nrows, g->n, g->d_in_ptr,
+                                             g->d_in_src, g->d_in_eid, g->d_in_w, pred_local_dev);
+  else if (mode == DRS_MODE_I32)
+    pred_kernel<int><<<grid, 256, 0, st>>>((const int*)local_dev, ld, row0, nrows, g->n, g->d_in_ptr,
+                                           g->d_in_src, g->d_in_eid, g->d_in_w, pred_local_dev);
+  else
+    DRS_REQUIRE(false, DRS_ERR_ARG, "drs_pred_build: unknown mode %d", mode);
+  DRS_CUDA(cudaGetLastError());
+  return DRS_OK;
+}
