@@ -30,6 +30,24 @@ _i32p = C.POINTER(C.c_int32)
 _f64p = C.POINTER(C.c_double)
 _vp = C.c_void_p
 
+_i8p = C.POINTER(C.c_int8)
+_u8p = C.POINTER(C.c_uint8)
+_i64p = C.POINTER(C.c_int64)
+
+
+class VehicleBatch(C.Structure):
+    """drs_vehicle_batch (include/drs_b200.h)."""
+    _fields_ = [("n_veh", C.c_int32), ("start_node", _i32p), ("start_delay", _f64p), ("capacity", _i32p),
+                ("onboard", _i32p), ("stop_off", _i32p), ("stop_node", _i32p), ("stop_rid", _i32p),
+                ("stop_pod", _i8p), ("stop_prev", _i8p), ("stop_lb", _f64p), ("stop_ub", _f64p)]
+
+
+class RequestBatch(C.Structure):
+    """drs_request_batch (include/drs_b200.h)."""
+    _fields_ = [("n_req", C.c_int32), ("rid", _i32p), ("o_node", _i32p), ("d_node", _i32p), ("lb_p", _f64p),
+                ("ub_p", _f64p), ("lb_d", _f64p), ("ub_d", _f64p)]
+
+
 # name -> (restype, argtypes); kept in one table so tests can check that every
 # symbol declared in include/drs_b200.h is exported and bound.
 SIGNATURES = {
@@ -52,6 +70,14 @@ SIGNATURES = {
     "drs_query_matrix": (C.c_int, [_vp, C.c_int32, _i32p, _i32p, _f64p]),
     "drs_path": (C.c_int, [_vp, C.c_int32, C.c_int32, _i32p, _i32p, _i32p]),
     "drs_alu_peak": (C.c_int, [C.c_int32, C.c_int32, _f64p]),
+    "drs_tick_create": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "drs_tick_destroy": (C.c_int, [_vp]),
+    "drs_tick_set_vehicles": (C.c_int, [_vp, C.POINTER(VehicleBatch)]),
+    "drs_tick_set_requests": (C.c_int, [_vp, C.POINTER(RequestBatch)]),
+    "drs_tick_rv_eval": (C.c_int, [_vp, C.c_double, C.c_int32, _i32p, _i64p]),
+    "drs_tick_rv_fetch": (C.c_int, [_vp, C.c_int32, _i32p, _i32p, _f64p, _u8p, _i32p]),
+    "drs_tick_trip_eval": (C.c_int, [_vp, C.c_double, C.c_int32, C.c_int32, _i32p, _i32p, _i32p, _f64p, _u8p,
+                                     _i32p]),
 }
 
 

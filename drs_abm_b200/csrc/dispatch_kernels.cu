@@ -1,0 +1,585 @@
+// Per-tick vehicle-by-request evaluation (K3 in SURVEY.md section 2).
+//
+// Replaces the Python loops of AlonsoMora.generatePairwiseGraph / generateRTVGraph
+// with routing_method "enumerate" (lib/Optimization.py:104-357) and the functions
+// they call (lib/optimUtils.py: findOptimalRouting :113-160, minimalDelayPath
+// :432-453, permutePassengerOrder :41-81, computeRoutingCost :456-557,
+// shortestPathTime :656-664).  All arithmetic that decides feasibility or cost is
+// fp64 in the reference's operation order, so integer-weighted inputs give
+// bit-identical costs; travel times are gathered from the resident matrix.
+//
+// Two kernels:
+//   rv_filter_kernel   one thread per (request, vehicle) pair: the reachability
+//                      pre-filter (lib/Optimization.py:183-186) and the
+//                      empty-dummy-vehicle check (:193-202); survivors are appended
+//                      to a compact task list.
+//   trip_eval_kernel   one thread per task: gathers the (S+1)^2 travel times among
+//                      the task's vertices, runs the pairwise pre-checks
+//                      (lib/optimUtils.py:127-156) and a depth-first enumeration of
+//                      the precedence-respecting orderings in lexicographic order
+//                      with exact feasibility / cost-bound pruning.
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+
+#include "drs_common.cuh"
+
+namespace {
+
+constexpr int MAXS = DRS_MAX_STOPS;
+constexpr int MAXR = DRS_MAX_TRIP_REQS;
+
+struct TickDev {
+  // vehicles
+  int n_veh = 0, n_stops = 0;
+  int32_t *v_node = nullptr, *v_cap = nullptr, *v_pax = nullptr, *v_off = nullptr;
+  double* v_delay = nullptr;
+  int32_t *s_node = nullptr, *s_rid = nullptr;
+  int8_t *s_pod = nullptr, *s_prev = nullptr;
+  double *s_lb = nullptr, *s_ub = nullptr;
+  // requests
+  int n_req = 0;
+  int32_t *r_rid = nullptr, *r_o = nullptr, *r_d = nullptr;
+  double *r_lbp = nullptr, *r_ubp = nullptr, *r_lbd = nullptr, *r_ubd = nullptr;
+};
+
+struct DistView {
+  const void* dist;
+  int64_t ld;
+  int mode;
+  __device__ __forceinline__ double at(int a, int b) const {
+    if (mode == DRS_MODE_F32) return (double)((const float*)dist)[(int64_t)a * ld + b];
+    const int d = ((const int*)dist)[(int64_t)a * ld + b];
+    return d >= DRS_I32_INF ? __longlong_as_double(0x7ff0000000000000LL) : (double)d;
+  }
+};
+
+// One evaluation problem in thread-local storage.  Vertex 0 of `tt` is the start.
+struct Trip {
+  int ns;                 // stops
+  int has_start;          // 1: vertex 0 is the vehicle's next node; 0: route starts at its first stop
+  double t_start;         // T + veh["t"]  (or T without a vehicle)
+  double cap;             // capacity (1e6 when unconstrained, lib/optimUtils.py:432)
+  int pax0;               // passengers on board at the start
+  int node[MAXS + 1];
+  double lb[MAXS], ub[MAXS];
+  int8_t pod[MAXS], prev[MAXS];
+  int group[MAXS];        // request group of each stop (for the pairwise pre-checks)
+  double tt[(MAXS + 1) * (MAXS + 1)];   // travel times among the trip's vertices (matrix entries, exact)
+};
+
+__device__ __forceinline__ double trip_tt(const Trip& tr, int a, int b) {
+  return tr.tt[a * (MAXS + 1) + b];
+}
+
+// Depth-first enumeration over the stops in `subset` (bit mask).  Mirrors
+// minimalDelayPath + computeRoutingCost (lib/optimUtils.py:432-557):
+//   arrival_k = t_start + (((0 + seg_0) + seg_1) + ... + seg_k)        (:536)
+//   feasible  = pax <= capacity at every stop (:488-492) and lb <= arrival <= ub (:540-545)
+//   cost      = sum over drop-offs of (arrival - lb)                    (:549-550)
+// Orderings are visited in lexicographic stop-index order and only a strictly
+// smaller cost replaces the incumbent (:447), i.e. the canonical tie rule.
+// first_only: return as soon as one feasible complete ordering is found.
+__device__ double trip_dfs(const Trip& tr, unsigned subset, double cap, int pax0, bool first_only,
+                           uint8_t* best_order) {
+  const int total = __popc(subset);
+  double best = DRS_INF_ROUTE_COST;
+  int ord[MAXS];
+  int cand[MAXS + 1];
+  double psum[MAXS + 1], cost[MAXS + 1];
+  int pax[MAXS + 1], cur[MAXS + 1];
+  unsigned used = 0;
+  int d = 0;
+  cand[0] = 0; psum[0] = 0.0; cost[0] = 0.0; pax[0] = pax0; cur[0] = 0;
+  while (d >= 0) {
+    int i = cand[d];
+    // next admissible stop at this depth
+    while (i < tr.ns) {
+      const unsigned bit = 1u << i;
+      if ((subset & bit) && !(used & bit)) {
+        const int pv = tr.prev[i];
+        if (pv < 0 || !((subset >> pv) & 1u) || ((used >> pv) & 1u)) break;
+      }
+      ++i;
+    }
+    if (i >= tr.ns) {   // exhausted: backtrack
+      --d;
+      if (d >= 0) { used &= ~(1u << ord[d]); }
+      continue;
+    }
+    cand[d] = i + 1;
+    double np, nc;
+    int npax;
+    if (d == 0 && !tr.has_start) {
+      // no vehicle: the first stop is the start; never capacity-counted nor window-checked
+      // (lib/optimUtils.py:475-488,540 iterate over orderedLocs[1:])
+      np = 0.0; nc = 0.0; npax = pax0;
+    } else {
+      npax = pax[d] + tr.pod[i];
+      if ((double)npax > cap) continue;
+      np = psum[d] + trip_tt(tr, cur[d], i + 1);
+      const double arr = tr.t_start + np;
+      if (!(arr >= tr.lb[i] && arr <= tr.ub[i])) continue;
+      nc = cost[d];
+      if (tr.pod[i] < 0) nc += arr - tr.lb[i];
+      if (!(nc < best)) continue;   // cost is non-decreasing along an ordering: exact pruning
+    }
+    ord[d] = i;
+    used |= 1u << i;
+    ++d;
+    if (d == total) {
+      best = nc;
+      if (best_order)
+        for (int k = 0; k < total; ++k) best_order[k] = (uint8_t)ord[k];
+      if (first_only) return best;
+      --d;
+      used &= ~(1u << i);
+      continue;
+    }
+    cand[d] = 0; psum[d] = np; cost[d] = nc; pax[d] = npax; cur[d] = i + 1;
+  }
+  return best;
+}
+
+// findOptimalRouting (lib/optimUtils.py:113-160) on a prepared Trip.
+// n_groups = number of distinct requests; groups [0, n_new) are the new ones.
+__device__ double trip_solve(const Trip& tr, int n_groups, int n_new, int flags, uint8_t* best_order) {
+  const unsigned all = (tr.ns >= 32) ? 0xffffffffu : ((1u << tr.ns) - 1u);
+  if ((flags & DRS_EVAL_PAIRWISE_CHECKS) && tr.has_start && n_groups >= 3) {
+    for (int a = 0; a < n_groups; ++a)
+      for (int b = a + 1; b < n_groups; ++b) {
+        if (a >= n_new && b >= n_new) continue;   // both already on the vehicle (:142-143)
+        unsigned sub = 0;
+        for (int i = 0; i < tr.ns; ++i)
+          if (tr.group[i] == a || tr.group[i] == b) sub |= 1u << i;
+        // minimalDelayPath(comboLocs, G, startTime, startLoc): default capacity 1e6, startPax 0 (:148-149)
+        const double c = trip_dfs(tr, sub, 1e6, 0, true, nullptr);
+        if (!(c < DRS_INF_ROUTE_COST)) return DRS_INF_ROUTE_COST;
+      }
+  }
+  return trip_dfs(tr, all, tr.cap, tr.pax0, false, best_order);
+}
+
+struct TaskList {
+  int32_t* veh;     // vehicle index or -1
+  int32_t* nreq;
+  int32_t* req;     // MAXR per task
+};
+
+__device__ bool build_trip(Trip& tr, const TickDev& tk, const DistView& dv, double T, int v, int nreq,
+                           const int32_t* reqs, int* n_groups) {
+  int ns = 0;
+  for (int k = 0; k < nreq; ++k) {   // createLocations: new requests first (lib/optimUtils.py:86-92)
+    const int r = reqs[k];
+    tr.node[1 + ns] = tk.r_o[r]; tr.lb[ns] = tk.r_lbp[r]; tr.ub[ns] = tk.r_ubp[r]; tr.pod[ns] = 1;
+    tr.prev[ns] = -1; tr.group[ns] = k; ++ns;
+    tr.node[1 + ns] = tk.r_d[r]; tr.lb[ns] = tk.r_lbd[r]; tr.ub[ns] = tk.r_ubd[r]; tr.pod[ns] = -1;
+    tr.prev[ns] = (int8_t)(ns - 1); tr.group[ns] = k; ++ns;
+  }
+  int groups = nreq;
+  if (v >= 0) {
+    const int s0 = tk.v_off[v], s1 = tk.v_off[v + 1];
+    if (ns + (s1 - s0) > MAXS) return false;
+    const int base = ns;
+    for (int s = s0; s < s1; ++s) {
+      tr.node[1 + ns] = tk.s_node[s]; tr.lb[ns] = tk.s_lb[s]; tr.ub[ns] = tk.s_ub[s]; tr.pod[ns] = tk.s_pod[s];
+      const int pv = tk.s_prev[s];
+      tr.prev[ns] = (int8_t)(pv < 0 ? -1 : base + pv);
+      tr.group[ns] = pv < 0 ? groups++ : tr.group[base + pv];
+      ++ns;
+    }
+    tr.has_start = 1;
+    tr.node[0] = tk.v_node[v];
+    tr.t_start = T + tk.v_delay[v];           // lib/optimUtils.py:117
+    tr.cap = (double)tk.v_cap[v];
+    tr.pax0 = tk.v_pax[v];
+  } else {
+    tr.has_start = 0;
+    tr.node[0] = tr.node[1];
+    tr.t_start = T;                            // lib/optimUtils.py:160
+    tr.cap = 1e6;
+    tr.pax0 = 0;
+  }
+  tr.ns = ns;
+  *n_groups = groups;
+  for (int a = 0; a <= ns; ++a)
+    for (int b = 1; b <= ns; ++b) {
+      tr.tt[a * (MAXS + 1) + b] = (tr.node[a] == tr.node[b]) ? 0.0 : dv.at(tr.node[a], tr.node[b]);
+    }
+  return true;
+}
+
+__global__ void trip_eval_kernel(TickDev tk, DistView dv, double T, int flags, int ntasks, TaskList tl, double* cost_out,
+                                 uint8_t* order_out, int32_t* nstops_out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= ntasks) return;
+  Trip tr;
+  int groups = 0;
+  uint8_t order[MAXS];
+  for (int i = 0; i < MAXS; ++i) order[i] = 0xff;
+  double cost = DRS_INF_ROUTE_COST;
+  int ns = -1;   // -1: too many stops for DRS_MAX_STOPS
+  if (build_trip(tr, tk, dv, T, tl.veh[k], tl.nreq[k], tl.req + (int64_t)k * MAXR, &groups)) {
+    ns = tr.ns;
+    cost = trip_solve(tr, groups, tl.nreq[k], flags, order);
+  }
+  cost_out[k] = cost;
+  nstops_out[k] = ns;
+  for (int i = 0; i < MAXS; ++i) order_out[(int64_t)k * MAXS + i] = order[i];
+}
+
+// status per pair + compact survivor list (warp-aggregated append)
+__global__ void rv_filter_kernel(TickDev tk, DistView dv, double T, int8_t* status, int32_t* surv_veh,
+                                 int32_t* surv_req, int* surv_count) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)tk.n_veh * tk.n_req;
+  bool survive = false;
+  int v = 0, r = 0;
+  if (idx < total) {
+    v = (int)(idx / tk.n_req);
+    r = (int)(idx % tk.n_req);
+    const int vn = tk.v_node[v], o = tk.r_o[r];
+    const double tvo = (vn == o) ? 0.0 : dv.at(vn, o);
+    int st;
+    if (T + tvo > tk.r_ubp[r]) {               // lib/Optimization.py:183-186
+      st = DRS_RV_SKIPPED;
+    } else {
+      st = -1;
+      if (tk.v_off[v + 1] > tk.v_off[v]) {     // busy vehicle: empty-dummy check (:193-202)
+        const double t0 = T + tk.v_delay[v];
+        bool ok = 1 <= tk.v_cap[v];
+        const double p1 = 0.0 + tvo;
+        const double a1 = t0 + p1;
+        ok = ok && a1 >= tk.r_lbp[r] && a1 <= tk.r_ubp[r];
+        const int dn = tk.r_d[r];
+        const double p2 = p1 + ((o == dn) ? 0.0 : dv.at(o, dn));
+        const double a2 = t0 + p2;
+        ok = ok && a2 >= tk.r_lbd[r] && a2 <= tk.r_ubd[r];
+        ok = ok && ((a2 - tk.r_lbd[r]) < DRS_INF_ROUTE_COST);
+        if (!ok) st = DRS_RV_SAVED;
+      }
+      if (st < 0) survive = true;
+    }
+    if (!survive) status[idx] = (int8_t)st;
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, survive);
+  if (m) {
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(surv_count, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (survive) {
+      const int pos = base + __popc(m & ((1u << lane) - 1u));
+      surv_veh[pos] = v;
+      surv_req[pos] = r;
+    }
+  }
+}
+
+// RV stage, second half: one thread per surviving pair
+__global__ void rv_eval_kernel(TickDev tk, DistView dv, double T, int flags, int nsurv, const int32_t* surv_veh,
+                               const int32_t* surv_req, int8_t* status, double* cost_out, uint8_t* order_out,
+                               int32_t* nstops_out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nsurv) return;
+  const int v = surv_veh[k], r = surv_req[k];
+  Trip tr;
+  int groups = 0;
+  uint8_t order[MAXS];
+  for (int i = 0; i < MAXS; ++i) order[i] = 0xff;
+  double cost = DRS_INF_ROUTE_COST;
+  int ns = -1;
+  int32_t one = r;
+  if (build_trip(tr, tk, dv, T, v, 1, &one, &groups)) {
+    ns = tr.ns;
+    cost = trip_solve(tr, groups, 1, flags, order);
+  }
+  status[(int64_t)v * tk.n_req + r] = (int8_t)((cost < DRS_INF_ROUTE_COST) ? DRS_RV_FEASIBLE : DRS_RV_INFEASIBLE);
+  cost_out[k] = cost;
+  nstops_out[k] = ns;
+  for (int i = 0; i < MAXS; ++i) order_out[(int64_t)k * MAXS + i] = order[i];
+}
+
+__global__ void count_status_kernel(const int8_t* status, int64_t total, unsigned long long* counters) {
+  unsigned long long c[4] = {0, 0, 0, 0};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int s = status[i];
+    if (s >= 0 && s < 4) c[s]++;
+  }
+  for (int s = 0; s < 4; ++s) {
+    unsigned long long x = c[s];
+    for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
+    if ((threadIdx.x & 31) == 0 && x) atomicAdd(&counters[s], x);
+  }
+}
+
+template <typename T> int upload(T** dptr, const T* h, size_t n, cudaStream_t st) {
+  if (*dptr) { cudaFree(*dptr); *dptr = nullptr; }
+  DRS_CUDA(cudaMalloc((void**)dptr, std::max<size_t>(n, 1) * sizeof(T)));
+  if (n) DRS_CUDA(cudaMemcpyAsync(*dptr, h, n * sizeof(T), cudaMemcpyHostToDevice, st));
+  return DRS_OK;
+}
+
+}  // namespace
+
+struct drs_tick {
+  drs_graph* g = nullptr;
+  TickDev dev;
+  // RV results (device)
+  int64_t rv_pairs = 0;
+  int rv_nsurv = 0;
+  int8_t* d_status = nullptr;
+  int32_t *d_surv_veh = nullptr, *d_surv_req = nullptr;
+  int* d_surv_count = nullptr;
+  double* d_cost = nullptr;
+  uint8_t* d_order = nullptr;
+  int32_t* d_nstops = nullptr;
+  unsigned long long* d_counters = nullptr;
+  int64_t surv_capacity = 0;
+};
+
+static void tick_free_results(drs_tick* t) {
+  void* ptrs[] = {t->d_status, t->d_surv_veh, t->d_surv_req, t->d_surv_count, t->d_cost, t->d_order, t->d_nstops,
+                  t->d_counters};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  t->d_status = nullptr; t->d_surv_veh = t->d_surv_req = nullptr; t->d_surv_count = nullptr; t->d_cost = nullptr;
+  t->d_order = nullptr; t->d_nstops = nullptr; t->d_counters = nullptr;
+  t->surv_capacity = 0; t->rv_pairs = 0; t->rv_nsurv = 0;
+}
+
+extern "C" int drs_tick_create(drs_graph* g, drs_tick** out) {
+  DRS_REQUIRE(g && out, DRS_ERR_ARG, "drs_tick_create: null argument");
+  drs_tick* t = new (std::nothrow) drs_tick();
+  DRS_REQUIRE(t, DRS_ERR_NOMEM, "drs_tick_create: out of host memory");
+  t->g = g;
+  *out = t;
+  return DRS_OK;
+}
+
+extern "C" int drs_tick_destroy(drs_tick* t) {
+  if (!t) return DRS_OK;
+  DrsDeviceGuard guard(t->g->device);
+  tick_free_results(t);
+  TickDev& d = t->dev;
+  void* ptrs[] = {d.v_node, d.v_cap, d.v_pax, d.v_off, d.v_delay, d.s_node, d.s_rid, d.s_pod, d.s_prev, d.s_lb, d.s_ub,
+                  d.r_rid, d.r_o, d.r_d, d.r_lbp, d.r_ubp, d.r_lbd, d.r_ubd};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  delete t;
+  return DRS_OK;
+}
+
+extern "C" int drs_tick_set_vehicles(drs_tick* t, const drs_vehicle_batch* b) {
+  DRS_REQUIRE(t && b, DRS_ERR_ARG, "drs_tick_set_vehicles: null argument");
+  DRS_REQUIRE(b->n_veh >= 0, DRS_ERR_ARG, "drs_tick_set_vehicles: negative n_veh");
+  const int nv = b->n_veh;
+  DRS_REQUIRE(nv == 0 || (b->start_node && b->start_delay && b->capacity && b->onboard && b->stop_off), DRS_ERR_ARG,
+              "drs_tick_set_vehicles: null vehicle array");
+  const int n = t->g->n;
+  int nstops = nv ? b->stop_off[nv] : 0;
+  DRS_REQUIRE(nv == 0 || b->stop_off[0] == 0, DRS_ERR_ARG, "drs_tick_set_vehicles: stop_off[0] must be 0");
+  for (int v = 0; v < nv; ++v) {
+    DRS_REQUIRE(b->start_node[v] >= 0 && b->start_node[v] < n, DRS_ERR_RANGE,
+                "drs_tick_set_vehicles: vehicle %d start node %d out of range", v, b->start_node[v]);
+    const int cnt = b->stop_off[v + 1] - b->stop_off[v];
+    DRS_REQUIRE(cnt >= 0 && cnt <= DRS_MAX_STOPS - 2, DRS_ERR_ARG,
+                "drs_tick_set_vehicles: vehicle %d has %d planned stops (max %d)", v, cnt, DRS_MAX_STOPS - 2);
+    DRS_REQUIRE(b->onboard[v] <= b->capacity[v], DRS_ERR_ARG,
+                "drs_tick_set_vehicles: vehicle %d starts over capacity (lib/optimUtils.py:468)", v);
+    for (int s = b->stop_off[v]; s < b->stop_off[v + 1]; ++s) {
+      DRS_REQUIRE(b->stop_node[s] >= 0 && b->stop_node[s] < n, DRS_ERR_RANGE,
+                  "drs_tick_set_vehicles: stop %d node %d out of range", s, b->stop_node[s]);
+      DRS_REQUIRE(b->stop_prev[s] < s - b->stop_off[v], DRS_ERR_ARG,
+                  "drs_tick_set_vehicles: stop %d must come after its predecessor", s);
+    }
+  }
+  DrsDeviceGuard guard(t->g->device);
+  cudaStream_t st = t->g->stream;
+  TickDev& d = t->dev;
+  int rc;
+  if ((rc = upload(&d.v_node, b->start_node, nv, st)) || (rc = upload(&d.v_delay, b->start_delay, nv, st)) ||
+      (rc = upload(&d.v_cap, b->capacity, nv, st)) || (rc = upload(&d.v_pax, b->onboard, nv, st)) ||
+      (rc = upload(&d.v_off, b->stop_off, nv ? nv + 1 : 0, st)) || (rc = upload(&d.s_node, b->stop_node, nstops, st)) ||
+      (rc = upload(&d.s_rid, b->stop_rid, nstops, st)) || (rc = upload(&d.s_pod, b->stop_pod, nstops, st)) ||
+      (rc = upload(&d.s_prev, b->stop_prev, nstops, st)) || (rc = upload(&d.s_lb, b->stop_lb, nstops, st)) ||
+      (rc = upload(&d.s_ub, b->stop_ub, nstops, st)))
+    return rc;
+  DRS_CUDA(cudaStreamSynchronize(st));
+  d.n_veh = nv;
+  d.n_stops = nstops;
+  return DRS_OK;
+}
+
+extern "C" int drs_tick_set_requests(drs_tick* t, const drs_request_batch* b) {
+  DRS_REQUIRE(t && b, DRS_ERR_ARG, "drs_tick_set_requests: null argument");
+  const int nr = b->n_req;
+  DRS_REQUIRE(nr >= 0, DRS_ERR_ARG, "drs_tick_set_requests: negative n_req");
+  DRS_REQUIRE(nr == 0 || (b->rid && b->o_node && b->d_node && b->lb_p && b->ub_p && b->lb_d && b->ub_d), DRS_ERR_ARG,
+              "drs_tick_set_requests: null request array");
+  for (int r = 0; r < nr; ++r)
+    DRS_REQUIRE(b->o_node[r] >= 0 && b->o_node[r] < t->g->n && b->d_node[r] >= 0 && b->d_node[r] < t->g->n,
+                DRS_ERR_RANGE, "drs_tick_set_requests: request %d node out of range", r);
+  DrsDeviceGuard guard(t->g->device);
+  cudaStream_t st = t->g->stream;
+  TickDev& d = t->dev;
+  int rc;
+  if ((rc = upload(&d.r_rid, b->rid, nr, st)) || (rc = upload(&d.r_o, b->o_node, nr, st)) ||
+      (rc = upload(&d.r_d, b->d_node, nr, st)) || (rc = upload(&d.r_lbp, b->lb_p, nr, st)) ||
+      (rc = upload(&d.r_ubp, b->ub_p, nr, st)) || (rc = upload(&d.r_lbd, b->lb_d, nr, st)) ||
+      (rc = upload(&d.r_ubd, b->ub_d, nr, st)))
+    return rc;
+  DRS_CUDA(cudaStreamSynchronize(st));
+  d.n_req = nr;
+  return DRS_OK;
+}
+
+static int tick_ready(const drs_tick* t, const char* who) {
+  DRS_REQUIRE(t, DRS_ERR_ARG, "%s: null tick", who);
+  DRS_REQUIRE(t->g->apsp_valid, DRS_ERR_STATE, "%s: travel-time matrix not built (or invalidated by a weight update)", who);
+  return DRS_OK;
+}
+
+extern "C" int drs_tick_rv_eval(drs_tick* t, double T, int32_t flags, int32_t* n_edges, int64_t* counters_host) {
+  int rc = tick_ready(t, "drs_tick_rv_eval");
+  if (rc) return rc;
+  DrsDeviceGuard guard(t->g->device);
+  cudaStream_t st = t->g->stream;
+  const TickDev& d = t->dev;
+  const int64_t total = (int64_t)d.n_veh * d.n_req;
+  DRS_REQUIRE(total < (int64_t)1 << 31, DRS_ERR_ARG, "drs_tick_rv_eval: %lld pairs exceed 2^31", (long long)total);
+  if (n_edges) *n_edges = 0;
+  if (counters_host) std::memset(counters_host, 0, 4 * sizeof(int64_t));
+  t->rv_pairs = total;
+  t->rv_nsurv = 0;
+  if (total == 0) return DRS_OK;
+  if (t->surv_capacity < total) {
+    tick_free_results(t);
+    t->rv_pairs = total;
+    DRS_CUDA(cudaMalloc((void**)&t->d_status, total));
+    DRS_CUDA(cudaMalloc((void**)&t->d_surv_veh, sizeof(int32_t) * total));
+    DRS_CUDA(cudaMalloc((void**)&t->d_surv_req, sizeof(int32_t) * total));
+    DRS_CUDA(cudaMalloc((void**)&t->d_surv_count, sizeof(int)));
+    DRS_CUDA(cudaMalloc((void**)&t->d_counters, 4 * sizeof(unsigned long long)));
+    t->surv_capacity = total;
+  }
+  DistView dv{t->g->d_dist, t->g->ld, t->g->mode};
+  DRS_CUDA(cudaMemsetAsync(t->d_surv_count, 0, sizeof(int), st));
+  DRS_CUDA(cudaMemsetAsync(t->d_counters, 0, 4 * sizeof(unsigned long long), st));
+  const int threads = 256;
+  rv_filter_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, st>>>(d, dv, T, t->d_status, t->d_surv_veh,
+                                                                                    t->d_surv_req, t->d_surv_count);
+  DRS_CUDA(cudaGetLastError());
+  int nsurv = 0;
+  DRS_CUDA(cudaMemcpyAsync(&nsurv, t->d_surv_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+  DRS_CUDA(cudaStreamSynchronize(st));
+  t->rv_nsurv = nsurv;
+  if (t->d_cost) { cudaFree(t->d_cost); cudaFree(t->d_order); cudaFree(t->d_nstops); t->d_cost = nullptr; t->d_order = nullptr; t->d_nstops = nullptr; }
+  DRS_CUDA(cudaMalloc((void**)&t->d_cost, sizeof(double) * std::max(nsurv, 1)));
+  DRS_CUDA(cudaMalloc((void**)&t->d_order, (size_t)MAXS * std::max(nsurv, 1)));
+  DRS_CUDA(cudaMalloc((void**)&t->d_nstops, sizeof(int32_t) * std::max(nsurv, 1)));
+  if (nsurv > 0) {
+    rv_eval_kernel<<<(nsurv + 63) / 64, 64, 0, st>>>(d, dv, T, flags, nsurv, t->d_surv_veh, t->d_surv_req, t->d_status,
+                                                     t->d_cost, t->d_order, t->d_nstops);
+    DRS_CUDA(cudaGetLastError());
+  }
+  count_status_kernel<<<148 * 2, 256, 0, st>>>(t->d_status, total, t->d_counters);
+  DRS_CUDA(cudaGetLastError());
+  unsigned long long c[4];
+  DRS_CUDA(cudaMemcpyAsync(c, t->d_counters, sizeof(c), cudaMemcpyDeviceToHost, st));
+  DRS_CUDA(cudaStreamSynchronize(st));
+  if (counters_host)
+    for (int s = 0; s < 4; ++s) counters_host[s] = (int64_t)c[s];
+  if (n_edges) *n_edges = (int32_t)c[DRS_RV_FEASIBLE];
+  return DRS_OK;
+}
+
+extern "C" int drs_tick_rv_fetch(drs_tick* t, int32_t capacity_edges, int32_t* veh_idx, int32_t* req_idx, double* cost,
+                                 uint8_t* order, int32_t* n_stops) {
+  DRS_REQUIRE(t, DRS_ERR_ARG, "drs_tick_rv_fetch: null tick");
+  const int ns = t->rv_nsurv;
+  if (ns == 0) return DRS_OK;
+  DrsDeviceGuard guard(t->g->device);
+  cudaStream_t st = t->g->stream;
+  std::vector<int32_t> v(ns), r(ns), nst(ns);
+  std::vector<double> c(ns);
+  std::vector<uint8_t> o((size_t)ns * MAXS);
+  DRS_CUDA(cudaMemcpyAsync(v.data(), t->d_surv_veh, sizeof(int32_t) * ns, cudaMemcpyDeviceToHost, st));
+  DRS_CUDA(cudaMemcpyAsync(r.data(), t->d_surv_req, sizeof(int32_t) * ns, cudaMemcpyDeviceToHost, st));
+  DRS_CUDA(cudaMemcpyAsync(c.data(), t->d_cost, sizeof(double) * ns, cudaMemcpyDeviceToHost, st));
+  DRS_CUDA(cudaMemcpyAsync(nst.data(), t->d_nstops, sizeof(int32_t) * ns, cudaMemcpyDeviceToHost, st));
+  DRS_CUDA(cudaMemcpyAsync(o.data(), t->d_order, (size_t)ns * MAXS, cudaMemcpyDeviceToHost, st));
+  DRS_CUDA(cudaStreamSynchronize(st));
+  for (int k = 0; k < ns; ++k)
+    DRS_REQUIRE(nst[k] >= 0, DRS_ERR_ARG, "drs_tick_rv_fetch: vehicle %d + request %d exceed DRS_MAX_STOPS", v[k], r[k]);
+  std::vector<int> idx;
+  idx.reserve(ns);
+  for (int k = 0; k < ns; ++k)
+    if (c[k] < DRS_INF_ROUTE_COST) idx.push_back(k);
+  DRS_REQUIRE((int)idx.size() <= capacity_edges, DRS_ERR_CAPACITY, "drs_tick_rv_fetch: %d edges, buffer holds %d",
+              (int)idx.size(), capacity_edges);
+  std::sort(idx.begin(), idx.end(), [&](int a, int b) { return r[a] != r[b] ? r[a] < r[b] : v[a] < v[b]; });
+  for (size_t e = 0; e < idx.size(); ++e) {
+    const int k = idx[e];
+    if (veh_idx) veh_idx[e] = v[k];
+    if (req_idx) req_idx[e] = r[k];
+    if (cost) cost[e] = c[k];
+    if (n_stops) n_stops[e] = nst[k];
+    if (order) std::memcpy(order + e * MAXS, o.data() + (size_t)k * MAXS, MAXS);
+  }
+  return DRS_OK;
+}
+
+extern "C" int drs_tick_trip_eval(drs_tick* t, double T, int32_t flags, int32_t n_tasks, const int32_t* task_veh,
+                                  const int32_t* task_nreq, const int32_t* task_req, double* cost_host,
+                                  uint8_t* order_host, int32_t* n_stops_host) {
+  int rc = tick_ready(t, "drs_tick_trip_eval");
+  if (rc) return rc;
+  DRS_REQUIRE(n_tasks >= 0 && (n_tasks == 0 || (task_veh && task_nreq && task_req && cost_host)), DRS_ERR_ARG,
+              "drs_tick_trip_eval: bad argument");
+  if (n_tasks == 0) return DRS_OK;
+  const TickDev& d = t->dev;
+  for (int k = 0; k < n_tasks; ++k) {
+    DRS_REQUIRE(task_veh[k] >= -1 && task_veh[k] < d.n_veh, DRS_ERR_RANGE, "drs_tick_trip_eval: task %d vehicle %d out of range",
+                k, task_veh[k]);
+    DRS_REQUIRE(task_nreq[k] >= 1 && task_nreq[k] <= MAXR, DRS_ERR_ARG, "drs_tick_trip_eval: task %d has %d requests (1..%d)", k,
+                task_nreq[k], MAXR);
+    for (int j = 0; j < task_nreq[k]; ++j)
+      DRS_REQUIRE(task_req[k * MAXR + j] >= 0 && task_req[k * MAXR + j] < d.n_req, DRS_ERR_RANGE,
+                  "drs_tick_trip_eval: task %d request index out of range", k);
+  }
+  DrsDeviceGuard guard(t->g->device);
+  cudaStream_t st = t->g->stream;
+  int32_t *dv_ = nullptr, *dn = nullptr, *dr = nullptr, *dns = nullptr;
+  double* dc = nullptr;
+  uint8_t* dord = nullptr;
+  auto cleanup = [&]() { cudaFree(dv_); cudaFree(dn); cudaFree(dr); cudaFree(dns); cudaFree(dc); cudaFree(dord); };
+  if ((rc = upload(&dv_, task_veh, n_tasks, st)) || (rc = upload(&dn, task_nreq, n_tasks, st)) ||
+      (rc = upload(&dr, task_req, (size_t)n_tasks * MAXR, st))) { cleanup(); return rc; }
+  if (cudaMalloc((void**)&dc, sizeof(double) * n_tasks) != cudaSuccess ||
+      cudaMalloc((void**)&dord, (size_t)n_tasks * MAXS) != cudaSuccess ||
+      cudaMalloc((void**)&dns, sizeof(int32_t) * n_tasks) != cudaSuccess) {
+    cleanup();
+    drs_set_error("drs_tick_trip_eval: cudaMalloc failed");
+    return DRS_ERR_NOMEM;
+  }
+  DistView dv{t->g->d_dist, t->g->ld, t->g->mode};
+  TaskList tl{dv_, dn, dr};
+  trip_eval_kernel<<<(n_tasks + 63) / 64, 64, 0, st>>>(d, dv, T, flags, n_tasks, tl, dc, dord, dns);
+  std::vector<int32_t> nst(n_tasks);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(cost_host, dc, sizeof(double) * n_tasks, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && order_host) e = cudaMemcpyAsync(order_host, dord, (size_t)n_tasks * MAXS, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(nst.data(), dns, sizeof(int32_t) * n_tasks, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cleanup();
+  if (e != cudaSuccess) {
+    drs_set_error("drs_tick_trip_eval: %s", cudaGetErrorString(e));
+    return DRS_ERR_CUDA;
+  }
+  for (int k = 0; k < n_tasks; ++k)
+    DRS_REQUIRE(nst[k] >= 0, DRS_ERR_ARG, "drs_tick_trip_eval: task %d exceeds DRS_MAX_STOPS (%d)", k, DRS_MAX_STOPS);
+  if (n_stops_host) std::memcpy(n_stops_host, nst.data(), sizeof(int32_t) * n_tasks);
+  return DRS_OK;
+}

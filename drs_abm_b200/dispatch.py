@@ -1,0 +1,476 @@
+"""Drop-in assignment optimizers: the reference's ``AssignmentMethod`` family over
+the B200 per-tick evaluation kernels.
+
+Mirrors /root/reference lib/Optimization.py:13-408 (``AssignmentMethod``,
+``VehReqMatchingAssignment``, ``AlonsoMora``): same class names, constructor
+parameters, ``optimizeAssignment(vehs, reqs, G, T=0)`` signature and return
+convention ``((veh_routes, rejected_rids), metadata)``.
+
+What runs where
+  * RV stage (every request x vehicle pair: reachability pre-filter, dummy-vehicle
+    check, optimal ordering of the request inserted into the vehicle's plan) and
+    every RR / RTV trip costing: CUDA (drs_tick_rv_eval / drs_tick_trip_eval),
+    exact enumeration with the reference's fp64 arithmetic.
+  * RTV clique growth (set logic, lib/Optimization.py:265-347) and the final
+    set-packing ILP (lib/Optimization.py:359-408; Gurobi in the reference, a
+    third-party solver): host.  The ILP goes to scipy's HiGHS, or to the
+    rectangular assignment solver when every trip has one request.
+
+``routing_method`` "tabu" (the reference default, lib/Optimization.py:96-100) is a
+non-reproducible heuristic (unseeded random(), wall-clock limits:
+lib/optimUtils.py:312,339-343); here both methods use the exact enumeration, so a
+"tabu" run returns a cost <= the reference's.  "enumerate" additionally applies
+findOptimalRouting's pairwise pre-filter (lib/optimUtils.py:127-156), which the
+tabu front end has commented out (lib/optimUtils.py:172-200).
+
+Tie rules that the reference leaves to set-iteration order / Gurobi are defined
+in DESIGN.md ("canonical ties").
+"""
+import ctypes as C
+import math
+import time
+
+import numpy as np
+
+from . import _lib
+from .routing import RoadGraph
+
+CST_SPEED = 9              # lib/Constants.py:148, used by the RR pre-filter (lib/Optimization.py:148-151)
+COST_IGNORED = 1e6         # lib/Optimization.py:373
+INF_ROUTE_COST = 1e6       # lib/optimUtils.py:156,437
+MAX_STOPS = 16
+MAX_TRIP_REQS = 4
+EVAL_PAIRWISE_CHECKS = 1
+
+_i8p, _u8p, _i64p = _lib._i8p, _lib._u8p, _lib._i64p
+VehicleBatch, RequestBatch = _lib.VehicleBatch, _lib.RequestBatch
+
+
+def great_circle_distance(olat, olng, dlat, dlng):
+    """lib/optimUtils.py:651-653."""
+    return (6371000 * 2 * math.pi / 360 * np.sqrt(
+        (math.cos((olat + dlat) * math.pi / 360) * (olng - dlng)) ** 2 + (olat - dlat) ** 2))
+
+
+class Tick(object):
+    """Host view of one assignment tick: marshals Veh / Req objects into the SoA
+    batches of include/drs_b200.h and runs the evaluation kernels."""
+
+    def __init__(self, G, vehs, reqs, T, pairwise_checks=True):
+        if not isinstance(G, RoadGraph):
+            raise TypeError("G must be the RoadGraph proxy (router.G) of drs_abm_b200.routing.RoutingEngine")
+        self.G = G
+        self.T = T
+        self.flags = EVAL_PAIRWISE_CHECKS if pairwise_checks else 0
+        self.lib = _lib.load()
+        self.vehs = list(vehs)
+        # ---- request vertices: lib/Optimization.py:106-118
+        self.new_reqs = [r for r in reqs if r.assigned is not None and not r.assigned]
+        node = G.node_of_location
+        nr = len(self.new_reqs)
+        self.r_rid = np.array([r.id for r in self.new_reqs], dtype=np.int32)
+        self.r_o = np.array([node(r.olng, r.olat) for r in self.new_reqs], dtype=np.int32)
+        self.r_d = np.array([node(r.dlng, r.dlat) for r in self.new_reqs], dtype=np.int32)
+        self.r_lbp = np.array([r.Cep - T for r in self.new_reqs], dtype=np.float64)       # Cep - T (:117)
+        self.r_ubp = np.array([r.Clp for r in self.new_reqs], dtype=np.float64)
+        dw = [r.get_dropoff_time_window() for r in self.new_reqs]                          # (:111)
+        self.r_lbd = np.array([w[0] for w in dw], dtype=np.float64)
+        self.r_ubd = np.array([w[1] for w in dw], dtype=np.float64)
+        assert len(self.r_rid) == nr
+        # ---- vehicle vertices: lib/Optimization.py:120-134 ; stop list in createLocations order
+        #      (lib/optimUtils.py:94-108): on-board drop-offs, then (pickup, drop-off) per waiting request
+        v_node, v_delay, v_cap, v_pax, off = [], [], [], [], [0]
+        s_node, s_rid, s_pod, s_prev, s_lb, s_ub = [], [], [], [], [], []
+        self.veh_stops = []       # per vehicle: [(rid, pod, lng, lat)] in batch order
+        for veh in self.vehs:
+            pax_rids, wait_rids = veh.get_passenger_requests()
+            (vlng, vlat), t = veh.get_next_node()
+            v_node.append(node(vlng, vlat)); v_delay.append(float(t)); v_cap.append(int(veh.K))
+            pax_list, wait_list = list(pax_rids), list(wait_rids)
+            v_pax.append(len(pax_list))
+            stops = []
+            for rid in pax_list:
+                rq = reqs[rid]
+                Ced, Cld = rq.get_dropoff_time_window()
+                s_node.append(node(rq.dlng, rq.dlat)); s_rid.append(rq.id); s_pod.append(-1); s_prev.append(-1)
+                s_lb.append(Ced); s_ub.append(Cld)
+                stops.append((rq.id, -1, rq.dlng, rq.dlat))
+            for rid in wait_list:
+                rq = reqs[rid]
+                Ced, Cld = rq.get_dropoff_time_window()
+                s_node.append(node(rq.olng, rq.olat)); s_rid.append(rq.id); s_pod.append(1); s_prev.append(-1)
+                s_lb.append(rq.Cep); s_ub.append(rq.Clp)
+                stops.append((rq.id, 1, rq.olng, rq.olat))
+                s_node.append(node(rq.dlng, rq.dlat)); s_rid.append(rq.id); s_pod.append(-1)
+                s_prev.append(len(stops) - 1)
+                s_lb.append(Ced); s_ub.append(Cld)
+                stops.append((rq.id, -1, rq.dlng, rq.dlat))
+            if len(stops) > MAX_STOPS - 2:
+                raise ValueError("vehicle %r has %d planned stops; the kernel handles %d" % (veh.id, len(stops), MAX_STOPS - 2))
+            self.veh_stops.append(stops)
+            off.append(len(s_node))
+        self._v = dict(node=np.array(v_node, dtype=np.int32), delay=np.array(v_delay, dtype=np.float64),
+                       cap=np.array(v_cap, dtype=np.int32), pax=np.array(v_pax, dtype=np.int32),
+                       off=np.array(off, dtype=np.int32), s_node=np.array(s_node, dtype=np.int32),
+                       s_rid=np.array(s_rid, dtype=np.int32), s_pod=np.array(s_pod, dtype=np.int8),
+                       s_prev=np.array(s_prev, dtype=np.int8), s_lb=np.array(s_lb, dtype=np.float64),
+                       s_ub=np.array(s_ub, dtype=np.float64))
+        self.handle = C.c_void_p()
+        _lib.check(self.lib.drs_tick_create(G.handle, C.byref(self.handle)), self.lib)
+        self._upload()
+
+    def _upload(self):
+        v = self._v
+
+        def p8(a):
+            return a.ctypes.data_as(_i8p)
+        vb = VehicleBatch(len(self.vehs), _lib.ptr_i32(v["node"]), _lib.ptr_f64(v["delay"]), _lib.ptr_i32(v["cap"]),
+                          _lib.ptr_i32(v["pax"]), _lib.ptr_i32(v["off"]), _lib.ptr_i32(v["s_node"]),
+                          _lib.ptr_i32(v["s_rid"]), p8(v["s_pod"]), p8(v["s_prev"]), _lib.ptr_f64(v["s_lb"]),
+                          _lib.ptr_f64(v["s_ub"]))
+        _lib.check(self.lib.drs_tick_set_vehicles(self.handle, C.byref(vb)), self.lib)
+        rb = RequestBatch(len(self.new_reqs), _lib.ptr_i32(self.r_rid), _lib.ptr_i32(self.r_o), _lib.ptr_i32(self.r_d),
+                          _lib.ptr_f64(self.r_lbp), _lib.ptr_f64(self.r_ubp), _lib.ptr_f64(self.r_lbd),
+                          _lib.ptr_f64(self.r_ubd))
+        _lib.check(self.lib.drs_tick_set_requests(self.handle, C.byref(rb)), self.lib)
+
+    def close(self):
+        if self.handle:
+            self.lib.drs_tick_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ kernels
+    def rv_eval(self):
+        """RV stage.  Returns (edges, counters): edges = list of (veh_index, req_index, cost, order)."""
+        n_edges = C.c_int32(0)
+        counters = np.zeros(4, dtype=np.int64)
+        _lib.check(self.lib.drs_tick_rv_eval(self.handle, float(self.T), self.flags, C.byref(n_edges),
+                                             counters.ctypes.data_as(_i64p)), self.lib)
+        ne = n_edges.value
+        vi, ri = np.empty(ne, dtype=np.int32), np.empty(ne, dtype=np.int32)
+        cost = np.empty(ne, dtype=np.float64)
+        order = np.empty((ne, MAX_STOPS), dtype=np.uint8)
+        ns = np.empty(ne, dtype=np.int32)
+        _lib.check(self.lib.drs_tick_rv_fetch(self.handle, ne, _lib.ptr_i32(vi), _lib.ptr_i32(ri), _lib.ptr_f64(cost),
+                                              order.ctypes.data_as(_u8p), _lib.ptr_i32(ns)), self.lib)
+        edges = [(int(vi[e]), int(ri[e]), float(cost[e]), [int(x) for x in order[e, :ns[e]]]) for e in range(ne)]
+        return edges, {"feasible": int(counters[0]), "skipped": int(counters[1]), "saved": int(counters[2]),
+                       "infeasible": int(counters[3])}
+
+    def trip_eval(self, tasks):
+        """tasks: list of (veh_index or -1, [request indices]).  Returns list of (cost, order or None)."""
+        nt = len(tasks)
+        if nt == 0:
+            return []
+        tv = np.array([t[0] for t in tasks], dtype=np.int32)
+        tn = np.array([len(t[1]) for t in tasks], dtype=np.int32)
+        tr = np.zeros((nt, MAX_TRIP_REQS), dtype=np.int32)
+        for k, t in enumerate(tasks):
+            if len(t[1]) > MAX_TRIP_REQS:
+                raise ValueError("a trip holds at most %d new requests" % MAX_TRIP_REQS)
+            tr[k, :len(t[1])] = t[1]
+        cost = np.empty(nt, dtype=np.float64)
+        order = np.empty((nt, MAX_STOPS), dtype=np.uint8)
+        ns = np.empty(nt, dtype=np.int32)
+        _lib.check(self.lib.drs_tick_trip_eval(self.handle, float(self.T), self.flags, nt, _lib.ptr_i32(tv),
+                                               _lib.ptr_i32(tn), _lib.ptr_i32(tr), _lib.ptr_f64(cost),
+                                               order.ctypes.data_as(_u8p), _lib.ptr_i32(ns)), self.lib)
+        out = []
+        for k in range(nt):
+            if cost[k] < INF_ROUTE_COST:
+                out.append((float(cost[k]), [int(x) for x in order[k, :ns[k]]]))
+            else:
+                out.append((INF_ROUTE_COST, None))
+        return out
+
+    # ------------------------------------------------------------------ routes
+    def route_of(self, veh_index, req_indices, order):
+        """Kernel stop numbering -> the reference's route format [(rid, pod, lng, lat), ...]
+        (lib/optimUtils.py:358,449)."""
+        stops = []
+        for ri in req_indices:
+            rq = self.new_reqs[ri]
+            stops.append((rq.id, 1, rq.olng, rq.olat))
+            stops.append((rq.id, -1, rq.dlng, rq.dlat))
+        if veh_index >= 0:
+            stops.extend(self.veh_stops[veh_index])
+        return [stops[i] for i in order]
+
+
+class _Listing(object):
+    """len()-able stand-in for the igraph graphs the reference passes between stages."""
+
+    def __init__(self, vs, es):
+        self.vs, self.es = vs, es
+
+
+class AssignmentMethod():
+    """lib/Optimization.py:13-27."""
+
+    def __init__(self, params):
+        self.parameters = params
+
+    def optimizeAssignment(self, vehs, reqs, G, T=0):
+        pass
+
+
+class VehReqMatchingAssignment(AssignmentMethod):
+    """lib/Optimization.py:29-85: RV graph -> RTV graph -> assignment."""
+
+    verbose = True
+
+    def _print(self, *a):
+        if self.verbose:
+            print(*a)
+
+    def optimizeAssignment(self, vehs, reqs, G, T=0):
+        self._print("  Generating R-V graph for T={}".format(T))
+        t = time.time()
+        rvGraph = self.generatePairwiseGraph(vehs, reqs, G, T)
+        rvTime = time.time() - t
+        self._print("  R-V Graph successfully generated  in {:.2f} seconds! |V|={}, |E|={}".format(
+            rvTime, len(rvGraph.vs), len(rvGraph.es)))
+        self._print("  Generating RTV graph for T={}".format(T))
+        t = time.time()
+        rtvGraph = self.generateRTVGraph(rvGraph, G, T)
+        rtvTime = time.time() - t
+        self._print("  RTV Graph successfully generated in {:.2f} seconds! |V|={}, |E|={}".format(
+            rtvTime, len(rtvGraph.vs), len(rtvGraph.es)))
+        try:
+            if len(rtvGraph.vs) > 0 and len(rtvGraph.es) > 0:
+                t = time.time()
+                assignment = self.assignFromRTVGraph(rtvGraph)
+                assTime = time.time() - t
+                self._print("  Assignment completed in {:.2f} seconds!".format(assTime))
+                metadata = {"benders_iters": 0, "total_feas_cuts": 0, "total_opt_cuts": 0, "solve_time": assTime,
+                            "rv_time": rvTime, "rtv_time": rtvTime, "objective": rtvGraph.objective}
+                return assignment, metadata
+            return (list(), list()), {"solve_time": 0}      # lib/Optimization.py:75-76
+        finally:
+            rvGraph.tick.close()
+
+    def generatePairwiseGraph(self, vehs, reqs, G, T=0):
+        pass
+
+    def generateRTVGraph(self, rvGraph, G, T=0):
+        pass
+
+    def assignFromRTVGraph(self, rtvGraph):
+        pass
+
+
+class AlonsoMora(VehReqMatchingAssignment):
+    """lib/Optimization.py:88-408."""
+
+    def __init__(self, params):
+        self.parameters = params
+        if "routing_method" not in params.keys():
+            self.parameters["routing_method"] = "tabu"
+        if self.parameters["routing_method"] == "tabu" and "tabu_max_time" not in params.keys():
+            self.parameters["tabu_max_time"] = 3
+        if self.parameters["routing_method"] not in ("tabu", "enumerate"):
+            raise ValueError("routing_method must be 'tabu' or 'enumerate'")
+        self.title = "Alonso-Mora"
+        self.verbose = bool(params.get("verbose", True))
+        self.max_trip_size = params.get("max_trip_size", None)   # extension: cap RTV trip size (None = veh capacity)
+
+    # ------------------------------------------------------------------ RV graph
+    def generatePairwiseGraph(self, vehs, reqs, G, T=0):
+        """lib/Optimization.py:104-225.  Returns an object with .vs / .es (for len()) carrying the
+        request-request and request-vehicle edges."""
+        tick = Tick(G, vehs, reqs, T, pairwise_checks=(self.parameters["routing_method"] == "enumerate"))
+        nr = len(tick.new_reqs)
+        # ---- R x R (lib/Optimization.py:142-165): crow-flies pre-filter on the host, costing on the GPU
+        rr_tasks = []
+        for a in range(nr):
+            r1 = tick.new_reqs[a]
+            for b in range(a + 1, nr):
+                r2 = tick.new_reqs[b]
+                reqsDist = great_circle_distance(r1.olat, r1.olng, r2.olat, r2.olng)
+                reqsMinTime = reqsDist / CST_SPEED
+                if T + reqsMinTime > r1.Clp or T + reqsMinTime > r2.Clp:
+                    continue
+                rr_tasks.append((-1, [a, b]))
+        rr = {}
+        feas = inf = 0
+        for (task, (cost, order)) in zip(rr_tasks, tick.trip_eval(rr_tasks)):
+            if order is not None:
+                a, b = task[1]
+                rr[(a, b)] = (cost, tick.route_of(-1, [a, b], order))
+                feas += 1
+            else:
+                inf += 1
+        self._print("    Feasible pairings found amongst requests: {}".format(feas))
+        self._print("    Infeasible pairings evaluated: {}".format(inf))
+        # ---- R x V (lib/Optimization.py:176-218)
+        edges, counters = tick.rv_eval()
+        rv = {}
+        for (vi, ri, cost, order) in edges:
+            rv[(vi, ri)] = (cost, tick.route_of(vi, [ri], order))
+        self._print("    Feasible pairings found between requests and vehicles: {}".format(counters["feasible"]))
+        self._print("    Infeasible pairings evaluated: {}".format(counters["infeasible"]))
+        self._print("    Infeasible pairings skipped via dummy evaluation: {}".format(counters["saved"]))
+        self._print("    Pairings skipped because vehicle was too far away: {}".format(counters["skipped"]))
+        g = _Listing(vs=list(tick.new_reqs) + list(tick.vehs), es=list(rr) + list(rv))
+        g.tick, g.rr, g.rv, g.counters = tick, rr, rv, counters
+        return g
+
+    # ------------------------------------------------------------------ RTV graph
+    def generateRTVGraph(self, rvGraph, G, T=0):
+        """lib/Optimization.py:227-357.  Trips are keyed by tuples of request indices in RV-vertex
+        order; each level's candidates (all vehicles) are costed in one kernel launch."""
+        tick, rr, rv = rvGraph.tick, rvGraph.rr, rvGraph.rv
+        nv = len(tick.vehs)
+        veh_trips = {}                                        # (vi, trip tuple) -> (cost, route)
+        level = {}                                            # vi -> ordered list of trip tuples of the current size
+        for vi in range(nv):
+            level[vi] = []
+        for (vi, ri) in sorted(rv, key=lambda k: (k[0], k[1])):   # veh.neighbors(): ascending vertex id (:243-262)
+            veh_trips[(vi, (ri,))] = rv[(vi, ri)]
+            level[vi].append((ri,))
+        feas = inf = saved = 0
+
+        def has_rr(a, b):
+            return ((a, b) if a < b else (b, a)) in rr
+
+        # trips of size two (:265-288)
+        tasks = []
+        for vi in range(nv):
+            if self.max_trip_size is not None and int(self.max_trip_size) < 2:
+                continue
+            singles = [t[0] for t in level[vi]]
+            for x in range(len(singles)):
+                for y in range(x + 1, len(singles)):
+                    if has_rr(singles[x], singles[y]):
+                        tasks.append((vi, [singles[x], singles[y]]))
+                    else:
+                        saved += 1
+        prev_level = level
+        level = {vi: [] for vi in range(nv)}
+        for (task, (cost, order)) in zip(tasks, tick.trip_eval(tasks)):
+            vi, members = task
+            if order is not None:
+                veh_trips[(vi, tuple(members))] = (cost, tick.route_of(vi, members, order))
+                level[vi].append(tuple(members))
+                feas += 1
+            else:
+                inf += 1
+        # trips of size three and more (:291-347)
+        k = 3
+        while any(level[vi] for vi in range(nv)):
+            tasks = []
+            for vi in range(nv):
+                if self._max_size(tick, vi) < k or not level[vi]:
+                    continue
+                keys = level[vi]
+                keysets = [frozenset(t) for t in keys]
+                tested = []
+                for t1 in keys:
+                    for t2 in keys:
+                        trip = frozenset(t1) | frozenset(t2)
+                        if len(trip) == k and trip not in tested:
+                            tested.append(trip)
+                            subsets_ok = all(sum(1 for ks in keysets if (trip - {r}) <= ks) == 1 for r in trip)
+                            if not subsets_ok:
+                                saved += 1
+                                break                          # the reference leaves the t2 loop here (:325-327)
+                            members = sorted(trip)
+                            if all(has_rr(a, b) for i, a in enumerate(members) for b in members[i + 1:]):
+                                tasks.append((vi, members))
+                            else:
+                                saved += 1
+            level = {vi: [] for vi in range(nv)}
+            for (task, (cost, order)) in zip(tasks, tick.trip_eval(tasks)):
+                vi, members = task
+                if order is not None:
+                    veh_trips[(vi, tuple(members))] = (cost, tick.route_of(vi, members, order))
+                    level[vi].append(tuple(members))
+                    feas += 1
+                else:
+                    inf += 1
+            k += 1
+        self._print("    Feasible trip assignments evaluated: {}".format(feas))
+        self._print("    Infeasible trip assignments evaluated: {}".format(inf))
+        self._print("    Infeasible trip evaluations skipped via incomplete subgraphs / previous trip length checks: {}".format(saved))
+        trips = sorted(set(t for (_, t) in veh_trips))
+        g = _Listing(vs=list(rvGraph.vs) + trips, es=list(veh_trips))
+        g.tick, g.veh_trips, g.objective = tick, veh_trips, None
+        return g
+
+    def _max_size(self, tick, vi):
+        cap = int(tick.vehs[vi].K)
+        return cap if self.max_trip_size is None else min(cap, int(self.max_trip_size))
+
+    # ------------------------------------------------------------------ assignment
+    def assignFromRTVGraph(self, rtvGraph):
+        """lib/Optimization.py:359-408: min sum cost*e + 1e6*sum x; one trip per vehicle; every request in
+        exactly one chosen trip or ignored.  Returns (veh_routes {vid: route}, rejected {rid})."""
+        tick = rtvGraph.tick
+        keys = sorted(rtvGraph.veh_trips, key=lambda k: (k[0], len(k[1]), k[1]))
+        nreq = len(tick.new_reqs)
+        costs = np.array([rtvGraph.veh_trips[k][0] for k in keys], dtype=np.float64)
+        chosen, ignored, objective = solve_set_packing(len(tick.vehs), nreq, [(k[0], k[1]) for k in keys], costs)
+        if chosen is None:
+            return None, None                                 # lib/Optimization.py:405-406
+        rtvGraph.objective = objective
+        veh_routes = dict()
+        for idx in chosen:
+            vi, trip = keys[idx]
+            veh_routes[tick.vehs[vi].id] = rtvGraph.veh_trips[keys[idx]][1]
+        rejected = set(int(tick.new_reqs[ri].id) for ri in ignored)
+        return veh_routes, rejected
+
+
+def solve_set_packing(nveh, nreq, trips, costs):
+    """The ILP of lib/Optimization.py:359-408.  trips: list of (veh_index, tuple of request
+    indices).  Returns (chosen trip indices, ignored request indices, objective)."""
+    nt = len(trips)
+    if nt == 0:
+        return [], list(range(nreq)), COST_IGNORED * nreq
+    if all(len(t[1]) == 1 for t in trips):
+        # rectangular assignment: serve request r by vehicle v at cost c, or ignore it at 1e6
+        from scipy.optimize import linear_sum_assignment
+        big = 4.0 * COST_IGNORED
+        M = np.full((nreq, nveh + nreq), big)
+        tid = -np.ones((nreq, nveh), dtype=np.int64)
+        for k, (vi, tr) in enumerate(trips):
+            if costs[k] < M[tr[0], vi]:
+                M[tr[0], vi] = costs[k]
+                tid[tr[0], vi] = k
+        for r in range(nreq):
+            M[r, nveh + r] = COST_IGNORED
+        rows, cols = linear_sum_assignment(M)
+        chosen, ignored = [], []
+        for r, c in zip(rows, cols):
+            if c < nveh and tid[r, c] >= 0:
+                chosen.append(int(tid[r, c]))
+            else:
+                ignored.append(int(r))
+        obj = float(sum(costs[k] for k in chosen) + COST_IGNORED * len(ignored))
+        return sorted(chosen), sorted(ignored), obj
+    from scipy.optimize import milp, LinearConstraint, Bounds
+    from scipy.sparse import lil_matrix
+    nvar = nt + nreq
+    c = np.concatenate([costs, np.full(nreq, COST_IGNORED)])
+    A = lil_matrix((nveh + nreq, nvar))
+    lo = np.concatenate([np.full(nveh, -np.inf), np.ones(nreq)])
+    hi = np.ones(nveh + nreq)
+    for k, (vi, tr) in enumerate(trips):
+        A[vi, k] = 1
+        for r in tr:
+            A[nveh + r, k] = 1
+    for r in range(nreq):
+        A[nveh + r, nt + r] = 1
+    res = milp(c, constraints=LinearConstraint(A.tocsr(), lo, hi), integrality=np.ones(nvar), bounds=Bounds(0, 1))
+    if res.status != 0:
+        return None, None, None
+    x = np.round(res.x).astype(np.int64)
+    chosen = [k for k in range(nt) if x[k] > 0]
+    ignored = [r for r in range(nreq) if x[nt + r] > 0]
+    return chosen, ignored, float(res.fun)

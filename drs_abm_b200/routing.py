@@ -1,0 +1,529 @@
+"""Drop-in routing engine: the reference's ``RoutingEngine`` call surface over the
+B200 travel-time matrix.
+
+Mirrors /root/reference lib/RoutingEngine.py:20-229 (same constructor signature,
+method names, argument meaning, return shapes and error behaviour) and the
+subset of the python-igraph ``Graph`` API that lib/Agents.py, lib/optimUtils.py,
+lib/Optimization.py and the experiment scripts touch through ``router.G``
+("G proxy").  Every shortest-path question is answered by
+libdrs_b200.so (hand-written sm_100a CUDA behind a C-ABI); there is no CPU
+fallback -- if the library or the GPU is missing the first query raises.
+"""
+import ctypes as C
+import math
+import os
+import re
+
+import numpy as np
+
+from . import _lib
+from .gml import RoadGraphData, read_gml
+
+MPH_2_MPS = 0.44704            # lib/Constants.py:152
+UNCERTAINTY_MULTIPLIER = 1.5   # lib/Constants.py:99
+
+_NUM = re.compile(r"[-+]?(?:\d+\.?\d*|\.\d+)(?:[eE][-+]?\d+)?")
+
+
+class Vertex(object):
+    """igraph.Vertex stand-in: ``v['lng']``, ``v['lat']``, ``v['name']``, ``v.index``."""
+    __slots__ = ("graph", "index")
+
+    def __init__(self, graph, index):
+        self.graph = graph
+        self.index = int(index)
+
+    def __getitem__(self, key):
+        return self.graph._vattrs[key][self.index]
+
+    def __setitem__(self, key, value):
+        self.graph._vattrs.setdefault(key, [None] * self.graph.n)[self.index] = value
+        if key in ("name", "lng", "lat"):
+            self.graph._index_nodes()
+
+    def attributes(self):
+        return {k: v[self.index] for k, v in self.graph._vattrs.items()}
+
+    def __eq__(self, other):
+        return isinstance(other, Vertex) and other.graph is self.graph and other.index == self.index
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
+
+    def __hash__(self):
+        return hash((id(self.graph), self.index))
+
+    def __repr__(self):
+        return "Vertex(%d, %r)" % (self.index, self.attributes())
+
+
+class Edge(object):
+    """igraph.Edge stand-in: ``.index/.source/.target/.tuple``, ``e['length']``, ``e['ttmedian'] = x``."""
+    __slots__ = ("graph", "index")
+
+    def __init__(self, graph, index):
+        self.graph = graph
+        self.index = int(index)
+
+    @property
+    def source(self):
+        return int(self.graph._src[self.index])
+
+    @property
+    def target(self):
+        return int(self.graph._dst[self.index])
+
+    @property
+    def tuple(self):
+        return (self.source, self.target)
+
+    def __getitem__(self, key):
+        v = self.graph._eattrs[key][self.index]
+        return float(v) if isinstance(v, (np.floating, np.integer)) else v
+
+    def __setitem__(self, key, value):
+        self.graph._set_edge_attr(key, self.index, value)
+
+    def attributes(self):
+        return {k: self[k] for k in self.graph._eattrs}
+
+
+class VertexSeq(object):
+    def __init__(self, graph):
+        self.graph = graph
+
+    def __len__(self):
+        return self.graph.n
+
+    def __iter__(self):
+        return (Vertex(self.graph, i) for i in range(self.graph.n))
+
+    def __getitem__(self, key):
+        if isinstance(key, str):
+            return list(self.graph._vattrs[key])
+        i = int(key)
+        if i < 0:
+            i += self.graph.n
+        if not 0 <= i < self.graph.n:
+            raise IndexError("vertex index out of range")
+        return Vertex(self.graph, i)
+
+    def find(self, *args, **kwds):
+        """``vs.find(name=...)`` / ``vs.find("...")`` / ``vs.find(i)``; unknown -> ValueError like igraph
+        (relied on at lib/Agents.py:1508-1512)."""
+        if args:
+            if isinstance(args[0], str):
+                kwds = dict(kwds, name=args[0])
+            else:
+                return self[int(args[0])]
+        if list(kwds) == ["name"]:
+            return Vertex(self.graph, self.graph.node_index(kwds["name"]))
+        for i in range(self.graph.n):
+            if all(self.graph._vattrs[k][i] == v for k, v in kwds.items()):
+                return Vertex(self.graph, i)
+        raise ValueError("no such vertex")
+
+
+class EdgeSeq(object):
+    def __init__(self, graph):
+        self.graph = graph
+
+    def __len__(self):
+        return self.graph.m
+
+    def __iter__(self):
+        return (Edge(self.graph, i) for i in range(self.graph.m))
+
+    def __getitem__(self, key):
+        if isinstance(key, str):
+            return [float(x) if isinstance(x, (np.floating, np.integer)) else x for x in self.graph._eattrs[key]]
+        i = int(key)
+        if i < 0:
+            i += self.graph.m
+        if not 0 <= i < self.graph.m:
+            raise IndexError("edge index out of range")
+        return Edge(self.graph, i)
+
+    def __setitem__(self, key, values):
+        """``G.es["ttmedian"] = array`` (generateMetadata.py:42-43)."""
+        self.graph._set_edge_attr(key, None, values)
+
+
+class RoadGraph(object):
+    """The object callers know as ``router.G``: igraph look-alike backed by a device
+    CSR graph and the resident travel-time / predecessor matrices.
+
+    The matrix is built lazily for one weight attribute at a time and rebuilt
+    after any write to that attribute (optimizationTesting.py:221-226 mutates
+    ``ttmedian`` after load).
+    """
+
+    def __init__(self, data, mode=_lib.MODE_F32):
+        if not isinstance(data, RoadGraphData):
+            raise TypeError("RoadGraph needs RoadGraphData (use RoadGraph.Read_GML)")
+        self.n, self.m = data.n, data.m
+        self.directed = data.directed
+        self._src, self._dst = data.src, data.dst
+        self._vattrs = {k: list(v) for k, v in data.vattrs.items()}
+        self._eattrs = {k: (np.array(v, dtype=np.float64) if isinstance(v, np.ndarray) else list(v))
+                        for k, v in data.eattrs.items()}
+        self.mode = mode
+        self._handle = None
+        self._weight_attr = None      # attribute the device weights / matrix were built from
+        self._lib = None
+        self._index_nodes()
+
+    # ------------------------------------------------------------------ igraph surface
+    @classmethod
+    def Read_GML(cls, path, **kw):
+        return cls(read_gml(path), **kw)
+
+    @property
+    def vs(self):
+        return VertexSeq(self)
+
+    @property
+    def es(self):
+        return EdgeSeq(self)
+
+    def vcount(self):
+        return self.n
+
+    def ecount(self):
+        return self.m
+
+    def is_directed(self):
+        return self.directed
+
+    def get_shortest_paths(self, v, to=None, weights=None, output="vpath"):
+        """``G.get_shortest_paths(o, to=d, weights=w, output='epath')[0]`` (lib/RoutingEngine.py:87)."""
+        s, t = self._resolve(v), self._resolve(to)
+        epath = self.epath(s, t, weights)
+        if output == "epath":
+            return [epath]
+        vpath, cur = [s], s
+        for e in epath:
+            a, b = int(self._src[e]), int(self._dst[e])
+            cur = b if a == cur else a
+            vpath.append(cur)
+        return [vpath if (epath or s == t) else []]
+
+    def shortest_paths(self, source=None, target=None, weights=None):
+        """``G.shortest_paths(src, tgt, weights=)`` -> list of lists (lib/optimUtils.py:528,531,659)."""
+        srcs = list(source) if isinstance(source, (list, tuple)) else ([source] if source is not None else range(self.n))
+        tgts = list(target) if isinstance(target, (list, tuple)) else ([target] if target is not None else range(self.n))
+        si = [self._resolve(s) for s in srcs]
+        ti = [self._resolve(t) for t in tgts]
+        if not si or not ti:
+            return [[] for _ in si]
+        ss = np.repeat(np.asarray(si, dtype=np.int32), len(ti))
+        tt = np.tile(np.asarray(ti, dtype=np.int32), len(si))
+        d = self.matrix_lookup(ss, tt, weights)
+        return [[float(x) for x in row] for row in d.reshape(len(si), len(ti))]
+
+    distances = shortest_paths   # python-igraph >= 0.10 spelling
+
+    # ------------------------------------------------------------------ node identity
+    def _index_nodes(self):
+        names = self._vattrs.get("name")
+        self._by_name = {}
+        if names is not None:
+            for i in range(self.n - 1, -1, -1):
+                self._by_name[names[i]] = i
+        self._by_coord = {}
+        if "lng" in self._vattrs and "lat" in self._vattrs:
+            lng, lat = self._vattrs["lng"], self._vattrs["lat"]
+            for i in range(self.n - 1, -1, -1):
+                try:
+                    self._by_coord[(float(lng[i]), float(lat[i]))] = i
+                except (TypeError, ValueError):
+                    pass
+
+    def node_index(self, name):
+        """Vertex id of a ``str((lng, lat))`` name.  The literal name wins; otherwise the two
+        numbers in the string are matched against the (lng, lat) attributes, which makes
+        ``"(3, 4)"``, ``"(3.0, 4.0)"`` and numpy-2 reprs such as
+        ``"(np.float64(3.0), np.float64(4.0))"`` equivalent.
+        Unknown -> ValueError (igraph's behaviour)."""
+        i = self._by_name.get(name)
+        if i is not None:
+            return i
+        if isinstance(name, str):
+            nums = _NUM.findall(name.replace("float64", "").replace("float32", "").replace("int64", ""))
+            if len(nums) == 2:
+                i = self._by_coord.get((float(nums[0]), float(nums[1])))
+                if i is not None:
+                    return i
+        raise ValueError("no such vertex: %r" % (name,))
+
+    def node_of_location(self, lng, lat):
+        i = self._by_coord.get((float(lng), float(lat)))
+        if i is None:
+            return self.node_index(str((lng, lat)))
+        return i
+
+    def _resolve(self, v):
+        if isinstance(v, Vertex):
+            return v.index
+        if isinstance(v, str):
+            return self.node_index(v)
+        i = int(v)
+        if not 0 <= i < self.n:
+            raise ValueError("vertex index %d out of range" % i)
+        return i
+
+    # ------------------------------------------------------------------ device state
+    def _set_edge_attr(self, key, index, value):
+        if index is None:
+            vals = np.asarray(value, dtype=np.float64) if not isinstance(value, str) else value
+            if isinstance(vals, np.ndarray) and vals.ndim == 0:
+                vals = np.full(self.m, float(vals))
+            if len(vals) != self.m:
+                raise ValueError("attribute list length (%d) != edge count (%d)" % (len(vals), self.m))
+            self._eattrs[key] = np.array(vals, dtype=np.float64)
+        else:
+            if key not in self._eattrs:
+                self._eattrs[key] = np.zeros(self.m, dtype=np.float64)
+            self._eattrs[key][index] = value
+        if key == self._weight_attr:
+            self._weights_dirty = True
+
+    _weights_dirty = False
+
+    def _ensure(self, weights):
+        """Device graph exists, carries `weights`, and the APSP matrix is valid."""
+        attr = weights if weights is not None else (self._weight_attr or "ttmedian")
+        if not isinstance(attr, str):
+            raise ValueError("weights must name an edge attribute")
+        if attr not in self._eattrs:
+            raise ValueError("no such edge attribute: %r" % (attr,))
+        lib = self._lib or _lib.load()
+        self._lib = lib
+        tt = _lib.as_f64(self._eattrs[attr])
+        if self._handle is None:
+            h = C.c_void_p()
+            length = _lib.as_f64(self._eattrs.get("length", np.zeros(self.m)))
+            src, dst = _lib.as_i32(self._src), _lib.as_i32(self._dst)
+            _lib.check(lib.drs_graph_create(self.n, self.m, 1 if self.directed else 0, _lib.ptr_i32(src),
+                                            _lib.ptr_i32(dst), _lib.ptr_f64(tt), _lib.ptr_f64(length), C.byref(h)), lib)
+            self._handle = h
+            self._weight_attr = attr
+            self._weights_dirty = False
+            self._valid = False
+        elif attr != self._weight_attr or self._weights_dirty:
+            _lib.check(lib.drs_graph_set_weights(self._handle, _lib.ptr_f64(tt)), lib)
+            self._weight_attr = attr
+            self._weights_dirty = False
+            self._valid = False
+        if not self._valid:
+            _lib.check(lib.drs_apsp_build(self._handle, self.mode), lib)
+            self._valid = True
+        return lib
+
+    _valid = False
+
+    def build(self, weights=None):
+        """Builds (or rebuilds) the travel-time matrix now instead of at the first query."""
+        self._ensure(weights)
+        return self
+
+    @property
+    def handle(self):
+        """drs_graph* with a valid matrix for the current weight attribute."""
+        self._ensure(None)
+        return self._handle
+
+    def close(self):
+        if self._handle is not None and self._lib is not None:
+            self._lib.drs_graph_destroy(self._handle)
+        self._handle = None
+        self._valid = False
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ bulk queries
+    def matrix_lookup(self, s, t, weights=None):
+        """dist[s[i], t[i]] as float64 (inf = unreachable): one gather kernel."""
+        lib = self._ensure(weights)
+        s, t = _lib.as_i32(s), _lib.as_i32(t)
+        out = np.empty(len(s), dtype=np.float64)
+        _lib.check(lib.drs_query_matrix(self._handle, len(s), _lib.ptr_i32(s), _lib.ptr_i32(t), _lib.ptr_f64(out)), lib)
+        return out
+
+    def path_sums(self, s, t, weights=None):
+        """(duration, length, hops) along the canonical paths: fp64 left-to-right sums."""
+        lib = self._ensure(weights)
+        s, t = _lib.as_i32(s), _lib.as_i32(t)
+        n = len(s)
+        tt, ln, hops = np.empty(n), np.empty(n), np.empty(n, dtype=np.int32)
+        _lib.check(lib.drs_query_pairs(self._handle, n, _lib.ptr_i32(s), _lib.ptr_i32(t), _lib.ptr_f64(tt),
+                                       _lib.ptr_f64(ln), _lib.ptr_i32(hops)), lib)
+        return tt, ln, hops
+
+    def epath(self, s, t, weights=None):
+        lib = self._ensure(weights)
+        cap = 256
+        while True:
+            buf = np.empty(cap, dtype=np.int32)
+            n = C.c_int32(cap)
+            reach = C.c_int32(0)
+            rc = lib.drs_path(self._handle, int(s), int(t), _lib.ptr_i32(buf), C.byref(n), C.byref(reach))
+            if rc == _lib.ERR_CAPACITY:
+                cap = max(n.value, cap * 2)
+                continue
+            _lib.check(rc, lib)
+            return [int(e) for e in buf[:n.value]]
+
+    def dist_rows(self, row0, nrows, weights=None):
+        lib = self._ensure(weights)
+        out = np.empty((nrows, self.n), dtype=np.float64)
+        _lib.check(lib.drs_apsp_rows_to_host(self._handle, int(row0), int(nrows), _lib.ptr_f64(out)), lib)
+        return out
+
+
+class RoutingEngine(object):
+    """Same call surface as the reference class (lib/RoutingEngine.py:20-229).
+
+    Attributes (as in the reference): G, cst_speed, rs, ttweight, hour, speeds.
+    """
+
+    def __init__(self, graph_loc=None, cst_speed=6, graph=None, ttweight='ttmedian', seed=None, initial_hour=None,
+                 speed_table=None):
+        if graph_loc is not None:                            # lib/RoutingEngine.py:32-35
+            self.G = RoadGraph.Read_GML(graph_loc)
+        elif graph is not None:
+            self.G = graph if isinstance(graph, RoadGraph) else RoadGraph(graph)
+        self.cst_speed = cst_speed
+        if seed is None:                                     # :37-39
+            seed = np.random.randint(0, 1000000)
+            os.makedirs("output", exist_ok=True)
+            print('ROUTING ENGINE SEED: {}'.format(seed), file=open('output/seeds.txt', 'a+'))
+        self.rs = np.random.RandomState(seed)
+        self.ttweight = ttweight
+        if initial_hour is not None:                         # :43-48
+            self.hour = initial_hour
+            self.speeds = speed_table[speed_table["hour"] == self.hour].sample()
+        else:
+            self.hour = None
+            self.speeds = None
+
+    def update_hour(self, new_hour, speed_table=None):
+        """lib/RoutingEngine.py:51-53 (the reference method is missing ``self`` and reads an undefined
+        global; here the table is passed in)."""
+        self.hour = new_hour
+        if speed_table is not None:
+            self.speeds = speed_table[speed_table["hour"] == self.hour].sample()
+
+    def draw_link_travel_time(self, link_index, use_uncertainty=True):
+        """lib/RoutingEngine.py:56-79.  Stays on the host: it consumes ``self.rs`` in edge order."""
+        graph_link = self.G.es[link_index]
+        if use_uncertainty:
+            if self.speeds is not None:
+                mu = float(self.speeds["edge_{}_speed_mean".format(int(link_index))])
+                sigma = float(self.speeds["edge_{}_speed_stddev".format(int(link_index))])
+                speed_draw = np.max([self.rs.normal(mu, sigma), 5])
+                return graph_link["length"] / (speed_draw * MPH_2_MPS)
+            delta = graph_link["slnshift"]
+            mu = graph_link["slnmean"]
+            sigma = UNCERTAINTY_MULTIPLIER * graph_link["slnsd"]
+            return delta + np.exp(self.rs.normal(mu, sigma))
+        return graph_link[self.ttweight]
+
+    def _path(self, olng, olat, dlng, dlat):
+        onodename = str((olng, olat))                        # :85-87
+        dnodename = str((dlng, dlat))
+        o, d = self.G.node_index(onodename), self.G.node_index(dnodename)
+        return o, d, self.G.epath(o, d, self.ttweight)
+
+    def get_routing(self, olng, olat, dlng, dlat, pre_drawn_tt=None, use_uncertainty=False):
+        """lib/RoutingEngine.py:84-191: route dict with per-edge steps."""
+        o, d, path = self._path(olng, olat, dlng, dlat)
+        G = self.G
+        length = G._eattrs["length"]
+        route = dict()
+        route['distance'] = sum([float(length[idx]) for idx in path])
+        route['steps'] = list()
+        route['duration'] = 0
+        if pre_drawn_tt is not None:
+            if pre_drawn_tt[2] != path:                      # :102-109 path must be reproducible
+                print("Path found in routing doesn't match pre-drawn path!!")
+                print("ROUTE ALREADY FOUND:\n{}\n".format(pre_drawn_tt[2]))
+                print("ROUTE FOUND NOW:\n{}\n".format(path))
+                return None
+            route['duration'] = pre_drawn_tt[0]
+            routing_path = pre_drawn_tt[1]
+        else:
+            routing_path = path
+        cur = o
+        lng, lat = G._vattrs["lng"], G._vattrs["lat"]
+        for edge_index in routing_path:
+            step = dict()
+            step['distance'] = float(length[edge_index])
+            step['mean_duration'] = self.draw_link_travel_time(edge_index, use_uncertainty=False)
+            if pre_drawn_tt is not None:
+                step['duration'] = pre_drawn_tt[1][edge_index]
+            else:
+                drawn = self.draw_link_travel_time(edge_index, use_uncertainty)
+                step['duration'] = drawn
+                route['duration'] += drawn
+            if not use_uncertainty:
+                assert step['duration'] == step['mean_duration']
+            step['weight'] = step['duration']
+            a, b = int(G._src[edge_index]), int(G._dst[edge_index])
+            if cur == a:                                     # :146-153 orient undirected edges along the walk
+                nxt = b
+            else:
+                assert cur == b
+                nxt = a
+            step['intersections'] = [{'location': (lng[cur], lat[cur])}, {'location': (lng[nxt], lat[nxt])}]
+            route['steps'].append(step)
+            cur = nxt
+        route['weight'] = route['duration']
+        if len(path) == 0:                                   # :173-189 stay-in-place dummy step
+            assert o == d
+            loc = (lng[o], lat[o])
+            route['steps'].append({'distance': 0.0, 'duration': 0.0, 'mean_duration': 0.0, 'weight': 0.0,
+                                   'intersections': [{'location': loc}, {'location': loc}]})
+        return route
+
+    def _sums(self, olng, olat, dlng, dlat):
+        o = self.G.node_index(str((olng, olat)))
+        d = self.G.node_index(str((dlng, dlat)))
+        tt, ln, hops = self.G.path_sums([o], [d], self.ttweight)
+        return float(tt[0]), float(ln[0]), int(hops[0])
+
+    def get_distance(self, olng, olat, dlng, dlat):
+        """lib/RoutingEngine.py:195-205: length along the TIME-shortest path (int 0 for an empty path)."""
+        _, ln, hops = self._sums(olng, olat, dlng, dlat)
+        return ln if hops > 0 else 0
+
+    def get_duration(self, olng, olat, dlng, dlat):
+        """lib/RoutingEngine.py:209-218: left-to-right fp64 sum of the path's weights (int 0 for an empty path;
+        igraph returns an empty path for an unreachable target)."""
+        tt, _, hops = self._sums(olng, olat, dlng, dlat)
+        return tt if hops > 0 else 0
+
+    def get_distance_duration(self, olng, olat, dlng, dlat, euclidean=False):
+        """lib/RoutingEngine.py:221-226."""
+        if euclidean:
+            gc_dist = (6371000 * 2 * math.pi / 360 * np.sqrt(
+                (math.cos((olat + dlat) * math.pi / 360) * (olng - dlng)) ** 2 + (olat - dlat) ** 2))
+            return gc_dist, gc_dist / self.cst_speed
+        tt, ln, hops = self._sums(olng, olat, dlng, dlat)
+        return (ln, tt) if hops > 0 else (0, 0)
+
+    def generateRandomLocation(self):
+        """lib/RoutingEngine.py:228-229: ``rs.choice(G.vs)`` draws exactly one ``randint(0, n)``."""
+        return self.G.vs[int(self.rs.randint(0, self.G.n))]
+
+    # ---- batched extensions (not in the reference; same results as calling the scalar methods in a loop)
+    def get_durations(self, pairs):
+        """pairs: iterable of (olng, olat, dlng, dlat) -> np.ndarray of durations."""
+        o = [self.G.node_index(str((p[0], p[1]))) for p in pairs]
+        d = [self.G.node_index(str((p[2], p[3]))) for p in pairs]
+        tt, _, hops = self.G.path_sums(o, d, self.ttweight)
+        return np.where(hops > 0, tt, 0.0)

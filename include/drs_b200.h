@@ -145,6 +145,93 @@ int drs_query_matrix(const drs_graph* g, int32_t npairs, const int32_t* s_host,
 int drs_path(const drs_graph* g, int32_t s, int32_t t, int32_t* edge_ids_host, int32_t* nedges,
              int32_t* reachable);
 
+/* --------------------------------------------------------------- dispatch --
+ * Per-tick vehicle-by-request evaluation.  Replaces the Python loops of
+ * AlonsoMora.generatePairwiseGraph / generateRTVGraph with routing_method
+ * "enumerate" (lib/Optimization.py:104-357) and the functions they call:
+ * findOptimalRouting, minimalDelayPath, permutePassengerOrder,
+ * computeRoutingCost, shortestPathTime (lib/optimUtils.py:41-160,432-557,656-664).
+ *
+ * A "tick" handle owns device copies of the vehicle and request batches, so the
+ * evaluation itself runs on inputs resident in HBM.  All batch arrays are HOST
+ * pointers copied at call time (callers mutate Veh / Req freely between ticks).
+ *
+ * Stop record (one per pickup / drop-off already on a vehicle's plan, in
+ * createLocations order, lib/optimUtils.py:94-108: drop-offs of on-board
+ * requests first, then (pickup, drop-off) of each waiting request):
+ *   node   road-graph vertex            rid   request id (opaque to the kernel)
+ *   pod    +1 pickup / -1 drop-off      prev  index WITHIN THE VEHICLE'S LIST of
+ *   lb,ub  absolute time window               the stop that must precede it, or -1
+ */
+#define DRS_MAX_STOPS 16       /* stops per evaluated trip (new + planned) */
+#define DRS_MAX_TRIP_REQS 4    /* new requests per trip */
+#define DRS_INF_ROUTE_COST 1e6 /* lib/optimUtils.py:156,437: (1e6, None) == infeasible */
+
+typedef struct drs_tick drs_tick;
+
+typedef struct {
+  int32_t n_veh;
+  const int32_t* start_node;  /* veh.get_next_node() vertex (lib/Optimization.py:124,130) */
+  const double* start_delay;  /* its t: time to reach that vertex (veh["t"]) */
+  const int32_t* capacity;    /* veh.K */
+  const int32_t* onboard;     /* len(pax_reqs) */
+  const int32_t* stop_off;    /* n_veh + 1 offsets into the stop arrays */
+  const int32_t* stop_node;
+  const int32_t* stop_rid;
+  const int8_t* stop_pod;
+  const int8_t* stop_prev;
+  const double* stop_lb;
+  const double* stop_ub;
+} drs_vehicle_batch;
+
+typedef struct {
+  int32_t n_req;
+  const int32_t* rid;
+  const int32_t* o_node;
+  const int32_t* d_node;
+  const double* lb_p; /* Cep - T  (relative lower bound, lib/Optimization.py:117) */
+  const double* ub_p; /* Clp */
+  const double* lb_d; /* Ced */
+  const double* ub_d; /* Cld */
+} drs_request_batch;
+
+/* status of one (vehicle, request) pair of the RV stage */
+#define DRS_RV_FEASIBLE 0   /* edge with (cost, route)                 lib/Optimization.py:212-214 */
+#define DRS_RV_SKIPPED 1    /* T + tt(veh -> origin) > Clp             lib/Optimization.py:183-186 */
+#define DRS_RV_SAVED 2      /* empty-dummy-vehicle check failed        lib/Optimization.py:193-202,217-218 */
+#define DRS_RV_INFEASIBLE 3 /* no feasible ordering                    lib/Optimization.py:215-216 */
+
+int drs_tick_create(drs_graph* g, drs_tick** out);
+int drs_tick_destroy(drs_tick* t);
+int drs_tick_set_vehicles(drs_tick* t, const drs_vehicle_batch* vehicles);
+int drs_tick_set_requests(drs_tick* t, const drs_request_batch* requests);
+
+/* flags for the evaluation calls */
+#define DRS_EVAL_PAIRWISE_CHECKS 1 /* findOptimalRouting's pairwise pre-filter when >= 3 requests are
+                                      involved (lib/optimUtils.py:127-156); "enumerate" sets it, the
+                                      tabu front end (lib/optimUtils.py:163-212) has it commented out */
+
+/* RV stage for every (request, vehicle) pair, results left on the device.
+ * counters_host[4] receives the number of pairs per status; *n_edges the number
+ * of feasible edges. */
+int drs_tick_rv_eval(drs_tick* t, double T, int32_t flags, int32_t* n_edges, int64_t* counters_host);
+/* Copy the feasible edges to the host, sorted by (request index, vehicle index):
+ * order[e*DRS_MAX_STOPS + k] is the k-th visited stop, numbered 0 = new pickup,
+ * 1 = new drop-off, 2.. = the vehicle's planned stops in batch order. */
+int drs_tick_rv_fetch(drs_tick* t, int32_t capacity_edges, int32_t* veh_idx, int32_t* req_idx,
+                      double* cost, uint8_t* order, int32_t* n_stops);
+
+/* Explicit trip list (RR edges, RTV trips of size >= 2, or single pairs):
+ * task k = vehicle task_veh[k] (-1: no vehicle, route starts at the first stop at
+ * time T, lib/optimUtils.py:160) with the task_nreq[k] new requests
+ * task_req[k*DRS_MAX_TRIP_REQS ..] (indices into the request batch).  Implements
+ * findOptimalRouting (lib/optimUtils.py:113-160).  cost_host[k] ==
+ * DRS_INF_ROUTE_COST means infeasible.  Stop numbering in order_host: new
+ * requests' (pickup, drop-off) pairs in task order, then the vehicle's stops. */
+int drs_tick_trip_eval(drs_tick* t, double T, int32_t flags, int32_t n_tasks, const int32_t* task_veh,
+                       const int32_t* task_nreq, const int32_t* task_req, double* cost_host,
+                       uint8_t* order_host, int32_t* n_stops_host);
+
 /* ------------------------------------------------------------- ALU peak ---
  * Register-resident add+min stream used as the ALU roofline denominator
  * (SURVEY.md section 8d).  Returns relaxations per second of the fp32
