@@ -1,0 +1,167 @@
+"""CUDA dispatch path (RV stage, trip costing, AlonsoMora drop-in) against the oracle and
+against the reference-generated golden fixtures."""
+import numpy as np
+import pytest
+
+from conftest import OReq, OVeh, golden_map_path, load_golden, oracle_graph, unjf
+
+pytestmark = pytest.mark.gpu
+
+
+def _graph(name):
+    from drs_abm_b200.routing import RoadGraph
+    return RoadGraph.Read_GML(golden_map_path(name))
+
+
+class ReqTable(dict):
+    """``reqs[rid]`` and ``for req in reqs`` like the reference's request list, for sparse rids."""
+
+    def __iter__(self):
+        return iter(list(self.values()))
+
+
+def _objects(G, case_reqs, vehs_spec):
+    """Builds OReq / OVeh objects; reqs is a list indexable by rid."""
+    reqs = ReqTable()
+    for r in case_reqs:
+        o, d = G.vs[r["o"]], G.vs[r["d"]]
+        reqs[r["rid"]] = OReq(r["rid"], o["lng"], o["lat"], d["lng"], d["lat"], unjf(r["Cep"]), unjf(r["Clp"]),
+                              unjf(r["Ced"]), unjf(r["Cld"]), assigned=r.get("assigned", False))
+    vehs = []
+    for v in vehs_spec:
+        nd = G.vs[v["node"]]
+        vehs.append(OVeh(v["vid"], v["K"], (nd["lng"], nd["lat"]), unjf(v["t"]), v["pax"], v["wait"]))
+    return vehs, reqs
+
+
+@pytest.mark.parametrize("name", ["g8_int", "g12_float", "g20_int"])
+def test_trip_costing_matches_reference_golden(name):
+    """findOptimalRouting on the golden stop sets: cost bit-exact on integer maps (1e-5 relative on the
+    float map, where the matrix is fp32), the canonical ordering equal to the oracle's, and the
+    reference's own route wherever its optimum is unique."""
+    from drs_abm_b200.dispatch import Tick
+    from oracle import dispatch_oracle as D
+    from test_oracle_golden import _case_inputs
+    gold = load_golden("cost_%s.json" % name)
+    G = _graph(name)
+    O = oracle_graph(name)
+    Gd = G.dist_rows(0, G.n)
+    tt = lambda a, b: float(Gd[a, b])          # the oracle evaluates on the SAME matrix entries the kernel gathers
+    tol = dict(rel=1e-5, abs=1e-6) if "float" in name else dict(rel=0, abs=0)
+    for case in gold["cases"]:
+        T = case["T"]
+        all_reqs = [dict(r, assigned=True) for r in case["pax"] + case["wait"]] + [dict(case["new"], assigned=False),
+                                                                                   dict(case["other"], assigned=False)]
+        vehs, reqs = _objects(G, all_reqs, [{"vid": 0, "K": case["capacity"], "node": case["start"], "t": case["t0"],
+                                             "pax": [r["rid"] for r in case["pax"]],
+                                             "wait": [r["rid"] for r in case["wait"]]}])
+        tick = Tick(G, vehs, reqs, T, pairwise_checks=True)
+        idx = {r.id: i for i, r in enumerate(tick.new_reqs)}
+        (cost, order), (rr_cost, rr_order) = tick.trip_eval([(0, [idx[1]]), (-1, [idx[1], idx[2]])])
+        assert cost == pytest.approx(unjf(case["cost"]), **tol)
+        assert rr_cost == pytest.approx(unjf(case["rr_cost"]), **tol)
+        # oracle on the kernel's own matrix: identical cost and canonical order
+        veh, new, other = _case_inputs(O, case)
+        # the Tick lists pax / wait stops in set-iteration order; mirror it for the oracle
+        pax_rids, wait_rids = vehs[0].get_passenger_requests()
+        veh["pax_reqs"] = [[r for r in veh["pax_reqs"] if r["rid"] == k][0] for k in pax_rids]
+        veh["wait_reqs"] = [[r for r in veh["wait_reqs"] if r["rid"] == k][0] for k in wait_rids]
+        ocost, oroute, oorder = D.find_optimal_routing([D.request_vertex(new, T)], tt, veh, T)
+        assert cost == ocost
+        assert (order is None) == (oorder is None)
+        if order is not None:
+            assert order == list(oorder)
+            route = tick.route_of(0, [idx[1]], order)
+            assert [(r[0], r[1]) for r in route] == [(r[0], r[1]) for r in oroute]
+            if case["route_unique"] and "float" not in name:
+                assert [[r[0], r[1]] for r in route] == case["route"]
+        orr, _, orr_order = D.find_optimal_routing((D.request_vertex(new, T), D.request_vertex(other, T)), tt, None, T)
+        assert rr_cost == orr and (rr_order is None) == (orr_order is None)
+        if rr_order is not None:
+            assert rr_order == list(orr_order)
+        tick.close()
+    G.close()
+
+
+@pytest.mark.parametrize("fname,name", [("sim_g8_int_K4.json", "g8_int"), ("sim_g20_int_K4.json", "g20_int"),
+                                        ("sim_g20_int_K1.json", "g20_int"), ("sim_g12_float_K2.json", "g12_float")])
+def test_alonso_mora_matches_reference_golden(fname, name):
+    """AlonsoMora("enumerate").optimizeAssignment on the ticks the reference's own classes produced."""
+    from drs_abm_b200.dispatch import AlonsoMora
+    from oracle import dispatch_oracle as D
+    from test_oracle_golden import route_cost, sim_tick_inputs
+    gold = load_golden(fname)
+    G = _graph(name)
+    O = oracle_graph(name)
+    odist = O.dist_matrix()
+    tt = lambda a, b: float(odist[a, b])
+    exact = "float" not in name
+    tol = dict(rel=0, abs=0) if exact else dict(rel=1e-5, abs=1e-6)
+    opt = AlonsoMora({"routing_method": "enumerate", "verbose": False})
+    for tick in gold["ticks"]:
+        T = tick["T"]
+        vehs, reqs = _objects(G, tick["reqs"], tick["vehs"])
+        rv = opt.generatePairwiseGraph(vehs, reqs, G, T)
+        got = {(vehs[vi].id, rv.tick.new_reqs[ri].id): c for (vi, ri), (c, _) in rv.rv.items()}
+        want = {(e["vid"], e["rid"]): unjf(e["cost"]) for e in tick["rv_edges"]}
+        assert set(got) == set(want)
+        for k in want:
+            assert got[k] == pytest.approx(want[k], **tol)
+        got_rr = {tuple(sorted((rv.tick.new_reqs[a].id, rv.tick.new_reqs[b].id))): c for (a, b), (c, _) in rv.rr.items()}
+        want_rr = {tuple(sorted((e["rid1"], e["rid2"]))): unjf(e["cost"]) for e in tick["rr_edges"]}
+        assert set(got_rr) == set(want_rr)
+        for k in want_rr:
+            assert got_rr[k] == pytest.approx(want_rr[k], **tol)
+        rv.tick.close()
+        (routes, rejected), meta = opt.optimizeAssignment(vehs, reqs, G, T)
+        ref_obj = 1e6 * len(tick["rejected"])
+        for vid, route in tick["veh_routes"].items():
+            ref_obj += route_cost(O, tt, tick, int(vid), [tuple(x) for x in route])
+        if not tick["veh_routes"] and not tick["rejected"]:
+            assert len(routes) == 0
+            continue
+        assert meta["objective"] == pytest.approx(ref_obj, rel=0 if exact else 1e-5, abs=1e-6)
+        assert len(rejected) == len(tick["rejected"])
+        # every returned route is feasible at the cost the oracle computes for it, and the vehicle / request
+        # bookkeeping is consistent (each new request served at most once)
+        served = []
+        new_ids = set(r["rid"] for r in tick["reqs"] if r["assigned"] is False)
+        total = 1e6 * len(rejected)
+        for vid, route in routes.items():
+            c = route_cost(O, tt, tick, int(vid), [(r[0], r[1]) for r in route])
+            assert c < 1e6
+            total += c
+            served += [r[0] for r in route if r[1] == 1 and r[0] in new_ids]
+        assert len(served) == len(set(served)) and set(served) | set(rejected) == new_ids
+        assert total == pytest.approx(meta["objective"], rel=0 if exact else 1e-5, abs=1e-6)
+        # oracle end to end: same RTV trip set, same objective
+        ovehs, oreqs = sim_tick_inputs(O, tick)
+        (_, _), ometa = D.optimize_assignment(ovehs, oreqs, tt, T)
+        assert meta["objective"] == pytest.approx(ometa["objective"], rel=0 if exact else 1e-5, abs=1e-6)
+    G.close()
+
+
+def test_empty_and_infeasible_ticks():
+    from drs_abm_b200.dispatch import AlonsoMora
+    G = _graph("g8_int")
+    opt = AlonsoMora({"routing_method": "enumerate", "verbose": False})
+    a, b = G.vs[0], G.vs[G.n - 1]
+    veh = OVeh(0, 4, (a["lng"], a["lat"]), 0, [], [])
+    # no requests at all -> ((list(), list()), {"solve_time": 0})  (lib/Optimization.py:75-76)
+    assert opt.optimizeAssignment([veh], [], G, 0) == ((list(), list()), {"solve_time": 0})
+    # a request nobody can reach in time is rejected
+    far = OReq(0, b["lng"], b["lat"], a["lng"], a["lat"], 0.0, 1.0, 100.0, 200.0)
+    (routes, rejected), meta = opt.optimizeAssignment([veh], [far], G, 0)
+    assert routes == [] and rejected == []                  # empty RTV graph: the reference returns two empty lists
+    # requests already assigned (True) or rejected for distance (None) are not request vertices (:107)
+    done = OReq(1, a["lng"], a["lat"], b["lng"], b["lat"], 0.0, 600.0, 0.0, 1e5, assigned=True)
+    assert opt.optimizeAssignment([veh], [far, done], G, 0)[0] == (list(), list())
+    # a feasible request on the vehicle's own node
+    Ts = G.shortest_paths(a["name"], b["name"], weights="ttmedian")[0][0]
+    ok = OReq(0, a["lng"], a["lat"], b["lng"], b["lat"], 0.0, 600.0, Ts, 600.0 + 1.5 * Ts)
+    (routes, rejected), meta = opt.optimizeAssignment([veh], [ok], G, 0)
+    assert routes == {0: [(0, 1, a["lng"], a["lat"]), (0, -1, b["lng"], b["lat"])]} and rejected == set()
+    assert meta["objective"] == 0.0                           # direct trip arrives exactly at Ced: zero delay
+    # no vehicles
+    assert opt.optimizeAssignment([], [ok], G, 0)[0] == (list(), list())
+    G.close()

@@ -1,0 +1,182 @@
+"""CUDA routing path (through the C-ABI / the RoutingEngine drop-in) against the oracle
+and against the reference-generated golden fixtures."""
+import numpy as np
+import pytest
+
+from conftest import golden_map_path, load_golden, oracle_graph, oracle_graph_from_data, unjf
+
+pytestmark = pytest.mark.gpu
+
+MAPS = ["g8_int", "g12_float", "g20_int", "g20_uniform"]
+
+
+def _engine(name, **kw):
+    from drs_abm_b200.routing import RoutingEngine
+    return RoutingEngine(graph_loc=golden_map_path(name), cst_speed=9, seed=7, **kw)
+
+
+@pytest.mark.parametrize("name", MAPS)
+@pytest.mark.parametrize("mode", [0, 1])
+def test_matrix_and_paths_match_oracle(name, mode):
+    if mode == 1 and "float" in name:
+        pytest.skip("int32 mode needs integer weights")
+    from drs_abm_b200.routing import RoadGraph
+    G = RoadGraph.Read_GML(golden_map_path(name), mode=mode)
+    O = oracle_graph(name)
+    got = G.dist_rows(0, G.n)
+    want = O.dist_matrix()
+    if "float" in name:
+        # north_star tolerance for float travel times: 1e-5 relative
+        assert np.max(np.abs(got - want) / np.maximum(want, 1e-12)) < 1e-5
+    else:
+        assert np.array_equal(got, want)                      # integer weights: bit-exact
+    # canonical predecessor paths
+    rs = np.random.RandomState(1)
+    for _ in range(300):
+        s, t = int(rs.randint(G.n)), int(rs.randint(G.n))
+        ep = G.epath(s, t)
+        if "float" in name:
+            assert np.isclose(sum(O.tt[e] for e in ep), want[s, t], rtol=1e-5)
+            if ep:
+                assert {int(O.src[ep[0]]), int(O.dst[ep[0]])} & {s} and {int(O.src[ep[-1]]), int(O.dst[ep[-1]])} & {t}
+        else:
+            assert ep == O.epath(s, t)                        # integer weights: identical edge ids, ties included
+    G.close()
+
+
+@pytest.mark.parametrize("name", MAPS)
+def test_routing_engine_matches_reference_golden(name):
+    gold = load_golden("routing_%s.json" % name)
+    router = _engine(name)
+    G = router.G
+    tol = dict(rel=1e-5, abs=0) if "float" in name else dict(rel=0, abs=0)
+    for rec in gold["pairs"]:
+        o, d = G.vs[rec["o"]], G.vs[rec["d"]]
+        args = (o["lng"], o["lat"], d["lng"], d["lat"])
+        assert router.get_duration(*args) == pytest.approx(unjf(rec["duration"]), **tol)
+        if "distance" in rec:
+            assert router.get_distance(*args) == pytest.approx(unjf(rec["distance"]), **tol)
+        assert G.shortest_paths(o["name"], d["name"], weights="ttmedian")[0][0] == pytest.approx(
+            unjf(rec["shortest_path_time"]), **tol)
+        eu = router.get_distance_duration(*args, euclidean=True)
+        assert [float(eu[0]), float(eu[1])] == [unjf(rec["euclid"][0]), unjf(rec["euclid"][1])]
+        if "epath" in rec:
+            assert G.get_shortest_paths(o["name"], to=d["name"], weights="ttmedian", output="epath")[0] == rec["epath"]
+    for rec in gold["routes"]:
+        o, d = G.vs[rec["o"]], G.vs[rec["d"]]
+        got = router.get_routing(o["lng"], o["lat"], d["lng"], d["lat"])
+        want = rec["route"]
+        assert got["distance"] == want["distance"] and got["duration"] == want["duration"]
+        assert len(got["steps"]) == len(want["steps"])
+        for gs, ws in zip(got["steps"], want["steps"]):
+            assert gs["distance"] == ws["distance"] and gs["duration"] == ws["duration"] == gs["mean_duration"]
+            assert [list(x["location"]) for x in gs["intersections"]] == [list(x["location"]) for x in ws["intersections"]]
+    from drs_abm_b200.routing import RoutingEngine
+    r2 = RoutingEngine(graph=G, cst_speed=9, seed=11)
+    for rec in gold["random_locations"]:
+        v = r2.generateRandomLocation()
+        assert (v.index, v["lng"], v["lat"]) == (rec["index"], rec["lng"], rec["lat"])
+
+
+def test_routing_engine_matches_oracle_engine_on_ties():
+    """Uniform grid: every pair has many equal-cost paths; the drop-in and the oracle must pick the
+    same canonical one, and the reference's invariants must hold."""
+    from oracle.routing_oracle import OracleRoutingEngine
+    router = _engine("g20_uniform")
+    O = OracleRoutingEngine(oracle_graph("g20_uniform"), cst_speed=9, seed=7)
+    rs = np.random.RandomState(5)
+    n = router.G.n
+    for _ in range(60):
+        o, d = router.G.vs[int(rs.randint(n))], router.G.vs[int(rs.randint(n))]
+        args = (o["lng"], o["lat"], d["lng"], d["lat"])
+        a, b = router.get_routing(*args), O.get_routing(*args)
+        assert a == b
+        # lib/Agents.py:358,999-1000: get_duration == sum of the step durations of get_routing
+        assert router.get_duration(*args) == sum(s["duration"] for s in a["steps"])
+        assert router.get_distance_duration(*args) == O.get_distance_duration(*args)
+
+
+def test_same_node_unknown_vertex_and_weight_updates():
+    router = _engine("g8_int")
+    G = router.G
+    v = G.vs[3]
+    assert router.get_duration(v["lng"], v["lat"], v["lng"], v["lat"]) == 0
+    assert router.get_distance(v["lng"], v["lat"], v["lng"], v["lat"]) == 0
+    r = router.get_routing(v["lng"], v["lat"], v["lng"], v["lat"])
+    assert len(r["steps"]) == 1 and r["steps"][0]["distance"] == 0.0       # lib/RoutingEngine.py:173-189
+    with pytest.raises(ValueError):                                          # igraph vs.find -> ValueError
+        router.get_duration(0.5, 0.5, v["lng"], v["lat"])
+    with pytest.raises(ValueError):
+        G.vs.find(name="(1.0, 2.0)")
+    assert G.vs.find(name=v["name"]).index == 3
+    # numpy-2 scalar reprs resolve to the same vertex (last row)
+    assert G.node_index(str((np.float64(v["lng"]), np.float64(v["lat"])))) == 3
+    # weight mutation after load (optimizationTesting.py:221-226) invalidates the matrix
+    O = oracle_graph_from_data(__import__("drs_abm_b200.gml", fromlist=["read_gml"]).read_gml(golden_map_path("g8_int")))
+    before = G.shortest_paths(G.vs[0]["name"], G.vs[G.n - 1]["name"], weights="ttmedian")[0][0]
+    assert before == O.dist_matrix()[0, G.n - 1]
+    new_tt = np.array(G.es["ttmedian"]) * 2.0 + 1.0
+    for i in range(G.m):
+        G.es[i]["ttmedian"] = float(new_tt[i])
+    O.tt = new_tt.copy(); O.invalidate()
+    after = G.shortest_paths(G.vs[0]["name"], G.vs[G.n - 1]["name"], weights="ttmedian")[0][0]
+    assert after == O.dist_matrix()[0, G.n - 1] and after != before
+    G.es["ttmedian"] = new_tt * 3.0
+    O.tt = new_tt * 3.0; O.invalidate()
+    assert np.array_equal(G.dist_rows(0, G.n), O.dist_matrix())
+
+
+def test_c2_full_size_properties():
+    """BASELINE config C2 (5k nodes): exact match with the oracle's Dijkstra on sampled rows plus
+    size-independent properties of the whole matrix (symmetry, zero diagonal, triangle inequality
+    through random pivots, tight predecessor edges)."""
+    from drs_abm_b200 import synth
+    from drs_abm_b200.routing import RoadGraph
+    data = synth.config_graph("C2")
+    G = RoadGraph(data)
+    O = oracle_graph_from_data(data)
+    D = G.dist_rows(0, G.n)
+    idx = np.random.RandomState(0).randint(0, G.n, 40)
+    assert np.array_equal(D[idx], O.dist_rows(idx))
+    assert np.array_equal(D, D.T) and np.all(np.diag(D) == 0) and np.isfinite(D).all()
+    rs = np.random.RandomState(2)
+    for _ in range(20):
+        k = int(rs.randint(G.n))
+        assert np.all(D <= D[:, [k]] + D[[k], :])
+    s = rs.randint(0, G.n, 500).astype(np.int32); t = rs.randint(0, G.n, 500).astype(np.int32)
+    tt, ln, hops = G.path_sums(s, t)
+    assert np.array_equal(tt, D[s, t]) and np.array_equal(ln, 10.0 * tt)     # length = 10 * ttmedian on "int" maps
+    G.close()
+
+
+def test_query_before_build_and_bad_arguments():
+    import ctypes as C
+    from drs_abm_b200 import _lib
+    lib = _lib.load()
+    h = C.c_void_p()
+    src = np.array([0, 1], dtype=np.int32); dst = np.array([1, 2], dtype=np.int32)
+    tt = np.array([1.0, 2.0]); ln = np.array([10.0, 20.0])
+    assert lib.drs_graph_create(3, 2, 0, _lib.ptr_i32(src), _lib.ptr_i32(dst), _lib.ptr_f64(tt), _lib.ptr_f64(ln), C.byref(h)) == 0
+    out = np.zeros(1)
+    s = np.array([0], dtype=np.int32); t = np.array([2], dtype=np.int32)
+    assert lib.drs_query_matrix(h, 1, _lib.ptr_i32(s), _lib.ptr_i32(t), _lib.ptr_f64(out)) == _lib.ERR_STATE
+    assert lib.drs_apsp_build(h, 0) == 0
+    assert lib.drs_query_matrix(h, 1, _lib.ptr_i32(s), _lib.ptr_i32(t), _lib.ptr_f64(out)) == 0 and out[0] == 3.0
+    bad = np.array([7], dtype=np.int32)
+    assert lib.drs_query_matrix(h, 1, _lib.ptr_i32(bad), _lib.ptr_i32(t), _lib.ptr_f64(out)) == _lib.ERR_RANGE
+    neg = np.array([1.0, -2.0])
+    assert lib.drs_graph_set_weights(h, _lib.ptr_f64(neg)) == _lib.ERR_ARG
+    frac = np.array([1.5, 2.0])
+    assert lib.drs_graph_set_weights(h, _lib.ptr_f64(frac)) == 0
+    assert lib.drs_apsp_build(h, 1) == _lib.ERR_ARG          # int32 mode refuses fractional weights
+    lib.drs_graph_destroy(h)
+    # disconnected graph: unreachable = inf, empty path, duration 0 like igraph's empty epath
+    h = C.c_void_p()
+    assert lib.drs_graph_create(4, 2, 0, _lib.ptr_i32(src), _lib.ptr_i32(dst), _lib.ptr_f64(tt), _lib.ptr_f64(ln), C.byref(h)) == 0
+    assert lib.drs_apsp_build(h, 0) == 0
+    t3 = np.array([3], dtype=np.int32)
+    assert lib.drs_query_matrix(h, 1, _lib.ptr_i32(s), _lib.ptr_i32(t3), _lib.ptr_f64(out)) == 0 and np.isinf(out[0])
+    hops = np.zeros(1, dtype=np.int32)
+    assert lib.drs_query_pairs(h, 1, _lib.ptr_i32(s), _lib.ptr_i32(t3), _lib.ptr_f64(out), None, _lib.ptr_i32(hops)) == 0
+    assert hops[0] == -1
+    lib.drs_graph_destroy(h)
