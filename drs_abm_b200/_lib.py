@@ -48,6 +48,25 @@ class RequestBatch(C.Structure):
                 ("ub_p", _f64p), ("lb_d", _f64p), ("ub_d", _f64p)]
 
 
+class PlanBatch(C.Structure):
+    """drs_plan_batch (include/drs_b200.h)."""
+    _fields_ = [("n_veh", C.c_int32), ("start_node", _i32p), ("start_delay", _f64p), ("onboard", _i32p),
+                ("clock", _f64p), ("capacity", _i32p), ("cost", _f64p), ("stop_off", _i32p), ("stop_node", _i32p),
+                ("stop_req", _i32p), ("stop_pod", _i8p)]
+
+
+class RequestTable(C.Structure):
+    """drs_request_table (include/drs_b200.h)."""
+    _fields_ = [("n_rows", C.c_int32), ("o_node", _i32p), ("d_node", _i32p), ("Cep", _f64p), ("Clp", _f64p),
+                ("Cld", _f64p), ("Ts", _f64p), ("Tr", _f64p), ("pwt", _f64p)]
+
+
+class InsertionParams(C.Structure):
+    """drs_insertion_params (include/drs_b200.h)."""
+    _fields_ = [("max_detour", C.c_double), ("coef_inveh", C.c_double), ("coef_wait", C.c_double),
+                ("coef_extra_wait", C.c_double)]
+
+
 # name -> (restype, argtypes); kept in one table so tests can check that every
 # symbol declared in include/drs_b200.h is exported and bound.
 SIGNATURES = {
@@ -70,12 +89,17 @@ SIGNATURES = {
     "drs_query_matrix": (C.c_int, [_vp, C.c_int32, _i32p, _i32p, _f64p]),
     "drs_path": (C.c_int, [_vp, C.c_int32, C.c_int32, _i32p, _i32p, _i32p]),
     "drs_alu_peak": (C.c_int, [C.c_int32, C.c_int32, _f64p]),
+    "drs_graph_stream": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "drs_launch_count": (C.c_int64, []),
+    "drs_apsp_last_profile": (C.c_int, [_vp, _f64p, _i32p]),
     "drs_tick_create": (C.c_int, [_vp, C.POINTER(_vp)]),
     "drs_tick_destroy": (C.c_int, [_vp]),
     "drs_tick_set_vehicles": (C.c_int, [_vp, C.POINTER(VehicleBatch)]),
     "drs_tick_set_requests": (C.c_int, [_vp, C.POINTER(RequestBatch)]),
     "drs_tick_rv_eval": (C.c_int, [_vp, C.c_double, C.c_int32, _i32p, _i64p]),
     "drs_tick_rv_fetch": (C.c_int, [_vp, C.c_int32, _i32p, _i32p, _f64p, _u8p, _i32p]),
+    "drs_tick_set_plans": (C.c_int, [_vp, C.POINTER(PlanBatch), C.POINTER(RequestTable), C.POINTER(InsertionParams)]),
+    "drs_tick_insertion_eval": (C.c_int, [_vp, C.c_int32, _i32p, _i32p, _i32p, _i32p, _f64p, _i64p]),
     "drs_tick_trip_eval": (C.c_int, [_vp, C.c_double, C.c_int32, C.c_int32, _i32p, _i32p, _i32p, _f64p, _u8p,
                                      _i32p]),
 }

@@ -23,36 +23,12 @@
 #include <numeric>
 
 #include "drs_common.cuh"
+#include "drs_tick.cuh"
 
 namespace {
 
 constexpr int MAXS = DRS_MAX_STOPS;
 constexpr int MAXR = DRS_MAX_TRIP_REQS;
-
-struct TickDev {
-  // vehicles
-  int n_veh = 0, n_stops = 0;
-  int32_t *v_node = nullptr, *v_cap = nullptr, *v_pax = nullptr, *v_off = nullptr;
-  double* v_delay = nullptr;
-  int32_t *s_node = nullptr, *s_rid = nullptr;
-  int8_t *s_pod = nullptr, *s_prev = nullptr;
-  double *s_lb = nullptr, *s_ub = nullptr;
-  // requests
-  int n_req = 0;
-  int32_t *r_rid = nullptr, *r_o = nullptr, *r_d = nullptr;
-  double *r_lbp = nullptr, *r_ubp = nullptr, *r_lbd = nullptr, *r_ubd = nullptr;
-};
-
-struct DistView {
-  const void* dist;
-  int64_t ld;
-  int mode;
-  __device__ __forceinline__ double at(int a, int b) const {
-    if (mode == DRS_MODE_F32) return (double)((const float*)dist)[(int64_t)a * ld + b];
-    const int d = ((const int*)dist)[(int64_t)a * ld + b];
-    return d >= DRS_I32_INF ? __longlong_as_double(0x7ff0000000000000LL) : (double)d;
-  }
-};
 
 // One evaluation problem in thread-local storage.  Vertex 0 of `tt` is the start.
 struct Trip {
@@ -314,30 +290,9 @@ __global__ void count_status_kernel(const int8_t* status, int64_t total, unsigne
   }
 }
 
-template <typename T> int upload(T** dptr, const T* h, size_t n, cudaStream_t st) {
-  if (*dptr) { cudaFree(*dptr); *dptr = nullptr; }
-  DRS_CUDA(cudaMalloc((void**)dptr, std::max<size_t>(n, 1) * sizeof(T)));
-  if (n) DRS_CUDA(cudaMemcpyAsync(*dptr, h, n * sizeof(T), cudaMemcpyHostToDevice, st));
-  return DRS_OK;
-}
+template <typename T> int upload(T** dptr, const T* h, size_t n, cudaStream_t st) { return drs_upload(dptr, h, n, st); }
 
 }  // namespace
-
-struct drs_tick {
-  drs_graph* g = nullptr;
-  TickDev dev;
-  // RV results (device)
-  int64_t rv_pairs = 0;
-  int rv_nsurv = 0;
-  int8_t* d_status = nullptr;
-  int32_t *d_surv_veh = nullptr, *d_surv_req = nullptr;
-  int* d_surv_count = nullptr;
-  double* d_cost = nullptr;
-  uint8_t* d_order = nullptr;
-  int32_t* d_nstops = nullptr;
-  unsigned long long* d_counters = nullptr;
-  int64_t surv_capacity = 0;
-};
 
 static void tick_free_results(drs_tick* t) {
   void* ptrs[] = {t->d_status, t->d_surv_veh, t->d_surv_req, t->d_surv_count, t->d_cost, t->d_order, t->d_nstops,
@@ -362,6 +317,7 @@ extern "C" int drs_tick_destroy(drs_tick* t) {
   if (!t) return DRS_OK;
   DrsDeviceGuard guard(t->g->device);
   tick_free_results(t);
+  drs_tick_free_plans(t);
   TickDev& d = t->dev;
   void* ptrs[] = {d.v_node, d.v_cap, d.v_pax, d.v_off, d.v_delay, d.s_node, d.s_rid, d.s_pod, d.s_prev, d.s_lb, d.s_ub,
                   d.r_rid, d.r_o, d.r_d, d.r_lbp, d.r_ubp, d.r_lbd, d.r_ubd};
@@ -470,6 +426,7 @@ extern "C" int drs_tick_rv_eval(drs_tick* t, double T, int32_t flags, int32_t* n
   const int threads = 256;
   rv_filter_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, st>>>(d, dv, T, t->d_status, t->d_surv_veh,
                                                                                     t->d_surv_req, t->d_surv_count);
+  drs_count_launch();
   DRS_CUDA(cudaGetLastError());
   int nsurv = 0;
   DRS_CUDA(cudaMemcpyAsync(&nsurv, t->d_surv_count, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -482,9 +439,11 @@ extern "C" int drs_tick_rv_eval(drs_tick* t, double T, int32_t flags, int32_t* n
   if (nsurv > 0) {
     rv_eval_kernel<<<(nsurv + 63) / 64, 64, 0, st>>>(d, dv, T, flags, nsurv, t->d_surv_veh, t->d_surv_req, t->d_status,
                                                      t->d_cost, t->d_order, t->d_nstops);
-    DRS_CUDA(cudaGetLastError());
+    drs_count_launch();
+  DRS_CUDA(cudaGetLastError());
   }
   count_status_kernel<<<148 * 2, 256, 0, st>>>(t->d_status, total, t->d_counters);
+  drs_count_launch();
   DRS_CUDA(cudaGetLastError());
   unsigned long long c[4];
   DRS_CUDA(cudaMemcpyAsync(c, t->d_counters, sizeof(c), cudaMemcpyDeviceToHost, st));
@@ -567,6 +526,7 @@ extern "C" int drs_tick_trip_eval(drs_tick* t, double T, int32_t flags, int32_t 
   DistView dv{t->g->d_dist, t->g->ld, t->g->mode};
   TaskList tl{dv_, dn, dr};
   trip_eval_kernel<<<(n_tasks + 63) / 64, 64, 0, st>>>(d, dv, T, flags, n_tasks, tl, dc, dord, dns);
+  drs_count_launch();
   std::vector<int32_t> nst(n_tasks);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpyAsync(cost_host, dc, sizeof(double) * n_tasks, cudaMemcpyDeviceToHost, st);

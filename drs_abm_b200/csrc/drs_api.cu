@@ -17,6 +17,11 @@ void drs_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+#include <atomic>
+static std::atomic<long long> g_launches{0};
+void drs_count_launch(int n) { g_launches += n; }
+extern "C" int64_t drs_launch_count(void) { return (int64_t)g_launches.load(); }
+
 extern "C" const char* drs_last_error(void) { return g_err; }
 extern "C" int drs_version(void) { return 100; }
 
@@ -186,16 +191,49 @@ extern "C" int drs_apsp_build(drs_graph* g, int32_t mode) {
   g->apsp_valid = false;
   g->mode = mode;
   int rc;
-  if ((rc = drs_fw_init(g, mode, g->d_dist, ld, 0, g->npad, g->stream))) return rc;
   const int nb = g->npad / DRS_FW_TILE;
+  cudaStream_t st = g->stream;
+  // events: [0] start, [1] after init, then per round (after pivot row, after update), last after pred
+  std::vector<cudaEvent_t> ev(3 + 2 * nb);
+  for (auto& e : ev) DRS_CUDA(cudaEventCreate(&e));
+  auto release = [&]() { for (auto& e : ev) cudaEventDestroy(e); };
+  DRS_CUDA(cudaEventRecord(ev[0], st));
+  if ((rc = drs_fw_init(g, mode, g->d_dist, ld, 0, g->npad, st))) { release(); return rc; }
+  DRS_CUDA(cudaEventRecord(ev[1], st));
   for (int kb = 0; kb < nb; ++kb) {
     char* panel = (char*)g->d_dist + sizeof(float) * (int64_t)kb * DRS_FW_TILE * ld;
-    if ((rc = drs_fw_pivot_row(mode, panel, ld, kb, g->stream))) return rc;
-    if ((rc = drs_fw_update(mode, g->d_dist, ld, g->npad, panel, kb, kb, 0, nb, g->stream))) return rc;
+    if ((rc = drs_fw_pivot_row(mode, panel, ld, kb, st))) { release(); return rc; }
+    DRS_CUDA(cudaEventRecord(ev[2 + 2 * kb], st));
+    if ((rc = drs_fw_update(mode, g->d_dist, ld, g->npad, panel, kb, kb, 0, nb, st))) { release(); return rc; }
+    DRS_CUDA(cudaEventRecord(ev[3 + 2 * kb], st));
   }
-  if ((rc = drs_pred_build(g, mode, g->d_dist, ld, 0, g->npad, g->d_pred, g->stream))) return rc;
-  DRS_CUDA(cudaStreamSynchronize(g->stream));
+  if ((rc = drs_pred_build(g, mode, g->d_dist, ld, 0, g->npad, g->d_pred, st))) { release(); return rc; }
+  DRS_CUDA(cudaEventRecord(ev[2 + 2 * nb], st));
+  DRS_CUDA(cudaStreamSynchronize(st));
+  float ms = 0;
+  g->prof_ms[0] = g->prof_ms[1] = g->prof_ms[2] = g->prof_ms[3] = 0;
+  cudaEventElapsedTime(&ms, ev[0], ev[1]); g->prof_ms[0] = ms;
+  for (int kb = 0; kb < nb; ++kb) {
+    cudaEventElapsedTime(&ms, ev[1 + 2 * kb], ev[2 + 2 * kb]); g->prof_ms[1] += ms;
+    cudaEventElapsedTime(&ms, ev[2 + 2 * kb], ev[3 + 2 * kb]); g->prof_ms[2] += ms;
+  }
+  cudaEventElapsedTime(&ms, ev[1 + 2 * nb], ev[2 + 2 * nb]); g->prof_ms[3] = ms;
+  g->prof_rounds = nb;
+  release();
   g->apsp_valid = true;
+  return DRS_OK;
+}
+
+extern "C" int drs_graph_stream(const drs_graph* g, void** stream) {
+  DRS_REQUIRE(g && stream, DRS_ERR_ARG, "drs_graph_stream: null argument");
+  *stream = (void*)g->stream;
+  return DRS_OK;
+}
+
+extern "C" int drs_apsp_last_profile(const drs_graph* g, double* ms, int32_t* rounds) {
+  DRS_REQUIRE(g && ms, DRS_ERR_ARG, "drs_apsp_last_profile: null argument");
+  for (int i = 0; i < 4; ++i) ms[i] = g->prof_ms[i];
+  if (rounds) *rounds = g->prof_rounds;
   return DRS_OK;
 }
 
@@ -336,6 +374,7 @@ extern "C" int drs_query_pairs(const drs_graph* g, int32_t npairs, const int32_t
   const int blocks = (npairs + 127) / 128;
   path_count_kernel<<<blocks, 128, 0, st>>>(npairs, ds.as<int32_t>(), dt.as<int32_t>(), g->d_pred, g->ld, g->n,
                                             g->d_esrc, g->d_edst, dh.as<int32_t>());
+  drs_count_launch();
   DRS_CUDA(cudaGetLastError());
   std::vector<int32_t> hops(npairs);
   DRS_CUDA(cudaMemcpyAsync(hops.data(), dh.p, sizeof(int32_t) * npairs, cudaMemcpyDeviceToHost, st));
@@ -348,6 +387,7 @@ extern "C" int drs_query_pairs(const drs_graph* g, int32_t npairs, const int32_t
   path_fill_kernel<<<blocks, 128, 0, st>>>(npairs, ds.as<int32_t>(), dt.as<int32_t>(), g->d_pred, g->ld, g->d_esrc,
                                            g->d_edst, dh.as<int32_t>(), doff.as<int64_t>(), dpath.as<int32_t>(),
                                            g->d_tt64, g->d_len64, dtt.as<double>(), dlen.as<double>());
+  drs_count_launch();
   DRS_CUDA(cudaGetLastError());
   if (tt_out) DRS_CUDA(cudaMemcpyAsync(tt_out, dtt.p, sizeof(double) * npairs, cudaMemcpyDeviceToHost, st));
   if (len_out) DRS_CUDA(cudaMemcpyAsync(len_out, dlen.p, sizeof(double) * npairs, cudaMemcpyDeviceToHost, st));
@@ -377,6 +417,7 @@ extern "C" int drs_query_matrix(const drs_graph* g, int32_t npairs, const int32_
   else
     matrix_gather_kernel<int><<<blocks, 128, 0, st>>>(npairs, ds.as<int32_t>(), dt.as<int32_t>(),
                                                       (const int*)g->d_dist, g->ld, dout.as<double>());
+  drs_count_launch();
   DRS_CUDA(cudaGetLastError());
   DRS_CUDA(cudaMemcpyAsync(tt_out, dout.p, sizeof(double) * npairs, cudaMemcpyDeviceToHost, st));
   DRS_CUDA(cudaStreamSynchronize(st));
@@ -400,6 +441,7 @@ extern "C" int drs_apsp_rows_to_host(const drs_graph* g, int32_t row0, int32_t n
   else
     rows_to_double_kernel<int><<<148 * 4, 256, 0, g->stream>>>((const int*)g->d_dist, g->ld, row0, nrows, g->n,
                                                                 tmp.as<double>());
+  drs_count_launch();
   DRS_CUDA(cudaGetLastError());
   DRS_CUDA(cudaMemcpyAsync(out, tmp.p, bytes, cudaMemcpyDeviceToHost, g->stream));
   DRS_CUDA(cudaStreamSynchronize(g->stream));
@@ -421,6 +463,7 @@ extern "C" int drs_path(const drs_graph* g, int32_t s, int32_t t, int32_t* edge_
   DRS_CUDA(cudaMemcpyAsync(dq.p, q, sizeof(q), cudaMemcpyHostToDevice, st));
   path_count_kernel<<<1, 32, 0, st>>>(1, dq.as<int32_t>(), dq.as<int32_t>() + 1, g->d_pred, g->ld, g->n, g->d_esrc,
                                       g->d_edst, dh.as<int32_t>());
+  drs_count_launch();
   DRS_CUDA(cudaGetLastError());
   int32_t h = 0;
   DRS_CUDA(cudaMemcpyAsync(&h, dh.p, sizeof(h), cudaMemcpyDeviceToHost, st));
@@ -434,6 +477,7 @@ extern "C" int drs_path(const drs_graph* g, int32_t s, int32_t t, int32_t* edge_
   path_fill_kernel<<<1, 32, 0, st>>>(1, dq.as<int32_t>(), dq.as<int32_t>() + 1, g->d_pred, g->ld, g->d_esrc, g->d_edst,
                                      dh.as<int32_t>(), doff.as<int64_t>(), dpath.as<int32_t>(), g->d_tt64, g->d_len64,
                                      nullptr, nullptr);
+  drs_count_launch();
   DRS_CUDA(cudaGetLastError());
   DRS_CUDA(cudaMemcpyAsync(edge_ids, dpath.p, sizeof(int32_t) * h, cudaMemcpyDeviceToHost, st));
   DRS_CUDA(cudaStreamSynchronize(st));

@@ -9,6 +9,7 @@
 #include "drs_b200.h"
 
 void drs_set_error(const char* fmt, ...);
+void drs_count_launch(int n = 1);
 
 #define DRS_CUDA(call)                                                                      \
   do {                                                                                      \
@@ -64,6 +65,9 @@ struct drs_graph {
   int64_t ld = 0;
 
   cudaStream_t stream = nullptr;
+
+  double prof_ms[4] = {0, 0, 0, 0};   // last build, by phase (drs_apsp_last_profile)
+  int prof_rounds = 0;
 };
 
 int drs_graph_upload_weights(drs_graph* g);

@@ -1,0 +1,57 @@
+// Per-tick device state shared by the dispatch and insertion translation units.
+#pragma once
+#include "drs_common.cuh"
+
+struct TickDev {
+  // vehicles
+  int n_veh = 0, n_stops = 0;
+  int32_t *v_node = nullptr, *v_cap = nullptr, *v_pax = nullptr, *v_off = nullptr;
+  double* v_delay = nullptr;
+  int32_t *s_node = nullptr, *s_rid = nullptr;
+  int8_t *s_pod = nullptr, *s_prev = nullptr;
+  double *s_lb = nullptr, *s_ub = nullptr;
+  // requests
+  int n_req = 0;
+  int32_t *r_rid = nullptr, *r_o = nullptr, *r_d = nullptr;
+  double *r_lbp = nullptr, *r_ubp = nullptr, *r_lbd = nullptr, *r_ubd = nullptr;
+};
+
+struct DistView {
+  const void* dist;
+  int64_t ld;
+  int mode;
+  __device__ __forceinline__ double at(int a, int b) const {
+    if (mode == DRS_MODE_F32) return (double)((const float*)dist)[(int64_t)a * ld + b];
+    const int d = ((const int*)dist)[(int64_t)a * ld + b];
+    return d >= DRS_I32_INF ? __longlong_as_double(0x7ff0000000000000LL) : (double)d;
+  }
+};
+
+struct LegacyDev;   // insertion_kernels.cu
+
+struct drs_tick {
+  drs_graph* g = nullptr;
+  TickDev dev;
+  // RV results (device)
+  int64_t rv_pairs = 0;
+  int rv_nsurv = 0;
+  int8_t* d_status = nullptr;
+  int32_t *d_surv_veh = nullptr, *d_surv_req = nullptr;
+  int* d_surv_count = nullptr;
+  double* d_cost = nullptr;
+  uint8_t* d_order = nullptr;
+  int32_t* d_nstops = nullptr;
+  unsigned long long* d_counters = nullptr;
+  int64_t surv_capacity = 0;
+  LegacyDev* legacy = nullptr;   // plans + request table of the insertion heuristic
+};
+
+
+void drs_tick_free_plans(drs_tick* t);
+
+template <typename T> inline int drs_upload(T** dptr, const T* h, size_t n, cudaStream_t st) {
+  if (*dptr) { cudaFree(*dptr); *dptr = nullptr; }
+  DRS_CUDA(cudaMalloc((void**)dptr, (n > 0 ? n : 1) * sizeof(T)));
+  if (n) DRS_CUDA(cudaMemcpyAsync(*dptr, h, n * sizeof(T), cudaMemcpyHostToDevice, st));
+  return DRS_OK;
+}

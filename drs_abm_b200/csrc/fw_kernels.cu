@@ -273,6 +273,7 @@ int launch_tile(const TileArgs<T>& p, dim3 grid, cudaStream_t st) {
   }
   if (grid.x == 0 || grid.y == 0) return DRS_OK;
   fw_minplus_tile_kernel<T><<<grid, NTHREADS, kTileSmemBytes, st>>>(p);
+  drs_count_launch();
   DRS_CUDA(cudaGetLastError());
   return DRS_OK;
 }
@@ -290,6 +291,7 @@ int pivot_row_impl(T* panel, int64_t ld, int kb, cudaStream_t st) {
   int rc = launch_tile<T>(p, dim3(0, 0), st);   // configure only
   if (rc) return rc;
   fw_diag_kernel<T><<<1, 1024, kDiagSmemBytes, st>>>(diag, ld);
+  drs_count_launch();
   DRS_CUDA(cudaGetLastError());
   return launch_tile<T>(p, dim3(nb, 1), st);
 }
@@ -340,6 +342,7 @@ extern "C" int drs_fw_init(const drs_graph* g, int32_t mode, void* local_dev, in
   } else {
     DRS_REQUIRE(false, DRS_ERR_ARG, "drs_fw_init: unknown mode %d", mode);
   }
+  drs_count_launch(nreal > 0 ? 2 : 1);
   DRS_CUDA(cudaGetLastError());
   return DRS_OK;
 }
@@ -384,6 +387,7 @@ extern "C" int drs_pred_build(const drs_graph* g, int32_t mode, const void* loca
                                            g->d_in_src, g->d_in_eid, g->d_in_w, pred_local_dev);
   else
     DRS_REQUIRE(false, DRS_ERR_ARG, "drs_pred_build: unknown mode %d", mode);
+  drs_count_launch();
   DRS_CUDA(cudaGetLastError());
   return DRS_OK;
 }

@@ -1,0 +1,339 @@
+// (vehicle, pickup slot, drop-off slot) insertion evaluation and argmin.
+//
+// Replaces Model.insert_heuristics / test_constraints_get_cost
+// (lib/Agents.py:1451-1572).  Per (vehicle, request) pair the kernel gathers the
+// 4L+3 travel times between the request's origin / destination and the vehicle's
+// L planned stops (plus the L segment times of the plan itself) from the resident
+// matrix and walks every candidate route in fp64 with the reference's operation
+// order, so costs are bit-identical for integer-weighted maps.
+//
+//   insertion_scan_kernel   one thread per (vehicle, request) pair, requests
+//       fastest: a warp shares the vehicle (uniform control flow, broadcast plan
+//       loads) and its gathers stay inside the plan stops' matrix rows.  Every
+//       (i, j) candidate is evaluated WITHOUT the incumbent bound; the pair's
+//       smallest successful total cost is written out (+inf if none).
+//   insertion_fold_kernel   one thread per request walks the vehicles in the
+//       reference's order.  A vehicle can only change the incumbent if its
+//       smallest cost is <= the bound C = veh.c + dc (lib/Agents.py:1470); only
+//       then is the pair re-scanned exactly as the reference does it -- with the
+//       bound, "last equal-or-better wins" and the viol-code loop breaks.
+#include <algorithm>
+#include <cstring>
+
+#include "drs_tick.cuh"
+
+namespace {
+
+constexpr int MAXL = DRS_MAX_STOPS - 2;   // planned stops per vehicle
+
+struct PlanView {
+  int n_veh;
+  const int32_t *node, *onboard, *cap, *off, *s_node, *s_req;
+  const double *delay, *clock, *cost;
+  const int8_t* s_pod;
+  // request table
+  const int32_t *q_o, *q_d;
+  const double *q_cep, *q_clp, *q_cld, *q_ts, *q_tr, *q_pwt;
+  drs_insertion_params prm;
+};
+
+// Everything one (vehicle, request) pair needs, in thread-local storage.
+struct Pair {
+  int L;                    // planned stops
+  int n0, K;
+  double T, t0, c0;
+  int8_t pod[MAXL];
+  int req[MAXL];
+  double seg[MAXL];         // seg[k]  = tt(stop k-1 -> stop k), stop -1 = start vertex
+  double to_o[MAXL + 1];    // to_o[k] = tt(stop k-1 -> origin)      (k = 0: from the start vertex)
+  double to_d[MAXL + 1];    // to_d[k] = tt(stop k-1 -> destination)
+  double from_o[MAXL];      // from_o[k] = tt(origin -> stop k)
+  double from_d[MAXL];      // from_d[k] = tt(destination -> stop k)
+  double od;                // tt(origin -> destination)
+  int new_req;
+};
+
+__device__ void load_pair(Pair& p, const PlanView& pv, const DistView& dv, int v, int rrow) {
+  const int s0 = pv.off[v];
+  p.L = pv.off[v + 1] - s0;
+  p.n0 = pv.onboard[v]; p.K = pv.cap[v];
+  p.T = pv.clock[v]; p.t0 = pv.delay[v]; p.c0 = pv.cost[v];
+  p.new_req = rrow;
+  const int o = pv.q_o[rrow], d = pv.q_d[rrow];
+  int prev = pv.node[v];
+  p.to_o[0] = (prev == o) ? 0.0 : dv.at(prev, o);
+  p.to_d[0] = (prev == d) ? 0.0 : dv.at(prev, d);
+  for (int k = 0; k < p.L; ++k) {
+    const int nd = pv.s_node[s0 + k];
+    p.pod[k] = pv.s_pod[s0 + k];
+    p.req[k] = pv.s_req[s0 + k];
+    p.seg[k] = (prev == nd) ? 0.0 : dv.at(prev, nd);
+    p.from_o[k] = (o == nd) ? 0.0 : dv.at(o, nd);
+    p.from_d[k] = (d == nd) ? 0.0 : dv.at(d, nd);
+    p.to_o[k + 1] = (nd == o) ? 0.0 : dv.at(nd, o);
+    p.to_d[k + 1] = (nd == d) ? 0.0 : dv.at(nd, d);
+    prev = nd;
+  }
+  p.od = (o == d) ? 0.0 : dv.at(o, d);
+}
+
+// test_constraints_get_cost (lib/Agents.py:1493-1572) for the candidate "pickup after a
+// planned stops, drop-off after b planned stops" (a <= b), i.e. (i, j) = (a, b + 1).
+// Returns viol (-1 = success) and the total cost through *c_out.
+__device__ int eval_candidate(const Pair& p, const PlanView& pv, int a, int b, double C, double* c_out) {
+  // capacity pre-check over the whole candidate route (:1518-1521)
+  {
+    int n = p.n0;
+    for (int k = 0; k <= p.L; ++k) {
+      if (k == a) { n += 1; if (n > p.K) return 1; }
+      if (k == b) { n -= 1; }
+      if (k < p.L) { n += p.pod[k]; if (n > p.K) return 1; }
+    }
+  }
+  double cld_local[MAXL];            // Cld of requests picked up inside this candidate (:1550,1554)
+  double cld_new = 0.0;
+  double c = 0.0, t = 0.0 + p.t0;
+  int n = p.n0;
+  const double T = p.T;
+  // sequence: planned stops 0..L-1 with the pickup before stop a and the drop-off before stop b
+  // (after the pickup when a == b)
+  int last = -1;                     // -1 start vertex, 0..L-1 planned stop, L pickup, L+1 drop-off
+  for (int pos = 0; pos < p.L + 2; ++pos) {
+    // which element comes next?
+    int kind;                        // 0 planned stop, 1 new pickup, 2 new drop-off
+    int k = 0;
+    {
+      // elements before planned stop index x: x planned + (x > a or (x == a ... )) handled by counting
+      // position layout: [stops 0..a-1] P [stops a..b-1] D [stops b..L-1]
+      if (pos < a) { kind = 0; k = pos; }
+      else if (pos == a) { kind = 1; }
+      else if (pos <= b) { kind = 0; k = pos - 1; }
+      else if (pos == b + 1) { kind = 2; }
+      else { kind = 0; k = pos - 2; }
+    }
+    double dt;
+    int pod, rq;
+    if (kind == 0) {
+      if (last == p.L) dt = p.from_o[k];
+      else if (last == p.L + 1) dt = p.from_d[k];
+      else dt = p.seg[k];            // previous element is stop k-1 (or the start): the plan's own segment
+      pod = p.pod[k]; rq = p.req[k];
+    } else if (kind == 1) {
+      dt = p.to_o[a];
+      pod = 1; rq = p.new_req;
+    } else {
+      dt = (last == p.L) ? p.od : p.to_d[b];
+      pod = -1; rq = p.new_req;
+    }
+    t += dt;
+    if (pod == 1) {
+      const double cep = pv.q_cep[rq];
+      double cld;
+      if (T + t < cep) {             // early: wait until Cep (:1547-1550)
+        dt += cep - T - t;
+        t += cep - T - t;
+        cld = cep + pv.prm.max_detour * pv.q_ts[rq];
+      } else if (T + t > pv.q_clp[rq]) {
+        return 2;                    // late pickup (:1551-1552)
+      } else {
+        cld = T + t + pv.prm.max_detour * pv.q_ts[rq];
+      }
+      if (kind == 1) cld_new = cld; else cld_local[k] = cld;
+    } else if (pod == -1) {
+      double cld;
+      if (kind == 2) cld = cld_new;
+      else {
+        // drop-off of a planned request: Cld set by its pickup earlier in this walk, else the stored value
+        cld = pv.q_cld[rq];
+        for (int m = 0; m < k; ++m)
+          if (p.req[m] == rq && p.pod[m] == 1) cld = cld_local[m];
+      }
+      if (T + t > cld) return 3;     // late drop-off (:1555-1556)
+    }
+    c += n * dt * pv.prm.coef_inveh;
+    n += pod;
+    if (pod == 1) {
+      const double pwt = pv.q_pwt[rq];
+      if (pwt > 0) c += (T + t - pv.q_tr[rq] - pwt) * pv.prm.coef_extra_wait;
+      else c += t * pv.prm.coef_wait;
+    }
+    if (c > C) return 0;             // over the incumbent bound (:1568-1569)
+    last = (kind == 0) ? k : (kind == 1 ? p.L : p.L + 1);
+  }
+  *c_out = c;
+  return -1;
+}
+
+__global__ void insertion_scan_kernel(PlanView pv, DistView dv, int n_new, const int32_t* new_rows, double* cmin_out,
+                                      unsigned long long* n_cand) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)pv.n_veh * n_new;
+  unsigned long long evaluated = 0;
+  if (idx < total) {
+    const int v = (int)(idx / n_new), r = (int)(idx % n_new);
+    Pair p;
+    load_pair(p, pv, dv, v, new_rows[r]);
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    double cmin = inf;
+    for (int a = 0; a <= p.L; ++a)
+      for (int b = a; b <= p.L; ++b) {
+        double c;
+        if (eval_candidate(p, pv, a, b, inf, &c) < 0 && c < cmin) cmin = c;
+        ++evaluated;
+      }
+    cmin_out[idx] = cmin;
+  }
+  for (int off = 16; off > 0; off >>= 1) evaluated += __shfl_down_sync(0xffffffffu, evaluated, off);
+  if ((threadIdx.x & 31) == 0 && evaluated) atomicAdd(n_cand, evaluated);
+}
+
+__global__ void insertion_fold_kernel(PlanView pv, DistView dv, int n_new, const int32_t* new_rows, const double* cmin,
+                                      int32_t* best_veh, int32_t* best_i, int32_t* best_j, double* best_dc) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_new) return;
+  const double inf = __longlong_as_double(0x7ff0000000000000LL);
+  double dc = inf;                   // dc_ = np.inf (:1452)
+  int wv = -1, wi = -1, wj = -1;
+  for (int v = 0; v < pv.n_veh; ++v) {
+    const double c0 = pv.cost[v];
+    const double cm = cmin[(int64_t)v * n_new + r];
+    if (cm == inf || cm > c0 + dc) continue;   // no candidate of this vehicle can pass `c > C`
+    Pair p;
+    load_pair(p, pv, dv, v, new_rows[r]);
+    int viol = -1;
+    for (int i = 0; i <= p.L; ++i) {                         // (:1466-1482)
+      for (int j = i + 1; j <= p.L + 1; ++j) {
+        double c;
+        viol = eval_candidate(p, pv, i, j - 1, c0 + dc, &c);
+        if (viol < 0) { dc = c - c0; wv = v; wi = i; wj = j; }
+        if (viol > 0) break;
+      }
+      if (viol == 2) break;
+    }
+  }
+  best_veh[r] = wv; best_i[r] = wi; best_j[r] = wj; best_dc[r] = dc;
+}
+
+}  // namespace
+
+struct LegacyDev {
+  int n_veh = 0, n_stops = 0, n_rows = 0;
+  int32_t *node = nullptr, *onboard = nullptr, *cap = nullptr, *off = nullptr, *s_node = nullptr, *s_req = nullptr;
+  double *delay = nullptr, *clock = nullptr, *cost = nullptr;
+  int8_t* s_pod = nullptr;
+  int32_t *q_o = nullptr, *q_d = nullptr;
+  double *q_cep = nullptr, *q_clp = nullptr, *q_cld = nullptr, *q_ts = nullptr, *q_tr = nullptr, *q_pwt = nullptr;
+  drs_insertion_params prm{1.5, 1.0, 1.5, 3.0};
+};
+
+void drs_tick_free_plans(drs_tick* t) {
+  LegacyDev* d = t->legacy;
+  if (!d) return;
+  void* ptrs[] = {d->node, d->onboard, d->cap, d->off, d->s_node, d->s_req, d->delay, d->clock, d->cost, d->s_pod,
+                  d->q_o, d->q_d, d->q_cep, d->q_clp, d->q_cld, d->q_ts, d->q_tr, d->q_pwt};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  delete d;
+  t->legacy = nullptr;
+}
+
+extern "C" int drs_tick_set_plans(drs_tick* t, const drs_plan_batch* b, const drs_request_table* q,
+                                  const drs_insertion_params* prm) {
+  DRS_REQUIRE(t && b && q, DRS_ERR_ARG, "drs_tick_set_plans: null argument");
+  const int nv = b->n_veh, nq = q->n_rows;
+  DRS_REQUIRE(nv >= 0 && nq >= 0, DRS_ERR_ARG, "drs_tick_set_plans: negative size");
+  DRS_REQUIRE(nv == 0 || (b->start_node && b->start_delay && b->onboard && b->clock && b->capacity && b->cost && b->stop_off),
+              DRS_ERR_ARG, "drs_tick_set_plans: null vehicle array");
+  DRS_REQUIRE(nq == 0 || (q->o_node && q->d_node && q->Cep && q->Clp && q->Cld && q->Ts && q->Tr && q->pwt), DRS_ERR_ARG,
+              "drs_tick_set_plans: null request-table array");
+  const int n = t->g->n;
+  const int nstops = nv ? b->stop_off[nv] : 0;
+  for (int v = 0; v < nv; ++v) {
+    DRS_REQUIRE(b->start_node[v] >= 0 && b->start_node[v] < n, DRS_ERR_RANGE, "drs_tick_set_plans: vehicle %d node out of range", v);
+    const int cnt = b->stop_off[v + 1] - b->stop_off[v];
+    DRS_REQUIRE(cnt >= 0 && cnt <= MAXL, DRS_ERR_ARG, "drs_tick_set_plans: vehicle %d has %d planned stops (max %d)", v, cnt, MAXL);
+    for (int s = b->stop_off[v]; s < b->stop_off[v + 1]; ++s) {
+      DRS_REQUIRE(b->stop_node[s] >= 0 && b->stop_node[s] < n, DRS_ERR_RANGE, "drs_tick_set_plans: stop %d node out of range", s);
+      DRS_REQUIRE(b->stop_req[s] >= 0 && b->stop_req[s] < nq, DRS_ERR_RANGE, "drs_tick_set_plans: stop %d request row out of range", s);
+    }
+  }
+  for (int r = 0; r < nq; ++r)
+    DRS_REQUIRE(q->o_node[r] >= 0 && q->o_node[r] < n && q->d_node[r] >= 0 && q->d_node[r] < n, DRS_ERR_RANGE,
+                "drs_tick_set_plans: request row %d node out of range", r);
+  DrsDeviceGuard guard(t->g->device);
+  cudaStream_t st = t->g->stream;
+  if (!t->legacy) t->legacy = new LegacyDev();
+  LegacyDev& d = *t->legacy;
+  int rc;
+  if ((rc = drs_upload(&d.node, b->start_node, nv, st)) || (rc = drs_upload(&d.delay, b->start_delay, nv, st)) ||
+      (rc = drs_upload(&d.onboard, b->onboard, nv, st)) || (rc = drs_upload(&d.clock, b->clock, nv, st)) ||
+      (rc = drs_upload(&d.cap, b->capacity, nv, st)) || (rc = drs_upload(&d.cost, b->cost, nv, st)) ||
+      (rc = drs_upload(&d.off, b->stop_off, nv ? nv + 1 : 0, st)) || (rc = drs_upload(&d.s_node, b->stop_node, nstops, st)) ||
+      (rc = drs_upload(&d.s_req, b->stop_req, nstops, st)) || (rc = drs_upload(&d.s_pod, b->stop_pod, nstops, st)) ||
+      (rc = drs_upload(&d.q_o, q->o_node, nq, st)) || (rc = drs_upload(&d.q_d, q->d_node, nq, st)) ||
+      (rc = drs_upload(&d.q_cep, q->Cep, nq, st)) || (rc = drs_upload(&d.q_clp, q->Clp, nq, st)) ||
+      (rc = drs_upload(&d.q_cld, q->Cld, nq, st)) || (rc = drs_upload(&d.q_ts, q->Ts, nq, st)) ||
+      (rc = drs_upload(&d.q_tr, q->Tr, nq, st)) || (rc = drs_upload(&d.q_pwt, q->pwt, nq, st)))
+    return rc;
+  DRS_CUDA(cudaStreamSynchronize(st));
+  d.n_veh = nv; d.n_stops = nstops; d.n_rows = nq;
+  if (prm) d.prm = *prm;
+  return DRS_OK;
+}
+
+extern "C" int drs_tick_insertion_eval(drs_tick* t, int32_t n_new, const int32_t* new_rows, int32_t* best_veh,
+                                       int32_t* best_i, int32_t* best_j, double* best_dc, int64_t* n_candidates) {
+  DRS_REQUIRE(t && t->legacy, DRS_ERR_STATE, "drs_tick_insertion_eval: call drs_tick_set_plans first");
+  DRS_REQUIRE(t->g->apsp_valid, DRS_ERR_STATE, "drs_tick_insertion_eval: travel-time matrix not built (or invalidated)");
+  DRS_REQUIRE(n_new >= 0 && (n_new == 0 || (new_rows && best_veh && best_i && best_j && best_dc)), DRS_ERR_ARG,
+              "drs_tick_insertion_eval: bad argument");
+  if (n_candidates) *n_candidates = 0;
+  if (n_new == 0) return DRS_OK;
+  LegacyDev& d = *t->legacy;
+  for (int r = 0; r < n_new; ++r)
+    DRS_REQUIRE(new_rows[r] >= 0 && new_rows[r] < d.n_rows, DRS_ERR_RANGE, "drs_tick_insertion_eval: request row %d out of range",
+                new_rows[r]);
+  const int64_t total = (int64_t)d.n_veh * n_new;
+  DRS_REQUIRE(total < ((int64_t)1 << 31), DRS_ERR_ARG, "drs_tick_insertion_eval: %lld pairs exceed 2^31", (long long)total);
+  DrsDeviceGuard guard(t->g->device);
+  cudaStream_t st = t->g->stream;
+  PlanView pv{d.n_veh, d.node, d.onboard, d.cap, d.off, d.s_node, d.s_req, d.delay, d.clock, d.cost, d.s_pod,
+              d.q_o, d.q_d, d.q_cep, d.q_clp, d.q_cld, d.q_ts, d.q_tr, d.q_pwt, d.prm};
+  DistView dv{t->g->d_dist, t->g->ld, t->g->mode};
+  int32_t *d_rows = nullptr, *d_bv = nullptr, *d_bi = nullptr, *d_bj = nullptr;
+  double *d_cmin = nullptr, *d_dc = nullptr;
+  unsigned long long* d_ncand = nullptr;
+  auto cleanup = [&]() { cudaFree(d_rows); cudaFree(d_bv); cudaFree(d_bi); cudaFree(d_bj); cudaFree(d_cmin); cudaFree(d_dc); cudaFree(d_ncand); };
+  int rc = drs_upload(&d_rows, new_rows, n_new, st);
+  if (rc) { cleanup(); return rc; }
+  if (cudaMalloc((void**)&d_bv, sizeof(int32_t) * n_new) != cudaSuccess || cudaMalloc((void**)&d_bi, sizeof(int32_t) * n_new) != cudaSuccess ||
+      cudaMalloc((void**)&d_bj, sizeof(int32_t) * n_new) != cudaSuccess || cudaMalloc((void**)&d_dc, sizeof(double) * n_new) != cudaSuccess ||
+      cudaMalloc((void**)&d_cmin, sizeof(double) * std::max<int64_t>(total, 1)) != cudaSuccess ||
+      cudaMalloc((void**)&d_ncand, sizeof(unsigned long long)) != cudaSuccess) {
+    cleanup();
+    drs_set_error("drs_tick_insertion_eval: cudaMalloc failed");
+    return DRS_ERR_NOMEM;
+  }
+  cudaMemsetAsync(d_ncand, 0, sizeof(unsigned long long), st);
+  if (total > 0) {
+    insertion_scan_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(pv, dv, n_new, d_rows, d_cmin, d_ncand);
+    drs_count_launch();
+  }
+  insertion_fold_kernel<<<(n_new + 63) / 64, 64, 0, st>>>(pv, dv, n_new, d_rows, d_cmin, d_bv, d_bi, d_bj, d_dc);
+  drs_count_launch();
+  unsigned long long ncand = 0;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(best_veh, d_bv, sizeof(int32_t) * n_new, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(best_i, d_bi, sizeof(int32_t) * n_new, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(best_j, d_bj, sizeof(int32_t) * n_new, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(best_dc, d_dc, sizeof(double) * n_new, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&ncand, d_ncand, sizeof(ncand), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cleanup();
+  if (e != cudaSuccess) {
+    drs_set_error("drs_tick_insertion_eval: %s", cudaGetErrorString(e));
+    return DRS_ERR_CUDA;
+  }
+  if (n_candidates) *n_candidates = (int64_t)ncand;
+  return DRS_OK;
+}

@@ -474,3 +474,154 @@ def solve_set_packing(nveh, nreq, trips, costs):
     chosen = [k for k in range(nt) if x[k] > 0]
     ignored = [r for r in range(nreq) if x[nt + r] > 0]
     return chosen, ignored, float(res.fun)
+
+
+# ---------------------------------------------------------------------------------------------
+# Legacy insertion heuristic (lib/Agents.py:1429-1572)
+# ---------------------------------------------------------------------------------------------
+MAX_DETOUR = 1.5           # lib/Constants.py:144
+COEF_INVEH = 1.0           # lib/Constants.py:163-165
+COEF_WAIT = 1.5
+COEF_EXTRA_WAIT = 3.0
+
+
+class InsertionTick(object):
+    """Array-level front end of drs_tick_set_plans / drs_tick_insertion_eval.
+
+    vehs: list of dicts {node, t0, n, T, K, c, route: [(request row, pod, node)]};
+    table: dict of request-table columns o, d, Cep, Clp, Cld, Ts, Tr, pwt (numpy arrays)."""
+
+    def __init__(self, G, vehs, table, params=None):
+        if not isinstance(G, RoadGraph):
+            raise TypeError("G must be the RoadGraph proxy (router.G)")
+        self.lib = _lib.load()
+        self.G = G
+        nv = len(vehs)
+        off = np.zeros(nv + 1, dtype=np.int32)
+        for v, veh in enumerate(vehs):
+            off[v + 1] = off[v] + len(veh["route"])
+        self._a = dict(
+            node=np.array([v["node"] for v in vehs], dtype=np.int32),
+            delay=np.array([v["t0"] for v in vehs], dtype=np.float64),
+            onboard=np.array([v["n"] for v in vehs], dtype=np.int32),
+            clock=np.array([v["T"] for v in vehs], dtype=np.float64),
+            cap=np.array([v["K"] for v in vehs], dtype=np.int32),
+            cost=np.array([v["c"] for v in vehs], dtype=np.float64),
+            off=off,
+            s_node=np.array([s[2] for v in vehs for s in v["route"]], dtype=np.int32),
+            s_req=np.array([s[0] for v in vehs for s in v["route"]], dtype=np.int32),
+            s_pod=np.array([s[1] for v in vehs for s in v["route"]], dtype=np.int8))
+        self._t = {k: (_lib.as_i32(table[k]) if k in ("o", "d") else _lib.as_f64(table[k]))
+                   for k in ("o", "d", "Cep", "Clp", "Cld", "Ts", "Tr", "pwt")}
+        a, t = self._a, self._t
+        pb = _lib.PlanBatch(nv, _lib.ptr_i32(a["node"]), _lib.ptr_f64(a["delay"]), _lib.ptr_i32(a["onboard"]),
+                            _lib.ptr_f64(a["clock"]), _lib.ptr_i32(a["cap"]), _lib.ptr_f64(a["cost"]),
+                            _lib.ptr_i32(a["off"]), _lib.ptr_i32(a["s_node"]), _lib.ptr_i32(a["s_req"]),
+                            a["s_pod"].ctypes.data_as(_i8p))
+        rt = _lib.RequestTable(len(t["o"]), _lib.ptr_i32(t["o"]), _lib.ptr_i32(t["d"]), _lib.ptr_f64(t["Cep"]),
+                               _lib.ptr_f64(t["Clp"]), _lib.ptr_f64(t["Cld"]), _lib.ptr_f64(t["Ts"]),
+                               _lib.ptr_f64(t["Tr"]), _lib.ptr_f64(t["pwt"]))
+        p = params or {}
+        prm = _lib.InsertionParams(p.get("max_detour", MAX_DETOUR), p.get("coef_inveh", COEF_INVEH),
+                                   p.get("coef_wait", COEF_WAIT), p.get("coef_extra_wait", COEF_EXTRA_WAIT))
+        self.handle = C.c_void_p()
+        _lib.check(self.lib.drs_tick_create(G.handle, C.byref(self.handle)), self.lib)
+        _lib.check(self.lib.drs_tick_set_plans(self.handle, C.byref(pb), C.byref(rt), C.byref(prm)), self.lib)
+
+    def evaluate(self, new_rows):
+        """Returns (best_veh, best_i, best_j, best_dc, n_candidates) for the new-request rows."""
+        rows = _lib.as_i32(new_rows)
+        n = len(rows)
+        bv, bi, bj = (np.empty(n, dtype=np.int32) for _ in range(3))
+        dc = np.empty(n, dtype=np.float64)
+        nc = C.c_int64(0)
+        _lib.check(self.lib.drs_tick_insertion_eval(self.handle, n, _lib.ptr_i32(rows), _lib.ptr_i32(bv), _lib.ptr_i32(bi),
+                                                    _lib.ptr_i32(bj), _lib.ptr_f64(dc), C.byref(nc)), self.lib)
+        return bv, bi, bj, dc, nc.value
+
+    def close(self):
+        if self.handle:
+            self.lib.drs_tick_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class InsertionHeuristics(object):
+    """Object-level drop-in for ``Model.insertion_heuristics`` / ``insert_heuristics``
+    (lib/Agents.py:1429-1490): holds ``vehs`` / ``reqs`` / ``queue`` / ``rejs`` like the legacy Model
+    and assigns each queued request to the vehicle and (pickup, drop-off) slots the reference's
+    scan would pick.  Vehicles are read through the reference's attribute surface (idle, route legs
+    with rid/pod/tlng/tlat, c, n, T, K, lng, lat); requests through id, olng, olat, dlng, dlat, Cep,
+    Clp, Cld, Ts, Tr, pwt."""
+
+    def __init__(self, vehs, reqs, params=None):
+        from collections import deque
+        self.vehs, self.reqs = vehs, reqs
+        self.queue = deque()
+        self.rejs = []
+        self.params = params
+
+    def _marshal(self, router, extra_req):
+        G = router.G
+        rows, table = {}, {k: [] for k in ("o", "d", "Cep", "Clp", "Cld", "Ts", "Tr", "pwt")}
+
+        def row_of(rq):
+            if rq.id not in rows:
+                rows[rq.id] = len(table["o"])
+                table["o"].append(G.node_of_location(rq.olng, rq.olat))
+                table["d"].append(G.node_of_location(rq.dlng, rq.dlat))
+                for k in ("Cep", "Clp", "Cld", "Ts", "Tr", "pwt"):
+                    table[k].append(float(getattr(rq, k)))
+            return rows[rq.id]
+        vehs = []
+        for veh in self.vehs:
+            try:                                               # lib/Agents.py:1508-1516
+                node = G.node_index(str((veh.lng, veh.lat)))
+                t0 = 0.0
+            except ValueError:
+                assert len(veh.route) > 0
+                geo = veh.route[0].steps[0].geo[1]
+                node = G.node_of_location(geo[0], geo[1])
+                t0 = float(veh.route[0].steps[0].t)
+            route = []
+            if not veh.idle:                                   # lib/Agents.py:1458-1461
+                for leg in veh.route:
+                    route.append((row_of(self.reqs[leg.rid]), int(leg.pod), G.node_of_location(leg.tlng, leg.tlat)))
+            vehs.append({"node": node, "t0": t0, "n": int(veh.n), "T": float(veh.T), "K": int(veh.K), "c": float(veh.c),
+                         "route": route})
+        new_row = row_of(extra_req)
+        return vehs, {k: np.asarray(v) for k, v in table.items()}, new_row
+
+    def insert_heuristics(self, router, req, T):
+        """lib/Agents.py:1451-1490.  Returns True when the request was assigned."""
+        vehs, table, new_row = self._marshal(router, req)
+        tick = InsertionTick(router.G, vehs, table, self.params)
+        try:
+            bv, bi, bj, dc, _ = tick.evaluate([new_row])
+        finally:
+            tick.close()
+        if bv[0] < 0:
+            return False
+        veh = self.vehs[int(bv[0])]
+        route = []
+        if not veh.idle:
+            route = [(leg.rid, leg.pod, leg.tlng, leg.tlat) for leg in veh.route]
+        route.insert(int(bi[0]), (req.id, 1, req.olng, req.olat))
+        route.insert(int(bj[0]), (req.id, -1, req.dlng, req.dlat))
+        self.last_choice = (veh, route, float(dc[0]))
+        if hasattr(veh, "build_route"):
+            veh.build_route(router, route, self.reqs, T, None)
+        return True
+
+    def insertion_heuristics(self, router, T):
+        """lib/Agents.py:1429-1448 (DISTANCE_THRESHOLD = 0, lib/Constants.py:81)."""
+        for _ in range(len(self.queue)):
+            req = self.queue.popleft()
+            if not self.insert_heuristics(router, req, T):
+                self.rejs.append(req)
+            req.assigned = True

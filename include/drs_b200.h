@@ -232,6 +232,73 @@ int drs_tick_trip_eval(drs_tick* t, double T, int32_t flags, int32_t n_tasks, co
                        const int32_t* task_nreq, const int32_t* task_req, double* cost_host,
                        uint8_t* order_host, int32_t* n_stops_host);
 
+/* ------------------------------------------------------ legacy insertion --
+ * The (vehicle, pickup slot, drop-off slot) insertion heuristic: replaces
+ * Model.insert_heuristics / test_constraints_get_cost (lib/Agents.py:1451-1572;
+ * dead code at the reference's HEAD, semantics in SURVEY.md section 3.4).  For each
+ * new request the vehicles are scanned in order, the request's pickup is tried
+ * after `i` planned stops and its drop-off after `j-1`, and the LAST candidate
+ * whose running cost never exceeds the incumbent bound wins (lib/Agents.py:1470-1476),
+ * with the violation-code loop breaks of lib/Agents.py:1479-1482.
+ *
+ * The request table holds every request referenced by a plan plus the new ones;
+ * plan stops and new requests point into it by row.
+ */
+typedef struct {
+  int32_t n_veh;
+  const int32_t* start_node;   /* vehicle position if it is a vertex, else next downstream vertex */
+  const double* start_delay;   /* 0, or the remaining time of the current step (lib/Agents.py:1508-1516) */
+  const int32_t* onboard;      /* veh.n */
+  const double* clock;         /* veh.T */
+  const int32_t* capacity;     /* veh.K */
+  const double* cost;          /* veh.c */
+  const int32_t* stop_off;     /* n_veh + 1 */
+  const int32_t* stop_node;    /* plan stops in route order (leg.tlng, leg.tlat) */
+  const int32_t* stop_req;     /* row of the request table */
+  const int8_t* stop_pod;
+} drs_plan_batch;
+
+typedef struct {
+  int32_t n_rows;
+  const int32_t* o_node;
+  const int32_t* d_node;
+  const double* Cep;
+  const double* Clp;
+  const double* Cld;  /* current value; only read for on-board requests */
+  const double* Ts;
+  const double* Tr;
+  const double* pwt;
+} drs_request_table;
+
+typedef struct {
+  double max_detour;      /* lib/Constants.py:144 MAX_DETOUR = 1.5 */
+  double coef_inveh;      /* lib/Constants.py:163 */
+  double coef_wait;       /* lib/Constants.py:164 */
+  double coef_extra_wait; /* lib/Constants.py:165 */
+} drs_insertion_params;
+
+int drs_tick_set_plans(drs_tick* t, const drs_plan_batch* plans, const drs_request_table* table,
+                       const drs_insertion_params* params);
+/* Evaluates every (vehicle, i, j) candidate for each new request (rows into the
+ * request table) and folds them in the reference's scan order.  Outputs (host,
+ * one per new request): winning vehicle index (-1: rejected), i, j (as in
+ * lib/Agents.py:1466-1469) and the cost increase dc.  *n_candidates = number of
+ * (vehicle, i, j) triples evaluated. */
+int drs_tick_insertion_eval(drs_tick* t, int32_t n_new, const int32_t* new_rows_host, int32_t* best_veh,
+                            int32_t* best_i, int32_t* best_j, double* best_dc, int64_t* n_candidates);
+
+/* ---------------------------------------------------------- instrumentation --
+ * The CUDA stream (cudaStream_t as void*) every call on this graph launches on:
+ * lets the host time kernels with events on the launching stream. */
+int drs_graph_stream(const drs_graph* g, void** stream);
+/* Number of kernels this library has launched in this process so far. */
+int64_t drs_launch_count(void);
+/* Device time of the last drs_apsp_build by phase, from CUDA events on the
+ * graph's stream: ms[0] init (fill + edge scatter), ms[1] phase 1 + row part of
+ * phase 2 (all rounds), ms[2] column part of phase 2 + phase 3 (all rounds),
+ * ms[3] predecessor pass; *rounds = number of pivot blocks. */
+int drs_apsp_last_profile(const drs_graph* g, double* ms, int32_t* rounds);
+
 /* ------------------------------------------------------------- ALU peak ---
  * Register-resident add+min stream used as the ALU roofline denominator
  * (SURVEY.md section 8d).  Returns relaxations per second of the fp32

@@ -1,0 +1,103 @@
+"""CUDA (vehicle, pickup slot, drop-off slot) insertion evaluation against the oracle's restatement
+of Model.insert_heuristics / test_constraints_get_cost (lib/Agents.py:1451-1572)."""
+import copy
+
+import numpy as np
+import pytest
+
+from conftest import golden_map_path, oracle_graph
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_reqs(tab):
+    return {r: {"o_node": int(tab["o"][r]), "d_node": int(tab["d"][r]), "Cep": float(tab["Cep"][r]),
+                "Clp": float(tab["Clp"][r]), "Cld": float(tab["Cld"][r]), "Ts": float(tab["Ts"][r]),
+                "Tr": float(tab["Tr"][r]), "pwt": float(tab["pwt"][r])} for r in range(len(tab["o"]))}
+
+
+def _run_case(name, n_veh, n_new, seed, capacity, plan_stops, tweak=None):
+    from drs_abm_b200 import synth
+    from drs_abm_b200.dispatch import InsertionTick
+    from drs_abm_b200.gml import read_gml
+    from drs_abm_b200.routing import RoadGraph
+    from oracle import dispatch_oracle as D
+    data = read_gml(golden_map_path(name))
+    G = RoadGraph(data)
+    dist = G.dist_rows(0, G.n)
+    assert np.array_equal(dist, oracle_graph(name).dist_matrix())
+    tt = lambda a, b: float(dist[a, b])
+    sc = synth.fleet_scenario(data, n_veh, n_new, 600.0, seed, lambda s, t: dist[s, t], plan_stops=plan_stops,
+                              capacity=capacity, radius=4)
+    if tweak:
+        tweak(sc)
+    tick = InsertionTick(G, sc["vehs"], dict(sc["table"], Cld=sc["table"]["Cld"]))
+    bv, bi, bj, dc, ncand = tick.evaluate(sc["new_rows"])
+    tick.close()
+    assert ncand == sum((len(v["route"]) + 1) * (len(v["route"]) + 2) // 2 for v in sc["vehs"]) * n_new
+    ovehs = [{"vid": k, "n": v["n"], "T": v["T"], "K": v["K"], "c": v["c"], "node": v["node"], "t0": v["t0"],
+              "route": list(v["route"])} for k, v in enumerate(sc["vehs"])]
+    assigned = 0
+    for k, row in enumerate(sc["new_rows"]):
+        reqs = _oracle_reqs(sc["table"])                       # fresh snapshot: the scan mutates Cld
+        vid, route, odc, _ = D.legacy_insert_heuristics(tt, ovehs, reqs, int(row))
+        if vid is None:
+            assert bv[k] == -1 and np.isinf(dc[k])
+            continue
+        assigned += 1
+        i = [x for x, s in enumerate(route) if s[0] == row and s[1] == 1][0]
+        j = [x for x, s in enumerate(route) if s[0] == row and s[1] == -1][0]
+        assert (int(bv[k]), int(bi[k]), int(bj[k])) == (vid, i, j)
+        assert dc[k] == odc                                    # bit-exact (integer-weighted map, fp64 both sides)
+    G.close()
+    return assigned
+
+
+def test_insertion_matches_oracle_mixed_plans():
+    assert _run_case("g20_int", 60, 40, 4, 4, (0, 2, 4, 6, 8)) >= 20
+
+
+def test_insertion_matches_oracle_tight_capacity_and_idle_fleet():
+    _run_case("g20_int", 40, 30, 5, 2, (0, 2, 4))
+    assert _run_case("g8_int", 12, 25, 6, 1, (0,)) >= 10        # idle vehicles only: one candidate each
+
+
+def test_insertion_ties_last_wins_and_rejection():
+    """Identical vehicles give identical costs: the reference keeps the LAST equal-or-better candidate
+    (lib/Agents.py:1471-1476).  Requests nobody can reach in time are rejected."""
+    def clones(sc):
+        v0 = sc["vehs"][0]
+        for v in sc["vehs"][1:]:
+            v.update(node=v0["node"], route=list(v0["route"]), n=v0["n"], c=v0["c"])
+        sc["table"]["Clp"][sc["new_rows"][:5]] = sc["table"]["Cep"][sc["new_rows"][:5]] - 1e4   # unreachable windows
+    _run_case("g20_int", 8, 20, 7, 4, (2,), tweak=clones)
+
+
+def test_insertion_object_front_end():
+    """InsertionHeuristics over Veh / Req-like objects (reference attribute surface)."""
+    from drs_abm_b200.dispatch import InsertionHeuristics
+    from drs_abm_b200.routing import RoutingEngine
+    router = RoutingEngine(graph_loc=golden_map_path("g8_int"), cst_speed=9, seed=1)
+    G = router.G
+
+    class R(object):
+        pass
+
+    class V(object):
+        pass
+    a, b, c = G.vs[0], G.vs[G.n - 1], G.vs[9]
+    req = R()
+    req.id, req.olng, req.olat, req.dlng, req.dlat = 0, a["lng"], a["lat"], b["lng"], b["lat"]
+    req.Ts = router.get_duration(a["lng"], a["lat"], b["lng"], b["lat"])
+    req.Tr = req.Cep = 0.0; req.Clp = 600.0; req.Cld = 600.0 + 1.5 * req.Ts; req.pwt = 0.0; req.assigned = False
+    near, far = V(), V()
+    for v, node, vid in ((far, b, 0), (near, c, 1)):
+        v.id, v.idle, v.route, v.c, v.n, v.T, v.K, v.lng, v.lat = vid, True, [], 0.0, 0, 0.0, 4, node["lng"], node["lat"]
+    ins = InsertionHeuristics([far, near], [req])
+    ins.queue.append(req)
+    ins.insertion_heuristics(router, 0)
+    veh, route, dc = ins.last_choice
+    assert veh is near and [(s[0], s[1]) for s in route] == [(0, 1), (0, -1)] and req.assigned and not ins.rejs
+    t_pick = router.get_duration(c["lng"], c["lat"], a["lng"], a["lat"])
+    # empty until the pickup (n * dt = 0), wait term t * COEF_WAIT at the pickup, then one rider for Ts seconds
+    assert dc == t_pick * 1.5 + req.Ts * 1.0
