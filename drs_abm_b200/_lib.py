@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libdrs_b200.so")
 MODE_F32 = 0
 MODE_I32 = 1
 FW_TILE = 128
+APSP_FW, APSP_SSSP, APSP_AUTO = 0, 1, 2
 I32_INF = 0x3FFFFFFF
 
 ERR_ARG, ERR_CUDA, ERR_STATE, ERR_NOMEM, ERR_RANGE, ERR_CAPACITY = -1, -2, -3, -4, -5, -6
@@ -90,7 +91,12 @@ SIGNATURES = {
     "drs_path": (C.c_int, [_vp, C.c_int32, C.c_int32, _i32p, _i32p, _i32p]),
     "drs_alu_peak": (C.c_int, [C.c_int32, C.c_int32, _f64p]),
     "drs_graph_stream": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "drs_apsp_set_algorithm": (C.c_int, [_vp, C.c_int32]),
+    "drs_sssp_batch_dev": (C.c_int, [_vp, C.c_int32, C.c_int32, _i32p, _vp, C.c_int64, C.c_double, _vp]),
+    "drs_sssp_batch": (C.c_int, [_vp, C.c_int32, C.c_int32, _i32p, _f64p]),
+    "drs_apsp_rows_sssp": (C.c_int, [_vp, C.c_int32, _vp, C.c_int64, C.c_int32, C.c_int32, C.c_double, _vp]),
     "drs_launch_count": (C.c_int64, []),
+    "drs_tick_last_ms": (C.c_int, [_vp, _f64p]),
     "drs_apsp_last_profile": (C.c_int, [_vp, _f64p, _i32p]),
     "drs_tick_create": (C.c_int, [_vp, C.POINTER(_vp)]),
     "drs_tick_destroy": (C.c_int, [_vp]),

@@ -78,6 +78,10 @@ class CudaTiles(object):
                                           C.c_void_p(panel.data_ptr()), kb, skip_local, blo, bhi, self._stream()),
                    self.lib)
 
+    def sssp_rows(self, local, row0):
+        _lib.check(self.lib.drs_apsp_rows_sssp(self.g, self.mode, C.c_void_p(local.data_ptr()), local.shape[1], row0,
+                                               local.shape[0], 0.0, self._stream()), self.lib)
+
     def pred(self, local, row0, out):
         _lib.check(self.lib.drs_pred_build(self.g, self.mode, C.c_void_p(local.data_ptr()), local.shape[1], row0,
                                            local.shape[0], C.c_void_p(out.data_ptr()), self._stream()), self.lib)
@@ -86,9 +90,13 @@ class CudaTiles(object):
         self.torch.cuda.synchronize()
 
 
-def build_sharded(tiles, npad, rank=0, world=1, dist=None, lookahead=True, with_pred=True):
+def build_sharded(tiles, npad, rank=0, world=1, dist=None, lookahead=True, with_pred=True, algorithm="fw"):
     """Runs the sharded build.  ``tiles`` is a backend (CudaTiles), ``dist`` the
     torch.distributed module (or None when world == 1).
+
+    algorithm "fw": blocked Floyd-Warshall with pivot-panel broadcasts (below).
+    algorithm "sssp": every rank runs the delta-stepping searches of its own source rows;
+    sources are independent, so there is no collective at all.
 
     Returns (local, pred_local, row0): this rank's rows of the distance and
     predecessor matrices and the global index of its first row.
@@ -98,6 +106,14 @@ def build_sharded(tiles, npad, rank=0, world=1, dist=None, lookahead=True, with_
     b0, b1 = starts[rank], starts[rank + 1]
     row0 = b0 * TILE
     local = tiles.empty((b1 - b0) * TILE, npad)
+    if algorithm == "sssp":
+        tiles.sssp_rows(local, row0)
+        pred_local = None
+        if with_pred:
+            pred_local = tiles.empty_pred((b1 - b0) * TILE, npad)
+            tiles.pred(local, row0, pred_local)
+        tiles.synchronize()
+        return local, pred_local, row0
     tiles.init(local, row0)
     bufs = [tiles.empty(TILE, npad), tiles.empty(TILE, npad)] if world > 1 else [None, None]
 

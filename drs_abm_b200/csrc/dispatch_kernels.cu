@@ -391,6 +391,12 @@ extern "C" int drs_tick_set_requests(drs_tick* t, const drs_request_batch* b) {
   return DRS_OK;
 }
 
+extern "C" int drs_tick_last_ms(const drs_tick* t, double* ms) {
+  DRS_REQUIRE(t && ms, DRS_ERR_ARG, "drs_tick_last_ms: null argument");
+  for (int i = 0; i < 4; ++i) ms[i] = t->last_ms[i];
+  return DRS_OK;
+}
+
 static int tick_ready(const drs_tick* t, const char* who) {
   DRS_REQUIRE(t, DRS_ERR_ARG, "%s: null tick", who);
   DRS_REQUIRE(t->g->apsp_valid, DRS_ERR_STATE, "%s: travel-time matrix not built (or invalidated by a weight update)", who);
@@ -424,10 +430,13 @@ extern "C" int drs_tick_rv_eval(drs_tick* t, double T, int32_t flags, int32_t* n
   DRS_CUDA(cudaMemsetAsync(t->d_surv_count, 0, sizeof(int), st));
   DRS_CUDA(cudaMemsetAsync(t->d_counters, 0, 4 * sizeof(unsigned long long), st));
   const int threads = 256;
+  DrsTimer tm_filter(st), tm_eval(st);
+  tm_filter.start();
   rv_filter_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, st>>>(d, dv, T, t->d_status, t->d_surv_veh,
                                                                                     t->d_surv_req, t->d_surv_count);
   drs_count_launch();
   DRS_CUDA(cudaGetLastError());
+  tm_filter.stop();
   int nsurv = 0;
   DRS_CUDA(cudaMemcpyAsync(&nsurv, t->d_surv_count, sizeof(int), cudaMemcpyDeviceToHost, st));
   DRS_CUDA(cudaStreamSynchronize(st));
@@ -436,18 +445,22 @@ extern "C" int drs_tick_rv_eval(drs_tick* t, double T, int32_t flags, int32_t* n
   DRS_CUDA(cudaMalloc((void**)&t->d_cost, sizeof(double) * std::max(nsurv, 1)));
   DRS_CUDA(cudaMalloc((void**)&t->d_order, (size_t)MAXS * std::max(nsurv, 1)));
   DRS_CUDA(cudaMalloc((void**)&t->d_nstops, sizeof(int32_t) * std::max(nsurv, 1)));
+  tm_eval.start();
   if (nsurv > 0) {
     rv_eval_kernel<<<(nsurv + 63) / 64, 64, 0, st>>>(d, dv, T, flags, nsurv, t->d_surv_veh, t->d_surv_req, t->d_status,
                                                      t->d_cost, t->d_order, t->d_nstops);
     drs_count_launch();
   DRS_CUDA(cudaGetLastError());
   }
+  tm_eval.stop();
   count_status_kernel<<<148 * 2, 256, 0, st>>>(t->d_status, total, t->d_counters);
   drs_count_launch();
   DRS_CUDA(cudaGetLastError());
   unsigned long long c[4];
   DRS_CUDA(cudaMemcpyAsync(c, t->d_counters, sizeof(c), cudaMemcpyDeviceToHost, st));
   DRS_CUDA(cudaStreamSynchronize(st));
+  t->last_ms[0] = tm_filter.ms();
+  t->last_ms[1] = tm_eval.ms();
   if (counters_host)
     for (int s = 0; s < 4; ++s) counters_host[s] = (int64_t)c[s];
   if (n_edges) *n_edges = (int32_t)c[DRS_RV_FEASIBLE];

@@ -143,6 +143,7 @@ extern "C" int drs_graph_set_weights(drs_graph* g, const double* tt) {
   DrsDeviceGuard guard(g->device);
   g->h_tt.assign(tt, tt + g->m);
   g->apsp_valid = false;
+  g->sssp_arcs_valid = false;
   return drs_graph_upload_weights(g);
 }
 
@@ -154,6 +155,8 @@ extern "C" int drs_graph_destroy(drs_graph* g) {
                   g->d_out_w, g->d_in_ptr, g->d_in_src, g->d_in_eid, g->d_in_w};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  if (g->sssp_queues) cudaFree(g->sssp_queues);
+  if (g->sssp_arcs) cudaFree(g->sssp_arcs);
   if (g->stream) cudaStreamDestroy(g->stream);
   delete g;
   return DRS_OK;
@@ -198,6 +201,16 @@ extern "C" int drs_apsp_build(drs_graph* g, int32_t mode) {
   for (auto& e : ev) DRS_CUDA(cudaEventCreate(&e));
   auto release = [&]() { for (auto& e : ev) cudaEventDestroy(e); };
   DRS_CUDA(cudaEventRecord(ev[0], st));
+  int algo = g->algorithm;
+  if (algo == DRS_APSP_AUTO) algo = (g->narcs <= 16 * (int64_t)g->n) ? DRS_APSP_SSSP : DRS_APSP_FW;
+  if (algo == DRS_APSP_SSSP) {
+    DRS_CUDA(cudaEventRecord(ev[1], st));
+    if ((rc = drs_apsp_rows_sssp(g, mode, g->d_dist, ld, 0, g->npad, 0.0, st))) { release(); return rc; }
+    for (int kb = 0; kb < nb; ++kb) {   // keep the event layout: everything is booked under "update"
+      DRS_CUDA(cudaEventRecord(ev[2 + 2 * kb], st));
+      DRS_CUDA(cudaEventRecord(ev[3 + 2 * kb], st));
+    }
+  } else {
   if ((rc = drs_fw_init(g, mode, g->d_dist, ld, 0, g->npad, st))) { release(); return rc; }
   DRS_CUDA(cudaEventRecord(ev[1], st));
   for (int kb = 0; kb < nb; ++kb) {
@@ -207,13 +220,15 @@ extern "C" int drs_apsp_build(drs_graph* g, int32_t mode) {
     if ((rc = drs_fw_update(mode, g->d_dist, ld, g->npad, panel, kb, kb, 0, nb, st))) { release(); return rc; }
     DRS_CUDA(cudaEventRecord(ev[3 + 2 * kb], st));
   }
+  }
   if ((rc = drs_pred_build(g, mode, g->d_dist, ld, 0, g->npad, g->d_pred, st))) { release(); return rc; }
   DRS_CUDA(cudaEventRecord(ev[2 + 2 * nb], st));
   DRS_CUDA(cudaStreamSynchronize(st));
   float ms = 0;
   g->prof_ms[0] = g->prof_ms[1] = g->prof_ms[2] = g->prof_ms[3] = 0;
   cudaEventElapsedTime(&ms, ev[0], ev[1]); g->prof_ms[0] = ms;
-  for (int kb = 0; kb < nb; ++kb) {
+  if (algo == DRS_APSP_SSSP) { cudaEventElapsedTime(&ms, ev[1], ev[2]); g->prof_ms[2] = ms; }
+  else for (int kb = 0; kb < nb; ++kb) {
     cudaEventElapsedTime(&ms, ev[1 + 2 * kb], ev[2 + 2 * kb]); g->prof_ms[1] += ms;
     cudaEventElapsedTime(&ms, ev[2 + 2 * kb], ev[3 + 2 * kb]); g->prof_ms[2] += ms;
   }
@@ -221,6 +236,14 @@ extern "C" int drs_apsp_build(drs_graph* g, int32_t mode) {
   g->prof_rounds = nb;
   release();
   g->apsp_valid = true;
+  return DRS_OK;
+}
+
+extern "C" int drs_apsp_set_algorithm(drs_graph* g, int32_t algorithm) {
+  DRS_REQUIRE(g, DRS_ERR_ARG, "drs_apsp_set_algorithm: null graph");
+  DRS_REQUIRE(algorithm == DRS_APSP_FW || algorithm == DRS_APSP_SSSP || algorithm == DRS_APSP_AUTO, DRS_ERR_ARG,
+              "drs_apsp_set_algorithm: unknown algorithm %d", algorithm);
+  g->algorithm = algorithm;
   return DRS_OK;
 }
 

@@ -58,6 +58,7 @@ struct drs_graph {
 
   // resident matrices
   int mode = DRS_MODE_F32;
+  int algorithm = DRS_APSP_FW;
   bool apsp_valid = false;
   bool owns_matrices = false;
   void* d_dist = nullptr;
@@ -65,6 +66,12 @@ struct drs_graph {
   int64_t ld = 0;
 
   cudaStream_t stream = nullptr;
+
+  // persistent SSSP scratch (sssp_kernels.cu): work queues and packed (target, weight) arcs
+  void* sssp_queues = nullptr;
+  size_t sssp_queue_bytes = 0;
+  void* sssp_arcs = nullptr;
+  bool sssp_arcs_valid = false;
 
   double prof_ms[4] = {0, 0, 0, 0};   // last build, by phase (drs_apsp_last_profile)
   int prof_rounds = 0;

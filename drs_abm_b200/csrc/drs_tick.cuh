@@ -44,6 +44,7 @@ struct drs_tick {
   unsigned long long* d_counters = nullptr;
   int64_t surv_capacity = 0;
   LegacyDev* legacy = nullptr;   // plans + request table of the insertion heuristic
+  double last_ms[4] = {0, 0, 0, 0};
 };
 
 
@@ -55,3 +56,14 @@ template <typename T> inline int drs_upload(T** dptr, const T* h, size_t n, cuda
   if (n) DRS_CUDA(cudaMemcpyAsync(*dptr, h, n * sizeof(T), cudaMemcpyHostToDevice, st));
   return DRS_OK;
 }
+
+// CUDA-event stopwatch on one stream
+struct DrsTimer {
+  cudaEvent_t a = nullptr, b = nullptr;
+  cudaStream_t st;
+  explicit DrsTimer(cudaStream_t s) : st(s) { cudaEventCreate(&a); cudaEventCreate(&b); }
+  ~DrsTimer() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+  void start() { cudaEventRecord(a, st); }
+  void stop() { cudaEventRecord(b, st); }
+  double ms() { float m = 0; cudaEventSynchronize(b); cudaEventElapsedTime(&m, a, b); return (double)m; }
+};

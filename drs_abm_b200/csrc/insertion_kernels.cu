@@ -315,12 +315,17 @@ extern "C" int drs_tick_insertion_eval(drs_tick* t, int32_t n_new, const int32_t
     return DRS_ERR_NOMEM;
   }
   cudaMemsetAsync(d_ncand, 0, sizeof(unsigned long long), st);
+  DrsTimer tm_scan(st), tm_fold(st);
+  tm_scan.start();
   if (total > 0) {
     insertion_scan_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(pv, dv, n_new, d_rows, d_cmin, d_ncand);
     drs_count_launch();
   }
+  tm_scan.stop();
+  tm_fold.start();
   insertion_fold_kernel<<<(n_new + 63) / 64, 64, 0, st>>>(pv, dv, n_new, d_rows, d_cmin, d_bv, d_bi, d_bj, d_dc);
   drs_count_launch();
+  tm_fold.stop();
   unsigned long long ncand = 0;
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpyAsync(best_veh, d_bv, sizeof(int32_t) * n_new, cudaMemcpyDeviceToHost, st);
@@ -329,6 +334,7 @@ extern "C" int drs_tick_insertion_eval(drs_tick* t, int32_t n_new, const int32_t
   if (e == cudaSuccess) e = cudaMemcpyAsync(best_dc, d_dc, sizeof(double) * n_new, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(&ncand, d_ncand, sizeof(ncand), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) { t->last_ms[2] = tm_scan.ms(); t->last_ms[3] = tm_fold.ms(); }
   cleanup();
   if (e != cudaSuccess) {
     drs_set_error("drs_tick_insertion_eval: %s", cudaGetErrorString(e));

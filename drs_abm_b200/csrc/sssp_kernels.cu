@@ -1,0 +1,273 @@
+// Batched single-source shortest paths over the device CSR (K2 in SURVEY.md section 2):
+// delta-stepping in its near/far form, one CTA per source, many sources in flight.
+//
+// Serves (a) networks whose N x N matrix does not fit in HBM (BASELINE config C5: rows
+// for a batch of sources only) and (b) the all-pairs build of SPARSE road networks,
+// where N Dijkstra-like searches do ~N*E*c edge relaxations instead of the N^3 of
+// Floyd-Warshall.  It replaces the same igraph Dijkstra calls as the FW path
+// (lib/RoutingEngine.py:87,199,212; lib/optimUtils.py:528,531,659).
+//
+// Per source: the distance row lives directly in the output matrix (global memory,
+// L2-resident while the CTA works on it).  A vertex whose tentative distance improves
+// is appended to the NEAR queue when the new distance is below the current threshold
+// theta, otherwise to the FAR pile; when NEAR drains, theta jumps to the bucket of the
+// smallest valid FAR entry and the pile is split again.  Entries carry the distance they
+// were pushed with, so stale ones (a better distance arrived later) are skipped.
+// Relaxations are atomicMin on the row (non-negative floats order like their bit
+// patterns); arcs are read as one 8-byte (target, weight) record per arc.
+#include <algorithm>
+#include <limits>
+#include <vector>
+
+#include "drs_common.cuh"
+
+namespace {
+
+constexpr int SSSP_THREADS = 256;
+
+template <typename T> struct Dist;
+template <> struct Dist<float> {
+  static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
+  static __device__ __forceinline__ float weight(int bits) { return __int_as_float(bits); }
+  static __device__ __forceinline__ int key(float d) { return __float_as_int(d); }
+  static __device__ __forceinline__ float unkey(int k) { return __int_as_float(k); }
+  static __device__ __forceinline__ float next_theta(float dmin, float delta) { return (floorf(dmin / delta) + 1.0f) * delta; }
+};
+template <> struct Dist<int> {
+  static __device__ __forceinline__ int inf() { return DRS_I32_INF; }
+  static __device__ __forceinline__ int weight(int bits) { return (int)__int_as_float(bits); }
+  static __device__ __forceinline__ int key(int d) { return d; }
+  static __device__ __forceinline__ int unkey(int k) { return k; }
+  static __device__ __forceinline__ int next_theta(int dmin, int delta) { return (dmin / delta + 1) * delta; }
+};
+
+struct Entry { int v; int key; };   // key = distance bits at push time
+
+template <typename T>
+__global__ void __launch_bounds__(SSSP_THREADS) sssp_batch_kernel(
+    int n, const int32_t* __restrict__ out_ptr, const int2* __restrict__ arcs, T* dist, int64_t ld, int64_t row_stride,
+    const int32_t* __restrict__ sources, int nsrc, Entry* queues, int cap, T delta, int* overflow) {
+  __shared__ int s_near, s_next, s_far, s_keep, s_min;
+  Entry* cur = queues + (int64_t)blockIdx.x * 4 * cap;
+  Entry* nxt = cur + cap;
+  Entry* far = nxt + cap;
+  Entry* far2 = far + cap;
+  const int tid = threadIdx.x;
+  for (int k = blockIdx.x; k < nsrc; k += gridDim.x) {
+    const int src = sources[k];
+    T* row = dist + (int64_t)k * row_stride;
+    for (int64_t t = tid; t < ld; t += SSSP_THREADS) row[t] = Dist<T>::inf();
+    __syncthreads();
+    if (tid == 0) {
+      row[src] = (T)0;
+      cur[0] = Entry{src, Dist<T>::key((T)0)};
+      s_near = 1; s_next = 0; s_far = 0;
+    }
+    T theta = delta;
+    __syncthreads();
+    while (true) {
+      // ---- drain the NEAR queue (light phase of the current bucket)
+      while (true) {
+        const int nn = s_near;
+        if (nn == 0) break;
+        for (int e = tid; e < nn; e += SSSP_THREADS) {
+          const Entry en = cur[e];
+          const T du = Dist<T>::unkey(en.key);
+          if (Dist<T>::key(__ldcg(&row[en.v])) != en.key) continue;   // stale: a shorter distance arrived later (L2 read: atomics live there)
+          const int a1 = out_ptr[en.v + 1];
+          for (int a = out_ptr[en.v]; a < a1; ++a) {
+            const int2 arc = arcs[a];
+            const T nd = du + Dist<T>::weight(arc.y);
+            const int nk = Dist<T>::key(nd);
+            const int old = atomicMin(reinterpret_cast<int*>(row) + arc.x, nk);
+            if (nk < old) {
+              if (nd < theta) {
+                const int pos = atomicAdd(&s_next, 1);
+                if (pos < cap) nxt[pos] = Entry{arc.x, nk}; else *overflow = 1;
+              } else {
+                const int pos = atomicAdd(&s_far, 1);
+                if (pos < cap) far[pos] = Entry{arc.x, nk}; else *overflow = 1;
+              }
+            }
+          }
+        }
+        __syncthreads();
+        if (tid == 0) { s_near = min(s_next, cap); s_next = 0; }
+        Entry* tmp = cur; cur = nxt; nxt = tmp;
+        __syncthreads();
+      }
+      // ---- NEAR is empty: advance theta to the bucket of the smallest valid FAR entry
+      const int nf = min(s_far, cap);
+      if (nf == 0) break;
+      if (tid == 0) { s_min = 0x7fffffff; s_keep = 0; }
+      __syncthreads();
+      int lmin = 0x7fffffff;
+      for (int e = tid; e < nf; e += SSSP_THREADS) {
+        const Entry en = far[e];
+        if (Dist<T>::key(__ldcg(&row[en.v])) == en.key) lmin = min(lmin, en.key);
+      }
+      for (int off = 16; off > 0; off >>= 1) lmin = min(lmin, __shfl_down_sync(0xffffffffu, lmin, off));
+      if ((tid & 31) == 0 && lmin != 0x7fffffff) atomicMin(&s_min, lmin);
+      __syncthreads();
+      const int kmin = s_min;
+      if (kmin == 0x7fffffff) break;   // only stale entries left
+      theta = Dist<T>::next_theta(Dist<T>::unkey(kmin), delta);
+      for (int e = tid; e < nf; e += SSSP_THREADS) {
+        const Entry en = far[e];
+        if (Dist<T>::key(__ldcg(&row[en.v])) != en.key) continue;
+        if (Dist<T>::unkey(en.key) < theta) cur[atomicAdd(&s_near, 1)] = en;
+        else far2[atomicAdd(&s_keep, 1)] = en;
+      }
+      __syncthreads();
+      if (tid == 0) { s_far = s_keep; }
+      Entry* tmp = far; far = far2; far2 = tmp;
+      __syncthreads();
+    }
+    __syncthreads();
+  }
+}
+
+// rows >= n of the padded matrix: 0 on the diagonal, inf elsewhere (what drs_fw_init writes)
+template <typename T>
+__global__ void pad_rows_kernel(T* local, int64_t ld, int row0, int r_begin, int r_end) {
+  const int64_t total = (int64_t)(r_end - r_begin) * ld;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int i = r_begin + (int)(idx / ld), j = (int)(idx % ld);
+    local[(int64_t)i * ld + j] = (row0 + i == j) ? (T)0 : Dist<T>::inf();
+  }
+}
+
+__global__ void pack_arcs_kernel(int narcs, const int32_t* col, const float* w, int2* arcs) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a < narcs) arcs[a] = make_int2(col[a], __float_as_int(w[a]));
+}
+
+template <typename T>
+int sssp_run(const drs_graph* g, int nsrc, const int32_t* sources_dev, T* dist, int64_t ld, int64_t row_stride, double delta,
+             cudaStream_t st, const int2* arcs, Entry* queues, int cap, int grid, int* overflow) {
+  T d = (T)delta;
+  if (!(d > (T)0)) d = (T)1;
+  sssp_batch_kernel<T><<<grid, SSSP_THREADS, 0, st>>>(g->n, g->d_out_ptr, arcs, dist, ld, row_stride, sources_dev, nsrc, queues,
+                                                       cap, d, overflow);
+  drs_count_launch();
+  DRS_CUDA(cudaGetLastError());
+  return DRS_OK;
+}
+
+}  // namespace
+
+// Distances from `nsrc` sources into rows 0..nsrc-1 of dist_dev (row k <- sources[k]).
+extern "C" int drs_sssp_batch_dev(const drs_graph* g, int32_t mode, int32_t nsrc, const int32_t* sources_host, void* dist_dev,
+                                  int64_t ld, double delta, void* stream) {
+  DRS_REQUIRE(g && dist_dev && (nsrc == 0 || sources_host), DRS_ERR_ARG, "drs_sssp_batch_dev: null argument");
+  DRS_REQUIRE(ld >= g->n && nsrc >= 0, DRS_ERR_ARG, "drs_sssp_batch_dev: ld (%lld) must be >= n (%d)", (long long)ld, g->n);
+  DRS_REQUIRE(mode == DRS_MODE_F32 || mode == DRS_MODE_I32, DRS_ERR_ARG, "drs_sssp_batch_dev: unknown mode %d", mode);
+  for (int k = 0; k < nsrc; ++k)
+    DRS_REQUIRE(sources_host[k] >= 0 && sources_host[k] < g->n, DRS_ERR_RANGE, "drs_sssp_batch_dev: source %d out of range", sources_host[k]);
+  if (nsrc == 0) return DRS_OK;
+  DrsDeviceGuard guard(g->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (delta <= 0) {   // default bucket width: six times the mean arc weight (measured sweet spot on grid cities)
+    double s = 0;
+    for (double w : g->h_tt) s += w;
+    delta = g->m ? 6.0 * s / g->m : 1.0;
+  }
+  drs_graph* gm = const_cast<drs_graph*>(g);   // scratch buffers are cached on the handle
+  int sms = 148, per_sm = 1;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g->device);
+  if (mode == DRS_MODE_F32) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sssp_batch_kernel<float>, SSSP_THREADS, 0);
+  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sssp_batch_kernel<int>, SSSP_THREADS, 0);
+  const int grid = std::max(1, std::min(nsrc, sms * std::max(per_sm, 1)));
+  if (!gm->sssp_arcs) DRS_CUDA(cudaMalloc(&gm->sssp_arcs, sizeof(int2) * std::max(g->narcs, 1)));
+  if (!gm->sssp_arcs_valid && g->narcs) {
+    pack_arcs_kernel<<<(g->narcs + 255) / 256, 256, 0, st>>>(g->narcs, g->d_out_col, g->d_out_w, (int2*)gm->sssp_arcs);
+    drs_count_launch();
+    DRS_CUDA(cudaGetLastError());
+    gm->sssp_arcs_valid = true;
+  }
+  int32_t* d_sources = nullptr;
+  int* d_overflow = nullptr;
+  DRS_CUDA(cudaMalloc((void**)&d_sources, sizeof(int32_t) * nsrc + sizeof(int)));
+  d_overflow = reinterpret_cast<int*>(d_sources + nsrc);
+  int cap = std::max(4096, g->narcs + 1);
+  int rc = DRS_OK;
+  for (int attempt = 0; attempt < 3 && rc == DRS_OK; ++attempt) {
+    const size_t need = sizeof(Entry) * 4 * (size_t)cap * grid;
+    if (gm->sssp_queue_bytes < need) {
+      if (gm->sssp_queues) cudaFree(gm->sssp_queues);
+      gm->sssp_queues = nullptr; gm->sssp_queue_bytes = 0;
+      if (cudaMalloc(&gm->sssp_queues, need) != cudaSuccess) {
+        cudaFree(d_sources);
+        DRS_REQUIRE(false, DRS_ERR_NOMEM, "drs_sssp_batch_dev: cannot allocate %zu bytes of work queues", need);
+      }
+      gm->sssp_queue_bytes = need;
+    }
+    cudaMemsetAsync(d_overflow, 0, sizeof(int), st);
+    cudaMemcpyAsync(d_sources, sources_host, sizeof(int32_t) * nsrc, cudaMemcpyHostToDevice, st);
+    if (mode == DRS_MODE_F32)
+      rc = sssp_run<float>(g, nsrc, d_sources, (float*)dist_dev, ld, ld, delta, st, (const int2*)gm->sssp_arcs,
+                           (Entry*)gm->sssp_queues, cap, grid, d_overflow);
+    else
+      rc = sssp_run<int>(g, nsrc, d_sources, (int*)dist_dev, ld, ld, delta, st, (const int2*)gm->sssp_arcs,
+                         (Entry*)gm->sssp_queues, cap, grid, d_overflow);
+    if (rc) break;
+    int ovf = 0;
+    cudaMemcpyAsync(&ovf, d_overflow, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) { drs_set_error("drs_sssp_batch_dev: kernel failed: %s", cudaGetErrorString(cudaGetLastError())); rc = DRS_ERR_CUDA; break; }
+    if (!ovf) { cudaFree(d_sources); return DRS_OK; }
+    cap *= 4;   // queue overflow: retry with larger queues
+  }
+  cudaFree(d_sources);
+  if (rc) return rc;
+  DRS_REQUIRE(false, DRS_ERR_NOMEM, "drs_sssp_batch_dev: work queues overflowed three times");
+}
+
+// Host-output variant (BASELINE config C5): dist_out_host is nsrc x n doubles (inf = unreachable).
+extern "C" int drs_sssp_batch(const drs_graph* g, int32_t mode, int32_t nsrc, const int32_t* sources_host, double* dist_out_host) {
+  DRS_REQUIRE(g && (nsrc == 0 || (sources_host && dist_out_host)), DRS_ERR_ARG, "drs_sssp_batch: null argument");
+  if (nsrc == 0) return DRS_OK;
+  DrsDeviceGuard guard(g->device);
+  const int64_t ld = g->npad;
+  void* d = nullptr;
+  DRS_CUDA(cudaMalloc(&d, sizeof(float) * ld * nsrc));
+  int rc = drs_sssp_batch_dev(g, mode, nsrc, sources_host, d, ld, 0.0, g->stream);
+  if (rc == DRS_OK) {
+    std::vector<float> tmp((size_t)ld * nsrc);
+    cudaError_t e = cudaMemcpy(tmp.data(), d, sizeof(float) * ld * nsrc, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { drs_set_error("drs_sssp_batch: %s", cudaGetErrorString(e)); rc = DRS_ERR_CUDA; }
+    else {
+      const double inf = std::numeric_limits<double>::infinity();
+      for (int k = 0; k < nsrc; ++k)
+        for (int j = 0; j < g->n; ++j) {
+          double v;
+          if (mode == DRS_MODE_F32) v = (double)tmp[(size_t)k * ld + j];
+          else { int iv = reinterpret_cast<const int*>(tmp.data())[(size_t)k * ld + j]; v = iv >= DRS_I32_INF ? inf : (double)iv; }
+          dist_out_host[(size_t)k * g->n + j] = v;
+        }
+    }
+  }
+  cudaFree(d);
+  return rc;
+}
+
+// All-pairs by N searches: rows [row0, row0+nrows) of the padded matrix (same layout and
+// padding as drs_fw_init + the FW rounds produce).
+extern "C" int drs_apsp_rows_sssp(const drs_graph* g, int32_t mode, void* local_dev, int64_t ld, int32_t row0, int32_t nrows,
+                                  double delta, void* stream) {
+  DRS_REQUIRE(g && local_dev, DRS_ERR_ARG, "drs_apsp_rows_sssp: null argument");
+  DRS_REQUIRE(ld == g->npad && row0 >= 0 && nrows >= 0 && row0 + nrows <= g->npad, DRS_ERR_ARG, "drs_apsp_rows_sssp: bad shard");
+  if (nrows == 0) return DRS_OK;
+  DrsDeviceGuard guard(g->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nreal = std::max(0, std::min(nrows, g->n - row0));
+  if (nreal < nrows) {
+    if (mode == DRS_MODE_F32) pad_rows_kernel<float><<<148, 256, 0, st>>>((float*)local_dev, ld, row0, nreal, nrows);
+    else pad_rows_kernel<int><<<148, 256, 0, st>>>((int*)local_dev, ld, row0, nreal, nrows);
+    drs_count_launch();
+    DRS_CUDA(cudaGetLastError());
+  }
+  if (nreal == 0) return DRS_OK;
+  std::vector<int32_t> src(nreal);
+  for (int i = 0; i < nreal; ++i) src[i] = row0 + i;
+  return drs_sssp_batch_dev(g, mode, nreal, src.data(), local_dev, ld, delta, stream);
+}

@@ -158,7 +158,7 @@ class RoadGraph(object):
     ``ttmedian`` after load).
     """
 
-    def __init__(self, data, mode=_lib.MODE_F32):
+    def __init__(self, data, mode=_lib.MODE_F32, algorithm=_lib.APSP_AUTO):
         if not isinstance(data, RoadGraphData):
             raise TypeError("RoadGraph needs RoadGraphData (use RoadGraph.Read_GML)")
         self.n, self.m = data.n, data.m
@@ -168,6 +168,7 @@ class RoadGraph(object):
         self._eattrs = {k: (np.array(v, dtype=np.float64) if isinstance(v, np.ndarray) else list(v))
                         for k, v in data.eattrs.items()}
         self.mode = mode
+        self.algorithm = algorithm    # _lib.APSP_FW (blocked Floyd-Warshall) | APSP_SSSP (N delta-stepping searches) | APSP_AUTO
         self._handle = None
         self._weight_attr = None      # attribute the device weights / matrix were built from
         self._lib = None
@@ -290,8 +291,8 @@ class RoadGraph(object):
 
     _weights_dirty = False
 
-    def _ensure(self, weights):
-        """Device graph exists, carries `weights`, and the APSP matrix is valid."""
+    def _ensure(self, weights, build=True):
+        """Device graph exists, carries `weights`, and (build=True) the APSP matrix is valid."""
         attr = weights if weights is not None else (self._weight_attr or "ttmedian")
         if not isinstance(attr, str):
             raise ValueError("weights must name an edge attribute")
@@ -315,12 +316,27 @@ class RoadGraph(object):
             self._weight_attr = attr
             self._weights_dirty = False
             self._valid = False
-        if not self._valid:
+        if build and not self._valid:
+            _lib.check(lib.drs_apsp_set_algorithm(self._handle, self.algorithm), lib)
             _lib.check(lib.drs_apsp_build(self._handle, self.mode), lib)
             self._valid = True
         return lib
 
     _valid = False
+
+    def upload(self, weights=None):
+        """Creates the device CSR graph (and refreshes its weights) WITHOUT building the matrix;
+        returns the drs_graph* handle.  Used by the multi-GPU build and by benchmarks."""
+        self._ensure(weights, build=False)
+        return self._handle
+
+    def adopt(self, dist_tensor, pred_tensor):
+        """Adopts externally built matrices (torch CUDA tensors from apsp_dist.gather_replica)."""
+        lib = self._ensure(None, build=False)
+        _lib.check(lib.drs_apsp_adopt(self._handle, self.mode, C.c_void_p(dist_tensor.data_ptr()),
+                                      C.c_void_p(pred_tensor.data_ptr()), dist_tensor.shape[1]), lib)
+        self._adopted = (dist_tensor, pred_tensor)     # keep the tensors alive
+        self._valid = True
 
     def build(self, weights=None):
         """Builds (or rebuilds) the travel-time matrix now instead of at the first query."""
@@ -377,6 +393,16 @@ class RoadGraph(object):
                 continue
             _lib.check(rc, lib)
             return [int(e) for e in buf[:n.value]]
+
+    def sssp(self, sources, weights=None):
+        """Distances from the given sources WITHOUT the N x N matrix (batched delta-stepping SSSP);
+        returns a len(sources) x n float64 array.  For networks too large for the matrix
+        (BASELINE config C5) and for ``G.shortest_paths(src_list)``-style row queries."""
+        lib = self._ensure(weights, build=False)
+        src = _lib.as_i32([self._resolve(s) for s in sources])
+        out = np.empty((len(src), self.n), dtype=np.float64)
+        _lib.check(lib.drs_sssp_batch(self._handle, self.mode, len(src), _lib.ptr_i32(src), _lib.ptr_f64(out)), lib)
+        return out
 
     def dist_rows(self, row0, nrows, weights=None):
         lib = self._ensure(weights)

@@ -96,6 +96,30 @@ int drs_apsp_adopt(drs_graph* g, int32_t mode, void* dist_dev, int32_t* pred_dev
  * G.shortest_paths(src, tgt, weights=) (lib/optimUtils.py:528,531,659). */
 int drs_apsp_rows_to_host(const drs_graph* g, int32_t row0, int32_t nrows, double* out_host);
 
+/* Algorithm used by drs_apsp_build.  FW: blocked min-plus Floyd-Warshall (N^3 work, ALU
+ * bound, independent of sparsity).  SSSP: N delta-stepping searches over the CSR (about
+ * N*E work, memory-latency bound; far less work on sparse road networks).  Both give the
+ * same matrix bit for bit on integer weights.  AUTO picks SSSP when arcs/vertex <= 16. */
+#define DRS_APSP_FW 0
+#define DRS_APSP_SSSP 1
+#define DRS_APSP_AUTO 2
+int drs_apsp_set_algorithm(drs_graph* g, int32_t algorithm);
+
+/* --------------------------------------------------------- batched SSSP --
+ * Distances from nsrc sources (delta-stepping, one CTA per source).  Replaces the same
+ * igraph Dijkstra calls when the N x N matrix does not fit in HBM (BASELINE config C5).
+ * _dev: row k of dist_dev (float or int32 per mode, leading dimension ld >= n) receives
+ * the distances from sources_host[k]; delta <= 0 selects the default bucket width (twice
+ * the mean arc weight).  The host variant returns nsrc x n doubles (inf = unreachable). */
+int drs_sssp_batch_dev(const drs_graph* g, int32_t mode, int32_t nsrc, const int32_t* sources_host,
+                       void* dist_dev, int64_t ld, double delta, void* stream);
+int drs_sssp_batch(const drs_graph* g, int32_t mode, int32_t nsrc, const int32_t* sources_host,
+                   double* dist_out_host);
+/* Rows [row0, row0+nrows) of the padded all-pairs matrix by SSSP (sources are independent:
+ * the multi-GPU build shards them across ranks with no collective). */
+int drs_apsp_rows_sssp(const drs_graph* g, int32_t mode, void* local_dev, int64_t ld, int32_t row0,
+                       int32_t nrows, double delta, void* stream);
+
 /* ---------------------------------------------------- FW building blocks --
  * Used by the single-GPU build and by the row-block-sharded multi-GPU build
  * (SURVEY.md section 8e).  `local` is this rank's shard: rows
@@ -291,6 +315,10 @@ int drs_tick_insertion_eval(drs_tick* t, int32_t n_new, const int32_t* new_rows_
  * The CUDA stream (cudaStream_t as void*) every call on this graph launches on:
  * lets the host time kernels with events on the launching stream. */
 int drs_graph_stream(const drs_graph* g, void** stream);
+/* Device time (ms, CUDA events on the graph's stream) of the last evaluation kernels of a tick:
+ * ms[0] rv_filter, ms[1] rv_eval (drs_tick_rv_eval); ms[2] insertion_scan, ms[3] insertion_fold
+ * (drs_tick_insertion_eval). */
+int drs_tick_last_ms(const drs_tick* t, double* ms);
 /* Number of kernels this library has launched in this process so far. */
 int64_t drs_launch_count(void);
 /* Device time of the last drs_apsp_build by phase, from CUDA events on the

@@ -17,11 +17,12 @@ def _engine(name, **kw):
 
 @pytest.mark.parametrize("name", MAPS)
 @pytest.mark.parametrize("mode", [0, 1])
-def test_matrix_and_paths_match_oracle(name, mode):
+@pytest.mark.parametrize("algorithm", [0, 1], ids=["fw", "sssp"])
+def test_matrix_and_paths_match_oracle(name, mode, algorithm):
     if mode == 1 and "float" in name:
         pytest.skip("int32 mode needs integer weights")
     from drs_abm_b200.routing import RoadGraph
-    G = RoadGraph.Read_GML(golden_map_path(name), mode=mode)
+    G = RoadGraph.Read_GML(golden_map_path(name), mode=mode, algorithm=algorithm)
     O = oracle_graph(name)
     got = G.dist_rows(0, G.n)
     want = O.dist_matrix()
@@ -126,14 +127,15 @@ def test_same_node_unknown_vertex_and_weight_updates():
     assert np.array_equal(G.dist_rows(0, G.n), O.dist_matrix())
 
 
-def test_c2_full_size_properties():
+@pytest.mark.parametrize("algorithm", [0, 1], ids=["fw", "sssp"])
+def test_c2_full_size_properties(algorithm):
     """BASELINE config C2 (5k nodes): exact match with the oracle's Dijkstra on sampled rows plus
     size-independent properties of the whole matrix (symmetry, zero diagonal, triangle inequality
     through random pivots, tight predecessor edges)."""
     from drs_abm_b200 import synth
     from drs_abm_b200.routing import RoadGraph
     data = synth.config_graph("C2")
-    G = RoadGraph(data)
+    G = RoadGraph(data, algorithm=algorithm)
     O = oracle_graph_from_data(data)
     D = G.dist_rows(0, G.n)
     idx = np.random.RandomState(0).randint(0, G.n, 40)
@@ -146,6 +148,33 @@ def test_c2_full_size_properties():
     s = rs.randint(0, G.n, 500).astype(np.int32); t = rs.randint(0, G.n, 500).astype(np.int32)
     tt, ln, hops = G.path_sums(s, t)
     assert np.array_equal(tt, D[s, t]) and np.array_equal(ln, 10.0 * tt)     # length = 10 * ttmedian on "int" maps
+    G.close()
+
+
+def test_batched_sssp_without_matrix():
+    """BASELINE config C5 usage: distance rows for a batch of sources, no N x N matrix."""
+    from drs_abm_b200 import synth
+    from drs_abm_b200.routing import RoadGraph
+    for name, mode in (("C2", 0), ("C2", 1), ("C2_float", 0)):
+        data = synth.config_graph(name)
+        G = RoadGraph(data, mode=mode)
+        O = oracle_graph_from_data(data)
+        src = np.random.RandomState(3).randint(0, G.n, 200)
+        got = G.sssp([int(x) for x in src])
+        want = O.dist_rows(src)
+        if "float" in name:
+            assert np.max(np.abs(got - want) / np.maximum(want, 1e-12)) < 1e-5
+        else:
+            assert np.array_equal(got, want)
+        assert not G._valid                       # the matrix was never built
+        G.close()
+    # disconnected components stay at inf
+    from drs_abm_b200.gml import RoadGraphData
+    d2 = RoadGraphData(5, False, [0, 1, 3], [1, 2, 4], {"name": list("abcde"), "lng": [0., 1., 2., 3., 4.], "lat": [0.] * 5},
+                       {"ttmedian": np.array([1., 2., 5.]), "length": np.array([1., 1., 1.])})
+    G = RoadGraph(d2)
+    r = G.sssp([0, 4])
+    assert r[0].tolist() == [0.0, 1.0, 3.0, np.inf, np.inf] and r[1].tolist() == [np.inf, np.inf, np.inf, 5.0, 0.0]
     G.close()
 
 
