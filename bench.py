@@ -349,8 +349,9 @@ def main():
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-        keep = None
+        keep = local = None
         for _ in range(steps):
+            del keep, local                                  # never hold two matrices: the allocator reuses the block
             local, pred, row0 = one_build(algorithm)
             del pred
             keep = local

@@ -1,0 +1,152 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/drs_b200.h declares
+(no compute calls), host-side formats and helpers, and that the product refuses to run without its
+CUDA extension (no CPU fallback)."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "drs_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(drs_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+    path = ge.build()
+    assert os.path.exists(path)
+    from drs_abm_b200 import _lib
+    lib = _lib.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(lib, name), "declared in include/drs_b200.h but not exported: %s" % name
+        assert name in _lib.SIGNATURES, "exported but not bound in drs_abm_b200/_lib.py: %s" % name
+    exported = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True).stdout
+    for name in re.findall(r" T (drs_[a-z0-9_]+)", exported):
+        assert name in declared, "exported without a declaration in include/drs_b200.h: %s" % name
+    assert lib.drs_version() == 100 and lib.drs_launch_count() == 0      # nothing has run on a GPU here
+
+
+def test_sass_is_sm100a_only():
+    from drs_abm_b200 import _lib
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_no_cpu_fallback_when_library_is_missing(tmp_path, monkeypatch):
+    from drs_abm_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "missing.so"))
+    with pytest.raises(_lib.DrsError, match="no CPU fallback"):
+        _lib.load()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "drs_abm_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src.replace("the oracle", "").replace("oracle/", ""), fn
+            assert "/root/reference" not in src.replace("/root/reference lib", "").replace("/root/reference/.gitignore", ""), fn
+
+
+def test_gml_roundtrip_and_independent_reader(tmp_path):
+    from drs_abm_b200 import gml, synth
+    from oracle.routing_oracle import OracleGraph
+    data = synth.grid_city(9, 3, 0.9, "float")
+    p = str(tmp_path / "g.gml")
+    gml.write_gml(p, data)
+    back = gml.read_gml(p)
+    assert (back.n, back.m, back.directed) == (data.n, data.m, False)
+    assert np.array_equal(back.src, data.src) and np.array_equal(back.dst, data.dst)
+    for k in ("length", "ttmedian", "slnshift", "slnmean", "slnsd"):
+        assert np.array_equal(back.eattrs[k], data.eattrs[k])          # repr() round-trips doubles exactly
+    assert back.vattrs["name"] == data.vattrs["name"] and back.vattrs["lng"] == data.vattrs["lng"]
+    assert all(isinstance(x, float) for x in back.vattrs["lng"])       # igraph hands numeric attrs back as floats
+    O = OracleGraph.from_gml(p)                                          # networkx reader agrees
+    assert (O.n, O.m) == (data.n, data.m) and O.names == data.vattrs["name"]
+    assert np.array_equal(O.tt, data.eattrs["ttmedian"]) and np.array_equal(O.src, data.src)
+
+
+def test_synthetic_configs_are_deterministic_and_connected():
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    from drs_abm_b200 import synth
+    a, b = synth.config_graph("C2"), synth.config_graph("C2")
+    assert a.n == b.n == 5040 and np.array_equal(a.src, b.src) and np.array_equal(a.eattrs["ttmedian"], b.eattrs["ttmedian"])
+    adj = coo_matrix((np.ones(a.m), (a.src, a.dst)), shape=(a.n, a.n))
+    assert connected_components(adj, directed=False)[0] == 1
+    c1 = synth.config_graph("C1")
+    assert (c1.n, c1.m) == (400, 760) and c1.eattrs["ttmedian"].min() >= 20 and c1.eattrs["ttmedian"].max() <= 60
+    assert np.array_equal(c1.eattrs["length"], 10 * c1.eattrs["ttmedian"])
+    assert len(set(c1.vattrs["name"])) == c1.n and c1.vattrs["name"][0] == str((c1.vattrs["lng"][0], c1.vattrs["lat"][0]))
+    o, d = synth.random_od_pairs(400, 1000, 1)
+    assert (o != d).all()
+
+
+def test_node_identity_rules():
+    from drs_abm_b200 import synth
+    from drs_abm_b200.routing import RoadGraph
+    G = RoadGraph(synth.config_graph("C1"))
+    v = G.vs[37]
+    assert G.node_index(v["name"]) == 37
+    assert G.node_index(str((v["lng"], v["lat"]))) == 37
+    assert G.node_index(str((np.float64(v["lng"]), np.float64(v["lat"])))) == 37      # numpy-2 scalar repr
+    assert G.node_of_location(np.float64(v["lng"]), v["lat"]) == 37
+    assert G.vs.find(name=v["name"]).index == 37 and G.vs.find(v["name"])["lat"] == v["lat"]
+    with pytest.raises(ValueError):
+        G.vs.find(name="(0.0, 0.0)")
+    with pytest.raises(ValueError):
+        G.node_index("nonsense")
+    e = G.es[5]
+    assert (e.source, e.target) == (int(G._src[5]), int(G._dst[5])) and e["length"] == 10 * e["ttmedian"]
+    assert len(G.es) == 760 and len(G.vs) == 400 and len(G.es["length"]) == 760
+    e["ttmedian"] = 99.0
+    assert G.es[5]["ttmedian"] == 99.0
+    with pytest.raises(ValueError):
+        G.es["ttmedian"] = [1.0, 2.0]
+
+
+def test_rng_parity_of_generate_random_location():
+    """lib/RoutingEngine.py:228-229 ``rs.choice(G.vs)`` consumes exactly one randint(0, n)."""
+    n = 400
+    a, b = np.random.RandomState(11), np.random.RandomState(11)
+    seq = list(range(n))
+    for _ in range(20):
+        assert a.choice(seq) == int(b.randint(0, n))
+
+
+def test_set_packing_solver_matches_the_ilp_objective():
+    from drs_abm_b200.dispatch import solve_set_packing
+    from oracle.dispatch_oracle import assign_ilp
+    rs = np.random.RandomState(0)
+    for case in range(25):
+        nveh, nreq = int(rs.randint(1, 7)), int(rs.randint(1, 8))
+        trips = []
+        for v in range(nveh):
+            for r in range(nreq):
+                if rs.rand() < 0.5:
+                    trips.append((v, (r,), float(rs.randint(0, 500))))
+            if case % 2:                                        # multi-request trips -> general ILP path
+                for _ in range(int(rs.randint(0, 4))):
+                    k = int(rs.randint(2, min(4, nreq) + 1)) if nreq >= 2 else 1
+                    members = tuple(sorted(rs.choice(nreq, size=k, replace=False).tolist()))
+                    if len(members) > 1 and (v, members) not in [(t[0], t[1]) for t in trips]:
+                        trips.append((v, members, float(rs.randint(0, 900))))
+        chosen, ignored, obj = solve_set_packing(nveh, nreq, [(t[0], t[1]) for t in trips], np.array([t[2] for t in trips]))
+        _, orej, oobj = assign_ilp(list(range(nveh)), list(range(nreq)), trips)
+        assert obj == pytest.approx(oobj, abs=1e-6)
+        served = [r for k in chosen for r in trips[k][1]]
+        assert len(served) == len(set(served)) and sorted(served + ignored) == list(range(nreq))
+        assert len(set(trips[k][0] for k in chosen)) == len(chosen)
+        assert len(ignored) == len(orej)
