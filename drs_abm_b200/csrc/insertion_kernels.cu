@@ -35,6 +35,15 @@ struct PlanView {
   const int32_t *q_o, *q_d;
   const double *q_cep, *q_clp, *q_cld, *q_ts, *q_tr, *q_pwt;
   drs_insertion_params prm;
+  // per-vehicle precomputation (plan_prep_kernel): plan segment times and the walk of the
+  // unmodified plan, which is the common prefix of every candidate
+  const double* seg;        // [stop]      tt(previous stop or start vertex -> stop)
+  const int8_t* partner;    // [stop]      plan index of the pickup belonging to a drop-off, -1 if on board
+  const double* base_t;     // [stop + v]  t before plan stop k, k = 0..L
+  const double* base_c;     // [stop + v]  c before plan stop k
+  const double* base_cld;   // [stop]      Cld assigned when plan stop k is a pickup
+  const int32_t* base_viol; // [v]         first plan stop the unmodified walk fails at (L if none), -1: over capacity
+  int directed;
 };
 
 // Everything one (vehicle, request) pair needs, in thread-local storage.
@@ -214,6 +223,194 @@ __global__ void insertion_fold_kernel(PlanView pv, DistView dv, int n_new, const
   best_veh[r] = wv; best_i[r] = wi; best_j[r] = wj; best_dc[r] = dc;
 }
 
+
+// One stop of test_constraints_get_cost's walk (lib/Agents.py:1523-1567) without the bound test.
+struct Walk { double t, c; int n; };
+__device__ __forceinline__ int walk_stop(Walk& w, double dt, int pod, int rq, double T, const PlanView& pv,
+                                         double cld_drop, double* cld_set) {
+  w.t += dt;
+  if (pod == 1) {
+    const double cep = pv.q_cep[rq];
+    if (T + w.t < cep) {
+      dt += cep - T - w.t;
+      w.t += cep - T - w.t;
+      *cld_set = cep + pv.prm.max_detour * pv.q_ts[rq];
+    } else if (T + w.t > pv.q_clp[rq]) {
+      return 2;
+    } else {
+      *cld_set = T + w.t + pv.prm.max_detour * pv.q_ts[rq];
+    }
+  } else if (pod == -1 && T + w.t > cld_drop) {
+    return 3;
+  }
+  w.c += w.n * dt * pv.prm.coef_inveh;
+  w.n += pod;
+  if (pod == 1) {
+    const double pwt = pv.q_pwt[rq];
+    if (pwt > 0) w.c += (T + w.t - pv.q_tr[rq] - pwt) * pv.prm.coef_extra_wait;
+    else w.c += w.t * pv.prm.coef_wait;
+  }
+  return -1;
+}
+
+// Per vehicle: plan segment times and the walk of the unmodified plan.
+__global__ void plan_prep_kernel(PlanView pv, DistView dv, double* seg, double* base_t, double* base_c, double* base_cld,
+                                 int32_t* base_viol) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= pv.n_veh) return;
+  const int s0 = pv.off[v], L = pv.off[v + 1] - s0;
+  int prev = pv.node[v];
+  for (int k = 0; k < L; ++k) {
+    const int nd = pv.s_node[s0 + k];
+    seg[s0 + k] = (prev == nd) ? 0.0 : dv.at(prev, nd);
+    prev = nd;
+  }
+  int occ = pv.onboard[v], viol_at = L;
+  bool over = occ > pv.cap[v];
+  for (int k = 0; k < L; ++k) { occ += pv.s_pod[s0 + k]; if (occ > pv.cap[v]) over = true; }
+  Walk w{0.0 + pv.delay[v], 0.0, pv.onboard[v]};
+  const double T = pv.clock[v];
+  for (int k = 0; k <= L; ++k) {
+    base_t[s0 + v + k] = w.t;
+    base_c[s0 + v + k] = w.c;
+    if (k == L || viol_at < L) continue;
+    const int pod = pv.s_pod[s0 + k], rq = pv.s_req[s0 + k];
+    double cld_drop = pv.q_cld[rq];
+    const int pk = pv.partner[s0 + k];
+    if (pk >= 0) cld_drop = base_cld[s0 + pk];
+    double cld_set = 0.0;
+    if (walk_stop(w, seg[s0 + k], pod, rq, T, pv, cld_drop, &cld_set) >= 0) viol_at = k;
+    base_cld[s0 + k] = cld_set;
+  }
+  base_viol[v] = over ? -1 : viol_at;
+}
+
+// Scan, second version: the unmodified-plan prefix is shared (precomputed per vehicle), the state
+// "pickup inserted after a stops, b-a further stops served" is advanced incrementally over b, and only
+// the tail after the drop-off is re-walked per candidate.  Same arithmetic, same operation order per
+// candidate as eval_candidate; only successes matter here (cmin), so no viol bookkeeping.
+__global__ void __launch_bounds__(128) insertion_scan2_kernel(PlanView pv, DistView dv, int n_new, const int32_t* __restrict__ new_rows,
+                                                              const double* __restrict__ od_tt, double* __restrict__ cmin_out,
+                                                              unsigned long long* n_cand) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)pv.n_veh * n_new;
+  if (idx >= total) return;
+  const int v = (int)(idx / n_new), r = (int)(idx % n_new);
+  const double inf = __longlong_as_double(0x7ff0000000000000LL);
+  const int s0 = pv.off[v], L = pv.off[v + 1] - s0;
+  if (r == 0) atomicAdd(n_cand, (unsigned long long)((L + 1) * (L + 2) / 2) * (unsigned long long)n_new);
+  double cmin = inf;
+  const int bviol = pv.base_viol[v];
+  if (bviol >= 0) {
+    const int rq = new_rows[r];
+    const int o = pv.q_o[rq], d = pv.q_d[rq];
+    const int K = pv.cap[v];
+    const double T = pv.clock[v];
+    double to_o[MAXL + 1], to_d[MAXL + 1], from_o[MAXL], from_d[MAXL], cld_cur[MAXL];
+    {
+      int prev = pv.node[v];
+      to_o[0] = (prev == o) ? 0.0 : dv.at(prev, o);
+      to_d[0] = (prev == d) ? 0.0 : dv.at(prev, d);
+      for (int k = 0; k < L; ++k) {
+        const int nd = pv.s_node[s0 + k];
+        to_o[k + 1] = (nd == o) ? 0.0 : dv.at(nd, o);
+        to_d[k + 1] = (nd == d) ? 0.0 : dv.at(nd, d);
+        if (pv.directed) {
+          from_o[k] = (o == nd) ? 0.0 : dv.at(o, nd);
+          from_d[k] = (d == nd) ? 0.0 : dv.at(d, nd);
+        } else {                       // undirected graph: the matrix is symmetric
+          from_o[k] = to_o[k + 1];
+          from_d[k] = to_d[k + 1];
+        }
+      }
+    }
+    const double od = od_tt[r];
+    int occ_before = pv.onboard[v];    // occupancy before plan stop a in the unmodified plan
+    for (int a = 0; a <= L && a <= bviol; ++a) {
+      if (a > 0) {
+        cld_cur[a - 1] = pv.base_cld[s0 + a - 1];
+        occ_before += pv.s_pod[s0 + a - 1];
+      }
+      if (occ_before + 1 > K) continue;
+      Walk S{pv.base_t[s0 + v + a], pv.base_c[s0 + v + a], occ_before};
+      double cld_new = 0.0;
+      if (walk_stop(S, to_o[a], 1, rq, T, pv, 0.0, &cld_new) >= 0) continue;   // late pickup
+      int occ_after = occ_before;      // occupancy of the unmodified plan after stop b-1
+      for (int b = a; b <= L; ++b) {
+        // ---- candidate (a, b): drop-off now, then the rest of the plan
+        Walk W = S;
+        double dummy;
+        if (walk_stop(W, b == a ? od : to_d[b], -1, rq, T, pv, cld_new, &dummy) < 0) {
+          bool ok = true;
+          for (int k = b; k < L; ++k) {
+            const int pod = pv.s_pod[s0 + k], q = pv.s_req[s0 + k];
+            double cld_drop = 0.0;
+            if (pod < 0) { const int pk = pv.partner[s0 + k]; cld_drop = pk >= 0 ? cld_cur[pk] : pv.q_cld[q]; }
+            if (walk_stop(W, k == b ? from_d[k] : pv.seg[s0 + k], pod, q, T, pv, cld_drop, &cld_cur[k]) >= 0) { ok = false; break; }
+          }
+          if (ok && W.c < cmin) cmin = W.c;
+        }
+        // ---- serve plan stop b with the new rider on board
+        if (b == L) break;
+        const int pod = pv.s_pod[s0 + b], q = pv.s_req[s0 + b];
+        occ_after += pod;
+        if (occ_after + 1 > K) break;                   // over capacity for every larger b
+        double cld_drop = 0.0;
+        if (pod < 0) { const int pk = pv.partner[s0 + b]; cld_drop = pk >= 0 ? cld_cur[pk] : pv.q_cld[q]; }
+        if (walk_stop(S, b == a ? from_o[b] : pv.seg[s0 + b], pod, q, T, pv, cld_drop, &cld_cur[b]) >= 0) break;
+      }
+    }
+  }
+  cmin_out[idx] = cmin;
+}
+
+__global__ void od_gather_kernel(PlanView pv, DistView dv, int n_new, const int32_t* new_rows, double* od_tt) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_new) return;
+  const int o = pv.q_o[new_rows[r]], d = pv.q_d[new_rows[r]];
+  od_tt[r] = (o == d) ? 0.0 : dv.at(o, d);
+}
+
+// Fold, second version: one WARP per request.  Lanes read the smallest costs of 32 consecutive
+// vehicles; only flagged vehicles are re-scanned (by their lane) in vehicle order with the running bound.
+__global__ void insertion_fold2_kernel(PlanView pv, DistView dv, int n_new, const int32_t* new_rows, const double* cmin,
+                                       int32_t* best_veh, int32_t* best_i, int32_t* best_j, double* best_dc) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= n_new) return;
+  const double inf = __longlong_as_double(0x7ff0000000000000LL);
+  double dc = inf;                   // dc_ = np.inf (:1452)
+  int wv = -1, wi = -1, wj = -1;
+  for (int base = 0; base < pv.n_veh; base += 32) {
+    const int v = base + lane;
+    double cm = inf, c0 = 0.0;
+    if (v < pv.n_veh) { cm = cmin[(int64_t)v * n_new + r]; c0 = pv.cost[v]; }
+    unsigned mask = __ballot_sync(0xffffffffu, cm != inf && !(cm > c0 + dc));
+    while (mask) {
+      const int l = __ffs(mask) - 1;
+      mask &= mask - 1;
+      double ndc = dc; int nv = wv, ni = wi, nj = wj;
+      if (lane == l && !(cm > c0 + dc)) {              // re-check: dc may have dropped inside this chunk
+        Pair p;
+        load_pair(p, pv, dv, v, new_rows[r]);
+        int viol = -1;
+        for (int i = 0; i <= p.L; ++i) {                         // (:1466-1482)
+          for (int j = i + 1; j <= p.L + 1; ++j) {
+            double c;
+            viol = eval_candidate(p, pv, i, j - 1, c0 + ndc, &c);
+            if (viol < 0) { ndc = c - c0; nv = v; ni = i; nj = j; }
+            if (viol > 0) break;
+          }
+          if (viol == 2) break;
+        }
+      }
+      dc = __shfl_sync(0xffffffffu, ndc, l); wv = __shfl_sync(0xffffffffu, nv, l);
+      wi = __shfl_sync(0xffffffffu, ni, l); wj = __shfl_sync(0xffffffffu, nj, l);
+    }
+  }
+  if (lane == 0) { best_veh[r] = wv; best_i[r] = wi; best_j[r] = wj; best_dc[r] = dc; }
+}
+
 }  // namespace
 
 struct LegacyDev {
@@ -223,6 +420,9 @@ struct LegacyDev {
   int8_t* s_pod = nullptr;
   int32_t *q_o = nullptr, *q_d = nullptr;
   double *q_cep = nullptr, *q_clp = nullptr, *q_cld = nullptr, *q_ts = nullptr, *q_tr = nullptr, *q_pwt = nullptr;
+  int8_t* partner = nullptr;
+  double *seg = nullptr, *base_t = nullptr, *base_c = nullptr, *base_cld = nullptr;
+  int32_t* base_viol = nullptr;
   drs_insertion_params prm{1.5, 1.0, 1.5, 3.0};
 };
 
@@ -230,7 +430,8 @@ void drs_tick_free_plans(drs_tick* t) {
   LegacyDev* d = t->legacy;
   if (!d) return;
   void* ptrs[] = {d->node, d->onboard, d->cap, d->off, d->s_node, d->s_req, d->delay, d->clock, d->cost, d->s_pod,
-                  d->q_o, d->q_d, d->q_cep, d->q_clp, d->q_cld, d->q_ts, d->q_tr, d->q_pwt};
+                  d->q_o, d->q_d, d->q_cep, d->q_clp, d->q_cld, d->q_ts, d->q_tr, d->q_pwt, d->partner, d->seg, d->base_t,
+                  d->base_c, d->base_cld, d->base_viol};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete d;
@@ -275,6 +476,21 @@ extern "C" int drs_tick_set_plans(drs_tick* t, const drs_plan_batch* b, const dr
       (rc = drs_upload(&d.q_cld, q->Cld, nq, st)) || (rc = drs_upload(&d.q_ts, q->Ts, nq, st)) ||
       (rc = drs_upload(&d.q_tr, q->Tr, nq, st)) || (rc = drs_upload(&d.q_pwt, q->pwt, nq, st)))
     return rc;
+  // plan index of the pickup that belongs to each drop-off (-1: the rider is already on board)
+  std::vector<int8_t> partner(std::max(nstops, 1), -1);
+  for (int v = 0; v < nv; ++v)
+    for (int s = b->stop_off[v]; s < b->stop_off[v + 1]; ++s)
+      if (b->stop_pod[s] < 0)
+        for (int m = b->stop_off[v]; m < s; ++m)
+          if (b->stop_req[m] == b->stop_req[s] && b->stop_pod[m] > 0) partner[s] = (int8_t)(m - b->stop_off[v]);
+  if ((rc = drs_upload(&d.partner, partner.data(), nstops, st))) return rc;
+  void** scratch[] = {(void**)&d.seg, (void**)&d.base_t, (void**)&d.base_c, (void**)&d.base_cld, (void**)&d.base_viol};
+  const size_t bytes[] = {sizeof(double) * std::max(nstops, 1), sizeof(double) * (nstops + nv + 1), sizeof(double) * (nstops + nv + 1),
+                          sizeof(double) * std::max(nstops, 1), sizeof(int32_t) * std::max(nv, 1)};
+  for (int i = 0; i < 5; ++i) {
+    if (*scratch[i]) { cudaFree(*scratch[i]); *scratch[i] = nullptr; }
+    DRS_CUDA(cudaMalloc(scratch[i], bytes[i]));
+  }
   DRS_CUDA(cudaStreamSynchronize(st));
   d.n_veh = nv; d.n_stops = nstops; d.n_rows = nq;
   if (prm) d.prm = *prm;
@@ -298,17 +514,19 @@ extern "C" int drs_tick_insertion_eval(drs_tick* t, int32_t n_new, const int32_t
   DrsDeviceGuard guard(t->g->device);
   cudaStream_t st = t->g->stream;
   PlanView pv{d.n_veh, d.node, d.onboard, d.cap, d.off, d.s_node, d.s_req, d.delay, d.clock, d.cost, d.s_pod,
-              d.q_o, d.q_d, d.q_cep, d.q_clp, d.q_cld, d.q_ts, d.q_tr, d.q_pwt, d.prm};
+              d.q_o, d.q_d, d.q_cep, d.q_clp, d.q_cld, d.q_ts, d.q_tr, d.q_pwt, d.prm,
+              d.seg, d.partner, d.base_t, d.base_c, d.base_cld, d.base_viol, t->g->directed};
   DistView dv{t->g->d_dist, t->g->ld, t->g->mode};
   int32_t *d_rows = nullptr, *d_bv = nullptr, *d_bi = nullptr, *d_bj = nullptr;
-  double *d_cmin = nullptr, *d_dc = nullptr;
+  double *d_cmin = nullptr, *d_dc = nullptr, *d_od = nullptr;
   unsigned long long* d_ncand = nullptr;
-  auto cleanup = [&]() { cudaFree(d_rows); cudaFree(d_bv); cudaFree(d_bi); cudaFree(d_bj); cudaFree(d_cmin); cudaFree(d_dc); cudaFree(d_ncand); };
+  auto cleanup = [&]() { cudaFree(d_rows); cudaFree(d_bv); cudaFree(d_bi); cudaFree(d_bj); cudaFree(d_cmin); cudaFree(d_dc); cudaFree(d_ncand); cudaFree(d_od); };
   int rc = drs_upload(&d_rows, new_rows, n_new, st);
   if (rc) { cleanup(); return rc; }
   if (cudaMalloc((void**)&d_bv, sizeof(int32_t) * n_new) != cudaSuccess || cudaMalloc((void**)&d_bi, sizeof(int32_t) * n_new) != cudaSuccess ||
       cudaMalloc((void**)&d_bj, sizeof(int32_t) * n_new) != cudaSuccess || cudaMalloc((void**)&d_dc, sizeof(double) * n_new) != cudaSuccess ||
       cudaMalloc((void**)&d_cmin, sizeof(double) * std::max<int64_t>(total, 1)) != cudaSuccess ||
+      cudaMalloc((void**)&d_od, sizeof(double) * n_new) != cudaSuccess ||
       cudaMalloc((void**)&d_ncand, sizeof(unsigned long long)) != cudaSuccess) {
     cleanup();
     drs_set_error("drs_tick_insertion_eval: cudaMalloc failed");
@@ -318,12 +536,14 @@ extern "C" int drs_tick_insertion_eval(drs_tick* t, int32_t n_new, const int32_t
   DrsTimer tm_scan(st), tm_fold(st);
   tm_scan.start();
   if (total > 0) {
-    insertion_scan_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(pv, dv, n_new, d_rows, d_cmin, d_ncand);
-    drs_count_launch();
+    plan_prep_kernel<<<(d.n_veh + 127) / 128, 128, 0, st>>>(pv, dv, d.seg, d.base_t, d.base_c, d.base_cld, d.base_viol);
+    od_gather_kernel<<<(n_new + 127) / 128, 128, 0, st>>>(pv, dv, n_new, d_rows, d_od);
+    insertion_scan2_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(pv, dv, n_new, d_rows, d_od, d_cmin, d_ncand);
+    drs_count_launch(3);
   }
   tm_scan.stop();
   tm_fold.start();
-  insertion_fold_kernel<<<(n_new + 63) / 64, 64, 0, st>>>(pv, dv, n_new, d_rows, d_cmin, d_bv, d_bi, d_bj, d_dc);
+  insertion_fold2_kernel<<<(n_new * 32 + 127) / 128, 128, 0, st>>>(pv, dv, n_new, d_rows, d_cmin, d_bv, d_bi, d_bj, d_dc);
   drs_count_launch();
   tm_fold.stop();
   unsigned long long ncand = 0;
