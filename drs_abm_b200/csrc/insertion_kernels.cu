@@ -37,12 +37,21 @@ struct PlanView {
   drs_insertion_params prm;
   // per-vehicle precomputation (plan_prep_kernel): plan segment times and the walk of the
   // unmodified plan, which is the common prefix of every candidate
-  const double* seg;        // [stop]      tt(previous stop or start vertex -> stop)
-  const int8_t* partner;    // [stop]      plan index of the pickup belonging to a drop-off, -1 if on board
-  const double* base_t;     // [stop + v]  t before plan stop k, k = 0..L
-  const double* base_c;     // [stop + v]  c before plan stop k
-  const double* base_cld;   // [stop]      Cld assigned when plan stop k is a pickup
-  const int32_t* base_viol; // [v]         first plan stop the unmodified walk fails at (L if none), -1: over capacity
+  // Slot-major copy for the scan kernel: vehicles sorted by plan length (vs = sorted index), element
+  // [k * n_veh + vs] is plan stop k of that vehicle, so that a warp of consecutive vehicles loads
+  // coalesced and runs the same trip counts.  perm[vs] = original vehicle index.
+  const int32_t* perm;
+  const int32_t* m_node;    // [k][vs] vertex of plan stop k
+  const int32_t* m_req;     // [k][vs] request-table row
+  const int8_t* m_pod;      // [k][vs]
+  const int8_t* m_partner;  // [k][vs] plan index of the pickup belonging to a drop-off, -1 if on board
+  // per-vehicle precomputation (plan_prep_kernel): plan segment times and the walk of the unmodified
+  // plan, which is the common prefix of every candidate
+  double* m_seg;            // [k][vs]  tt(previous stop or start vertex -> stop k)
+  double* m_base_t;         // [k][vs]  t before plan stop k, k = 0..L
+  double* m_base_c;         // [k][vs]  c before plan stop k
+  double* m_base_cld;       // [k][vs]  Cld assigned when plan stop k is a pickup
+  int32_t* m_base_viol;     // [vs]     first plan stop the unmodified walk fails at (L if none), -1: over capacity
   int directed;
 };
 
@@ -173,57 +182,6 @@ __device__ int eval_candidate(const Pair& p, const PlanView& pv, int a, int b, d
   return -1;
 }
 
-__global__ void insertion_scan_kernel(PlanView pv, DistView dv, int n_new, const int32_t* new_rows, double* cmin_out,
-                                      unsigned long long* n_cand) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t total = (int64_t)pv.n_veh * n_new;
-  unsigned long long evaluated = 0;
-  if (idx < total) {
-    const int v = (int)(idx / n_new), r = (int)(idx % n_new);
-    Pair p;
-    load_pair(p, pv, dv, v, new_rows[r]);
-    const double inf = __longlong_as_double(0x7ff0000000000000LL);
-    double cmin = inf;
-    for (int a = 0; a <= p.L; ++a)
-      for (int b = a; b <= p.L; ++b) {
-        double c;
-        if (eval_candidate(p, pv, a, b, inf, &c) < 0 && c < cmin) cmin = c;
-        ++evaluated;
-      }
-    cmin_out[idx] = cmin;
-  }
-  for (int off = 16; off > 0; off >>= 1) evaluated += __shfl_down_sync(0xffffffffu, evaluated, off);
-  if ((threadIdx.x & 31) == 0 && evaluated) atomicAdd(n_cand, evaluated);
-}
-
-__global__ void insertion_fold_kernel(PlanView pv, DistView dv, int n_new, const int32_t* new_rows, const double* cmin,
-                                      int32_t* best_veh, int32_t* best_i, int32_t* best_j, double* best_dc) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n_new) return;
-  const double inf = __longlong_as_double(0x7ff0000000000000LL);
-  double dc = inf;                   // dc_ = np.inf (:1452)
-  int wv = -1, wi = -1, wj = -1;
-  for (int v = 0; v < pv.n_veh; ++v) {
-    const double c0 = pv.cost[v];
-    const double cm = cmin[(int64_t)v * n_new + r];
-    if (cm == inf || cm > c0 + dc) continue;   // no candidate of this vehicle can pass `c > C`
-    Pair p;
-    load_pair(p, pv, dv, v, new_rows[r]);
-    int viol = -1;
-    for (int i = 0; i <= p.L; ++i) {                         // (:1466-1482)
-      for (int j = i + 1; j <= p.L + 1; ++j) {
-        double c;
-        viol = eval_candidate(p, pv, i, j - 1, c0 + dc, &c);
-        if (viol < 0) { dc = c - c0; wv = v; wi = i; wj = j; }
-        if (viol > 0) break;
-      }
-      if (viol == 2) break;
-    }
-  }
-  best_veh[r] = wv; best_i[r] = wi; best_j[r] = wj; best_dc[r] = dc;
-}
-
-
 // One stop of test_constraints_get_cost's walk (lib/Agents.py:1523-1567) without the bound test.
 struct Walk { double t, c; int n; };
 __device__ __forceinline__ int walk_stop(Walk& w, double dt, int pod, int rq, double T, const PlanView& pv,
@@ -253,54 +211,62 @@ __device__ __forceinline__ int walk_stop(Walk& w, double dt, int pod, int rq, do
   return -1;
 }
 
-// Per vehicle: plan segment times and the walk of the unmodified plan.
-__global__ void plan_prep_kernel(PlanView pv, DistView dv, double* seg, double* base_t, double* base_c, double* base_cld,
-                                 int32_t* base_viol) {
-  const int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= pv.n_veh) return;
-  const int s0 = pv.off[v], L = pv.off[v + 1] - s0;
+// Per vehicle: plan segment times and the walk of the unmodified plan (slot-major outputs).
+__global__ void plan_prep_kernel(PlanView pv, DistView dv) {
+  const int vs = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nv = pv.n_veh;
+  if (vs >= nv) return;
+  const int v = pv.perm[vs];
+  const int L = pv.off[v + 1] - pv.off[v];
   int prev = pv.node[v];
   for (int k = 0; k < L; ++k) {
-    const int nd = pv.s_node[s0 + k];
-    seg[s0 + k] = (prev == nd) ? 0.0 : dv.at(prev, nd);
+    const int nd = pv.m_node[k * nv + vs];
+    pv.m_seg[k * nv + vs] = (prev == nd) ? 0.0 : dv.at(prev, nd);
     prev = nd;
   }
   int occ = pv.onboard[v], viol_at = L;
   bool over = occ > pv.cap[v];
-  for (int k = 0; k < L; ++k) { occ += pv.s_pod[s0 + k]; if (occ > pv.cap[v]) over = true; }
+  for (int k = 0; k < L; ++k) { occ += pv.m_pod[k * nv + vs]; if (occ > pv.cap[v]) over = true; }
   Walk w{0.0 + pv.delay[v], 0.0, pv.onboard[v]};
   const double T = pv.clock[v];
   for (int k = 0; k <= L; ++k) {
-    base_t[s0 + v + k] = w.t;
-    base_c[s0 + v + k] = w.c;
+    pv.m_base_t[k * nv + vs] = w.t;
+    pv.m_base_c[k * nv + vs] = w.c;
     if (k == L || viol_at < L) continue;
-    const int pod = pv.s_pod[s0 + k], rq = pv.s_req[s0 + k];
+    const int pod = pv.m_pod[k * nv + vs], rq = pv.m_req[k * nv + vs];
     double cld_drop = pv.q_cld[rq];
-    const int pk = pv.partner[s0 + k];
-    if (pk >= 0) cld_drop = base_cld[s0 + pk];
+    const int pk = pv.m_partner[k * nv + vs];
+    if (pk >= 0) cld_drop = pv.m_base_cld[pk * nv + vs];
     double cld_set = 0.0;
-    if (walk_stop(w, seg[s0 + k], pod, rq, T, pv, cld_drop, &cld_set) >= 0) viol_at = k;
-    base_cld[s0 + k] = cld_set;
+    if (walk_stop(w, pv.m_seg[k * nv + vs], pod, rq, T, pv, cld_drop, &cld_set) >= 0) viol_at = k;
+    pv.m_base_cld[k * nv + vs] = cld_set;
   }
-  base_viol[v] = over ? -1 : viol_at;
+  pv.m_base_viol[vs] = over ? -1 : viol_at;
 }
 
-// Scan, second version: the unmodified-plan prefix is shared (precomputed per vehicle), the state
-// "pickup inserted after a stops, b-a further stops served" is advanced incrementally over b, and only
-// the tail after the drop-off is re-walked per candidate.  Same arithmetic, same operation order per
-// candidate as eval_candidate; only successes matter here (cmin), so no viol bookkeeping.
-__global__ void __launch_bounds__(128) insertion_scan2_kernel(PlanView pv, DistView dv, int n_new, const int32_t* __restrict__ new_rows,
-                                                              const double* __restrict__ od_tt, double* __restrict__ cmin_out,
-                                                              unsigned long long* n_cand) {
+// Scan: one thread per (request, vehicle) pair, VEHICLES fastest and sorted by plan length.
+//   * On an undirected map the matrix is symmetric, so every travel time the pair needs lives in the two
+//     matrix rows of the request (origin row, destination row): all warps working on a request gather
+//     from the same 2 x 4n bytes, which stay in L2 -- DRAM sees each request row once instead of one
+//     32-byte sector per gathered element.
+//   * The unmodified-plan prefix is shared (precomputed per vehicle), the state "pickup inserted after a
+//     stops, b-a further stops served" is advanced incrementally over b, and only the tail after the
+//     drop-off is re-walked per candidate.  Arithmetic and operation order per candidate are those of
+//     eval_candidate; only successes matter here (the pair's smallest total cost), so no viol codes.
+__global__ void __launch_bounds__(128) insertion_scan_kernel(PlanView pv, DistView dv, int n_new,
+                                                             const int32_t* __restrict__ new_rows, double* __restrict__ cmin_out,
+                                                             unsigned long long* n_cand) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t total = (int64_t)pv.n_veh * n_new;
+  const int nv = pv.n_veh;
+  const int64_t total = (int64_t)nv * n_new;
   if (idx >= total) return;
-  const int v = (int)(idx / n_new), r = (int)(idx % n_new);
+  const int r = (int)(idx / nv), vs = (int)(idx % nv);
+  const int v = pv.perm[vs];
   const double inf = __longlong_as_double(0x7ff0000000000000LL);
-  const int s0 = pv.off[v], L = pv.off[v + 1] - s0;
+  const int L = pv.off[v + 1] - pv.off[v];
   if (r == 0) atomicAdd(n_cand, (unsigned long long)((L + 1) * (L + 2) / 2) * (unsigned long long)n_new);
   double cmin = inf;
-  const int bviol = pv.base_viol[v];
+  const int bviol = pv.m_base_viol[vs];
   if (bviol >= 0) {
     const int rq = new_rows[r];
     const int o = pv.q_o[rq], d = pv.q_d[rq];
@@ -308,31 +274,36 @@ __global__ void __launch_bounds__(128) insertion_scan2_kernel(PlanView pv, DistV
     const double T = pv.clock[v];
     double to_o[MAXL + 1], to_d[MAXL + 1], from_o[MAXL], from_d[MAXL], cld_cur[MAXL];
     {
-      int prev = pv.node[v];
-      to_o[0] = (prev == o) ? 0.0 : dv.at(prev, o);
-      to_d[0] = (prev == d) ? 0.0 : dv.at(prev, d);
+      const int start = pv.node[v];
+      if (pv.directed) {
+        to_o[0] = (start == o) ? 0.0 : dv.at(start, o);
+        to_d[0] = (start == d) ? 0.0 : dv.at(start, d);
+      } else {
+        to_o[0] = (start == o) ? 0.0 : dv.at(o, start);
+        to_d[0] = (start == d) ? 0.0 : dv.at(d, start);
+      }
       for (int k = 0; k < L; ++k) {
-        const int nd = pv.s_node[s0 + k];
-        to_o[k + 1] = (nd == o) ? 0.0 : dv.at(nd, o);
-        to_d[k + 1] = (nd == d) ? 0.0 : dv.at(nd, d);
+        const int nd = pv.m_node[k * nv + vs];
+        from_o[k] = (o == nd) ? 0.0 : dv.at(o, nd);
+        from_d[k] = (d == nd) ? 0.0 : dv.at(d, nd);
         if (pv.directed) {
-          from_o[k] = (o == nd) ? 0.0 : dv.at(o, nd);
-          from_d[k] = (d == nd) ? 0.0 : dv.at(d, nd);
+          to_o[k + 1] = (nd == o) ? 0.0 : dv.at(nd, o);
+          to_d[k + 1] = (nd == d) ? 0.0 : dv.at(nd, d);
         } else {                       // undirected graph: the matrix is symmetric
-          from_o[k] = to_o[k + 1];
-          from_d[k] = to_d[k + 1];
+          to_o[k + 1] = from_o[k];
+          to_d[k + 1] = from_d[k];
         }
       }
     }
-    const double od = od_tt[r];
+    const double od = (o == d) ? 0.0 : dv.at(o, d);
     int occ_before = pv.onboard[v];    // occupancy before plan stop a in the unmodified plan
     for (int a = 0; a <= L && a <= bviol; ++a) {
       if (a > 0) {
-        cld_cur[a - 1] = pv.base_cld[s0 + a - 1];
-        occ_before += pv.s_pod[s0 + a - 1];
+        cld_cur[a - 1] = pv.m_base_cld[(a - 1) * nv + vs];
+        occ_before += pv.m_pod[(a - 1) * nv + vs];
       }
       if (occ_before + 1 > K) continue;
-      Walk S{pv.base_t[s0 + v + a], pv.base_c[s0 + v + a], occ_before};
+      Walk S{pv.m_base_t[a * nv + vs], pv.m_base_c[a * nv + vs], occ_before};
       double cld_new = 0.0;
       if (walk_stop(S, to_o[a], 1, rq, T, pv, 0.0, &cld_new) >= 0) continue;   // late pickup
       int occ_after = occ_before;      // occupancy of the unmodified plan after stop b-1
@@ -343,37 +314,30 @@ __global__ void __launch_bounds__(128) insertion_scan2_kernel(PlanView pv, DistV
         if (walk_stop(W, b == a ? od : to_d[b], -1, rq, T, pv, cld_new, &dummy) < 0) {
           bool ok = true;
           for (int k = b; k < L; ++k) {
-            const int pod = pv.s_pod[s0 + k], q = pv.s_req[s0 + k];
+            const int pod = pv.m_pod[k * nv + vs], q = pv.m_req[k * nv + vs];
             double cld_drop = 0.0;
-            if (pod < 0) { const int pk = pv.partner[s0 + k]; cld_drop = pk >= 0 ? cld_cur[pk] : pv.q_cld[q]; }
-            if (walk_stop(W, k == b ? from_d[k] : pv.seg[s0 + k], pod, q, T, pv, cld_drop, &cld_cur[k]) >= 0) { ok = false; break; }
+            if (pod < 0) { const int pk = pv.m_partner[k * nv + vs]; cld_drop = pk >= 0 ? cld_cur[pk] : pv.q_cld[q]; }
+            if (walk_stop(W, k == b ? from_d[k] : pv.m_seg[k * nv + vs], pod, q, T, pv, cld_drop, &cld_cur[k]) >= 0) { ok = false; break; }
           }
           if (ok && W.c < cmin) cmin = W.c;
         }
         // ---- serve plan stop b with the new rider on board
         if (b == L) break;
-        const int pod = pv.s_pod[s0 + b], q = pv.s_req[s0 + b];
+        const int pod = pv.m_pod[b * nv + vs], q = pv.m_req[b * nv + vs];
         occ_after += pod;
         if (occ_after + 1 > K) break;                   // over capacity for every larger b
         double cld_drop = 0.0;
-        if (pod < 0) { const int pk = pv.partner[s0 + b]; cld_drop = pk >= 0 ? cld_cur[pk] : pv.q_cld[q]; }
-        if (walk_stop(S, b == a ? from_o[b] : pv.seg[s0 + b], pod, q, T, pv, cld_drop, &cld_cur[b]) >= 0) break;
+        if (pod < 0) { const int pk = pv.m_partner[b * nv + vs]; cld_drop = pk >= 0 ? cld_cur[pk] : pv.q_cld[q]; }
+        if (walk_stop(S, b == a ? from_o[b] : pv.m_seg[b * nv + vs], pod, q, T, pv, cld_drop, &cld_cur[b]) >= 0) break;
       }
     }
   }
-  cmin_out[idx] = cmin;
+  cmin_out[(int64_t)r * nv + v] = cmin;
 }
 
-__global__ void od_gather_kernel(PlanView pv, DistView dv, int n_new, const int32_t* new_rows, double* od_tt) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n_new) return;
-  const int o = pv.q_o[new_rows[r]], d = pv.q_d[new_rows[r]];
-  od_tt[r] = (o == d) ? 0.0 : dv.at(o, d);
-}
-
-// Fold, second version: one WARP per request.  Lanes read the smallest costs of 32 consecutive
+// Fold: one WARP per request.  Lanes read the smallest costs of 32 consecutive
 // vehicles; only flagged vehicles are re-scanned (by their lane) in vehicle order with the running bound.
-__global__ void insertion_fold2_kernel(PlanView pv, DistView dv, int n_new, const int32_t* new_rows, const double* cmin,
+__global__ void insertion_fold_kernel(PlanView pv, DistView dv, int n_new, const int32_t* new_rows, const double* cmin,
                                        int32_t* best_veh, int32_t* best_i, int32_t* best_j, double* best_dc) {
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -384,7 +348,7 @@ __global__ void insertion_fold2_kernel(PlanView pv, DistView dv, int n_new, cons
   for (int base = 0; base < pv.n_veh; base += 32) {
     const int v = base + lane;
     double cm = inf, c0 = 0.0;
-    if (v < pv.n_veh) { cm = cmin[(int64_t)v * n_new + r]; c0 = pv.cost[v]; }
+    if (v < pv.n_veh) { cm = cmin[(int64_t)r * pv.n_veh + v]; c0 = pv.cost[v]; }
     unsigned mask = __ballot_sync(0xffffffffu, cm != inf && !(cm > c0 + dc));
     while (mask) {
       const int l = __ffs(mask) - 1;
@@ -420,9 +384,9 @@ struct LegacyDev {
   int8_t* s_pod = nullptr;
   int32_t *q_o = nullptr, *q_d = nullptr;
   double *q_cep = nullptr, *q_clp = nullptr, *q_cld = nullptr, *q_ts = nullptr, *q_tr = nullptr, *q_pwt = nullptr;
-  int8_t* partner = nullptr;
-  double *seg = nullptr, *base_t = nullptr, *base_c = nullptr, *base_cld = nullptr;
-  int32_t* base_viol = nullptr;
+  int32_t *perm = nullptr, *m_node = nullptr, *m_req = nullptr, *m_base_viol = nullptr;
+  int8_t *m_pod = nullptr, *m_partner = nullptr;
+  double *m_seg = nullptr, *m_base_t = nullptr, *m_base_c = nullptr, *m_base_cld = nullptr;
   drs_insertion_params prm{1.5, 1.0, 1.5, 3.0};
 };
 
@@ -430,8 +394,8 @@ void drs_tick_free_plans(drs_tick* t) {
   LegacyDev* d = t->legacy;
   if (!d) return;
   void* ptrs[] = {d->node, d->onboard, d->cap, d->off, d->s_node, d->s_req, d->delay, d->clock, d->cost, d->s_pod,
-                  d->q_o, d->q_d, d->q_cep, d->q_clp, d->q_cld, d->q_ts, d->q_tr, d->q_pwt, d->partner, d->seg, d->base_t,
-                  d->base_c, d->base_cld, d->base_viol};
+                  d->q_o, d->q_d, d->q_cep, d->q_clp, d->q_cld, d->q_ts, d->q_tr, d->q_pwt, d->perm, d->m_node, d->m_req,
+                  d->m_base_viol, d->m_pod, d->m_partner, d->m_seg, d->m_base_t, d->m_base_c, d->m_base_cld};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete d;
@@ -476,17 +440,32 @@ extern "C" int drs_tick_set_plans(drs_tick* t, const drs_plan_batch* b, const dr
       (rc = drs_upload(&d.q_cld, q->Cld, nq, st)) || (rc = drs_upload(&d.q_ts, q->Ts, nq, st)) ||
       (rc = drs_upload(&d.q_tr, q->Tr, nq, st)) || (rc = drs_upload(&d.q_pwt, q->pwt, nq, st)))
     return rc;
-  // plan index of the pickup that belongs to each drop-off (-1: the rider is already on board)
-  std::vector<int8_t> partner(std::max(nstops, 1), -1);
-  for (int v = 0; v < nv; ++v)
-    for (int s = b->stop_off[v]; s < b->stop_off[v + 1]; ++s)
-      if (b->stop_pod[s] < 0)
-        for (int m = b->stop_off[v]; m < s; ++m)
-          if (b->stop_req[m] == b->stop_req[s] && b->stop_pod[m] > 0) partner[s] = (int8_t)(m - b->stop_off[v]);
-  if ((rc = drs_upload(&d.partner, partner.data(), nstops, st))) return rc;
-  void** scratch[] = {(void**)&d.seg, (void**)&d.base_t, (void**)&d.base_c, (void**)&d.base_cld, (void**)&d.base_viol};
-  const size_t bytes[] = {sizeof(double) * std::max(nstops, 1), sizeof(double) * (nstops + nv + 1), sizeof(double) * (nstops + nv + 1),
-                          sizeof(double) * std::max(nstops, 1), sizeof(int32_t) * std::max(nv, 1)};
+  // slot-major copy, vehicles stably sorted by plan length
+  std::vector<int32_t> perm(std::max(nv, 1));
+  for (int v = 0; v < nv; ++v) perm[v] = v;
+  std::stable_sort(perm.begin(), perm.begin() + nv, [&](int x, int y) {
+    return (b->stop_off[x + 1] - b->stop_off[x]) < (b->stop_off[y + 1] - b->stop_off[y]);
+  });
+  const size_t slots = (size_t)(MAXL + 1) * std::max(nv, 1);
+  std::vector<int32_t> m_node(slots, 0), m_req(slots, 0);
+  std::vector<int8_t> m_pod(slots, 0), m_partner(slots, -1);
+  for (int vs = 0; vs < nv; ++vs) {
+    const int v = perm[vs], s0 = b->stop_off[v], L = b->stop_off[v + 1] - s0;
+    for (int k = 0; k < L; ++k) {
+      const size_t at = (size_t)k * nv + vs;
+      m_node[at] = b->stop_node[s0 + k]; m_req[at] = b->stop_req[s0 + k]; m_pod[at] = b->stop_pod[s0 + k];
+      if (b->stop_pod[s0 + k] < 0)   // plan index of the pickup that belongs to this drop-off (-1: rider on board)
+        for (int m = 0; m < k; ++m)
+          if (b->stop_req[s0 + m] == b->stop_req[s0 + k] && b->stop_pod[s0 + m] > 0) m_partner[at] = (int8_t)m;
+    }
+  }
+  if ((rc = drs_upload(&d.perm, perm.data(), nv, st)) || (rc = drs_upload(&d.m_node, m_node.data(), slots, st)) ||
+      (rc = drs_upload(&d.m_req, m_req.data(), slots, st)) || (rc = drs_upload(&d.m_pod, m_pod.data(), slots, st)) ||
+      (rc = drs_upload(&d.m_partner, m_partner.data(), slots, st)))
+    return rc;
+  void** scratch[] = {(void**)&d.m_seg, (void**)&d.m_base_t, (void**)&d.m_base_c, (void**)&d.m_base_cld, (void**)&d.m_base_viol};
+  const size_t bytes[] = {sizeof(double) * slots, sizeof(double) * slots, sizeof(double) * slots, sizeof(double) * slots,
+                          sizeof(int32_t) * std::max(nv, 1)};
   for (int i = 0; i < 5; ++i) {
     if (*scratch[i]) { cudaFree(*scratch[i]); *scratch[i] = nullptr; }
     DRS_CUDA(cudaMalloc(scratch[i], bytes[i]));
@@ -515,18 +494,18 @@ extern "C" int drs_tick_insertion_eval(drs_tick* t, int32_t n_new, const int32_t
   cudaStream_t st = t->g->stream;
   PlanView pv{d.n_veh, d.node, d.onboard, d.cap, d.off, d.s_node, d.s_req, d.delay, d.clock, d.cost, d.s_pod,
               d.q_o, d.q_d, d.q_cep, d.q_clp, d.q_cld, d.q_ts, d.q_tr, d.q_pwt, d.prm,
-              d.seg, d.partner, d.base_t, d.base_c, d.base_cld, d.base_viol, t->g->directed};
+              d.perm, d.m_node, d.m_req, d.m_pod, d.m_partner, d.m_seg, d.m_base_t, d.m_base_c, d.m_base_cld, d.m_base_viol,
+              t->g->directed};
   DistView dv{t->g->d_dist, t->g->ld, t->g->mode};
   int32_t *d_rows = nullptr, *d_bv = nullptr, *d_bi = nullptr, *d_bj = nullptr;
-  double *d_cmin = nullptr, *d_dc = nullptr, *d_od = nullptr;
+  double *d_cmin = nullptr, *d_dc = nullptr;
   unsigned long long* d_ncand = nullptr;
-  auto cleanup = [&]() { cudaFree(d_rows); cudaFree(d_bv); cudaFree(d_bi); cudaFree(d_bj); cudaFree(d_cmin); cudaFree(d_dc); cudaFree(d_ncand); cudaFree(d_od); };
+  auto cleanup = [&]() { cudaFree(d_rows); cudaFree(d_bv); cudaFree(d_bi); cudaFree(d_bj); cudaFree(d_cmin); cudaFree(d_dc); cudaFree(d_ncand); };
   int rc = drs_upload(&d_rows, new_rows, n_new, st);
   if (rc) { cleanup(); return rc; }
   if (cudaMalloc((void**)&d_bv, sizeof(int32_t) * n_new) != cudaSuccess || cudaMalloc((void**)&d_bi, sizeof(int32_t) * n_new) != cudaSuccess ||
       cudaMalloc((void**)&d_bj, sizeof(int32_t) * n_new) != cudaSuccess || cudaMalloc((void**)&d_dc, sizeof(double) * n_new) != cudaSuccess ||
       cudaMalloc((void**)&d_cmin, sizeof(double) * std::max<int64_t>(total, 1)) != cudaSuccess ||
-      cudaMalloc((void**)&d_od, sizeof(double) * n_new) != cudaSuccess ||
       cudaMalloc((void**)&d_ncand, sizeof(unsigned long long)) != cudaSuccess) {
     cleanup();
     drs_set_error("drs_tick_insertion_eval: cudaMalloc failed");
@@ -536,14 +515,13 @@ extern "C" int drs_tick_insertion_eval(drs_tick* t, int32_t n_new, const int32_t
   DrsTimer tm_scan(st), tm_fold(st);
   tm_scan.start();
   if (total > 0) {
-    plan_prep_kernel<<<(d.n_veh + 127) / 128, 128, 0, st>>>(pv, dv, d.seg, d.base_t, d.base_c, d.base_cld, d.base_viol);
-    od_gather_kernel<<<(n_new + 127) / 128, 128, 0, st>>>(pv, dv, n_new, d_rows, d_od);
-    insertion_scan2_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(pv, dv, n_new, d_rows, d_od, d_cmin, d_ncand);
-    drs_count_launch(3);
+    plan_prep_kernel<<<(d.n_veh + 127) / 128, 128, 0, st>>>(pv, dv);
+    insertion_scan_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(pv, dv, n_new, d_rows, d_cmin, d_ncand);
+    drs_count_launch(2);
   }
   tm_scan.stop();
   tm_fold.start();
-  insertion_fold2_kernel<<<(n_new * 32 + 127) / 128, 128, 0, st>>>(pv, dv, n_new, d_rows, d_cmin, d_bv, d_bi, d_bj, d_dc);
+  insertion_fold_kernel<<<(n_new * 32 + 127) / 128, 128, 0, st>>>(pv, dv, n_new, d_rows, d_cmin, d_bv, d_bi, d_bj, d_dc);
   drs_count_launch();
   tm_fold.stop();
   unsigned long long ncand = 0;

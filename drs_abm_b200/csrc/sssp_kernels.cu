@@ -23,7 +23,6 @@
 
 namespace {
 
-constexpr int SSSP_THREADS = 256;
 
 template <typename T> struct Dist;
 template <> struct Dist<float> {
@@ -43,7 +42,7 @@ template <> struct Dist<int> {
 
 struct Entry { int v; int key; };   // key = distance bits at push time
 
-template <typename T>
+template <typename T, int SSSP_THREADS>
 __global__ void __launch_bounds__(SSSP_THREADS) sssp_batch_kernel(
     int n, const int32_t* __restrict__ out_ptr, const int2* __restrict__ arcs, T* dist, int64_t ld, int64_t row_stride,
     const int32_t* __restrict__ sources, int nsrc, Entry* queues, int cap, T delta, int* overflow) {
@@ -142,13 +141,42 @@ __global__ void pack_arcs_kernel(int narcs, const int32_t* col, const float* w, 
   if (a < narcs) arcs[a] = make_int2(col[a], __float_as_int(w[a]));
 }
 
+int sssp_threads() {   // CTA size: tuning knob (64 / 128 / 256), default chosen by measurement on B200
+  static int t = 0;
+  if (!t) {
+    const char* e = getenv("DRS_SSSP_THREADS");
+    t = e ? atoi(e) : 128;
+    if (t != 64 && t != 128 && t != 256) t = 128;
+  }
+  return t;
+}
+
+template <typename T, int TH>
+int sssp_occupancy() {
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sssp_batch_kernel<T, TH>, TH, 0);
+  return per_sm;
+}
+
+template <typename T>
+int sssp_grid(int sms, int nsrc) {
+  const int th = sssp_threads();
+  const int per_sm = th == 64 ? sssp_occupancy<T, 64>() : th == 128 ? sssp_occupancy<T, 128>() : sssp_occupancy<T, 256>();
+  return std::max(1, std::min(nsrc, sms * std::max(per_sm, 1)));
+}
+
 template <typename T>
 int sssp_run(const drs_graph* g, int nsrc, const int32_t* sources_dev, T* dist, int64_t ld, int64_t row_stride, double delta,
              cudaStream_t st, const int2* arcs, Entry* queues, int cap, int grid, int* overflow) {
   T d = (T)delta;
   if (!(d > (T)0)) d = (T)1;
-  sssp_batch_kernel<T><<<grid, SSSP_THREADS, 0, st>>>(g->n, g->d_out_ptr, arcs, dist, ld, row_stride, sources_dev, nsrc, queues,
-                                                       cap, d, overflow);
+  const int th = sssp_threads();
+  if (th == 64)
+    sssp_batch_kernel<T, 64><<<grid, 64, 0, st>>>(g->n, g->d_out_ptr, arcs, dist, ld, row_stride, sources_dev, nsrc, queues, cap, d, overflow);
+  else if (th == 128)
+    sssp_batch_kernel<T, 128><<<grid, 128, 0, st>>>(g->n, g->d_out_ptr, arcs, dist, ld, row_stride, sources_dev, nsrc, queues, cap, d, overflow);
+  else
+    sssp_batch_kernel<T, 256><<<grid, 256, 0, st>>>(g->n, g->d_out_ptr, arcs, dist, ld, row_stride, sources_dev, nsrc, queues, cap, d, overflow);
   drs_count_launch();
   DRS_CUDA(cudaGetLastError());
   return DRS_OK;
@@ -173,11 +201,9 @@ extern "C" int drs_sssp_batch_dev(const drs_graph* g, int32_t mode, int32_t nsrc
     delta = g->m ? 6.0 * s / g->m : 1.0;
   }
   drs_graph* gm = const_cast<drs_graph*>(g);   // scratch buffers are cached on the handle
-  int sms = 148, per_sm = 1;
+  int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g->device);
-  if (mode == DRS_MODE_F32) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sssp_batch_kernel<float>, SSSP_THREADS, 0);
-  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sssp_batch_kernel<int>, SSSP_THREADS, 0);
-  const int grid = std::max(1, std::min(nsrc, sms * std::max(per_sm, 1)));
+  const int grid = mode == DRS_MODE_F32 ? sssp_grid<float>(sms, nsrc) : sssp_grid<int>(sms, nsrc);
   if (!gm->sssp_arcs) DRS_CUDA(cudaMalloc(&gm->sssp_arcs, sizeof(int2) * std::max(g->narcs, 1)));
   if (!gm->sssp_arcs_valid && g->narcs) {
     pack_arcs_kernel<<<(g->narcs + 255) / 256, 256, 0, st>>>(g->narcs, g->d_out_col, g->d_out_w, (int2*)gm->sssp_arcs);
@@ -189,7 +215,8 @@ extern "C" int drs_sssp_batch_dev(const drs_graph* g, int32_t mode, int32_t nsrc
   int* d_overflow = nullptr;
   DRS_CUDA(cudaMalloc((void**)&d_sources, sizeof(int32_t) * nsrc + sizeof(int)));
   d_overflow = reinterpret_cast<int*>(d_sources + nsrc);
-  int cap = std::max(4096, g->narcs + 1);
+  // queue capacity per CTA: frontiers of road networks are a few thousand entries; overflow is detected and retried
+  int cap = std::max(4096, std::min(g->narcs + 1, 65536));
   int rc = DRS_OK;
   for (int attempt = 0; attempt < 3 && rc == DRS_OK; ++attempt) {
     const size_t need = sizeof(Entry) * 4 * (size_t)cap * grid;
