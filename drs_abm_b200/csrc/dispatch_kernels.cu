@@ -212,10 +212,12 @@ __global__ void rv_filter_kernel(TickDev tk, DistView dv, double T, int8_t* stat
   bool survive = false;
   int v = 0, r = 0;
   if (idx < total) {
-    v = (int)(idx / tk.n_req);
-    r = (int)(idx % tk.n_req);
+    // vehicles fastest (sorted by plan length): on an undirected map tt(veh -> origin) is read from the
+    // ORIGIN's matrix row, which all warps working on this request share (L2 resident)
+    r = (int)(idx / tk.n_veh);
+    v = tk.v_perm[(int)(idx % tk.n_veh)];
     const int vn = tk.v_node[v], o = tk.r_o[r];
-    const double tvo = (vn == o) ? 0.0 : dv.at(vn, o);
+    const double tvo = (vn == o) ? 0.0 : (tk.directed ? dv.at(vn, o) : dv.at(o, vn));
     int st;
     if (T + tvo > tk.r_ubp[r]) {               // lib/Optimization.py:183-186
       st = DRS_RV_SKIPPED;
@@ -236,7 +238,7 @@ __global__ void rv_filter_kernel(TickDev tk, DistView dv, double T, int8_t* stat
       }
       if (st < 0) survive = true;
     }
-    if (!survive) status[idx] = (int8_t)st;
+    if (!survive) status[(int64_t)v * tk.n_req + r] = (int8_t)st;
   }
   const unsigned m = __ballot_sync(0xffffffffu, survive);
   if (m) {
@@ -319,7 +321,7 @@ extern "C" int drs_tick_destroy(drs_tick* t) {
   tick_free_results(t);
   drs_tick_free_plans(t);
   TickDev& d = t->dev;
-  void* ptrs[] = {d.v_node, d.v_cap, d.v_pax, d.v_off, d.v_delay, d.s_node, d.s_rid, d.s_pod, d.s_prev, d.s_lb, d.s_ub,
+  void* ptrs[] = {d.v_perm, d.v_node, d.v_cap, d.v_pax, d.v_off, d.v_delay, d.s_node, d.s_rid, d.s_pod, d.s_prev, d.s_lb, d.s_ub,
                   d.r_rid, d.r_o, d.r_d, d.r_lbp, d.r_ubp, d.r_lbd, d.r_ubd};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -355,6 +357,13 @@ extern "C" int drs_tick_set_vehicles(drs_tick* t, const drs_vehicle_batch* b) {
   cudaStream_t st = t->g->stream;
   TickDev& d = t->dev;
   int rc;
+  std::vector<int32_t> perm(std::max(nv, 1));
+  for (int v = 0; v < nv; ++v) perm[v] = v;
+  std::stable_sort(perm.begin(), perm.begin() + nv, [&](int x, int y) {
+    return (b->stop_off[x + 1] - b->stop_off[x]) < (b->stop_off[y + 1] - b->stop_off[y]);
+  });
+  if ((rc = upload(&d.v_perm, perm.data(), nv, st))) return rc;
+  d.directed = t->g->directed;
   if ((rc = upload(&d.v_node, b->start_node, nv, st)) || (rc = upload(&d.v_delay, b->start_delay, nv, st)) ||
       (rc = upload(&d.v_cap, b->capacity, nv, st)) || (rc = upload(&d.v_pax, b->onboard, nv, st)) ||
       (rc = upload(&d.v_off, b->stop_off, nv ? nv + 1 : 0, st)) || (rc = upload(&d.s_node, b->stop_node, nstops, st)) ||

@@ -10,6 +10,8 @@ struct TickDev {
   int32_t *s_node = nullptr, *s_rid = nullptr;
   int8_t *s_pod = nullptr, *s_prev = nullptr;
   double *s_lb = nullptr, *s_ub = nullptr;
+  int32_t* v_perm = nullptr;   // vehicles sorted by number of planned stops (uniform work per warp)
+  int directed = 0;
   // requests
   int n_req = 0;
   int32_t *r_rid = nullptr, *r_o = nullptr, *r_d = nullptr;

@@ -230,33 +230,73 @@ __global__ void fw_scatter_kernel(T* local, int64_t ld, int row0, int nrows, con
 }
 
 // Canonical predecessor edge: among in-arcs (u->t, w, eid) minimise
-// (dist[s,u] + w, dist[s,u], eid) lexicographically.
+// (dist[s,u] + w, dist[s,u], eid) lexicographically.  One thread per target t keeps t's in-arcs in
+// registers and sweeps PRED_ROWS source rows, so the CSR is read once per 32 rows instead of once per
+// matrix element; row reads are coalesced over t and the neighbour reads hit L1/L2 (neighbours of
+// consecutive vertices are close in a road network).
+constexpr int PRED_ROWS = 32;
+constexpr int PRED_MAXDEG = 6;    // in-arcs held in registers; vertices with more fall back to the CSR loop
 template <typename T>
-__global__ void pred_kernel(const T* __restrict__ local, int64_t ld, int row0, int nrows, int n,
-                            const int32_t* __restrict__ in_ptr, const int32_t* __restrict__ in_src,
-                            const int32_t* __restrict__ in_eid, const float* __restrict__ in_w,
-                            int32_t* __restrict__ pred) {
+__global__ void __launch_bounds__(256) pred_kernel(const T* __restrict__ local, int64_t ld, int row0, int nrows, int n,
+                                                   const int32_t* __restrict__ in_ptr, const int32_t* __restrict__ in_src,
+                                                   const int32_t* __restrict__ in_eid, const float* __restrict__ in_w,
+                                                   int32_t* __restrict__ pred) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int ls = blockIdx.y;
-  if (t >= ld || ls >= nrows) return;
-  const int s = row0 + ls;
-  const T* row = local + (int64_t)ls * ld;
-  int best_e = -1;
-  if (t < n && s < n && t != s && row[t] < Semiring<T>::inf()) {
-    T best_c = Semiring<T>::inf(), best_du = Semiring<T>::inf();
-    const int a1 = in_ptr[t + 1];
-    for (int a = in_ptr[t]; a < a1; ++a) {
-      const int u = in_src[a];
-      const T du = row[u];
-      if (!(du < Semiring<T>::inf())) continue;
-      const T cand = du + (T)in_w[a];
-      const int e = in_eid[a];
-      if (cand < best_c || (cand == best_c && (du < best_du || (du == best_du && e < best_e)))) {
-        best_c = cand; best_du = du; best_e = e;
+  if (t >= ld) return;
+  const int r_begin = blockIdx.y * PRED_ROWS;
+  const int r_end = min(r_begin + PRED_ROWS, nrows);
+  int a0 = 0, deg = 0;
+  if (t < n) { a0 = in_ptr[t]; deg = in_ptr[t + 1] - a0; }
+  int us[PRED_MAXDEG], es[PRED_MAXDEG];
+  T ws[PRED_MAXDEG];
+  const int dreg = min(deg, PRED_MAXDEG);
+#pragma unroll
+  for (int k = 0; k < PRED_MAXDEG; ++k) {
+    us[k] = 0; es[k] = 0; ws[k] = (T)0;
+    if (k < dreg) { us[k] = in_src[a0 + k]; es[k] = in_eid[a0 + k]; ws[k] = (T)in_w[a0 + k]; }
+  }
+  if (deg <= PRED_MAXDEG) {
+    // branch-free body, four rows in flight per thread (the loads of different rows are independent)
+#pragma unroll 4
+    for (int ls = r_begin; ls < r_end; ++ls) {
+      const int s = row0 + ls;
+      const T* row = local + (int64_t)ls * ld;
+      const T dt = row[t];
+      T du[PRED_MAXDEG];
+#pragma unroll
+      for (int k = 0; k < PRED_MAXDEG; ++k) du[k] = (k < dreg) ? row[us[k]] : Semiring<T>::inf();
+      T best_c = Semiring<T>::inf(), best_du = Semiring<T>::inf();
+      int best_e = -1;
+#pragma unroll
+      for (int k = 0; k < PRED_MAXDEG; ++k) {
+        const bool fin = (k < dreg) && (du[k] < Semiring<T>::inf());
+        const T cand = du[k] + ws[k];
+        const bool better = fin && (cand < best_c || (cand == best_c && (du[k] < best_du || (du[k] == best_du && es[k] < best_e))));
+        if (better) { best_c = cand; best_du = du[k]; best_e = es[k]; }
+      }
+      const bool valid = t < n && s < n && t != s && dt < Semiring<T>::inf();
+      pred[(int64_t)ls * ld + t] = valid ? best_e : -1;
+    }
+    return;
+  }
+  for (int ls = r_begin; ls < r_end; ++ls) {   // high-degree vertices: CSR loop
+    const int s = row0 + ls;
+    const T* row = local + (int64_t)ls * ld;
+    int best_e = -1;
+    if (s < n && t != s && row[t] < Semiring<T>::inf()) {
+      T best_c = Semiring<T>::inf(), best_du = Semiring<T>::inf();
+      for (int a = a0; a < a0 + deg; ++a) {
+        const T du = row[in_src[a]];
+        if (!(du < Semiring<T>::inf())) continue;
+        const T cand = du + (T)in_w[a];
+        const int e = in_eid[a];
+        if (cand < best_c || (cand == best_c && (du < best_du || (du == best_du && e < best_e)))) {
+          best_c = cand; best_du = du; best_e = e;
+        }
       }
     }
+    pred[(int64_t)ls * ld + t] = best_e;
   }
-  pred[(int64_t)ls * ld + t] = best_e;
 }
 
 template <typename T>
@@ -378,7 +418,7 @@ extern "C" int drs_pred_build(const drs_graph* g, int32_t mode, const void* loca
               "drs_pred_build: bad shard");
   if (nrows == 0) return DRS_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  dim3 grid((unsigned)((ld + 255) / 256), (unsigned)nrows);
+  dim3 grid((unsigned)((ld + 255) / 256), (unsigned)((nrows + PRED_ROWS - 1) / PRED_ROWS));
   if (mode == DRS_MODE_F32)
     pred_kernel<float><<<grid, 256, 0, st>>>((const float*)local_dev, ld, row0, nrows, g->n, g->d_in_ptr,
                                              g->d_in_src, g->d_in_eid, g->d_in_w, pred_local_dev);
