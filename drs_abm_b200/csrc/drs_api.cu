@@ -157,6 +157,7 @@ extern "C" int drs_graph_destroy(drs_graph* g) {
     if (p) cudaFree(p);
   if (g->sssp_queues) cudaFree(g->sssp_queues);
   if (g->sssp_arcs) cudaFree(g->sssp_arcs);
+  if (g->sssp_sources) cudaFree(g->sssp_sources);
   if (g->stream) cudaStreamDestroy(g->stream);
   delete g;
   return DRS_OK;

@@ -72,6 +72,8 @@ struct drs_graph {
   size_t sssp_queue_bytes = 0;
   void* sssp_arcs = nullptr;
   bool sssp_arcs_valid = false;
+  int32_t* sssp_sources = nullptr;   // nsrc source ids followed by the overflow flag
+  int sssp_sources_cap = 0;
 
   double prof_ms[4] = {0, 0, 0, 0};   // last build, by phase (drs_apsp_last_profile)
   int prof_rounds = 0;

@@ -40,9 +40,15 @@ template <> struct Dist<int> {
   static __device__ __forceinline__ int next_theta(int dmin, int delta) { return (dmin / delta + 1) * delta; }
 };
 
-struct Entry { int v; int key; };   // key = distance bits at push time
+struct Entry { int v; int key; };   // v = vertex | (source slot << 24); key = distance bits at push time
+constexpr int SSSP_D = 4;            // arcs per entry handled in registers (road networks: degree <= 4 almost everywhere)
+constexpr int SLOT_SHIFT = 24;
+constexpr int VERTEX_MASK = (1 << SLOT_SHIFT) - 1;
 
-template <typename T, int SSSP_THREADS>
+// One CTA advances SSSP_S sources in lock step: their wavefronts pass the same distance buckets at the
+// same time, so one near queue / far pile / theta serves all of them and every barrier and dependent L2
+// round trip of an iteration is shared by SSSP_S searches (the kernel is latency bound, not bandwidth bound).
+template <typename T, int SSSP_THREADS, int SSSP_S>
 __global__ void __launch_bounds__(SSSP_THREADS) sssp_batch_kernel(
     int n, const int32_t* __restrict__ out_ptr, const int2* __restrict__ arcs, T* dist, int64_t ld, int64_t row_stride,
     const int32_t* __restrict__ sources, int nsrc, Entry* queues, int cap, T delta, int* overflow) {
@@ -52,16 +58,18 @@ __global__ void __launch_bounds__(SSSP_THREADS) sssp_batch_kernel(
   Entry* far = nxt + cap;
   Entry* far2 = far + cap;
   const int tid = threadIdx.x;
-  for (int k = blockIdx.x; k < nsrc; k += gridDim.x) {
-    const int src = sources[k];
-    T* row = dist + (int64_t)k * row_stride;
-    for (int64_t t = tid; t < ld; t += SSSP_THREADS) row[t] = Dist<T>::inf();
+  for (int k0 = blockIdx.x * SSSP_S; k0 < nsrc; k0 += gridDim.x * SSSP_S) {
+    const int ns = min(SSSP_S, nsrc - k0);
+    T* rows = dist + (int64_t)k0 * row_stride;
+    for (int sl = 0; sl < ns; ++sl)
+      for (int64_t t = tid; t < ld; t += SSSP_THREADS) rows[(int64_t)sl * row_stride + t] = Dist<T>::inf();
     __syncthreads();
-    if (tid == 0) {
-      row[src] = (T)0;
-      cur[0] = Entry{src, Dist<T>::key((T)0)};
-      s_near = 1; s_next = 0; s_far = 0;
+    if (tid < ns) {
+      const int src = sources[k0 + tid];
+      rows[(int64_t)tid * row_stride + src] = (T)0;
+      cur[tid] = Entry{src | (tid << SLOT_SHIFT), Dist<T>::key((T)0)};
     }
+    if (tid == 0) { s_near = ns; s_next = 0; s_far = 0; }
     T theta = delta;
     __syncthreads();
     while (true) {
@@ -71,21 +79,54 @@ __global__ void __launch_bounds__(SSSP_THREADS) sssp_batch_kernel(
         if (nn == 0) break;
         for (int e = tid; e < nn; e += SSSP_THREADS) {
           const Entry en = cur[e];
-          const T du = Dist<T>::unkey(en.key);
-          if (Dist<T>::key(__ldcg(&row[en.v])) != en.key) continue;   // stale: a shorter distance arrived later (L2 read: atomics live there)
-          const int a1 = out_ptr[en.v + 1];
-          for (int a = out_ptr[en.v]; a < a1; ++a) {
-            const int2 arc = arcs[a];
-            const T nd = du + Dist<T>::weight(arc.y);
-            const int nk = Dist<T>::key(nd);
-            const int old = atomicMin(reinterpret_cast<int*>(row) + arc.x, nk);
-            if (nk < old) {
-              if (nd < theta) {
+          const int v = en.v & VERTEX_MASK, slot = en.v >> SLOT_SHIFT;
+          T* row = rows + (int64_t)slot * row_stride;
+          const int kcur = Dist<T>::key(__ldcg(&row[v]));   // L2 read: the atomics live there
+          const int a0 = out_ptr[v];
+          int deg = out_ptr[v + 1] - a0;
+          if (kcur != en.key) deg = 0;                       // stale: a shorter distance arrived later
+          // arc records, then ALL atomicMins in flight together, then the queue pushes
+          int2 arc[SSSP_D];
+          int nk[SSSP_D], old[SSSP_D];
+#pragma unroll
+          for (int j = 0; j < SSSP_D; ++j)
+            if (j < deg) arc[j] = arcs[a0 + j];
+          // plain L2 reads first: most arcs point back at settled vertices and need no atomic at all
+          // (the kernel is bound by L2 atomic throughput, loads are several times cheaper)
+#pragma unroll
+          for (int j = 0; j < SSSP_D; ++j)
+            if (j < deg) {
+              nk[j] = Dist<T>::key(Dist<T>::unkey(en.key) + Dist<T>::weight(arc[j].y));
+              old[j] = Dist<T>::key(__ldcg(&row[arc[j].x]));
+            }
+#pragma unroll
+          for (int j = 0; j < SSSP_D; ++j)
+            if (j < deg && nk[j] < old[j]) old[j] = atomicMin(reinterpret_cast<int*>(row) + arc[j].x, nk[j]);
+#pragma unroll
+          for (int j = 0; j < SSSP_D; ++j)
+            if (j < deg && nk[j] < old[j]) {
+              const Entry ne{arc[j].x | (slot << SLOT_SHIFT), nk[j]};
+              if (Dist<T>::unkey(nk[j]) < theta) {
                 const int pos = atomicAdd(&s_next, 1);
-                if (pos < cap) nxt[pos] = Entry{arc.x, nk}; else *overflow = 1;
+                if (pos < cap) nxt[pos] = ne; else *overflow = 1;
               } else {
                 const int pos = atomicAdd(&s_far, 1);
-                if (pos < cap) far[pos] = Entry{arc.x, nk}; else *overflow = 1;
+                if (pos < cap) far[pos] = ne; else *overflow = 1;
+              }
+            }
+          for (int a = a0 + SSSP_D; a < a0 + deg; ++a) {   // vertices with more than SSSP_D arcs
+            const int2 ar = arcs[a];
+            const int k2 = Dist<T>::key(Dist<T>::unkey(en.key) + Dist<T>::weight(ar.y));
+            int o2 = Dist<T>::key(__ldcg(&row[ar.x]));
+            if (k2 < o2) o2 = atomicMin(reinterpret_cast<int*>(row) + ar.x, k2);
+            if (k2 < o2) {
+              const Entry ne{ar.x | (slot << SLOT_SHIFT), k2};
+              if (Dist<T>::unkey(k2) < theta) {
+                const int pos = atomicAdd(&s_next, 1);
+                if (pos < cap) nxt[pos] = ne; else *overflow = 1;
+              } else {
+                const int pos = atomicAdd(&s_far, 1);
+                if (pos < cap) far[pos] = ne; else *overflow = 1;
               }
             }
           }
@@ -95,7 +136,7 @@ __global__ void __launch_bounds__(SSSP_THREADS) sssp_batch_kernel(
         Entry* tmp = cur; cur = nxt; nxt = tmp;
         __syncthreads();
       }
-      // ---- NEAR is empty: advance theta to the bucket of the smallest valid FAR entry
+      // ---- NEAR is empty: advance theta to the bucket of the smallest valid FAR entry (any source)
       const int nf = min(s_far, cap);
       if (nf == 0) break;
       if (tid == 0) { s_min = 0x7fffffff; s_keep = 0; }
@@ -103,7 +144,8 @@ __global__ void __launch_bounds__(SSSP_THREADS) sssp_batch_kernel(
       int lmin = 0x7fffffff;
       for (int e = tid; e < nf; e += SSSP_THREADS) {
         const Entry en = far[e];
-        if (Dist<T>::key(__ldcg(&row[en.v])) == en.key) lmin = min(lmin, en.key);
+        const T* row = rows + (int64_t)(en.v >> SLOT_SHIFT) * row_stride;
+        if (Dist<T>::key(__ldcg(&row[en.v & VERTEX_MASK])) == en.key) lmin = min(lmin, en.key);
       }
       for (int off = 16; off > 0; off >>= 1) lmin = min(lmin, __shfl_down_sync(0xffffffffu, lmin, off));
       if ((tid & 31) == 0 && lmin != 0x7fffffff) atomicMin(&s_min, lmin);
@@ -113,7 +155,8 @@ __global__ void __launch_bounds__(SSSP_THREADS) sssp_batch_kernel(
       theta = Dist<T>::next_theta(Dist<T>::unkey(kmin), delta);
       for (int e = tid; e < nf; e += SSSP_THREADS) {
         const Entry en = far[e];
-        if (Dist<T>::key(__ldcg(&row[en.v])) != en.key) continue;
+        const T* row = rows + (int64_t)(en.v >> SLOT_SHIFT) * row_stride;
+        if (Dist<T>::key(__ldcg(&row[en.v & VERTEX_MASK])) != en.key) continue;
         if (Dist<T>::unkey(en.key) < theta) cur[atomicAdd(&s_near, 1)] = en;
         else far2[atomicAdd(&s_keep, 1)] = en;
       }
@@ -141,28 +184,44 @@ __global__ void pack_arcs_kernel(int narcs, const int32_t* col, const float* w, 
   if (a < narcs) arcs[a] = make_int2(col[a], __float_as_int(w[a]));
 }
 
-int sssp_threads() {   // CTA size: tuning knob (64 / 128 / 256), default chosen by measurement on B200
-  static int t = 0;
-  if (!t) {
-    const char* e = getenv("DRS_SSSP_THREADS");
-    t = e ? atoi(e) : 128;
-    if (t != 64 && t != 128 && t != 256) t = 128;
+int sssp_env(const char* name, int dflt, int a, int b, int c) {
+  const char* e = getenv(name);
+  const int t = e ? atoi(e) : dflt;
+  return (t == a || t == b || t == c || t == 8) ? t : dflt;
+}
+// tuning knobs, defaults chosen by measurement on B200 (tools/gpu_check_sssp2.py)
+int sssp_threads() { static int t = sssp_env("DRS_SSSP_THREADS", 128, 64, 128, 256); return t; }
+int sssp_slots() { static int u = sssp_env("DRS_SSSP_S", 1, 1, 2, 4) ; return u; }   // sources per CTA (also 8 below)
+
+template <typename T, int TH, int U>
+int sssp_launch(bool query, int* per_sm, int grid, cudaStream_t st, int n, const int32_t* out_ptr, const int2* arcs, T* dist,
+                int64_t ld, int64_t row_stride, const int32_t* sources, int nsrc, Entry* queues, int cap, T delta, int* overflow) {
+  if (query) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, sssp_batch_kernel<T, TH, U>, TH, 0);
+    return DRS_OK;
   }
-  return t;
+  sssp_batch_kernel<T, TH, U><<<grid, TH, 0, st>>>(n, out_ptr, arcs, dist, ld, row_stride, sources, nsrc, queues, cap, delta, overflow);
+  return DRS_OK;
 }
 
-template <typename T, int TH>
-int sssp_occupancy() {
-  int per_sm = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sssp_batch_kernel<T, TH>, TH, 0);
-  return per_sm;
+template <typename T, typename... A>
+int sssp_dispatch(A... args) {
+  const int th = sssp_threads(), u = sssp_slots();
+#define DRS_SSSP_CASE(TH, U) if (th == TH && u == U) return sssp_launch<T, TH, U>(args...);
+  DRS_SSSP_CASE(64, 1) DRS_SSSP_CASE(64, 2) DRS_SSSP_CASE(64, 4) DRS_SSSP_CASE(64, 8)
+  DRS_SSSP_CASE(128, 1) DRS_SSSP_CASE(128, 2) DRS_SSSP_CASE(128, 4) DRS_SSSP_CASE(128, 8)
+  DRS_SSSP_CASE(256, 1) DRS_SSSP_CASE(256, 2) DRS_SSSP_CASE(256, 4) DRS_SSSP_CASE(256, 8)
+#undef DRS_SSSP_CASE
+  return DRS_ERR_ARG;
 }
 
 template <typename T>
 int sssp_grid(int sms, int nsrc) {
-  const int th = sssp_threads();
-  const int per_sm = th == 64 ? sssp_occupancy<T, 64>() : th == 128 ? sssp_occupancy<T, 128>() : sssp_occupancy<T, 256>();
-  return std::max(1, std::min(nsrc, sms * std::max(per_sm, 1)));
+  int per_sm = 1;
+  sssp_dispatch<T>(true, &per_sm, 0, (cudaStream_t) nullptr, 0, (const int32_t*)nullptr, (const int2*)nullptr, (T*)nullptr,
+                   (int64_t)0, (int64_t)0, (const int32_t*)nullptr, 0, (Entry*)nullptr, 0, (T)0, (int*)nullptr);
+  const int groups = (nsrc + sssp_slots() - 1) / sssp_slots();
+  return std::max(1, std::min(groups, sms * std::max(per_sm, 1)));
 }
 
 template <typename T>
@@ -170,13 +229,9 @@ int sssp_run(const drs_graph* g, int nsrc, const int32_t* sources_dev, T* dist, 
              cudaStream_t st, const int2* arcs, Entry* queues, int cap, int grid, int* overflow) {
   T d = (T)delta;
   if (!(d > (T)0)) d = (T)1;
-  const int th = sssp_threads();
-  if (th == 64)
-    sssp_batch_kernel<T, 64><<<grid, 64, 0, st>>>(g->n, g->d_out_ptr, arcs, dist, ld, row_stride, sources_dev, nsrc, queues, cap, d, overflow);
-  else if (th == 128)
-    sssp_batch_kernel<T, 128><<<grid, 128, 0, st>>>(g->n, g->d_out_ptr, arcs, dist, ld, row_stride, sources_dev, nsrc, queues, cap, d, overflow);
-  else
-    sssp_batch_kernel<T, 256><<<grid, 256, 0, st>>>(g->n, g->d_out_ptr, arcs, dist, ld, row_stride, sources_dev, nsrc, queues, cap, d, overflow);
+  int dummy = 0;
+  sssp_dispatch<T>(false, &dummy, grid, st, g->n, (const int32_t*)g->d_out_ptr, arcs, dist, ld, row_stride, sources_dev, nsrc, queues,
+                   cap, d, overflow);
   drs_count_launch();
   DRS_CUDA(cudaGetLastError());
   return DRS_OK;
@@ -189,6 +244,7 @@ extern "C" int drs_sssp_batch_dev(const drs_graph* g, int32_t mode, int32_t nsrc
                                   int64_t ld, double delta, void* stream) {
   DRS_REQUIRE(g && dist_dev && (nsrc == 0 || sources_host), DRS_ERR_ARG, "drs_sssp_batch_dev: null argument");
   DRS_REQUIRE(ld >= g->n && nsrc >= 0, DRS_ERR_ARG, "drs_sssp_batch_dev: ld (%lld) must be >= n (%d)", (long long)ld, g->n);
+  DRS_REQUIRE(g->n <= VERTEX_MASK, DRS_ERR_ARG, "drs_sssp_batch_dev: at most %d vertices (queue entries pack the source slot above bit 24)", VERTEX_MASK);
   DRS_REQUIRE(mode == DRS_MODE_F32 || mode == DRS_MODE_I32, DRS_ERR_ARG, "drs_sssp_batch_dev: unknown mode %d", mode);
   for (int k = 0; k < nsrc; ++k)
     DRS_REQUIRE(sources_host[k] >= 0 && sources_host[k] < g->n, DRS_ERR_RANGE, "drs_sssp_batch_dev: source %d out of range", sources_host[k]);
@@ -211,12 +267,16 @@ extern "C" int drs_sssp_batch_dev(const drs_graph* g, int32_t mode, int32_t nsrc
     DRS_CUDA(cudaGetLastError());
     gm->sssp_arcs_valid = true;
   }
-  int32_t* d_sources = nullptr;
-  int* d_overflow = nullptr;
-  DRS_CUDA(cudaMalloc((void**)&d_sources, sizeof(int32_t) * nsrc + sizeof(int)));
-  d_overflow = reinterpret_cast<int*>(d_sources + nsrc);
+  if (gm->sssp_sources_cap < nsrc) {
+    if (gm->sssp_sources) cudaFree(gm->sssp_sources);
+    gm->sssp_sources = nullptr; gm->sssp_sources_cap = 0;
+    DRS_CUDA(cudaMalloc((void**)&gm->sssp_sources, sizeof(int32_t) * (size_t)nsrc + sizeof(int)));
+    gm->sssp_sources_cap = nsrc;
+  }
+  int32_t* d_sources = gm->sssp_sources;
+  int* d_overflow = reinterpret_cast<int*>(d_sources + gm->sssp_sources_cap);
   // queue capacity per CTA: frontiers of road networks are a few thousand entries; overflow is detected and retried
-  int cap = std::max(4096, std::min(g->narcs + 1, 65536));
+  int cap = std::max(4096, std::min(g->narcs + 1, 65536)) * sssp_slots();
   int rc = DRS_OK;
   for (int attempt = 0; attempt < 3 && rc == DRS_OK; ++attempt) {
     const size_t need = sizeof(Entry) * 4 * (size_t)cap * grid;
@@ -224,7 +284,6 @@ extern "C" int drs_sssp_batch_dev(const drs_graph* g, int32_t mode, int32_t nsrc
       if (gm->sssp_queues) cudaFree(gm->sssp_queues);
       gm->sssp_queues = nullptr; gm->sssp_queue_bytes = 0;
       if (cudaMalloc(&gm->sssp_queues, need) != cudaSuccess) {
-        cudaFree(d_sources);
         DRS_REQUIRE(false, DRS_ERR_NOMEM, "drs_sssp_batch_dev: cannot allocate %zu bytes of work queues", need);
       }
       gm->sssp_queue_bytes = need;
@@ -241,10 +300,9 @@ extern "C" int drs_sssp_batch_dev(const drs_graph* g, int32_t mode, int32_t nsrc
     int ovf = 0;
     cudaMemcpyAsync(&ovf, d_overflow, sizeof(int), cudaMemcpyDeviceToHost, st);
     if (cudaStreamSynchronize(st) != cudaSuccess) { drs_set_error("drs_sssp_batch_dev: kernel failed: %s", cudaGetErrorString(cudaGetLastError())); rc = DRS_ERR_CUDA; break; }
-    if (!ovf) { cudaFree(d_sources); return DRS_OK; }
+    if (!ovf) return DRS_OK;
     cap *= 4;   // queue overflow: retry with larger queues
   }
-  cudaFree(d_sources);
   if (rc) return rc;
   DRS_REQUIRE(false, DRS_ERR_NOMEM, "drs_sssp_batch_dev: work queues overflowed three times");
 }
