@@ -224,33 +224,7 @@ def insertion_section(G, data, config, peaks, cpu_seconds=8.0):
                                                   "(travel times pre-fetched from the matrix, i.e. without the reference's "
                                                   "per-leg Dijkstra)" % (nreq, sub_v)}
     # ---- Alonso-Mora RV stage on the same state
-    class _R(object):
-        pass
-
-    class _V(object):
-        def get_passenger_requests(self):
-            return self._pax, self._wait
-
-        def get_next_node(self):
-            return self._loc, 0.0
-    lng, lat = data.vattrs["lng"], data.vattrs["lat"]
-    reqs = []
-    is_new = np.zeros(len(tab["o"]), dtype=bool)
-    is_new[sc["new_rows"]] = True
-    for r in range(len(tab["o"])):
-        q = _R()
-        o, d = int(tab["o"][r]), int(tab["d"][r])
-        q.id, q.olng, q.olat, q.dlng, q.dlat = r, lng[o], lat[o], lng[d], lat[d]
-        q.Cep, q.Clp, q.Ced, q.Cld = float(tab["Cep"][r]), float(tab["Clp"][r]), float(tab["Ced"][r]), float(tab["Cld"][r])
-        q.assigned = not is_new[r]
-        q.get_dropoff_time_window = (lambda q=q: [q.Ced, q.Cld])
-        reqs.append(q)
-    vehs = []
-    for k, v in enumerate(sc["vehs"]):
-        o = _V()
-        o.id, o.K, o._loc = k, v["K"], (lng[v["node"]], lat[v["node"]])
-        o._pax, o._wait = set(v["pax"]), set(v["wait"])
-        vehs.append(o)
+    vehs, reqs = scenario_objects(data, sc)
     t0 = time.time()
     rvt = Tick(G, vehs, reqs, sc["T"], pairwise_checks=True)
     t_marshal = time.time() - t0
@@ -274,6 +248,85 @@ def insertion_section(G, data, config, peaks, cpu_seconds=8.0):
                                     "traffic": None, "kernel": "rv_filter_kernel",
                                     "algorithmic_bytes_per_launch": pairs * 12.0}}
     return out
+
+
+def scenario_objects(data, sc):
+    """Veh / Req objects with the reference's attribute surface from a synth.fleet_scenario dict."""
+    tab = sc["table"]
+    lng, lat = data.vattrs["lng"], data.vattrs["lat"]
+
+    class _R(object):
+        def get_dropoff_time_window(self):
+            return [self.Ced, self.Cld]
+
+    class _V(object):
+        def get_passenger_requests(self):
+            return self._pax, self._wait
+
+        def get_next_node(self):
+            return self._loc, 0.0
+    is_new = np.zeros(len(tab["o"]), dtype=bool)
+    is_new[sc["new_rows"]] = True
+    reqs = []
+    for r in range(len(tab["o"])):
+        q = _R()
+        o, d = int(tab["o"][r]), int(tab["d"][r])
+        q.id, q.olng, q.olat, q.dlng, q.dlat = r, lng[o], lat[o], lng[d], lat[d]
+        q.Cep, q.Clp, q.Ced, q.Cld = float(tab["Cep"][r]), float(tab["Clp"][r]), float(tab["Ced"][r]), float(tab["Cld"][r])
+        q.assigned = not is_new[r]
+        reqs.append(q)
+    vehs = []
+    for k, v in enumerate(sc["vehs"]):
+        o = _V()
+        o.id, o.K, o._loc = k, v["K"], (lng[v["node"]], lat[v["node"]])
+        o._pax, o._wait = set(v["pax"]), set(v["wait"])
+        vehs.append(o)
+    return vehs, reqs
+
+
+def tick_e2e_section(G, data, config):
+    """One assignment tick through the drop-in API (AlonsoMora.optimizeAssignment: marshalling, RV stage,
+    RR / RTV trip costing on the GPU, set-packing on the host) at the fleet size of BASELINE config C3/C2,
+    next to the oracle's restatement of the reference on a bounded sample of the same tick."""
+    from drs_abm_b200 import synth
+    from drs_abm_b200.dispatch import AlonsoMora
+    from oracle import dispatch_oracle as D
+    n_veh, n_new = {"C3": (2000, 70), "C2": (200, 7), "C1": (10, 5)}[config]
+    sc = synth.fleet_scenario(data, n_veh, n_new, 600.0, 11, lambda s, t: G.matrix_lookup(s, t), plan_stops=(0, 0, 2, 4))
+    vehs, reqs = scenario_objects(data, sc)
+    opt = AlonsoMora({"routing_method": "enumerate", "verbose": False, "max_trip_size": 2})
+    times = []
+    for it in range(3):
+        t0 = time.time()
+        (routes, rejected), meta = opt.optimizeAssignment(vehs, reqs, G, sc["T"])
+        times.append(time.time() - t0)
+    # CPU: the oracle on the first `sub` vehicles, all new requests (pairs scale linearly with vehicles)
+    sub = min(n_veh, 60)
+    tab = sc["table"]
+    rows = {}
+
+    def tt(a, b):
+        r = rows.get(a)
+        if r is None:
+            r = rows[a] = G.dist_rows(int(a), 1)[0]
+        return float(r[b])
+
+    def rec(r):
+        return {"rid": r, "o_node": int(tab["o"][r]), "d_node": int(tab["d"][r]), "olng": 0.0, "olat": 0.0, "dlng": 0.0, "dlat": 0.0,
+                "Cep": float(tab["Cep"][r]), "Clp": float(tab["Clp"][r]), "Ced": float(tab["Ced"][r]), "Cld": float(tab["Cld"][r])}
+    ovehs = [{"vid": k, "capacity": v["K"], "node": v["node"], "location": (0.0, 0.0), "t": 0.0,
+              "pax_reqs": [rec(r) for r in v["pax"]], "wait_reqs": [rec(r) for r in v["wait"]]}
+             for k, v in enumerate(sc["vehs"][:sub])]
+    oreqs = [rec(int(r)) for r in sc["new_rows"]]
+    t0 = time.time()
+    D.rv_graph(ovehs, oreqs, tt, sc["T"], with_rr=False)
+    t_cpu = (time.time() - t0) * n_veh / sub
+    return {"tick_e2e": {"workload": "%d vehicles x %d new requests, AlonsoMora(enumerate, trips <= 2) on the %s map" % (n_veh, n_new, config),
+                         "value": float(np.median(times)), "unit": "s/tick", "assigned_vehicles": len(routes), "rejected": len(rejected),
+                         "rv_time_s": meta.get("rv_time"), "rtv_time_s": meta.get("rtv_time"), "solve_time_s": meta.get("solve_time"),
+                         "cpu_baseline": {"value": t_cpu, "unit": "s/tick", "cores": 1, "kind": "port",
+                                          "sample": "oracle RV stage only (no RR / RTV / ILP) on %d of %d vehicles, travel times "
+                                                    "pre-fetched from the matrix (no per-query Dijkstra), extrapolated" % (sub, n_veh)}}}
 
 
 def sssp_c5_section(peaks, n_sources=4096):
@@ -527,6 +580,7 @@ def main():
             if not G2._valid:
                 G2.build()
             line.update(insertion_section(G2, data, args.config, peaks))
+            line.update(tick_e2e_section(G2, data, args.config))
         if world == 1 and not args.no_insertion and args.config == "C3":
             G2.close()
             torch.cuda.empty_cache()
