@@ -388,6 +388,7 @@ def main():
     ap.add_argument("--no-insertion", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lookahead", action="store_true")
+    ap.add_argument("--no-p2p", action="store_true", help="skip the fused-broadcast FW measurement at N > 1")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -427,9 +428,16 @@ def main():
     sparse = 2 * data.m <= 16 * data.n                    # the library's AUTO rule (drs_apsp_build)
     algo = args.algorithm if args.algorithm != "auto" else ("sssp" if sparse else "fw")
 
+    comm = [None]
+
     def one_build(algorithm=None):
+        a = algorithm or algo
+        if a == "fw_p2p":        # blocked FW whose pivot step stores the panel into the peers' buffers (fused broadcast)
+            if comm[0] is None:
+                comm[0] = apsp_dist.P2PComm(tiles, npad, rank, world, dist)
+            return apsp_dist.build_sharded_p2p(tiles, npad, rank, world, dist, comm[0], lookahead=not args.no_lookahead)
         return apsp_dist.build_sharded(tiles, npad, rank, world, dist if world > 1 else None,
-                                       lookahead=not args.no_lookahead, with_pred=True, algorithm=algorithm or algo)
+                                       lookahead=not args.no_lookahead, with_pred=True, algorithm=a)
 
     # ALU roofline denominator, measured live (rank 0): best add+min stream of the three instruction mixes
     alu = {}
@@ -481,6 +489,9 @@ def main():
             sampler2.start()
         other_res = timed_builds(other, 3 if other == "sssp" else 1, max(1, min(args.steps, 2)))
         other_clocks = sampler2.stop(args.gpus) if rank == 0 else None
+    p2p_res = None
+    if world > 1 and not args.no_p2p:
+        p2p_res = timed_builds("fw_p2p", 1, max(1, min(args.steps, 2)))
 
     # end to end through the public API: host arrays in, query results out
     barrier()
@@ -570,6 +581,12 @@ def main():
                 t_k = prof_sssp[2] * 1e-3 if prof_sssp is not None else osec * world
                 sub["roofline"] = sssp_roofline(t_k)
                 line["sssp"] = sub
+        if p2p_res is not None:
+            psec, plaunch, pcs = p2p_res
+            line["fw_p2p"] = {"value": psec, "unit": "s", "gpu_launches": plaunch, "checksum": pcs,
+                              "same_matrix_as_headline": bool(pcs == checksum), "roofline": fw_roofline(psec * world),
+                              "transport": "pivot-panel tiles stored straight into the peers' buffers by the tile kernel's epilogue "
+                                           "(CUDA IPC peer memory over NVLink), signal / acknowledgement words instead of ncclBroadcast"}
         line["e2e"] = {"value": float(e2e_t.item()), "unit": "s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
         if world == 1 and not args.no_cpu_baseline:
             ns = 256 if data.n > 10000 else data.n
@@ -586,6 +603,8 @@ def main():
             torch.cuda.empty_cache()
             line.update(sssp_c5_section(peaks))
         print(json.dumps(line), flush=True)
+    if comm[0] is not None:
+        comm[0].close()
     G2.close()
     G.close()
     if world > 1:

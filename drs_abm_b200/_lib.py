@@ -85,6 +85,13 @@ SIGNATURES = {
     "drs_fw_pivot_row": (C.c_int, [C.c_int32, _vp, C.c_int64, C.c_int32, _vp]),
     "drs_fw_update": (C.c_int, [C.c_int32, _vp, C.c_int64, C.c_int32, _vp, C.c_int32, C.c_int32, C.c_int32,
                                 C.c_int32, _vp]),
+    "drs_p2p_alloc": (C.c_int, [C.c_int64, C.POINTER(_vp), C.POINTER(C.c_ubyte)]),
+    "drs_p2p_open": (C.c_int, [C.POINTER(C.c_ubyte), C.POINTER(_vp)]),
+    "drs_p2p_close": (C.c_int, [_vp]),
+    "drs_p2p_free": (C.c_int, [_vp]),
+    "drs_fw_pivot_row_p2p": (C.c_int, [C.c_int32, _vp, C.c_int64, C.c_int32, C.c_int32, C.POINTER(_vp), C.POINTER(_vp), C.c_int32, _vp]),
+    "drs_fw_post_words": (C.c_int, [C.c_int32, C.POINTER(_vp), C.c_int32, _vp]),
+    "drs_fw_wait_words": (C.c_int, [C.c_int32, C.POINTER(_vp), C.c_int32, C.c_int64, _vp, _vp]),
     "drs_pred_build": (C.c_int, [_vp, C.c_int32, _vp, C.c_int64, C.c_int32, C.c_int32, _vp, _vp]),
     "drs_query_pairs": (C.c_int, [_vp, C.c_int32, _i32p, _i32p, _f64p, _f64p, _i32p]),
     "drs_query_matrix": (C.c_int, [_vp, C.c_int32, _i32p, _i32p, _f64p]),

@@ -90,6 +90,155 @@ class CudaTiles(object):
         self.torch.cuda.synchronize()
 
 
+class P2PComm(object):
+    """Per-rank communication block for the fused pivot step (drs_fw_pivot_row_p2p): signal word,
+    acknowledgement words (one per sender), a time-out word and two pivot-panel buffers, allocated with
+    cudaMalloc, exported by CUDA IPC and mapped by every other rank of the host."""
+    HEADER = 1024          # bytes: [0] signal, [64 + 4*r] ack of rank r, [512] time-out flag
+
+    def __init__(self, tiles, npad, rank, world, dist, timeout_ms=20000):
+        self.lib, self.rank, self.world, self.npad = tiles.lib, rank, world, npad
+        self.tiles = tiles
+        self.timeout_ms = timeout_ms
+        self.panel_bytes = TILE * npad * 4
+        total = self.HEADER + 2 * self.panel_bytes
+        base = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        _lib.check(self.lib.drs_p2p_alloc(total, C.byref(base), handle), self.lib)
+        self.base = base.value
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle))
+        self.peer_base = {}
+        for r in range(world):
+            if r == rank:
+                continue
+            ptr = C.c_void_p()
+            hb = (C.c_ubyte * 64).from_buffer_copy(handles[r])
+            _lib.check(self.lib.drs_p2p_open(hb, C.byref(ptr)), self.lib)
+            self.peer_base[r] = ptr.value
+        self.peers = sorted(self.peer_base)
+        self.builds = 0
+        dist.barrier()
+
+    # addresses inside a block
+    def signal(self, base):
+        return base
+
+    def ack(self, base, sender):
+        return base + 64 + 4 * sender
+
+    def panel_addr(self, base, which):
+        return base + self.HEADER + which * self.panel_bytes
+
+    def local_panel(self, which):
+        """torch view of one of this rank's panel buffers."""
+        return _as_tensor(self.tiles.torch, self.panel_addr(self.base, which), (TILE, self.npad), self.tiles.dtype)
+
+    def _ptr_array(self, values):
+        arr = (C.c_void_p * max(len(values), 1))(*values)
+        return arr
+
+    def pivot_row(self, panel, kb, which, value):
+        stream = self.tiles._stream()
+        panels = self._ptr_array([self.panel_addr(self.peer_base[r], which) for r in self.peers])
+        sigs = self._ptr_array([self.signal(self.peer_base[r]) for r in self.peers])
+        _lib.check(self.lib.drs_fw_pivot_row_p2p(self.tiles.mode, C.c_void_p(panel.data_ptr()), panel.shape[1], kb,
+                                                 len(self.peers), panels, sigs, value, stream), self.lib)
+
+    def wait_signal(self, value):
+        words = self._ptr_array([self.signal(self.base)])
+        _lib.check(self.lib.drs_fw_wait_words(1, words, value, self.timeout_ms, C.c_void_p(self.base + 512),
+                                              self.tiles._stream()), self.lib)
+
+    def wait_acks(self, value):
+        words = self._ptr_array([self.ack(self.base, r) for r in self.peers])
+        _lib.check(self.lib.drs_fw_wait_words(len(self.peers), words, value, self.timeout_ms, C.c_void_p(self.base + 512),
+                                              self.tiles._stream()), self.lib)
+
+    def post_ack(self, value):
+        words = self._ptr_array([self.ack(self.peer_base[r], self.rank) for r in self.peers])
+        _lib.check(self.lib.drs_fw_post_words(len(self.peers), words, value, self.tiles._stream()), self.lib)
+
+    def timed_out(self):
+        torch = self.tiles.torch
+        flag = _as_tensor(torch, self.base + 512, (1,), torch.int32)
+        return bool(flag.item())
+
+    def close(self):
+        for r, ptr in self.peer_base.items():
+            self.lib.drs_p2p_close(C.c_void_p(ptr))
+        self.peer_base = {}
+        if self.base:
+            self.lib.drs_p2p_free(C.c_void_p(self.base))
+            self.base = None
+
+
+def _as_tensor(torch, addr, shape, dtype):
+    """torch tensor over raw device memory owned by the library (no copy)."""
+    class _Holder(object):
+        pass
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4" if dtype == torch.float32 else "<i4",
+                                  "data": (int(addr), False), "version": 2, "strides": None}
+    return torch.as_tensor(h, device="cuda")
+
+
+def build_sharded_p2p(tiles, npad, rank, world, dist, comm, lookahead=True, with_pred=True):
+    """Sharded FW whose pivot step stores its panel straight into the peers' buffers (fused compute +
+    broadcast over NVLink); same schedule as build_sharded(algorithm="fw")."""
+    nb = npad // TILE
+    starts = block_partition(nb, world)
+    b0, b1 = starts[rank], starts[rank + 1]
+    row0 = b0 * TILE
+    local = tiles.empty((b1 - b0) * TILE, npad)
+    tiles.init(local, row0)
+    bufs = [comm.local_panel(0), comm.local_panel(1)]
+    base = comm.builds * (nb + 4) + 1
+    comm.builds += 1
+    dist.barrier()                      # nobody may still be using the buffers of an earlier build
+
+    def own_panel(kb):
+        return local[(kb - b0) * TILE:(kb - b0 + 1) * TILE]
+
+    def pivot(kb):
+        """Owner side: wait until the peers are done with the buffer panel kb goes to, then close + push."""
+        if kb >= 2:
+            comm.wait_acks(base + kb - 1)       # ack value of round kb-2
+        comm.pivot_row(own_panel(kb), kb, kb % 2, base + kb + 1)
+
+    if owner_of(0, starts) == rank:
+        pivot(0)
+    for kb in range(nb):
+        owner = owner_of(kb, starts)
+        if owner == rank:
+            panel = own_panel(kb)
+        else:
+            comm.wait_signal(base + kb + 1)
+            panel = bufs[kb % 2]
+        skip = (kb - b0) if owner == rank else -1
+        if kb + 1 < nb and owner_of(kb + 1, starts) == rank:
+            lb = kb + 1 - b0
+            if lookahead:
+                tiles.update(local, panel, kb, skip, lb, lb + 1)
+                pivot(kb + 1)
+                tiles.update(local, panel, kb, skip, 0, lb)
+                tiles.update(local, panel, kb, skip, lb + 1, b1 - b0)
+            else:
+                tiles.update(local, panel, kb, skip, 0, b1 - b0)
+                pivot(kb + 1)
+        else:
+            tiles.update(local, panel, kb, skip, 0, b1 - b0)
+        comm.post_ack(base + kb + 1)
+    pred_local = None
+    if with_pred:
+        pred_local = tiles.empty_pred((b1 - b0) * TILE, npad)
+        tiles.pred(local, row0, pred_local)
+    tiles.synchronize()
+    if comm.timed_out():
+        raise RuntimeError("fused pivot broadcast timed out waiting for a peer (rank %d)" % rank)
+    return local, pred_local, row0
+
+
 def build_sharded(tiles, npad, rank=0, world=1, dist=None, lookahead=True, with_pred=True, algorithm="fw"):
     """Runs the sharded build.  ``tiles`` is a backend (CudaTiles), ``dist`` the
     torch.distributed module (or None when world == 1).

@@ -16,6 +16,8 @@
 // chunks.  The work is ALU-bound (one add + one min per relaxation, two issue
 // slots); HBM traffic per round is one read + one write of the matrix, a factor
 // ~5 below the ALU time at tile width 128 (kernel K1).
+#include <cstring>
+
 #include "drs_common.cuh"
 
 namespace {
@@ -72,6 +74,8 @@ template <typename T> struct TileArgs {
   int i_off;   // first block-row index handled by blockIdx.y == 0
   int skip_i;  // block-row to skip (-1: none), compared against i_off + blockIdx.y
   int skip_j;  // block-column to skip (-1: none)
+  int n_peers; // fused broadcast: the finished C tile is also stored at the same offset of these buffers
+  T* peer[DRS_MAX_PEERS];
 };
 
 template <typename T>
@@ -160,6 +164,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) fw_minplus_tile_kernel(TileArgs<T
     hi.x = acc[r][4]; hi.y = acc[r][5]; hi.z = acc[r][6]; hi.w = acc[r][7];
     *reinterpret_cast<V4*>(crow + tx * 4) = lo;
     *reinterpret_cast<V4*>(crow + 64 + tx * 4) = hi;
+    // fused broadcast: P2P stores of the finished tile into every peer's panel buffer (NVLink)
+    for (int pr = 0; pr < p.n_peers; ++pr) {
+      T* prow = p.peer[pr] + bi * p.c_si + bj * p.c_sj + (int64_t)(ty + 16 * r) * p.ldc;
+      *reinterpret_cast<V4*>(prow + tx * 4) = lo;
+      *reinterpret_cast<V4*>(prow + 64 + tx * 4) = hi;
+    }
   }
 }
 
@@ -167,8 +177,10 @@ constexpr size_t kTileSmemBytes = sizeof(float) * STAGES * (TILE * APAD + KC * T
 
 // Phase 1: close the 128x128 diagonal tile in shared memory (classic FW, one CTA).
 constexpr int P1PAD = TILE + 4;
+template <typename T> struct PeerList { int n; T* ptr[DRS_MAX_PEERS]; };
+
 template <typename T>
-__global__ void __launch_bounds__(1024, 1) fw_diag_kernel(T* D, int64_t ld) {
+__global__ void __launch_bounds__(1024, 1) fw_diag_kernel(T* D, int64_t ld, PeerList<T> peers) {
   using V4 = typename Vec4<T>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T(*s)[P1PAD] = reinterpret_cast<T(*)[P1PAD]>(smem_raw);
@@ -198,7 +210,11 @@ __global__ void __launch_bounds__(1024, 1) fw_diag_kernel(T* D, int64_t ld) {
     __syncthreads();
   }
 #pragma unroll
-  for (int r = 0; r < 4; ++r) *reinterpret_cast<V4*>(D + (int64_t)(ty * 4 + r) * ld + tx * 4) = c[r];
+  for (int r = 0; r < 4; ++r) {
+    *reinterpret_cast<V4*>(D + (int64_t)(ty * 4 + r) * ld + tx * 4) = c[r];
+    for (int pr = 0; pr < peers.n; ++pr)
+      *reinterpret_cast<V4*>(peers.ptr[pr] + (int64_t)(ty * 4 + r) * ld + tx * 4) = c[r];
+  }
 }
 constexpr size_t kDiagSmemBytes = sizeof(float) * TILE * P1PAD;
 
@@ -319,10 +335,16 @@ int launch_tile(const TileArgs<T>& p, dim3 grid, cudaStream_t st) {
 }
 
 template <typename T>
-int pivot_row_impl(T* panel, int64_t ld, int kb, cudaStream_t st) {
+int pivot_row_impl(T* panel, int64_t ld, int kb, cudaStream_t st, int n_peers = 0, void* const* peer_panels = nullptr) {
   const int nb = (int)(ld / TILE);
   T* diag = panel + (int64_t)kb * TILE;
   TileArgs<T> p{};
+  PeerList<T> pl{};
+  pl.n = n_peers; p.n_peers = n_peers;
+  for (int i = 0; i < n_peers; ++i) {
+    p.peer[i] = (T*)peer_panels[i];
+    pl.ptr[i] = (T*)peer_panels[i] + (int64_t)kb * TILE;
+  }
   // make sure attributes are configured before the first diag launch
   p.A = diag; p.a_si = 0; p.a_sj = 0; p.lda = ld;
   p.B = panel; p.b_si = 0; p.b_sj = TILE; p.ldb = ld;
@@ -330,7 +352,7 @@ int pivot_row_impl(T* panel, int64_t ld, int kb, cudaStream_t st) {
   p.i_off = 0; p.skip_i = -1; p.skip_j = kb;
   int rc = launch_tile<T>(p, dim3(0, 0), st);   // configure only
   if (rc) return rc;
-  fw_diag_kernel<T><<<1, 1024, kDiagSmemBytes, st>>>(diag, ld);
+  fw_diag_kernel<T><<<1, 1024, kDiagSmemBytes, st>>>(diag, ld, pl);
   drs_count_launch();
   DRS_CUDA(cudaGetLastError());
   return launch_tile<T>(p, dim3(nb, 1), st);
@@ -393,6 +415,103 @@ extern "C" int drs_fw_pivot_row(int32_t mode, void* panel_dev, int64_t ld, int32
   if (mode == DRS_MODE_F32) return pivot_row_impl<float>((float*)panel_dev, ld, kb, (cudaStream_t)stream);
   if (mode == DRS_MODE_I32) return pivot_row_impl<int>((int*)panel_dev, ld, kb, (cudaStream_t)stream);
   DRS_REQUIRE(false, DRS_ERR_ARG, "drs_fw_pivot_row: unknown mode %d", mode);
+}
+
+// ---------------------------------------------------------------- fused pivot + P2P broadcast
+namespace {
+struct WordList { int n; int32_t* w[DRS_MAX_PEERS + 1]; };
+
+__global__ void post_words_kernel(WordList wl, int value) {
+  __threadfence_system();   // everything this stream wrote before (the panel tiles) is visible first
+  if (threadIdx.x < wl.n) atomicMax_system(wl.w[threadIdx.x], value);   // monotone: posts from different owners may race
+  __threadfence_system();
+}
+
+__global__ void wait_words_kernel(WordList wl, int value, long long timeout_cycles, int32_t* timed_out) {
+  if (threadIdx.x >= wl.n) return;
+  const volatile int32_t* w = wl.w[threadIdx.x];
+  const long long t0 = clock64();
+  while (*w < value) {
+    if (clock64() - t0 > timeout_cycles) { *timed_out = 1; break; }
+    __nanosleep(200);
+  }
+  __threadfence_system();
+}
+}  // namespace
+
+extern "C" int drs_p2p_alloc(int64_t bytes, void** dev_ptr, unsigned char* handle) {
+  DRS_REQUIRE(bytes > 0 && dev_ptr && handle, DRS_ERR_ARG, "drs_p2p_alloc: bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  DRS_CUDA(cudaMalloc(dev_ptr, (size_t)bytes));
+  DRS_CUDA(cudaMemset(*dev_ptr, 0, (size_t)bytes));
+  cudaIpcMemHandle_t h;
+  DRS_CUDA(cudaIpcGetMemHandle(&h, *dev_ptr));
+  memcpy(handle, &h, 64);
+  return DRS_OK;
+}
+
+extern "C" int drs_p2p_open(const unsigned char* handle, void** peer_ptr) {
+  DRS_REQUIRE(handle && peer_ptr, DRS_ERR_ARG, "drs_p2p_open: null argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  DRS_CUDA(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return DRS_OK;
+}
+
+extern "C" int drs_p2p_close(void* peer_ptr) {
+  if (peer_ptr) DRS_CUDA(cudaIpcCloseMemHandle(peer_ptr));
+  return DRS_OK;
+}
+
+extern "C" int drs_p2p_free(void* dev_ptr) {
+  if (dev_ptr) DRS_CUDA(cudaFree(dev_ptr));
+  return DRS_OK;
+}
+
+extern "C" int drs_fw_post_words(int32_t n, int32_t* const* words, int32_t value, void* stream) {
+  DRS_REQUIRE(n >= 0 && n <= DRS_MAX_PEERS + 1 && (n == 0 || words), DRS_ERR_ARG, "drs_fw_post_words: bad argument");
+  if (n == 0) return DRS_OK;
+  WordList wl{};
+  wl.n = n;
+  for (int i = 0; i < n; ++i) wl.w[i] = words[i];
+  post_words_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(wl, value);
+  drs_count_launch();
+  DRS_CUDA(cudaGetLastError());
+  return DRS_OK;
+}
+
+extern "C" int drs_fw_wait_words(int32_t n, const int32_t* const* words, int32_t value, int64_t timeout_ms,
+                                 int32_t* timed_out_dev, void* stream) {
+  DRS_REQUIRE(n >= 0 && n <= DRS_MAX_PEERS + 1 && (n == 0 || words) && timed_out_dev, DRS_ERR_ARG, "drs_fw_wait_words: bad argument");
+  if (n == 0) return DRS_OK;
+  WordList wl{};
+  wl.n = n;
+  for (int i = 0; i < n; ++i) wl.w[i] = const_cast<int32_t*>(words[i]);
+  static int khz = 0;          // cudaDevAttrClockRate is a slow query (milliseconds): ask once
+  if (!khz) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev) != cudaSuccess || khz <= 0) khz = 1965000;
+  }
+  wait_words_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(wl, value, (long long)timeout_ms * khz, timed_out_dev);
+  drs_count_launch();
+  DRS_CUDA(cudaGetLastError());
+  return DRS_OK;
+}
+
+extern "C" int drs_fw_pivot_row_p2p(int32_t mode, void* panel_dev, int64_t ld, int32_t kb, int32_t n_peers,
+                                    void* const* peer_panels, int32_t* const* peer_signal_words, int32_t signal_value,
+                                    void* stream) {
+  DRS_REQUIRE(panel_dev && ld > 0 && ld % TILE == 0 && kb >= 0 && kb < ld / TILE, DRS_ERR_ARG,
+              "drs_fw_pivot_row_p2p: bad argument (ld=%lld kb=%d)", (long long)ld, kb);
+  DRS_REQUIRE(n_peers >= 0 && n_peers <= DRS_MAX_PEERS && (n_peers == 0 || (peer_panels && peer_signal_words)), DRS_ERR_ARG,
+              "drs_fw_pivot_row_p2p: at most %d peers", DRS_MAX_PEERS);
+  int rc;
+  if (mode == DRS_MODE_F32) rc = pivot_row_impl<float>((float*)panel_dev, ld, kb, (cudaStream_t)stream, n_peers, peer_panels);
+  else if (mode == DRS_MODE_I32) rc = pivot_row_impl<int>((int*)panel_dev, ld, kb, (cudaStream_t)stream, n_peers, peer_panels);
+  else DRS_REQUIRE(false, DRS_ERR_ARG, "drs_fw_pivot_row_p2p: unknown mode %d", mode);
+  if (rc) return rc;
+  return drs_fw_post_words(n_peers, peer_signal_words, signal_value, stream);
 }
 
 extern "C" int drs_fw_update(int32_t mode, void* local_dev, int64_t ld, int32_t nrows, const void* panel_dev,

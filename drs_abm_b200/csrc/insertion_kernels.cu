@@ -1,22 +1,21 @@
 // (vehicle, pickup slot, drop-off slot) insertion evaluation and argmin.
 //
 // Replaces Model.insert_heuristics / test_constraints_get_cost
-// (lib/Agents.py:1451-1572).  Per (vehicle, request) pair the kernel gathers the
-// 4L+3 travel times between the request's origin / destination and the vehicle's
-// L planned stops (plus the L segment times of the plan itself) from the resident
-// matrix and walks every candidate route in fp64 with the reference's operation
-// order, so costs are bit-identical for integer-weighted maps.
+// (lib/Agents.py:1451-1572).  Every candidate route is walked in fp64 with the
+// reference's operation order, so costs are bit-identical for integer-weighted maps;
+// travel times are gathered from the resident matrix.
 //
-//   insertion_scan_kernel   one thread per (vehicle, request) pair, requests
-//       fastest: a warp shares the vehicle (uniform control flow, broadcast plan
-//       loads) and its gathers stay inside the plan stops' matrix rows.  Every
-//       (i, j) candidate is evaluated WITHOUT the incumbent bound; the pair's
+//   plan_prep_kernel        per vehicle: plan segment times and the walk of the
+//       unmodified plan (the common prefix of every candidate), slot-major.
+//   insertion_scan_kernel   one thread per (request, vehicle) pair, vehicles fastest:
+//       every (i, j) candidate is evaluated WITHOUT the incumbent bound and the pair's
 //       smallest successful total cost is written out (+inf if none).
-//   insertion_fold_kernel   one thread per request walks the vehicles in the
+//   insertion_fold_kernel   one warp per request walks the vehicles in the
 //       reference's order.  A vehicle can only change the incumbent if its
 //       smallest cost is <= the bound C = veh.c + dc (lib/Agents.py:1470); only
 //       then is the pair re-scanned exactly as the reference does it -- with the
-//       bound, "last equal-or-better wins" and the viol-code loop breaks.
+//       bound, "last equal-or-better wins" and the viol-code loop breaks
+//       (load_pair / eval_candidate below are that literal restatement).
 #include <algorithm>
 #include <cstring>
 

@@ -42,6 +42,7 @@ typedef struct drs_graph drs_graph;
 
 /* tile edge of the blocked Floyd-Warshall: matrices are padded to a multiple */
 #define DRS_FW_TILE 128
+#define DRS_MAX_PEERS 15 /* peers a fused pivot step can store to (one host: <= 16 GPUs) */
 
 const char* drs_last_error(void);
 int drs_version(void);
@@ -141,6 +142,29 @@ int drs_fw_pivot_row(int32_t mode, void* panel_dev, int64_t ld, int32_t kb, void
 int drs_fw_update(int32_t mode, void* local_dev, int64_t ld, int32_t nrows, const void* panel_dev,
                   int32_t kb, int32_t skip_local_block, int32_t block_lo, int32_t block_hi,
                   void* stream);
+/* ---- fused pivot step + broadcast over NVLink peer memory (multi-GPU FW) ----
+ * Each rank allocates one communication block with drs_p2p_alloc (device memory + a CUDA IPC
+ * handle the other ranks open with drs_p2p_open).  Layout of a block (see drs_p2p_layout):
+ * signal words, acknowledgement words, a time-out word and two DRS_FW_TILE x ld panel buffers.
+ * drs_fw_pivot_row_p2p is drs_fw_pivot_row whose tile epilogues ALSO store every finished tile of
+ * the pivot panel straight into each peer's panel buffer (P2P stores: the transfer overlaps the
+ * tile arithmetic), followed by a release of the peers' signal word for round kb.  Receivers order
+ * their stream behind the signal with drs_fw_wait_word; before a panel buffer is overwritten the
+ * owner waits for the peers' acknowledgements of the round that last used it.  Every wait has a
+ * time-out (it sets the block's time-out word instead of hanging). */
+int drs_p2p_alloc(int64_t bytes, void** dev_ptr, unsigned char* ipc_handle_64);
+int drs_p2p_open(const unsigned char* ipc_handle_64, void** peer_ptr);
+int drs_p2p_close(void* peer_ptr);
+int drs_p2p_free(void* dev_ptr);
+int drs_fw_pivot_row_p2p(int32_t mode, void* panel_dev, int64_t ld, int32_t kb, int32_t n_peers,
+                         void* const* peer_panels, int32_t* const* peer_signal_words, int32_t signal_value,
+                         void* stream);
+/* stream-ordered: store `value` (system-scope release) into n remote or local words */
+int drs_fw_post_words(int32_t n, int32_t* const* words, int32_t value, void* stream);
+/* stream-ordered: wait until each of the n words is >= value; on time-out set *timed_out_dev = 1 */
+int drs_fw_wait_words(int32_t n, const int32_t* const* words, int32_t value, int64_t timeout_ms,
+                      int32_t* timed_out_dev, void* stream);
+
 /* canonical predecessor edges for rows [row0, row0+nrows) from finished
  * distances (rule: DESIGN.md "canonical predecessor"). */
 int drs_pred_build(const drs_graph* g, int32_t mode, const void* local_dev, int64_t ld,
