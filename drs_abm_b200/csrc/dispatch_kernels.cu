@@ -56,9 +56,15 @@ __device__ __forceinline__ double trip_tt(const Trip& tr, int a, int b) {
 // Orderings are visited in lexicographic stop-index order and only a strictly
 // smaller cost replaces the incumbent (:447), i.e. the canonical tie rule.
 // first_only: return as soon as one feasible complete ordering is found.
+// The enumeration is exact and therefore exponential in the number of stops (as in the reference); a
+// budget on visited search nodes turns a hopeless instance into an error instead of a kernel that runs
+// for hours (*exhausted is set; the host reports it).
+constexpr long long kSearchBudget = 20000000LL;   // ~20x the largest instance of a K=4 fleet (10 stops: 113 400 orderings)
+
 __device__ double trip_dfs(const Trip& tr, unsigned subset, double cap, int pax0, bool first_only,
-                           uint8_t* best_order) {
+                           uint8_t* best_order, bool* exhausted) {
   const int total = __popc(subset);
+  long long visited = 0;
   double best = DRS_INF_ROUTE_COST;
   int ord[MAXS];
   int cand[MAXS + 1];
@@ -68,6 +74,7 @@ __device__ double trip_dfs(const Trip& tr, unsigned subset, double cap, int pax0
   int d = 0;
   cand[0] = 0; psum[0] = 0.0; cost[0] = 0.0; pax[0] = pax0; cur[0] = 0;
   while (d >= 0) {
+    if (++visited > kSearchBudget) { *exhausted = true; break; }
     int i = cand[d];
     // next admissible stop at this depth
     while (i < tr.ns) {
@@ -119,7 +126,7 @@ __device__ double trip_dfs(const Trip& tr, unsigned subset, double cap, int pax0
 
 // findOptimalRouting (lib/optimUtils.py:113-160) on a prepared Trip.
 // n_groups = number of distinct requests; groups [0, n_new) are the new ones.
-__device__ double trip_solve(const Trip& tr, int n_groups, int n_new, int flags, uint8_t* best_order) {
+__device__ double trip_solve(const Trip& tr, int n_groups, int n_new, int flags, uint8_t* best_order, bool* exhausted) {
   const unsigned all = (tr.ns >= 32) ? 0xffffffffu : ((1u << tr.ns) - 1u);
   if ((flags & DRS_EVAL_PAIRWISE_CHECKS) && tr.has_start && n_groups >= 3) {
     for (int a = 0; a < n_groups; ++a)
@@ -129,11 +136,11 @@ __device__ double trip_solve(const Trip& tr, int n_groups, int n_new, int flags,
         for (int i = 0; i < tr.ns; ++i)
           if (tr.group[i] == a || tr.group[i] == b) sub |= 1u << i;
         // minimalDelayPath(comboLocs, G, startTime, startLoc): default capacity 1e6, startPax 0 (:148-149)
-        const double c = trip_dfs(tr, sub, 1e6, 0, true, nullptr);
+        const double c = trip_dfs(tr, sub, 1e6, 0, true, nullptr, exhausted);
         if (!(c < DRS_INF_ROUTE_COST)) return DRS_INF_ROUTE_COST;
       }
   }
-  return trip_dfs(tr, all, tr.cap, tr.pax0, false, best_order);
+  return trip_dfs(tr, all, tr.cap, tr.pax0, false, best_order, exhausted);
 }
 
 struct TaskList {
@@ -197,7 +204,9 @@ __global__ void trip_eval_kernel(TickDev tk, DistView dv, double T, int flags, i
   int ns = -1;   // -1: too many stops for DRS_MAX_STOPS
   if (build_trip(tr, tk, dv, T, tl.veh[k], tl.nreq[k], tl.req + (int64_t)k * MAXR, &groups)) {
     ns = tr.ns;
-    cost = trip_solve(tr, groups, tl.nreq[k], flags, order);
+    bool exhausted = false;
+    cost = trip_solve(tr, groups, tl.nreq[k], flags, order, &exhausted);
+    if (exhausted) ns = -2;
   }
   cost_out[k] = cost;
   nstops_out[k] = ns;
@@ -271,7 +280,9 @@ __global__ void rv_eval_kernel(TickDev tk, DistView dv, double T, int flags, int
   int32_t one = r;
   if (build_trip(tr, tk, dv, T, v, 1, &one, &groups)) {
     ns = tr.ns;
-    cost = trip_solve(tr, groups, 1, flags, order);
+    bool exhausted = false;
+    cost = trip_solve(tr, groups, 1, flags, order, &exhausted);
+    if (exhausted) { ns = -2; cost = DRS_INF_ROUTE_COST; }
   }
   status[(int64_t)v * tk.n_req + r] = (int8_t)((cost < DRS_INF_ROUTE_COST) ? DRS_RV_FEASIBLE : DRS_RV_INFEASIBLE);
   cost_out[k] = cost;
@@ -492,8 +503,11 @@ extern "C" int drs_tick_rv_fetch(drs_tick* t, int32_t capacity_edges, int32_t* v
   DRS_CUDA(cudaMemcpyAsync(nst.data(), t->d_nstops, sizeof(int32_t) * ns, cudaMemcpyDeviceToHost, st));
   DRS_CUDA(cudaMemcpyAsync(o.data(), t->d_order, (size_t)ns * MAXS, cudaMemcpyDeviceToHost, st));
   DRS_CUDA(cudaStreamSynchronize(st));
-  for (int k = 0; k < ns; ++k)
+  for (int k = 0; k < ns; ++k) {
+    DRS_REQUIRE(nst[k] != -2, DRS_ERR_CAPACITY,
+                "drs_tick_rv_fetch: exact ordering search for vehicle %d + request %d exceeded its budget (too many stops to enumerate)", v[k], r[k]);
     DRS_REQUIRE(nst[k] >= 0, DRS_ERR_ARG, "drs_tick_rv_fetch: vehicle %d + request %d exceed DRS_MAX_STOPS", v[k], r[k]);
+  }
   std::vector<int> idx;
   idx.reserve(ns);
   for (int k = 0; k < ns; ++k)
@@ -560,8 +574,11 @@ extern "C" int drs_tick_trip_eval(drs_tick* t, double T, int32_t flags, int32_t 
     drs_set_error("drs_tick_trip_eval: %s", cudaGetErrorString(e));
     return DRS_ERR_CUDA;
   }
-  for (int k = 0; k < n_tasks; ++k)
+  for (int k = 0; k < n_tasks; ++k) {
+    DRS_REQUIRE(nst[k] != -2, DRS_ERR_CAPACITY,
+                "drs_tick_trip_eval: exact ordering search for task %d exceeded its budget (too many stops to enumerate)", k);
     DRS_REQUIRE(nst[k] >= 0, DRS_ERR_ARG, "drs_tick_trip_eval: task %d exceeds DRS_MAX_STOPS (%d)", k, DRS_MAX_STOPS);
+  }
   if (n_stops_host) std::memcpy(n_stops_host, nst.data(), sizeof(int32_t) * n_tasks);
   return DRS_OK;
 }
