@@ -442,7 +442,7 @@ def main():
     # ALU roofline denominator, measured live (rank 0): best add+min stream of the three instruction mixes
     alu = {}
     if rank == 0:
-        for v, name in ((0, "fadd_fmnmx"), (1, "viaddmnmx_s32"), (2, "fadd_fadd_fmnmx3")):
+        for v, name in ((0, "fadd_fadd_fmnmx3"), (1, "viaddmnmx_s32"), (2, "fadd2_fmnmx3")):
             r = __import__("ctypes").c_double()
             _lib.check(lib.drs_alu_peak(v, 8000, __import__("ctypes").byref(r)), lib)
             alu[name] = r.value

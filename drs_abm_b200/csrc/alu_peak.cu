@@ -1,43 +1,54 @@
 // Register-resident add+min stream: the ALU roofline denominator for the
 // Floyd-Warshall tiles (SURVEY.md section 8d asks the build to measure one).
 // Same shape as the FW inner loop (64 independent accumulators per thread, 8+8
-// operands) but operands never leave registers, so the result is the issue-rate
-// ceiling of the add+min instruction pair on this GPU at its running clock.
+// operands per k) but operands never leave registers, so the result is the ceiling
+// of the add+min relaxation on this GPU at its running clock.  Measured on B200: all
+// instruction mixes (2xFADD+FMNMX3, FADD2+FMNMX3, 2xFFMA-imm+FMNMX3, VIADDMNMX) saturate
+// at ~60-63 relaxations/clk/SM although FADD alone issues at ~109 and FMNMX3 alone at
+// ~61 warp-lanes/clk/SM: the pair is limited by register-operand bandwidth (7 operand
+// reads per two relaxations), not by either pipe or by issue slots.
 #include "drs_common.cuh"
 
 namespace {
 
+// Every body uses its own operand pair (a0[r], b0[c]) / (a1[r], b1[c]); no two bodies share a sum, so
+// the compiler cannot merge adds (an earlier probe that reused sums across bodies over-reported by 1.4x).
 template <int VAR>
 __global__ void __launch_bounds__(256, 2) alu_stream_kernel(float* out, int iters, float seed) {
   float accf[64]; int acci[64];
-  float af[8], bf[8]; int ai[8], bi[8];
+  float a0[8], a1[8], b0[8], b1[8]; int ai[8], bi[8], ai1[8], bi1[8];
 #pragma unroll
-  for (int i = 0; i < 64; ++i) { accf[i] = 1e30f; acci[i] = DRS_I32_INF; }
+  for (int i = 0; i < 64; ++i) { accf[i] = 1e30f + i; acci[i] = DRS_I32_INF - i; }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    af[i] = seed + threadIdx.x * 0.001f + i; bf[i] = seed * 2 + i * 3 + blockIdx.x;
-    ai[i] = (int)af[i] * 1000; bi[i] = (int)bf[i] * 1000;
+    a0[i] = seed + threadIdx.x * 0.001f + i; a1[i] = seed * 1.7f + i * 0.3f;
+    b0[i] = seed * 2 + i * 3 + blockIdx.x; b1[i] = seed * 0.9f + i * 1.1f;
+    ai[i] = (int)a0[i] * 1000; bi[i] = (int)b0[i] * 1000; ai1[i] = (int)a1[i] * 777; bi1[i] = (int)b1[i] * 333;
   }
   for (int it = 0; it < iters; ++it) {
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
+    for (int kk = 0; kk < 2; ++kk) {   // 2 x 64 bodies x 2 relaxations = 4 x 64 relaxations per iteration
 #pragma unroll
       for (int r = 0; r < 8; ++r)
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          if (VAR == 0) {          // FADD + FMNMX
-            accf[r * 8 + c] = fminf(accf[r * 8 + c], af[r] + bf[c]);
-          } else if (VAR == 1) {   // VIADDMNMX
-            acci[r * 8 + c] = __viaddmin_s32(ai[r], bi[c], acci[r * 8 + c]);
-          } else {                 // 2 x FADD + FMNMX3 (two relaxations per body)
-            if (kk & 1) continue;
-            float d, s0 = af[r] + bf[c], s1 = af[(r + 1) & 7] + bf[(c + 3) & 7];
+          if (VAR == 0) {          // 2 x FADD + FMNMX3
+            float d, s0 = a0[r] + b0[c], s1 = a1[r] + b1[c];
             asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(accf[r * 8 + c]), "f"(s0), "f"(s1));
+            accf[r * 8 + c] = d;
+          } else if (VAR == 1) {   // 2 x VIADDMNMX
+            acci[r * 8 + c] = __viaddmin_s32(ai1[r], bi1[c], __viaddmin_s32(ai[r], bi[c], acci[r * 8 + c]));
+          } else {                 // FADD2 (packed fp32x2 add, sm_100) + FMNMX3
+            const float2 s = __fadd2_rn(make_float2(a0[r], a1[r]), make_float2(b0[c], b1[c]));
+            float d;
+            asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(accf[r * 8 + c]), "f"(s.x), "f"(s.y));
             accf[r * 8 + c] = d;
           }
         }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { af[i] += 1.0f; bf[i] += 0.5f; ai[i] += 3; bi[i] += 1; }
+      for (int i = 0; i < 8; ++i) {
+        a0[i] += 1.0f; a1[i] += 0.25f; b0[i] += 0.5f; b1[i] += 0.125f; ai[i] += 3; bi[i] += 1; ai1[i] += 5; bi1[i] += 7;
+      }
     }
   }
   float s = 0; int si = 0;

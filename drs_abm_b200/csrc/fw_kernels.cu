@@ -30,6 +30,7 @@ constexpr int NTHREADS = 256;
 
 template <typename T> struct Semiring;
 template <> struct Semiring<float> {
+  static constexpr bool packed = true;    // sm_100 packed fp32x2 add (FADD2) in the tile kernel
   static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
   // acc = min(acc, a0+b0, a1+b1): two FADD + one 3-input FMNMX3 (sm_100+)
   static __device__ __forceinline__ float relax2(float acc, float a0, float b0, float a1, float b1) {
@@ -41,6 +42,7 @@ template <> struct Semiring<float> {
   static __device__ __forceinline__ float relax1(float acc, float a, float b) { return fminf(acc, a + b); }
 };
 template <> struct Semiring<int> {
+  static constexpr bool packed = false;
   static __device__ __forceinline__ int inf() { return DRS_I32_INF; }
   // VIADDMNMX: add and min in one DPX instruction
   static __device__ __forceinline__ int relax2(int acc, int a0, int b0, int a1, int b1) {
@@ -59,6 +61,10 @@ template <> struct Vec2<int> { using type = int2; };
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() {
@@ -95,6 +101,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) fw_minplus_tile_kernel(TileArgs<T
 
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
+  constexpr bool kPacked = Semiring<T>::packed;
 
   auto load_chunk = [&](int kc, int stage) {
     const int k0 = kc * KC;
@@ -104,11 +111,23 @@ __global__ void __launch_bounds__(NTHREADS, 2) fw_minplus_tile_kernel(TileArgs<T
       const int row = v >> 3, cv = v & 7;
       cp_async16(&As[stage][row][cv * 4], A + (int64_t)row * p.lda + k0 + cv * 4);
     }
+    if (kPacked) {
+      // fp32: B is stored k-pair interleaved, Bs2[k/2][column] = (b[k][column], b[k+1][column]), so that one
+      // 8-byte shared load yields the operand pair of a packed add (FADD2) -- 4-byte cp.async, coalesced per row
+      float* Bf = reinterpret_cast<float*>(&Bs[stage][0][0]);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {   // B chunk: 32 k x 128 columns
-      const int v = tid + NTHREADS * q;
-      const int row = v >> 5, cv = v & 31;
-      cp_async16(&Bs[stage][row][cv * 4], B + (int64_t)(k0 + row) * p.ldb + cv * 4);
+      for (int q = 0; q < 16; ++q) {
+        const int e = tid + NTHREADS * q;
+        const int row = e >> 7, col = e & 127;
+        cp_async4(Bf + ((row >> 1) * TILE + col) * 2 + (row & 1), B + (int64_t)(k0 + row) * p.ldb + col);
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {   // B chunk: 32 k x 128 columns
+        const int v = tid + NTHREADS * q;
+        const int row = v >> 5, cv = v & 31;
+        cp_async16(&Bs[stage][row][cv * 4], B + (int64_t)(k0 + row) * p.ldb + cv * 4);
+      }
     }
   };
 
@@ -137,6 +156,34 @@ __global__ void __launch_bounds__(NTHREADS, 2) fw_minplus_tile_kernel(TileArgs<T
     if (kc + STAGES - 1 < NCHUNK) load_chunk(kc + STAGES - 1, (kc + STAGES - 1) % STAGES);
     cp_async_commit();
 
+    if (kPacked) {
+      // acc = min3(acc, a0+b0, a1+b1) with BOTH sums from one packed add: 1 FADD2 + 1 FMNMX3 per two
+      // relaxations = one issue slot per relaxation (the scalar form needs 1.5)
+      const float2* Bp = reinterpret_cast<const float2*>(&Bs[stage][0][0]);
+#pragma unroll
+      for (int kk = 0; kk < KC; kk += 2) {
+        float2 a[8], b[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) a[r] = *reinterpret_cast<const float2*>(&As[stage][ty + 16 * r][kk]);
+        const float2* brow = Bp + (kk >> 1) * TILE;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float4 q0 = *reinterpret_cast<const float4*>(brow + h * 64 + tx * 4);       // columns +0, +1
+          const float4 q1 = *reinterpret_cast<const float4*>(brow + h * 64 + tx * 4 + 2);   // columns +2, +3
+          b[h * 4 + 0] = make_float2(q0.x, q0.y); b[h * 4 + 1] = make_float2(q0.z, q0.w);
+          b[h * 4 + 2] = make_float2(q1.x, q1.y); b[h * 4 + 3] = make_float2(q1.z, q1.w);
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float2 sum = __fadd2_rn(a[r], b[c]);
+            float d;
+            asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"((float)acc[r][c]), "f"(sum.x), "f"(sum.y));
+            acc[r][c] = (T)d;
+          }
+      }
+    } else {
 #pragma unroll
     for (int kk = 0; kk < KC; kk += 2) {   // two k per step: acc = min3(acc, a0+b0, a1+b1)
       V2 a[8];
@@ -152,6 +199,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) fw_minplus_tile_kernel(TileArgs<T
       for (int r = 0; r < 8; ++r)
 #pragma unroll
         for (int c = 0; c < 8; ++c) acc[r][c] = Semiring<T>::relax2(acc[r][c], a[r].x, b0[c], a[r].y, b1[c]);
+    }
     }
   }
   cp_async_wait<0>();

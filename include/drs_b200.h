@@ -353,8 +353,8 @@ int drs_apsp_last_profile(const drs_graph* g, double* ms, int32_t* rounds);
 
 /* ------------------------------------------------------------- ALU peak ---
  * Register-resident add+min stream used as the ALU roofline denominator
- * (SURVEY.md section 8d).  Returns relaxations per second of the fp32
- * FADD+FMNMX pair stream (variant 0) or the int32 stream (variant 1). */
+ * (SURVEY.md section 8d).  Returns relaxations per second of the stream
+ * 2xFADD+FMNMX3 (variant 0), 2xVIADDMNMX int32 (variant 1) or FADD2+FMNMX3 (variant 2). */
 int drs_alu_peak(int32_t variant, int32_t iters, double* relax_per_s);
 
 #ifdef __cplusplus
