@@ -272,31 +272,37 @@ __global__ void __launch_bounds__(128) insertion_scan_kernel(PlanView pv, DistVi
     const int K = pv.cap[v];
     const double T = pv.clock[v];
     double to_o[MAXL + 1], to_d[MAXL + 1], from_o[MAXL], from_d[MAXL], cld_cur[MAXL];
+    // origin-side travel times first: most vehicles cannot reach the pickup in time at any position, and
+    // for those the destination-side gathers (half of the traffic) are never needed
     {
       const int start = pv.node[v];
-      if (pv.directed) {
-        to_o[0] = (start == o) ? 0.0 : dv.at(start, o);
-        to_d[0] = (start == d) ? 0.0 : dv.at(start, d);
-      } else {
-        to_o[0] = (start == o) ? 0.0 : dv.at(o, start);
-        to_d[0] = (start == d) ? 0.0 : dv.at(d, start);
-      }
+      to_o[0] = (start == o) ? 0.0 : (pv.directed ? dv.at(start, o) : dv.at(o, start));
       for (int k = 0; k < L; ++k) {
         const int nd = pv.m_node[k * nv + vs];
         from_o[k] = (o == nd) ? 0.0 : dv.at(o, nd);
+        to_o[k + 1] = pv.directed ? ((nd == o) ? 0.0 : dv.at(nd, o)) : from_o[k];
+      }
+    }
+    bool reachable = false;
+    {
+      const double clp = pv.q_clp[rq], cep = pv.q_cep[rq];
+      for (int a = 0; a <= L && a <= bviol; ++a) {
+        const double t = pv.m_base_t[a * nv + vs] + to_o[a];      // same sum walk_stop forms for the pickup
+        if (T + t < cep || !(T + t > clp)) { reachable = true; break; }
+      }
+    }
+    if (reachable) {
+      const int start = pv.node[v];
+      to_d[0] = (start == d) ? 0.0 : (pv.directed ? dv.at(start, d) : dv.at(d, start));
+      for (int k = 0; k < L; ++k) {
+        const int nd = pv.m_node[k * nv + vs];
         from_d[k] = (d == nd) ? 0.0 : dv.at(d, nd);
-        if (pv.directed) {
-          to_o[k + 1] = (nd == o) ? 0.0 : dv.at(nd, o);
-          to_d[k + 1] = (nd == d) ? 0.0 : dv.at(nd, d);
-        } else {                       // undirected graph: the matrix is symmetric
-          to_o[k + 1] = from_o[k];
-          to_d[k + 1] = from_d[k];
-        }
+        to_d[k + 1] = pv.directed ? ((nd == d) ? 0.0 : dv.at(nd, d)) : from_d[k];
       }
     }
     const double od = (o == d) ? 0.0 : dv.at(o, d);
     int occ_before = pv.onboard[v];    // occupancy before plan stop a in the unmodified plan
-    for (int a = 0; a <= L && a <= bviol; ++a) {
+    for (int a = 0; reachable && a <= L && a <= bviol; ++a) {
       if (a > 0) {
         cld_cur[a - 1] = pv.m_base_cld[(a - 1) * nv + vs];
         occ_before += pv.m_pod[(a - 1) * nv + vs];

@@ -39,7 +39,7 @@ class Vertex(object):
     def __setitem__(self, key, value):
         self.graph._vattrs.setdefault(key, [None] * self.graph.n)[self.index] = value
         if key in ("name", "lng", "lat"):
-            self.graph._index_nodes()
+            self.graph._by_name = self.graph._by_coord = None
 
     def attributes(self):
         return {k: v[self.index] for k, v in self.graph._vattrs.items()}
@@ -172,7 +172,7 @@ class RoadGraph(object):
         self._handle = None
         self._weight_attr = None      # attribute the device weights / matrix were built from
         self._lib = None
-        self._index_nodes()
+        self._by_name = self._by_coord = None    # name / coordinate indexes are built on first look-up
 
     # ------------------------------------------------------------------ igraph surface
     @classmethod
@@ -226,6 +226,7 @@ class RoadGraph(object):
 
     # ------------------------------------------------------------------ node identity
     def _index_nodes(self):
+        """(Re)builds the name -> vertex and (lng, lat) -> vertex dictionaries."""
         names = self._vattrs.get("name")
         self._by_name = {}
         if names is not None:
@@ -246,6 +247,8 @@ class RoadGraph(object):
         ``"(3, 4)"``, ``"(3.0, 4.0)"`` and numpy-2 reprs such as
         ``"(np.float64(3.0), np.float64(4.0))"`` equivalent.
         Unknown -> ValueError (igraph's behaviour)."""
+        if self._by_name is None:
+            self._index_nodes()
         i = self._by_name.get(name)
         if i is not None:
             return i
@@ -258,6 +261,8 @@ class RoadGraph(object):
         raise ValueError("no such vertex: %r" % (name,))
 
     def node_of_location(self, lng, lat):
+        if self._by_coord is None:
+            self._index_nodes()
         i = self._by_coord.get((float(lng), float(lat)))
         if i is None:
             return self.node_index(str((lng, lat)))
