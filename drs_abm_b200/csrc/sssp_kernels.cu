@@ -52,13 +52,18 @@ template <typename T, int SSSP_THREADS, int SSSP_S>
 __global__ void __launch_bounds__(SSSP_THREADS) sssp_batch_kernel(
     int n, const int32_t* __restrict__ out_ptr, const int2* __restrict__ arcs, T* dist, int64_t ld, int64_t row_stride,
     const int32_t* __restrict__ sources, int nsrc, Entry* queues, int cap, T delta, int* overflow) {
-  __shared__ int s_near, s_next, s_far, s_keep, s_min;
+  __shared__ int s_near, s_next, s_far, s_keep, s_min, s_group;
+  int* next_group = overflow + 1;   // dynamic work distribution: searches differ in length (corner vs centre sources)
   Entry* cur = queues + (int64_t)blockIdx.x * 4 * cap;
   Entry* nxt = cur + cap;
   Entry* far = nxt + cap;
   Entry* far2 = far + cap;
   const int tid = threadIdx.x;
-  for (int k0 = blockIdx.x * SSSP_S; k0 < nsrc; k0 += gridDim.x * SSSP_S) {
+  while (true) {
+    if (tid == 0) s_group = atomicAdd(next_group, 1);
+    __syncthreads();
+    const int k0 = s_group * SSSP_S;
+    if (k0 >= nsrc) break;
     const int ns = min(SSSP_S, nsrc - k0);
     T* rows = dist + (int64_t)k0 * row_stride;
     for (int sl = 0; sl < ns; ++sl)
@@ -270,7 +275,7 @@ extern "C" int drs_sssp_batch_dev(const drs_graph* g, int32_t mode, int32_t nsrc
   if (gm->sssp_sources_cap < nsrc) {
     if (gm->sssp_sources) cudaFree(gm->sssp_sources);
     gm->sssp_sources = nullptr; gm->sssp_sources_cap = 0;
-    DRS_CUDA(cudaMalloc((void**)&gm->sssp_sources, sizeof(int32_t) * (size_t)nsrc + sizeof(int)));
+    DRS_CUDA(cudaMalloc((void**)&gm->sssp_sources, sizeof(int32_t) * (size_t)nsrc + 2 * sizeof(int)));
     gm->sssp_sources_cap = nsrc;
   }
   int32_t* d_sources = gm->sssp_sources;
@@ -288,7 +293,7 @@ extern "C" int drs_sssp_batch_dev(const drs_graph* g, int32_t mode, int32_t nsrc
       }
       gm->sssp_queue_bytes = need;
     }
-    cudaMemsetAsync(d_overflow, 0, sizeof(int), st);
+    cudaMemsetAsync(d_overflow, 0, 2 * sizeof(int), st);   // overflow flag + work counter
     cudaMemcpyAsync(d_sources, sources_host, sizeof(int32_t) * nsrc, cudaMemcpyHostToDevice, st);
     if (mode == DRS_MODE_F32)
       rc = sssp_run<float>(g, nsrc, d_sources, (float*)dist_dev, ld, ld, delta, st, (const int2*)gm->sssp_arcs,
