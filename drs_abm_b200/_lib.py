@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdrs_b200.so")
+LIB_PATH = os.environ.get("DRS_B200_LIB") or os.path.join(_HERE, "libdrs_b200.so")   # env override: kernel-variant experiments
 
 MODE_F32 = 0
 MODE_I32 = 1

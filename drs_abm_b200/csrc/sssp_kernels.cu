@@ -48,8 +48,11 @@ constexpr int VERTEX_MASK = (1 << SLOT_SHIFT) - 1;
 // One CTA advances SSSP_S sources in lock step: their wavefronts pass the same distance buckets at the
 // same time, so one near queue / far pile / theta serves all of them and every barrier and dependent L2
 // round trip of an iteration is shared by SSSP_S searches (the kernel is latency bound, not bandwidth bound).
+#ifndef DRS_SSSP_MIN_THREADS_PER_SM
+#define DRS_SSSP_MIN_THREADS_PER_SM 1152   // resident threads per SM the register allocation must allow (measured best)
+#endif
 template <typename T, int SSSP_THREADS, int SSSP_S>
-__global__ void __launch_bounds__(SSSP_THREADS) sssp_batch_kernel(
+__global__ void __launch_bounds__(SSSP_THREADS, DRS_SSSP_MIN_THREADS_PER_SM / SSSP_THREADS) sssp_batch_kernel(
     int n, const int32_t* __restrict__ out_ptr, const int2* __restrict__ arcs, T* dist, int64_t ld, int64_t row_stride,
     const int32_t* __restrict__ sources, int nsrc, Entry* queues, int cap, T delta, int* overflow) {
   __shared__ int s_near, s_next, s_far, s_keep, s_min, s_group;
@@ -226,6 +229,11 @@ int sssp_grid(int sms, int nsrc) {
   sssp_dispatch<T>(true, &per_sm, 0, (cudaStream_t) nullptr, 0, (const int32_t*)nullptr, (const int2*)nullptr, (T*)nullptr,
                    (int64_t)0, (int64_t)0, (const int32_t*)nullptr, 0, (Entry*)nullptr, 0, (T)0, (int*)nullptr);
   const int groups = (nsrc + sssp_slots() - 1) / sssp_slots();
+  // CTAs in flight per SM: every CTA keeps one distance row (4n bytes) hot, and the rows of all resident CTAs
+  // should stay in the 126 MB L2 (the kernel runs at >70 % of L2 throughput); DRS_SSSP_CTAS_PER_SM overrides
+  static int cap_per_sm = -1;
+  if (cap_per_sm < 0) { const char* e = getenv("DRS_SSSP_CTAS_PER_SM"); cap_per_sm = e ? atoi(e) : 0; }
+  if (cap_per_sm > 0) per_sm = std::min(per_sm, cap_per_sm);
   return std::max(1, std::min(groups, sms * std::max(per_sm, 1)));
 }
 

@@ -551,6 +551,45 @@ class RoutingEngine(object):
         """lib/RoutingEngine.py:228-229: ``rs.choice(G.vs)`` draws exactly one ``randint(0, n)``."""
         return self.G.vs[int(self.rs.randint(0, self.G.n))]
 
+    def offer_queries(self, vehs, trips, num_closest_vehs=3):
+        """The routing half of ``Fleet.generate_offer`` (lib/Agents.py:875-923) for a batch of arriving trips in ONE
+        device query: per trip the ``num_closest_vehs`` vehicles closest by crow-flies distance among those with a
+        free seat (``get_n_closest_vehs``, lib/Agents.py:1208-1223: equirectangular metres, stable argsort, full
+        vehicles pushed to 1e10), ``get_duration(vehicle's next node -> origin) + delay`` for each of them
+        (lib/Agents.py:898), and ``get_duration`` / ``get_distance`` origin -> destination (lib/Agents.py:904,923).
+        The KDE-conditioned pdfs stay on the host.  ``trips`` need ``olng, olat, dlng, dlat``.
+
+        Returns a list with one dict per trip: closest (vehicle objects), veh_dists, direct_wt (list), direct_tt, distance.
+        """
+        G = self.G
+        locs = [veh.get_next_node() for veh in vehs]
+        vlng = np.array([l[0][0] for l in locs], dtype=np.float64)
+        vlat = np.array([l[0][1] for l in locs], dtype=np.float64)
+        free = np.array([veh.n < veh.K for veh in vehs], dtype=bool)
+        s, t, meta = [], [], []
+        for trip in trips:
+            # math.cos per vehicle, like the reference (numpy's vectorised cos may differ in the last bit)
+            cosv = np.array([math.cos(x) for x in (vlat + trip.olat) * math.pi / 360])
+            gc = 6371000 * 2 * math.pi / 360 * np.sqrt((cosv * (vlng - trip.olng)) ** 2 + (vlat - trip.olat) ** 2)
+            dists = np.where(free, gc, 1e10)
+            order = np.argsort(dists)[:num_closest_vehs]          # np.argsort: same (quicksort) order as the reference
+            o = G.node_of_location(trip.olng, trip.olat)
+            d = G.node_of_location(trip.dlng, trip.dlat)
+            for k in order:
+                s.append(G.node_of_location(vlng[k], vlat[k])); t.append(o)
+            s.append(o); t.append(d)
+            meta.append((order, dists[order]))
+        tt, ln, hops = G.path_sums(s, t, self.ttweight) if s else (np.zeros(0), np.zeros(0), np.zeros(0, dtype=np.int32))
+        out, pos = [], 0
+        for (order, vd) in meta:
+            k = len(order)
+            wt = [(float(tt[pos + i]) if hops[pos + i] > 0 else 0) + locs[order[i]][1] for i in range(k)]
+            od = pos + k
+            out.append({"closest": [vehs[i] for i in order], "veh_dists": [float(x) for x in vd], "direct_wt": wt,
+                        "direct_tt": float(tt[od]) if hops[od] > 0 else 0, "distance": float(ln[od]) if hops[od] > 0 else 0})
+            pos += k + 1
+        return out
+
     # ---- batched extensions (not in the reference; same results as calling the scalar methods in a loop)
     def get_durations(self, pairs):
         """pairs: iterable of (olng, olat, dlng, dlat) -> np.ndarray of durations."""

@@ -12,7 +12,7 @@ Restates, in plain Python (fp64, like the reference):
   * lib/optimUtils.py:113-160   findOptimalRouting           -> find_optimal_routing
   * lib/optimUtils.py:651-664   greatCircleDistance, shortestPathTime
   * lib/Optimization.py:104-225 AlonsoMora.generatePairwiseGraph ("enumerate") -> rv_graph
-  * lib/Optimization.py:227-262 generateRTVGraph, trips of size 1            -> (inside assign)
+  * lib/Optimization.py:227-357 generateRTVGraph (trips of every size)       -> rtv_trips
   * lib/Optimization.py:359-408 assignFromRTVGraph (Gurobi ILP)              -> assign_ilp (HiGHS)
   * lib/Agents.py:1451-1572     Model.insert_heuristics / test_constraints_get_cost -> legacy_*
 

@@ -101,3 +101,49 @@ def test_insertion_object_front_end():
     t_pick = router.get_duration(c["lng"], c["lat"], a["lng"], a["lat"])
     # empty until the pickup (n * dt = 0), wait term t * COEF_WAIT at the pickup, then one rider for Ts seconds
     assert dc == t_pick * 1.5 + req.Ts * 1.0
+
+
+def test_insertion_object_front_end_with_vehicle_between_nodes():
+    """A vehicle in the middle of a link is not a graph vertex: the scan starts at the next downstream node
+    with the remaining step time added (lib/Agents.py:1508-1516), and a busy vehicle's legs become its plan."""
+    from drs_abm_b200.dispatch import InsertionHeuristics
+    from drs_abm_b200.routing import RoutingEngine
+    from oracle import dispatch_oracle as D
+    router = RoutingEngine(graph_loc=golden_map_path("g20_int"), cst_speed=9, seed=1)
+    G = router.G
+    dist = G.dist_rows(0, G.n)
+    tt = lambda a, b: float(dist[a, b])
+
+    class Obj(object):
+        pass
+
+    def mkreq(rid, o, d, Cep, pwt=0.0):
+        r = Obj()
+        r.id, r.olng, r.olat, r.dlng, r.dlat = rid, G.vs[o]["lng"], G.vs[o]["lat"], G.vs[d]["lng"], G.vs[d]["lat"]
+        r.Ts = tt(o, d); r.Tr = r.Cep = Cep; r.Clp = Cep + 600.0; r.Cld = r.Clp + 1.5 * r.Ts; r.pwt = pwt; r.assigned = False
+        r._o, r._d = o, d
+        return r
+    reqs = [mkreq(0, 45, 250, 100.0, pwt=80.0), mkreq(1, 61, 300, 90.0), mkreq(2, 44, 330, 110.0)]
+    veh = Obj()
+    veh.id, veh.idle, veh.c, veh.n, veh.T, veh.K = 0, False, 37.5, 0, 120.0, 4
+    veh.lng, veh.lat = G.vs[42]["lng"] + 1e-4, G.vs[42]["lat"]          # between vertices 42 and 43
+    step = Obj(); step.geo = [[veh.lng, veh.lat], [G.vs[43]["lng"], G.vs[43]["lat"]]]; step.t = 11.5
+    legs = []
+    for (rid, pod, node) in [(0, 1, 45), (0, -1, 250)]:
+        leg = Obj(); leg.rid, leg.pod, leg.tlng, leg.tlat, leg.steps = rid, pod, G.vs[node]["lng"], G.vs[node]["lat"], [step]
+        legs.append(leg)
+    veh.route = legs
+    idle = Obj()
+    idle.id, idle.idle, idle.c, idle.n, idle.T, idle.K, idle.route = 1, True, 0.0, 0, 120.0, 4, []
+    idle.lng, idle.lat = G.vs[399]["lng"], G.vs[399]["lat"]
+    ins = InsertionHeuristics([veh, idle], reqs)
+    for new in (reqs[1], reqs[2]):
+        assert ins.insert_heuristics(router, new, 120.0)
+        wveh, wroute, wdc = ins.last_choice
+        ovehs = [{"vid": 0, "n": 0, "T": 120.0, "K": 4, "c": 37.5, "node": 43, "t0": 11.5, "route": [(0, 1, 45), (0, -1, 250)]},
+                 {"vid": 1, "n": 0, "T": 120.0, "K": 4, "c": 0.0, "node": 399, "t0": 0.0, "route": []}]
+        oreqs = {r.id: {"o_node": r._o, "d_node": r._d, "Cep": r.Cep, "Clp": r.Clp, "Cld": r.Cld, "Ts": r.Ts, "Tr": r.Tr, "pwt": r.pwt}
+                 for r in reqs}
+        vid, route, odc, _ = D.legacy_insert_heuristics(tt, ovehs, oreqs, new.id)
+        assert wveh.id == vid and wdc == odc
+        assert [(s[0], s[1]) for s in wroute] == [(s[0], s[1]) for s in route]

@@ -97,6 +97,76 @@ def test_routing_engine_matches_oracle_engine_on_ties():
         assert router.get_distance_duration(*args) == O.get_distance_duration(*args)
 
 
+def test_link_uncertainty_and_pre_drawn_paths():
+    """draw_link_travel_time consumes the engine's RandomState edge by edge (lib/RoutingEngine.py:56-79);
+    pre-drawn travel times must ride on the identical path (lib/RoutingEngine.py:96-112)."""
+    from oracle.routing_oracle import OracleGraph, OracleRoutingEngine
+    from drs_abm_b200.gml import read_gml
+    name = "g12_float"
+    router = _engine(name)
+    data = read_gml(golden_map_path(name))
+    O = OracleRoutingEngine(oracle_graph_from_data(data), cst_speed=9, seed=7)
+    G = router.G
+    rs = np.random.RandomState(8)
+    for _ in range(15):
+        o, d = G.vs[int(rs.randint(G.n))], G.vs[int(rs.randint(G.n))]
+        args = (o["lng"], o["lat"], d["lng"], d["lat"])
+        a, b = router.get_routing(*args, use_uncertainty=True), O.get_routing(*args, use_uncertainty=True)
+        assert a == b                                         # same path, same draws in the same order
+        assert a["duration"] == sum(s["duration"] for s in a["steps"]) or not a["steps"][0]["distance"]
+        # pre-drawn: (total, {edge: tt}, path) as built at lib/Agents.py:1533-1541
+        path = G.get_shortest_paths(o["name"], to=d["name"], weights=router.ttweight, output="epath")[0]
+        drawn = {e: router.draw_link_travel_time(e) for e in path}
+        odrawn = {e: O.draw_link_travel_time(e) for e in path}
+        assert drawn == odrawn
+        pre = (sum(drawn.values()), drawn, path)
+        r = router.get_routing(*args, pre_drawn_tt=pre)
+        assert r is not None and r["duration"] == pre[0] and [s["duration"] for s in r["steps"]] == [drawn[e] for e in path]
+        if len(path) > 1:
+            assert router.get_routing(*args, pre_drawn_tt=(pre[0], drawn, path[::-1])) is None     # path mismatch -> None
+
+
+def test_offer_queries_match_scalar_calls():
+    """Batched routing half of Fleet.generate_offer == the reference's per-trip scalar calls (lib/Agents.py:881-923,1208-1223)."""
+    router = _engine("g20_int")
+    G = router.G
+    rs = np.random.RandomState(2)
+
+    class V(object):
+        pass
+
+    class Tr(object):
+        pass
+    vehs = []
+    for i in range(25):
+        v = V(); nd = G.vs[int(rs.randint(G.n))]
+        v.n, v.K = int(rs.randint(0, 3)), 2
+        v._loc, v._t = (nd["lng"], nd["lat"]), float(rs.choice([0.0, 4.5]))
+        v.get_next_node = (lambda v=v: (v._loc, v._t))
+        vehs.append(v)
+    trips = []
+    for i in range(12):
+        tr = Tr(); o, d = G.vs[int(rs.randint(G.n))], G.vs[int(rs.randint(G.n))]
+        tr.olng, tr.olat, tr.dlng, tr.dlat = o["lng"], o["lat"], d["lng"], d["lat"]
+        trips.append(tr)
+    got = router.offer_queries(vehs, trips, 3)
+    for tr, g in zip(trips, got):
+        dists = []
+        for veh in vehs:                                   # get_n_closest_vehs, lib/Agents.py:1208-1223
+            if veh.n < veh.K:
+                loc, _ = veh.get_next_node()
+                dists.append(router.get_distance_duration(loc[0], loc[1], tr.olng, tr.olat, euclidean="True")[0])
+            else:
+                dists.append(1e10)
+        order = np.argsort(dists)[:3]
+        assert [vehs[k] for k in order] == g["closest"] and [dists[k] for k in order] == g["veh_dists"]
+        for k, wt in zip(order, g["direct_wt"]):
+            loc, delay = vehs[k].get_next_node()
+            assert wt == router.get_duration(loc[0], loc[1], tr.olng, tr.olat) + delay
+        assert g["direct_tt"] == router.get_duration(tr.olng, tr.olat, tr.dlng, tr.dlat)
+        assert g["distance"] == router.get_distance(tr.olng, tr.olat, tr.dlng, tr.dlat)
+
+
 def test_same_node_unknown_vertex_and_weight_updates():
     router = _engine("g8_int")
     G = router.G

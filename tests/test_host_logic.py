@@ -150,3 +150,20 @@ def test_set_packing_solver_matches_the_ilp_objective():
         assert len(served) == len(set(served)) and sorted(served + ignored) == list(range(nreq))
         assert len(set(trips[k][0] for k in chosen)) == len(chosen)
         assert len(ignored) == len(orej)
+
+
+def test_draw_link_travel_time_matches_the_oracle_stream():
+    """lib/RoutingEngine.py:56-79 stays on the host (RNG-order sensitive): same seed, same draws as the restatement."""
+    from conftest import golden_map_path, oracle_graph_from_data
+    from drs_abm_b200.gml import read_gml
+    from drs_abm_b200.routing import RoadGraph, RoutingEngine
+    from oracle.routing_oracle import OracleRoutingEngine
+    data = read_gml(golden_map_path("g12_float"))
+    ours = RoutingEngine(graph=RoadGraph(data), cst_speed=9, seed=123)
+    ref = OracleRoutingEngine(oracle_graph_from_data(data), cst_speed=9, seed=123)
+    for e in [0, 5, 17, 3, 3, 40]:
+        assert ours.draw_link_travel_time(e) == ref.draw_link_travel_time(e)
+        assert ours.draw_link_travel_time(e, use_uncertainty=False) == data.eattrs["ttmedian"][e]
+    assert ours.generateRandomLocation().index == ref.generateRandomLocation().index
+    d = ours.get_distance_duration(-71.1, 42.3, -71.09, 42.31, euclidean=True)
+    assert d == ref.get_distance_duration(-71.1, 42.3, -71.09, 42.31, euclidean=True) and d[1] == d[0] / 9
