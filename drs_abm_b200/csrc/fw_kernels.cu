@@ -137,15 +137,24 @@ __global__ void __launch_bounds__(NTHREADS, 2) fw_minplus_tile_kernel(TileArgs<T
   load_chunk(1, 1);
   cp_async_commit();
 
-  // accumulators start from the C tile: rows ty+16r, columns tx*4.. and 64+tx*4..
+  // accumulators start from the C tile: rows ty+16r; columns tx*4.. and 64+tx*4.. (scalar / int path) or the
+  // four column pairs 32j + 2tx (packed path: keeps the k-pair-interleaved B loads conflict-free)
   T acc[8][8];
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
     const T* crow = C + (int64_t)(ty + 16 * r) * p.ldc;
-    V4 lo = *reinterpret_cast<const V4*>(crow + tx * 4);
-    V4 hi = *reinterpret_cast<const V4*>(crow + 64 + tx * 4);
-    acc[r][0] = lo.x; acc[r][1] = lo.y; acc[r][2] = lo.z; acc[r][3] = lo.w;
-    acc[r][4] = hi.x; acc[r][5] = hi.y; acc[r][6] = hi.z; acc[r][7] = hi.w;
+    if (kPacked) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const V2 v = *reinterpret_cast<const V2*>(crow + 32 * j + tx * 2);
+        acc[r][2 * j] = v.x; acc[r][2 * j + 1] = v.y;
+      }
+    } else {
+      V4 lo = *reinterpret_cast<const V4*>(crow + tx * 4);
+      V4 hi = *reinterpret_cast<const V4*>(crow + 64 + tx * 4);
+      acc[r][0] = lo.x; acc[r][1] = lo.y; acc[r][2] = lo.z; acc[r][3] = lo.w;
+      acc[r][4] = hi.x; acc[r][5] = hi.y; acc[r][6] = hi.z; acc[r][7] = hi.w;
+    }
   }
 
 #pragma unroll 1
@@ -167,11 +176,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) fw_minplus_tile_kernel(TileArgs<T
         for (int r = 0; r < 8; ++r) a[r] = *reinterpret_cast<const float2*>(&As[stage][ty + 16 * r][kk]);
         const float2* brow = Bp + (kk >> 1) * TILE;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const float4 q0 = *reinterpret_cast<const float4*>(brow + h * 64 + tx * 4);       // columns +0, +1
-          const float4 q1 = *reinterpret_cast<const float4*>(brow + h * 64 + tx * 4 + 2);   // columns +2, +3
-          b[h * 4 + 0] = make_float2(q0.x, q0.y); b[h * 4 + 1] = make_float2(q0.z, q0.w);
-          b[h * 4 + 2] = make_float2(q1.x, q1.y); b[h * 4 + 3] = make_float2(q1.z, q1.w);
+        for (int j = 0; j < 4; ++j) {   // columns 32j + 2tx, +1: 16 lanes x 16 B contiguous per load
+          const float4 q = *reinterpret_cast<const float4*>(brow + 32 * j + tx * 2);
+          b[2 * j] = make_float2(q.x, q.y); b[2 * j + 1] = make_float2(q.z, q.w);
         }
 #pragma unroll
         for (int r = 0; r < 8; ++r)
@@ -206,17 +213,27 @@ __global__ void __launch_bounds__(NTHREADS, 2) fw_minplus_tile_kernel(TileArgs<T
 
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
-    T* crow = C + (int64_t)(ty + 16 * r) * p.ldc;
-    V4 lo, hi;
-    lo.x = acc[r][0]; lo.y = acc[r][1]; lo.z = acc[r][2]; lo.w = acc[r][3];
-    hi.x = acc[r][4]; hi.y = acc[r][5]; hi.z = acc[r][6]; hi.w = acc[r][7];
-    *reinterpret_cast<V4*>(crow + tx * 4) = lo;
-    *reinterpret_cast<V4*>(crow + 64 + tx * 4) = hi;
-    // fused broadcast: P2P stores of the finished tile into every peer's panel buffer (NVLink)
-    for (int pr = 0; pr < p.n_peers; ++pr) {
-      T* prow = p.peer[pr] + bi * p.c_si + bj * p.c_sj + (int64_t)(ty + 16 * r) * p.ldc;
-      *reinterpret_cast<V4*>(prow + tx * 4) = lo;
-      *reinterpret_cast<V4*>(prow + 64 + tx * 4) = hi;
+    const int64_t roff = (int64_t)(ty + 16 * r) * p.ldc;
+    if (kPacked) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        V2 v; v.x = acc[r][2 * j]; v.y = acc[r][2 * j + 1];
+        *reinterpret_cast<V2*>(C + roff + 32 * j + tx * 2) = v;
+        // fused broadcast: P2P stores of the finished tile into every peer's panel buffer (NVLink)
+        for (int pr = 0; pr < p.n_peers; ++pr)
+          *reinterpret_cast<V2*>(p.peer[pr] + bi * p.c_si + bj * p.c_sj + roff + 32 * j + tx * 2) = v;
+      }
+    } else {
+      V4 lo, hi;
+      lo.x = acc[r][0]; lo.y = acc[r][1]; lo.z = acc[r][2]; lo.w = acc[r][3];
+      hi.x = acc[r][4]; hi.y = acc[r][5]; hi.z = acc[r][6]; hi.w = acc[r][7];
+      *reinterpret_cast<V4*>(C + roff + tx * 4) = lo;
+      *reinterpret_cast<V4*>(C + roff + 64 + tx * 4) = hi;
+      for (int pr = 0; pr < p.n_peers; ++pr) {
+        T* prow = p.peer[pr] + bi * p.c_si + bj * p.c_sj + roff;
+        *reinterpret_cast<V4*>(prow + tx * 4) = lo;
+        *reinterpret_cast<V4*>(prow + 64 + tx * 4) = hi;
+      }
     }
   }
 }

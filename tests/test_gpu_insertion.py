@@ -123,7 +123,7 @@ def test_insertion_object_front_end_with_vehicle_between_nodes():
         r.Ts = tt(o, d); r.Tr = r.Cep = Cep; r.Clp = Cep + 600.0; r.Cld = r.Clp + 1.5 * r.Ts; r.pwt = pwt; r.assigned = False
         r._o, r._d = o, d
         return r
-    reqs = [mkreq(0, 45, 250, 100.0, pwt=80.0), mkreq(1, 61, 300, 90.0), mkreq(2, 44, 330, 110.0)]
+    reqs = [mkreq(0, 45, 250, 100.0, pwt=80.0), mkreq(1, 46, 66, 90.0), mkreq(2, 44, 104, 110.0)]
     veh = Obj()
     veh.id, veh.idle, veh.c, veh.n, veh.T, veh.K = 0, False, 37.5, 0, 120.0, 4
     veh.lng, veh.lat = G.vs[42]["lng"] + 1e-4, G.vs[42]["lat"]          # between vertices 42 and 43

@@ -120,10 +120,16 @@ def test_link_uncertainty_and_pre_drawn_paths():
         odrawn = {e: O.draw_link_travel_time(e) for e in path}
         assert drawn == odrawn
         pre = (sum(drawn.values()), drawn, path)
-        r = router.get_routing(*args, pre_drawn_tt=pre)
-        assert r is not None and r["duration"] == pre[0] and [s["duration"] for s in r["steps"]] == [drawn[e] for e in path]
+        # (use_uncertainty=True: with the default False the reference asserts duration == mean_duration,
+        #  lib/RoutingEngine.py:134-135, which pre-drawn times violate by construction -- mirrored, not fixed)
+        r = router.get_routing(*args, pre_drawn_tt=pre, use_uncertainty=True)
+        assert r is not None and r["duration"] == pre[0]
+        if path:                                              # (an empty path yields the single stay-in-place step)
+            assert [s["duration"] for s in r["steps"]] == [drawn[e] for e in path]
         if len(path) > 1:
-            assert router.get_routing(*args, pre_drawn_tt=(pre[0], drawn, path[::-1])) is None     # path mismatch -> None
+            assert router.get_routing(*args, pre_drawn_tt=(pre[0], drawn, path[::-1]), use_uncertainty=True) is None   # mismatch -> None
+            with pytest.raises(AssertionError):
+                router.get_routing(*args, pre_drawn_tt=pre)
 
 
 def test_offer_queries_match_scalar_calls():
