@@ -455,19 +455,16 @@ def solve_set_packing(nveh, nreq, trips, costs):
         obj = float(sum(costs[k] for k in chosen) + COST_IGNORED * len(ignored))
         return sorted(chosen), sorted(ignored), obj
     from scipy.optimize import milp, LinearConstraint, Bounds
-    from scipy.sparse import lil_matrix
+    from scipy.sparse import csr_matrix
     nvar = nt + nreq
     c = np.concatenate([costs, np.full(nreq, COST_IGNORED)])
-    A = lil_matrix((nveh + nreq, nvar))
     lo = np.concatenate([np.full(nveh, -np.inf), np.ones(nreq)])
     hi = np.ones(nveh + nreq)
-    for k, (vi, tr) in enumerate(trips):
-        A[vi, k] = 1
-        for r in tr:
-            A[nveh + r, k] = 1
-    for r in range(nreq):
-        A[nveh + r, nt + r] = 1
-    res = milp(c, constraints=LinearConstraint(A.tocsr(), lo, hi), integrality=np.ones(nvar), bounds=Bounds(0, 1))
+    # rows 0..nveh-1: one trip per vehicle; rows nveh..: each request in exactly one chosen trip or ignored
+    rows = [t[0] for t in trips] + [nveh + r for t in trips for r in t[1]] + [nveh + r for r in range(nreq)]
+    cols = list(range(nt)) + [k for k, t in enumerate(trips) for _ in t[1]] + [nt + r for r in range(nreq)]
+    A = csr_matrix((np.ones(len(rows)), (rows, cols)), shape=(nveh + nreq, nvar))
+    res = milp(c, constraints=LinearConstraint(A, lo, hi), integrality=np.ones(nvar), bounds=Bounds(0, 1))
     if res.status != 0:
         return None, None, None
     x = np.round(res.x).astype(np.int64)

@@ -165,3 +165,50 @@ def test_empty_and_infeasible_ticks():
     # no vehicles
     assert opt.optimizeAssignment([], [ok], G, 0)[0] == (list(), list())
     G.close()
+
+
+def test_rv_stage_at_fleet_scale_matches_oracle():
+    """BASELINE config C2 fleet (200 vehicles, busy plans of up to 4 stops) x 16 new requests: every RV edge
+    (cost and canonical route), the status counters and the assignment objective against the oracle."""
+    from drs_abm_b200 import synth
+    from drs_abm_b200.dispatch import AlonsoMora
+    from drs_abm_b200.routing import RoadGraph
+    from oracle import dispatch_oracle as D
+    data = synth.config_graph("C2")
+    G = RoadGraph(data)
+    sc = synth.fleet_scenario(data, 200, 16, 600.0, 21, lambda s, t: G.matrix_lookup(s, t), plan_stops=(0, 2, 4), radius=5)
+    tab = sc["table"]
+    lng, lat = data.vattrs["lng"], data.vattrs["lat"]
+    is_new = np.zeros(len(tab["o"]), dtype=bool); is_new[sc["new_rows"]] = True
+    reqs = [OReq(r, lng[tab["o"][r]], lat[tab["o"][r]], lng[tab["d"][r]], lat[tab["d"][r]], float(tab["Cep"][r]), float(tab["Clp"][r]),
+                 float(tab["Ced"][r]), float(tab["Cld"][r]), assigned=not is_new[r]) for r in range(len(tab["o"]))]
+    vehs = [OVeh(k, v["K"], (lng[v["node"]], lat[v["node"]]), 0.0, v["pax"], v["wait"]) for k, v in enumerate(sc["vehs"])]
+    rows = {}
+
+    def tt(a, b):
+        if a not in rows:
+            rows[a] = G.dist_rows(int(a), 1)[0]
+        return float(rows[a][b])
+
+    def rec(r):
+        return {"rid": r, "o_node": int(tab["o"][r]), "d_node": int(tab["d"][r]), "olng": reqs[r].olng, "olat": reqs[r].olat,
+                "dlng": reqs[r].dlng, "dlat": reqs[r].dlat, "Cep": reqs[r].Cep, "Clp": reqs[r].Clp, "Ced": reqs[r].Ced, "Cld": reqs[r].Cld}
+    ovehs = []
+    for k, v in enumerate(sc["vehs"]):
+        pax, wait = vehs[k].get_passenger_requests()          # same (set-iteration) order the drop-in marshals
+        ovehs.append({"vid": k, "capacity": v["K"], "node": v["node"], "location": (lng[v["node"]], lat[v["node"]]), "t": 0.0,
+                      "pax_reqs": [rec(r) for r in pax], "wait_reqs": [rec(r) for r in wait]})
+    oreqs = [rec(int(r)) for r in sc["new_rows"]]
+    T = sc["T"]
+    opt = AlonsoMora({"routing_method": "enumerate", "verbose": False, "max_trip_size": 1})
+    rv = opt.generatePairwiseGraph(vehs, reqs, G, T)
+    _, orv, ocount = D.rv_graph(ovehs, oreqs, tt, T, with_rr=False)
+    got = {(vi, rv.tick.new_reqs[ri].id): (c, [(s[0], s[1]) for s in route]) for (vi, ri), (c, route) in rv.rv.items()}
+    want = {k: (c, [(s[0], s[1]) for s in route]) for k, (c, route, _) in orv.items()}
+    assert got == want and len(got) >= 30
+    assert rv.counters == ocount
+    rv.tick.close()
+    (routes, rejected), meta = opt.optimizeAssignment(vehs, reqs, G, T)
+    (oroutes, orej), ometa = D.optimize_assignment(ovehs, oreqs, tt, T, max_trip_size=1)
+    assert meta["objective"] == pytest.approx(ometa["objective"], abs=1e-6) and len(rejected) == len(orej)
+    G.close()
