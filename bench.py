@@ -385,6 +385,9 @@ def main():
     ap.add_argument("--algorithm", default="auto", choices=["auto", "fw", "sssp"],
                     help="APSP algorithm of the headline value; auto = the library default (SSSP on sparse road networks). "
                          "The blocked Floyd-Warshall is always measured too and reported under \"fw\".")
+    ap.add_argument("--pred-matrix", action="store_true",
+                    help="also materialise the predecessor matrix inside the timed build (default: lazy predecessors -- path "
+                         "queries evaluate the canonical rule per hop; the matrix pass is reported separately under phase_ms)")
     ap.add_argument("--no-insertion", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lookahead", action="store_true")
@@ -435,9 +438,10 @@ def main():
         if a == "fw_p2p":        # blocked FW whose pivot step stores the panel into the peers' buffers (fused broadcast)
             if comm[0] is None:
                 comm[0] = apsp_dist.P2PComm(tiles, npad, rank, world, dist)
-            return apsp_dist.build_sharded_p2p(tiles, npad, rank, world, dist, comm[0], lookahead=not args.no_lookahead)
+            return apsp_dist.build_sharded_p2p(tiles, npad, rank, world, dist, comm[0], lookahead=not args.no_lookahead,
+                                               with_pred=args.pred_matrix)
         return apsp_dist.build_sharded(tiles, npad, rank, world, dist if world > 1 else None,
-                                       lookahead=not args.no_lookahead, with_pred=True, algorithm=a)
+                                       lookahead=not args.no_lookahead, with_pred=args.pred_matrix, algorithm=a)
 
     # ALU roofline denominator, measured live (rank 0): best add+min stream of the three instruction mixes
     alu = {}
@@ -504,8 +508,8 @@ def main():
         tt, ln, hops = G2.path_sums(o, d)
         d2h = tt.nbytes + ln.nbytes + hops.nbytes
     else:
-        loc2, pred2, r02 = apsp_dist.build_sharded(apsp_dist.CudaTiles(h2, mode), npad, rank, world, dist, with_pred=True,
-                                                   algorithm=algo)
+        loc2, pred2, r02 = apsp_dist.build_sharded(apsp_dist.CudaTiles(h2, mode), npad, rank, world, dist,
+                                                   with_pred=args.pred_matrix, algorithm=algo)
         sample = loc2[:8].cpu()
         d2h = sample.numel() * sample.element_size()
         del loc2, pred2
@@ -539,6 +543,8 @@ def main():
                 "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": False, "scaling": "strong",
                 "vs_baseline": None, "dtype": args.mode, "data": "synthetic",
                 "config": {"workload": WORKLOADS[args.config], "n_nodes": data.n, "n_edges": data.m, "npad": npad,
+                           "predecessors": "matrix built inside the timed step" if args.pred_matrix else
+                                           "lazy (canonical rule evaluated per hop by the path queries; no predecessor matrix)",
                            "apsp_algorithm": {"sssp": "batched delta-stepping SSSP, one CTA per source (library default on sparse graphs)",
                                               "fw": "blocked min-plus Floyd-Warshall"}[algo],
                            "l2": "inputs larger than L2: the %d MB matrix is written (SSSP) / streamed once per round (FW); L2 is 126 MB" % (npad * npad * 4 >> 20),
@@ -550,7 +556,7 @@ def main():
         if world == 1:
             # per-kernel device times from the library's own CUDA events (public single-GPU build)
             def profile(algorithm):
-                Gp = RoadGraph(data, mode=mode, algorithm=algorithm)
+                Gp = RoadGraph(data, mode=mode, algorithm=algorithm, pred=_lib.PRED_MATRIX)
                 Gp.build(); Gp._valid = False; Gp.build()
                 prof = np.zeros(4); rounds = C.c_int32(0)
                 _lib.check(lib.drs_apsp_last_profile(Gp._handle, _lib.ptr_f64(prof), C.byref(rounds)), lib)
@@ -563,7 +569,7 @@ def main():
             t_k = prof_sssp[2] * 1e-3 if prof_sssp is not None else sec * world
             line["roofline"] = sssp_roofline(t_k)
             if prof_sssp is not None:
-                line["phase_ms"] = {"sssp": prof_sssp[2], "pred": prof_sssp[3]}
+                line["phase_ms"] = {"sssp": prof_sssp[2], "pred_matrix_optional": prof_sssp[3]}
         else:
             t_k = prof_fw[2] * 1e-3 if prof_fw is not None else sec * world
             line["roofline"] = fw_roofline(t_k)

@@ -16,6 +16,7 @@ MODE_F32 = 0
 MODE_I32 = 1
 FW_TILE = 128
 APSP_FW, APSP_SSSP, APSP_AUTO = 0, 1, 2
+PRED_LAZY, PRED_MATRIX = 0, 1
 I32_INF = 0x3FFFFFFF
 
 ERR_ARG, ERR_CUDA, ERR_STATE, ERR_NOMEM, ERR_RANGE, ERR_CAPACITY = -1, -2, -3, -4, -5, -6
@@ -99,6 +100,7 @@ SIGNATURES = {
     "drs_alu_peak": (C.c_int, [C.c_int32, C.c_int32, _f64p]),
     "drs_graph_stream": (C.c_int, [_vp, C.POINTER(_vp)]),
     "drs_apsp_set_algorithm": (C.c_int, [_vp, C.c_int32]),
+    "drs_apsp_set_pred_mode": (C.c_int, [_vp, C.c_int32]),
     "drs_sssp_batch_dev": (C.c_int, [_vp, C.c_int32, C.c_int32, _i32p, _vp, C.c_int64, C.c_double, _vp]),
     "drs_sssp_batch": (C.c_int, [_vp, C.c_int32, C.c_int32, _i32p, _f64p]),
     "drs_apsp_rows_sssp": (C.c_int, [_vp, C.c_int32, _vp, C.c_int64, C.c_int32, C.c_int32, C.c_double, _vp]),

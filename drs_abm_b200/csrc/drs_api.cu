@@ -188,10 +188,11 @@ extern "C" int drs_apsp_build(drs_graph* g, int32_t mode) {
   if (!g->owns_matrices || g->ld != ld) {
     free_matrices(g);
     DRS_CUDA(cudaMalloc(&g->d_dist, sizeof(float) * ld * ld));
-    DRS_CUDA(cudaMalloc((void**)&g->d_pred, sizeof(int32_t) * ld * ld));
     g->owns_matrices = true;
     g->ld = ld;
   }
+  if (g->pred_mode == DRS_PRED_MATRIX && !g->d_pred) DRS_CUDA(cudaMalloc((void**)&g->d_pred, sizeof(int32_t) * ld * ld));
+  if (g->pred_mode == DRS_PRED_LAZY && g->d_pred) { cudaFree(g->d_pred); g->d_pred = nullptr; }
   g->apsp_valid = false;
   g->mode = mode;
   int rc;
@@ -222,7 +223,7 @@ extern "C" int drs_apsp_build(drs_graph* g, int32_t mode) {
     DRS_CUDA(cudaEventRecord(ev[3 + 2 * kb], st));
   }
   }
-  if ((rc = drs_pred_build(g, mode, g->d_dist, ld, 0, g->npad, g->d_pred, st))) { release(); return rc; }
+  if (g->d_pred && (rc = drs_pred_build(g, mode, g->d_dist, ld, 0, g->npad, g->d_pred, st))) { release(); return rc; }
   DRS_CUDA(cudaEventRecord(ev[2 + 2 * nb], st));
   DRS_CUDA(cudaStreamSynchronize(st));
   float ms = 0;
@@ -245,6 +246,13 @@ extern "C" int drs_apsp_set_algorithm(drs_graph* g, int32_t algorithm) {
   DRS_REQUIRE(algorithm == DRS_APSP_FW || algorithm == DRS_APSP_SSSP || algorithm == DRS_APSP_AUTO, DRS_ERR_ARG,
               "drs_apsp_set_algorithm: unknown algorithm %d", algorithm);
   g->algorithm = algorithm;
+  return DRS_OK;
+}
+
+extern "C" int drs_apsp_set_pred_mode(drs_graph* g, int32_t pred_mode) {
+  DRS_REQUIRE(g, DRS_ERR_ARG, "drs_apsp_set_pred_mode: null graph");
+  DRS_REQUIRE(pred_mode == DRS_PRED_LAZY || pred_mode == DRS_PRED_MATRIX, DRS_ERR_ARG, "drs_apsp_set_pred_mode: unknown mode %d", pred_mode);
+  g->pred_mode = pred_mode;
   return DRS_OK;
 }
 
@@ -271,7 +279,7 @@ extern "C" int drs_apsp_matrices(const drs_graph* g, void** dist_dev, int32_t** 
 }
 
 extern "C" int drs_apsp_adopt(drs_graph* g, int32_t mode, void* dist_dev, int32_t* pred_dev, int64_t ld) {
-  DRS_REQUIRE(g && dist_dev && pred_dev, DRS_ERR_ARG, "drs_apsp_adopt: null argument");
+  DRS_REQUIRE(g && dist_dev, DRS_ERR_ARG, "drs_apsp_adopt: null argument");   // pred_dev may be null (lazy predecessors)
   DRS_REQUIRE(ld == g->npad, DRS_ERR_ARG, "drs_apsp_adopt: ld must equal npad (%d)", g->npad);
   DRS_REQUIRE(mode == DRS_MODE_F32 || mode == DRS_MODE_I32, DRS_ERR_ARG, "drs_apsp_adopt: unknown mode %d", mode);
   DrsDeviceGuard guard(g->device);
@@ -290,15 +298,53 @@ __device__ __forceinline__ int prev_node(int e, int t, const int32_t* esrc, cons
   return (b == t) ? a : b;   // undirected edges are walked against either orientation
 }
 
+// Where the last edge of the canonical path s -> t comes from: the materialised predecessor matrix, or --
+// when it was not built (DRS_PRED_LAZY) -- the canonical rule evaluated on the spot from the distance row
+// of s and t's in-arcs (same rule as pred_kernel: minimise (dist[s,u] + w, dist[s,u], eid)).
+struct PredSource {
+  const int32_t* pred;      // may be null
+  const void* dist;
+  int64_t ld;
+  int mode;
+  const int32_t *in_ptr, *in_src, *in_eid;
+  const float* in_w;
+
+  template <typename T> __device__ int rule(const T* row, T inf, int t) const {
+    int best_e = -1;
+    T best_c = inf, best_du = inf;
+    for (int a = in_ptr[t]; a < in_ptr[t + 1]; ++a) {
+      const T du = row[in_src[a]];
+      if (!(du < inf)) continue;
+      const T cand = du + (T)in_w[a];
+      const int e = in_eid[a];
+      if (cand < best_c || (cand == best_c && (du < best_du || (du == best_du && e < best_e)))) {
+        best_c = cand; best_du = du; best_e = e;
+      }
+    }
+    return best_e;
+  }
+  __device__ int last_edge(int s, int t) const {
+    if (pred) return pred[(int64_t)s * ld + t];
+    if (s == t) return -1;
+    if (mode == DRS_MODE_F32) {
+      const float* row = (const float*)dist + (int64_t)s * ld;
+      const float inf = __int_as_float(0x7f800000);
+      return (row[t] < inf) ? rule<float>(row, inf, t) : -1;
+    }
+    const int* row = (const int*)dist + (int64_t)s * ld;
+    return (row[t] < DRS_I32_INF) ? rule<int>(row, DRS_I32_INF, t) : -1;
+  }
+};
+
 // hops[q] = number of edges on the canonical path (-1 unreachable / broken chain)
-__global__ void path_count_kernel(int npairs, const int32_t* s, const int32_t* t, const int32_t* pred,
-                                  int64_t ld, int n, const int32_t* esrc, const int32_t* edst, int32_t* hops) {
+__global__ void path_count_kernel(int npairs, const int32_t* s, const int32_t* t, PredSource ps, int n,
+                                  const int32_t* esrc, const int32_t* edst, int32_t* hops) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= npairs) return;
   const int src = s[q];
   int cur = t[q], h = 0;
   while (cur != src) {
-    const int e = pred[(int64_t)src * ld + cur];
+    const int e = ps.last_edge(src, cur);
     if (e < 0 || h >= n) { h = -1; break; }
     cur = prev_node(e, cur, esrc, edst);
     ++h;
@@ -307,8 +353,8 @@ __global__ void path_count_kernel(int npairs, const int32_t* s, const int32_t* t
 }
 
 // writes the path of query q in travel order at path[offset[q] ..] and the fp64 left-to-right sums
-__global__ void path_fill_kernel(int npairs, const int32_t* s, const int32_t* t, const int32_t* pred,
-                                 int64_t ld, const int32_t* esrc, const int32_t* edst, const int32_t* hops,
+__global__ void path_fill_kernel(int npairs, const int32_t* s, const int32_t* t, PredSource ps,
+                                 const int32_t* esrc, const int32_t* edst, const int32_t* hops,
                                  const int64_t* offset, int32_t* path, const double* tt64, const double* len64,
                                  double* tt_out, double* len_out) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -323,7 +369,7 @@ __global__ void path_fill_kernel(int npairs, const int32_t* s, const int32_t* t,
   int cur = t[q];
   int32_t* out = path + offset[q];
   for (int i = h - 1; i >= 0; --i) {
-    const int e = pred[(int64_t)src * ld + cur];
+    const int e = ps.last_edge(src, cur);
     out[i] = e;
     cur = prev_node(e, cur, esrc, edst);
   }
@@ -357,6 +403,10 @@ __global__ void rows_to_double_kernel(const T* dist, int64_t ld, int row0, int n
     const int i = (int)(idx / n), j = (int)(idx % n);
     out[idx] = dist_to_double(dist[(int64_t)(row0 + i) * ld + j]);
   }
+}
+
+PredSource pred_source(const drs_graph* g) {
+  return PredSource{g->d_pred, g->d_dist, g->ld, g->mode, g->d_in_ptr, g->d_in_src, g->d_in_eid, g->d_in_w};
 }
 
 struct DevBuf {
@@ -396,7 +446,7 @@ extern "C" int drs_query_pairs(const drs_graph* g, int32_t npairs, const int32_t
   DRS_CUDA(cudaMemcpyAsync(ds.p, s, sizeof(int32_t) * npairs, cudaMemcpyHostToDevice, st));
   DRS_CUDA(cudaMemcpyAsync(dt.p, t, sizeof(int32_t) * npairs, cudaMemcpyHostToDevice, st));
   const int blocks = (npairs + 127) / 128;
-  path_count_kernel<<<blocks, 128, 0, st>>>(npairs, ds.as<int32_t>(), dt.as<int32_t>(), g->d_pred, g->ld, g->n,
+  path_count_kernel<<<blocks, 128, 0, st>>>(npairs, ds.as<int32_t>(), dt.as<int32_t>(), pred_source(g), g->n,
                                             g->d_esrc, g->d_edst, dh.as<int32_t>());
   drs_count_launch();
   DRS_CUDA(cudaGetLastError());
@@ -408,7 +458,7 @@ extern "C" int drs_query_pairs(const drs_graph* g, int32_t npairs, const int32_t
   for (int q = 0; q < npairs; ++q) { off[q] = total; total += std::max(hops[q], 0); }
   if ((rc = dpath.alloc(sizeof(int32_t) * (size_t)total))) return rc;
   DRS_CUDA(cudaMemcpyAsync(doff.p, off.data(), sizeof(int64_t) * npairs, cudaMemcpyHostToDevice, st));
-  path_fill_kernel<<<blocks, 128, 0, st>>>(npairs, ds.as<int32_t>(), dt.as<int32_t>(), g->d_pred, g->ld, g->d_esrc,
+  path_fill_kernel<<<blocks, 128, 0, st>>>(npairs, ds.as<int32_t>(), dt.as<int32_t>(), pred_source(g), g->d_esrc,
                                            g->d_edst, dh.as<int32_t>(), doff.as<int64_t>(), dpath.as<int32_t>(),
                                            g->d_tt64, g->d_len64, dtt.as<double>(), dlen.as<double>());
   drs_count_launch();
@@ -485,7 +535,7 @@ extern "C" int drs_path(const drs_graph* g, int32_t s, int32_t t, int32_t* edge_
     return rc;
   const int32_t q[2] = {s, t};
   DRS_CUDA(cudaMemcpyAsync(dq.p, q, sizeof(q), cudaMemcpyHostToDevice, st));
-  path_count_kernel<<<1, 32, 0, st>>>(1, dq.as<int32_t>(), dq.as<int32_t>() + 1, g->d_pred, g->ld, g->n, g->d_esrc,
+  path_count_kernel<<<1, 32, 0, st>>>(1, dq.as<int32_t>(), dq.as<int32_t>() + 1, pred_source(g), g->n, g->d_esrc,
                                       g->d_edst, dh.as<int32_t>());
   drs_count_launch();
   DRS_CUDA(cudaGetLastError());
@@ -498,7 +548,7 @@ extern "C" int drs_path(const drs_graph* g, int32_t s, int32_t t, int32_t* edge_
   DRS_REQUIRE(edge_ids && cap >= h, DRS_ERR_CAPACITY, "drs_path: path has %d edges, buffer holds %d", h, cap);
   if ((rc = dpath.alloc(sizeof(int32_t) * h))) return rc;
   DRS_CUDA(cudaMemsetAsync(doff.p, 0, sizeof(int64_t), st));
-  path_fill_kernel<<<1, 32, 0, st>>>(1, dq.as<int32_t>(), dq.as<int32_t>() + 1, g->d_pred, g->ld, g->d_esrc, g->d_edst,
+  path_fill_kernel<<<1, 32, 0, st>>>(1, dq.as<int32_t>(), dq.as<int32_t>() + 1, pred_source(g), g->d_esrc, g->d_edst,
                                      dh.as<int32_t>(), doff.as<int64_t>(), dpath.as<int32_t>(), g->d_tt64, g->d_len64,
                                      nullptr, nullptr);
   drs_count_launch();

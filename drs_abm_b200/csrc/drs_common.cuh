@@ -59,6 +59,7 @@ struct drs_graph {
   // resident matrices
   int mode = DRS_MODE_F32;
   int algorithm = DRS_APSP_FW;
+  int pred_mode = DRS_PRED_LAZY;
   bool apsp_valid = false;
   bool owns_matrices = false;
   void* d_dist = nullptr;

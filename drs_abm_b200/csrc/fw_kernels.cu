@@ -316,9 +316,13 @@ __global__ void fw_scatter_kernel(T* local, int64_t ld, int row0, int nrows, con
 // matrix element; row reads are coalesced over t and the neighbour reads hit L1/L2 (neighbours of
 // consecutive vertices are close in a road network).
 constexpr int PRED_ROWS = 32;
+#ifndef DRS_PRED_THREADS
+#define DRS_PRED_THREADS 1024   // a CTA spans 1024 consecutive targets: the +-n_side neighbours of a grid city stay inside its L1
+#endif
+constexpr int PRED_THREADS = DRS_PRED_THREADS;
 constexpr int PRED_MAXDEG = 6;    // in-arcs held in registers; vertices with more fall back to the CSR loop
 template <typename T>
-__global__ void __launch_bounds__(256) pred_kernel(const T* __restrict__ local, int64_t ld, int row0, int nrows, int n,
+__global__ void __launch_bounds__(PRED_THREADS) pred_kernel(const T* __restrict__ local, int64_t ld, int row0, int nrows, int n,
                                                    const int32_t* __restrict__ in_ptr, const int32_t* __restrict__ in_src,
                                                    const int32_t* __restrict__ in_eid, const float* __restrict__ in_w,
                                                    int32_t* __restrict__ pred) {
@@ -602,12 +606,12 @@ extern "C" int drs_pred_build(const drs_graph* g, int32_t mode, const void* loca
               "drs_pred_build: bad shard");
   if (nrows == 0) return DRS_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  dim3 grid((unsigned)((ld + 255) / 256), (unsigned)((nrows + PRED_ROWS - 1) / PRED_ROWS));
+  dim3 grid((unsigned)((ld + PRED_THREADS - 1) / PRED_THREADS), (unsigned)((nrows + PRED_ROWS - 1) / PRED_ROWS));
   if (mode == DRS_MODE_F32)
-    pred_kernel<float><<<grid, 256, 0, st>>>((const float*)local_dev, ld, row0, nrows, g->n, g->d_in_ptr,
+    pred_kernel<float><<<grid, PRED_THREADS, 0, st>>>((const float*)local_dev, ld, row0, nrows, g->n, g->d_in_ptr,
                                              g->d_in_src, g->d_in_eid, g->d_in_w, pred_local_dev);
   else if (mode == DRS_MODE_I32)
-    pred_kernel<int><<<grid, 256, 0, st>>>((const int*)local_dev, ld, row0, nrows, g->n, g->d_in_ptr,
+    pred_kernel<int><<<grid, PRED_THREADS, 0, st>>>((const int*)local_dev, ld, row0, nrows, g->n, g->d_in_ptr,
                                            g->d_in_src, g->d_in_eid, g->d_in_w, pred_local_dev);
   else
     DRS_REQUIRE(false, DRS_ERR_ARG, "drs_pred_build: unknown mode %d", mode);

@@ -158,7 +158,7 @@ class RoadGraph(object):
     ``ttmedian`` after load).
     """
 
-    def __init__(self, data, mode=_lib.MODE_F32, algorithm=_lib.APSP_AUTO):
+    def __init__(self, data, mode=_lib.MODE_F32, algorithm=_lib.APSP_AUTO, pred=_lib.PRED_LAZY):
         if not isinstance(data, RoadGraphData):
             raise TypeError("RoadGraph needs RoadGraphData (use RoadGraph.Read_GML)")
         self.n, self.m = data.n, data.m
@@ -168,6 +168,7 @@ class RoadGraph(object):
         self._eattrs = {k: (np.array(v, dtype=np.float64) if isinstance(v, np.ndarray) else list(v))
                         for k, v in data.eattrs.items()}
         self.mode = mode
+        self.pred = pred              # _lib.PRED_LAZY (canonical rule evaluated per hop of a path query) | PRED_MATRIX
         self.algorithm = algorithm    # _lib.APSP_FW (blocked Floyd-Warshall) | APSP_SSSP (N delta-stepping searches) | APSP_AUTO
         self._handle = None
         self._weight_attr = None      # attribute the device weights / matrix were built from
@@ -323,6 +324,7 @@ class RoadGraph(object):
             self._valid = False
         if build and not self._valid:
             _lib.check(lib.drs_apsp_set_algorithm(self._handle, self.algorithm), lib)
+            _lib.check(lib.drs_apsp_set_pred_mode(self._handle, self.pred), lib)
             _lib.check(lib.drs_apsp_build(self._handle, self.mode), lib)
             self._valid = True
         return lib
@@ -336,10 +338,11 @@ class RoadGraph(object):
         return self._handle
 
     def adopt(self, dist_tensor, pred_tensor):
-        """Adopts externally built matrices (torch CUDA tensors from apsp_dist.gather_replica)."""
+        """Adopts externally built matrices (torch CUDA tensors from apsp_dist.gather_replica); pred_tensor may be None."""
         lib = self._ensure(None, build=False)
         _lib.check(lib.drs_apsp_adopt(self._handle, self.mode, C.c_void_p(dist_tensor.data_ptr()),
-                                      C.c_void_p(pred_tensor.data_ptr()), dist_tensor.shape[1]), lib)
+                                      C.c_void_p(pred_tensor.data_ptr()) if pred_tensor is not None else None,
+                                      dist_tensor.shape[1]), lib)
         self._adopted = (dist_tensor, pred_tensor)     # keep the tensors alive
         self._valid = True
 

@@ -84,12 +84,13 @@ int drs_apsp_build(drs_graph* g, int32_t mode);
 /* Device pointers of the resident matrices (row-major, leading dimension
  * npad).  dist is float (DRS_MODE_F32) or int32 (DRS_MODE_I32); unreachable =
  * +inf / DRS_I32_INF.  pred[s*npad+t] is the id of the last edge on the
- * canonical shortest path s->t (-1 for s == t or unreachable). */
+ * canonical shortest path s->t (-1 for s == t or unreachable); *pred_dev is NULL
+ * unless DRS_PRED_MATRIX was selected. */
 #define DRS_I32_INF 0x3fffffff
 int drs_apsp_matrices(const drs_graph* g, void** dist_dev, int32_t** pred_dev, int64_t* ld);
 
 /* Adopt externally built matrices (multi-GPU build, or a cached matrix): the
- * library takes no ownership. */
+ * library takes no ownership.  pred_dev may be NULL (lazy predecessors). */
 int drs_apsp_adopt(drs_graph* g, int32_t mode, void* dist_dev, int32_t* pred_dev, int64_t ld);
 
 /* Copy rows [row0, row0+nrows) x columns [0, n) of the distance matrix to the
@@ -105,6 +106,13 @@ int drs_apsp_rows_to_host(const drs_graph* g, int32_t row0, int32_t nrows, doubl
 #define DRS_APSP_SSSP 1
 #define DRS_APSP_AUTO 2
 int drs_apsp_set_algorithm(drs_graph* g, int32_t algorithm);
+
+/* Predecessors.  LAZY (default): no predecessor matrix; path queries evaluate the canonical rule on the
+ * spot from the distance row and the target's in-arcs (a handful of extra gathers per hop, half the HBM
+ * footprint and no predecessor pass at build time).  MATRIX: materialise pred[s*ld+t] during the build. */
+#define DRS_PRED_LAZY 0
+#define DRS_PRED_MATRIX 1
+int drs_apsp_set_pred_mode(drs_graph* g, int32_t pred_mode);
 
 /* --------------------------------------------------------- batched SSSP --
  * Distances from nsrc sources (delta-stepping, one CTA per source).  Replaces the same

@@ -18,11 +18,12 @@ def _engine(name, **kw):
 @pytest.mark.parametrize("name", MAPS)
 @pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("algorithm", [0, 1], ids=["fw", "sssp"])
-def test_matrix_and_paths_match_oracle(name, mode, algorithm):
+@pytest.mark.parametrize("pred", [0, 1], ids=["lazy", "matrix"])
+def test_matrix_and_paths_match_oracle(name, mode, algorithm, pred):
     if mode == 1 and "float" in name:
         pytest.skip("int32 mode needs integer weights")
     from drs_abm_b200.routing import RoadGraph
-    G = RoadGraph.Read_GML(golden_map_path(name), mode=mode, algorithm=algorithm)
+    G = RoadGraph.Read_GML(golden_map_path(name), mode=mode, algorithm=algorithm, pred=pred)
     O = oracle_graph(name)
     got = G.dist_rows(0, G.n)
     want = O.dist_matrix()
