@@ -329,6 +329,128 @@ def tick_e2e_section(G, data, config):
                                                     "pre-fetched from the matrix (no per-query Dijkstra), extrapolated" % (sub, n_veh)}}}
 
 
+class _SimReq(object):
+    def __init__(self, rid, o, d, lng, lat, Tr, Ts):
+        self.id, self.o, self.d = rid, o, d
+        self.olng, self.olat, self.dlng, self.dlat = lng[o], lat[o], lng[d], lat[d]
+        self.Tr, self.Ts = Tr, Ts
+        self.Cep, self.Clp = Tr, Tr + 600.0                       # lib/Agents.py:766-769 (MAX_WAIT, MAX_DETOUR)
+        self.Ced, self.Cld = self.Cep + Ts, self.Clp + 1.5 * Ts
+        self.assigned = False
+
+    def get_dropoff_time_window(self):
+        return [self.Ced, self.Cld]
+
+
+class _SimVeh(object):
+    """Vehicle state for the tick loop below: a plan of (rid, pod, node, arrival time).  Between two stops the
+    vehicle is represented by the node of its next stop and the time left to reach it (the reference uses the next
+    graph vertex on the path, lib/Agents.py:322-331; this coarser stand-in keeps the agents layer out of the bench)."""
+
+    def __init__(self, vid, K, node, lng, lat):
+        self.id, self.K, self.node, self.plan, self.onboard = vid, K, node, [], set()
+        self._lng, self._lat = lng, lat
+
+    def advance(self, T):
+        while self.plan and self.plan[0][3] <= T:
+            rid, pod, node, _ = self.plan.pop(0)
+            self.node = node
+            (self.onboard.add if pod > 0 else self.onboard.discard)(rid)
+
+    def get_next_node(self):
+        return (self._lng[self.node], self._lat[self.node]), 0.0
+
+    def get_passenger_requests(self):
+        return set(self.onboard), set(rid for (rid, pod, _, _) in self.plan if pod > 0)
+
+    def position(self, T):
+        """(node, delay): next stop and time to reach it, or the parked node."""
+        if self.plan:
+            return self.plan[0][2], max(0.0, self.plan[0][3] - T)
+        return self.node, 0.0
+
+
+def sim_section(G, data, config, ticks=40):
+    """A stretch of simulated operation through the drop-in API only: every 30 s new requests arrive, get their
+    windows from the router, AlonsoMora.optimizeAssignment (trips <= 2) assigns them, the plans of the chosen vehicles
+    are rebuilt from the matrix.  Fleet and demand of BASELINE config C3 / C2 (2 000 vehicles, 200k requests per day)."""
+    from drs_abm_b200.dispatch import AlonsoMora
+    n_veh, per_day = {"C3": (2000, 200000), "C2": (200, 10000), "C1": (10, 12000)}[config]
+    rate = per_day * 30.0 / 86400.0
+    rs = np.random.RandomState(17)
+    lng, lat = data.vattrs["lng"], data.vattrs["lat"]
+    node_of = {}
+
+    class V(_SimVeh):
+        def get_next_node(self):
+            nd, delay = self.position(self._T)
+            return (lng[nd], lat[nd]), delay
+    vehs = [V(k, 4, int(rs.randint(data.n)), lng, lat) for k in range(n_veh)]
+    reqs = []
+    opt = AlonsoMora({"routing_method": "enumerate", "verbose": False, "max_trip_size": 2})
+    served = rejected = 0
+    t_opt = t_all = 0.0
+    T = 0.0
+    for tick in range(ticks):
+        t0 = time.time()
+        T = 30.0 * tick
+        for v in vehs:
+            v._T = T
+            v.advance(T)
+        k = int(rs.poisson(rate))
+        if k:
+            o = rs.randint(0, data.n, k)
+            d = (o + 1 + rs.randint(0, data.n - 1, k)) % data.n
+            Ts = G.path_sums(o, d)[0]
+            for i in range(k):
+                if np.isfinite(Ts[i]):
+                    reqs.append(_SimReq(len(reqs), int(o[i]), int(d[i]), lng, lat, T - float(rs.randint(0, 30)), float(Ts[i])))
+        t1 = time.time()
+        (routes, rej), meta = opt.optimizeAssignment(vehs, reqs, G, T)
+        t_opt += time.time() - t1
+        if isinstance(routes, dict):
+            by_loc = {}
+            legs_s, legs_t, owners = [], [], []
+            for vid, route in routes.items():
+                veh = vehs[vid]
+                cur, _ = veh.position(T)
+                for (rid, pod, slng, slat) in route:
+                    nd = G.node_of_location(slng, slat)
+                    legs_s.append(cur); legs_t.append(nd); owners.append(vid); cur = nd
+            tt = G.matrix_lookup(legs_s, legs_t) if legs_s else []
+            pos = 0
+            for vid, route in routes.items():
+                veh = vehs[vid]
+                _, delay = veh.position(T)
+                t = T + delay
+                plan = []
+                for (rid, pod, slng, slat) in route:
+                    t += float(tt[pos]); pos += 1
+                    plan.append((rid, pod, G.node_of_location(slng, slat), t))
+                    if pod > 0 and not reqs[rid].assigned:
+                        reqs[rid].assigned = True
+                        served += 1
+                # the first stop's node stays the vehicle's anchor until it is reached
+                veh.plan = plan
+            for rid in rej:
+                reqs[rid].assigned = True
+                rejected += 1
+        else:
+            for r in reqs:                                   # empty RTV graph: nothing assignable this tick
+                if r.assigned is False:
+                    r.assigned = True
+                    rejected += 1
+        t_all += time.time() - t0
+    return {"sim": {"workload": "%d ticks of 30 s, %d vehicles (K=4), %.0f requests/day, AlonsoMora(enumerate, trips <= 2) on the %s map"
+                                % (ticks, n_veh, per_day, config),
+                    "requests": len(reqs), "served": served, "rejected": rejected,
+                    "s_per_tick": t_all / ticks, "s_per_tick_in_optimizer": t_opt / ticks,
+                    "simulated_seconds_per_wall_second": 30.0 * ticks / t_all,
+                    "wall_seconds_per_simulated_day": t_all / ticks * 2880,
+                    "note": "agents layer replaced by a minimal plan follower (vehicles are anchored at their next stop); "
+                            "routing and dispatch go through the public drop-in API only"}}
+
+
 def sssp_c5_section(peaks, n_sources=4096):
     """BASELINE config C5: 200k-node metro CSR, batched delta-stepping SSSP only (no N x N matrix)."""
     import ctypes as C
@@ -604,6 +726,7 @@ def main():
                 G2.build()
             line.update(insertion_section(G2, data, args.config, peaks))
             line.update(tick_e2e_section(G2, data, args.config))
+            line.update(sim_section(G2, data, args.config))
         if world == 1 and not args.no_insertion and args.config == "C3":
             G2.close()
             torch.cuda.empty_cache()
