@@ -8,16 +8,18 @@
 // fp64 in the reference's operation order, so integer-weighted inputs give
 // bit-identical costs; travel times are gathered from the resident matrix.
 //
-// Two kernels:
-//   rv_filter_kernel   one thread per (request, vehicle) pair: the reachability
-//                      pre-filter (lib/Optimization.py:183-186) and the
+// Kernels:
+//   rv_filter_kernel   one thread per (request, vehicle) pair, vehicles fastest: the
+//                      reachability pre-filter (lib/Optimization.py:183-186) and the
 //                      empty-dummy-vehicle check (:193-202); survivors are appended
-//                      to a compact task list.
-//   trip_eval_kernel   one thread per task: gathers the (S+1)^2 travel times among
-//                      the task's vertices, runs the pairwise pre-checks
-//                      (lib/optimUtils.py:127-156) and a depth-first enumeration of
-//                      the precedence-respecting orderings in lexicographic order
-//                      with exact feasibility / cost-bound pruning.
+//                      to a compact task list (warp-aggregated atomic).
+//   rv_eval_kernel     one thread per surviving pair: findOptimalRouting of the
+//                      request inserted into the vehicle's plan.
+//   trip_eval_kernel   one thread per explicit trip (RR edges, RTV trips): gathers the
+//                      (S+1)^2 travel times among the trip's vertices, runs the pairwise
+//                      pre-checks (lib/optimUtils.py:127-156) and a depth-first
+//                      enumeration of the precedence-respecting orderings in
+//                      lexicographic order with exact feasibility / cost-bound pruning.
 #include <algorithm>
 #include <cstring>
 #include <numeric>
