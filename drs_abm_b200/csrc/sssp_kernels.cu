@@ -9,12 +9,14 @@
 //
 // Per source: the distance row lives directly in the output matrix (global memory,
 // L2-resident while the CTA works on it).  A vertex whose tentative distance improves
-// is appended to the NEAR queue when the new distance is below the current threshold
-// theta, otherwise to the FAR pile; when NEAR drains, theta jumps to the bucket of the
-// smallest valid FAR entry and the pile is split again.  Entries carry the distance they
-// were pushed with, so stale ones (a better distance arrived later) are skipped.
-// Relaxations are atomicMin on the row (non-negative floats order like their bit
-// patterns); arcs are read as one 8-byte (target, weight) record per arc.
+// is appended to the NEAR queue (shared memory, spilling to global) when the new distance
+// is below the current threshold theta, otherwise to the FAR pile (global); when NEAR
+// drains, theta jumps to the bucket of the smallest valid FAR entry and the pile is split
+// again.  Entries carry the distance they were pushed with, so stale ones (a better
+// distance arrived later) are skipped.  Relaxations read the target first and issue an
+// atomicMin on the row only when they improve it (non-negative floats order like their
+// bit patterns); the adjacency of a vertex is one 32-byte ELL record of four
+// (target, weight) slots, read with two 16-byte loads.
 #include <algorithm>
 #include <limits>
 #include <vector>
@@ -40,28 +42,44 @@ template <> struct Dist<int> {
   static __device__ __forceinline__ int next_theta(int dmin, int delta) { return (dmin / delta + 1) * delta; }
 };
 
+#ifndef DRS_SSSP_MIN_THREADS_PER_SM
+#define DRS_SSSP_MIN_THREADS_PER_SM 1152   // resident threads per SM the register allocation must allow (measured best)
+#endif
 struct Entry { int v; int key; };   // v = vertex | (source slot << 24); key = distance bits at push time
 constexpr int SSSP_D = 4;            // arcs per entry handled in registers (road networks: degree <= 4 almost everywhere)
 constexpr int SLOT_SHIFT = 24;
 constexpr int VERTEX_MASK = (1 << SLOT_SHIFT) - 1;
 
-// One CTA advances SSSP_S sources in lock step: their wavefronts pass the same distance buckets at the
-// same time, so one near queue / far pile / theta serves all of them and every barrier and dependent L2
-// round trip of an iteration is shared by SSSP_S searches (the kernel is latency bound, not bandwidth bound).
-#ifndef DRS_SSSP_MIN_THREADS_PER_SM
-#define DRS_SSSP_MIN_THREADS_PER_SM 1152   // resident threads per SM the register allocation must allow (measured best)
+#ifndef DRS_SSSP_NQ
+#define DRS_SSSP_NQ 512
 #endif
+constexpr int SSSP_NQ = DRS_SSSP_NQ;  // NEAR-queue entries held in shared memory per buffer; the rest spills to global (a large carve-out would cost the L1 that caches the adjacency)
+
+// One CTA advances SSSP_S sources in lock step (S = 1 by default): their wavefronts pass the same distance
+// buckets at the same time, so one near queue / far pile / theta serves all of them.
+//
+// Dependent memory round trips per NEAR iteration: queue entry (shared memory) -> {stale check of the row,
+// the vertex's 4-slot adjacency record} (both need only the vertex id) -> target distances -> atomicMins ->
+// pushes (shared memory).  The adjacency is an ELL record of 4 (target, weight) slots per vertex (32 bytes, two
+// 16-byte loads); slot 3 == (-2, a) says "more arcs follow in the CSR from index a".
 template <typename T, int SSSP_THREADS, int SSSP_S>
 __global__ void __launch_bounds__(SSSP_THREADS, DRS_SSSP_MIN_THREADS_PER_SM / SSSP_THREADS) sssp_batch_kernel(
-    int n, const int32_t* __restrict__ out_ptr, const int2* __restrict__ arcs, T* dist, int64_t ld, int64_t row_stride,
-    const int32_t* __restrict__ sources, int nsrc, Entry* queues, int cap, T delta, int* overflow) {
+    int n, const int32_t* __restrict__ out_ptr, const int2* __restrict__ arcs, const int4* __restrict__ ell, T* dist, int64_t ld,
+    int64_t row_stride, const int32_t* __restrict__ sources, int nsrc, Entry* queues, int cap, T delta, int* overflow) {
   __shared__ int s_near, s_next, s_far, s_keep, s_min, s_group;
+  __shared__ Entry s_q[2][SSSP_NQ];
   int* next_group = overflow + 1;   // dynamic work distribution: searches differ in length (corner vs centre sources)
-  Entry* cur = queues + (int64_t)blockIdx.x * 4 * cap;
-  Entry* nxt = cur + cap;
-  Entry* far = nxt + cap;
+  Entry* gq[2] = {queues + (int64_t)blockIdx.x * 4 * cap, queues + (int64_t)blockIdx.x * 4 * cap + cap};
+  Entry* far = gq[1] + cap;
   Entry* far2 = far + cap;
+  int sel = 0;                       // s_q[sel] / gq[sel] is the current NEAR queue
   const int tid = threadIdx.x;
+  auto q_put = [&](int which, int pos, Entry e) {
+    if (pos < SSSP_NQ) s_q[which][pos] = e;
+    else if (pos - SSSP_NQ < cap) gq[which][pos - SSSP_NQ] = e;
+    else *overflow = 1;
+  };
+  auto q_get = [&](int which, int pos) { return pos < SSSP_NQ ? s_q[which][pos] : gq[which][pos - SSSP_NQ]; };
   while (true) {
     if (tid == 0) s_group = atomicAdd(next_group, 1);
     __syncthreads();
@@ -75,7 +93,7 @@ __global__ void __launch_bounds__(SSSP_THREADS, DRS_SSSP_MIN_THREADS_PER_SM / SS
     if (tid < ns) {
       const int src = sources[k0 + tid];
       rows[(int64_t)tid * row_stride + src] = (T)0;
-      cur[tid] = Entry{src | (tid << SLOT_SHIFT), Dist<T>::key((T)0)};
+      s_q[sel][tid] = Entry{src | (tid << SLOT_SHIFT), Dist<T>::key((T)0)};
     }
     if (tid == 0) { s_near = ns; s_next = 0; s_far = 0; }
     T theta = delta;
@@ -86,62 +104,57 @@ __global__ void __launch_bounds__(SSSP_THREADS, DRS_SSSP_MIN_THREADS_PER_SM / SS
         const int nn = s_near;
         if (nn == 0) break;
         for (int e = tid; e < nn; e += SSSP_THREADS) {
-          const Entry en = cur[e];
+          const Entry en = q_get(sel, e);
           const int v = en.v & VERTEX_MASK, slot = en.v >> SLOT_SHIFT;
           T* row = rows + (int64_t)slot * row_stride;
           const int kcur = Dist<T>::key(__ldcg(&row[v]));   // L2 read: the atomics live there
-          const int a0 = out_ptr[v];
-          int deg = out_ptr[v + 1] - a0;
-          if (kcur != en.key) deg = 0;                       // stale: a shorter distance arrived later
-          // arc records, then ALL atomicMins in flight together, then the queue pushes
-          int2 arc[SSSP_D];
+          const int4 r0 = ell[2 * v], r1 = ell[2 * v + 1];
+          if (kcur != en.key) continue;                      // stale: a shorter distance arrived later
+          const int2 arc[SSSP_D] = {make_int2(r0.x, r0.y), make_int2(r0.z, r0.w), make_int2(r1.x, r1.y), make_int2(r1.z, r1.w)};
           int nk[SSSP_D], old[SSSP_D];
-#pragma unroll
-          for (int j = 0; j < SSSP_D; ++j)
-            if (j < deg) arc[j] = arcs[a0 + j];
           // plain L2 reads first: most arcs point back at settled vertices and need no atomic at all
-          // (the kernel is bound by L2 atomic throughput, loads are several times cheaper)
 #pragma unroll
           for (int j = 0; j < SSSP_D; ++j)
-            if (j < deg) {
+            if (arc[j].x >= 0) {
               nk[j] = Dist<T>::key(Dist<T>::unkey(en.key) + Dist<T>::weight(arc[j].y));
               old[j] = Dist<T>::key(__ldcg(&row[arc[j].x]));
             }
 #pragma unroll
           for (int j = 0; j < SSSP_D; ++j)
-            if (j < deg && nk[j] < old[j]) old[j] = atomicMin(reinterpret_cast<int*>(row) + arc[j].x, nk[j]);
+            if (arc[j].x >= 0 && nk[j] < old[j]) old[j] = atomicMin(reinterpret_cast<int*>(row) + arc[j].x, nk[j]);
 #pragma unroll
           for (int j = 0; j < SSSP_D; ++j)
-            if (j < deg && nk[j] < old[j]) {
+            if (arc[j].x >= 0 && nk[j] < old[j]) {
               const Entry ne{arc[j].x | (slot << SLOT_SHIFT), nk[j]};
               if (Dist<T>::unkey(nk[j]) < theta) {
-                const int pos = atomicAdd(&s_next, 1);
-                if (pos < cap) nxt[pos] = ne; else *overflow = 1;
+                q_put(sel ^ 1, atomicAdd(&s_next, 1), ne);
               } else {
                 const int pos = atomicAdd(&s_far, 1);
                 if (pos < cap) far[pos] = ne; else *overflow = 1;
               }
             }
-          for (int a = a0 + SSSP_D; a < a0 + deg; ++a) {   // vertices with more than SSSP_D arcs
-            const int2 ar = arcs[a];
-            const int k2 = Dist<T>::key(Dist<T>::unkey(en.key) + Dist<T>::weight(ar.y));
-            int o2 = Dist<T>::key(__ldcg(&row[ar.x]));
-            if (k2 < o2) o2 = atomicMin(reinterpret_cast<int*>(row) + ar.x, k2);
-            if (k2 < o2) {
-              const Entry ne{ar.x | (slot << SLOT_SHIFT), k2};
-              if (Dist<T>::unkey(k2) < theta) {
-                const int pos = atomicAdd(&s_next, 1);
-                if (pos < cap) nxt[pos] = ne; else *overflow = 1;
-              } else {
-                const int pos = atomicAdd(&s_far, 1);
-                if (pos < cap) far[pos] = ne; else *overflow = 1;
+          if (arc[SSSP_D - 1].x == -2) {                      // high-degree vertex: the remaining arcs live in the CSR
+            const int a1 = out_ptr[v + 1];
+            for (int a = arc[SSSP_D - 1].y; a < a1; ++a) {
+              const int2 ar = arcs[a];
+              const int k2 = Dist<T>::key(Dist<T>::unkey(en.key) + Dist<T>::weight(ar.y));
+              int o2 = Dist<T>::key(__ldcg(&row[ar.x]));
+              if (k2 < o2) o2 = atomicMin(reinterpret_cast<int*>(row) + ar.x, k2);
+              if (k2 < o2) {
+                const Entry ne{ar.x | (slot << SLOT_SHIFT), k2};
+                if (Dist<T>::unkey(k2) < theta) {
+                  q_put(sel ^ 1, atomicAdd(&s_next, 1), ne);
+                } else {
+                  const int pos = atomicAdd(&s_far, 1);
+                  if (pos < cap) far[pos] = ne; else *overflow = 1;
+                }
               }
             }
           }
         }
         __syncthreads();
-        if (tid == 0) { s_near = min(s_next, cap); s_next = 0; }
-        Entry* tmp = cur; cur = nxt; nxt = tmp;
+        if (tid == 0) { s_near = min(s_next, SSSP_NQ + cap); s_next = 0; }
+        sel ^= 1;
         __syncthreads();
       }
       // ---- NEAR is empty: advance theta to the bucket of the smallest valid FAR entry (any source)
@@ -165,7 +178,7 @@ __global__ void __launch_bounds__(SSSP_THREADS, DRS_SSSP_MIN_THREADS_PER_SM / SS
         const Entry en = far[e];
         const T* row = rows + (int64_t)(en.v >> SLOT_SHIFT) * row_stride;
         if (Dist<T>::key(__ldcg(&row[en.v & VERTEX_MASK])) != en.key) continue;
-        if (Dist<T>::unkey(en.key) < theta) cur[atomicAdd(&s_near, 1)] = en;
+        if (Dist<T>::unkey(en.key) < theta) q_put(sel, atomicAdd(&s_near, 1), en);
         else far2[atomicAdd(&s_keep, 1)] = en;
       }
       __syncthreads();
@@ -187,6 +200,19 @@ __global__ void pad_rows_kernel(T* local, int64_t ld, int row0, int r_begin, int
   }
 }
 
+// ELL adjacency: 4 (target, weight) slots per vertex; unused slots (-1, 0); slot 3 = (-2, a) when more arcs follow at CSR index a
+__global__ void build_ell_kernel(int n, const int32_t* out_ptr, const int32_t* col, const float* w, int2* ell) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  const int a0 = out_ptr[v], deg = out_ptr[v + 1] - a0;
+  for (int j = 0; j < SSSP_D; ++j) {
+    int2 rec = make_int2(-1, 0);
+    if (j < deg) rec = make_int2(col[a0 + j], __float_as_int(w[a0 + j]));
+    if (j == SSSP_D - 1 && deg > SSSP_D) rec = make_int2(-2, a0 + SSSP_D - 1);
+    ell[(int64_t)v * SSSP_D + j] = rec;
+  }
+}
+
 __global__ void pack_arcs_kernel(int narcs, const int32_t* col, const float* w, int2* arcs) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a < narcs) arcs[a] = make_int2(col[a], __float_as_int(w[a]));
@@ -202,13 +228,13 @@ int sssp_threads() { static int t = sssp_env("DRS_SSSP_THREADS", 128, 64, 128, 2
 int sssp_slots() { static int u = sssp_env("DRS_SSSP_S", 1, 1, 2, 4) ; return u; }   // sources per CTA (also 8 below)
 
 template <typename T, int TH, int U>
-int sssp_launch(bool query, int* per_sm, int grid, cudaStream_t st, int n, const int32_t* out_ptr, const int2* arcs, T* dist,
-                int64_t ld, int64_t row_stride, const int32_t* sources, int nsrc, Entry* queues, int cap, T delta, int* overflow) {
+int sssp_launch(bool query, int* per_sm, int grid, cudaStream_t st, int n, const int32_t* out_ptr, const int2* arcs, const int4* ell,
+                T* dist, int64_t ld, int64_t row_stride, const int32_t* sources, int nsrc, Entry* queues, int cap, T delta, int* overflow) {
   if (query) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, sssp_batch_kernel<T, TH, U>, TH, 0);
     return DRS_OK;
   }
-  sssp_batch_kernel<T, TH, U><<<grid, TH, 0, st>>>(n, out_ptr, arcs, dist, ld, row_stride, sources, nsrc, queues, cap, delta, overflow);
+  sssp_batch_kernel<T, TH, U><<<grid, TH, 0, st>>>(n, out_ptr, arcs, ell, dist, ld, row_stride, sources, nsrc, queues, cap, delta, overflow);
   return DRS_OK;
 }
 
@@ -226,7 +252,7 @@ int sssp_dispatch(A... args) {
 template <typename T>
 int sssp_grid(int sms, int nsrc) {
   int per_sm = 1;
-  sssp_dispatch<T>(true, &per_sm, 0, (cudaStream_t) nullptr, 0, (const int32_t*)nullptr, (const int2*)nullptr, (T*)nullptr,
+  sssp_dispatch<T>(true, &per_sm, 0, (cudaStream_t) nullptr, 0, (const int32_t*)nullptr, (const int2*)nullptr, (const int4*)nullptr, (T*)nullptr,
                    (int64_t)0, (int64_t)0, (const int32_t*)nullptr, 0, (Entry*)nullptr, 0, (T)0, (int*)nullptr);
   const int groups = (nsrc + sssp_slots() - 1) / sssp_slots();
   // CTAs in flight per SM: every CTA keeps one distance row (4n bytes) hot, and the rows of all resident CTAs
@@ -239,11 +265,11 @@ int sssp_grid(int sms, int nsrc) {
 
 template <typename T>
 int sssp_run(const drs_graph* g, int nsrc, const int32_t* sources_dev, T* dist, int64_t ld, int64_t row_stride, double delta,
-             cudaStream_t st, const int2* arcs, Entry* queues, int cap, int grid, int* overflow) {
+             cudaStream_t st, const int2* arcs, const int4* ell, Entry* queues, int cap, int grid, int* overflow) {
   T d = (T)delta;
   if (!(d > (T)0)) d = (T)1;
   int dummy = 0;
-  sssp_dispatch<T>(false, &dummy, grid, st, g->n, (const int32_t*)g->d_out_ptr, arcs, dist, ld, row_stride, sources_dev, nsrc, queues,
+  sssp_dispatch<T>(false, &dummy, grid, st, g->n, (const int32_t*)g->d_out_ptr, arcs, ell, dist, ld, row_stride, sources_dev, nsrc, queues,
                    cap, d, overflow);
   drs_count_launch();
   DRS_CUDA(cudaGetLastError());
@@ -273,10 +299,13 @@ extern "C" int drs_sssp_batch_dev(const drs_graph* g, int32_t mode, int32_t nsrc
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g->device);
   const int grid = mode == DRS_MODE_F32 ? sssp_grid<float>(sms, nsrc) : sssp_grid<int>(sms, nsrc);
-  if (!gm->sssp_arcs) DRS_CUDA(cudaMalloc(&gm->sssp_arcs, sizeof(int2) * std::max(g->narcs, 1)));
-  if (!gm->sssp_arcs_valid && g->narcs) {
-    pack_arcs_kernel<<<(g->narcs + 255) / 256, 256, 0, st>>>(g->narcs, g->d_out_col, g->d_out_w, (int2*)gm->sssp_arcs);
-    drs_count_launch();
+  // packed arcs (narcs records) followed by the ELL records (4 per vertex)
+  if (!gm->sssp_arcs) DRS_CUDA(cudaMalloc(&gm->sssp_arcs, sizeof(int2) * ((size_t)std::max(g->narcs, 1) + 1 + (size_t)SSSP_D * g->n)));
+  int2* d_ell = (int2*)gm->sssp_arcs + ((std::max(g->narcs, 1) + 1) & ~1);   // 16-byte aligned
+  if (!gm->sssp_arcs_valid) {
+    if (g->narcs) pack_arcs_kernel<<<(g->narcs + 255) / 256, 256, 0, st>>>(g->narcs, g->d_out_col, g->d_out_w, (int2*)gm->sssp_arcs);
+    build_ell_kernel<<<(g->n + 255) / 256, 256, 0, st>>>(g->n, g->d_out_ptr, g->d_out_col, g->d_out_w, d_ell);
+    drs_count_launch(2);
     DRS_CUDA(cudaGetLastError());
     gm->sssp_arcs_valid = true;
   }
@@ -304,10 +333,10 @@ extern "C" int drs_sssp_batch_dev(const drs_graph* g, int32_t mode, int32_t nsrc
     cudaMemsetAsync(d_overflow, 0, 2 * sizeof(int), st);   // overflow flag + work counter
     cudaMemcpyAsync(d_sources, sources_host, sizeof(int32_t) * nsrc, cudaMemcpyHostToDevice, st);
     if (mode == DRS_MODE_F32)
-      rc = sssp_run<float>(g, nsrc, d_sources, (float*)dist_dev, ld, ld, delta, st, (const int2*)gm->sssp_arcs,
+      rc = sssp_run<float>(g, nsrc, d_sources, (float*)dist_dev, ld, ld, delta, st, (const int2*)gm->sssp_arcs, (const int4*)d_ell,
                            (Entry*)gm->sssp_queues, cap, grid, d_overflow);
     else
-      rc = sssp_run<int>(g, nsrc, d_sources, (int*)dist_dev, ld, ld, delta, st, (const int2*)gm->sssp_arcs,
+      rc = sssp_run<int>(g, nsrc, d_sources, (int*)dist_dev, ld, ld, delta, st, (const int2*)gm->sssp_arcs, (const int4*)d_ell,
                          (Entry*)gm->sssp_queues, cap, grid, d_overflow);
     if (rc) break;
     int ovf = 0;
