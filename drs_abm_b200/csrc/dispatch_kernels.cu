@@ -372,8 +372,9 @@ extern "C" int drs_tick_set_vehicles(drs_tick* t, const drs_vehicle_batch* b) {
   int rc;
   std::vector<int32_t> perm(std::max(nv, 1));
   for (int v = 0; v < nv; ++v) perm[v] = v;
+  // longest plans first: their ordering searches are the long ones and should not form the tail of the launch
   std::stable_sort(perm.begin(), perm.begin() + nv, [&](int x, int y) {
-    return (b->stop_off[x + 1] - b->stop_off[x]) < (b->stop_off[y + 1] - b->stop_off[y]);
+    return (b->stop_off[x + 1] - b->stop_off[x]) > (b->stop_off[y + 1] - b->stop_off[y]);
   });
   if ((rc = upload(&d.v_perm, perm.data(), nv, st))) return rc;
   d.directed = t->g->directed;
