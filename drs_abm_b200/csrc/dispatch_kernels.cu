@@ -13,9 +13,9 @@
 //                      reachability pre-filter (lib/Optimization.py:183-186) and the
 //                      empty-dummy-vehicle check (:193-202); survivors are appended
 //                      to a compact task list (warp-aggregated atomic).
-//   rv_eval_kernel     one thread per surviving pair: findOptimalRouting of the
+//   rv_eval_kernel     eight lanes per surviving pair: findOptimalRouting of the
 //                      request inserted into the vehicle's plan.
-//   trip_eval_kernel   one thread per explicit trip (RR edges, RTV trips): gathers the
+//   trip_eval_kernel   eight lanes per explicit trip (RR edges, RTV trips): gathers the
 //                      (S+1)^2 travel times among the trip's vertices, runs the pairwise
 //                      pre-checks (lib/optimUtils.py:127-156) and a depth-first
 //                      enumeration of the precedence-respecting orderings in
@@ -42,7 +42,8 @@ struct Trip {
   int node[MAXS + 1];
   double lb[MAXS], ub[MAXS];
   int8_t pod[MAXS], prev[MAXS];
-  int group[MAXS];        // request group of each stop (for the pairwise pre-checks)
+  uint8_t group[MAXS];    // request group of each stop (for the pairwise pre-checks)
+  unsigned dropmask[MAXS];// bit j set in dropmask[i]: stop j is the drop-off whose pick-up is stop i
   double tt[(MAXS + 1) * (MAXS + 1)];   // travel times among the trip's vertices (matrix entries, exact)
 };
 
@@ -63,86 +64,82 @@ __device__ __forceinline__ double trip_tt(const Trip& tr, int a, int b) {
 // for hours (*exhausted is set; the host reports it).
 constexpr long long kSearchBudget = 20000000LL;   // ~20x the largest instance of a K=4 fleet (10 stops: 113 400 orderings)
 
+//
+// forced_first >= 0 restricts the first position to that stop (the lanes of a task split the search by first
+// stop); shared_best (may be null) is the task's incumbent cost as unsigned-long-long bits, shared by its lanes:
+// a partial ordering is dropped only when it is STRICTLY worse than the shared incumbent, so an equal-cost
+// ordering with a lexicographically smaller first stop is still found by its own lane.
+//
+// The loop is flat -- one candidate stop (or one backtrack) per iteration, the next admissible stop found with
+// bit masks (`unlocked` = stops whose pick-up precedes them or is outside the subset) -- so the lanes of a warp,
+// each on its own search, stay converged at the loop head.  The ordering in progress is packed 4 bits per depth.
 __device__ double trip_dfs(const Trip& tr, unsigned subset, double cap, int pax0, bool first_only,
-                           uint8_t* best_order, bool* exhausted) {
+                           uint8_t* best_order, bool* exhausted, int forced_first = -1,
+                           unsigned long long* shared_best = nullptr) {
   const int total = __popc(subset);
   long long visited = 0;
   double best = DRS_INF_ROUTE_COST;
-  int ord[MAXS];
-  int cand[MAXS + 1];
   double psum[MAXS + 1], cost[MAXS + 1];
-  int pax[MAXS + 1], cur[MAXS + 1];
-  unsigned used = 0;
-  int d = 0;
-  cand[0] = 0; psum[0] = 0.0; cost[0] = 0.0; pax[0] = pax0; cur[0] = 0;
-  while (d >= 0) {
+  unsigned long long ord = 0;
+  unsigned used = 0, unlocked = 0;
+  for (int i = 0; i < tr.ns; ++i) {
+    const int pv = tr.prev[i];
+    if (pv < 0 || !((subset >> pv) & 1u)) unlocked |= 1u << i;
+  }
+  const unsigned first_mask = forced_first >= 0 ? (1u << forced_first) : 0xffffffffu;
+  int d = 0, pax = pax0, start = 0;
+  psum[0] = 0.0; cost[0] = 0.0;
+  while (true) {
     if (++visited > kSearchBudget) { *exhausted = true; break; }
-    int i = cand[d];
-    // next admissible stop at this depth
-    while (i < tr.ns) {
-      const unsigned bit = 1u << i;
-      if ((subset & bit) && !(used & bit)) {
-        const int pv = tr.prev[i];
-        if (pv < 0 || !((subset >> pv) & 1u) || ((used >> pv) & 1u)) break;
-      }
-      ++i;
-    }
-    if (i >= tr.ns) {   // exhausted: backtrack
+    unsigned candm = subset & ~used & unlocked & (0xffffffffu << start);
+    if (d == 0) candm &= first_mask;
+    if (!candm) {   // no stop left at this depth: backtrack
+      if (d == 0) break;
       --d;
-      if (d >= 0) { used &= ~(1u << ord[d]); }
+      const int j = (int)((ord >> (4 * d)) & 15ull);
+      used &= ~(1u << j);
+      unlocked &= ~tr.dropmask[j];
+      if (d > 0 || tr.has_start) pax -= tr.pod[j];
+      start = j + 1;
       continue;
     }
-    cand[d] = i + 1;
+    const int i = __ffs(candm) - 1;   // orderings in lexicographic stop-index order
+    start = i + 1;
     double np, nc;
     int npax;
     if (d == 0 && !tr.has_start) {
       // no vehicle: the first stop is the start; never capacity-counted nor window-checked
       // (lib/optimUtils.py:475-488,540 iterate over orderedLocs[1:])
-      np = 0.0; nc = 0.0; npax = pax0;
+      np = 0.0; nc = 0.0; npax = pax;
     } else {
-      npax = pax[d] + tr.pod[i];
+      npax = pax + tr.pod[i];
       if ((double)npax > cap) continue;
-      np = psum[d] + trip_tt(tr, cur[d], i + 1);
+      const int cur = d == 0 ? 0 : (int)((ord >> (4 * (d - 1))) & 15ull) + 1;
+      np = psum[d] + trip_tt(tr, cur, i + 1);
       const double arr = tr.t_start + np;
       if (!(arr >= tr.lb[i] && arr <= tr.ub[i])) continue;
       nc = cost[d];
       if (tr.pod[i] < 0) nc += arr - tr.lb[i];
       if (!(nc < best)) continue;   // cost is non-decreasing along an ordering: exact pruning
+      if (shared_best && nc > __longlong_as_double((long long)*((volatile unsigned long long*)shared_best))) continue;
     }
-    ord[d] = i;
-    used |= 1u << i;
-    ++d;
-    if (d == total) {
+    ord = (ord & ~(15ull << (4 * d))) | ((unsigned long long)i << (4 * d));
+    if (d + 1 == total) {   // complete ordering, strictly cheaper than the incumbent
       best = nc;
+      if (shared_best) atomicMin(shared_best, (unsigned long long)__double_as_longlong(nc));   // costs are >= 0
       if (best_order)
-        for (int k = 0; k < total; ++k) best_order[k] = (uint8_t)ord[k];
+        for (int k = 0; k < total; ++k) best_order[k] = (uint8_t)((ord >> (4 * k)) & 15ull);
       if (first_only) return best;
-      --d;
-      used &= ~(1u << i);
       continue;
     }
-    cand[d] = 0; psum[d] = np; cost[d] = nc; pax[d] = npax; cur[d] = i + 1;
+    used |= 1u << i;
+    unlocked |= tr.dropmask[i];
+    pax = npax;
+    ++d;
+    psum[d] = np; cost[d] = nc;
+    start = 0;
   }
   return best;
-}
-
-// findOptimalRouting (lib/optimUtils.py:113-160) on a prepared Trip.
-// n_groups = number of distinct requests; groups [0, n_new) are the new ones.
-__device__ double trip_solve(const Trip& tr, int n_groups, int n_new, int flags, uint8_t* best_order, bool* exhausted) {
-  const unsigned all = (tr.ns >= 32) ? 0xffffffffu : ((1u << tr.ns) - 1u);
-  if ((flags & DRS_EVAL_PAIRWISE_CHECKS) && tr.has_start && n_groups >= 3) {
-    for (int a = 0; a < n_groups; ++a)
-      for (int b = a + 1; b < n_groups; ++b) {
-        if (a >= n_new && b >= n_new) continue;   // both already on the vehicle (:142-143)
-        unsigned sub = 0;
-        for (int i = 0; i < tr.ns; ++i)
-          if (tr.group[i] == a || tr.group[i] == b) sub |= 1u << i;
-        // minimalDelayPath(comboLocs, G, startTime, startLoc): default capacity 1e6, startPax 0 (:148-149)
-        const double c = trip_dfs(tr, sub, 1e6, 0, true, nullptr, exhausted);
-        if (!(c < DRS_INF_ROUTE_COST)) return DRS_INF_ROUTE_COST;
-      }
-  }
-  return trip_dfs(tr, all, tr.cap, tr.pax0, false, best_order, exhausted);
 }
 
 struct TaskList {
@@ -151,15 +148,19 @@ struct TaskList {
   int32_t* req;     // MAXR per task
 };
 
-__device__ bool build_trip(Trip& tr, const TickDev& tk, const DistView& dv, double T, int v, int nreq,
-                           const int32_t* reqs, int* n_groups) {
+constexpr int GROUP = 8;                 // lanes cooperating on one task
+constexpr int TASKS_PER_BLOCK = 8;       // 64 threads per block
+
+// Stop records of a task (lane 0 of the group) -- createLocations order (lib/optimUtils.py:84-110).
+__device__ bool fill_trip(Trip& tr, const TickDev& tk, double T, int v, int nreq, const int32_t* reqs, int* n_groups) {
   int ns = 0;
-  for (int k = 0; k < nreq; ++k) {   // createLocations: new requests first (lib/optimUtils.py:86-92)
+  for (int i = 0; i < MAXS; ++i) tr.dropmask[i] = 0;
+  for (int k = 0; k < nreq; ++k) {   // new requests first (:86-92)
     const int r = reqs[k];
     tr.node[1 + ns] = tk.r_o[r]; tr.lb[ns] = tk.r_lbp[r]; tr.ub[ns] = tk.r_ubp[r]; tr.pod[ns] = 1;
     tr.prev[ns] = -1; tr.group[ns] = k; ++ns;
     tr.node[1 + ns] = tk.r_d[r]; tr.lb[ns] = tk.r_lbd[r]; tr.ub[ns] = tk.r_ubd[r]; tr.pod[ns] = -1;
-    tr.prev[ns] = (int8_t)(ns - 1); tr.group[ns] = k; ++ns;
+    tr.prev[ns] = (int8_t)(ns - 1); tr.group[ns] = k; tr.dropmask[ns - 1] = 1u << ns; ++ns;
   }
   int groups = nreq;
   if (v >= 0) {
@@ -170,7 +171,8 @@ __device__ bool build_trip(Trip& tr, const TickDev& tk, const DistView& dv, doub
       tr.node[1 + ns] = tk.s_node[s]; tr.lb[ns] = tk.s_lb[s]; tr.ub[ns] = tk.s_ub[s]; tr.pod[ns] = tk.s_pod[s];
       const int pv = tk.s_prev[s];
       tr.prev[ns] = (int8_t)(pv < 0 ? -1 : base + pv);
-      tr.group[ns] = pv < 0 ? groups++ : tr.group[base + pv];
+      tr.group[ns] = (uint8_t)(pv < 0 ? groups++ : tr.group[base + pv]);
+      if (pv >= 0) tr.dropmask[base + pv] = 1u << ns;
       ++ns;
     }
     tr.has_start = 1;
@@ -187,32 +189,112 @@ __device__ bool build_trip(Trip& tr, const TickDev& tk, const DistView& dv, doub
   }
   tr.ns = ns;
   *n_groups = groups;
-  for (int a = 0; a <= ns; ++a)
-    for (int b = 1; b <= ns; ++b) {
-      tr.tt[a * (MAXS + 1) + b] = (tr.node[a] == tr.node[b]) ? 0.0 : dv.at(tr.node[a], tr.node[b]);
-    }
   return true;
 }
 
-__global__ void trip_eval_kernel(TickDev tk, DistView dv, double T, int flags, int ntasks, TaskList tl, double* cost_out,
-                                 uint8_t* order_out, int32_t* nstops_out) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= ntasks) return;
-  Trip tr;
-  int groups = 0;
-  uint8_t order[MAXS];
-  for (int i = 0; i < MAXS; ++i) order[i] = 0xff;
-  double cost = DRS_INF_ROUTE_COST;
-  int ns = -1;   // -1: too many stops for DRS_MAX_STOPS
-  if (build_trip(tr, tk, dv, T, tl.veh[k], tl.nreq[k], tl.req + (int64_t)k * MAXR, &groups)) {
-    ns = tr.ns;
-    bool exhausted = false;
-    cost = trip_solve(tr, groups, tl.nreq[k], flags, order, &exhausted);
-    if (exhausted) ns = -2;
+// findOptimalRouting (lib/optimUtils.py:113-160) for one task by a group of GROUP lanes: the trip lives in
+// shared memory; the lanes gather the (S+1) x S travel times together, split the pairwise pre-checks by pair and
+// the final enumeration by first stop, share the incumbent cost, and lane 0 writes the result.  The winner among
+// equal costs is the lane with the smallest first stop = the lexicographically smallest ordering (each lane visits
+// its own orderings in lexicographic order and keeps the first minimum).
+__device__ void group_solve(Trip& tr, unsigned long long& shared_best, int* s_flag, const TickDev& tk, const DistView& dv,
+                            double T, int flags, bool active, int v, int nreq, const int32_t* reqs, int lane, unsigned gmask,
+                            double* cost_out, int* ns_out, uint8_t* order_out) {
+  // s_flag[0]: trip fits, [1]: groups, [2]: a pairwise check failed, [3]: budget exhausted
+  if (lane == 0) {
+    int groups = 0;
+    const bool ok = active && fill_trip(tr, tk, T, v, nreq, reqs, &groups);
+    s_flag[0] = ok ? 1 : 0; s_flag[1] = groups; s_flag[2] = 0; s_flag[3] = 0;
+    shared_best = (unsigned long long)__double_as_longlong(DRS_INF_ROUTE_COST);
   }
-  cost_out[k] = cost;
-  nstops_out[k] = ns;
-  for (int i = 0; i < MAXS; ++i) order_out[(int64_t)k * MAXS + i] = order[i];
+  __syncwarp(gmask);
+  const bool fits = s_flag[0] != 0;
+  const int ns = fits ? tr.ns : 0, groups = s_flag[1];
+  for (int idx = lane; idx < (ns + 1) * ns; idx += GROUP) {   // travel times among the trip's vertices
+    const int a = idx / ns, b = idx % ns + 1;
+    tr.tt[a * (MAXS + 1) + b] = (tr.node[a] == tr.node[b]) ? 0.0 : dv.at(tr.node[a], tr.node[b]);
+  }
+  __syncwarp(gmask);
+  bool exhausted = false;
+  // Work is dealt to the lanes so that all of them enter trip_dfs at the same point of the program (a lane that
+  // called it from inside a divergent branch would run alone while the others wait).
+  if (fits && (flags & DRS_EVAL_PAIRWISE_CHECKS) && tr.has_start && groups >= 3) {
+    int npairs = 0;
+    for (int a = 0; a < groups; ++a)
+      for (int b = a + 1; b < groups; ++b)
+        if (!(a >= nreq && b >= nreq)) ++npairs;   // both already on the vehicle: skipped (:142-143)
+    for (int p0 = 0; p0 < npairs; p0 += GROUP) {
+      const int mine = p0 + lane;
+      int pa = -1, pb = -1, pidx = 0;
+      for (int a = 0; a < groups; ++a)
+        for (int b = a + 1; b < groups; ++b) {
+          if (a >= nreq && b >= nreq) continue;
+          if (pidx++ == mine) { pa = a; pb = b; }
+        }
+      unsigned sub = 0;
+      for (int i = 0; i < ns; ++i)
+        if (tr.group[i] == pa || tr.group[i] == pb) sub |= 1u << i;
+      // minimalDelayPath(comboLocs, G, startTime, startLoc): default capacity 1e6, startPax 0 (:148-149)
+      const double c = sub ? trip_dfs(tr, sub, 1e6, 0, true, nullptr, &exhausted) : 0.0;
+      if (!(c < DRS_INF_ROUTE_COST)) s_flag[2] = 1;
+    }
+  }
+  __syncwarp(gmask);
+  double best = DRS_INF_ROUTE_COST;
+  uint8_t order[MAXS];
+  int best_first = MAXS;
+  if (fits && !s_flag[2]) {
+    const unsigned all = (ns >= 32) ? 0xffffffffu : ((1u << ns) - 1u);
+    unsigned firsts = 0;   // stops that may come first
+    for (int f = 0; f < ns; ++f)
+      if (tr.prev[f] < 0) firsts |= 1u << f;
+    const int nf = __popc(firsts);
+    for (int k0 = 0; k0 < nf; k0 += GROUP) {
+      unsigned m = firsts;
+      for (int q = 0; q < k0 + lane; ++q) m &= m - 1;   // drop the k lowest
+      const int f = m ? __ffs(m) - 1 : -1;
+      uint8_t ord[MAXS];
+      const double c = f >= 0 ? trip_dfs(tr, all, tr.cap, tr.pax0, false, ord, &exhausted, f, &shared_best) : DRS_INF_ROUTE_COST;
+      if (c < best) { best = c; best_first = f; for (int k = 0; k < ns; ++k) order[k] = ord[k]; }
+    }
+  }
+  if (exhausted) s_flag[3] = 1;
+  // reduce over the group: smallest cost, then smallest first stop
+  for (int off = GROUP / 2; off > 0; off >>= 1) {
+    const double oc = __shfl_down_sync(gmask, best, off, GROUP);
+    const int of = __shfl_down_sync(gmask, best_first, off, GROUP);
+    int take = (oc < best || (oc == best && of < best_first)) ? 1 : 0;
+    // the winner's order travels with it
+    for (int k = 0; k < MAXS; k += 4) {
+      unsigned w = (unsigned)order[k] | ((unsigned)order[k + 1] << 8) | ((unsigned)order[k + 2] << 16) | ((unsigned)order[k + 3] << 24);
+      const unsigned ow = __shfl_down_sync(gmask, w, off, GROUP);
+      if (take) { order[k] = ow & 255; order[k + 1] = (ow >> 8) & 255; order[k + 2] = (ow >> 16) & 255; order[k + 3] = (ow >> 24) & 255; }
+    }
+    if (take) { best = oc; best_first = of; }
+  }
+  __syncwarp(gmask);
+  if (lane == 0 && active) {
+    int nso = fits ? ns : -1;                    // -1: too many stops for DRS_MAX_STOPS
+    if (s_flag[3]) { nso = -2; best = DRS_INF_ROUTE_COST; }   // -2: search budget exhausted
+    *cost_out = fits ? best : DRS_INF_ROUTE_COST;
+    *ns_out = nso;
+    for (int i = 0; i < MAXS; ++i) order_out[i] = (best < DRS_INF_ROUTE_COST && i < ns) ? order[i] : 0xff;
+  }
+}
+
+__global__ void __launch_bounds__(GROUP * TASKS_PER_BLOCK) trip_eval_kernel(TickDev tk, DistView dv, double T, int flags, int ntasks,
+                                                                            TaskList tl, double* cost_out, uint8_t* order_out,
+                                                                            int32_t* nstops_out) {
+  __shared__ Trip s_trip[TASKS_PER_BLOCK];
+  __shared__ unsigned long long s_best[TASKS_PER_BLOCK];
+  __shared__ int s_flag[TASKS_PER_BLOCK][4];
+  const int slot = threadIdx.x / GROUP, lane = threadIdx.x % GROUP;
+  const int k = blockIdx.x * TASKS_PER_BLOCK + slot;
+  const bool active = k < ntasks;
+  const unsigned gmask = 0xffu << (((threadIdx.x & 31) / GROUP) * GROUP);
+  const int kk = active ? k : 0;
+  group_solve(s_trip[slot], s_best[slot], s_flag[slot], tk, dv, T, flags, active, active ? tl.veh[kk] : -1, active ? tl.nreq[kk] : 0,
+              tl.req + (int64_t)kk * MAXR, lane, gmask, cost_out + kk, nstops_out + kk, order_out + (int64_t)kk * MAXS);
 }
 
 // status per pair + compact survivor list (warp-aggregated append)
@@ -266,30 +348,27 @@ __global__ void rv_filter_kernel(TickDev tk, DistView dv, double T, int8_t* stat
   }
 }
 
-// RV stage, second half: one thread per surviving pair
-__global__ void rv_eval_kernel(TickDev tk, DistView dv, double T, int flags, int nsurv, const int32_t* surv_veh,
-                               const int32_t* surv_req, int8_t* status, double* cost_out, uint8_t* order_out,
-                               int32_t* nstops_out) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= nsurv) return;
-  const int v = surv_veh[k], r = surv_req[k];
-  Trip tr;
-  int groups = 0;
-  uint8_t order[MAXS];
-  for (int i = 0; i < MAXS; ++i) order[i] = 0xff;
-  double cost = DRS_INF_ROUTE_COST;
-  int ns = -1;
-  int32_t one = r;
-  if (build_trip(tr, tk, dv, T, v, 1, &one, &groups)) {
-    ns = tr.ns;
-    bool exhausted = false;
-    cost = trip_solve(tr, groups, 1, flags, order, &exhausted);
-    if (exhausted) { ns = -2; cost = DRS_INF_ROUTE_COST; }
-  }
-  status[(int64_t)v * tk.n_req + r] = (int8_t)((cost < DRS_INF_ROUTE_COST) ? DRS_RV_FEASIBLE : DRS_RV_INFEASIBLE);
-  cost_out[k] = cost;
-  nstops_out[k] = ns;
-  for (int i = 0; i < MAXS; ++i) order_out[(int64_t)k * MAXS + i] = order[i];
+// RV stage, second half: one group of GROUP lanes per surviving pair
+__global__ void __launch_bounds__(GROUP * TASKS_PER_BLOCK) rv_eval_kernel(TickDev tk, DistView dv, double T, int flags, int nsurv,
+                                                                          const int32_t* surv_veh, const int32_t* surv_req,
+                                                                          int8_t* status, double* cost_out, uint8_t* order_out,
+                                                                          int32_t* nstops_out) {
+  __shared__ Trip s_trip[TASKS_PER_BLOCK];
+  __shared__ unsigned long long s_best[TASKS_PER_BLOCK];
+  __shared__ int s_flag[TASKS_PER_BLOCK][4];
+  __shared__ int32_t s_req[TASKS_PER_BLOCK];
+  const int slot = threadIdx.x / GROUP, lane = threadIdx.x % GROUP;
+  const int k = blockIdx.x * TASKS_PER_BLOCK + slot;
+  const bool active = k < nsurv;
+  const unsigned gmask = 0xffu << (((threadIdx.x & 31) / GROUP) * GROUP);
+  const int kk = active ? k : 0;
+  const int v = active ? surv_veh[kk] : -1, r = active ? surv_req[kk] : 0;
+  if (lane == 0) s_req[slot] = r;
+  __syncwarp(gmask);
+  group_solve(s_trip[slot], s_best[slot], s_flag[slot], tk, dv, T, flags, active, v, active ? 1 : 0, &s_req[slot], lane, gmask,
+              cost_out + kk, nstops_out + kk, order_out + (int64_t)kk * MAXS);
+  if (lane == 0 && active)
+    status[(int64_t)v * tk.n_req + r] = (int8_t)((cost_out[kk] < DRS_INF_ROUTE_COST) ? DRS_RV_FEASIBLE : DRS_RV_INFEASIBLE);
 }
 
 __global__ void count_status_kernel(const int8_t* status, int64_t total, unsigned long long* counters) {
@@ -470,7 +549,7 @@ extern "C" int drs_tick_rv_eval(drs_tick* t, double T, int32_t flags, int32_t* n
   DRS_CUDA(cudaMalloc((void**)&t->d_nstops, sizeof(int32_t) * std::max(nsurv, 1)));
   tm_eval.start();
   if (nsurv > 0) {
-    rv_eval_kernel<<<(nsurv + 63) / 64, 64, 0, st>>>(d, dv, T, flags, nsurv, t->d_surv_veh, t->d_surv_req, t->d_status,
+    rv_eval_kernel<<<(nsurv + TASKS_PER_BLOCK - 1) / TASKS_PER_BLOCK, GROUP * TASKS_PER_BLOCK, 0, st>>>(d, dv, T, flags, nsurv, t->d_surv_veh, t->d_surv_req, t->d_status,
                                                      t->d_cost, t->d_order, t->d_nstops);
     drs_count_launch();
   DRS_CUDA(cudaGetLastError());
@@ -564,7 +643,7 @@ extern "C" int drs_tick_trip_eval(drs_tick* t, double T, int32_t flags, int32_t 
   }
   DistView dv{t->g->d_dist, t->g->ld, t->g->mode};
   TaskList tl{dv_, dn, dr};
-  trip_eval_kernel<<<(n_tasks + 63) / 64, 64, 0, st>>>(d, dv, T, flags, n_tasks, tl, dc, dord, dns);
+  trip_eval_kernel<<<(n_tasks + TASKS_PER_BLOCK - 1) / TASKS_PER_BLOCK, GROUP * TASKS_PER_BLOCK, 0, st>>>(d, dv, T, flags, n_tasks, tl, dc, dord, dns);
   drs_count_launch();
   std::vector<int32_t> nst(n_tasks);
   cudaError_t e = cudaGetLastError();

@@ -27,13 +27,6 @@ extern "C" int drs_version(void) { return 100; }
 
 namespace {
 
-template <typename T> int dev_upload(T** dptr, const std::vector<T>& h) {
-  const size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
-  DRS_CUDA(cudaMalloc((void**)dptr, bytes));
-  if (!h.empty()) DRS_CUDA(cudaMemcpy(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
-  return DRS_OK;
-}
-
 void free_matrices(drs_graph* g) {
   if (g->owns_matrices) {
     if (g->d_dist) cudaFree(g->d_dist);
@@ -47,15 +40,12 @@ void free_matrices(drs_graph* g) {
 
 }  // namespace
 
-// (Re)builds the float weight arrays of both CSRs from h_tt.
+// (Re)builds the float weight arrays of both CSRs from h_tt (drs_graph_set_weights; creation fills them in the arena copy).
 int drs_graph_upload_weights(drs_graph* g) {
-  std::vector<int32_t> out_eid(g->narcs), in_eid(g->narcs);
-  DRS_CUDA(cudaMemcpy(out_eid.data(), g->d_out_eid, sizeof(int32_t) * g->narcs, cudaMemcpyDeviceToHost));
-  DRS_CUDA(cudaMemcpy(in_eid.data(), g->d_in_eid, sizeof(int32_t) * g->narcs, cudaMemcpyDeviceToHost));
   std::vector<float> out_w(g->narcs), in_w(g->narcs);
   for (int a = 0; a < g->narcs; ++a) {
-    out_w[a] = (float)g->h_tt[out_eid[a]];
-    in_w[a] = (float)g->h_tt[in_eid[a]];
+    out_w[a] = (float)g->h_tt[g->h_out_eid[a]];
+    in_w[a] = (float)g->h_tt[g->h_in_eid[a]];
   }
   DRS_CUDA(cudaMemcpy(g->d_out_w, out_w.data(), sizeof(float) * g->narcs, cudaMemcpyHostToDevice));
   DRS_CUDA(cudaMemcpy(g->d_in_w, in_w.data(), sizeof(float) * g->narcs, cudaMemcpyHostToDevice));
@@ -99,34 +89,50 @@ extern "C" int drs_graph_create(int32_t n, int32_t m, int32_t directed, const in
   for (const Arc& a : arcs) { out_ptr[a.u + 1]++; in_ptr[a.v + 1]++; }
   std::partial_sum(out_ptr.begin(), out_ptr.end(), out_ptr.begin());
   std::partial_sum(in_ptr.begin(), in_ptr.end(), in_ptr.begin());
-  std::vector<int32_t> out_col(g->narcs), out_eid(g->narcs), in_src(g->narcs), in_eid(g->narcs);
+  // one host image of every device array (256-byte aligned slices), one allocation, one copy
+  const size_t na = (size_t)g->narcs, me = (size_t)m, np1 = (size_t)g->npad + 1;
+  size_t off = 0;
+  auto slice = [&](size_t bytes) { const size_t o = off; off = (off + std::max<size_t>(bytes, 1) + 255) & ~(size_t)255; return o; };
+  const size_t o_tt = slice(me * 8), o_len = slice(me * 8), o_esrc = slice(me * 4), o_edst = slice(me * 4);
+  const size_t o_optr = slice(np1 * 4), o_ocol = slice(na * 4), o_oeid = slice(na * 4), o_ow = slice(na * 4);
+  const size_t o_iptr = slice(np1 * 4), o_isrc = slice(na * 4), o_ieid = slice(na * 4), o_iw = slice(na * 4);
+  std::vector<unsigned char> img(off, 0);
+  auto at = [&](size_t o) { return img.data() + o; };
+  if (m) {
+    std::memcpy(at(o_tt), tt, me * 8); std::memcpy(at(o_len), length, me * 8);
+    std::memcpy(at(o_esrc), src, me * 4); std::memcpy(at(o_edst), dst, me * 4);
+  }
+  std::memcpy(at(o_optr), out_ptr.data(), np1 * 4); std::memcpy(at(o_iptr), in_ptr.data(), np1 * 4);
+  int32_t* out_col = (int32_t*)at(o_ocol); int32_t* out_eid = (int32_t*)at(o_oeid); float* out_w = (float*)at(o_ow);
+  int32_t* in_src = (int32_t*)at(o_isrc); int32_t* in_eid = (int32_t*)at(o_ieid); float* in_w = (float*)at(o_iw);
   {
+    // arcs were generated in edge-id order, so a single pass keeps every adjacency list in edge-id order
     std::vector<int32_t> op(out_ptr.begin(), out_ptr.end() - 1), ip(in_ptr.begin(), in_ptr.end() - 1);
-    std::vector<int> order(arcs.size());
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return arcs[x].e < arcs[y].e; });
-    for (int idx : order) {
-      const Arc& a = arcs[idx];
-      out_col[op[a.u]] = a.v; out_eid[op[a.u]] = a.e; op[a.u]++;
-      in_src[ip[a.v]] = a.u; in_eid[ip[a.v]] = a.e; ip[a.v]++;
+    for (const Arc& a : arcs) {
+      const float w = (float)tt[a.e];
+      out_col[op[a.u]] = a.v; out_eid[op[a.u]] = a.e; out_w[op[a.u]] = w; op[a.u]++;
+      in_src[ip[a.v]] = a.u; in_eid[ip[a.v]] = a.e; in_w[ip[a.v]] = w; ip[a.v]++;
     }
   }
-  int rc = DRS_OK;
+  g->h_out_eid.assign(out_eid, out_eid + na);
+  g->h_in_eid.assign(in_eid, in_eid + na);
   auto fail = [&](int code) { drs_graph_destroy(g); return code; };
-  if ((rc = dev_upload(&g->d_esrc, g->h_src))) return fail(rc);
-  if ((rc = dev_upload(&g->d_edst, g->h_dst))) return fail(rc);
-  if ((rc = dev_upload(&g->d_tt64, g->h_tt))) return fail(rc);
-  if ((rc = dev_upload(&g->d_len64, g->h_len))) return fail(rc);
-  if ((rc = dev_upload(&g->d_out_ptr, out_ptr))) return fail(rc);
-  if ((rc = dev_upload(&g->d_out_col, out_col))) return fail(rc);
-  if ((rc = dev_upload(&g->d_out_eid, out_eid))) return fail(rc);
-  if ((rc = dev_upload(&g->d_in_ptr, in_ptr))) return fail(rc);
-  if ((rc = dev_upload(&g->d_in_src, in_src))) return fail(rc);
-  if ((rc = dev_upload(&g->d_in_eid, in_eid))) return fail(rc);
-  std::vector<float> wtmp(g->narcs, 0.f);
-  if ((rc = dev_upload(&g->d_out_w, wtmp))) return fail(rc);
-  if ((rc = dev_upload(&g->d_in_w, wtmp))) return fail(rc);
-  if ((rc = drs_graph_upload_weights(g))) return fail(rc);
+  if (cudaMalloc(&g->d_arena, img.size()) != cudaSuccess) {
+    cudaGetLastError();
+    drs_set_error("drs_graph_create: cudaMalloc(%zu bytes) failed", img.size());
+    return fail(DRS_ERR_NOMEM);
+  }
+  if (cudaMemcpy(g->d_arena, img.data(), img.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+    drs_set_error("drs_graph_create: host-to-device copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return fail(DRS_ERR_CUDA);
+  }
+  unsigned char* base = (unsigned char*)g->d_arena;
+  g->d_tt64 = (double*)(base + o_tt); g->d_len64 = (double*)(base + o_len);
+  g->d_esrc = (int32_t*)(base + o_esrc); g->d_edst = (int32_t*)(base + o_edst);
+  g->d_out_ptr = (int32_t*)(base + o_optr); g->d_out_col = (int32_t*)(base + o_ocol);
+  g->d_out_eid = (int32_t*)(base + o_oeid); g->d_out_w = (float*)(base + o_ow);
+  g->d_in_ptr = (int32_t*)(base + o_iptr); g->d_in_src = (int32_t*)(base + o_isrc);
+  g->d_in_eid = (int32_t*)(base + o_ieid); g->d_in_w = (float*)(base + o_iw);
   if (cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking) != cudaSuccess) {
     drs_set_error("drs_graph_create: cudaStreamCreate failed");
     return fail(DRS_ERR_CUDA);
@@ -151,10 +157,7 @@ extern "C" int drs_graph_destroy(drs_graph* g) {
   if (!g) return DRS_OK;
   DrsDeviceGuard guard(g->device);
   free_matrices(g);
-  void* ptrs[] = {g->d_esrc, g->d_edst, g->d_tt64, g->d_len64, g->d_out_ptr, g->d_out_col, g->d_out_eid,
-                  g->d_out_w, g->d_in_ptr, g->d_in_src, g->d_in_eid, g->d_in_w};
-  for (void* p : ptrs)
-    if (p) cudaFree(p);
+  if (g->d_arena) cudaFree(g->d_arena);
   if (g->sssp_queues) cudaFree(g->sssp_queues);
   if (g->sssp_arcs) cudaFree(g->sssp_arcs);
   if (g->sssp_sources) cudaFree(g->sssp_sources);
@@ -198,20 +201,20 @@ extern "C" int drs_apsp_build(drs_graph* g, int32_t mode) {
   int rc;
   const int nb = g->npad / DRS_FW_TILE;
   cudaStream_t st = g->stream;
-  // events: [0] start, [1] after init, then per round (after pivot row, after update), last after pred
-  std::vector<cudaEvent_t> ev(3 + 2 * nb);
+  int algo = g->algorithm;
+  if (algo == DRS_APSP_AUTO) algo = (g->narcs <= 16 * (int64_t)g->n) ? DRS_APSP_SSSP : DRS_APSP_FW;
+  // events: [0] start, [1] after init, then per round (after pivot row, after update), last after pred;
+  // the SSSP build is one "round" booked under "update"
+  const int ner = (algo == DRS_APSP_SSSP) ? 1 : nb;
+  std::vector<cudaEvent_t> ev(3 + 2 * ner);
   for (auto& e : ev) DRS_CUDA(cudaEventCreate(&e));
   auto release = [&]() { for (auto& e : ev) cudaEventDestroy(e); };
   DRS_CUDA(cudaEventRecord(ev[0], st));
-  int algo = g->algorithm;
-  if (algo == DRS_APSP_AUTO) algo = (g->narcs <= 16 * (int64_t)g->n) ? DRS_APSP_SSSP : DRS_APSP_FW;
   if (algo == DRS_APSP_SSSP) {
     DRS_CUDA(cudaEventRecord(ev[1], st));
+    DRS_CUDA(cudaEventRecord(ev[2], st));
     if ((rc = drs_apsp_rows_sssp(g, mode, g->d_dist, ld, 0, g->npad, 0.0, st))) { release(); return rc; }
-    for (int kb = 0; kb < nb; ++kb) {   // keep the event layout: everything is booked under "update"
-      DRS_CUDA(cudaEventRecord(ev[2 + 2 * kb], st));
-      DRS_CUDA(cudaEventRecord(ev[3 + 2 * kb], st));
-    }
+    DRS_CUDA(cudaEventRecord(ev[3], st));
   } else {
   if ((rc = drs_fw_init(g, mode, g->d_dist, ld, 0, g->npad, st))) { release(); return rc; }
   DRS_CUDA(cudaEventRecord(ev[1], st));
@@ -224,17 +227,16 @@ extern "C" int drs_apsp_build(drs_graph* g, int32_t mode) {
   }
   }
   if (g->d_pred && (rc = drs_pred_build(g, mode, g->d_dist, ld, 0, g->npad, g->d_pred, st))) { release(); return rc; }
-  DRS_CUDA(cudaEventRecord(ev[2 + 2 * nb], st));
+  DRS_CUDA(cudaEventRecord(ev[2 + 2 * ner], st));
   DRS_CUDA(cudaStreamSynchronize(st));
   float ms = 0;
   g->prof_ms[0] = g->prof_ms[1] = g->prof_ms[2] = g->prof_ms[3] = 0;
   cudaEventElapsedTime(&ms, ev[0], ev[1]); g->prof_ms[0] = ms;
-  if (algo == DRS_APSP_SSSP) { cudaEventElapsedTime(&ms, ev[1], ev[2]); g->prof_ms[2] = ms; }
-  else for (int kb = 0; kb < nb; ++kb) {
+  for (int kb = 0; kb < ner; ++kb) {
     cudaEventElapsedTime(&ms, ev[1 + 2 * kb], ev[2 + 2 * kb]); g->prof_ms[1] += ms;
     cudaEventElapsedTime(&ms, ev[2 + 2 * kb], ev[3 + 2 * kb]); g->prof_ms[2] += ms;
   }
-  cudaEventElapsedTime(&ms, ev[1 + 2 * nb], ev[2 + 2 * nb]); g->prof_ms[3] = ms;
+  cudaEventElapsedTime(&ms, ev[1 + 2 * ner], ev[2 + 2 * ner]); g->prof_ms[3] = ms;
   g->prof_rounds = nb;
   release();
   g->apsp_valid = true;

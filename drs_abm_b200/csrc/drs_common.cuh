@@ -40,6 +40,12 @@ struct drs_graph {
   std::vector<int32_t> h_src, h_dst;
   std::vector<double> h_tt, h_len;
 
+  // host copies of the arc -> edge id maps of both CSRs (weight refresh without a device round trip)
+  std::vector<int32_t> h_out_eid, h_in_eid;
+
+  // every array below is a slice of ONE device allocation (d_arena), filled by ONE host-to-device copy
+  void* d_arena = nullptr;
+
   // per-edge attributes on device, indexed by edge id
   int32_t* d_esrc = nullptr;
   int32_t* d_edst = nullptr;
