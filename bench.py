@@ -31,6 +31,13 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (C3 map, one
+# B200, f32); reported as roofline.traffic only for the configuration the capture was taken on
+NCU_TRAFFIC = {
+    "sssp_batch_kernel": (10.41e9 + 25.70e9, "profiles/r01_sssp_ncu_full_final2.txt"),
+    "insertion_scan_kernel": (0.553e9 + 0.426e9, "profiles/r01_ins_ncu_full_final.txt"),
+}
+
 WORKLOADS = {
     "C1": "C1: synthetic 20x20 grid GML (400 nodes, integer ttmedian 20..60 s)",
     "C2": "C2: synthetic 5k-node city GML (71x71 grid, keep 0.92, seed 5000)",
@@ -190,7 +197,9 @@ def insertion_section(G, data, config, peaks, cpu_seconds=8.0):
         "candidates_per_tick": int(ncand), "pairs_per_tick": int(n_veh) * int(n_new), "assigned": int((bv >= 0).sum()),
         "ms_scan_kernel": t_scan * 1e3, "ms_fold_kernel": t_fold * 1e3,
         "roofline": {"bound": "hbm", "achieved": pair_bytes / t_scan / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": pair_bytes / t_scan / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                     "frac": pair_bytes / t_scan / 1e9 / peaks["hbm_gbs"],
+                     "traffic": NCU_TRAFFIC["insertion_scan_kernel"][0] if config == "C3" else None,
+                     "traffic_source": NCU_TRAFFIC["insertion_scan_kernel"][1],
                      "kernel": "insertion_scan_kernel", "algorithmic_bytes_per_launch": pair_bytes},
         "e2e": {"value": ncand / e2e, "unit": "candidates/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(n_new) * 20}}
@@ -665,7 +674,9 @@ def main():
 
         def sssp_roofline(t_gpu_seconds):
             return {"bound": "hbm", "achieved": sssp_bytes / t_gpu_seconds / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": sssp_bytes / t_gpu_seconds / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                    "frac": sssp_bytes / t_gpu_seconds / 1e9 / peaks["hbm_gbs"],
+                    "traffic": NCU_TRAFFIC["sssp_batch_kernel"][0] if (args.config == "C3" and world == 1 and args.mode == "f32") else None,
+                    "traffic_source": NCU_TRAFFIC["sssp_batch_kernel"][1],
                     "kernel": "sssp_batch_kernel", "algorithmic_bytes_per_launch": sssp_bytes,
                     "note": "(16 E_dir + 8 N) bytes per source; the working set (one row + the CSR per CTA) is L2 resident, "
                             "so the kernel is bound by dependent L2 round trips per bucket, not by HBM bandwidth"}
