@@ -13,14 +13,17 @@
 //                      reachability pre-filter (lib/Optimization.py:183-186) and the
 //                      empty-dummy-vehicle check (:193-202); survivors are appended
 //                      to a compact task list (warp-aggregated atomic).
-//   rv_eval_kernel     eight lanes per surviving pair: findOptimalRouting of the
-//                      request inserted into the vehicle's plan.
-//   trip_eval_kernel   eight lanes per explicit trip (RR edges, RTV trips): gathers the
+//   rv_eval_kernel     findOptimalRouting of each surviving request inserted into the
+//                      vehicle's plan: 8 trips per CTA in shared memory, the searches
+//                      (pairwise pre-checks, then exact searches split by the first 1-3
+//                      stops) pulled by the 128 lanes from a CTA-wide work list.
+//   trip_eval_kernel   the same for explicit trips (RR edges, RTV trips): gathers the
 //                      (S+1)^2 travel times among the trip's vertices, runs the pairwise
 //                      pre-checks (lib/optimUtils.py:127-156) and a depth-first
 //                      enumeration of the precedence-respecting orderings in
 //                      lexicographic order with exact feasibility / cost-bound pruning.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -32,23 +35,27 @@ namespace {
 constexpr int MAXS = DRS_MAX_STOPS;
 constexpr int MAXR = DRS_MAX_TRIP_REQS;
 
-// One evaluation problem in thread-local storage.  Vertex 0 of `tt` is the start.
+// One evaluation problem ("trip": the stops of a vehicle's plan plus up to four new requests) in shared
+// memory.  Vertex 0 of `tt` is the start.
 struct Trip {
-  int ns;                 // stops
-  int has_start;          // 1: vertex 0 is the vehicle's next node; 0: route starts at its first stop
+  double lb[MAXS], ub[MAXS];
   double t_start;         // T + veh["t"]  (or T without a vehicle)
   double cap;             // capacity (1e6 when unconstrained, lib/optimUtils.py:432)
-  int pax0;               // passengers on board at the start
+  int tt[(MAXS + 1) * (MAXS + 1)];   // raw matrix entries (float bits or int32) among the trip's vertices
   int node[MAXS + 1];
-  double lb[MAXS], ub[MAXS];
+  unsigned short dropmask[MAXS];     // bit j of dropmask[i]: stop j is the drop-off whose pick-up is stop i
   int8_t pod[MAXS], prev[MAXS];
   uint8_t group[MAXS];    // request group of each stop (for the pairwise pre-checks)
-  unsigned dropmask[MAXS];// bit j set in dropmask[i]: stop j is the drop-off whose pick-up is stop i
-  double tt[(MAXS + 1) * (MAXS + 1)];   // travel times among the trip's vertices (matrix entries, exact)
+  int ns;                 // stops
+  int has_start;          // 1: vertex 0 is the vehicle's next node; 0: route starts at its first stop
+  int pax0;               // passengers on board at the start
+  int groups, nreq;       // distinct requests; the first nreq groups are the new ones
+  int fits;               // 0: more than DRS_MAX_STOPS stops (or an inactive slot)
 };
 
-__device__ __forceinline__ double trip_tt(const Trip& tr, int a, int b) {
-  return tr.tt[a * (MAXS + 1) + b];
+__device__ __forceinline__ double decode_tt(int raw, int mode) {
+  if (mode == DRS_MODE_F32) return (double)__int_as_float(raw);
+  return raw >= DRS_I32_INF ? __longlong_as_double(0x7ff0000000000000LL) : (double)raw;
 }
 
 // Depth-first enumeration over the stops in `subset` (bit mask).  Mirrors
@@ -58,244 +65,391 @@ __device__ __forceinline__ double trip_tt(const Trip& tr, int a, int b) {
 //   cost      = sum over drop-offs of (arrival - lb)                    (:549-550)
 // Orderings are visited in lexicographic stop-index order and only a strictly
 // smaller cost replaces the incumbent (:447), i.e. the canonical tie rule.
-// first_only: return as soon as one feasible complete ordering is found.
 // The enumeration is exact and therefore exponential in the number of stops (as in the reference); a
 // budget on visited search nodes turns a hopeless instance into an error instead of a kernel that runs
-// for hours (*exhausted is set; the host reports it).
-constexpr long long kSearchBudget = 20000000LL;   // ~20x the largest instance of a K=4 fleet (10 stops: 113 400 orderings)
+// for hours (`exhausted` is set; the host reports it).
+constexpr int kSearchBudget = 20000000;   // steps per trip and work list; ~20x the largest instance of a K=4 fleet (10 stops: 113 400 orderings)
+constexpr int kChargeEvery = 256;         // a search charges its trip's step counter every so many steps
 
-//
-// forced_first >= 0 restricts the first position to that stop (the lanes of a task split the search by first
-// stop); shared_best (may be null) is the task's incumbent cost as unsigned-long-long bits, shared by its lanes:
-// a partial ordering is dropped only when it is STRICTLY worse than the shared incumbent, so an equal-cost
-// ordering with a lexicographically smaller first stop is still found by its own lane.
-//
-// The loop is flat -- one candidate stop (or one backtrack) per iteration, the next admissible stop found with
-// bit masks (`unlocked` = stops whose pick-up precedes them or is outside the subset) -- so the lanes of a warp,
-// each on its own search, stay converged at the loop head.  The ordering in progress is packed 4 bits per depth.
-__device__ double trip_dfs(const Trip& tr, unsigned subset, double cap, int pax0, bool first_only,
-                           uint8_t* best_order, bool* exhausted, int forced_first = -1,
-                           unsigned long long* shared_best = nullptr) {
-  const int total = __popc(subset);
-  long long visited = 0;
-  double best = DRS_INF_ROUTE_COST;
-  double psum[MAXS + 1], cost[MAXS + 1];
-  unsigned long long ord = 0;
-  unsigned used = 0, unlocked = 0;
-  for (int i = 0; i < tr.ns; ++i) {
-    const int pv = tr.prev[i];
+// The search is a resumable state machine: dfs_step tries ONE candidate stop (or backtracks once).  Every lane of
+// a CTA runs its own searches, pulled from a CTA-wide work list, inside one flat loop -- so lanes whose searches
+// differ in length by orders of magnitude stay converged at the loop head and none waits for another.
+//   pmask[0..2] restrict the first three positions (the searches of a trip are split by its first stops)
+//   shared_best the trip's incumbent cost (fp64 bits; costs are >= 0 so the bit patterns order like the values),
+//               shared by its searches: a partial ordering is dropped only when STRICTLY worse, so equal-cost
+//               orderings in other sub-trees are still found
+//   first_only  stop at the first complete feasible ordering
+// The next admissible stop comes from bit masks (`unlocked` = stops whose pick-up precedes them or is outside
+// the subset); the ordering in progress is packed 4 bits per position, FIRST position in the most significant
+// nibble, so that comparing two packed orderings of a trip as integers compares them lexicographically.
+struct Dfs {   // scalars only, so that it lives in registers; the per-depth sums are separate local arrays
+  double best, cap;
+  unsigned long long ord, best_ord;
+  unsigned long long* shared_best;
+  int* steps;             // the trip's step counter (shared by its searches), charged every kChargeEvery steps
+  const Trip* tr;
+  unsigned subset, used, unlocked, pmask0, pmask1, pmask2;
+  int total, d, pax, start, visited;
+  bool first_only, done, exhausted;
+};
+
+struct DfsStack {
+  double psum[MAXS + 1], cost[MAXS + 1];   // partial travel-time sum and cost at each depth
+};
+
+__device__ __forceinline__ int ord_at(unsigned long long ord, int pos) { return (int)((ord >> (4 * (15 - pos))) & 15ull); }
+
+__device__ __forceinline__ void dfs_begin(Dfs& s, DfsStack& k, const Trip* tr, unsigned subset, double cap, int pax0, bool first_only,
+                                          const unsigned* pmask, unsigned long long* shared_best, int* steps) {
+  s.steps = steps;
+  s.tr = tr; s.subset = subset; s.cap = cap; s.pax = pax0; s.first_only = first_only;
+  s.pmask0 = pmask ? pmask[0] : 0xffffffffu; s.pmask1 = pmask ? pmask[1] : 0xffffffffu; s.pmask2 = pmask ? pmask[2] : 0xffffffffu;
+  s.shared_best = shared_best;
+  s.total = __popc(subset);
+  s.best = DRS_INF_ROUTE_COST; s.ord = 0; s.best_ord = 0; s.used = 0; s.d = 0; s.start = 0; s.visited = 0;
+  s.done = (s.total == 0); s.exhausted = false;
+  unsigned unlocked = 0;
+  for (int i = 0; i < tr->ns; ++i) {
+    const int pv = tr->prev[i];
     if (pv < 0 || !((subset >> pv) & 1u)) unlocked |= 1u << i;
   }
-  const unsigned first_mask = forced_first >= 0 ? (1u << forced_first) : 0xffffffffu;
-  int d = 0, pax = pax0, start = 0;
-  psum[0] = 0.0; cost[0] = 0.0;
-  while (true) {
-    if (++visited > kSearchBudget) { *exhausted = true; break; }
-    unsigned candm = subset & ~used & unlocked & (0xffffffffu << start);
-    if (d == 0) candm &= first_mask;
-    if (!candm) {   // no stop left at this depth: backtrack
-      if (d == 0) break;
-      --d;
-      const int j = (int)((ord >> (4 * d)) & 15ull);
-      used &= ~(1u << j);
-      unlocked &= ~tr.dropmask[j];
-      if (d > 0 || tr.has_start) pax -= tr.pod[j];
-      start = j + 1;
-      continue;
-    }
-    const int i = __ffs(candm) - 1;   // orderings in lexicographic stop-index order
-    start = i + 1;
-    double np, nc;
-    int npax;
-    if (d == 0 && !tr.has_start) {
-      // no vehicle: the first stop is the start; never capacity-counted nor window-checked
-      // (lib/optimUtils.py:475-488,540 iterate over orderedLocs[1:])
-      np = 0.0; nc = 0.0; npax = pax;
-    } else {
-      npax = pax + tr.pod[i];
-      if ((double)npax > cap) continue;
-      const int cur = d == 0 ? 0 : (int)((ord >> (4 * (d - 1))) & 15ull) + 1;
-      np = psum[d] + trip_tt(tr, cur, i + 1);
-      const double arr = tr.t_start + np;
-      if (!(arr >= tr.lb[i] && arr <= tr.ub[i])) continue;
-      nc = cost[d];
-      if (tr.pod[i] < 0) nc += arr - tr.lb[i];
-      if (!(nc < best)) continue;   // cost is non-decreasing along an ordering: exact pruning
-      if (shared_best && nc > __longlong_as_double((long long)*((volatile unsigned long long*)shared_best))) continue;
-    }
-    ord = (ord & ~(15ull << (4 * d))) | ((unsigned long long)i << (4 * d));
-    if (d + 1 == total) {   // complete ordering, strictly cheaper than the incumbent
-      best = nc;
-      if (shared_best) atomicMin(shared_best, (unsigned long long)__double_as_longlong(nc));   // costs are >= 0
-      if (best_order)
-        for (int k = 0; k < total; ++k) best_order[k] = (uint8_t)((ord >> (4 * k)) & 15ull);
-      if (first_only) return best;
-      continue;
-    }
-    used |= 1u << i;
-    unlocked |= tr.dropmask[i];
-    pax = npax;
-    ++d;
-    psum[d] = np; cost[d] = nc;
-    start = 0;
+  s.unlocked = unlocked;
+  k.psum[0] = 0.0; k.cost[0] = 0.0;
+}
+
+__device__ __forceinline__ void dfs_step(Dfs& s, DfsStack& k, int mode) {
+  const Trip& tr = *s.tr;
+  if ((++s.visited & (kChargeEvery - 1)) == 0 && atomicAdd(s.steps, kChargeEvery) > kSearchBudget) {
+    s.exhausted = true; s.done = true;
+    return;
   }
-  return best;
+  const int d = s.d;
+  unsigned candm = s.subset & ~s.used & s.unlocked & (0xffffffffu << s.start);
+  if (d < 3) candm &= (d == 0 ? s.pmask0 : d == 1 ? s.pmask1 : s.pmask2);
+  if (!candm) {   // no stop left at this depth: backtrack
+    if (d == 0) { s.done = true; return; }
+    const int j = ord_at(s.ord, d - 1);
+    s.d = d - 1;
+    s.used &= ~(1u << j);
+    s.unlocked &= ~(unsigned)tr.dropmask[j];
+    if (d - 1 > 0 || tr.has_start) s.pax -= tr.pod[j];
+    s.start = j + 1;
+    return;
+  }
+  const int i = __ffs(candm) - 1;   // orderings in lexicographic stop-index order
+  s.start = i + 1;
+  double np, nc;
+  int npax;
+  if (d == 0 && !tr.has_start) {
+    // no vehicle: the first stop is the start; never capacity-counted nor window-checked
+    // (lib/optimUtils.py:475-488,540 iterate over orderedLocs[1:])
+    np = 0.0; nc = 0.0; npax = s.pax;
+  } else {
+    npax = s.pax + tr.pod[i];
+    if ((double)npax > s.cap) return;
+    const int cur = d == 0 ? 0 : ord_at(s.ord, d - 1) + 1;
+    np = k.psum[d] + decode_tt(tr.tt[cur * (MAXS + 1) + i + 1], mode);
+    const double arr = tr.t_start + np;
+    if (!(arr >= tr.lb[i] && arr <= tr.ub[i])) return;
+    nc = k.cost[d];
+    if (tr.pod[i] < 0) nc += arr - tr.lb[i];
+    if (!(nc < s.best)) return;   // cost is non-decreasing along an ordering: exact pruning
+    if (s.shared_best && nc > __longlong_as_double((long long)*((volatile unsigned long long*)s.shared_best))) return;
+  }
+  const int sh4 = 4 * (15 - d);
+  s.ord = (s.ord & ~(15ull << sh4)) | ((unsigned long long)i << sh4);
+  if (d + 1 == s.total) {   // complete ordering, strictly cheaper than this search's incumbent
+    s.best = nc;
+    s.best_ord = s.ord;
+    if (s.shared_best) atomicMin(s.shared_best, (unsigned long long)__double_as_longlong(nc));
+    if (s.first_only) s.done = true;
+    return;
+  }
+  s.used |= 1u << i;
+  s.unlocked |= (unsigned)tr.dropmask[i];
+  s.pax = npax;
+  s.d = d + 1;
+  k.psum[d + 1] = np; k.cost[d + 1] = nc;
+  s.start = 0;
 }
 
 struct TaskList {
-  int32_t* veh;     // vehicle index or -1
-  int32_t* nreq;
-  int32_t* req;     // MAXR per task
+  const int32_t* veh;     // vehicle index or -1
+  const int32_t* nreq;    // null: one request per task
+  const int32_t* req;     // MAXR per task (stride 1 when nreq is null)
 };
 
-constexpr int GROUP = 8;                 // lanes cooperating on one task
-constexpr int TASKS_PER_BLOCK = 8;       // 64 threads per block
-
-// Stop records of a task (lane 0 of the group) -- createLocations order (lib/optimUtils.py:84-110).
-__device__ bool fill_trip(Trip& tr, const TickDev& tk, double T, int v, int nreq, const int32_t* reqs, int* n_groups) {
-  int ns = 0;
-  for (int i = 0; i < MAXS; ++i) tr.dropmask[i] = 0;
-  for (int k = 0; k < nreq; ++k) {   // new requests first (:86-92)
-    const int r = reqs[k];
-    tr.node[1 + ns] = tk.r_o[r]; tr.lb[ns] = tk.r_lbp[r]; tr.ub[ns] = tk.r_ubp[r]; tr.pod[ns] = 1;
-    tr.prev[ns] = -1; tr.group[ns] = k; ++ns;
-    tr.node[1 + ns] = tk.r_d[r]; tr.lb[ns] = tk.r_lbd[r]; tr.ub[ns] = tk.r_ubd[r]; tr.pod[ns] = -1;
-    tr.prev[ns] = (int8_t)(ns - 1); tr.group[ns] = k; tr.dropmask[ns - 1] = 1u << ns; ++ns;
-  }
-  int groups = nreq;
-  if (v >= 0) {
-    const int s0 = tk.v_off[v], s1 = tk.v_off[v + 1];
-    if (ns + (s1 - s0) > MAXS) return false;
-    const int base = ns;
-    for (int s = s0; s < s1; ++s) {
-      tr.node[1 + ns] = tk.s_node[s]; tr.lb[ns] = tk.s_lb[s]; tr.ub[ns] = tk.s_ub[s]; tr.pod[ns] = tk.s_pod[s];
-      const int pv = tk.s_prev[s];
-      tr.prev[ns] = (int8_t)(pv < 0 ? -1 : base + pv);
-      tr.group[ns] = (uint8_t)(pv < 0 ? groups++ : tr.group[base + pv]);
-      if (pv >= 0) tr.dropmask[base + pv] = 1u << ns;
-      ++ns;
+// Stop records of a task -- createLocations order (lib/optimUtils.py:84-110): the new requests first (:86-92),
+// then the vehicle's planned stops.  The `lanes` lanes of the trip load one stop each (the loads of a serial loop
+// would each wait for the previous one's store); number_groups then numbers the request groups in stop order.
+__device__ void fill_trip(Trip& tr, const TickDev& tk, double T, int v, int nreq, const int32_t* reqs, int sub, int lanes) {
+  const int s0 = v >= 0 ? tk.v_off[v] : 0, s1 = v >= 0 ? tk.v_off[v + 1] : 0;
+  const int base = 2 * nreq, ns = base + (s1 - s0);
+  const bool fits = ns <= MAXS;
+  if (sub == 0) {
+    tr.nreq = nreq;
+    tr.fits = fits ? 1 : 0;
+    tr.ns = fits ? ns : 0;
+    if (v >= 0) {
+      tr.has_start = 1;
+      tr.node[0] = tk.v_node[v];
+      tr.t_start = T + tk.v_delay[v];           // lib/optimUtils.py:117
+      tr.cap = (double)tk.v_cap[v];
+      tr.pax0 = tk.v_pax[v];
+    } else {
+      tr.has_start = 0;
+      tr.node[0] = tk.r_o[reqs[0]];             // the first stop is the start (lib/optimUtils.py:160)
+      tr.t_start = T;
+      tr.cap = 1e6;
+      tr.pax0 = 0;
     }
-    tr.has_start = 1;
-    tr.node[0] = tk.v_node[v];
-    tr.t_start = T + tk.v_delay[v];           // lib/optimUtils.py:117
-    tr.cap = (double)tk.v_cap[v];
-    tr.pax0 = tk.v_pax[v];
-  } else {
-    tr.has_start = 0;
-    tr.node[0] = tr.node[1];
-    tr.t_start = T;                            // lib/optimUtils.py:160
-    tr.cap = 1e6;
-    tr.pax0 = 0;
   }
-  tr.ns = ns;
-  *n_groups = groups;
+  if (!fits) return;
+  for (int q = sub; q < nreq; q += lanes) {
+    const int r = reqs[q], i = 2 * q;
+    tr.node[1 + i] = tk.r_o[r]; tr.lb[i] = tk.r_lbp[r]; tr.ub[i] = tk.r_ubp[r]; tr.pod[i] = 1; tr.prev[i] = -1;
+    tr.node[2 + i] = tk.r_d[r]; tr.lb[i + 1] = tk.r_lbd[r]; tr.ub[i + 1] = tk.r_ubd[r]; tr.pod[i + 1] = -1; tr.prev[i + 1] = (int8_t)i;
+  }
+  for (int q = sub; q < s1 - s0; q += lanes) {
+    const int s = s0 + q, i = base + q;
+    tr.node[1 + i] = tk.s_node[s]; tr.lb[i] = tk.s_lb[s]; tr.ub[i] = tk.s_ub[s]; tr.pod[i] = tk.s_pod[s];
+    const int pv = tk.s_prev[s];
+    tr.prev[i] = (int8_t)(pv < 0 ? -1 : base + pv);
+  }
+}
+
+// Request group of each stop (new request k = group k; planned stops in order of first appearance) and the
+// pick-up -> drop-off masks; one lane, shared memory only.
+__device__ void number_groups(Trip& tr) {
+  int groups = tr.nreq;
+  for (int i = 0; i < MAXS; ++i) tr.dropmask[i] = 0;
+  for (int i = 0; i < tr.ns; ++i) {
+    const int pv = tr.prev[i];
+    if (i < 2 * tr.nreq) tr.group[i] = (uint8_t)(i >> 1);
+    else tr.group[i] = (uint8_t)(pv < 0 ? groups++ : tr.group[pv]);
+    if (pv >= 0) tr.dropmask[pv] = (unsigned short)(1u << i);
+  }
+  tr.groups = tr.fits ? groups : 0;
+}
+
+// Pairs of request groups findOptimalRouting pre-checks (lib/optimUtils.py:127-156): every pair that is not
+// already on the vehicle together, when there are at least three groups and a vehicle.
+__device__ __forceinline__ int pair_count(const Trip& tr, int flags) {
+  if (!tr.fits || !(flags & DRS_EVAL_PAIRWISE_CHECKS) || !tr.has_start || tr.groups < 3) return 0;
+  const int g = tr.groups, old = g - tr.nreq;
+  return g * (g - 1) / 2 - old * (old - 1) / 2;
+}
+
+// A trip's searches are split by its first `depth` stops (1..3).  Search k of a trip stands for the prefix whose
+// stops are the digits of k in base ns (most significant first), so k order is lexicographic order; prefixes that
+// repeat a stop or place a drop-off before its pick-up are empty searches.  Returns false for those, else the
+// one-bit masks of the first `depth` positions (all-ones beyond) and the packed key (like Dfs::ord).
+__device__ __forceinline__ int prefix_count(const Trip& tr, int depth) {
+  return depth == 1 ? tr.ns : depth == 2 ? tr.ns * tr.ns : tr.ns * tr.ns * tr.ns;
+}
+
+__device__ __forceinline__ bool prefix_masks(const Trip& tr, int depth, int k, unsigned* pmask, unsigned long long* key) {
+  pmask[0] = pmask[1] = pmask[2] = 0xffffffffu;
+  int digit[3];
+  for (int p = depth - 1; p >= 0; --p) { digit[p] = k % tr.ns; k /= tr.ns; }
+  unsigned used = 0;
+  unsigned long long kk = 0;
+  for (int p = 0; p < depth; ++p) {
+    const int f = digit[p], pv = tr.prev[f];
+    if (((used >> f) & 1u) || (pv >= 0 && !((used >> pv) & 1u))) return false;
+    used |= 1u << f;
+    pmask[p] = 1u << f;
+    kk |= (unsigned long long)f << (4 * (15 - p));
+  }
+  *key = kk;
   return true;
 }
 
-// findOptimalRouting (lib/optimUtils.py:113-160) for one task by a group of GROUP lanes: the trip lives in
-// shared memory; the lanes gather the (S+1) x S travel times together, split the pairwise pre-checks by pair and
-// the final enumeration by first stop, share the incumbent cost, and lane 0 writes the result.  The winner among
-// equal costs is the lane with the smallest first stop = the lexicographically smallest ordering (each lane visits
-// its own orderings in lexicographic order and keeps the first minimum).
-__device__ void group_solve(Trip& tr, unsigned long long& shared_best, int* s_flag, const TickDev& tk, const DistView& dv,
-                            double T, int flags, bool active, int v, int nreq, const int32_t* reqs, int lane, unsigned gmask,
-                            double* cost_out, int* ns_out, uint8_t* order_out) {
-  // s_flag[0]: trip fits, [1]: groups, [2]: a pairwise check failed, [3]: budget exhausted
-  if (lane == 0) {
-    int groups = 0;
-    const bool ok = active && fill_trip(tr, tk, T, v, nreq, reqs, &groups);
-    s_flag[0] = ok ? 1 : 0; s_flag[1] = groups; s_flag[2] = 0; s_flag[3] = 0;
-    shared_best = (unsigned long long)__double_as_longlong(DRS_INF_ROUTE_COST);
-  }
-  __syncwarp(gmask);
-  const bool fits = s_flag[0] != 0;
-  const int ns = fits ? tr.ns : 0, groups = s_flag[1];
-  for (int idx = lane; idx < (ns + 1) * ns; idx += GROUP) {   // travel times among the trip's vertices
-    const int a = idx / ns, b = idx % ns + 1;
-    tr.tt[a * (MAXS + 1) + b] = (tr.node[a] == tr.node[b]) ? 0.0 : dv.at(tr.node[a], tr.node[b]);
-  }
-  __syncwarp(gmask);
-  bool exhausted = false;
-  // Work is dealt to the lanes so that all of them enter trip_dfs at the same point of the program (a lane that
-  // called it from inside a divergent branch would run alone while the others wait).
-  if (fits && (flags & DRS_EVAL_PAIRWISE_CHECKS) && tr.has_start && groups >= 3) {
-    int npairs = 0;
-    for (int a = 0; a < groups; ++a)
-      for (int b = a + 1; b < groups; ++b)
-        if (!(a >= nreq && b >= nreq)) ++npairs;   // both already on the vehicle: skipped (:142-143)
-    for (int p0 = 0; p0 < npairs; p0 += GROUP) {
-      const int mine = p0 + lane;
-      int pa = -1, pb = -1, pidx = 0;
-      for (int a = 0; a < groups; ++a)
-        for (int b = a + 1; b < groups; ++b) {
-          if (a >= nreq && b >= nreq) continue;
-          if (pidx++ == mine) { pa = a; pb = b; }
+// findOptimalRouting (lib/optimUtils.py:113-160) for TASKS trips per CTA of THREADS lanes.
+//   1. the trips are laid out in shared memory (the lanes of a trip load one stop each) and all lanes gather the
+//      travel times;
+//   2. work list A = the pairwise pre-checks of all trips (one search each, first feasible ordering wins);
+//   3. work list B = for the trips that passed, one exact search per admissible prefix of 1, 2 or 3 stops (longer
+//      trips are split deeper: their sub-trees are the long tail of the launch), sharing the trip's incumbent:
+//      the minimum cost;
+//   4. work list C = the same searches again with the minimum as the bound, each stopping at its first complete
+//      ordering (which attains the minimum, and is the lexicographically smallest that does in its sub-tree);
+//      a 64-bit atomicMin over the packed orderings leaves the lexicographically smallest optimal ordering of the
+//      trip = the canonical tie rule.  Searches whose prefix is already beaten are skipped.
+// Lanes pull searches from the work lists with a shared-memory counter.
+template <int TASKS, int THREADS>
+struct EvalShared {
+  Trip trip[TASKS];
+  unsigned long long best[TASKS];      // minimum cost (fp64 bits)
+  unsigned long long win_ord[TASKS];   // smallest packed ordering attaining it
+  int off[TASKS + 1];
+  int count[TASKS], depth[TASKS];
+  int fail[TASKS], exhausted[TASKS], steps[TASKS];
+  int next;
+};
+
+constexpr unsigned long long kNoOrder = ~0ull;
+
+template <int TASKS, int THREADS>
+__device__ void run_searches(EvalShared<TASKS, THREADS>& sh, int phase, int mode) {
+  const int nitems = sh.off[TASKS];
+  Dfs st;
+  DfsStack stk;
+  st.done = true; st.exhausted = false; st.best = DRS_INF_ROUTE_COST; st.best_ord = 0;
+  int item = -1, task = 0;
+  while (true) {
+    if (st.done) {
+      if (item >= 0) {   // retire the finished search
+        if (st.exhausted) sh.exhausted[task] = 1;
+        else if (phase == 0) { if (!(st.best < DRS_INF_ROUTE_COST)) sh.fail[task] = 1; }
+        else if (phase == 2) { if (st.best < DRS_INF_ROUTE_COST) atomicMin(&sh.win_ord[task], st.best_ord); }
+      }
+      item = atomicAdd(&sh.next, 1);
+      if (item >= nitems) break;
+      int lo = 0, hi = TASKS;   // task = last t with off[t] <= item
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sh.off[mid] <= item) lo = mid; else hi = mid; }
+      task = lo;
+      const Trip& tr = sh.trip[task];
+      const int k = item - sh.off[task];
+      if (sh.exhausted[task]) { item = -1; continue; }   // the trip is over budget: its result is an error anyway
+      if (phase == 0) {
+        if (sh.fail[task]) { item = -1; continue; }   // already infeasible: skip
+        int pa = -1, pb = -1, pidx = 0;
+        for (int a = 0; a < tr.groups; ++a)
+          for (int b = a + 1; b < tr.groups; ++b) {
+            if (a >= tr.nreq && b >= tr.nreq) continue;   // both already on the vehicle (:142-143)
+            if (pidx++ == k) { pa = a; pb = b; }
+          }
+        unsigned sub = 0;
+        for (int i = 0; i < tr.ns; ++i)
+          if (tr.group[i] == pa || tr.group[i] == pb) sub |= 1u << i;
+        // minimalDelayPath(comboLocs, G, startTime, startLoc): default capacity 1e6, startPax 0 (:148-149)
+        dfs_begin(st, stk, &tr, sub, 1e6, 0, true, nullptr, nullptr, &sh.steps[task]);
+      } else {
+        unsigned pm[3];
+        unsigned long long key;
+        const int dep = sh.depth[task];
+        if (!prefix_masks(tr, dep, k, pm, &key)) { item = -1; continue; }
+        if (phase == 2) {
+          // a smaller ordering is already known: this sub-tree cannot win
+          const int shift = 64 - 4 * dep;
+          const unsigned long long w = *((volatile unsigned long long*)&sh.win_ord[task]);
+          if ((w >> shift) < (key >> shift)) { item = -1; continue; }
         }
-      unsigned sub = 0;
-      for (int i = 0; i < ns; ++i)
-        if (tr.group[i] == pa || tr.group[i] == pb) sub |= 1u << i;
-      // minimalDelayPath(comboLocs, G, startTime, startLoc): default capacity 1e6, startPax 0 (:148-149)
-      const double c = sub ? trip_dfs(tr, sub, 1e6, 0, true, nullptr, &exhausted) : 0.0;
-      if (!(c < DRS_INF_ROUTE_COST)) s_flag[2] = 1;
+        dfs_begin(st, stk, &tr, (1u << tr.ns) - 1u, tr.cap, tr.pax0, phase == 2, pm, &sh.best[task], &sh.steps[task]);
+      }
+      continue;
     }
-  }
-  __syncwarp(gmask);
-  double best = DRS_INF_ROUTE_COST;
-  uint8_t order[MAXS];
-  int best_first = MAXS;
-  if (fits && !s_flag[2]) {
-    const unsigned all = (ns >= 32) ? 0xffffffffu : ((1u << ns) - 1u);
-    unsigned firsts = 0;   // stops that may come first
-    for (int f = 0; f < ns; ++f)
-      if (tr.prev[f] < 0) firsts |= 1u << f;
-    const int nf = __popc(firsts);
-    for (int k0 = 0; k0 < nf; k0 += GROUP) {
-      unsigned m = firsts;
-      for (int q = 0; q < k0 + lane; ++q) m &= m - 1;   // drop the k lowest
-      const int f = m ? __ffs(m) - 1 : -1;
-      uint8_t ord[MAXS];
-      const double c = f >= 0 ? trip_dfs(tr, all, tr.cap, tr.pax0, false, ord, &exhausted, f, &shared_best) : DRS_INF_ROUTE_COST;
-      if (c < best) { best = c; best_first = f; for (int k = 0; k < ns; ++k) order[k] = ord[k]; }
-    }
-  }
-  if (exhausted) s_flag[3] = 1;
-  // reduce over the group: smallest cost, then smallest first stop
-  for (int off = GROUP / 2; off > 0; off >>= 1) {
-    const double oc = __shfl_down_sync(gmask, best, off, GROUP);
-    const int of = __shfl_down_sync(gmask, best_first, off, GROUP);
-    int take = (oc < best || (oc == best && of < best_first)) ? 1 : 0;
-    // the winner's order travels with it
-    for (int k = 0; k < MAXS; k += 4) {
-      unsigned w = (unsigned)order[k] | ((unsigned)order[k + 1] << 8) | ((unsigned)order[k + 2] << 16) | ((unsigned)order[k + 3] << 24);
-      const unsigned ow = __shfl_down_sync(gmask, w, off, GROUP);
-      if (take) { order[k] = ow & 255; order[k + 1] = (ow >> 8) & 255; order[k + 2] = (ow >> 16) & 255; order[k + 3] = (ow >> 24) & 255; }
-    }
-    if (take) { best = oc; best_first = of; }
-  }
-  __syncwarp(gmask);
-  if (lane == 0 && active) {
-    int nso = fits ? ns : -1;                    // -1: too many stops for DRS_MAX_STOPS
-    if (s_flag[3]) { nso = -2; best = DRS_INF_ROUTE_COST; }   // -2: search budget exhausted
-    *cost_out = fits ? best : DRS_INF_ROUTE_COST;
-    *ns_out = nso;
-    for (int i = 0; i < MAXS; ++i) order_out[i] = (best < DRS_INF_ROUTE_COST && i < ns) ? order[i] : 0xff;
+    dfs_step(st, stk, mode);
   }
 }
 
-__global__ void __launch_bounds__(GROUP * TASKS_PER_BLOCK) trip_eval_kernel(TickDev tk, DistView dv, double T, int flags, int ntasks,
-                                                                            TaskList tl, double* cost_out, uint8_t* order_out,
-                                                                            int32_t* nstops_out) {
-  __shared__ Trip s_trip[TASKS_PER_BLOCK];
-  __shared__ unsigned long long s_best[TASKS_PER_BLOCK];
-  __shared__ int s_flag[TASKS_PER_BLOCK][4];
-  const int slot = threadIdx.x / GROUP, lane = threadIdx.x % GROUP;
-  const int k = blockIdx.x * TASKS_PER_BLOCK + slot;
-  const bool active = k < ntasks;
-  const unsigned gmask = 0xffu << (((threadIdx.x & 31) / GROUP) * GROUP);
-  const int kk = active ? k : 0;
-  group_solve(s_trip[slot], s_best[slot], s_flag[slot], tk, dv, T, flags, active, active ? tl.veh[kk] : -1, active ? tl.nreq[kk] : 0,
-              tl.req + (int64_t)kk * MAXR, lane, gmask, cost_out + kk, nstops_out + kk, order_out + (int64_t)kk * MAXS);
+__device__ __forceinline__ int split_depth(int ns, int split2_min, int split3_min) {
+  const int d = ns >= split3_min ? 3 : ns >= split2_min ? 2 : 1;
+  return d < ns ? d : (ns > 0 ? ns : 1);
 }
+
+template <int TASKS, int THREADS>
+__device__ void eval_block(EvalShared<TASKS, THREADS>& sh, const TickDev& tk, const DistView& dv, double T, int flags, int ntasks,
+                           const TaskList& tl, int split, double* cost_out, int32_t* nstops_out, uint8_t* order_out) {
+  constexpr int LPT = THREADS / TASKS;   // lanes per trip in the cooperative steps
+  const int tid = threadIdx.x;
+  const int slot = tid / LPT, sub = tid % LPT;
+  const int k = blockIdx.x * TASKS + slot;
+  const bool active = k < ntasks;
+  Trip& tr = sh.trip[slot];
+  if (active) {
+    const int nreq = tl.nreq ? tl.nreq[k] : 1;
+    fill_trip(tr, tk, T, tl.veh[k], nreq, tl.req + (int64_t)k * (tl.nreq ? MAXR : 1), sub, LPT);
+  } else if (sub == 0) {
+    tr.fits = 0; tr.ns = 0; tr.nreq = 0; tr.has_start = 0;
+  }
+  __syncthreads();
+  if (sub == 0) {
+    number_groups(tr);
+    sh.best[slot] = (unsigned long long)__double_as_longlong(DRS_INF_ROUTE_COST);
+    sh.win_ord[slot] = kNoOrder;
+    sh.fail[slot] = 0; sh.exhausted[slot] = 0;
+    sh.count[slot] = pair_count(tr, flags);
+  }
+  __syncthreads();
+  {
+    const int ns = tr.ns;
+    for (int idx = sub; idx < (ns + 1) * ns; idx += LPT) {   // travel times among the trip's vertices
+      const int a = idx / ns, b = idx % ns + 1;
+      const int na = tr.node[a], nb = tr.node[b];
+      int raw;
+      if (na == nb) raw = 0;   // +0.0f and integer 0 share the bit pattern
+      else raw = ((const int*)dv.dist)[(int64_t)na * dv.ld + nb];
+      tr.tt[a * (MAXS + 1) + b] = raw;
+    }
+  }
+  auto publish = [&]() {   // work list = concatenation of the trips' searches
+    if (tid == 0) {
+      int acc = 0;
+      for (int t = 0; t < TASKS; ++t) { sh.off[t] = acc; acc += sh.count[t]; sh.steps[t] = 0; }
+      sh.off[TASKS] = acc;
+      sh.next = 0;
+    }
+    __syncthreads();
+  };
+  publish();
+  run_searches(sh, 0, dv.mode);
+  __syncthreads();
+  if (sub == 0) {
+    const bool go = tr.fits && !sh.fail[slot] && !sh.exhausted[slot];
+    sh.depth[slot] = split_depth(tr.ns, split & 0xff, (split >> 8) & 0xff);
+    sh.count[slot] = go ? prefix_count(tr, sh.depth[slot]) : 0;
+  }
+  __syncthreads();
+  publish();
+  run_searches(sh, 1, dv.mode);
+  __syncthreads();
+  if (sub == 0 && (sh.exhausted[slot] || !(__longlong_as_double((long long)sh.best[slot]) < DRS_INF_ROUTE_COST))) sh.count[slot] = 0;
+  __syncthreads();
+  publish();
+  run_searches(sh, 2, dv.mode);
+  __syncthreads();
+  if (sub == 0 && active) {
+    double best = __longlong_as_double((long long)sh.best[slot]);
+    int nso = tr.fits ? tr.ns : -1;                    // -1: too many stops for DRS_MAX_STOPS
+    const unsigned long long ord = sh.win_ord[slot];
+    bool have = tr.fits && best < DRS_INF_ROUTE_COST && ord != kNoOrder;
+    if (sh.exhausted[slot]) { nso = -2; have = false; }   // -2: search budget exhausted
+    if (!have) best = DRS_INF_ROUTE_COST;
+    cost_out[k] = best;
+    nstops_out[k] = nso;
+    for (int i = 0; i < MAXS; ++i) order_out[(int64_t)k * MAXS + i] = (have && i < tr.ns) ? (uint8_t)ord_at(ord, i) : 0xff;
+  }
+}
+
+template <int TASKS, int THREADS>
+__global__ void __launch_bounds__(THREADS) trip_eval_kernel(TickDev tk, DistView dv, double T, int flags, int ntasks, TaskList tl,
+                                                            int split, double* cost_out, uint8_t* order_out, int32_t* nstops_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  auto& sh = *reinterpret_cast<EvalShared<TASKS, THREADS>*>(smem_raw);
+  eval_block<TASKS, THREADS>(sh, tk, dv, T, flags, ntasks, tl, split, cost_out, nstops_out, order_out);
+}
+
+// RV stage, second half: the surviving (vehicle, request) pairs are trips of one new request
+template <int TASKS, int THREADS>
+__global__ void __launch_bounds__(THREADS) rv_eval_kernel(TickDev tk, DistView dv, double T, int flags, int nsurv,
+                                                          const int32_t* surv_veh, const int32_t* surv_req, int8_t* status,
+                                                          int split, double* cost_out, uint8_t* order_out, int32_t* nstops_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  auto& sh = *reinterpret_cast<EvalShared<TASKS, THREADS>*>(smem_raw);
+  const TaskList tl{surv_veh, nullptr, surv_req};
+  eval_block<TASKS, THREADS>(sh, tk, dv, T, flags, nsurv, tl, split, cost_out, nstops_out, order_out);
+  __syncthreads();
+  constexpr int LPT = THREADS / TASKS;
+  const int k = blockIdx.x * TASKS + threadIdx.x / LPT;
+  if (threadIdx.x % LPT == 0 && k < nsurv)
+    status[(int64_t)surv_veh[k] * tk.n_req + surv_req[k]] = (int8_t)((cost_out[k] < DRS_INF_ROUTE_COST) ? DRS_RV_FEASIBLE : DRS_RV_INFEASIBLE);
+}
+
+// CTA shape of the evaluation kernels: 8 trips, 128 lanes (measured best of 8..64 trips x 32..256 lanes on the C4
+// tick: larger CTAs wait longer at the barriers between the work lists, fewer lanes leave searches queued)
+constexpr int EV_TASKS = 8, EV_THREADS = 128;
 
 // status per pair + compact survivor list (warp-aggregated append)
 __global__ void rv_filter_kernel(TickDev tk, DistView dv, double T, int8_t* status, int32_t* surv_veh,
@@ -348,29 +502,6 @@ __global__ void rv_filter_kernel(TickDev tk, DistView dv, double T, int8_t* stat
   }
 }
 
-// RV stage, second half: one group of GROUP lanes per surviving pair
-__global__ void __launch_bounds__(GROUP * TASKS_PER_BLOCK) rv_eval_kernel(TickDev tk, DistView dv, double T, int flags, int nsurv,
-                                                                          const int32_t* surv_veh, const int32_t* surv_req,
-                                                                          int8_t* status, double* cost_out, uint8_t* order_out,
-                                                                          int32_t* nstops_out) {
-  __shared__ Trip s_trip[TASKS_PER_BLOCK];
-  __shared__ unsigned long long s_best[TASKS_PER_BLOCK];
-  __shared__ int s_flag[TASKS_PER_BLOCK][4];
-  __shared__ int32_t s_req[TASKS_PER_BLOCK];
-  const int slot = threadIdx.x / GROUP, lane = threadIdx.x % GROUP;
-  const int k = blockIdx.x * TASKS_PER_BLOCK + slot;
-  const bool active = k < nsurv;
-  const unsigned gmask = 0xffu << (((threadIdx.x & 31) / GROUP) * GROUP);
-  const int kk = active ? k : 0;
-  const int v = active ? surv_veh[kk] : -1, r = active ? surv_req[kk] : 0;
-  if (lane == 0) s_req[slot] = r;
-  __syncwarp(gmask);
-  group_solve(s_trip[slot], s_best[slot], s_flag[slot], tk, dv, T, flags, active, v, active ? 1 : 0, &s_req[slot], lane, gmask,
-              cost_out + kk, nstops_out + kk, order_out + (int64_t)kk * MAXS);
-  if (lane == 0 && active)
-    status[(int64_t)v * tk.n_req + r] = (int8_t)((cost_out[kk] < DRS_INF_ROUTE_COST) ? DRS_RV_FEASIBLE : DRS_RV_INFEASIBLE);
-}
-
 __global__ void count_status_kernel(const int8_t* status, int64_t total, unsigned long long* counters) {
   unsigned long long c[4] = {0, 0, 0, 0};
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -385,6 +516,36 @@ __global__ void count_status_kernel(const int8_t* status, int64_t total, unsigne
 }
 
 template <typename T> int upload(T** dptr, const T* h, size_t n, cudaStream_t st) { return drs_upload(dptr, h, n, st); }
+
+// stop counts from which a trip's searches are split by its first two / three stops, packed (split3 << 8) | split2
+// (DRS_EVAL_SPLIT2 / DRS_EVAL_SPLIT3 override: tuning knobs; the split never changes the result)
+int eval_split() {
+  const char* e2 = getenv("DRS_EVAL_SPLIT2");
+  const char* e3 = getenv("DRS_EVAL_SPLIT3");
+  const int s2 = e2 ? atoi(e2) : 5, s3 = e3 ? atoi(e3) : 8;
+  return ((s3 & 0xff) << 8) | (s2 & 0xff);
+}
+
+int launch_rv_eval(const TickDev& d, const DistView& dv, double T, int flags, int nsurv, const int32_t* surv_veh,
+                   const int32_t* surv_req, int8_t* status, double* cost, uint8_t* order, int32_t* nstops, cudaStream_t st) {
+  auto k = rv_eval_kernel<EV_TASKS, EV_THREADS>;
+  const size_t smem = sizeof(EvalShared<EV_TASKS, EV_THREADS>);
+  k<<<(nsurv + EV_TASKS - 1) / EV_TASKS, EV_THREADS, smem, st>>>(d, dv, T, flags, nsurv, surv_veh, surv_req, status, eval_split(), cost, order, nstops);
+  drs_count_launch();
+  DRS_CUDA(cudaGetLastError());
+  return DRS_OK;
+}
+
+int launch_trip_eval(const TickDev& d, const DistView& dv, double T, int flags, int ntasks, const TaskList& tl, double* cost,
+                     uint8_t* order, int32_t* nstops, cudaStream_t st) {
+  auto k = trip_eval_kernel<EV_TASKS, EV_THREADS>;
+  const size_t smem = sizeof(EvalShared<EV_TASKS, EV_THREADS>);
+  k<<<(ntasks + EV_TASKS - 1) / EV_TASKS, EV_THREADS, smem, st>>>(d, dv, T, flags, ntasks, tl, eval_split(), cost, order, nstops);
+  drs_count_launch();
+  return DRS_OK;
+}
+
+static_assert(sizeof(EvalShared<EV_TASKS, EV_THREADS>) <= 48 * 1024, "evaluation CTA must fit the default dynamic shared memory");
 
 }  // namespace
 
@@ -549,10 +710,8 @@ extern "C" int drs_tick_rv_eval(drs_tick* t, double T, int32_t flags, int32_t* n
   DRS_CUDA(cudaMalloc((void**)&t->d_nstops, sizeof(int32_t) * std::max(nsurv, 1)));
   tm_eval.start();
   if (nsurv > 0) {
-    rv_eval_kernel<<<(nsurv + TASKS_PER_BLOCK - 1) / TASKS_PER_BLOCK, GROUP * TASKS_PER_BLOCK, 0, st>>>(d, dv, T, flags, nsurv, t->d_surv_veh, t->d_surv_req, t->d_status,
-                                                     t->d_cost, t->d_order, t->d_nstops);
-    drs_count_launch();
-  DRS_CUDA(cudaGetLastError());
+    int rc = launch_rv_eval(d, dv, T, flags, nsurv, t->d_surv_veh, t->d_surv_req, t->d_status, t->d_cost, t->d_order, t->d_nstops, st);
+    if (rc) return rc;
   }
   tm_eval.stop();
   count_status_kernel<<<148 * 2, 256, 0, st>>>(t->d_status, total, t->d_counters);
@@ -643,8 +802,8 @@ extern "C" int drs_tick_trip_eval(drs_tick* t, double T, int32_t flags, int32_t 
   }
   DistView dv{t->g->d_dist, t->g->ld, t->g->mode};
   TaskList tl{dv_, dn, dr};
-  trip_eval_kernel<<<(n_tasks + TASKS_PER_BLOCK - 1) / TASKS_PER_BLOCK, GROUP * TASKS_PER_BLOCK, 0, st>>>(d, dv, T, flags, n_tasks, tl, dc, dord, dns);
-  drs_count_launch();
+  rc = launch_trip_eval(d, dv, T, flags, n_tasks, tl, dc, dord, dns, st);
+  if (rc) { cleanup(); return rc; }
   std::vector<int32_t> nst(n_tasks);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpyAsync(cost_host, dc, sizeof(double) * n_tasks, cudaMemcpyDeviceToHost, st);

@@ -73,3 +73,17 @@ class OVeh(object):
 
     def get_next_node(self):
         return self._loc, self._t
+
+
+@pytest.fixture(params=["split_default", "split_deep", "split_none"])
+def eval_split(request, monkeypatch):
+    """Runs a dispatch test under three settings of how the trip-evaluation kernels split a trip's ordering search
+    into parallel searches (by the first 1, 2 or 3 stops): the default, as deep as possible for every trip, and no
+    deeper than the first stop.  The split is a scheduling decision and must never change a result."""
+    s2, s3 = {"split_default": (None, None), "split_deep": ("2", "3"), "split_none": ("99", "99")}[request.param]
+    for name, val in (("DRS_EVAL_SPLIT2", s2), ("DRS_EVAL_SPLIT3", s3)):
+        if val is None:
+            monkeypatch.delenv(name, raising=False)
+        else:
+            monkeypatch.setenv(name, val)
+    return request.param

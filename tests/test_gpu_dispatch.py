@@ -5,7 +5,7 @@ import pytest
 
 from conftest import OReq, OVeh, golden_map_path, load_golden, oracle_graph, unjf
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("eval_split")]
 
 
 def _graph(name):

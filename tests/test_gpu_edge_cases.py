@@ -7,7 +7,7 @@ import pytest
 
 from conftest import OReq, OVeh
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("eval_split")]
 
 
 def _directed_graph(n_side=9, seed=4):
