@@ -212,3 +212,96 @@ def test_rv_stage_at_fleet_scale_matches_oracle():
     (oroutes, orej), ometa = D.optimize_assignment(ovehs, oreqs, tt, T, max_trip_size=1)
     assert meta["objective"] == pytest.approx(ometa["objective"], abs=1e-6) and len(rejected) == len(orej)
     G.close()
+
+
+_TIE_CASES = {}
+
+
+def _tie_cases():
+    """Random trips on the uniform-weight grid and the oracle's answers (CPU only; built once per process)."""
+    if _TIE_CASES:
+        return _TIE_CASES
+    from scipy.sparse import csr_matrix
+    from scipy.sparse.csgraph import dijkstra
+    from drs_abm_b200 import synth
+    from oracle import dispatch_oracle as D
+    data = synth.config_graph("C1_uniform")
+    w = np.asarray(data.eattrs["ttmedian"], dtype=np.float64)
+    A = csr_matrix((np.concatenate([w, w]), (np.concatenate([data.src, data.dst]), np.concatenate([data.dst, data.src]))),
+                   shape=(data.n, data.n))
+    dist = dijkstra(A, directed=True)
+    tt = lambda a, b: float(dist[a, b])
+    lng, lat = data.vattrs["lng"], data.vattrs["lat"]
+    rs = np.random.RandomState(77)
+    nq, n_old = 64, 40       # requests 0..39 are already assigned (they appear on vehicles), 40..63 are new
+    node_o, node_d = rs.randint(0, data.n, nq), rs.randint(0, data.n, nq)
+    req_spec = []
+    for q in range(nq):
+        slack = float(rs.choice([300.0, 900.0, 3000.0, 20000.0]))
+        Ts = tt(int(node_o[q]), int(node_d[q]))
+        req_spec.append((q, lng[node_o[q]], lat[node_o[q]], lng[node_d[q]], lat[node_d[q]], 0.0, slack, Ts, slack + 1.5 * Ts + 600.0, q < n_old))
+    veh_spec, nxt = [], 0
+    for k, (npax, nwait) in enumerate([(0, 0), (1, 0), (0, 1), (2, 0), (1, 1), (0, 2), (2, 1), (1, 2), (3, 0), (0, 0), (2, 2), (1, 1)]):
+        pax, wait = list(range(nxt, nxt + npax)), list(range(nxt + npax, nxt + npax + nwait))
+        nxt += npax + nwait
+        nd = int(rs.randint(0, data.n))
+        veh_spec.append((k, 4, nd, float(rs.choice([0.0, 15.0])), pax, wait))
+    assert nxt <= n_old
+    reqs = [OReq(*sp[:9], assigned=sp[9]) for sp in req_spec]
+    vehs = [OVeh(k, K, (lng[nd], lat[nd]), t, pax, wait) for k, K, nd, t, pax, wait in veh_spec]
+
+    def rec(r):
+        return {"rid": r.id, "o_node": int(node_o[r.id]), "d_node": int(node_d[r.id]), "olng": r.olng, "olat": r.olat, "dlng": r.dlng,
+                "dlat": r.dlat, "Cep": r.Cep, "Clp": r.Clp, "Ced": r.Ced, "Cld": r.Cld}
+    ovehs = []
+    for v, sp in zip(vehs, veh_spec):
+        pax, wait = v.get_passenger_requests()          # same (set-iteration) order the drop-in marshals
+        ovehs.append({"vid": v.id, "capacity": v.K, "node": sp[2], "location": v.get_next_node()[0], "t": v.get_next_node()[1],
+                      "pax_reqs": [rec(reqs[q]) for q in pax], "wait_reqs": [rec(reqs[q]) for q in wait]})
+    T = 100.0
+    cases = {}
+    for pairwise in (True, False):
+        tasks, want = [], []
+        for _ in range(150):
+            vi = int(rs.randint(-1, len(vehs)))
+            planned = 0 if vi < 0 else len(ovehs[vi]["pax_reqs"]) + 2 * len(ovehs[vi]["wait_reqs"])
+            nnew = int(rs.randint(1, 4))
+            while planned + 2 * nnew > 8:
+                nnew -= 1
+            new = [int(x) for x in rs.choice(np.arange(n_old, nq), size=nnew, replace=False)]
+            verts = [D.request_vertex(rec(reqs[q]), T) for q in new]
+            if pairwise or vi < 0:
+                ocost, _, oorder = D.find_optimal_routing(verts, tt, ovehs[vi] if vi >= 0 else None, T)
+            else:   # the "tabu" front end skips the pairwise pre-checks
+                ov = ovehs[vi]
+                ocost, _, oorder = D.minimal_delay_path(D.create_locations(verts, ov), tt, T + ov["t"],
+                                                        D.Stop(ov["node"], ov["location"][0], ov["location"][1]),
+                                                        ov["capacity"], len(ov["pax_reqs"]))
+            tasks.append((vi, new))
+            want.append((ocost, None if oorder is None else list(oorder)))
+        cases[pairwise] = (tasks, want)
+    _TIE_CASES.update(data=data, dist=dist, reqs=reqs, vehs=vehs, T=T, cases=cases)
+    return _TIE_CASES
+
+
+def test_random_trips_on_a_uniform_map_match_oracle_including_ties():
+    """Tie stress for the canonical ordering rule: on the uniform-weight grid (every arc 30 s) many orderings of a
+    trip cost exactly the same, so cost AND ordering must agree with the oracle's first-minimum-in-lexicographic-order
+    for random trips of 2..8 stops (busy vehicles, empty vehicles, no vehicle), with and without the pairwise
+    pre-checks, windows from hopeless to wide open."""
+    from drs_abm_b200.dispatch import Tick
+    from drs_abm_b200.routing import RoadGraph
+    tc = _tie_cases()
+    G = RoadGraph(tc["data"])
+    assert np.array_equal(G.dist_rows(0, G.n)[:, :G.n], tc["dist"])
+    feasible = 0
+    for pairwise, (tasks, want) in tc["cases"].items():
+        tick = Tick(G, tc["vehs"], tc["reqs"], tc["T"], pairwise_checks=pairwise)
+        idx = {r.id: i for i, r in enumerate(tick.new_reqs)}
+        got = tick.trip_eval([(vi, [idx[q] for q in new]) for vi, new in tasks])
+        tick.close()
+        for g, w, t in zip(got, want, tasks):
+            assert g[0] == w[0] and g[1] == w[1], (t, g, w)
+            feasible += g[1] is not None
+    assert feasible >= 60
+    G.close()
