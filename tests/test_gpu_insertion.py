@@ -147,3 +147,52 @@ def test_insertion_object_front_end_with_vehicle_between_nodes():
         vid, route, odc, _ = D.legacy_insert_heuristics(tt, ovehs, oreqs, new.id)
         assert wveh.id == vid and wdc == odc
         assert [(s[0], s[1]) for s in wroute] == [(s[0], s[1]) for s in route]
+
+
+def test_c4_full_size_tick_sampled_against_oracle():
+    """BASELINE config C4 at full size (10 000 vehicles x 2 000 pending requests on the 50k-node C3 map, 3.9e8
+    candidates): the candidate count is the closed form, every reported winner is a valid (vehicle, i < j <= L+1)
+    with a finite cost, re-evaluating a request alone gives the same answer as inside the batch (requests are
+    independent), and sampled requests (two with a winner, one
+    without if there is any) equal the oracle's sequential scan over ALL 10 000 vehicles."""
+    from drs_abm_b200 import synth
+    from drs_abm_b200.dispatch import InsertionTick
+    from drs_abm_b200.routing import RoadGraph
+    from oracle import dispatch_oracle as D
+    data = synth.config_graph("C3")
+    G = RoadGraph(data).build()
+    n_veh, n_new = 10000, 2000
+    sc = synth.fleet_scenario(data, n_veh, n_new, 600.0, 4, lambda s, t: G.matrix_lookup(s, t))
+    tick = InsertionTick(G, sc["vehs"], sc["table"])
+    bv, bi, bj, dc, ncand = tick.evaluate(sc["new_rows"])
+    L = np.array([len(v["route"]) for v in sc["vehs"]], dtype=np.int64)
+    assert ncand == int(((L + 1) * (L + 2) // 2).sum()) * n_new
+    won = bv >= 0
+    assert won.sum() > n_new // 2
+    assert np.all(np.isfinite(dc[won])) and np.all(np.isinf(dc[~won]))
+    assert np.all(bi[won] >= 0) and np.all(bi[won] < bj[won]) and np.all(bj[won] <= L[bv[won]] + 1)
+    pick = np.random.RandomState(9).choice(n_new, 64, replace=False)
+    bv2, bi2, bj2, dc2, _ = tick.evaluate(sc["new_rows"][pick])
+    assert np.array_equal(bv2, bv[pick]) and np.array_equal(bi2, bi[pick]) and np.array_equal(bj2, bj[pick]) and np.array_equal(dc2, dc[pick])
+    tick.close()
+    rows = {}
+
+    def tt(a, b):
+        r = rows.get(a)
+        if r is None:
+            r = rows[a] = G.dist_rows(int(a), 1)[0]
+        return float(r[b])
+    ovehs = [{"vid": k, "n": v["n"], "T": v["T"], "K": v["K"], "c": v["c"], "node": v["node"], "t0": v["t0"],
+              "route": list(v["route"])} for k, v in enumerate(sc["vehs"])]
+    sampled = [int(np.flatnonzero(won)[7]), int(np.flatnonzero(won)[-3])] + [int(x) for x in np.flatnonzero(~won)[:1]]
+    for k in sampled:
+        row = int(sc["new_rows"][k])
+        vid, route, odc, _ = D.legacy_insert_heuristics(tt, ovehs, _oracle_reqs(sc["table"]), row)
+        if not won[k]:
+            assert vid is None
+            continue
+        assert vid is not None
+        i = [x for x, s in enumerate(route) if s[0] == row and s[1] == 1][0]
+        j = [x for x, s in enumerate(route) if s[0] == row and s[1] == -1][0]
+        assert (int(bv[k]), int(bi[k]), int(bj[k])) == (vid, i, j) and dc[k] == odc
+    G.close()

@@ -228,6 +228,64 @@ def test_c2_full_size_properties(algorithm):
     G.close()
 
 
+def test_c3_full_size_certificate_and_properties():
+    """BASELINE config C3 (50 171 nodes, the bench workload) at full size, checked on the device through
+    size-independent properties of the 9.6 GB matrix: zero diagonal, finiteness and symmetry of the whole matrix
+    (the map is connected and undirected), triangle inequality through random pivots, and for 1 024 sampled source
+    rows the shortest-path CERTIFICATE -- every arc satisfies d[s,v] <= d[s,u] + w and every vertex but the source
+    has an in-arc where that holds with equality -- plus exact equality with the oracle's Dijkstra on 24 rows and
+    path sums equal to the matrix entries."""
+    import ctypes as C
+    import torch
+    from drs_abm_b200 import _lib, synth
+    from drs_abm_b200.apsp_dist import _as_tensor
+    from drs_abm_b200.routing import RoadGraph
+    data = synth.config_graph("C3")
+    G = RoadGraph(data).build()
+    lib = _lib.load()
+    dptr, pptr, ld = C.c_void_p(), C.c_void_p(), C.c_int64(0)
+    _lib.check(lib.drs_apsp_matrices(G.handle, C.byref(dptr), C.byref(pptr), C.byref(ld)), lib)
+    n, npad = G.n, int(ld.value)
+    D = _as_tensor(torch, dptr.value, (npad, npad), torch.float32)
+    torch.cuda.synchronize()
+    assert bool((torch.diagonal(D) == 0).all())
+    blk = 4096
+    for a in range(0, n, blk):
+        b = min(n, a + blk)
+        rows = D[a:b, :n]
+        assert bool(torch.isfinite(rows).all())
+        assert bool((rows == D[:n, a:b].T).all())                       # symmetry, block by block
+    rs = np.random.RandomState(5)
+    for k in rs.randint(0, n, 4):                                        # triangle inequality through pivot k
+        colk, rowk = D[:n, int(k)].clone(), D[int(k), :n].clone()
+        for a in range(0, n, blk):
+            b = min(n, a + blk)
+            assert bool((D[a:b, :n] <= colk[a:b, None] + rowk[None, :]).all())
+    # certificate on sampled rows (integer weights: every sum is exact in fp32)
+    src = torch.as_tensor(np.concatenate([data.src, data.dst]).astype(np.int64), device="cuda")
+    dst = torch.as_tensor(np.concatenate([data.dst, data.src]).astype(np.int64), device="cuda")
+    w = torch.as_tensor(np.concatenate([data.eattrs["ttmedian"]] * 2).astype(np.float32), device="cuda")
+    sample = rs.choice(n, 1024, replace=False)
+    for a in range(0, len(sample), 256):
+        rows_idx = torch.as_tensor(sample[a:a + 256].astype(np.int64), device="cuda")
+        R = D[rows_idx][:, :n]
+        via = R[:, src] + w[None, :]
+        assert bool((R[:, dst] <= via).all())
+        tight = torch.full_like(R, float("inf")).scatter_reduce(1, dst[None, :].expand(len(rows_idx), -1), via, reduce="amin")
+        tight[torch.arange(len(rows_idx), device="cuda"), rows_idx] = 0.0
+        assert bool((tight == R).all())
+        del R, via, tight
+    O = oracle_graph_from_data(data)
+    idx = sample[:24]
+    assert np.array_equal(np.stack([G.dist_rows(int(i), 1)[0] for i in idx]), O.dist_rows(idx))
+    s = rs.randint(0, n, 2000).astype(np.int32); t = rs.randint(0, n, 2000).astype(np.int32)
+    tt, ln, hops = G.path_sums(s, t)
+    want = D[torch.as_tensor(s.astype(np.int64), device="cuda"), torch.as_tensor(t.astype(np.int64), device="cuda")].double().cpu().numpy()
+    assert np.array_equal(tt, want) and np.array_equal(ln, 10.0 * tt) and int(hops.max()) > 100
+    del D
+    G.close()
+
+
 def test_batched_sssp_without_matrix():
     """BASELINE config C5 usage: distance rows for a batch of sources, no N x N matrix."""
     from drs_abm_b200 import synth
