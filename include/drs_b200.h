@@ -283,7 +283,14 @@ int drs_tick_rv_fetch(drs_tick* t, int32_t capacity_edges, int32_t* veh_idx, int
  * task_req[k*DRS_MAX_TRIP_REQS ..] (indices into the request batch).  Implements
  * findOptimalRouting (lib/optimUtils.py:113-160).  cost_host[k] ==
  * DRS_INF_ROUTE_COST means infeasible.  Stop numbering in order_host: new
- * requests' (pickup, drop-off) pairs in task order, then the vehicle's stops. */
+ * requests' (pickup, drop-off) pairs in task order, then the vehicle's stops.
+ * Among equal-cost orderings the lexicographically smallest (by that numbering)
+ * is returned.  The search is exact and, like the reference's "enumerate",
+ * exponential in the stop count: a trip that needs more than 2*10^7 search steps
+ * makes the call fail with DRS_ERR_CAPACITY ("budget") -- the same holds for
+ * drs_tick_rv_eval.  Environment (tuning only, results never depend on them):
+ * DRS_EVAL_SPLIT2 / DRS_EVAL_SPLIT3 = stop counts from which a trip's search is
+ * split into parallel searches by its first two / three stops (default 5 / 8). */
 int drs_tick_trip_eval(drs_tick* t, double T, int32_t flags, int32_t n_tasks, const int32_t* task_veh,
                        const int32_t* task_nreq, const int32_t* task_req, double* cost_host,
                        uint8_t* order_host, int32_t* n_stops_host);
