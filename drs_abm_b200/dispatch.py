@@ -69,8 +69,8 @@ class Tick(object):
         node = G.node_of_location
         nr = len(self.new_reqs)
         self.r_rid = np.array([r.id for r in self.new_reqs], dtype=np.int32)
-        self.r_o = np.array([node(r.olng, r.olat) for r in self.new_reqs], dtype=np.int32)
-        self.r_d = np.array([node(r.dlng, r.dlat) for r in self.new_reqs], dtype=np.int32)
+        self.r_o = G.dev_ids(np.array([node(r.olng, r.olat) for r in self.new_reqs], dtype=np.int32))
+        self.r_d = G.dev_ids(np.array([node(r.dlng, r.dlat) for r in self.new_reqs], dtype=np.int32))
         self.r_lbp = np.array([r.Cep - T for r in self.new_reqs], dtype=np.float64)       # Cep - T (:117)
         self.r_ubp = np.array([r.Clp for r in self.new_reqs], dtype=np.float64)
         dw = [r.get_dropoff_time_window() for r in self.new_reqs]                          # (:111)
@@ -109,9 +109,9 @@ class Tick(object):
                 raise ValueError("vehicle %r has %d planned stops; the kernel handles %d" % (veh.id, len(stops), MAX_STOPS - 2))
             self.veh_stops.append(stops)
             off.append(len(s_node))
-        self._v = dict(node=np.array(v_node, dtype=np.int32), delay=np.array(v_delay, dtype=np.float64),
+        self._v = dict(node=G.dev_ids(np.array(v_node, dtype=np.int32)), delay=np.array(v_delay, dtype=np.float64),
                        cap=np.array(v_cap, dtype=np.int32), pax=np.array(v_pax, dtype=np.int32),
-                       off=np.array(off, dtype=np.int32), s_node=np.array(s_node, dtype=np.int32),
+                       off=np.array(off, dtype=np.int32), s_node=G.dev_ids(np.array(s_node, dtype=np.int32)),
                        s_rid=np.array(s_rid, dtype=np.int32), s_pod=np.array(s_pod, dtype=np.int8),
                        s_prev=np.array(s_prev, dtype=np.int8), s_lb=np.array(s_lb, dtype=np.float64),
                        s_ub=np.array(s_ub, dtype=np.float64))
@@ -498,17 +498,17 @@ class InsertionTick(object):
         for v, veh in enumerate(vehs):
             off[v + 1] = off[v] + len(veh["route"])
         self._a = dict(
-            node=np.array([v["node"] for v in vehs], dtype=np.int32),
+            node=G.dev_ids(np.array([v["node"] for v in vehs], dtype=np.int32)),
             delay=np.array([v["t0"] for v in vehs], dtype=np.float64),
             onboard=np.array([v["n"] for v in vehs], dtype=np.int32),
             clock=np.array([v["T"] for v in vehs], dtype=np.float64),
             cap=np.array([v["K"] for v in vehs], dtype=np.int32),
             cost=np.array([v["c"] for v in vehs], dtype=np.float64),
             off=off,
-            s_node=np.array([s[2] for v in vehs for s in v["route"]], dtype=np.int32),
+            s_node=G.dev_ids(np.array([s[2] for v in vehs for s in v["route"]], dtype=np.int32)),
             s_req=np.array([s[0] for v in vehs for s in v["route"]], dtype=np.int32),
             s_pod=np.array([s[1] for v in vehs for s in v["route"]], dtype=np.int8))
-        self._t = {k: (_lib.as_i32(table[k]) if k in ("o", "d") else _lib.as_f64(table[k]))
+        self._t = {k: (G.dev_ids(table[k]) if k in ("o", "d") else _lib.as_f64(table[k]))
                    for k in ("o", "d", "Cep", "Clp", "Cld", "Ts", "Tr", "pwt")}
         a, t = self._a, self._t
         pb = _lib.PlanBatch(nv, _lib.ptr_i32(a["node"]), _lib.ptr_f64(a["delay"]), _lib.ptr_i32(a["onboard"]),

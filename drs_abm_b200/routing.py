@@ -149,6 +149,45 @@ class EdgeSeq(object):
         self.graph._set_edge_attr(key, None, values)
 
 
+def _spread16(v):
+    """Bits of a 16-bit integer array moved to the even positions (Morton interleave)."""
+    v = v.astype(np.uint64) & np.uint64(0xffff)
+    v = (v | (v << np.uint64(8))) & np.uint64(0x00ff00ff)
+    v = (v | (v << np.uint64(4))) & np.uint64(0x0f0f0f0f)
+    v = (v | (v << np.uint64(2))) & np.uint64(0x33333333)
+    v = (v | (v << np.uint64(1))) & np.uint64(0x55555555)
+    return v
+
+
+def locality_order(n, src, dst, lng=None, lat=None):
+    """Vertex ids in the order of the DEVICE numbering: order[k] = caller's id of device vertex k.
+
+    The kernels index distance rows by vertex id, so neighbouring vertices should have neighbouring ids (the same
+    50k-node map builds in 84 ms numbered along a Morton curve, 93 ms row-major, 141 ms numbered at random --
+    profiles/r01_sssp_numbering_probe.jsonl).  With usable coordinates: Morton (Z-order) curve over (lng, lat)
+    ranked to at most 16 bits each; otherwise reverse Cuthill-McKee over the adjacency."""
+    try:
+        x, y = np.asarray(lng, dtype=np.float64), np.asarray(lat, dtype=np.float64)
+        if x.shape != (n,) or y.shape != (n,) or not (np.isfinite(x).all() and np.isfinite(y).all()):
+            raise ValueError
+        ux, qx = np.unique(x, return_inverse=True)      # rank of each coordinate among the distinct values: a regular
+        uy, qy = np.unique(y, return_inverse=True)      # grid gets its exact Z-curve, an irregular map a density-equalised one
+        if len(ux) == 1 and len(uy) == 1:
+            raise ValueError
+        if len(ux) > 65536:
+            qx = qx.astype(np.int64) * 65536 // len(ux)
+        if len(uy) > 65536:
+            qy = qy.astype(np.int64) * 65536 // len(uy)
+        return np.argsort(_spread16(qx) | (_spread16(qy) << np.uint64(1)), kind="stable").astype(np.int32)
+    except (TypeError, ValueError):
+        from scipy.sparse import csr_matrix
+        from scipy.sparse.csgraph import reverse_cuthill_mckee
+        if len(src) == 0:
+            return np.arange(n, dtype=np.int32)
+        A = csr_matrix((np.ones(2 * len(src), dtype=np.int8), (np.concatenate([src, dst]), np.concatenate([dst, src]))), shape=(n, n))
+        return np.asarray(reverse_cuthill_mckee(A, symmetric_mode=True), dtype=np.int32)
+
+
 class RoadGraph(object):
     """The object callers know as ``router.G``: igraph look-alike backed by a device
     CSR graph and the resident travel-time / predecessor matrices.
@@ -158,7 +197,7 @@ class RoadGraph(object):
     ``ttmedian`` after load).
     """
 
-    def __init__(self, data, mode=_lib.MODE_F32, algorithm=_lib.APSP_AUTO, pred=_lib.PRED_LAZY):
+    def __init__(self, data, mode=_lib.MODE_F32, algorithm=_lib.APSP_AUTO, pred=_lib.PRED_LAZY, numbering="locality"):
         if not isinstance(data, RoadGraphData):
             raise TypeError("RoadGraph needs RoadGraphData (use RoadGraph.Read_GML)")
         self.n, self.m = data.n, data.m
@@ -174,6 +213,13 @@ class RoadGraph(object):
         self._weight_attr = None      # attribute the device weights / matrix were built from
         self._lib = None
         self._by_name = self._by_coord = None    # name / coordinate indexes are built on first look-up
+        # Device numbering of the vertices: "locality" = along a space-filling curve (locality_order), "input" = the
+        # caller's.  Vertex ids are translated at every call into the library (dev_ids / host_cols); edge ids, and
+        # with them adjacency order, canonical predecessors and paths, do not depend on it.
+        if numbering not in ("locality", "input"):
+            raise ValueError("numbering must be 'locality' or 'input'")
+        self.numbering = numbering
+        self._new_of_old = self._old_of_new = None
 
     # ------------------------------------------------------------------ igraph surface
     @classmethod
@@ -297,6 +343,27 @@ class RoadGraph(object):
 
     _weights_dirty = False
 
+    def _number(self):
+        if self.numbering == "locality" and self._new_of_old is None:
+            order = locality_order(self.n, self._src, self._dst, self._vattrs.get("lng"), self._vattrs.get("lat"))
+            self._old_of_new = np.ascontiguousarray(order, dtype=np.int32)
+            self._new_of_old = np.empty(self.n, dtype=np.int32)
+            self._new_of_old[order] = np.arange(self.n, dtype=np.int32)
+
+    def dev_ids(self, ids):
+        """Caller's vertex ids -> the library's (int32 array).  Out of range -> ValueError (igraph's behaviour)."""
+        a = _lib.as_i32(ids)
+        if a.size and (int(a.min()) < 0 or int(a.max()) >= self.n):
+            raise ValueError("vertex index out of range (n=%d)" % self.n)
+        self._number()
+        return a if self._new_of_old is None else np.ascontiguousarray(self._new_of_old[a])
+
+    def host_cols(self, rows):
+        """Columns of distance rows (last axis = device vertex ids, at least n wide) -> the caller's numbering, n wide."""
+        self._number()
+        rows = np.asarray(rows)
+        return rows[..., :self.n] if self._new_of_old is None else rows[..., self._new_of_old]
+
     def _ensure(self, weights, build=True):
         """Device graph exists, carries `weights`, and (build=True) the APSP matrix is valid."""
         attr = weights if weights is not None else (self._weight_attr or "ttmedian")
@@ -310,7 +377,7 @@ class RoadGraph(object):
         if self._handle is None:
             h = C.c_void_p()
             length = _lib.as_f64(self._eattrs.get("length", np.zeros(self.m)))
-            src, dst = _lib.as_i32(self._src), _lib.as_i32(self._dst)
+            src, dst = self.dev_ids(self._src), self.dev_ids(self._dst)
             _lib.check(lib.drs_graph_create(self.n, self.m, 1 if self.directed else 0, _lib.ptr_i32(src),
                                             _lib.ptr_i32(dst), _lib.ptr_f64(tt), _lib.ptr_f64(length), C.byref(h)), lib)
             self._handle = h
@@ -373,7 +440,7 @@ class RoadGraph(object):
     def matrix_lookup(self, s, t, weights=None):
         """dist[s[i], t[i]] as float64 (inf = unreachable): one gather kernel."""
         lib = self._ensure(weights)
-        s, t = _lib.as_i32(s), _lib.as_i32(t)
+        s, t = self.dev_ids(s), self.dev_ids(t)
         out = np.empty(len(s), dtype=np.float64)
         _lib.check(lib.drs_query_matrix(self._handle, len(s), _lib.ptr_i32(s), _lib.ptr_i32(t), _lib.ptr_f64(out)), lib)
         return out
@@ -381,7 +448,7 @@ class RoadGraph(object):
     def path_sums(self, s, t, weights=None):
         """(duration, length, hops) along the canonical paths: fp64 left-to-right sums."""
         lib = self._ensure(weights)
-        s, t = _lib.as_i32(s), _lib.as_i32(t)
+        s, t = self.dev_ids(s), self.dev_ids(t)
         n = len(s)
         tt, ln, hops = np.empty(n), np.empty(n), np.empty(n, dtype=np.int32)
         _lib.check(lib.drs_query_pairs(self._handle, n, _lib.ptr_i32(s), _lib.ptr_i32(t), _lib.ptr_f64(tt),
@@ -390,6 +457,7 @@ class RoadGraph(object):
 
     def epath(self, s, t, weights=None):
         lib = self._ensure(weights)
+        s, t = (int(x) for x in self.dev_ids([s, t]))
         cap = 256
         while True:
             buf = np.empty(cap, dtype=np.int32)
@@ -407,16 +475,27 @@ class RoadGraph(object):
         returns a len(sources) x n float64 array.  For networks too large for the matrix
         (BASELINE config C5) and for ``G.shortest_paths(src_list)``-style row queries."""
         lib = self._ensure(weights, build=False)
-        src = _lib.as_i32([self._resolve(s) for s in sources])
+        src = self.dev_ids([self._resolve(s) for s in sources])
         out = np.empty((len(src), self.n), dtype=np.float64)
         _lib.check(lib.drs_sssp_batch(self._handle, self.mode, len(src), _lib.ptr_i32(src), _lib.ptr_f64(out)), lib)
-        return out
+        return self.host_cols(out)
 
     def dist_rows(self, row0, nrows, weights=None):
+        """Rows row0 .. row0+nrows-1 of the travel-time matrix (caller's numbering, float64, inf = unreachable)."""
         lib = self._ensure(weights)
+        if self._new_of_old is None:
+            out = np.empty((nrows, self.n), dtype=np.float64)
+            _lib.check(lib.drs_apsp_rows_to_host(self._handle, int(row0), int(nrows), _lib.ptr_f64(out)), lib)
+            return out
+        dev = self.dev_ids(np.arange(row0, row0 + nrows))
+        if nrows * 4 >= self.n:                   # most of the matrix: one copy, then reorder on the host
+            full = np.empty((self.n, self.n), dtype=np.float64)
+            _lib.check(lib.drs_apsp_rows_to_host(self._handle, 0, self.n, _lib.ptr_f64(full)), lib)
+            return self.host_cols(full[dev])
         out = np.empty((nrows, self.n), dtype=np.float64)
-        _lib.check(lib.drs_apsp_rows_to_host(self._handle, int(row0), int(nrows), _lib.ptr_f64(out)), lib)
-        return out
+        for k, r in enumerate(dev):
+            _lib.check(lib.drs_apsp_rows_to_host(self._handle, int(r), 1, _lib.ptr_f64(out[k:k + 1])), lib)
+        return self.host_cols(out)
 
 
 class RoutingEngine(object):

@@ -262,8 +262,10 @@ def test_c3_full_size_certificate_and_properties():
             b = min(n, a + blk)
             assert bool((D[a:b, :n] <= colk[a:b, None] + rowk[None, :]).all())
     # certificate on sampled rows (integer weights: every sum is exact in fp32)
-    src = torch.as_tensor(np.concatenate([data.src, data.dst]).astype(np.int64), device="cuda")
-    dst = torch.as_tensor(np.concatenate([data.dst, data.src]).astype(np.int64), device="cuda")
+    # the raw matrix is in the library's vertex numbering: translate the arc endpoints
+    esrc, edst = G.dev_ids(data.src), G.dev_ids(data.dst)
+    src = torch.as_tensor(np.concatenate([esrc, edst]).astype(np.int64), device="cuda")
+    dst = torch.as_tensor(np.concatenate([edst, esrc]).astype(np.int64), device="cuda")
     w = torch.as_tensor(np.concatenate([data.eattrs["ttmedian"]] * 2).astype(np.float32), device="cuda")
     sample = rs.choice(n, 1024, replace=False)
     for a in range(0, len(sample), 256):
@@ -280,7 +282,8 @@ def test_c3_full_size_certificate_and_properties():
     assert np.array_equal(np.stack([G.dist_rows(int(i), 1)[0] for i in idx]), O.dist_rows(idx))
     s = rs.randint(0, n, 2000).astype(np.int32); t = rs.randint(0, n, 2000).astype(np.int32)
     tt, ln, hops = G.path_sums(s, t)
-    want = D[torch.as_tensor(s.astype(np.int64), device="cuda"), torch.as_tensor(t.astype(np.int64), device="cuda")].double().cpu().numpy()
+    want = D[torch.as_tensor(G.dev_ids(s).astype(np.int64), device="cuda"),
+             torch.as_tensor(G.dev_ids(t).astype(np.int64), device="cuda")].double().cpu().numpy()
     assert np.array_equal(tt, want) and np.array_equal(ln, 10.0 * tt) and int(hops.max()) > 100
     del D
     G.close()
