@@ -347,3 +347,29 @@ def test_query_before_build_and_bad_arguments():
     assert lib.drs_query_pairs(h, 1, _lib.ptr_i32(s), _lib.ptr_i32(t3), _lib.ptr_f64(out), None, _lib.ptr_i32(hops)) == 0
     assert hops[0] == -1
     lib.drs_graph_destroy(h)
+
+
+def test_device_numbering_does_not_change_any_answer():
+    """The same map under the locality numbering (default), the caller's numbering, and with its coordinates withheld
+    from the numbering (reverse Cuthill-McKee fallback): identical matrices, path sums and edge paths."""
+    from drs_abm_b200 import synth
+    from drs_abm_b200.gml import RoadGraphData
+    from drs_abm_b200.routing import RoadGraph, locality_order
+    data = synth.config_graph("C1_uniform")                       # all ties: paths are decided by the canonical rule alone
+    graphs = [RoadGraph(data), RoadGraph(data, numbering="input"), RoadGraph(data)]
+    order = locality_order(data.n, data.src, data.dst, None, None)          # the third graph is numbered by the RCM fallback
+    graphs[2]._old_of_new = np.ascontiguousarray(order, dtype=np.int32)
+    graphs[2]._new_of_old = np.empty(data.n, dtype=np.int32); graphs[2]._new_of_old[order] = np.arange(data.n, dtype=np.int32)
+    o, d = synth.random_od_pairs(data.n, 300, 4)
+    ref = None
+    for G in graphs:
+        got = (G.dist_rows(0, G.n), G.dist_rows(37, 3), G.path_sums(o, d), [G.epath(int(a), int(b)) for a, b in zip(o[:40], d[:40])],
+               G.sssp([0, 123, 399]), G.matrix_lookup(o, d))
+        if ref is None:
+            ref = got
+        else:
+            assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]) and got[3] == ref[3]
+            assert all(np.array_equal(a, b) for a, b in zip(got[2], ref[2]))
+            assert np.array_equal(got[4], ref[4]) and np.array_equal(got[5], ref[5])
+        G.close()
+    assert np.array_equal(ref[1], ref[0][37:40]) and np.array_equal(ref[4], ref[0][[0, 123, 399]])

@@ -167,3 +167,34 @@ def test_draw_link_travel_time_matches_the_oracle_stream():
     assert ours.generateRandomLocation().index == ref.generateRandomLocation().index
     d = ours.get_distance_duration(-71.1, 42.3, -71.09, 42.31, euclidean=True)
     assert d == ref.get_distance_duration(-71.1, 42.3, -71.09, 42.31, euclidean=True) and d[1] == d[0] / 9
+
+
+def test_locality_numbering_is_a_permutation_with_fallback():
+    """Device numbering of the vertices (routing.locality_order): a permutation in every case; a regular grid gets its
+    exact Z-curve; maps without usable coordinates fall back to reverse Cuthill-McKee; the translation helpers of
+    RoadGraph invert each other and reject out-of-range ids like igraph does."""
+    from drs_abm_b200 import synth
+    from drs_abm_b200.routing import RoadGraph, locality_order
+    data = synth.config_graph("C1")
+    lng, lat = data.vattrs["lng"], data.vattrs["lat"]
+    order = locality_order(data.n, data.src, data.dst, lng, lat)
+    assert sorted(order.tolist()) == list(range(data.n))
+    assert order[:8].tolist() == [0, 20, 1, 21, 40, 60, 41, 61]          # Z-curve over the 20 x 20 grid (node = 20 * i + j)
+    for bad in ((None, None), (["a"] * data.n, lat), ([0.0] * data.n, [0.0] * data.n), (lng[:5], lat[:5]),
+                ([float("nan")] * data.n, lat)):
+        o = locality_order(data.n, data.src, data.dst, *bad)
+        assert sorted(o.tolist()) == list(range(data.n))
+    assert locality_order(3, [], [], None, None).tolist() == [0, 1, 2]
+    G = RoadGraph(data)
+    ids = np.array([0, 5, 399, 17], dtype=np.int32)
+    dev = G.dev_ids(ids)
+    assert dev.dtype == np.int32 and sorted(G.dev_ids(np.arange(data.n)).tolist()) == list(range(data.n))
+    rows = np.arange(2 * 512, dtype=np.float64).reshape(2, 512)          # two padded "device rows": value = device column
+    assert np.array_equal(G.host_cols(rows)[0, ids], dev.astype(np.float64)) and G.host_cols(rows).shape == (2, data.n)
+    for bad_ids in ([-1], [data.n], [0, 400]):
+        with pytest.raises(ValueError):
+            G.dev_ids(bad_ids)
+    Gi = RoadGraph(data, numbering="input")
+    assert np.array_equal(Gi.dev_ids(ids), ids) and np.array_equal(Gi.host_cols(rows), rows[:, :data.n])
+    with pytest.raises(ValueError):
+        RoadGraph(data, numbering="sorted")
