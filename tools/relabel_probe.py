@@ -28,6 +28,24 @@ def morton(x, y):
     return spread(x) | (spread(y) << 1)
 
 
+def hilbert(x, y, bits=8):
+    """Hilbert-curve index of integer grid points (vectorised xy2d)."""
+    x = x.astype(np.int64).copy(); y = y.astype(np.int64).copy()
+    d = np.zeros_like(x)
+    s = 1 << (bits - 1)
+    while s > 0:
+        rx = ((x & s) > 0).astype(np.int64)
+        ry = ((y & s) > 0).astype(np.int64)
+        d += s * s * ((3 * rx) ^ ry)
+        # rotate
+        flip = (ry == 0) & (rx == 1)
+        x = np.where(flip, s - 1 - x, x); y = np.where(flip, s - 1 - y, y)
+        swap = ry == 0
+        x, y = np.where(swap, y, x), np.where(swap, x, y)
+        s >>= 1
+    return d
+
+
 def bfs_order():
     import scipy.sparse as sp
     from scipy.sparse.csgraph import breadth_first_order
@@ -48,6 +66,8 @@ orders = {
     "as generated (row-major)": np.arange(n),
     "random": np.random.RandomState(0).permutation(n),
     "morton": np.argsort(morton(lng, lat), kind="stable"),
+    "hilbert": np.argsort(hilbert(lng, lat), kind="stable"),
+    "morton of 2x-coarse cells, row-major inside": np.argsort(morton(lng // 2, lat // 2) * 4 + (lat % 2) * 2 + (lng % 2), kind="stable"),
     "tiles 4x2": np.argsort((lat // 2) * 100000 * 8 + (lng // 4) * 8 + (lat % 2) * 4 + (lng % 4), kind="stable"),
     "tiles 8x4": np.argsort((lat // 4) * 100000 * 32 + (lng // 8) * 32 + (lat % 4) * 8 + (lng % 8), kind="stable"),
     "bfs": bfs_order(),
