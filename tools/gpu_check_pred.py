@@ -6,7 +6,7 @@ from drs_abm_b200 import _lib, synth
 from drs_abm_b200.routing import RoadGraph
 lib = _lib.load()
 data = synth.config_graph("C3")
-G = RoadGraph(data); G.build()
+G = RoadGraph(data, numbering="input"); G.build()
 dist = C.c_void_p(); pred = C.c_void_p(); ld = C.c_int64()
 _lib.check(lib.drs_apsp_matrices(G._handle, C.byref(dist), C.byref(pred), C.byref(ld)))
 out = torch.empty((ld.value, ld.value), dtype=torch.int32, device="cuda")

@@ -14,9 +14,9 @@ from drs_abm_b200.routing import RoadGraph
 lib = _lib.load()
 for name in sys.argv[1:] or ["C2", "C3"]:
     data = synth.config_graph(name)
-    Gf = RoadGraph(data, algorithm=_lib.APSP_FW)
+    Gf = RoadGraph(data, algorithm=_lib.APSP_FW, numbering="input")
     t0 = time.time(); Gf.build(); t_fw = time.time() - t0
-    Gs = RoadGraph(data, algorithm=_lib.APSP_SSSP)
+    Gs = RoadGraph(data, algorithm=_lib.APSP_SSSP, numbering="input")
     t0 = time.time(); Gs.build(); t_s1 = time.time() - t0
     Gs._valid = False
     t0 = time.time(); Gs.build(); t_s2 = time.time() - t0

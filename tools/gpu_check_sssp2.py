@@ -7,7 +7,7 @@ from drs_abm_b200.routing import RoadGraph
 lib = _lib.load()
 data = synth.config_graph(sys.argv[1] if len(sys.argv) > 1 else "C3")
 mults = [float(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [6.0]
-G = RoadGraph(data)
+G = RoadGraph(data, numbering="input")
 h = G.upload()
 npad = (data.n + 127) // 128 * 128
 buf = torch.empty((npad, npad), dtype=torch.float32, device="cuda")
