@@ -612,9 +612,12 @@ extern "C" int drs_tick_set_vehicles(drs_tick* t, const drs_vehicle_batch* b) {
   int rc;
   std::vector<int32_t> perm(std::max(nv, 1));
   for (int v = 0; v < nv; ++v) perm[v] = v;
-  // longest plans first: their ordering searches are the long ones and should not form the tail of the launch
+  // longest plans first: their ordering searches are the long ones and should not form the tail of the launch;
+  // within a plan length by start vertex, so that neighbouring lanes gather neighbouring columns of a request's
+  // matrix row (vertex ids are spatially coherent under the host layer's locality numbering)
   std::stable_sort(perm.begin(), perm.begin() + nv, [&](int x, int y) {
-    return (b->stop_off[x + 1] - b->stop_off[x]) > (b->stop_off[y + 1] - b->stop_off[y]);
+    const int lx = b->stop_off[x + 1] - b->stop_off[x], ly = b->stop_off[y + 1] - b->stop_off[y];
+    return lx != ly ? lx > ly : b->start_node[x] < b->start_node[y];
   });
   if ((rc = upload(&d.v_perm, perm.data(), nv, st))) return rc;
   d.directed = t->g->directed;

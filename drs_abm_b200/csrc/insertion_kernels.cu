@@ -445,11 +445,13 @@ extern "C" int drs_tick_set_plans(drs_tick* t, const drs_plan_batch* b, const dr
       (rc = drs_upload(&d.q_cld, q->Cld, nq, st)) || (rc = drs_upload(&d.q_ts, q->Ts, nq, st)) ||
       (rc = drs_upload(&d.q_tr, q->Tr, nq, st)) || (rc = drs_upload(&d.q_pwt, q->pwt, nq, st)))
     return rc;
-  // slot-major copy, vehicles stably sorted by plan length
+  // slot-major copy, vehicles sorted by plan length, then by start vertex (neighbouring lanes gather neighbouring
+  // columns of the request's rows: vertex ids are spatially coherent under the host layer's locality numbering)
   std::vector<int32_t> perm(std::max(nv, 1));
   for (int v = 0; v < nv; ++v) perm[v] = v;
   std::stable_sort(perm.begin(), perm.begin() + nv, [&](int x, int y) {
-    return (b->stop_off[x + 1] - b->stop_off[x]) < (b->stop_off[y + 1] - b->stop_off[y]);
+    const int lx = b->stop_off[x + 1] - b->stop_off[x], ly = b->stop_off[y + 1] - b->stop_off[y];
+    return lx != ly ? lx < ly : b->start_node[x] < b->start_node[y];
   });
   const size_t slots = (size_t)(MAXL + 1) * std::max(nv, 1);
   std::vector<int32_t> m_node(slots, 0), m_req(slots, 0);
