@@ -341,7 +341,8 @@ __global__ void __launch_bounds__(128) insertion_scan_kernel(PlanView pv, DistVi
 }
 
 // Fold: one WARP per request.  Lanes read the smallest costs of 32 consecutive
-// vehicles; only flagged vehicles are re-scanned (by their lane) in vehicle order with the running bound.
+// vehicles (four chunks ahead: the walk is a chain of dependent decisions, the loads are not); only flagged vehicles
+// are re-scanned (by their lane) in vehicle order with the running bound.
 __global__ void insertion_fold_kernel(PlanView pv, DistView dv, int n_new, const int32_t* new_rows, const double* cmin,
                                        int32_t* best_veh, int32_t* best_i, int32_t* best_j, double* best_dc) {
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -350,31 +351,41 @@ __global__ void insertion_fold_kernel(PlanView pv, DistView dv, int n_new, const
   const double inf = __longlong_as_double(0x7ff0000000000000LL);
   double dc = inf;                   // dc_ = np.inf (:1452)
   int wv = -1, wi = -1, wj = -1;
-  for (int base = 0; base < pv.n_veh; base += 32) {
-    const int v = base + lane;
-    double cm = inf, c0 = 0.0;
-    if (v < pv.n_veh) { cm = cmin[(int64_t)r * pv.n_veh + v]; c0 = pv.cost[v]; }
-    unsigned mask = __ballot_sync(0xffffffffu, cm != inf && !(cm > c0 + dc));
-    while (mask) {
-      const int l = __ffs(mask) - 1;
-      mask &= mask - 1;
-      double ndc = dc; int nv = wv, ni = wi, nj = wj;
-      if (lane == l && !(cm > c0 + dc)) {              // re-check: dc may have dropped inside this chunk
-        Pair p;
-        load_pair(p, pv, dv, v, new_rows[r]);
-        int viol = -1;
-        for (int i = 0; i <= p.L; ++i) {                         // (:1466-1482)
-          for (int j = i + 1; j <= p.L + 1; ++j) {
-            double c;
-            viol = eval_candidate(p, pv, i, j - 1, c0 + ndc, &c);
-            if (viol < 0) { ndc = c - c0; nv = v; ni = i; nj = j; }
-            if (viol > 0) break;
+  constexpr int AHEAD = 8;   // chunks of 32 vehicles whose costs are loaded together: the loads do not depend on the incumbent
+  for (int base0 = 0; base0 < pv.n_veh; base0 += 32 * AHEAD) {
+    double cms[AHEAD], c0s[AHEAD];
+#pragma unroll
+    for (int u = 0; u < AHEAD; ++u) {
+      const int v = base0 + 32 * u + lane;
+      cms[u] = inf; c0s[u] = 0.0;
+      if (v < pv.n_veh) { cms[u] = cmin[(int64_t)r * pv.n_veh + v]; c0s[u] = pv.cost[v]; }
+    }
+#pragma unroll
+    for (int u = 0; u < AHEAD; ++u) {
+      const int v = base0 + 32 * u + lane;
+      const double cm = cms[u], c0 = c0s[u];
+      unsigned mask = __ballot_sync(0xffffffffu, cm != inf && !(cm > c0 + dc));
+      while (mask) {
+        const int l = __ffs(mask) - 1;
+        mask &= mask - 1;
+        double ndc = dc; int nv = wv, ni = wi, nj = wj;
+        if (lane == l && !(cm > c0 + dc)) {              // re-check: dc may have dropped inside this chunk
+          Pair p;
+          load_pair(p, pv, dv, v, new_rows[r]);
+          int viol = -1;
+          for (int i = 0; i <= p.L; ++i) {                         // (:1466-1482)
+            for (int j = i + 1; j <= p.L + 1; ++j) {
+              double c;
+              viol = eval_candidate(p, pv, i, j - 1, c0 + ndc, &c);
+              if (viol < 0) { ndc = c - c0; nv = v; ni = i; nj = j; }
+              if (viol > 0) break;
+            }
+            if (viol == 2) break;
           }
-          if (viol == 2) break;
         }
+        dc = __shfl_sync(0xffffffffu, ndc, l); wv = __shfl_sync(0xffffffffu, nv, l);
+        wi = __shfl_sync(0xffffffffu, ni, l); wj = __shfl_sync(0xffffffffu, nj, l);
       }
-      dc = __shfl_sync(0xffffffffu, ndc, l); wv = __shfl_sync(0xffffffffu, nv, l);
-      wi = __shfl_sync(0xffffffffu, ni, l); wj = __shfl_sync(0xffffffffu, nj, l);
     }
   }
   if (lane == 0) { best_veh[r] = wv; best_i[r] = wi; best_j[r] = wj; best_dc[r] = dc; }
