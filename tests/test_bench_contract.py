@@ -42,3 +42,20 @@ def test_our_arm_line_on_c1():
     assert "workload" in d["config"] and "model" not in d["config"]
     assert d["fw"]["same_matrix_as_headline"] is True                       # SSSP and Floyd-Warshall agree
     assert d["insertion"]["value"] > 0 and d["insertion"]["roofline"]["bound"] == "hbm"
+
+
+@pytest.mark.parametrize("fname", ["r01_bench_c3_n1.json", "r01_bench_c3_n2.json", "r01_bench_c3_n4.json", "r01_bench_c3_n8.json"])
+def test_committed_bench_lines_keep_the_contract(fname):
+    """The bench lines committed under profiles/ (measured on B200s) carry the contract's keys and are self-consistent."""
+    d = json.load(open(os.path.join(ROOT, "profiles", fname)))
+    assert BASE_KEYS - {"cpu_baseline"} | {"roofline", "gpu_launches", "clocks"} <= set(d)
+    assert d["metric"] == "apsp_build_seconds" and d["unit"] == "s" and d["higher_is_better"] is False and d["vs_baseline"] is None
+    assert d["n_gpus"] == int(fname.split("_n")[1].split(".")[0]) and d["warmup"] >= 3
+    assert abs(d["ms_per_step"] - 1e3 * d["value"]) < 1e-6 and d["gpu_launches"] > 0
+    r = d["roofline"]
+    assert r["bound"] in ("hbm", "tensor", "alu") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert d["clocks"]["reasons"] == [] and d["clocks"]["sm_mhz"] >= 0.95 * d["clocks"]["sm_max_mhz"]
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["value"] >= d["value"]
+    assert d["fw"]["same_matrix_as_headline"] is True and d["checksum"] == 12082473595208.0
+    if d["n_gpus"] == 1:
+        assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"]) and r["traffic"] > 0
