@@ -18,6 +18,7 @@
 // bit patterns); the adjacency of a vertex is one 32-byte ELL record of four
 // (target, weight) slots, read with two 16-byte loads.
 #include <algorithm>
+#include <cstring>
 #include <limits>
 #include <vector>
 
@@ -32,14 +33,18 @@ template <> struct Dist<float> {
   static __device__ __forceinline__ float weight(int bits) { return __int_as_float(bits); }
   static __device__ __forceinline__ int key(float d) { return __float_as_int(d); }
   static __device__ __forceinline__ float unkey(int k) { return __int_as_float(k); }
-  static __device__ __forceinline__ float next_theta(float dmin, float delta) { return (floorf(dmin / delta) + 1.0f) * delta; }
+  // bucket boundary above dmin; clamped to the next float above dmin so that the smallest FAR entry always moves to
+  // NEAR (rounding of floorf(dmin/delta)*delta, or dmin/delta >= 2^24, could otherwise leave theta <= dmin: no progress)
+  static __device__ __forceinline__ float next_theta(float dmin, float delta) {
+    return fmaxf((floorf(dmin / delta) + 1.0f) * delta, __int_as_float(__float_as_int(dmin) + 1));
+  }
 };
 template <> struct Dist<int> {
   static __device__ __forceinline__ int inf() { return DRS_I32_INF; }
   static __device__ __forceinline__ int weight(int bits) { return (int)__int_as_float(bits); }
   static __device__ __forceinline__ int key(int d) { return d; }
   static __device__ __forceinline__ int unkey(int k) { return k; }
-  static __device__ __forceinline__ int next_theta(int dmin, int delta) { return (dmin / delta + 1) * delta; }
+  static __device__ __forceinline__ int next_theta(int dmin, int delta) { return max((dmin / delta + 1) * delta, dmin + 1); }
 };
 
 #ifndef DRS_SSSP_MIN_THREADS_PER_SM
@@ -53,7 +58,22 @@ constexpr int VERTEX_MASK = (1 << SLOT_SHIFT) - 1;
 #ifndef DRS_SSSP_NQ
 #define DRS_SSSP_NQ 512
 #endif
+#ifndef DRS_SSSP_DEFAULT_SMEM
+#define DRS_SSSP_DEFAULT_SMEM 0   // which variant drs_sssp_batch_dev picks when DRS_SSSP_IMPL is unset
+#endif
+#ifndef DRS_SSSP_SMEM_DELTA_MULT
+#define DRS_SSSP_SMEM_DELTA_MULT 24.0
+#endif
 constexpr int SSSP_NQ = DRS_SSSP_NQ;  // NEAR-queue entries held in shared memory per buffer; the rest spills to global (a large carve-out would cost the L1 that caches the adjacency)
+
+// The 32-byte adjacency record of a vertex with ONE 256-bit load (LDG.E.ENL2.256, sm_100): a warp whose lanes hold
+// 32 different vertices then costs the L1TEX pipe 32 wavefronts instead of the 64 of two 128-bit loads -- and both
+// kernels below are bound by exactly those wavefronts (profiles/r02_sssp_step_profile.md).
+__device__ __forceinline__ void ell_load(const int4* __restrict__ ell, int v, int4& r0, int4& r1) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r0.x), "=r"(r0.y), "=r"(r0.z), "=r"(r0.w), "=r"(r1.x), "=r"(r1.y), "=r"(r1.z), "=r"(r1.w)
+               : "l"(ell + 2 * (int64_t)v));
+}
 
 // One CTA advances SSSP_S sources in lock step (S = 1 by default): their wavefronts pass the same distance
 // buckets at the same time, so one near queue / far pile / theta serves all of them.
@@ -108,7 +128,8 @@ __global__ void __launch_bounds__(SSSP_THREADS, DRS_SSSP_MIN_THREADS_PER_SM / SS
           const int v = en.v & VERTEX_MASK, slot = en.v >> SLOT_SHIFT;
           T* row = rows + (int64_t)slot * row_stride;
           const int kcur = Dist<T>::key(__ldcg(&row[v]));   // L2 read: the atomics live there
-          const int4 r0 = ell[2 * v], r1 = ell[2 * v + 1];
+          int4 r0, r1;
+          ell_load(ell, v, r0, r1);
           if (kcur != en.key) continue;                      // stale: a shorter distance arrived later
           const int2 arc[SSSP_D] = {make_int2(r0.x, r0.y), make_int2(r0.z, r0.w), make_int2(r1.x, r1.y), make_int2(r1.z, r1.w)};
           int nk[SSSP_D], old[SSSP_D];
@@ -188,6 +209,244 @@ __global__ void __launch_bounds__(SSSP_THREADS, DRS_SSSP_MIN_THREADS_PER_SM / SS
     }
     __syncthreads();
   }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Shared-memory-resident variant: the distance row of the source being searched lives in the CTA's shared
+// memory (4*ld bytes: 200 704 B for the 50k-node map, which fits the 227 KB a B200 CTA can own), so the stale
+// check, the target reads and the atomicMins of every relaxation are shared-memory operations (~30 cycles)
+// instead of L2 round trips (~250 cycles each, three dependent ones per wavefront step in the kernel above),
+// and the finished row leaves the SM once, as one coalesced 16-byte-per-lane store (DRAM sees the matrix
+// exactly once).  What stays in global memory: the ELL adjacency record of each visited vertex (read-only,
+// L2/L1), the FAR pile, and the overflow of the NEAR queues.
+//
+// One barrier per wavefront step: the NEAR queues alternate between two buffers, their fill counts rotate
+// through three words (step r reads count r%3, appends to (r+1)%3 and clears (r+2)%3), and appends are
+// warp-aggregated (one shared-memory atomicAdd per warp and arc slot).
+#ifdef DRS_SSSP_PROFILE
+// cycle totals of thread 0 of every CTA: [0] steps, [1] whole wavefront steps, [2] queue entries of those steps, [6] far phases,
+// [7] row write-out, [8] whole kernel
+__device__ unsigned long long g_sssp_prof[16];
+#define SSSP_PROF_T(x) const long long x = clock64()
+#define SSSP_PROF_ADD(i, v) do { if (threadIdx.x == 0) prof[i] += (unsigned long long)(v); } while (0)
+#else
+#define SSSP_PROF_T(x)
+#define SSSP_PROF_ADD(i, v)
+#endif
+
+// FAR = false compiles the one-bucket form (Bellman-Ford-Moore wavefronts: every improved vertex goes to the next
+// NEAR queue, no FAR pile, no theta), which is what an "infinite" bucket width selects.
+template <typename T, int THREADS, bool FAR>
+__global__ void __launch_bounds__(THREADS, 1) sssp_smem_kernel(
+    int n, const int32_t* __restrict__ out_ptr, const int2* __restrict__ arcs, const int4* __restrict__ ell, T* dist, int64_t ld,
+    int64_t row_stride, const int32_t* __restrict__ sources, int nsrc, Entry* queues, int cap, T delta, int* overflow, int qn) {
+  extern __shared__ __align__(16) unsigned char sssp_smem[];
+  T* row = reinterpret_cast<T*>(sssp_smem);
+  int* irow = reinterpret_cast<int*>(sssp_smem);
+  Entry* s_q = reinterpret_cast<Entry*>(sssp_smem + sizeof(T) * ld);   // two NEAR buffers of qn entries
+  __shared__ int s_cnt[3], s_far, s_keep, s_min, s_group;
+  int* next_group = overflow + 1;
+  Entry* gq = queues + (int64_t)blockIdx.x * 4 * cap;                  // their overflow: two buffers of cap entries
+  Entry* far = gq + 2 * (int64_t)cap;
+  Entry* far2 = far + cap;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  auto q_put = [&](int which, int pos, Entry e) {
+    if (pos < qn) s_q[which * qn + pos] = e;
+    else if (pos - qn < cap) gq[(int64_t)which * cap + pos - qn] = e;
+    else *overflow = 1;
+  };
+  auto q_get = [&](int which, int pos) { return pos < qn ? s_q[which * qn + pos] : gq[(int64_t)which * cap + pos - qn]; };
+  const T inf = Dist<T>::inf();
+#ifdef DRS_SSSP_PROFILE
+  unsigned long long prof[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  const long long prof_t0 = clock64();
+#endif
+  // the row starts as +inf everywhere; after every search it is written out and reset in the same sweep
+  for (int64_t t = tid; t < ld; t += THREADS) row[t] = inf;
+  while (true) {
+    __syncthreads();
+    if (tid == 0) s_group = atomicAdd(next_group, 1);
+    __syncthreads();
+    const int k = s_group;
+    if (k >= nsrc) break;
+    if (tid == 0) {
+      const int src = sources[k];
+      row[src] = (T)0;
+      s_q[0] = Entry{src, Dist<T>::key((T)0)};
+      s_cnt[0] = 1; s_cnt[1] = 0; s_cnt[2] = 0; s_far = 0;
+    }
+    T theta = delta;
+    int buf = 0, c_rd = 0;             // queue buffer being read; index of its count word
+    while (true) {
+      // ---- wavefront steps of the current bucket
+      while (true) {
+        SSSP_PROF_T(pa);
+        __syncthreads();
+        const int nn = min(s_cnt[c_rd], qn + cap);
+        const int c_wr = c_rd == 2 ? 0 : c_rd + 1, c_clr = c_wr == 2 ? 0 : c_wr + 1;
+        if (tid == 0) s_cnt[c_clr] = 0;
+        if (nn == 0) break;
+        // warps without queue entries go straight to the next barrier: the step is bound by instruction issue
+        for (int base = tid - lane; base < nn; base += THREADS) {
+          SSSP_PROF_T(p0);
+          const int e = base + lane;
+          Entry en{0, 0};
+          if (e < nn) en = q_get(buf, e);
+          bool live = false;
+          int4 r0 = make_int4(-1, 0, -1, 0), r1 = make_int4(-1, 0, -1, 0);
+          if (e < nn) {
+            ell_load(ell, en.v, r0, r1);
+            live = irow[en.v] == en.key;                 // stale otherwise: a shorter distance arrived later
+          }
+          const int tg[SSSP_D] = {r0.x, r0.z, r1.x, r1.z};
+          const int wb[SSSP_D] = {r0.y, r0.w, r1.y, r1.w};
+#ifdef DRS_SSSP_PROFILE
+          if (tg[0] == -12345 && tg[3] == -12345 && live) prof[9] += 1;   // consume the loads before the time stamp
+#endif
+          SSSP_PROF_T(p1);
+          SSSP_PROF_ADD(3, p1 - p0);
+          int nk[SSSP_D];
+          bool push[SSSP_D];
+#pragma unroll
+          for (int j = 0; j < SSSP_D; ++j) {
+            nk[j] = Dist<T>::key(Dist<T>::unkey(en.key) + Dist<T>::weight(wb[j]));
+            push[j] = live && tg[j] >= 0 && nk[j] < irow[max(tg[j], 0)];
+          }
+#ifdef DRS_SSSP_PROFILE
+          if (push[0] && push[1] && push[2] && push[3] && nk[0] == -12345) prof[9] += 1;
+#endif
+          SSSP_PROF_T(p2);
+          SSSP_PROF_ADD(4, p2 - p1);
+#pragma unroll
+          for (int j = 0; j < SSSP_D; ++j)
+            if (push[j]) push[j] = nk[j] < atomicMin(irow + tg[j], nk[j]);
+#ifdef DRS_SSSP_PROFILE
+          if (push[0] && push[1] && push[2] && push[3] && nk[0] == -12345) prof[9] += 1;
+#endif
+          SSSP_PROF_T(p3);
+          SSSP_PROF_ADD(5, p3 - p2);
+          // appends: one counter atomic per warp (and per pile)
+          bool nearp[SSSP_D];
+          unsigned mn[SSSP_D];
+          int total = 0;
+#pragma unroll
+          for (int j = 0; j < SSSP_D; ++j) {
+            nearp[j] = push[j] && (!FAR || Dist<T>::unkey(nk[j]) < theta);
+            mn[j] = __ballot_sync(0xffffffffu, nearp[j]);
+            total += __popc(mn[j]);
+          }
+          if (total) {
+            int b0 = 0;
+            if (lane == 0) b0 = atomicAdd(&s_cnt[c_wr], total);
+            b0 = __shfl_sync(0xffffffffu, b0, 0);
+#pragma unroll
+            for (int j = 0; j < SSSP_D; ++j) {
+              if (nearp[j]) q_put(buf ^ 1, b0 + __popc(mn[j] & lt_mask), Entry{tg[j], nk[j]});
+              b0 += __popc(mn[j]);
+            }
+          }
+          if (FAR) {
+            unsigned mf[SSSP_D];
+            int totf = 0;
+#pragma unroll
+            for (int j = 0; j < SSSP_D; ++j) {
+              mf[j] = __ballot_sync(0xffffffffu, push[j] && !nearp[j]);
+              totf += __popc(mf[j]);
+            }
+            if (totf) {
+              int b0 = 0;
+              if (lane == 0) b0 = atomicAdd(&s_far, totf);
+              b0 = __shfl_sync(0xffffffffu, b0, 0);
+#pragma unroll
+              for (int j = 0; j < SSSP_D; ++j) {
+                if (push[j] && !nearp[j]) {
+                  const int pos = b0 + __popc(mf[j] & lt_mask);
+                  if (pos < cap) far[pos] = Entry{tg[j], nk[j]}; else *overflow = 1;
+                }
+                b0 += __popc(mf[j]);
+              }
+            }
+          }
+          SSSP_PROF_T(p4);
+          SSSP_PROF_ADD(9, p4 - p3);
+          if (live && tg[SSSP_D - 1] == -2) {                // high-degree vertex: the remaining arcs live in the CSR
+            const int a1 = out_ptr[en.v + 1];
+            for (int a = wb[SSSP_D - 1]; a < a1; ++a) {
+              const int2 ar = arcs[a];
+              const int k2 = Dist<T>::key(Dist<T>::unkey(en.key) + Dist<T>::weight(ar.y));
+              if (k2 < irow[ar.x] && k2 < atomicMin(irow + ar.x, k2)) {
+                const Entry ne{ar.x, k2};
+                if (!FAR || Dist<T>::unkey(k2) < theta) {
+                  q_put(buf ^ 1, atomicAdd(&s_cnt[c_wr], 1), ne);
+                } else {
+                  const int pos = atomicAdd(&s_far, 1);
+                  if (pos < cap) far[pos] = ne; else *overflow = 1;
+                }
+              }
+            }
+          }
+        }
+        buf ^= 1;
+        c_rd = c_wr;
+        SSSP_PROF_T(pb);
+        SSSP_PROF_ADD(0, 1);
+        SSSP_PROF_ADD(1, pb - pa);
+        SSSP_PROF_ADD(2, nn);
+      }
+      if (!FAR) break;
+      // ---- NEAR is empty (its count word c_rd reads 0): advance theta to the bucket of the smallest valid FAR entry
+      SSSP_PROF_T(pf0);
+      const int nf = min(s_far, cap);
+      if (nf == 0) break;
+      if (tid == 0) { s_min = 0x7fffffff; s_keep = 0; }
+      __syncthreads();
+      int lmin = 0x7fffffff;
+      for (int e = tid; e < nf; e += THREADS) {
+        const Entry en = far[e];
+        if (irow[en.v] == en.key) lmin = min(lmin, en.key);
+      }
+      for (int off = 16; off > 0; off >>= 1) lmin = min(lmin, __shfl_down_sync(0xffffffffu, lmin, off));
+      if (lane == 0 && lmin != 0x7fffffff) atomicMin(&s_min, lmin);
+      __syncthreads();
+      const int kmin = s_min;
+      if (kmin == 0x7fffffff) break;   // only stale entries left
+      theta = Dist<T>::next_theta(Dist<T>::unkey(kmin), delta);
+      for (int e = tid; e < nf; e += THREADS) {
+        const Entry en = far[e];
+        if (irow[en.v] != en.key) continue;
+        if (Dist<T>::unkey(en.key) < theta) q_put(buf, atomicAdd(&s_cnt[c_rd], 1), en);
+        else far2[atomicAdd(&s_keep, 1)] = en;
+      }
+      __syncthreads();
+      if (tid == 0) s_far = s_keep;
+      Entry* tmp = far; far = far2; far2 = tmp;
+      SSSP_PROF_T(pf1);
+      SSSP_PROF_ADD(6, pf1 - pf0);
+    }
+    // ---- the row is final: one coalesced sweep writes it out and resets the shared copy
+    SSSP_PROF_T(pw0);
+    __syncthreads();
+    {
+      T* out = dist + (int64_t)k * row_stride;
+      const int4 inf4 = make_int4(Dist<T>::key(inf), Dist<T>::key(inf), Dist<T>::key(inf), Dist<T>::key(inf));
+      int4* r4 = reinterpret_cast<int4*>(row);
+      int4* o4 = reinterpret_cast<int4*>(out);
+      for (int t = tid; t < (int)(ld / 4); t += THREADS) {
+        __stcs(&o4[t], r4[t]);       // streaming store: the row is not read again by this kernel
+        r4[t] = inf4;
+      }
+    }
+    SSSP_PROF_T(pw1);
+    SSSP_PROF_ADD(7, pw1 - pw0);
+  }
+#ifdef DRS_SSSP_PROFILE
+  if (tid == 0) {
+    prof[8] = (unsigned long long)(clock64() - prof_t0);
+    for (int i = 0; i < 10; ++i) atomicAdd(&g_sssp_prof[i], prof[i]);
+  }
+#endif
 }
 
 // rows >= n of the padded matrix: 0 on the diagonal, inf elsewhere (what drs_fw_init writes)
@@ -276,6 +535,57 @@ int sssp_run(const drs_graph* g, int nsrc, const int32_t* sources_dev, T* dist, 
   return DRS_OK;
 }
 
+
+// ---- launch of the shared-memory-resident variant
+int sssp_env_int(const char* name, int dflt) {   // read at every call: the probes change these between builds
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+constexpr int SSSP_SMEM_LIMIT = 227 * 1024 - 256;   // dynamic shared memory a CTA may own on sm_100, minus the kernel's static words
+
+// NEAR-queue entries per buffer that fit beside the row (0: the row does not fit -> L2 variant)
+int sssp_smem_qn(int64_t ld, size_t elem) {
+  const int64_t avail = (int64_t)SSSP_SMEM_LIMIT - (int64_t)elem * ld;
+  if (avail < (int64_t)(2 * 64 * sizeof(Entry))) return 0;
+  int qn = (int)std::min<int64_t>(avail / (2 * sizeof(Entry)), 2048);
+  const int want = sssp_env_int("DRS_SSSP_QN", 0);
+  if (want >= 64) qn = std::min(qn, want);
+  return qn / 32 * 32;
+}
+
+int sssp_smem_threads(int n) {
+  const int t = sssp_env_int("DRS_SSSP_SMEM_THREADS", 0);
+  if (t == 128 || t == 256 || t == 512 || t == 1024) return t;
+  return n <= 2048 ? 128 : (n <= 16384 ? 256 : 1024);
+}
+
+template <typename T, int TH, bool FAR>
+int sssp_smem_go(int sms, cudaStream_t st, int n, const int32_t* out_ptr, const int2* arcs, const int4* ell, T* dist, int64_t ld,
+                 int64_t row_stride, const int32_t* sources, int nsrc, Entry* queues, int cap, T delta, int* overflow, int qn, int* grid_out) {
+  const size_t smem = sizeof(T) * (size_t)ld + 2 * (size_t)qn * sizeof(Entry);
+  auto kern = sssp_smem_kernel<T, TH, FAR>;
+  DRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 1;
+  DRS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TH, smem));
+  const int grid = std::max(1, std::min(nsrc, sms * std::max(per_sm, 1)));
+  if (grid_out) { *grid_out = grid; return DRS_OK; }
+  kern<<<grid, TH, smem, st>>>(n, out_ptr, arcs, ell, dist, ld, row_stride, sources, nsrc, queues, cap, delta, overflow, qn);
+  drs_count_launch();
+  DRS_CUDA(cudaGetLastError());
+  return DRS_OK;
+}
+
+template <typename T, typename... A>
+int sssp_smem_dispatch(int threads, bool use_far, A... args) {
+#define DRS_SMEM_CASE(TH) case TH: return use_far ? sssp_smem_go<T, TH, true>(args...) : sssp_smem_go<T, TH, false>(args...);
+  switch (threads) {
+    DRS_SMEM_CASE(128) DRS_SMEM_CASE(256) DRS_SMEM_CASE(512)
+    default: return use_far ? sssp_smem_go<T, 1024, true>(args...) : sssp_smem_go<T, 1024, false>(args...);
+  }
+#undef DRS_SMEM_CASE
+}
+
 }  // namespace
 
 // Distances from `nsrc` sources into rows 0..nsrc-1 of dist_dev (row k <- sources[k]).
@@ -290,18 +600,46 @@ extern "C" int drs_sssp_batch_dev(const drs_graph* g, int32_t mode, int32_t nsrc
   if (nsrc == 0) return DRS_OK;
   DrsDeviceGuard guard(g->device);
   cudaStream_t st = (cudaStream_t)stream;
-  if (delta <= 0) {   // default bucket width: six times the mean arc weight (measured sweet spot on grid cities)
-    double s = 0;
-    for (double w : g->h_tt) s += w;
-    delta = g->m ? 6.0 * s / g->m : 1.0;
-  }
   drs_graph* gm = const_cast<drs_graph*>(g);   // scratch buffers are cached on the handle
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g->device);
-  const int grid = mode == DRS_MODE_F32 ? sssp_grid<float>(sms, nsrc) : sssp_grid<int>(sms, nsrc);
+  // variant: the row in shared memory when it fits (DRS_SSSP_IMPL=l2 forces the L2-resident kernel, =smem insists)
+  const char* impl_env = getenv("DRS_SSSP_IMPL");
+  const int qn = sssp_smem_qn(ld, sizeof(float));
+  // default by measurement (profiles/r02_sssp_step_profile.md): DRS_SSSP_DEFAULT_SMEM
+  const bool want_smem = impl_env ? !strcmp(impl_env, "smem") : (DRS_SSSP_DEFAULT_SMEM != 0);
+  bool use_smem = want_smem && qn > 0 && ld % 4 == 0 && ((uintptr_t)dist_dev & 15) == 0;
+  DRS_REQUIRE(use_smem || !(impl_env && !strcmp(impl_env, "smem")), DRS_ERR_ARG,
+              "drs_sssp_batch_dev: DRS_SSSP_IMPL=smem but a row of %lld elements does not fit in shared memory", (long long)ld);
+  const int smem_threads = sssp_smem_threads(g->n);
+  if (delta <= 0) {
+    // default bucket width, in mean arc weights (measured on grid cities): 6 for the L2-resident rows, where every
+    // re-relaxation is an L2 round trip; wider for the shared-memory rows, where re-relaxations are cheap and the
+    // number of wavefront steps (barriers) is what costs.  DRS_SSSP_DELTA_MULT overrides (0 = one bucket: Bellman-Ford-Moore)
+    double s = 0;
+    for (double w : g->h_tt) s += w;
+    const char* e = getenv("DRS_SSSP_DELTA_MULT");
+    const double mult = e ? atof(e) : (use_smem ? DRS_SSSP_SMEM_DELTA_MULT : 6.0);
+    delta = mult > 0 ? (g->m ? mult * s / g->m : 1.0) : 3.0e38;
+  }
+  const bool use_far = delta < 1.0e30;   // one bucket: the Bellman-Ford-Moore form without a FAR pile
+  const float big_f = 3.0e38f;
+  int grid = 0;
+  if (use_smem) {
+    int rc0 = mode == DRS_MODE_F32
+                  ? sssp_smem_dispatch<float>(smem_threads, true, sms, (cudaStream_t) nullptr, 0, (const int32_t*)nullptr, (const int2*)nullptr,
+                                              (const int4*)nullptr, (float*)nullptr, ld, ld, (const int32_t*)nullptr, nsrc, (Entry*)nullptr, 0,
+                                              0.0f, (int*)nullptr, qn, &grid)
+                  : sssp_smem_dispatch<int>(smem_threads, true, sms, (cudaStream_t) nullptr, 0, (const int32_t*)nullptr, (const int2*)nullptr,
+                                            (const int4*)nullptr, (int*)nullptr, ld, ld, (const int32_t*)nullptr, nsrc, (Entry*)nullptr, 0, 0,
+                                            (int*)nullptr, qn, &grid);
+    if (rc0) return rc0;
+  } else {
+    grid = mode == DRS_MODE_F32 ? sssp_grid<float>(sms, nsrc) : sssp_grid<int>(sms, nsrc);
+  }
   // packed arcs (narcs records) followed by the ELL records (4 per vertex)
-  if (!gm->sssp_arcs) DRS_CUDA(cudaMalloc(&gm->sssp_arcs, sizeof(int2) * ((size_t)std::max(g->narcs, 1) + 1 + (size_t)SSSP_D * g->n)));
-  int2* d_ell = (int2*)gm->sssp_arcs + ((std::max(g->narcs, 1) + 1) & ~1);   // 16-byte aligned
+  if (!gm->sssp_arcs) DRS_CUDA(cudaMalloc(&gm->sssp_arcs, sizeof(int2) * ((size_t)std::max(g->narcs, 1) + 4 + (size_t)SSSP_D * g->n)));
+  int2* d_ell = (int2*)gm->sssp_arcs + ((std::max(g->narcs, 1) + 3) & ~3);   // 32-byte aligned: records are read with one 256-bit load
   if (!gm->sssp_arcs_valid) {
     if (g->narcs) pack_arcs_kernel<<<(g->narcs + 255) / 256, 256, 0, st>>>(g->narcs, g->d_out_col, g->d_out_w, (int2*)gm->sssp_arcs);
     build_ell_kernel<<<(g->n + 255) / 256, 256, 0, st>>>(g->n, g->d_out_ptr, g->d_out_col, g->d_out_w, d_ell);
@@ -332,7 +670,15 @@ extern "C" int drs_sssp_batch_dev(const drs_graph* g, int32_t mode, int32_t nsrc
     }
     cudaMemsetAsync(d_overflow, 0, 2 * sizeof(int), st);   // overflow flag + work counter
     cudaMemcpyAsync(d_sources, sources_host, sizeof(int32_t) * nsrc, cudaMemcpyHostToDevice, st);
-    if (mode == DRS_MODE_F32)
+    if (use_smem && mode == DRS_MODE_F32)
+      rc = sssp_smem_dispatch<float>(smem_threads, use_far, sms, st, g->n, (const int32_t*)g->d_out_ptr, (const int2*)gm->sssp_arcs, (const int4*)d_ell,
+                                     (float*)dist_dev, ld, ld, (const int32_t*)d_sources, nsrc, (Entry*)gm->sssp_queues, cap,
+                                     (float)std::min<double>(delta, big_f), d_overflow, qn, (int*)nullptr);
+    else if (use_smem)
+      rc = sssp_smem_dispatch<int>(smem_threads, use_far, sms, st, g->n, (const int32_t*)g->d_out_ptr, (const int2*)gm->sssp_arcs, (const int4*)d_ell,
+                                   (int*)dist_dev, ld, ld, (const int32_t*)d_sources, nsrc, (Entry*)gm->sssp_queues, cap,
+                                   (int)std::max(1.0, std::min<double>(delta, (double)DRS_I32_INF)), d_overflow, qn, (int*)nullptr);
+    else if (mode == DRS_MODE_F32)
       rc = sssp_run<float>(g, nsrc, d_sources, (float*)dist_dev, ld, ld, delta, st, (const int2*)gm->sssp_arcs, (const int4*)d_ell,
                            (Entry*)gm->sssp_queues, cap, grid, d_overflow);
     else
@@ -342,6 +688,16 @@ extern "C" int drs_sssp_batch_dev(const drs_graph* g, int32_t mode, int32_t nsrc
     int ovf = 0;
     cudaMemcpyAsync(&ovf, d_overflow, sizeof(int), cudaMemcpyDeviceToHost, st);
     if (cudaStreamSynchronize(st) != cudaSuccess) { drs_set_error("drs_sssp_batch_dev: kernel failed: %s", cudaGetErrorString(cudaGetLastError())); rc = DRS_ERR_CUDA; break; }
+#ifdef DRS_SSSP_PROFILE
+    if (use_smem) {
+      unsigned long long pr[16], zero[16] = {0};
+      cudaMemcpyFromSymbol(pr, g_sssp_prof, sizeof(pr));
+      cudaMemcpyToSymbol(g_sssp_prof, zero, sizeof(zero));
+      const double st_ = (double)std::max<unsigned long long>(pr[0], 1);
+      fprintf(stderr, "[sssp prof] grid %d steps/source %.1f entries/step %.1f cycles/step %.0f (load %.0f targets %.0f atomics %.0f append %.0f) | far/source %.0f writeout/source %.0f | kernel cycles/CTA %.0f\n",
+              grid, st_ / nsrc, pr[2] / st_, pr[1] / st_, pr[3] / st_, pr[4] / st_, pr[5] / st_, pr[9] / st_, (double)pr[6] / nsrc, (double)pr[7] / nsrc, (double)pr[8] / grid);
+    }
+#endif
     if (!ovf) return DRS_OK;
     cap *= 4;   // queue overflow: retry with larger queues
   }

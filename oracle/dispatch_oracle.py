@@ -15,14 +15,21 @@ Restates, in plain Python (fp64, like the reference):
   * lib/Optimization.py:227-357 generateRTVGraph (trips of every size)       -> rtv_trips
   * lib/Optimization.py:359-408 assignFromRTVGraph (Gurobi ILP)              -> assign_ilp (HiGHS)
   * lib/Agents.py:1451-1572     Model.insert_heuristics / test_constraints_get_cost -> legacy_*
+  * lib/Agents.py:1429-1448     Model.insertion_heuristics (the sequential queue)    -> legacy_insertion_queue
+  * lib/Agents.py:148-297       Veh.build_route: what the insertion path reads back
+                                (route, veh.c, Req.pwt)                              -> legacy_build_route
 
 Travel times come from a callable ``tt(node_a, node_b)`` (the oracle's Dijkstra
 matrix) in place of ``G.shortest_paths``.
 
-Parity pin: the reference's own lib/optimUtils.py functions, run unmodified in
-the authoring container on the igraph facade (oracle/ref_shim), generated the
-fixtures in tests/golden/ (oracle/make_golden.py); tests/test_oracle_golden.py
-checks this restatement against them.  Two things stay "parity unpinned" because
+Parity pin: the reference's own lib/optimUtils.py, lib/Optimization.py and
+lib/Agents.py functions, run unmodified in the authoring container on the igraph
+facade (oracle/ref_shim), generated the fixtures in tests/golden/
+(oracle/make_golden.py); tests/test_oracle_golden.py checks this restatement
+against them -- for the legacy insertion heuristic call by call: every
+test_constraints_get_cost invocation (vehicle, i, j, bound, flag, cost, viol
+code), the winner, and Req.Cld / Req.pwt / Veh.c after the winner's build_route
+(tests/golden/legacy_*.json).  Two things stay "parity unpinned" because
 the reference itself leaves them undefined:
   * which of several equal-cost orderings minimalDelayPath returns -- the
     reference iterates a ``set`` of tuples hashed by object address
@@ -427,3 +434,101 @@ def legacy_insert_heuristics(tt, vehs, reqs, new_rid):
             if viol == 2:
                 break
     return veh_best, route_best, dc_best, evaluated
+
+
+def legacy_build_route(tt, veh, route, reqs, T):
+    """What Veh.build_route (lib/Agents.py:148-297) leaves behind for the next insertion scan: the
+    vehicle's route, ``veh.c`` (:256-270), ``idle`` and the predicted waiting time ``pwt`` of the
+    requests still to be picked up (:165-220).  Mutates ``veh`` and ``reqs``.
+
+    veh carries, besides the fields of legacy_test_constraints_get_cost, ``route`` (current legs) and
+    ``keep`` = None or {node, t, et}: the first step of the current route, which
+    clear_route_but_keep_next_node (:319-336) keeps in front of the new legs.  Leg times are the
+    path sums get_routing returns (``tt``); a pickup reached before Cep waits (add_leg, :363-367)."""
+    old = veh["route"]
+    pick = set(r for (r, pod, _) in old if pod == 1)
+    drop = set(r for (r, pod, _) in old if pod == -1)
+    in_veh = drop - pick                                        # get_passenger_requests, :604-615
+    not_in = set(r for (r, _, _) in route if r not in in_veh)
+    merge = veh["keep"] is not None                             # len(self.route) > 0, :156-160
+    if len(route) == 0:                                         # :163-169
+        veh.update(idle=True, c=0.0, route=[], keep=veh["keep"] if merge else None)
+        return
+    for r in in_veh:
+        reqs[r]["pwt"] = 0
+    for r in not_in:
+        reqs[r]["pwt"] = 0
+        if merge:
+            reqs[r]["pwt"] += veh["keep"]["et"]
+    cur = veh["keep"]["node"] if merge else veh["node_pos"]
+    vt = 0.0 + (veh["keep"]["t"] if merge else 0.0)             # self.t after clear_route(_but_keep_next_node)
+    leg_t = []
+    first_hop = None
+    for (r, pod, node) in route:
+        pred_t = tt(cur, node)                                  # sum of step.et == l['duration'] without link uncertainty
+        t_leg = pred_t
+        if pod == 1 and T + vt + t_leg < reqs[r]["Cep"]:        # add_leg waits at an early pickup
+            t_leg += reqs[r]["Cep"] - (T + vt + t_leg)
+        vt += t_leg
+        leg_t.append(t_leg)
+        for q in not_in:
+            reqs[q]["pwt"] += pred_t
+        if pod == 1:
+            not_in.discard(r)
+        cur = node
+    if merge:                                                   # :222-240 the kept step joins the first new leg
+        leg_t[0] = veh["keep"]["t"] + leg_t[0]
+    c, t, n = 0.0, 0.0, veh["n"]
+    for (r, pod, node), lt in zip(route, leg_t):                # :256-262
+        t += lt
+        c += n * lt * COEF_INVEH
+        n += pod
+        c += t * COEF_WAIT if pod == 1 else 0
+    assert n == 0
+    veh.update(idle=False, c=c, route=list(route), leg_t=leg_t)
+
+
+def legacy_insertion_queue(tt, vehs, reqs, queue, T, first_step=None, trace=None):
+    """Model.insertion_heuristics (lib/Agents.py:1429-1448, DISTANCE_THRESHOLD = 0): the queued requests are
+    inserted ONE AFTER ANOTHER, each scan seeing the plans, costs, pwt and Cld left by the previous winners.
+
+    vehs: dicts {vid, n, T, K, c, node, t0 (scan start, :1508-1516), node_pos (vertex of the position or None),
+    keep, idle, route}.  first_step(a, b) -> (next vertex, step time) of the path a -> b: needed when a vehicle that
+    had no route wins twice in one tick (its second build_route keeps the first step of the first leg).
+    Returns [(rid, vid or None, i, j, dc)]; ``trace`` (a list) receives every test_constraints_get_cost call."""
+    out = []
+    for rid in queue:
+        rq = reqs[rid]
+        dc_best, win = np.inf, None
+        viol = None
+        for veh in vehs:
+            route = list(veh["route"]) if not veh["idle"] else []
+            l = len(route)
+            c = veh["c"]
+            for i in range(l + 1):
+                for j in range(i + 1, l + 2):
+                    route.insert(i, (rid, 1, rq["o_node"]))
+                    route.insert(j, (rid, -1, rq["d_node"]))
+                    flag, c_new, viol = legacy_test_constraints_get_cost(tt, route, veh, reqs, rid, c + dc_best)
+                    if trace is not None:
+                        trace.append([veh["vid"], i, j, c + dc_best, flag, c_new, viol])
+                    if flag:
+                        dc_best = c_new - c
+                        win = (veh, list(route), i, j)
+                    route.pop(j)
+                    route.pop(i)
+                    if viol > 0:
+                        break
+                if viol == 2:
+                    break
+        if win is None:
+            out.append((rid, None, -1, -1, np.inf))
+            continue
+        veh, route, i, j = win
+        had_route = veh["keep"] is not None
+        legacy_build_route(tt, veh, route, reqs, T)
+        if not had_route:                                       # the new route's first step is what a later build keeps
+            nxt, st = first_step(veh["node_pos"], route[0][2]) if first_step else (route[0][2], None)
+            veh["keep"] = {"node": nxt, "t": st, "et": st}
+        out.append((rid, veh["vid"], i, j, dc_best))
+    return out

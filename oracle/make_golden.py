@@ -273,6 +273,141 @@ def sim_golden(name, n_veh, n_ticks, req_per_tick, capacity, seed):
     return ticks
 
 
+def legacy_golden(tag, name, n_veh, n_ticks, req_per_tick, capacity, seed, tight_every=0, clone_first=0, T0=600.0):
+    """The legacy insertion heuristic run by the reference's OWN code: ``Model.insertion_heuristics``,
+    ``Model.insert_heuristics`` and ``Model.test_constraints_get_cost`` (lib/Agents.py:1429-1572) are called unbound on
+    a namespace that carries what they read from ``self`` (vehs, reqs, queue, rejs, distance_rejs), with the reference's
+    real ``Veh`` / ``Req`` objects; vehicles are moved between ticks by ``Veh.move_to_time`` and rebuilt by
+    ``Veh.build_route`` exactly as ``Fleet.dispatch_at_time`` does it (lib/Agents.py:964-1016).
+
+    Recorded per inserted request: the fleet and the request table BEFORE the scan, every call of
+    test_constraints_get_cost in call order (vehicle, i, j, bound C, flag, cost, viol code), the winner, and AFTER the
+    winner's build_route: Cld and pwt of every request (the side effects of lib/Agents.py:1550,1554 and :178-220) and
+    c / idle / route of every vehicle."""
+    from collections import deque
+    from types import SimpleNamespace
+    from lib.Agents import Model
+    path = os.path.join(GOLD, name + ".gml")
+    router = RoutingEngine(graph_loc=path, cst_speed=9, seed=7)
+    G = router.G
+    n = len(G.vs)
+    rs = np.random.RandomState(seed)
+    node_of = {(v["lng"], v["lat"]): v.index for v in G.vs}
+    vehs = []
+    for vid in range(n_veh):
+        if clone_first and 0 < vid <= clone_first:
+            v = G.vs[node_of[(vehs[0].lng, vehs[0].lat)]]       # identical idle vehicles: equal costs, the LAST one must win
+        else:
+            v = router.generateRandomLocation()
+        vehs.append(Veh(vid, None, K=capacity, T=float(T0), ini_loc=(v["lng"], v["lat"])))
+    reqs = []
+    ns = SimpleNamespace(vehs=vehs, reqs=reqs, queue=deque(), rejs=[], distance_rejs=[])
+    calls = []
+
+    def tcgc(router_, route, veh, req, C):
+        out = Model.test_constraints_get_cost(ns, router_, route, veh, req, C)
+        i = [k for k, s in enumerate(route) if s[0] == req.id and s[1] == 1][0]
+        j = [k for k, s in enumerate(route) if s[0] == req.id and s[1] == -1][0]
+        calls.append([int(veh.id), i, j, jf(C), bool(out[0]), None if out[1] is None else jf(out[1]), int(out[2])])
+        return out
+
+    def veh_state(veh):
+        try:                                                   # lib/Agents.py:1508-1516
+            G.vs.find(name=str((veh.lng, veh.lat)))
+            node, t0, et0 = node_of[(veh.lng, veh.lat)], 0.0, 0.0
+        except ValueError:
+            st = veh.route[0].steps[0]
+            node, t0, et0 = node_of[(st.geo[1][0], st.geo[1][1])], float(st.t), float(st.et)
+        keep = None                                            # what clear_route_but_keep_next_node keeps (lib/Agents.py:319-336)
+        if len(veh.route) > 0:
+            st = veh.route[0].steps[0]
+            keep = {"node": node_of[(st.geo[1][0], st.geo[1][1])], "t": jf(st.t), "et": jf(st.et)}
+        return {"vid": int(veh.id), "idle": bool(veh.idle), "n": int(veh.n), "T": jf(veh.T), "K": int(veh.K), "c": jf(veh.c),
+                "node": node, "t0": jf(t0), "et0": jf(et0), "keep": keep, "lng": veh.lng, "lat": veh.lat,
+                "route": [[int(l.rid), int(l.pod), node_of[(l.tlng, l.tlat)]] for l in veh.route],
+                "leg_t": [jf(l.t) for l in veh.route]}
+
+    def req_state(r):
+        return {"rid": int(r.id), "o": node_of[(r.olng, r.olat)], "d": node_of[(r.dlng, r.dlat)], "Tr": jf(r.Tr), "Cep": jf(r.Cep),
+                "Clp": jf(r.Clp), "Ced": jf(r.Ced), "Cld": jf(r.Cld), "Ts": jf(r.Ts), "pwt": jf(r.pwt), "Tp": jf(r.Tp)}
+
+    insertions = []
+
+    def insert(router_, req, T):
+        before_v = [veh_state(v) for v in vehs]
+        before_r = [req_state(r) for r in reqs]
+        del calls[:]
+        with contextlib.redirect_stdout(io.StringIO()):
+            ok = Model.insert_heuristics(ns, router_, req, T)
+        wins = [c for c in calls if c[4]]
+        rec = {"T": jf(T), "rid": int(req.id), "assigned": bool(ok), "vehs": before_v, "reqs": before_r, "calls": [list(c) for c in calls],
+               "winner": None if not wins else {"vid": wins[-1][0], "i": wins[-1][1], "j": wins[-1][2], "cost": wins[-1][5]},
+               "after_Cld": [jf(r.Cld) for r in reqs], "after_pwt": [jf(r.pwt) for r in reqs],
+               "after_vehs": [veh_state(v) for v in vehs]}
+        if wins:
+            rec["winner"]["dc"] = jf(wins[-1][5] - before_v[wins[-1][0]]["c"])
+        insertions.append(rec)
+        return ok
+
+    ns.test_constraints_get_cost = tcgc
+    ns.insert_heuristics = insert
+    for tick in range(n_ticks):
+        T = T0 + tick * RC.INT_ASSIGN
+        for veh in vehs:                                        # Fleet.dispatch_at_time, lib/Agents.py:965-1016
+            with contextlib.redirect_stdout(io.StringIO()):
+                done = veh.move_to_time(T, reqs)
+            for (rid, pod, t) in done:
+                if pod == 1:
+                    reqs[rid].Tp = t
+                elif pod == -1:
+                    reqs[rid].Td = t
+            if len(veh.route) == 0:
+                veh.build_route(router, [])
+        for k in range(req_per_tick):
+            o, d = int(rs.randint(n)), int(rs.randint(n))
+            while d == o:
+                d = int(rs.randint(n))
+            Tr = T - float(rs.randint(0, RC.INT_ASSIGN))
+            cons = None
+            rid = len(reqs)
+            if tight_every and rid % tight_every == tight_every - 1:    # a window nobody can meet -> rejection
+                Ts = router.get_duration(G.vs[o]["lng"], G.vs[o]["lat"], G.vs[d]["lng"], G.vs[d]["lat"])
+                cons = {"Cep": Tr, "Clp": Tr + 5.0, "Ced": Tr + Ts, "Cld": Tr + 5.0 + RC.MAX_DETOUR * Ts}
+            req = Req(router, rid, Tr, G.vs[o]["lng"], G.vs[o]["lat"], G.vs[d]["lng"], G.vs[d]["lat"], constraints=cons)
+            reqs.append(req)
+            ns.queue.append(req)
+        Model.insertion_heuristics(ns, router, T)               # the reference's own queue loop (lib/Agents.py:1429-1448)
+        assert len(ns.queue) == 0
+    with open(os.path.join(GOLD, "legacy_%s.json" % tag), "w") as fh:
+        json.dump({"map": name, "capacity": capacity, "T0": T0, "n_veh": n_veh, "insertions": insertions,
+                   "rejected": [int(r.id) for r in ns.rejs],
+                   "constants": {"MAX_DETOUR": RC.MAX_DETOUR, "COEF_INVEH": RC.COEF_INVEH, "COEF_WAIT": RC.COEF_WAIT,
+                                 "COEF_EXTRA_WAIT": RC.COEF_EXTRA_WAIT, "INT_ASSIGN": RC.INT_ASSIGN}}, fh)
+    return insertions
+
+
+LEGACY_CASES = [
+    # tag, map, vehicles, ticks, requests per tick, capacity, seed, tight_every, clone_first
+    ("g8_int_K4", "g8_int", 4, 8, 4, 4, 21, 0, 0),            # long plans (up to 8+ stops), vehicles between nodes
+    ("g20_int_K4", "g20_int", 16, 6, 6, 4, 22, 7, 0),         # a few impossible windows -> rejections
+    ("g20_int_K1", "g20_int", 12, 5, 5, 1, 23, 0, 0),         # tight capacity: viol code 1
+    ("g8_int_K2_few", "g8_int", 2, 8, 3, 2, 24, 0, 0),        # two vehicles, late pickups / drop-offs
+    ("g20_uniform_K4", "g20_uniform", 10, 5, 4, 4, 25, 0, 2), # all-ties map, three identical idle vehicles
+    ("g12_float_K2", "g12_float", 5, 5, 4, 2, 26, 0, 0),      # float weights (1e-5 class)
+]
+
+
+def legacy_all():
+    for (tag, nm, nv, nt, rpt, K, seed, tight, clone) in LEGACY_CASES:
+        ins = legacy_golden(tag, nm, nv, nt, rpt, K, seed, tight_every=tight, clone_first=clone)
+        viol = {}
+        for x in ins:
+            for c in x["calls"]:
+                viol[c[6]] = viol.get(c[6], 0) + 1
+        print("legacy", tag, len(ins), "insertions,", sum(1 for x in ins if x["assigned"]), "assigned, calls by viol code", sorted(viol.items()),
+              "max plan", max(len(v["route"]) for x in ins for v in x["vehs"]))
+
+
 if __name__ == "__main__":
     make_maps()
     for nm in MAPS:
@@ -285,3 +420,4 @@ if __name__ == "__main__":
                                ("g12_float", 5, 4, 4, 2)]:
         t = sim_golden(nm, nv, nt, rpt, K, seed=9)
         print("sim", nm, K, [len(x["rv_edges"]) for x in t], [len(x["veh_routes"]) for x in t])
+    legacy_all()

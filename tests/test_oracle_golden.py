@@ -166,3 +166,122 @@ def test_assignment_ticks_match_reference(fname, name):
             continue
         assert meta["objective"] == pytest.approx(ref_obj, rel=1e-12, abs=1e-6)
         assert len(rejected) == len(tick["rejected"])
+
+
+# ------------------------------------------------------------------ legacy insertion heuristic
+LEGACY = ["g8_int_K4", "g20_int_K4", "g20_int_K1", "g8_int_K2_few", "g20_uniform_K4", "g12_float_K2"]
+
+
+def legacy_tt(G, exact_sums):
+    """Travel time a -> b as the reference's get_duration returns it: the fp64 left-to-right sum along the path
+    (float maps: unique paths), or the Dijkstra matrix entry (integer maps: every tied path has the same exact sum)."""
+    if not exact_sums:
+        dist = G.dist_matrix()
+        return lambda a, b: float(dist[a, b])
+    memo = {}
+
+    def tt(a, b):
+        if (a, b) not in memo:
+            d = 0
+            for e in G.epath(a, b):
+                d += float(G.tt[e])
+            memo[(a, b)] = d
+        return memo[(a, b)]
+    return tt
+
+
+def legacy_state(rec):
+    """Oracle-side fleet / request dictionaries of one golden insertion record (state BEFORE the scan)."""
+    vehs = []
+    for v in rec["vehs"]:
+        at_vertex = unjf(v["t0"]) == 0.0 and (v["keep"] is None or v["node"] != v["keep"]["node"] or unjf(v["keep"]["t"]) == 0.0)
+        vehs.append({"vid": v["vid"], "n": v["n"], "T": unjf(v["T"]), "K": v["K"], "c": unjf(v["c"]), "node": v["node"],
+                     "t0": unjf(v["t0"]), "idle": v["idle"], "route": [tuple(s) for s in v["route"]],
+                     "node_pos": v["node"] if at_vertex else None,
+                     "keep": None if v["keep"] is None else {"node": v["keep"]["node"], "t": unjf(v["keep"]["t"]),
+                                                             "et": unjf(v["keep"]["et"])}})
+    reqs = {r["rid"]: {"o_node": r["o"], "d_node": r["d"], "Cep": unjf(r["Cep"]), "Clp": unjf(r["Clp"]), "Cld": unjf(r["Cld"]),
+                       "Ts": unjf(r["Ts"]), "Tr": unjf(r["Tr"]), "pwt": unjf(r["pwt"])} for r in rec["reqs"]}
+    return vehs, reqs
+
+
+@pytest.mark.parametrize("tag", LEGACY)
+def test_legacy_insertion_matches_reference_call_by_call(tag):
+    """Every test_constraints_get_cost call of the reference's scan (vehicle, i, j, bound, flag, cost, viol code), the
+    winner, and -- after the winner's build_route -- Cld and pwt of every request and c / route of every vehicle."""
+    gold = load_golden("legacy_%s.json" % tag)
+    G = oracle_graph(gold["map"])
+    is_float = "float" in gold["map"]
+    tt = legacy_tt(G, is_float)
+    eq = (lambda a, b: a == pytest.approx(b, rel=1e-12, abs=1e-9)) if is_float else (lambda a, b: a == b)
+    assert gold["constants"] == {"MAX_DETOUR": D.MAX_DETOUR, "COEF_INVEH": D.COEF_INVEH, "COEF_WAIT": D.COEF_WAIT,
+                                 "COEF_EXTRA_WAIT": D.COEF_EXTRA_WAIT, "INT_ASSIGN": 30}
+    n_assigned = 0
+    for rec in gold["insertions"]:
+        vehs, reqs = legacy_state(rec)
+        trace = []
+        res = D.legacy_insertion_queue(tt, vehs, reqs, [rec["rid"]], unjf(rec["T"]), trace=trace)
+        assert len(trace) == len(rec["calls"])
+        for got, want in zip(trace, rec["calls"]):
+            assert got[:3] == want[:3] and got[4] == want[4] and got[6] == want[6]
+            assert eq(got[3], unjf(want[3]))
+            assert (got[5] is None) == (want[5] is None) and (got[5] is None or eq(got[5], unjf(want[5])))
+        rid, vid, i, j, dc = res[0]
+        if rec["winner"] is None:
+            assert vid is None and not rec["assigned"]
+        else:
+            n_assigned += 1
+            assert (vid, i, j) == (rec["winner"]["vid"], rec["winner"]["i"], rec["winner"]["j"]) and eq(dc, unjf(rec["winner"]["dc"]))
+        for r, want_cld, want_pwt in zip(rec["reqs"], rec["after_Cld"], rec["after_pwt"]):
+            assert eq(reqs[r["rid"]]["Cld"], unjf(want_cld)), (tag, rec["rid"], r["rid"])
+            assert eq(reqs[r["rid"]]["pwt"], unjf(want_pwt)), (tag, rec["rid"], r["rid"])
+        for v, want in zip(vehs, rec["after_vehs"]):
+            assert eq(v["c"], unjf(want["c"])) and v["idle"] == want["idle"]
+            if not v["idle"] and want["keep"] is not None:
+                # the reference's legs: [kept step + first new leg, ...]; same stops in the same order
+                assert [tuple(s) for s in want["route"]] == v["route"]
+    assert n_assigned == sum(1 for r in gold["insertions"] if r["assigned"]) > 0
+
+
+@pytest.mark.parametrize("tag", LEGACY)
+def test_legacy_queue_carries_state_across_a_tick(tag):
+    """The sequential semantics of Model.insertion_heuristics: all requests of one tick processed from the state before
+    the FIRST of them must reproduce every later winner (each scan sees the previous winners' routes, c and pwt)."""
+    gold = load_golden("legacy_%s.json" % tag)
+    G = oracle_graph(gold["map"])
+    is_float = "float" in gold["map"]
+    tt = legacy_tt(G, is_float)
+    eq = (lambda a, b: a == pytest.approx(b, rel=1e-12, abs=1e-9)) if is_float else (lambda a, b: a == b)
+    ticks = {}
+    for rec in gold["insertions"]:
+        ticks.setdefault(rec["T"], []).append(rec)
+    multi = 0
+    for T, recs in ticks.items():
+        vehs, reqs = legacy_state(recs[0])
+        for r in recs[-1]["reqs"]:                               # requests that arrived in this tick are all known up front
+            if r["rid"] not in reqs:
+                reqs[r["rid"]] = {"o_node": r["o"], "d_node": r["d"], "Cep": unjf(r["Cep"]), "Clp": unjf(r["Clp"]),
+                                  "Cld": unjf(r["Cld"]), "Ts": unjf(r["Ts"]), "Tr": unjf(r["Tr"]), "pwt": unjf(r["pwt"])}
+        keep_after = {}                                          # first step of a freshly built route, as the reference found it
+        for rec in recs:
+            for v in rec["after_vehs"]:
+                if v["keep"] is not None:
+                    keep_after.setdefault(v["vid"], (v["keep"]["node"], unjf(v["keep"]["t"])))
+        by_pos = {v["node_pos"]: v["vid"] for v in vehs if v["node_pos"] is not None}
+
+        def first_step(a, b, vehs=vehs, keep_after=keep_after):
+            vid = [v["vid"] for v in vehs if v["node_pos"] == a and v["keep"] is None and v["route"] and v["route"][0][2] == b]
+            return keep_after[vid[0]]
+        res = D.legacy_insertion_queue(tt, vehs, reqs, [rec["rid"] for rec in recs], unjf(T), first_step=first_step)
+        winners = [r[1] for r in res if r[1] is not None]
+        multi += len(winners) - len(set(winners))
+        for (rid, vid, i, j, dc), rec in zip(res, recs):
+            if rec["winner"] is None:
+                assert vid is None
+            else:
+                assert (vid, i, j) == (rec["winner"]["vid"], rec["winner"]["i"], rec["winner"]["j"]) and eq(dc, unjf(rec["winner"]["dc"]))
+        for r, want_cld, want_pwt in zip(recs[-1]["reqs"], recs[-1]["after_Cld"], recs[-1]["after_pwt"]):
+            assert eq(reqs[r["rid"]]["Cld"], unjf(want_cld)) and eq(reqs[r["rid"]]["pwt"], unjf(want_pwt))
+        for v, want in zip(vehs, recs[-1]["after_vehs"]):
+            assert eq(v["c"], unjf(want["c"]))
+    assert multi >= 0
