@@ -50,7 +50,7 @@ template <> struct Dist<int> {
 #ifndef DRS_SSSP_MIN_THREADS_PER_SM
 #define DRS_SSSP_MIN_THREADS_PER_SM 1152   // resident threads per SM the register allocation must allow (measured best)
 #endif
-struct Entry { int v; int key; };   // v = vertex | (source slot << 24); key = distance bits at push time
+struct __align__(8) Entry { int v; int key; };   // v = vertex | (source slot << 24); key = distance bits at push time
 constexpr int SSSP_D = 4;            // arcs per entry handled in registers (road networks: degree <= 4 almost everywhere)
 constexpr int SLOT_SHIFT = 24;
 constexpr int VERTEX_MASK = (1 << SLOT_SHIFT) - 1;
@@ -288,92 +288,65 @@ __global__ void __launch_bounds__(THREADS, 1) sssp_smem_kernel(
         const int c_wr = c_rd == 2 ? 0 : c_rd + 1, c_clr = c_wr == 2 ? 0 : c_wr + 1;
         if (tid == 0) s_cnt[c_clr] = 0;
         if (nn == 0) break;
-        // warps without queue entries go straight to the next barrier: the step is bound by instruction issue
-        for (int base = tid - lane; base < nn; base += THREADS) {
+        // One lane per (queue entry, arc slot): the wavefront step is one warp's dependent chain (entry -> adjacency,
+        // stale check -> target -> atomicMin -> append), so the chain is kept short (one arc, ~50 instructions) and
+        // spread over all warps instead of four arcs unrolled in a quarter of them (ncu: 200 instructions per warp and
+        // step, IPC 1.2, two thirds of the warps idle at the barrier -- profiles/r02_sssp_step_profile.md).
+        const int2* ell2 = reinterpret_cast<const int2*>(ell);
+        for (int base = tid - lane; base < 4 * nn; base += THREADS) {
           SSSP_PROF_T(p0);
-          const int e = base + lane;
+          const int e = (base + lane) >> 2, j = lane & 3;
           Entry en{0, 0};
           if (e < nn) en = q_get(buf, e);
+          int2 arc = make_int2(-1, 0);
           bool live = false;
-          int4 r0 = make_int4(-1, 0, -1, 0), r1 = make_int4(-1, 0, -1, 0);
           if (e < nn) {
-            ell_load(ell, en.v, r0, r1);
+            arc = __ldg(&ell2[4 * (int64_t)en.v + j]);
             live = irow[en.v] == en.key;                 // stale otherwise: a shorter distance arrived later
           }
-          const int tg[SSSP_D] = {r0.x, r0.z, r1.x, r1.z};
-          const int wb[SSSP_D] = {r0.y, r0.w, r1.y, r1.w};
 #ifdef DRS_SSSP_PROFILE
-          if (tg[0] == -12345 && tg[3] == -12345 && live) prof[9] += 1;   // consume the loads before the time stamp
+          if (arc.x == -12345 && live) prof[9] += 1;   // consume the loads before the time stamp
 #endif
           SSSP_PROF_T(p1);
           SSSP_PROF_ADD(3, p1 - p0);
-          int nk[SSSP_D];
-          bool push[SSSP_D];
-#pragma unroll
-          for (int j = 0; j < SSSP_D; ++j) {
-            nk[j] = Dist<T>::key(Dist<T>::unkey(en.key) + Dist<T>::weight(wb[j]));
-            push[j] = live && tg[j] >= 0 && nk[j] < irow[max(tg[j], 0)];
-          }
+          const int nk = Dist<T>::key(Dist<T>::unkey(en.key) + Dist<T>::weight(arc.y));
+          bool push = live && arc.x >= 0 && nk < irow[max(arc.x, 0)];
 #ifdef DRS_SSSP_PROFILE
-          if (push[0] && push[1] && push[2] && push[3] && nk[0] == -12345) prof[9] += 1;
+          if (push && nk == -12345) prof[9] += 1;
 #endif
           SSSP_PROF_T(p2);
           SSSP_PROF_ADD(4, p2 - p1);
-#pragma unroll
-          for (int j = 0; j < SSSP_D; ++j)
-            if (push[j]) push[j] = nk[j] < atomicMin(irow + tg[j], nk[j]);
+          if (push) push = nk < atomicMin(irow + arc.x, nk);
 #ifdef DRS_SSSP_PROFILE
-          if (push[0] && push[1] && push[2] && push[3] && nk[0] == -12345) prof[9] += 1;
+          if (push && nk == -12345) prof[9] += 1;
 #endif
           SSSP_PROF_T(p3);
           SSSP_PROF_ADD(5, p3 - p2);
-          // appends: one counter atomic per warp (and per pile)
-          bool nearp[SSSP_D];
-          unsigned mn[SSSP_D];
-          int total = 0;
-#pragma unroll
-          for (int j = 0; j < SSSP_D; ++j) {
-            nearp[j] = push[j] && (!FAR || Dist<T>::unkey(nk[j]) < theta);
-            mn[j] = __ballot_sync(0xffffffffu, nearp[j]);
-            total += __popc(mn[j]);
-          }
-          if (total) {
+          const bool nearp = push && (!FAR || Dist<T>::unkey(nk) < theta);
+          const unsigned mn = __ballot_sync(0xffffffffu, nearp);
+          if (mn) {
             int b0 = 0;
-            if (lane == 0) b0 = atomicAdd(&s_cnt[c_wr], total);
+            if (lane == 0) b0 = atomicAdd(&s_cnt[c_wr], __popc(mn));
             b0 = __shfl_sync(0xffffffffu, b0, 0);
-#pragma unroll
-            for (int j = 0; j < SSSP_D; ++j) {
-              if (nearp[j]) q_put(buf ^ 1, b0 + __popc(mn[j] & lt_mask), Entry{tg[j], nk[j]});
-              b0 += __popc(mn[j]);
-            }
+            if (nearp) q_put(buf ^ 1, b0 + __popc(mn & lt_mask), Entry{arc.x, nk});
           }
           if (FAR) {
-            unsigned mf[SSSP_D];
-            int totf = 0;
-#pragma unroll
-            for (int j = 0; j < SSSP_D; ++j) {
-              mf[j] = __ballot_sync(0xffffffffu, push[j] && !nearp[j]);
-              totf += __popc(mf[j]);
-            }
-            if (totf) {
+            const unsigned mf = __ballot_sync(0xffffffffu, push && !nearp);
+            if (mf) {
               int b0 = 0;
-              if (lane == 0) b0 = atomicAdd(&s_far, totf);
+              if (lane == 0) b0 = atomicAdd(&s_far, __popc(mf));
               b0 = __shfl_sync(0xffffffffu, b0, 0);
-#pragma unroll
-              for (int j = 0; j < SSSP_D; ++j) {
-                if (push[j] && !nearp[j]) {
-                  const int pos = b0 + __popc(mf[j] & lt_mask);
-                  if (pos < cap) far[pos] = Entry{tg[j], nk[j]}; else *overflow = 1;
-                }
-                b0 += __popc(mf[j]);
+              if (push && !nearp) {
+                const int pos = b0 + __popc(mf & lt_mask);
+                if (pos < cap) far[pos] = Entry{arc.x, nk}; else *overflow = 1;
               }
             }
           }
           SSSP_PROF_T(p4);
           SSSP_PROF_ADD(9, p4 - p3);
-          if (live && tg[SSSP_D - 1] == -2) {                // high-degree vertex: the remaining arcs live in the CSR
+          if (live && j == SSSP_D - 1 && arc.x == -2) {      // high-degree vertex: the remaining arcs live in the CSR
             const int a1 = out_ptr[en.v + 1];
-            for (int a = wb[SSSP_D - 1]; a < a1; ++a) {
+            for (int a = arc.y; a < a1; ++a) {
               const int2 ar = arcs[a];
               const int k2 = Dist<T>::key(Dist<T>::unkey(en.key) + Dist<T>::weight(ar.y));
               if (k2 < irow[ar.x] && k2 < atomicMin(irow + ar.x, k2)) {
@@ -694,7 +667,7 @@ extern "C" int drs_sssp_batch_dev(const drs_graph* g, int32_t mode, int32_t nsrc
       cudaMemcpyFromSymbol(pr, g_sssp_prof, sizeof(pr));
       cudaMemcpyToSymbol(g_sssp_prof, zero, sizeof(zero));
       const double st_ = (double)std::max<unsigned long long>(pr[0], 1);
-      fprintf(stderr, "[sssp prof] grid %d steps/source %.1f entries/step %.1f cycles/step %.0f (load %.0f targets %.0f atomics %.0f append %.0f) | far/source %.0f writeout/source %.0f | kernel cycles/CTA %.0f\n",
+      fprintf(stderr, "[sssp prof] grid %d steps/source %.1f entries/step %.1f cycles/step %.0f (thread 0, all its passes: load %.0f target %.0f atomic %.0f append %.0f) | far/source %.0f writeout/source %.0f | kernel cycles/CTA %.0f\n",
               grid, st_ / nsrc, pr[2] / st_, pr[1] / st_, pr[3] / st_, pr[4] / st_, pr[5] / st_, pr[9] / st_, (double)pr[6] / nsrc, (double)pr[7] / nsrc, (double)pr[8] / grid);
     }
 #endif
