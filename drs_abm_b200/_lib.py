@@ -54,7 +54,8 @@ class PlanBatch(C.Structure):
     """drs_plan_batch (include/drs_b200.h)."""
     _fields_ = [("n_veh", C.c_int32), ("start_node", _i32p), ("start_delay", _f64p), ("onboard", _i32p),
                 ("clock", _f64p), ("capacity", _i32p), ("cost", _f64p), ("stop_off", _i32p), ("stop_node", _i32p),
-                ("stop_req", _i32p), ("stop_pod", _i8p)]
+                ("stop_req", _i32p), ("stop_pod", _i8p), ("pos_node", _i32p), ("keep_node", _i32p), ("keep_t", _f64p),
+                ("keep_et", _f64p)]
 
 
 class RequestTable(C.Structure):
@@ -115,6 +116,10 @@ SIGNATURES = {
     "drs_tick_rv_fetch": (C.c_int, [_vp, C.c_int32, _i32p, _i32p, _f64p, _u8p, _i32p]),
     "drs_tick_set_plans": (C.c_int, [_vp, C.POINTER(PlanBatch), C.POINTER(RequestTable), C.POINTER(InsertionParams)]),
     "drs_tick_insertion_eval": (C.c_int, [_vp, C.c_int32, _i32p, _i32p, _i32p, _i32p, _f64p, _i64p]),
+    "drs_tick_insertion_queue": (C.c_int, [_vp, C.c_int32, _i32p, C.c_double, _i32p, _i32p, _i32p, _f64p, _i64p]),
+    "drs_tick_commit_insertion": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double]),
+    "drs_tick_fetch_plans": (C.c_int, [_vp, _f64p, _i32p, _i32p, _i8p, C.c_int32, _f64p, _f64p]),
+    "drs_alloc_count": (C.c_int64, []),
     "drs_tick_trip_eval": (C.c_int, [_vp, C.c_double, C.c_int32, C.c_int32, _i32p, _i32p, _i32p, _f64p, _u8p,
                                      _i32p]),
 }

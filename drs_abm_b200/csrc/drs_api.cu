@@ -7,6 +7,7 @@
 #include <numeric>
 
 #include "drs_common.cuh"
+#include "drs_paths.cuh"
 
 static thread_local char g_err[512] = "";
 
@@ -21,6 +22,9 @@ void drs_set_error(const char* fmt, ...) {
 static std::atomic<long long> g_launches{0};
 void drs_count_launch(int n) { g_launches += n; }
 extern "C" int64_t drs_launch_count(void) { return (int64_t)g_launches.load(); }
+static std::atomic<long long> g_allocs{0};
+void drs_count_alloc(int n) { g_allocs += n; }
+extern "C" int64_t drs_alloc_count(void) { return (int64_t)g_allocs.load(); }
 
 extern "C" const char* drs_last_error(void) { return g_err; }
 extern "C" int drs_version(void) { return 100; }
@@ -295,49 +299,6 @@ extern "C" int drs_apsp_adopt(drs_graph* g, int32_t mode, void* dist_dev, int32_
 // ---------------------------------------------------------------------------- queries
 namespace {
 
-__device__ __forceinline__ int prev_node(int e, int t, const int32_t* esrc, const int32_t* edst) {
-  const int a = esrc[e], b = edst[e];
-  return (b == t) ? a : b;   // undirected edges are walked against either orientation
-}
-
-// Where the last edge of the canonical path s -> t comes from: the materialised predecessor matrix, or --
-// when it was not built (DRS_PRED_LAZY) -- the canonical rule evaluated on the spot from the distance row
-// of s and t's in-arcs (same rule as pred_kernel: minimise (dist[s,u] + w, dist[s,u], eid)).
-struct PredSource {
-  const int32_t* pred;      // may be null
-  const void* dist;
-  int64_t ld;
-  int mode;
-  const int32_t *in_ptr, *in_src, *in_eid;
-  const float* in_w;
-
-  template <typename T> __device__ int rule(const T* row, T inf, int t) const {
-    int best_e = -1;
-    T best_c = inf, best_du = inf;
-    for (int a = in_ptr[t]; a < in_ptr[t + 1]; ++a) {
-      const T du = row[in_src[a]];
-      if (!(du < inf)) continue;
-      const T cand = du + (T)in_w[a];
-      const int e = in_eid[a];
-      if (cand < best_c || (cand == best_c && (du < best_du || (du == best_du && e < best_e)))) {
-        best_c = cand; best_du = du; best_e = e;
-      }
-    }
-    return best_e;
-  }
-  __device__ int last_edge(int s, int t) const {
-    if (pred) return pred[(int64_t)s * ld + t];
-    if (s == t) return -1;
-    if (mode == DRS_MODE_F32) {
-      const float* row = (const float*)dist + (int64_t)s * ld;
-      const float inf = __int_as_float(0x7f800000);
-      return (row[t] < inf) ? rule<float>(row, inf, t) : -1;
-    }
-    const int* row = (const int*)dist + (int64_t)s * ld;
-    return (row[t] < DRS_I32_INF) ? rule<int>(row, DRS_I32_INF, t) : -1;
-  }
-};
-
 // hops[q] = number of edges on the canonical path (-1 unreachable / broken chain)
 __global__ void path_count_kernel(int npairs, const int32_t* s, const int32_t* t, PredSource ps, int n,
                                   const int32_t* esrc, const int32_t* edst, int32_t* hops) {
@@ -407,9 +368,7 @@ __global__ void rows_to_double_kernel(const T* dist, int64_t ld, int row0, int n
   }
 }
 
-PredSource pred_source(const drs_graph* g) {
-  return PredSource{g->d_pred, g->d_dist, g->ld, g->mode, g->d_in_ptr, g->d_in_src, g->d_in_eid, g->d_in_w};
-}
+PredSource pred_source(const drs_graph* g) { return drs_pred_source(g); }
 
 struct DevBuf {
   void* p = nullptr;

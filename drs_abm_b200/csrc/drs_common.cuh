@@ -10,6 +10,7 @@
 
 void drs_set_error(const char* fmt, ...);
 void drs_count_launch(int n = 1);
+void drs_count_alloc(int n = 1);   // every cudaMalloc of the library (drs_alloc_count)
 
 #define DRS_CUDA(call)                                                                      \
   do {                                                                                      \

@@ -1,97 +1,126 @@
-// (vehicle, pickup slot, drop-off slot) insertion evaluation and argmin.
+// (vehicle, pickup slot, drop-off slot) insertion evaluation, argmin and commit.
 //
-// Replaces Model.insert_heuristics / test_constraints_get_cost
-// (lib/Agents.py:1451-1572).  Every candidate route is walked in fp64 with the
-// reference's operation order, so costs are bit-identical for integer-weighted maps;
+// Replaces Model.insertion_heuristics / insert_heuristics / test_constraints_get_cost
+// (lib/Agents.py:1429-1572) and, for the sequential queue, what Veh.build_route leaves behind for
+// the next scan (route, veh.c, Req.pwt: lib/Agents.py:148-297).  Every candidate route is walked in
+// fp64 with the reference's operation order, so costs are bit-identical on integer-weighted maps;
 // travel times are gathered from the resident matrix.
 //
-//   plan_prep_kernel        per vehicle: plan segment times and the walk of the
-//       unmodified plan (the common prefix of every candidate), slot-major.
-//   insertion_scan_kernel   one thread per (request, vehicle) pair, vehicles fastest:
-//       every (i, j) candidate is evaluated WITHOUT the incumbent bound and the pair's
-//       smallest successful total cost is written out (+inf if none).
-//   insertion_fold_kernel   one warp per request walks the vehicles in the
-//       reference's order.  A vehicle can only change the incumbent if its
-//       smallest cost is <= the bound C = veh.c + dc (lib/Agents.py:1470); only
-//       then is the pair re-scanned exactly as the reference does it -- with the
-//       bound, "last equal-or-better wins" and the viol-code loop breaks
-//       (load_pair / eval_candidate below are that literal restatement).
+// Plans live slot-major on the device (element [k][vs] = plan stop k of the vehicle at sorted
+// position vs; vehicles sorted by plan length, then start vertex), with room for INS_MAXL stops per
+// vehicle so that a winner's plan can be patched in place.
+//
+//   plan_prep_kernel     per vehicle: plan segment times, the walk of the unmodified plan (the common
+//       prefix of every candidate) and a conservative fp32 bound per pickup position for the reach test.
+//   insertion_reach_kernel<STAGED>   one persistent CTA per SM walks the new requests; for each it stages
+//       the request's ORIGIN ROW of the travel-time matrix (4*ld bytes, 200 KB on the 50k-node map) in
+//       shared memory with bulk asynchronous copies (cp.async.bulk -> UBLKCP, completion on an mbarrier)
+//       and tests every vehicle: can ANY pickup position be reached before the latest pickup time?  The
+//       (L+1) travel times per pair are shared-memory gathers; the plans stream in coalesced.  Survivors
+//       (~1 % of the pairs) go to a bit mask per request and a compact pair list.  Directed maps and rows
+//       that do not fit use the same kernel without staging (gathers from L2).
+//   insertion_eval_kernel   one thread per surviving pair: every (i, j) candidate WITHOUT the incumbent
+//       bound; the pair's smallest successful total cost is written out (+inf if none).
+//   insertion_fold_kernel   one warp per request walks the vehicles in the reference's order.  A vehicle
+//       can only change the incumbent if its smallest cost is <= the bound C = veh.c + dc
+//       (lib/Agents.py:1470); only then is the pair re-scanned exactly as the reference does it -- with
+//       the bound, "last equal-or-better wins" and the viol-code loop breaks.
+//   insertion_commit_kernel / insertion_rescan_kernel   the sequential queue: after a request is folded
+//       its winner's plan is patched on the device (build_route's route, veh.c and pwt), that vehicle is
+//       re-prepared and its column is re-evaluated for the requests still in the queue.
 #include <algorithm>
 #include <cstring>
 
+#include "drs_paths.cuh"
 #include "drs_tick.cuh"
 
 namespace {
 
-constexpr int MAXL = DRS_MAX_STOPS - 2;   // planned stops per vehicle
+constexpr int INS_MAXL = 16;            // plan slots per vehicle on the device
+constexpr int INS_SCAN_MAXL = 14;       // longest plan a request can still be inserted into (L + 2 <= INS_MAXL)
 
 struct PlanView {
   int n_veh;
-  const int32_t *node, *onboard, *cap, *off, *s_node, *s_req;
-  const double *delay, *clock, *cost;
-  const int8_t* s_pod;
-  // request table
+  // per vehicle, indexed by sorted position vs (perm[vs] = caller's vehicle index, inv[v] = vs)
+  const int32_t *perm, *inv;
+  const int32_t *node, *onboard, *cap;
+  int32_t* len;
+  const double *delay, *clock;
+  double* cost;
+  // what a later build_route keeps in front of a new route (lib/Agents.py:319-336)
+  const int32_t* pos_node;             // vertex of the vehicle's position, -1 between vertices
+  int32_t* keep_node;                  // -1: the vehicle has no route
+  double *keep_t, *keep_et;
+  // request table (Cld and pwt are updated by commits)
   const int32_t *q_o, *q_d;
-  const double *q_cep, *q_clp, *q_cld, *q_ts, *q_tr, *q_pwt;
+  const double *q_cep, *q_clp, *q_ts, *q_tr;
+  double *q_cld, *q_pwt;
   drs_insertion_params prm;
-  // per-vehicle precomputation (plan_prep_kernel): plan segment times and the walk of the
-  // unmodified plan, which is the common prefix of every candidate
-  // Slot-major copy for the scan kernel: vehicles sorted by plan length (vs = sorted index), element
-  // [k * n_veh + vs] is plan stop k of that vehicle, so that a warp of consecutive vehicles loads
-  // coalesced and runs the same trip counts.  perm[vs] = original vehicle index.
-  const int32_t* perm;
-  const int32_t* m_node;    // [k][vs] vertex of plan stop k
-  const int32_t* m_req;     // [k][vs] request-table row
-  const int8_t* m_pod;      // [k][vs]
-  const int8_t* m_partner;  // [k][vs] plan index of the pickup belonging to a drop-off, -1 if on board
-  // per-vehicle precomputation (plan_prep_kernel): plan segment times and the walk of the unmodified
-  // plan, which is the common prefix of every candidate
-  double* m_seg;            // [k][vs]  tt(previous stop or start vertex -> stop k)
-  double* m_base_t;         // [k][vs]  t before plan stop k, k = 0..L
-  double* m_base_c;         // [k][vs]  c before plan stop k
-  double* m_base_cld;       // [k][vs]  Cld assigned when plan stop k is a pickup
-  int32_t* m_base_viol;     // [vs]     first plan stop the unmodified walk fails at (L if none), -1: over capacity
+  // slot-major plan [k][vs]
+  int32_t *m_node, *m_req;
+  int8_t *m_pod, *m_partner;           // partner: plan index of the pickup belonging to a drop-off, -1 if on board
+  // per-vehicle precomputation (plan_prep): plan segment times and the walk of the unmodified plan
+  double* m_seg;                       // [k][vs]  tt(previous stop or start vertex -> stop k)
+  double* m_base_t;                    // [k][vs]  t before plan stop k, k = 0..L
+  double* m_base_c;                    // [k][vs]  c before plan stop k
+  double* m_base_cld;                  // [k][vs]  Cld assigned when plan stop k is a pickup
+  int32_t* m_base_viol;                // [vs]     first plan stop the unmodified walk fails at (L if none), -1: over capacity
+  float* m_lb;                         // [k][vs]  fp32 lower bound of clock + base_t[k] (reach test), +inf past the usable slots
+  uint8_t* m_nslots;                   // [vs]     pickup positions worth testing: min(L, base_viol) + 1, 0 if none
   int directed;
 };
 
+__device__ __forceinline__ double d_inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+
+// Travel times between a request vertex q (origin or destination) and a plan vertex x.  On an undirected map the
+// matrix is symmetric and EVERY kernel reads such a time from q's row (the reach test stages that row in shared
+// memory); reading one direction everywhere keeps the prefilter, the evaluation and the exact re-scan consistent
+// with each other even where an fp32 matrix is not bitwise symmetric (float-weighted maps).
+__device__ __forceinline__ double tt_into(const DistView& dv, int directed, int q, int x) {   // x -> q
+  return x == q ? 0.0 : (directed ? dv.at(x, q) : dv.at(q, x));
+}
+__device__ __forceinline__ double tt_outof(const DistView& dv, int q, int x) {                 // q -> x
+  return x == q ? 0.0 : dv.at(q, x);
+}
+
 // Everything one (vehicle, request) pair needs, in thread-local storage.
 struct Pair {
-  int L;                    // planned stops
-  int n0, K;
+  int L, n0, K;
   double T, t0, c0;
-  int8_t pod[MAXL];
-  int req[MAXL];
-  double seg[MAXL];         // seg[k]  = tt(stop k-1 -> stop k), stop -1 = start vertex
-  double to_o[MAXL + 1];    // to_o[k] = tt(stop k-1 -> origin)      (k = 0: from the start vertex)
-  double to_d[MAXL + 1];    // to_d[k] = tt(stop k-1 -> destination)
-  double from_o[MAXL];      // from_o[k] = tt(origin -> stop k)
-  double from_d[MAXL];      // from_d[k] = tt(destination -> stop k)
-  double od;                // tt(origin -> destination)
+  int8_t pod[INS_MAXL];
+  int8_t partner[INS_MAXL];
+  int req[INS_MAXL];
+  double seg[INS_MAXL];         // seg[k]  = tt(stop k-1 -> stop k), stop -1 = start vertex
+  double to_o[INS_MAXL + 1];    // to_o[k] = tt(stop k-1 -> origin)      (k = 0: from the start vertex)
+  double to_d[INS_MAXL + 1];    // to_d[k] = tt(stop k-1 -> destination)
+  double from_o[INS_MAXL];      // from_o[k] = tt(origin -> stop k)
+  double from_d[INS_MAXL];      // from_d[k] = tt(destination -> stop k)
+  double od;                    // tt(origin -> destination)
   int new_req;
 };
 
-__device__ void load_pair(Pair& p, const PlanView& pv, const DistView& dv, int v, int rrow) {
-  const int s0 = pv.off[v];
-  p.L = pv.off[v + 1] - s0;
-  p.n0 = pv.onboard[v]; p.K = pv.cap[v];
-  p.T = pv.clock[v]; p.t0 = pv.delay[v]; p.c0 = pv.cost[v];
+__device__ void load_pair(Pair& p, const PlanView& pv, const DistView& dv, int vs, int rrow) {
+  const int nv = pv.n_veh;
+  p.L = pv.len[vs];
+  p.n0 = pv.onboard[vs]; p.K = pv.cap[vs];
+  p.T = pv.clock[vs]; p.t0 = pv.delay[vs]; p.c0 = pv.cost[vs];
   p.new_req = rrow;
   const int o = pv.q_o[rrow], d = pv.q_d[rrow];
-  int prev = pv.node[v];
-  p.to_o[0] = (prev == o) ? 0.0 : dv.at(prev, o);
-  p.to_d[0] = (prev == d) ? 0.0 : dv.at(prev, d);
+  const int start = pv.node[vs];
+  p.to_o[0] = tt_into(dv, pv.directed, o, start);
+  p.to_d[0] = tt_into(dv, pv.directed, d, start);
   for (int k = 0; k < p.L; ++k) {
-    const int nd = pv.s_node[s0 + k];
-    p.pod[k] = pv.s_pod[s0 + k];
-    p.req[k] = pv.s_req[s0 + k];
-    p.seg[k] = (prev == nd) ? 0.0 : dv.at(prev, nd);
-    p.from_o[k] = (o == nd) ? 0.0 : dv.at(o, nd);
-    p.from_d[k] = (d == nd) ? 0.0 : dv.at(d, nd);
-    p.to_o[k + 1] = (nd == o) ? 0.0 : dv.at(nd, o);
-    p.to_d[k + 1] = (nd == d) ? 0.0 : dv.at(nd, d);
-    prev = nd;
+    const int nd = pv.m_node[k * nv + vs];
+    p.pod[k] = pv.m_pod[k * nv + vs];
+    p.partner[k] = pv.m_partner[k * nv + vs];
+    p.req[k] = pv.m_req[k * nv + vs];
+    p.seg[k] = pv.m_seg[k * nv + vs];
+    p.from_o[k] = tt_outof(dv, o, nd);
+    p.from_d[k] = tt_outof(dv, d, nd);
+    p.to_o[k + 1] = tt_into(dv, pv.directed, o, nd);
+    p.to_d[k + 1] = tt_into(dv, pv.directed, d, nd);
   }
-  p.od = (o == d) ? 0.0 : dv.at(o, d);
+  p.od = tt_outof(dv, o, d);
 }
 
 // test_constraints_get_cost (lib/Agents.py:1493-1572) for the candidate "pickup after a
@@ -107,7 +136,7 @@ __device__ int eval_candidate(const Pair& p, const PlanView& pv, int a, int b, d
       if (k < p.L) { n += p.pod[k]; if (n > p.K) return 1; }
     }
   }
-  double cld_local[MAXL];            // Cld of requests picked up inside this candidate (:1550,1554)
+  double cld_local[INS_MAXL];        // Cld of requests picked up inside this candidate (:1550,1554)
   double cld_new = 0.0;
   double c = 0.0, t = 0.0 + p.t0;
   int n = p.n0;
@@ -116,18 +145,14 @@ __device__ int eval_candidate(const Pair& p, const PlanView& pv, int a, int b, d
   // (after the pickup when a == b)
   int last = -1;                     // -1 start vertex, 0..L-1 planned stop, L pickup, L+1 drop-off
   for (int pos = 0; pos < p.L + 2; ++pos) {
-    // which element comes next?
     int kind;                        // 0 planned stop, 1 new pickup, 2 new drop-off
     int k = 0;
-    {
-      // elements before planned stop index x: x planned + (x > a or (x == a ... )) handled by counting
-      // position layout: [stops 0..a-1] P [stops a..b-1] D [stops b..L-1]
-      if (pos < a) { kind = 0; k = pos; }
-      else if (pos == a) { kind = 1; }
-      else if (pos <= b) { kind = 0; k = pos - 1; }
-      else if (pos == b + 1) { kind = 2; }
-      else { kind = 0; k = pos - 2; }
-    }
+    // position layout: [stops 0..a-1] P [stops a..b-1] D [stops b..L-1]
+    if (pos < a) { kind = 0; k = pos; }
+    else if (pos == a) { kind = 1; }
+    else if (pos <= b) { kind = 0; k = pos - 1; }
+    else if (pos == b + 1) { kind = 2; }
+    else { kind = 0; k = pos - 2; }
     double dt;
     int pod, rq;
     if (kind == 0) {
@@ -159,12 +184,7 @@ __device__ int eval_candidate(const Pair& p, const PlanView& pv, int a, int b, d
     } else if (pod == -1) {
       double cld;
       if (kind == 2) cld = cld_new;
-      else {
-        // drop-off of a planned request: Cld set by its pickup earlier in this walk, else the stored value
-        cld = pv.q_cld[rq];
-        for (int m = 0; m < k; ++m)
-          if (p.req[m] == rq && p.pod[m] == 1) cld = cld_local[m];
-      }
+      else cld = p.partner[k] >= 0 ? cld_local[p.partner[k]] : pv.q_cld[rq];   // set by its pickup earlier in this walk, else stored
       if (T + t > cld) return 3;     // late drop-off (:1555-1556)
     }
     c += n * dt * pv.prm.coef_inveh;
@@ -210,24 +230,21 @@ __device__ __forceinline__ int walk_stop(Walk& w, double dt, int pod, int rq, do
   return -1;
 }
 
-// Per vehicle: plan segment times and the walk of the unmodified plan (slot-major outputs).
-__global__ void plan_prep_kernel(PlanView pv, DistView dv) {
-  const int vs = blockIdx.x * blockDim.x + threadIdx.x;
+// Per vehicle: plan segment times, the walk of the unmodified plan, and the reach-test bounds.
+__device__ void plan_prep(const PlanView& pv, const DistView& dv, int vs) {
   const int nv = pv.n_veh;
-  if (vs >= nv) return;
-  const int v = pv.perm[vs];
-  const int L = pv.off[v + 1] - pv.off[v];
-  int prev = pv.node[v];
+  const int L = pv.len[vs];
+  int prev = pv.node[vs];
   for (int k = 0; k < L; ++k) {
     const int nd = pv.m_node[k * nv + vs];
     pv.m_seg[k * nv + vs] = (prev == nd) ? 0.0 : dv.at(prev, nd);
     prev = nd;
   }
-  int occ = pv.onboard[v], viol_at = L;
-  bool over = occ > pv.cap[v];
-  for (int k = 0; k < L; ++k) { occ += pv.m_pod[k * nv + vs]; if (occ > pv.cap[v]) over = true; }
-  Walk w{0.0 + pv.delay[v], 0.0, pv.onboard[v]};
-  const double T = pv.clock[v];
+  int occ = pv.onboard[vs], viol_at = L;
+  bool over = occ > pv.cap[vs];
+  for (int k = 0; k < L; ++k) { occ += pv.m_pod[k * nv + vs]; if (occ > pv.cap[vs]) over = true; }
+  Walk w{0.0 + pv.delay[vs], 0.0, pv.onboard[vs]};
+  const double T = pv.clock[vs];
   for (int k = 0; k <= L; ++k) {
     pv.m_base_t[k * nv + vs] = w.t;
     pv.m_base_c[k * nv + vs] = w.c;
@@ -240,138 +257,248 @@ __global__ void plan_prep_kernel(PlanView pv, DistView dv) {
     if (walk_stop(w, pv.m_seg[k * nv + vs], pod, rq, T, pv, cld_drop, &cld_set) >= 0) viol_at = k;
     pv.m_base_cld[k * nv + vs] = cld_set;
   }
-  pv.m_base_viol[vs] = over ? -1 : viol_at;
+  const int bviol = (over || L > INS_SCAN_MAXL) ? -1 : viol_at;   // plans too long to take two more stops are not insertable
+  pv.m_base_viol[vs] = bviol;
+  // reach test: pickup position a is worth a look iff clock + (base_t[a] + tt) can be <= the latest pickup time.
+  // lb = that sum's vehicle part rounded DOWN to fp32 and one ulp further, so that an fp32 add and compare against the
+  // rounded-UP limit can only err towards "reachable" (the exact fp64 test follows in insertion_eval_kernel).
+  const int ns = bviol < 0 ? 0 : min(L, bviol) + 1;
+  pv.m_nslots[vs] = (uint8_t)ns;
+  for (int k = 0; k <= INS_MAXL; ++k) {
+    float lb = __int_as_float(0x7f800000);
+    if (k < ns) {
+      lb = __double2float_rd(T + pv.m_base_t[k * nv + vs]);
+      lb = (lb > 0.f) ? __int_as_float(__float_as_int(lb) - 1) : ((lb < 0.f) ? __int_as_float(__float_as_int(lb) + 1) : -1.0e-30f);
+    }
+    pv.m_lb[k * nv + vs] = lb;
+  }
 }
 
-// Scan: one thread per (request, vehicle) pair, VEHICLES fastest and sorted by plan length.
-//   * On an undirected map the matrix is symmetric, so every travel time the pair needs lives in the two
-//     matrix rows of the request (origin row, destination row): all warps working on a request gather
-//     from the same 2 x 4n bytes, which stay in L2 -- DRAM sees each request row once instead of one
-//     32-byte sector per gathered element.
-//   * The unmodified-plan prefix is shared (precomputed per vehicle), the state "pickup inserted after a
-//     stops, b-a further stops served" is advanced incrementally over b, and only the tail after the
-//     drop-off is re-walked per candidate.  Arithmetic and operation order per candidate are those of
-//     eval_candidate; only successes matter here (the pair's smallest total cost), so no viol codes.
-__global__ void __launch_bounds__(128) insertion_scan_kernel(PlanView pv, DistView dv, int n_new,
-                                                             const int32_t* __restrict__ new_rows, double* __restrict__ cmin_out,
-                                                             unsigned long long* n_cand) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int nv = pv.n_veh;
-  const int64_t total = (int64_t)nv * n_new;
-  if (idx >= total) return;
-  const int r = (int)(idx / nv), vs = (int)(idx % nv);
-  const int v = pv.perm[vs];
-  const double inf = __longlong_as_double(0x7ff0000000000000LL);
-  const int L = pv.off[v + 1] - pv.off[v];
-  if (r == 0) atomicAdd(n_cand, (unsigned long long)((L + 1) * (L + 2) / 2) * (unsigned long long)n_new);
-  double cmin = inf;
-  const int bviol = pv.m_base_viol[vs];
-  if (bviol >= 0) {
+__global__ void plan_prep_kernel(PlanView pv, DistView dv) {
+  const int vs = blockIdx.x * blockDim.x + threadIdx.x;
+  if (vs < pv.n_veh) plan_prep(pv, dv, vs);
+}
+
+// ------------------------------------------------------------------------------------------------ reach test
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// fp32 upper bound of the latest time a pickup may still happen: max(Clp, Cep) rounded up, one ulp further
+__device__ __forceinline__ float reach_limit(const PlanView& pv, int rq) {
+  const double lim = fmax(pv.q_clp[rq], pv.q_cep[rq]);
+  float f = __double2float_ru(lim);
+  if (f > 0.f) f = __int_as_float(__float_as_int(f) + 1);
+  else if (f < 0.f) f = __int_as_float(__float_as_int(f) - 1);
+  else f = 1.0e-30f;
+  return f;
+}
+
+// STAGED: the origin row of each request is copied into shared memory by the bulk-copy engine (one elected thread
+// issues cp.async.bulk in 32 KB pieces, all threads wait on the mbarrier); otherwise the same gathers go to L2.
+template <bool STAGED>
+__global__ void __launch_bounds__(1024, 1) insertion_reach_kernel(PlanView pv, DistView dv, int n_new, const int32_t* __restrict__ new_rows,
+                                                                    uint32_t* __restrict__ mask, int words, int2* __restrict__ list,
+                                                                    int list_cap, int* __restrict__ counters /* [0] list fill, [1] next request */) {
+  extern __shared__ __align__(128) unsigned char reach_smem[];
+  __shared__ __align__(8) unsigned long long bar;
+  __shared__ int s_req;
+  const int nv = pv.n_veh, tid = threadIdx.x, lane = tid & 31;
+  const size_t row_bytes = (size_t)dv.ld * 4;
+  const float* frow = reinterpret_cast<const float*>(reach_smem);
+  const int* irow = reinterpret_cast<const int*>(reach_smem);
+  if (STAGED && tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar)), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  unsigned phase = 0;
+  while (true) {
+    __syncthreads();                                   // every lane is done with the previous row
+    if (tid == 0) s_req = atomicAdd(&counters[1], 1);
+    __syncthreads();
+    const int r = s_req;
+    if (r >= n_new) break;
     const int rq = new_rows[r];
-    const int o = pv.q_o[rq], d = pv.q_d[rq];
-    const int K = pv.cap[v];
-    const double T = pv.clock[v];
-    double to_o[MAXL + 1], to_d[MAXL + 1], from_o[MAXL], from_d[MAXL], cld_cur[MAXL];
-    // origin-side travel times first: most vehicles cannot reach the pickup in time at any position, and
-    // for those the destination-side gathers (half of the traffic) are never needed
-    {
-      const int start = pv.node[v];
-      to_o[0] = (start == o) ? 0.0 : (pv.directed ? dv.at(start, o) : dv.at(o, start));
-      for (int k = 0; k < L; ++k) {
-        const int nd = pv.m_node[k * nv + vs];
-        from_o[k] = (o == nd) ? 0.0 : dv.at(o, nd);
-        to_o[k + 1] = pv.directed ? ((nd == o) ? 0.0 : dv.at(nd, o)) : from_o[k];
-      }
-    }
-    bool reachable = false;
-    {
-      const double clp = pv.q_clp[rq], cep = pv.q_cep[rq];
-      for (int a = 0; a <= L && a <= bviol; ++a) {
-        const double t = pv.m_base_t[a * nv + vs] + to_o[a];      // same sum walk_stop forms for the pickup
-        if (T + t < cep || !(T + t > clp)) { reachable = true; break; }
-      }
-    }
-    if (reachable) {
-      const int start = pv.node[v];
-      to_d[0] = (start == d) ? 0.0 : (pv.directed ? dv.at(start, d) : dv.at(d, start));
-      for (int k = 0; k < L; ++k) {
-        const int nd = pv.m_node[k * nv + vs];
-        from_d[k] = (d == nd) ? 0.0 : dv.at(d, nd);
-        to_d[k + 1] = pv.directed ? ((nd == d) ? 0.0 : dv.at(nd, d)) : from_d[k];
-      }
-    }
-    const double od = (o == d) ? 0.0 : dv.at(o, d);
-    int occ_before = pv.onboard[v];    // occupancy before plan stop a in the unmodified plan
-    for (int a = 0; reachable && a <= L && a <= bviol; ++a) {
-      if (a > 0) {
-        cld_cur[a - 1] = pv.m_base_cld[(a - 1) * nv + vs];
-        occ_before += pv.m_pod[(a - 1) * nv + vs];
-      }
-      if (occ_before + 1 > K) continue;
-      Walk S{pv.m_base_t[a * nv + vs], pv.m_base_c[a * nv + vs], occ_before};
-      double cld_new = 0.0;
-      if (walk_stop(S, to_o[a], 1, rq, T, pv, 0.0, &cld_new) >= 0) continue;   // late pickup
-      int occ_after = occ_before;      // occupancy of the unmodified plan after stop b-1
-      for (int b = a; b <= L; ++b) {
-        // ---- candidate (a, b): drop-off now, then the rest of the plan
-        Walk W = S;
-        double dummy;
-        if (walk_stop(W, b == a ? od : to_d[b], -1, rq, T, pv, cld_new, &dummy) < 0) {
-          bool ok = true;
-          for (int k = b; k < L; ++k) {
-            const int pod = pv.m_pod[k * nv + vs], q = pv.m_req[k * nv + vs];
-            double cld_drop = 0.0;
-            if (pod < 0) { const int pk = pv.m_partner[k * nv + vs]; cld_drop = pk >= 0 ? cld_cur[pk] : pv.q_cld[q]; }
-            if (walk_stop(W, k == b ? from_d[k] : pv.m_seg[k * nv + vs], pod, q, T, pv, cld_drop, &cld_cur[k]) >= 0) { ok = false; break; }
-          }
-          if (ok && W.c < cmin) cmin = W.c;
+    const int o = pv.q_o[rq];
+    if (STAGED) {
+      if (tid == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)), "r"((uint32_t)row_bytes) : "memory");
+        const char* src = reinterpret_cast<const char*>(dv.dist) + (size_t)o * row_bytes;
+        for (size_t off = 0; off < row_bytes; off += 32768) {
+          const uint32_t bytes = (uint32_t)min((size_t)32768, row_bytes - off);
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(smem_u32(reach_smem + off)), "l"(src + off), "r"(bytes), "r"(smem_u32(&bar)) : "memory");
         }
-        // ---- serve plan stop b with the new rider on board
-        if (b == L) break;
-        const int pod = pv.m_pod[b * nv + vs], q = pv.m_req[b * nv + vs];
-        occ_after += pod;
-        if (occ_after + 1 > K) break;                   // over capacity for every larger b
-        double cld_drop = 0.0;
-        if (pod < 0) { const int pk = pv.m_partner[b * nv + vs]; cld_drop = pk >= 0 ? cld_cur[pk] : pv.q_cld[q]; }
-        if (walk_stop(S, b == a ? from_o[b] : pv.m_seg[b * nv + vs], pod, q, T, pv, cld_drop, &cld_cur[b]) >= 0) break;
+      }
+      // wait for the bytes (all threads; try_wait suspends the warp in hardware for a bounded time)
+      uint32_t landed = 0;
+      while (!landed)
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(landed) : "r"(smem_u32(&bar)), "r"(phase) : "memory");
+      phase ^= 1;
+    }
+    const float limit = reach_limit(pv, rq);
+    uint32_t* mrow = mask + (size_t)r * words;
+    for (int vs0 = tid - lane; vs0 < nv; vs0 += 1024) {
+      const int vs = vs0 + lane;
+      bool reach = false;
+      if (vs < nv) {
+        const int ns = pv.m_nslots[vs];
+        for (int a = 0; a < ns; ++a) {
+          const int x = a == 0 ? pv.node[vs] : pv.m_node[(a - 1) * nv + vs];
+          float w;
+          if (STAGED) {
+            w = dv.mode == DRS_MODE_F32 ? frow[x] : (irow[x] >= DRS_I32_INF ? __int_as_float(0x7f800000) : __int2float_rd(irow[x]));
+          } else {
+            const double wd = tt_into(dv, pv.directed, o, x);
+            w = __double2float_rd(wd);
+          }
+          if (pv.m_lb[a * nv + vs] + w <= limit) { reach = true; break; }
+        }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, reach);
+      if (lane == 0) mrow[vs0 >> 5] = m;
+      if (m) {
+        int b0 = 0;
+        if (lane == 0) b0 = atomicAdd(&counters[0], __popc(m));
+        b0 = __shfl_sync(0xffffffffu, b0, 0);
+        if (reach) {
+          const int pos = b0 + __popc(m & ((1u << lane) - 1u));
+          if (pos < list_cap) list[pos] = make_int2(r, vs);
+        }
       }
     }
   }
-  cmin_out[(int64_t)r * nv + v] = cmin;
 }
 
-// Fold: one WARP per request.  Lanes read the smallest costs of 32 consecutive
-// vehicles (four chunks ahead: the walk is a chain of dependent decisions, the loads are not); only flagged vehicles
-// are re-scanned (by their lane) in vehicle order with the running bound.
-__global__ void insertion_fold_kernel(PlanView pv, DistView dv, int n_new, const int32_t* new_rows, const double* cmin,
-                                       int32_t* best_veh, int32_t* best_i, int32_t* best_j, double* best_dc) {
-  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+// ------------------------------------------------------------------------------------------------ evaluation
+// Smallest successful total cost of one (request, vehicle) pair over all (i, j), WITHOUT the incumbent bound:
+//   * the unmodified-plan prefix is shared (precomputed per vehicle), the state "pickup inserted after a stops, b-a
+//     further stops served" is advanced incrementally over b, and only the tail after the drop-off is re-walked per
+//     candidate.  Arithmetic and operation order per candidate are those of eval_candidate; only successes matter
+//     here, so no viol codes.
+__device__ double pair_cmin(const PlanView& pv, const DistView& dv, int rq, int vs) {
+  const int nv = pv.n_veh;
+  const double inf = d_inf();
+  const int L = pv.len[vs];
+  double cmin = inf;
+  const int bviol = pv.m_base_viol[vs];
+  if (bviol < 0) return inf;
+  const int o = pv.q_o[rq], d = pv.q_d[rq];
+  const int K = pv.cap[vs];
+  const double T = pv.clock[vs];
+  double to_o[INS_MAXL + 1], to_d[INS_MAXL + 1], from_o[INS_MAXL], from_d[INS_MAXL], cld_cur[INS_MAXL];
+  // origin-side travel times first: most vehicles cannot reach the pickup in time at any position, and
+  // for those the destination-side gathers (half of the traffic) are never needed
+  const int start = pv.node[vs];
+  to_o[0] = tt_into(dv, pv.directed, o, start);
+  for (int k = 0; k < L; ++k) {
+    const int nd = pv.m_node[k * nv + vs];
+    from_o[k] = tt_outof(dv, o, nd);
+    to_o[k + 1] = pv.directed ? tt_into(dv, 1, o, nd) : from_o[k];
+  }
+  bool reachable = false;
+  {
+    const double clp = pv.q_clp[rq], cep = pv.q_cep[rq];
+    for (int a = 0; a <= L && a <= bviol; ++a) {
+      const double t = pv.m_base_t[a * nv + vs] + to_o[a];      // same sum walk_stop forms for the pickup
+      if (T + t < cep || !(T + t > clp)) { reachable = true; break; }
+    }
+  }
+  if (!reachable) return inf;
+  to_d[0] = tt_into(dv, pv.directed, d, start);
+  for (int k = 0; k < L; ++k) {
+    const int nd = pv.m_node[k * nv + vs];
+    from_d[k] = tt_outof(dv, d, nd);
+    to_d[k + 1] = pv.directed ? tt_into(dv, 1, d, nd) : from_d[k];
+  }
+  const double od = tt_outof(dv, o, d);
+  int occ_before = pv.onboard[vs];   // occupancy before plan stop a in the unmodified plan
+  for (int a = 0; a <= L && a <= bviol; ++a) {
+    if (a > 0) {
+      cld_cur[a - 1] = pv.m_base_cld[(a - 1) * nv + vs];
+      occ_before += pv.m_pod[(a - 1) * nv + vs];
+    }
+    if (occ_before + 1 > K) continue;
+    Walk S{pv.m_base_t[a * nv + vs], pv.m_base_c[a * nv + vs], occ_before};
+    double cld_new = 0.0;
+    if (walk_stop(S, to_o[a], 1, rq, T, pv, 0.0, &cld_new) >= 0) continue;   // late pickup
+    int occ_after = occ_before;      // occupancy of the unmodified plan after stop b-1
+    for (int b = a; b <= L; ++b) {
+      // ---- candidate (a, b): drop-off now, then the rest of the plan
+      Walk W = S;
+      double dummy;
+      if (walk_stop(W, b == a ? od : to_d[b], -1, rq, T, pv, cld_new, &dummy) < 0) {
+        bool ok = true;
+        for (int k = b; k < L; ++k) {
+          const int pod = pv.m_pod[k * nv + vs], q = pv.m_req[k * nv + vs];
+          double cld_drop = 0.0;
+          if (pod < 0) { const int pk = pv.m_partner[k * nv + vs]; cld_drop = pk >= 0 ? cld_cur[pk] : pv.q_cld[q]; }
+          if (walk_stop(W, k == b ? from_d[k] : pv.m_seg[k * nv + vs], pod, q, T, pv, cld_drop, &cld_cur[k]) >= 0) { ok = false; break; }
+        }
+        if (ok && W.c < cmin) cmin = W.c;
+      }
+      // ---- serve plan stop b with the new rider on board
+      if (b == L) break;
+      const int pod = pv.m_pod[b * nv + vs], q = pv.m_req[b * nv + vs];
+      occ_after += pod;
+      if (occ_after + 1 > K) break;                   // over capacity for every larger b
+      double cld_drop = 0.0;
+      if (pod < 0) { const int pk = pv.m_partner[b * nv + vs]; cld_drop = pk >= 0 ? cld_cur[pk] : pv.q_cld[q]; }
+      if (walk_stop(S, b == a ? from_o[b] : pv.m_seg[b * nv + vs], pod, q, T, pv, cld_drop, &cld_cur[b]) >= 0) break;
+    }
+  }
+  return cmin;
+}
+
+__global__ void __launch_bounds__(128) insertion_eval_kernel(PlanView pv, DistView dv, const int32_t* __restrict__ new_rows,
+                                                             const int2* __restrict__ list, const int* __restrict__ counters, int list_cap,
+                                                             double* __restrict__ cmin_out) {
+  const int n = min(counters[0], list_cap);
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+    const int2 e = list[idx];
+    cmin_out[(int64_t)e.x * pv.n_veh + e.y] = pair_cmin(pv, dv, new_rows[e.x], e.y);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ fold
+// One WARP per request.  Lanes read the smallest costs of 32 consecutive vehicles IN THE CALLER'S ORDER (eight chunks
+// ahead: the walk is a chain of dependent decisions, the loads are not); only flagged vehicles are re-scanned (by
+// their lane) with the running bound.  r_first / r_count select the requests (the sequential queue folds one at a time).
+__global__ void insertion_fold_kernel(PlanView pv, DistView dv, int r_first, int r_count, const int32_t* new_rows, const uint32_t* mask,
+                                      int words, const double* cmin, int32_t* best_veh, int32_t* best_i, int32_t* best_j, double* best_dc) {
+  const int rr = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (r >= n_new) return;
-  const double inf = __longlong_as_double(0x7ff0000000000000LL);
+  if (rr >= r_count) return;
+  const int r = r_first + rr;
+  const double inf = d_inf();
   double dc = inf;                   // dc_ = np.inf (:1452)
   int wv = -1, wi = -1, wj = -1;
-  constexpr int AHEAD = 8;   // chunks of 32 vehicles whose costs are loaded together: the loads do not depend on the incumbent
+  const uint32_t* mrow = mask + (size_t)r * words;
+  constexpr int AHEAD = 8;
   for (int base0 = 0; base0 < pv.n_veh; base0 += 32 * AHEAD) {
     double cms[AHEAD], c0s[AHEAD];
+    int vss[AHEAD];
 #pragma unroll
     for (int u = 0; u < AHEAD; ++u) {
       const int v = base0 + 32 * u + lane;
-      cms[u] = inf; c0s[u] = 0.0;
-      if (v < pv.n_veh) { cms[u] = cmin[(int64_t)r * pv.n_veh + v]; c0s[u] = pv.cost[v]; }
+      cms[u] = inf; c0s[u] = 0.0; vss[u] = 0;
+      if (v < pv.n_veh) {
+        const int vs = pv.inv[v];
+        vss[u] = vs;
+        if ((mrow[vs >> 5] >> (vs & 31)) & 1u) { cms[u] = cmin[(int64_t)r * pv.n_veh + vs]; c0s[u] = pv.cost[vs]; }
+      }
     }
 #pragma unroll
     for (int u = 0; u < AHEAD; ++u) {
       const int v = base0 + 32 * u + lane;
       const double cm = cms[u], c0 = c0s[u];
-      unsigned mask = __ballot_sync(0xffffffffu, cm != inf && !(cm > c0 + dc));
-      while (mask) {
-        const int l = __ffs(mask) - 1;
-        mask &= mask - 1;
+      unsigned m = __ballot_sync(0xffffffffu, cm != inf && !(cm > c0 + dc));
+      while (m) {
+        const int l = __ffs(m) - 1;
+        m &= m - 1;
         double ndc = dc; int nv = wv, ni = wi, nj = wj;
         if (lane == l && !(cm > c0 + dc)) {              // re-check: dc may have dropped inside this chunk
           Pair p;
-          load_pair(p, pv, dv, v, new_rows[r]);
+          load_pair(p, pv, dv, vss[u], new_rows[r]);
           int viol = -1;
           for (int i = 0; i <= p.L; ++i) {                         // (:1466-1482)
             for (int j = i + 1; j <= p.L + 1; ++j) {
@@ -391,32 +518,213 @@ __global__ void insertion_fold_kernel(PlanView pv, DistView dv, int n_new, const
   if (lane == 0) { best_veh[r] = wv; best_i[r] = wi; best_j[r] = wj; best_dc[r] = dc; }
 }
 
+// ------------------------------------------------------------------------------------------------ commit
+// What Veh.build_route(router, route_, reqs, T) leaves behind for the next scan (lib/Agents.py:148-297), for the
+// winner of request r: the route with the pickup inserted at i and the drop-off at j (:1468-1469), veh.c (:256-270),
+// pwt of the requests still to be picked up (:165-220), and -- when the vehicle had no route -- the first step of
+// the new one, which a later build_route would keep (:319-336).  One thread; then the vehicle is re-prepared.
+__device__ void commit_one(const PlanView& pv, const DistView& dv, const PredSource& ps, const int32_t* esrc, const int32_t* edst,
+                           const double* tt64, int rq, int v, int i, int j, double T_now, int* err) {
+  const int nv = pv.n_veh;
+  const int vs = pv.inv[v];
+  const int L = pv.len[vs];
+  if (L + 2 > INS_MAXL || i < 0 || i > L || j <= i || j > L + 1) { *err = 1; return; }
+  int node[INS_MAXL], req[INS_MAXL];
+  int8_t pod[INS_MAXL];
+  {
+    int k2 = 0;
+    for (int k = 0; k <= L; ++k) {                       // route.insert(i, pickup)
+      if (k == i) { node[k2] = pv.q_o[rq]; req[k2] = rq; pod[k2] = 1; ++k2; }
+      if (k < L) { node[k2] = pv.m_node[k * nv + vs]; req[k2] = pv.m_req[k * nv + vs]; pod[k2] = pv.m_pod[k * nv + vs]; ++k2; }
+    }
+    for (int k = L + 1; k > j; --k) { node[k] = node[k - 1]; req[k] = req[k - 1]; pod[k] = pod[k - 1]; }   // route.insert(j, drop-off)
+    node[j] = pv.q_d[rq]; req[j] = rq; pod[j] = -1;
+  }
+  const int L2 = L + 2;
+  for (int k = 0; k < L2; ++k) {
+    int8_t partner = -1;
+    if (pod[k] < 0)
+      for (int m = 0; m < k; ++m)
+        if (req[m] == req[k] && pod[m] > 0) partner = (int8_t)m;
+    pv.m_node[k * nv + vs] = node[k]; pv.m_req[k * nv + vs] = req[k]; pv.m_pod[k * nv + vs] = pod[k]; pv.m_partner[k * nv + vs] = partner;
+  }
+  pv.len[vs] = L2;
+  const bool merge = pv.keep_node[vs] >= 0;              // len(self.route) > 0 (:156-160)
+  for (int k = 0; k < L2; ++k)
+    if (pod[k] > 0) pv.q_pwt[req[k]] = merge ? 0.0 + pv.keep_et[vs] : 0.0;
+  int cur = merge ? pv.keep_node[vs] : pv.pos_node[vs];
+  if (cur < 0) { *err = 2; return; }                     // a vehicle without a route must stand on a vertex
+  const int first_from = cur;
+  double vt = merge ? 0.0 + pv.keep_t[vs] : 0.0;
+  double c = 0.0, t = 0.0;
+  int n = pv.onboard[vs];
+  for (int k = 0; k < L2; ++k) {
+    const double pred_t = (cur == node[k]) ? 0.0 : dv.at(cur, node[k]);
+    double t_leg = pred_t;
+    if (pod[k] > 0 && T_now + vt + t_leg < pv.q_cep[req[k]]) t_leg += pv.q_cep[req[k]] - (T_now + vt + t_leg);   // add_leg waits (:363-367)
+    vt += t_leg;
+    for (int m = k; m < L2; ++m)
+      if (pod[m] > 0) pv.q_pwt[req[m]] += pred_t;        // every request not yet picked up, this one included (:214-220)
+    const double leg_t = (k == 0 && merge) ? pv.keep_t[vs] + t_leg : t_leg;   // the kept step joins the first leg (:222-240)
+    t += leg_t;
+    c += n * leg_t * pv.prm.coef_inveh;
+    n += pod[k];
+    if (pod[k] > 0) c += t * pv.prm.coef_wait;
+    cur = node[k];
+  }
+  pv.cost[vs] = c;
+  if (!merge) {
+    // first step of the leg first_from -> node[0] along the canonical path: walk the predecessor chain back from the stop
+    int hop_to = node[0];
+    double hop_t = 0.0;
+    if (first_from != node[0]) {
+      int x = node[0], guard = 0;
+      while (x != first_from && guard++ < (1 << 22)) {
+        const int e = ps.last_edge(first_from, x);
+        if (e < 0) { *err = 3; break; }
+        const int y = prev_node(e, x, esrc, edst);
+        if (y == first_from) { hop_to = x; hop_t = tt64[e]; }
+        x = y;
+      }
+    } else {
+      hop_to = first_from;                               // zero-length leg: the dummy stay-in-place step (lib/RoutingEngine.py:173-189)
+    }
+    pv.keep_node[vs] = hop_to; pv.keep_t[vs] = hop_t; pv.keep_et[vs] = hop_t;
+  }
+  plan_prep(pv, dv, vs);
+}
+
+__global__ void insertion_commit_kernel(PlanView pv, DistView dv, PredSource ps, const int32_t* esrc, const int32_t* edst, const double* tt64,
+                                        const int32_t* new_rows, int r, const int32_t* best_veh, const int32_t* best_i,
+                                        const int32_t* best_j, double T_now, int* err) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  const int v = best_veh[r];
+  if (v < 0) return;
+  commit_one(pv, dv, ps, esrc, edst, tt64, new_rows[r], v, best_i[r], best_j[r], T_now, err);
+}
+
+__global__ void insertion_commit_explicit_kernel(PlanView pv, DistView dv, PredSource ps, const int32_t* esrc, const int32_t* edst,
+                                                 const double* tt64, int rq, int v, int i, int j, double T_now, int* err) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  commit_one(pv, dv, ps, esrc, edst, tt64, rq, v, i, j, T_now, err);
+}
+
+// the committed vehicle's column for the requests still in the queue (rows r+1 ..): exact re-evaluation, mask bit and cost
+__global__ void insertion_rescan_kernel(PlanView pv, DistView dv, int n_new, const int32_t* new_rows, int r, const int32_t* best_veh,
+                                        uint32_t* mask, int words, double* cmin) {
+  const int v = best_veh[r];
+  if (v < 0) return;
+  const int vs = pv.inv[v];
+  for (int r2 = r + 1 + blockIdx.x * blockDim.x + threadIdx.x; r2 < n_new; r2 += gridDim.x * blockDim.x) {
+    const double cm = pair_cmin(pv, dv, new_rows[r2], vs);
+    uint32_t* w = mask + (size_t)r2 * words + (vs >> 5);
+    if (cm != d_inf()) { cmin[(int64_t)r2 * pv.n_veh + vs] = cm; atomicOr(w, 1u << (vs & 31)); }
+    else atomicAnd(w, ~(1u << (vs & 31)));
+  }
+}
+
 }  // namespace
 
+// ====================================================================================================== host side
 struct LegacyDev {
-  int n_veh = 0, n_stops = 0, n_rows = 0;
-  int32_t *node = nullptr, *onboard = nullptr, *cap = nullptr, *off = nullptr, *s_node = nullptr, *s_req = nullptr;
-  double *delay = nullptr, *clock = nullptr, *cost = nullptr;
-  int8_t* s_pod = nullptr;
-  int32_t *q_o = nullptr, *q_d = nullptr;
-  double *q_cep = nullptr, *q_clp = nullptr, *q_cld = nullptr, *q_ts = nullptr, *q_tr = nullptr, *q_pwt = nullptr;
-  int32_t *perm = nullptr, *m_node = nullptr, *m_req = nullptr, *m_base_viol = nullptr;
-  int8_t *m_pod = nullptr, *m_partner = nullptr;
-  double *m_seg = nullptr, *m_base_t = nullptr, *m_base_c = nullptr, *m_base_cld = nullptr;
-  drs_insertion_params prm{1.5, 1.0, 1.5, 3.0};
+  int n_veh = 0, n_rows = 0;
+  DrsArena veh, tab, res;            // grow-only device allocations: vehicles + plans, request table, per-evaluation buffers
+  PlanView pv{};
+  std::vector<int32_t> h_perm, h_len;
+  // per-evaluation buffers (slices of `res`)
+  int cap_new = 0, words = 0, list_cap = 0;
+  int32_t *d_rows = nullptr, *d_bv = nullptr, *d_bi = nullptr, *d_bj = nullptr;
+  double *d_dc = nullptr, *d_cmin = nullptr;
+  uint32_t* d_mask = nullptr;
+  int2* d_list = nullptr;
+  int* d_counters = nullptr;         // [0] list fill, [1] next request, [2] commit error
+  int64_t base_candidates = 0;       // sum over vehicles of (L+1)(L+2)/2 for the plans as they are now
+  bool prepared = false, full_list = false, list_is_full = false;
+  std::vector<int32_t> h_rows;       // the new-request rows of the running call
 };
 
 void drs_tick_free_plans(drs_tick* t) {
   LegacyDev* d = t->legacy;
   if (!d) return;
-  void* ptrs[] = {d->node, d->onboard, d->cap, d->off, d->s_node, d->s_req, d->delay, d->clock, d->cost, d->s_pod,
-                  d->q_o, d->q_d, d->q_cep, d->q_clp, d->q_cld, d->q_ts, d->q_tr, d->q_pwt, d->perm, d->m_node, d->m_req,
-                  d->m_base_viol, d->m_pod, d->m_partner, d->m_seg, d->m_base_t, d->m_base_c, d->m_base_cld};
-  for (void* p : ptrs)
-    if (p) cudaFree(p);
+  d->veh.release(); d->tab.release(); d->res.release();
   delete d;
   t->legacy = nullptr;
 }
+
+namespace {
+
+int64_t candidates_of(int L) { return (int64_t)(L + 1) * (L + 2) / 2; }
+
+// (re)allocates the per-evaluation buffers for n_new requests; pointers stay valid while n_new does not grow
+int ensure_eval_buffers(LegacyDev& d, int n_new) {
+  const int nv = std::max(d.n_veh, 1);
+  const int words = (nv + 31) / 32;
+  if (n_new <= d.cap_new && words == d.words && d.d_rows && d.full_list == d.list_is_full) return DRS_OK;
+  const int cap = std::max(n_new, d.cap_new);
+  const int64_t pairs = (int64_t)cap * nv;
+  // survivors of the reach test are ~1 % of the pairs; the list starts at a quarter and grows to all pairs if it ever overflows
+  const int list_cap = (int)(d.full_list ? pairs : std::min<int64_t>(pairs, std::max<int64_t>(65536, pairs / 4)));
+  d.list_is_full = d.full_list;
+  DrsArenaLayout lay;
+  const size_t o_rows = lay.add(sizeof(int32_t) * cap), o_bv = lay.add(sizeof(int32_t) * cap), o_bi = lay.add(sizeof(int32_t) * cap),
+               o_bj = lay.add(sizeof(int32_t) * cap), o_dc = lay.add(sizeof(double) * cap), o_cnt = lay.add(sizeof(int) * 4),
+               o_mask = lay.add(sizeof(uint32_t) * (size_t)cap * words), o_list = lay.add(sizeof(int2) * (size_t)list_cap),
+               o_cmin = lay.add(sizeof(double) * (size_t)pairs);
+  int rc = d.res.reserve(lay.total);
+  if (rc) return rc;
+  unsigned char* b = (unsigned char*)d.res.ptr;
+  d.d_rows = (int32_t*)(b + o_rows); d.d_bv = (int32_t*)(b + o_bv); d.d_bi = (int32_t*)(b + o_bi); d.d_bj = (int32_t*)(b + o_bj);
+  d.d_dc = (double*)(b + o_dc); d.d_counters = (int*)(b + o_cnt); d.d_mask = (uint32_t*)(b + o_mask); d.d_list = (int2*)(b + o_list);
+  d.d_cmin = (double*)(b + o_cmin);
+  d.cap_new = cap; d.words = words; d.list_cap = list_cap;
+  return DRS_OK;
+}
+
+// reach test + evaluation of every (request, vehicle) pair against the plans as they are now
+int scan_all(drs_tick* t, LegacyDev& d, int n_new, cudaStream_t st) {
+  const drs_graph* g = t->g;
+  DistView dv{g->d_dist, g->ld, g->mode};
+  if (!d.prepared) {
+    plan_prep_kernel<<<(d.n_veh + 127) / 128, 128, 0, st>>>(d.pv, dv);
+    drs_count_launch();
+    d.prepared = true;
+  }
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g->device);
+  const size_t row_bytes = (size_t)g->ld * 4;
+  const char* env = getenv("DRS_INS_STAGED");
+  const bool staged = !g->directed && row_bytes <= 220 * 1024 && row_bytes % 16 == 0 && !(env && env[0] == '0');
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    DRS_CUDA(cudaMemsetAsync(d.d_counters, 0, sizeof(int) * 4, st));
+    const int grid = std::max(1, std::min(n_new, sms));
+    if (staged) {
+      DRS_CUDA(cudaFuncSetAttribute(insertion_reach_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_bytes));
+      insertion_reach_kernel<true><<<grid, 1024, row_bytes, st>>>(d.pv, dv, n_new, d.d_rows, d.d_mask, d.words, d.d_list, d.list_cap, d.d_counters);
+    } else {
+      insertion_reach_kernel<false><<<grid, 1024, 0, st>>>(d.pv, dv, n_new, d.d_rows, d.d_mask, d.words, d.d_list, d.list_cap, d.d_counters);
+    }
+    drs_count_launch();
+    DRS_CUDA(cudaGetLastError());
+    const int64_t pairs = (int64_t)n_new * d.n_veh;
+    if (d.list_cap >= pairs) break;                    // the list cannot overflow
+    int fill = 0;
+    DRS_CUDA(cudaMemcpyAsync(&fill, d.d_counters, sizeof(int), cudaMemcpyDeviceToHost, st));
+    DRS_CUDA(cudaStreamSynchronize(st));
+    if (fill <= d.list_cap) break;
+    // more survivors than the list holds (dense demand around the fleet): size it for every pair and redo the reach test
+    d.full_list = true;
+    int rc = ensure_eval_buffers(d, n_new);
+    if (rc) return rc;
+    DRS_CUDA(cudaMemcpyAsync(d.d_rows, d.h_rows.data(), sizeof(int32_t) * n_new, cudaMemcpyHostToDevice, st));
+  }
+  const int eval_blocks = std::max(1, std::min(sms * 8, (d.list_cap + 127) / 128));
+  insertion_eval_kernel<<<eval_blocks, 128, 0, st>>>(d.pv, dv, d.d_rows, d.d_list, d.d_counters, d.list_cap, d.d_cmin);
+  drs_count_launch();
+  DRS_CUDA(cudaGetLastError());
+  return DRS_OK;
+}
+
+}  // namespace
 
 extern "C" int drs_tick_set_plans(drs_tick* t, const drs_plan_batch* b, const drs_request_table* q,
                                   const drs_insertion_params* prm) {
@@ -428,15 +736,16 @@ extern "C" int drs_tick_set_plans(drs_tick* t, const drs_plan_batch* b, const dr
   DRS_REQUIRE(nq == 0 || (q->o_node && q->d_node && q->Cep && q->Clp && q->Cld && q->Ts && q->Tr && q->pwt), DRS_ERR_ARG,
               "drs_tick_set_plans: null request-table array");
   const int n = t->g->n;
-  const int nstops = nv ? b->stop_off[nv] : 0;
   for (int v = 0; v < nv; ++v) {
     DRS_REQUIRE(b->start_node[v] >= 0 && b->start_node[v] < n, DRS_ERR_RANGE, "drs_tick_set_plans: vehicle %d node out of range", v);
     const int cnt = b->stop_off[v + 1] - b->stop_off[v];
-    DRS_REQUIRE(cnt >= 0 && cnt <= MAXL, DRS_ERR_ARG, "drs_tick_set_plans: vehicle %d has %d planned stops (max %d)", v, cnt, MAXL);
+    DRS_REQUIRE(cnt >= 0 && cnt <= INS_MAXL, DRS_ERR_ARG, "drs_tick_set_plans: vehicle %d has %d planned stops (max %d)", v, cnt, INS_MAXL);
     for (int s = b->stop_off[v]; s < b->stop_off[v + 1]; ++s) {
       DRS_REQUIRE(b->stop_node[s] >= 0 && b->stop_node[s] < n, DRS_ERR_RANGE, "drs_tick_set_plans: stop %d node out of range", s);
       DRS_REQUIRE(b->stop_req[s] >= 0 && b->stop_req[s] < nq, DRS_ERR_RANGE, "drs_tick_set_plans: stop %d request row out of range", s);
     }
+    if (b->keep_node) DRS_REQUIRE(b->keep_node[v] >= -1 && b->keep_node[v] < n, DRS_ERR_RANGE, "drs_tick_set_plans: vehicle %d kept-step node out of range", v);
+    if (b->pos_node) DRS_REQUIRE(b->pos_node[v] >= -1 && b->pos_node[v] < n, DRS_ERR_RANGE, "drs_tick_set_plans: vehicle %d position node out of range", v);
   }
   for (int r = 0; r < nq; ++r)
     DRS_REQUIRE(q->o_node[r] >= 0 && q->o_node[r] < n && q->d_node[r] >= 0 && q->d_node[r] < n, DRS_ERR_RANGE,
@@ -445,117 +754,271 @@ extern "C" int drs_tick_set_plans(drs_tick* t, const drs_plan_batch* b, const dr
   cudaStream_t st = t->g->stream;
   if (!t->legacy) t->legacy = new LegacyDev();
   LegacyDev& d = *t->legacy;
-  int rc;
-  if ((rc = drs_upload(&d.node, b->start_node, nv, st)) || (rc = drs_upload(&d.delay, b->start_delay, nv, st)) ||
-      (rc = drs_upload(&d.onboard, b->onboard, nv, st)) || (rc = drs_upload(&d.clock, b->clock, nv, st)) ||
-      (rc = drs_upload(&d.cap, b->capacity, nv, st)) || (rc = drs_upload(&d.cost, b->cost, nv, st)) ||
-      (rc = drs_upload(&d.off, b->stop_off, nv ? nv + 1 : 0, st)) || (rc = drs_upload(&d.s_node, b->stop_node, nstops, st)) ||
-      (rc = drs_upload(&d.s_req, b->stop_req, nstops, st)) || (rc = drs_upload(&d.s_pod, b->stop_pod, nstops, st)) ||
-      (rc = drs_upload(&d.q_o, q->o_node, nq, st)) || (rc = drs_upload(&d.q_d, q->d_node, nq, st)) ||
-      (rc = drs_upload(&d.q_cep, q->Cep, nq, st)) || (rc = drs_upload(&d.q_clp, q->Clp, nq, st)) ||
-      (rc = drs_upload(&d.q_cld, q->Cld, nq, st)) || (rc = drs_upload(&d.q_ts, q->Ts, nq, st)) ||
-      (rc = drs_upload(&d.q_tr, q->Tr, nq, st)) || (rc = drs_upload(&d.q_pwt, q->pwt, nq, st)))
-    return rc;
-  // slot-major copy, vehicles sorted by plan length, then by start vertex (neighbouring lanes gather neighbouring
-  // columns of the request's rows: vertex ids are spatially coherent under the host layer's locality numbering)
-  std::vector<int32_t> perm(std::max(nv, 1));
-  for (int v = 0; v < nv; ++v) perm[v] = v;
-  std::stable_sort(perm.begin(), perm.begin() + nv, [&](int x, int y) {
+  // vehicles sorted by plan length, then by start vertex (neighbouring lanes run the same trip counts and gather
+  // neighbouring columns: vertex ids are spatially coherent under the host layer's locality numbering)
+  const int nvp = std::max(nv, 1);
+  d.h_perm.resize(nvp);
+  for (int v = 0; v < nv; ++v) d.h_perm[v] = v;
+  std::stable_sort(d.h_perm.begin(), d.h_perm.begin() + nv, [&](int x, int y) {
     const int lx = b->stop_off[x + 1] - b->stop_off[x], ly = b->stop_off[y + 1] - b->stop_off[y];
     return lx != ly ? lx < ly : b->start_node[x] < b->start_node[y];
   });
-  const size_t slots = (size_t)(MAXL + 1) * std::max(nv, 1);
-  std::vector<int32_t> m_node(slots, 0), m_req(slots, 0);
-  std::vector<int8_t> m_pod(slots, 0), m_partner(slots, -1);
+  // ---- one host image of the vehicle-side arrays, one copy
+  DrsArenaLayout lv;
+  const size_t slots = (size_t)INS_MAXL * nvp, slots1 = (size_t)(INS_MAXL + 1) * nvp;
+  const size_t o_perm = lv.add(4 * nvp), o_inv = lv.add(4 * nvp), o_node = lv.add(4 * nvp), o_onb = lv.add(4 * nvp), o_cap = lv.add(4 * nvp),
+               o_len = lv.add(4 * nvp), o_delay = lv.add(8 * nvp), o_clock = lv.add(8 * nvp), o_cost = lv.add(8 * nvp), o_pos = lv.add(4 * nvp),
+               o_kn = lv.add(4 * nvp), o_kt = lv.add(8 * nvp), o_ke = lv.add(8 * nvp), o_mnode = lv.add(4 * slots), o_mreq = lv.add(4 * slots),
+               o_mpod = lv.add(slots), o_mpar = lv.add(slots);
+  const size_t upload_bytes = lv.total;
+  const size_t o_seg = lv.add(8 * slots), o_bt = lv.add(8 * slots1), o_bc = lv.add(8 * slots1), o_bcld = lv.add(8 * slots), o_bv = lv.add(4 * nvp),
+               o_lb = lv.add(4 * slots1), o_ns = lv.add(nvp);
+  int rc = d.veh.reserve(lv.total);
+  if (rc) return rc;
+  std::vector<unsigned char>& img = d.veh.host;
+  img.assign(upload_bytes, 0);
+  auto I32 = [&](size_t o) { return (int32_t*)(img.data() + o); };
+  auto F64 = [&](size_t o) { return (double*)(img.data() + o); };
+  auto I8 = [&](size_t o) { return (int8_t*)(img.data() + o); };
+  d.h_len.assign(nvp, 0);
+  d.base_candidates = 0;
   for (int vs = 0; vs < nv; ++vs) {
-    const int v = perm[vs], s0 = b->stop_off[v], L = b->stop_off[v + 1] - s0;
+    const int v = d.h_perm[vs], s0 = b->stop_off[v], L = b->stop_off[v + 1] - s0;
+    I32(o_perm)[vs] = v; I32(o_inv)[v] = vs;
+    I32(o_node)[vs] = b->start_node[v]; I32(o_onb)[vs] = b->onboard[v]; I32(o_cap)[vs] = b->capacity[v]; I32(o_len)[vs] = L;
+    F64(o_delay)[vs] = b->start_delay[v]; F64(o_clock)[vs] = b->clock[v]; F64(o_cost)[vs] = b->cost[v];
+    // defaults: a vehicle with no delay stands on its start vertex; one under way keeps the step it is on
+    const int pos = b->pos_node ? b->pos_node[v] : (b->start_delay[v] == 0.0 ? b->start_node[v] : -1);
+    int kn = b->keep_node ? b->keep_node[v] : (b->start_delay[v] != 0.0 || L > 0 ? b->start_node[v] : -1);
+    I32(o_pos)[vs] = pos; I32(o_kn)[vs] = kn;
+    F64(o_kt)[vs] = b->keep_t ? b->keep_t[v] : b->start_delay[v];
+    F64(o_ke)[vs] = b->keep_et ? b->keep_et[v] : F64(o_kt)[vs];
+    d.h_len[vs] = L;
+    d.base_candidates += candidates_of(L);
     for (int k = 0; k < L; ++k) {
       const size_t at = (size_t)k * nv + vs;
-      m_node[at] = b->stop_node[s0 + k]; m_req[at] = b->stop_req[s0 + k]; m_pod[at] = b->stop_pod[s0 + k];
-      if (b->stop_pod[s0 + k] < 0)   // plan index of the pickup that belongs to this drop-off (-1: rider on board)
+      I32(o_mnode)[at] = b->stop_node[s0 + k]; I32(o_mreq)[at] = b->stop_req[s0 + k]; I8(o_mpod)[at] = b->stop_pod[s0 + k];
+      int8_t partner = -1;
+      if (b->stop_pod[s0 + k] < 0)
         for (int m = 0; m < k; ++m)
-          if (b->stop_req[s0 + m] == b->stop_req[s0 + k] && b->stop_pod[s0 + m] > 0) m_partner[at] = (int8_t)m;
+          if (b->stop_req[s0 + m] == b->stop_req[s0 + k] && b->stop_pod[s0 + m] > 0) partner = (int8_t)m;
+      I8(o_mpar)[at] = partner;
     }
   }
-  if ((rc = drs_upload(&d.perm, perm.data(), nv, st)) || (rc = drs_upload(&d.m_node, m_node.data(), slots, st)) ||
-      (rc = drs_upload(&d.m_req, m_req.data(), slots, st)) || (rc = drs_upload(&d.m_pod, m_pod.data(), slots, st)) ||
-      (rc = drs_upload(&d.m_partner, m_partner.data(), slots, st)))
-    return rc;
-  void** scratch[] = {(void**)&d.m_seg, (void**)&d.m_base_t, (void**)&d.m_base_c, (void**)&d.m_base_cld, (void**)&d.m_base_viol};
-  const size_t bytes[] = {sizeof(double) * slots, sizeof(double) * slots, sizeof(double) * slots, sizeof(double) * slots,
-                          sizeof(int32_t) * std::max(nv, 1)};
-  for (int i = 0; i < 5; ++i) {
-    if (*scratch[i]) { cudaFree(*scratch[i]); *scratch[i] = nullptr; }
-    DRS_CUDA(cudaMalloc(scratch[i], bytes[i]));
+  DRS_CUDA(cudaMemcpyAsync(d.veh.ptr, img.data(), upload_bytes, cudaMemcpyHostToDevice, st));
+  // ---- request table
+  DrsArenaLayout lt;
+  const int nqp = std::max(nq, 1);
+  const size_t t_o = lt.add(4 * nqp), t_d = lt.add(4 * nqp), t_cep = lt.add(8 * nqp), t_clp = lt.add(8 * nqp), t_cld = lt.add(8 * nqp),
+               t_ts = lt.add(8 * nqp), t_tr = lt.add(8 * nqp), t_pwt = lt.add(8 * nqp);
+  if ((rc = d.tab.reserve(lt.total))) return rc;
+  std::vector<unsigned char>& timg = d.tab.host;
+  timg.assign(lt.total, 0);
+  if (nq) {
+    std::memcpy(timg.data() + t_o, q->o_node, 4 * (size_t)nq); std::memcpy(timg.data() + t_d, q->d_node, 4 * (size_t)nq);
+    std::memcpy(timg.data() + t_cep, q->Cep, 8 * (size_t)nq); std::memcpy(timg.data() + t_clp, q->Clp, 8 * (size_t)nq);
+    std::memcpy(timg.data() + t_cld, q->Cld, 8 * (size_t)nq); std::memcpy(timg.data() + t_ts, q->Ts, 8 * (size_t)nq);
+    std::memcpy(timg.data() + t_tr, q->Tr, 8 * (size_t)nq); std::memcpy(timg.data() + t_pwt, q->pwt, 8 * (size_t)nq);
   }
+  DRS_CUDA(cudaMemcpyAsync(d.tab.ptr, timg.data(), lt.total, cudaMemcpyHostToDevice, st));
+  unsigned char* vb = (unsigned char*)d.veh.ptr;
+  unsigned char* tb = (unsigned char*)d.tab.ptr;
+  PlanView& pv = d.pv;
+  pv.n_veh = nv;
+  pv.perm = (int32_t*)(vb + o_perm); pv.inv = (int32_t*)(vb + o_inv); pv.node = (int32_t*)(vb + o_node); pv.onboard = (int32_t*)(vb + o_onb);
+  pv.cap = (int32_t*)(vb + o_cap); pv.len = (int32_t*)(vb + o_len); pv.delay = (double*)(vb + o_delay); pv.clock = (double*)(vb + o_clock);
+  pv.cost = (double*)(vb + o_cost); pv.pos_node = (int32_t*)(vb + o_pos); pv.keep_node = (int32_t*)(vb + o_kn); pv.keep_t = (double*)(vb + o_kt);
+  pv.keep_et = (double*)(vb + o_ke); pv.m_node = (int32_t*)(vb + o_mnode); pv.m_req = (int32_t*)(vb + o_mreq); pv.m_pod = (int8_t*)(vb + o_mpod);
+  pv.m_partner = (int8_t*)(vb + o_mpar); pv.m_seg = (double*)(vb + o_seg); pv.m_base_t = (double*)(vb + o_bt); pv.m_base_c = (double*)(vb + o_bc);
+  pv.m_base_cld = (double*)(vb + o_bcld); pv.m_base_viol = (int32_t*)(vb + o_bv); pv.m_lb = (float*)(vb + o_lb); pv.m_nslots = (uint8_t*)(vb + o_ns);
+  pv.q_o = (int32_t*)(tb + t_o); pv.q_d = (int32_t*)(tb + t_d); pv.q_cep = (double*)(tb + t_cep); pv.q_clp = (double*)(tb + t_clp);
+  pv.q_cld = (double*)(tb + t_cld); pv.q_ts = (double*)(tb + t_ts); pv.q_tr = (double*)(tb + t_tr); pv.q_pwt = (double*)(tb + t_pwt);
+  pv.prm = prm ? *prm : drs_insertion_params{1.5, 1.0, 1.5, 3.0};
+  pv.directed = t->g->directed;
   DRS_CUDA(cudaStreamSynchronize(st));
-  d.n_veh = nv; d.n_stops = nstops; d.n_rows = nq;
-  if (prm) d.prm = *prm;
+  d.n_veh = nv; d.n_rows = nq;
+  d.prepared = false;
   return DRS_OK;
 }
 
+namespace {
+
+int check_new_rows(const char* who, drs_tick* t, int32_t n_new, const int32_t* new_rows, int32_t* best_veh, int32_t* best_i, int32_t* best_j,
+                   double* best_dc) {
+  DRS_REQUIRE(t && t->legacy, DRS_ERR_STATE, "%s: call drs_tick_set_plans first", who);
+  DRS_REQUIRE(t->g->apsp_valid, DRS_ERR_STATE, "%s: travel-time matrix not built (or invalidated)", who);
+  DRS_REQUIRE(n_new >= 0 && (n_new == 0 || (new_rows && best_veh && best_i && best_j && best_dc)), DRS_ERR_ARG, "%s: bad argument", who);
+  LegacyDev& d = *t->legacy;
+  for (int r = 0; r < n_new; ++r)
+    DRS_REQUIRE(new_rows[r] >= 0 && new_rows[r] < d.n_rows, DRS_ERR_RANGE, "%s: request row %d out of range", who, new_rows[r]);
+  DRS_REQUIRE((int64_t)d.n_veh * n_new < ((int64_t)1 << 31), DRS_ERR_ARG, "%s: %lld pairs exceed 2^31", who, (long long)d.n_veh * n_new);
+  return DRS_OK;
+}
+
+int fetch_results(LegacyDev& d, int n_new, int32_t* best_veh, int32_t* best_i, int32_t* best_j, double* best_dc, cudaStream_t st) {
+  DRS_CUDA(cudaMemcpyAsync(best_veh, d.d_bv, sizeof(int32_t) * n_new, cudaMemcpyDeviceToHost, st));
+  DRS_CUDA(cudaMemcpyAsync(best_i, d.d_bi, sizeof(int32_t) * n_new, cudaMemcpyDeviceToHost, st));
+  DRS_CUDA(cudaMemcpyAsync(best_j, d.d_bj, sizeof(int32_t) * n_new, cudaMemcpyDeviceToHost, st));
+  DRS_CUDA(cudaMemcpyAsync(best_dc, d.d_dc, sizeof(double) * n_new, cudaMemcpyDeviceToHost, st));
+  DRS_CUDA(cudaStreamSynchronize(st));
+  return DRS_OK;
+}
+
+}  // namespace
+
 extern "C" int drs_tick_insertion_eval(drs_tick* t, int32_t n_new, const int32_t* new_rows, int32_t* best_veh,
                                        int32_t* best_i, int32_t* best_j, double* best_dc, int64_t* n_candidates) {
-  DRS_REQUIRE(t && t->legacy, DRS_ERR_STATE, "drs_tick_insertion_eval: call drs_tick_set_plans first");
-  DRS_REQUIRE(t->g->apsp_valid, DRS_ERR_STATE, "drs_tick_insertion_eval: travel-time matrix not built (or invalidated)");
-  DRS_REQUIRE(n_new >= 0 && (n_new == 0 || (new_rows && best_veh && best_i && best_j && best_dc)), DRS_ERR_ARG,
-              "drs_tick_insertion_eval: bad argument");
+  int rc = check_new_rows("drs_tick_insertion_eval", t, n_new, new_rows, best_veh, best_i, best_j, best_dc);
+  if (rc) return rc;
   if (n_candidates) *n_candidates = 0;
   if (n_new == 0) return DRS_OK;
   LegacyDev& d = *t->legacy;
-  for (int r = 0; r < n_new; ++r)
-    DRS_REQUIRE(new_rows[r] >= 0 && new_rows[r] < d.n_rows, DRS_ERR_RANGE, "drs_tick_insertion_eval: request row %d out of range",
-                new_rows[r]);
-  const int64_t total = (int64_t)d.n_veh * n_new;
-  DRS_REQUIRE(total < ((int64_t)1 << 31), DRS_ERR_ARG, "drs_tick_insertion_eval: %lld pairs exceed 2^31", (long long)total);
   DrsDeviceGuard guard(t->g->device);
   cudaStream_t st = t->g->stream;
-  PlanView pv{d.n_veh, d.node, d.onboard, d.cap, d.off, d.s_node, d.s_req, d.delay, d.clock, d.cost, d.s_pod,
-              d.q_o, d.q_d, d.q_cep, d.q_clp, d.q_cld, d.q_ts, d.q_tr, d.q_pwt, d.prm,
-              d.perm, d.m_node, d.m_req, d.m_pod, d.m_partner, d.m_seg, d.m_base_t, d.m_base_c, d.m_base_cld, d.m_base_viol,
-              t->g->directed};
+  if ((rc = ensure_eval_buffers(d, n_new))) return rc;
+  d.h_rows.assign(new_rows, new_rows + n_new);
+  DRS_CUDA(cudaMemcpyAsync(d.d_rows, d.h_rows.data(), sizeof(int32_t) * n_new, cudaMemcpyHostToDevice, st));
   DistView dv{t->g->d_dist, t->g->ld, t->g->mode};
-  int32_t *d_rows = nullptr, *d_bv = nullptr, *d_bi = nullptr, *d_bj = nullptr;
-  double *d_cmin = nullptr, *d_dc = nullptr;
-  unsigned long long* d_ncand = nullptr;
-  auto cleanup = [&]() { cudaFree(d_rows); cudaFree(d_bv); cudaFree(d_bi); cudaFree(d_bj); cudaFree(d_cmin); cudaFree(d_dc); cudaFree(d_ncand); };
-  int rc = drs_upload(&d_rows, new_rows, n_new, st);
-  if (rc) { cleanup(); return rc; }
-  if (cudaMalloc((void**)&d_bv, sizeof(int32_t) * n_new) != cudaSuccess || cudaMalloc((void**)&d_bi, sizeof(int32_t) * n_new) != cudaSuccess ||
-      cudaMalloc((void**)&d_bj, sizeof(int32_t) * n_new) != cudaSuccess || cudaMalloc((void**)&d_dc, sizeof(double) * n_new) != cudaSuccess ||
-      cudaMalloc((void**)&d_cmin, sizeof(double) * std::max<int64_t>(total, 1)) != cudaSuccess ||
-      cudaMalloc((void**)&d_ncand, sizeof(unsigned long long)) != cudaSuccess) {
-    cleanup();
-    drs_set_error("drs_tick_insertion_eval: cudaMalloc failed");
-    return DRS_ERR_NOMEM;
-  }
-  cudaMemsetAsync(d_ncand, 0, sizeof(unsigned long long), st);
   DrsTimer tm_scan(st), tm_fold(st);
   tm_scan.start();
-  if (total > 0) {
-    plan_prep_kernel<<<(d.n_veh + 127) / 128, 128, 0, st>>>(pv, dv);
-    insertion_scan_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(pv, dv, n_new, d_rows, d_cmin, d_ncand);
-    drs_count_launch(2);
-  }
+  if (d.n_veh > 0 && (rc = scan_all(t, d, n_new, st))) return rc;
   tm_scan.stop();
   tm_fold.start();
-  insertion_fold_kernel<<<(n_new * 32 + 127) / 128, 128, 0, st>>>(pv, dv, n_new, d_rows, d_cmin, d_bv, d_bi, d_bj, d_dc);
+  insertion_fold_kernel<<<(n_new * 32 + 127) / 128, 128, 0, st>>>(d.pv, dv, 0, n_new, d.d_rows, d.d_mask, d.words, d.d_cmin, d.d_bv, d.d_bi,
+                                                                    d.d_bj, d.d_dc);
   drs_count_launch();
   tm_fold.stop();
-  unsigned long long ncand = 0;
-  cudaError_t e = cudaGetLastError();
-  if (e == cudaSuccess) e = cudaMemcpyAsync(best_veh, d_bv, sizeof(int32_t) * n_new, cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(best_i, d_bi, sizeof(int32_t) * n_new, cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(best_j, d_bj, sizeof(int32_t) * n_new, cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(best_dc, d_dc, sizeof(double) * n_new, cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(&ncand, d_ncand, sizeof(ncand), cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  if (e == cudaSuccess) { t->last_ms[2] = tm_scan.ms(); t->last_ms[3] = tm_fold.ms(); }
-  cleanup();
-  if (e != cudaSuccess) {
-    drs_set_error("drs_tick_insertion_eval: %s", cudaGetErrorString(e));
-    return DRS_ERR_CUDA;
+  DRS_CUDA(cudaGetLastError());
+  if ((rc = fetch_results(d, n_new, best_veh, best_i, best_j, best_dc, st))) return rc;
+  t->last_ms[2] = tm_scan.ms(); t->last_ms[3] = tm_fold.ms();
+  if (n_candidates) *n_candidates = d.base_candidates * n_new;
+  return DRS_OK;
+}
+
+// Sequential queue (lib/Agents.py:1429-1448): the requests are inserted one after another, each scan seeing the routes,
+// costs and predicted waiting times the previous winners' build_route left behind.
+extern "C" int drs_tick_insertion_queue(drs_tick* t, int32_t n_new, const int32_t* new_rows, double T_now, int32_t* best_veh,
+                                        int32_t* best_i, int32_t* best_j, double* best_dc, int64_t* n_candidates) {
+  int rc = check_new_rows("drs_tick_insertion_queue", t, n_new, new_rows, best_veh, best_i, best_j, best_dc);
+  if (rc) return rc;
+  if (n_candidates) *n_candidates = 0;
+  if (n_new == 0) return DRS_OK;
+  LegacyDev& d = *t->legacy;
+  drs_graph* g = t->g;
+  DrsDeviceGuard guard(g->device);
+  cudaStream_t st = g->stream;
+  if ((rc = ensure_eval_buffers(d, n_new))) return rc;
+  d.h_rows.assign(new_rows, new_rows + n_new);
+  DRS_CUDA(cudaMemcpyAsync(d.d_rows, d.h_rows.data(), sizeof(int32_t) * n_new, cudaMemcpyHostToDevice, st));
+  DistView dv{g->d_dist, g->ld, g->mode};
+  PredSource ps = drs_pred_source(g);
+  DrsTimer tm_scan(st), tm_queue(st);
+  tm_scan.start();
+  if (d.n_veh > 0 && (rc = scan_all(t, d, n_new, st))) return rc;
+  tm_scan.stop();
+  tm_queue.start();
+  int* d_err = d.d_counters + 2;
+  const int rescan_blocks = std::max(1, std::min(148, (n_new + 127) / 128));
+  for (int r = 0; r < n_new; ++r) {
+    insertion_fold_kernel<<<1, 32, 0, st>>>(d.pv, dv, r, 1, d.d_rows, d.d_mask, d.words, d.d_cmin, d.d_bv, d.d_bi, d.d_bj, d.d_dc);
+    insertion_commit_kernel<<<1, 32, 0, st>>>(d.pv, dv, ps, g->d_esrc, g->d_edst, g->d_tt64, d.d_rows, r, d.d_bv, d.d_bi, d.d_bj, T_now, d_err);
+    if (r + 1 < n_new)
+      insertion_rescan_kernel<<<rescan_blocks, 128, 0, st>>>(d.pv, dv, n_new, d.d_rows, r, d.d_bv, d.d_mask, d.words, d.d_cmin);
+    drs_count_launch(r + 1 < n_new ? 3 : 2);
   }
-  if (n_candidates) *n_candidates = (int64_t)ncand;
+  tm_queue.stop();
+  DRS_CUDA(cudaGetLastError());
+  int err = 0;
+  DRS_CUDA(cudaMemcpyAsync(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+  if ((rc = fetch_results(d, n_new, best_veh, best_i, best_j, best_dc, st))) return rc;
+  t->last_ms[2] = tm_scan.ms(); t->last_ms[3] = tm_queue.ms();
+  DRS_REQUIRE(err == 0, DRS_ERR_STATE, "drs_tick_insertion_queue: a winner's plan could not be patched (code %d)", err);
+  if (n_candidates) {
+    // every request scans every vehicle's plan as it is at its turn;
+    // lengths of the winners grow by two per commit
+    std::vector<int> len(d.h_len);
+    std::vector<int32_t> inv(d.n_veh);
+    for (int vs = 0; vs < d.n_veh; ++vs) inv[d.h_perm[vs]] = vs;
+    int64_t per_req = d.base_candidates, total = 0;
+    for (int r = 0; r < n_new; ++r) {
+      total += per_req;
+      if (best_veh[r] >= 0) {
+        int& L = len[inv[best_veh[r]]];
+        per_req += candidates_of(L + 2) - candidates_of(L);
+        L += 2;
+      }
+    }
+    for (int vs = 0; vs < d.n_veh; ++vs) d.h_len[vs] = len[vs];
+    d.base_candidates = per_req;
+    *n_candidates = total;
+  }
+  return DRS_OK;
+}
+
+// One commit by hand (the building block of the queue): request row `req_row` joins vehicle `veh` with its pickup at
+// route position i and its drop-off at j (lib/Agents.py:1468-1469, then Veh.build_route).
+extern "C" int drs_tick_commit_insertion(drs_tick* t, int32_t req_row, int32_t veh, int32_t i, int32_t j, double T_now) {
+  DRS_REQUIRE(t && t->legacy, DRS_ERR_STATE, "drs_tick_commit_insertion: call drs_tick_set_plans first");
+  LegacyDev& d = *t->legacy;
+  DRS_REQUIRE(t->g->apsp_valid, DRS_ERR_STATE, "drs_tick_commit_insertion: travel-time matrix not built (or invalidated)");
+  DRS_REQUIRE(req_row >= 0 && req_row < d.n_rows && veh >= 0 && veh < d.n_veh, DRS_ERR_RANGE, "drs_tick_commit_insertion: row or vehicle out of range");
+  drs_graph* g = t->g;
+  DrsDeviceGuard guard(g->device);
+  cudaStream_t st = g->stream;
+  int rc;
+  if ((rc = ensure_eval_buffers(d, 1))) return rc;
+  DistView dv{g->d_dist, g->ld, g->mode};
+  if (!d.prepared) {
+    plan_prep_kernel<<<(d.n_veh + 127) / 128, 128, 0, st>>>(d.pv, dv);
+    drs_count_launch();
+    d.prepared = true;
+  }
+  int* d_err = d.d_counters + 2;
+  DRS_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), st));
+  insertion_commit_explicit_kernel<<<1, 32, 0, st>>>(d.pv, dv, drs_pred_source(g), g->d_esrc, g->d_edst, g->d_tt64, req_row, veh, i, j, T_now, d_err);
+  drs_count_launch();
+  DRS_CUDA(cudaGetLastError());
+  int err = 0;
+  DRS_CUDA(cudaMemcpyAsync(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+  DRS_CUDA(cudaStreamSynchronize(st));
+  DRS_REQUIRE(err == 0, DRS_ERR_ARG, "drs_tick_commit_insertion: the plan of vehicle %d cannot take (i=%d, j=%d) (code %d)", veh, i, j, err);
+  int inv = 0;
+  for (int vs = 0; vs < d.n_veh; ++vs) if (d.h_perm[vs] == veh) inv = vs;
+  d.base_candidates += candidates_of(d.h_len[inv] + 2) - candidates_of(d.h_len[inv]);
+  d.h_len[inv] += 2;
+  return DRS_OK;
+}
+
+// State of the plans after commits: per vehicle its cost and plan (request row, pod per stop), per request row Cld and pwt.
+extern "C" int drs_tick_fetch_plans(drs_tick* t, double* veh_cost, int32_t* plan_len, int32_t* stop_req, int8_t* stop_pod,
+                                    int32_t stops_per_vehicle, double* row_Cld, double* row_pwt) {
+  DRS_REQUIRE(t && t->legacy, DRS_ERR_STATE, "drs_tick_fetch_plans: call drs_tick_set_plans first");
+  LegacyDev& d = *t->legacy;
+  DRS_REQUIRE(!stop_req || stops_per_vehicle >= INS_MAXL, DRS_ERR_CAPACITY, "drs_tick_fetch_plans: stops_per_vehicle must be >= %d", INS_MAXL);
+  DrsDeviceGuard guard(t->g->device);
+  cudaStream_t st = t->g->stream;
+  const int nv = d.n_veh;
+  std::vector<double> cost(std::max(nv, 1));
+  std::vector<int32_t> len(std::max(nv, 1)), mreq((size_t)INS_MAXL * std::max(nv, 1));
+  std::vector<int8_t> mpod((size_t)INS_MAXL * std::max(nv, 1));
+  if (nv) {
+    DRS_CUDA(cudaMemcpyAsync(cost.data(), d.pv.cost, sizeof(double) * nv, cudaMemcpyDeviceToHost, st));
+    DRS_CUDA(cudaMemcpyAsync(len.data(), d.pv.len, sizeof(int32_t) * nv, cudaMemcpyDeviceToHost, st));
+    DRS_CUDA(cudaMemcpyAsync(mreq.data(), d.pv.m_req, sizeof(int32_t) * (size_t)INS_MAXL * nv, cudaMemcpyDeviceToHost, st));
+    DRS_CUDA(cudaMemcpyAsync(mpod.data(), d.pv.m_pod, (size_t)INS_MAXL * nv, cudaMemcpyDeviceToHost, st));
+  }
+  if (row_Cld && d.n_rows) DRS_CUDA(cudaMemcpyAsync(row_Cld, d.pv.q_cld, sizeof(double) * d.n_rows, cudaMemcpyDeviceToHost, st));
+  if (row_pwt && d.n_rows) DRS_CUDA(cudaMemcpyAsync(row_pwt, d.pv.q_pwt, sizeof(double) * d.n_rows, cudaMemcpyDeviceToHost, st));
+  DRS_CUDA(cudaStreamSynchronize(st));
+  for (int vs = 0; vs < nv; ++vs) {
+    const int v = d.h_perm[vs];
+    if (veh_cost) veh_cost[v] = cost[vs];
+    if (plan_len) plan_len[v] = len[vs];
+    if (stop_req)
+      for (int k = 0; k < len[vs]; ++k) {
+        stop_req[(size_t)v * stops_per_vehicle + k] = mreq[(size_t)k * nv + vs];
+        if (stop_pod) stop_pod[(size_t)v * stops_per_vehicle + k] = mpod[(size_t)k * nv + vs];
+      }
+  }
   return DRS_OK;
 }

@@ -483,20 +483,41 @@ COEF_EXTRA_WAIT = 3.0
 
 
 class InsertionTick(object):
-    """Array-level front end of drs_tick_set_plans / drs_tick_insertion_eval.
+    """Array-level front end of drs_tick_set_plans / drs_tick_insertion_eval / drs_tick_insertion_queue.
 
-    vehs: list of dicts {node, t0, n, T, K, c, route: [(request row, pod, node)]};
+    vehs: list of dicts {node, t0, n, T, K, c, route: [(request row, pod, node)]} and, for commits, optionally
+    ``pos`` (vertex the vehicle stands on, None between vertices) and ``keep`` = (node, t, et) of the first step of
+    its current route (None: no route) -- what Veh.build_route keeps in front of a new route (lib/Agents.py:319-336);
     table: dict of request-table columns o, d, Cep, Clp, Cld, Ts, Tr, pwt (numpy arrays)."""
+
+    MAX_PLAN = 16          # DRS_INS_MAX_PLAN
 
     def __init__(self, G, vehs, table, params=None):
         if not isinstance(G, RoadGraph):
             raise TypeError("G must be the RoadGraph proxy (router.G)")
         self.lib = _lib.load()
         self.G = G
+        self.handle = C.c_void_p()
+        _lib.check(self.lib.drs_tick_create(G.handle, C.byref(self.handle)), self.lib)
+        self.set_plans(vehs, table, params)
+
+    def set_plans(self, vehs, table, params=None):
+        """(Re)loads the fleet and the request table; device buffers are reused from tick to tick."""
+        G = self.G
         nv = len(vehs)
+        self.n_veh = nv
         off = np.zeros(nv + 1, dtype=np.int32)
         for v, veh in enumerate(vehs):
             off[v + 1] = off[v] + len(veh["route"])
+
+        def nodes_or_minus_one(vals):
+            a = np.array([-1 if x is None else int(x) for x in vals], dtype=np.int32)
+            ok = a >= 0
+            if ok.any():
+                a[ok] = G.dev_ids(a[ok])
+            return a
+        have_keep = any("keep" in v for v in vehs)
+        have_pos = any("pos" in v for v in vehs)
         self._a = dict(
             node=G.dev_ids(np.array([v["node"] for v in vehs], dtype=np.int32)),
             delay=np.array([v["t0"] for v in vehs], dtype=np.float64),
@@ -508,33 +529,75 @@ class InsertionTick(object):
             s_node=G.dev_ids(np.array([s[2] for v in vehs for s in v["route"]], dtype=np.int32)),
             s_req=np.array([s[0] for v in vehs for s in v["route"]], dtype=np.int32),
             s_pod=np.array([s[1] for v in vehs for s in v["route"]], dtype=np.int8))
+        a = self._a
+        if have_pos:
+            a["pos"] = nodes_or_minus_one([v.get("pos") for v in vehs])
+        if have_keep:
+            keeps = [v.get("keep") for v in vehs]
+            a["keep_node"] = nodes_or_minus_one([None if k is None else k[0] for k in keeps])
+            a["keep_t"] = np.array([0.0 if k is None else k[1] for k in keeps], dtype=np.float64)
+            a["keep_et"] = np.array([0.0 if k is None else k[2] for k in keeps], dtype=np.float64)
         self._t = {k: (G.dev_ids(table[k]) if k in ("o", "d") else _lib.as_f64(table[k]))
                    for k in ("o", "d", "Cep", "Clp", "Cld", "Ts", "Tr", "pwt")}
-        a, t = self._a, self._t
+        t = self._t
+        self.n_rows = len(t["o"])
         pb = _lib.PlanBatch(nv, _lib.ptr_i32(a["node"]), _lib.ptr_f64(a["delay"]), _lib.ptr_i32(a["onboard"]),
                             _lib.ptr_f64(a["clock"]), _lib.ptr_i32(a["cap"]), _lib.ptr_f64(a["cost"]),
                             _lib.ptr_i32(a["off"]), _lib.ptr_i32(a["s_node"]), _lib.ptr_i32(a["s_req"]),
-                            a["s_pod"].ctypes.data_as(_i8p))
+                            a["s_pod"].ctypes.data_as(_i8p),
+                            _lib.ptr_i32(a["pos"]) if have_pos else None,
+                            _lib.ptr_i32(a["keep_node"]) if have_keep else None,
+                            _lib.ptr_f64(a["keep_t"]) if have_keep else None,
+                            _lib.ptr_f64(a["keep_et"]) if have_keep else None)
         rt = _lib.RequestTable(len(t["o"]), _lib.ptr_i32(t["o"]), _lib.ptr_i32(t["d"]), _lib.ptr_f64(t["Cep"]),
                                _lib.ptr_f64(t["Clp"]), _lib.ptr_f64(t["Cld"]), _lib.ptr_f64(t["Ts"]),
                                _lib.ptr_f64(t["Tr"]), _lib.ptr_f64(t["pwt"]))
         p = params or {}
         prm = _lib.InsertionParams(p.get("max_detour", MAX_DETOUR), p.get("coef_inveh", COEF_INVEH),
                                    p.get("coef_wait", COEF_WAIT), p.get("coef_extra_wait", COEF_EXTRA_WAIT))
-        self.handle = C.c_void_p()
-        _lib.check(self.lib.drs_tick_create(G.handle, C.byref(self.handle)), self.lib)
         _lib.check(self.lib.drs_tick_set_plans(self.handle, C.byref(pb), C.byref(rt), C.byref(prm)), self.lib)
 
-    def evaluate(self, new_rows):
-        """Returns (best_veh, best_i, best_j, best_dc, n_candidates) for the new-request rows."""
+    def _run(self, fn, new_rows, *extra):
         rows = _lib.as_i32(new_rows)
         n = len(rows)
         bv, bi, bj = (np.empty(n, dtype=np.int32) for _ in range(3))
         dc = np.empty(n, dtype=np.float64)
         nc = C.c_int64(0)
-        _lib.check(self.lib.drs_tick_insertion_eval(self.handle, n, _lib.ptr_i32(rows), _lib.ptr_i32(bv), _lib.ptr_i32(bi),
-                                                    _lib.ptr_i32(bj), _lib.ptr_f64(dc), C.byref(nc)), self.lib)
+        _lib.check(fn(self.handle, n, _lib.ptr_i32(rows), *extra, _lib.ptr_i32(bv), _lib.ptr_i32(bi), _lib.ptr_i32(bj),
+                      _lib.ptr_f64(dc), C.byref(nc)), self.lib)
         return bv, bi, bj, dc, nc.value
+
+    def evaluate(self, new_rows):
+        """Every new request against the plans AS THEY ARE (requests do not see each other).
+        Returns (best_veh, best_i, best_j, best_dc, n_candidates) for the new-request rows."""
+        return self._run(self.lib.drs_tick_insertion_eval, new_rows)
+
+    def queue(self, new_rows, T_now):
+        """Model.insertion_heuristics (lib/Agents.py:1429-1448): the requests one after another, each seeing the plans
+        the previous winners' build_route left behind; the plans stay patched on the device."""
+        return self._run(self.lib.drs_tick_insertion_queue, new_rows, C.c_double(float(T_now)))
+
+    def commit(self, row, veh, i, j, T_now):
+        _lib.check(self.lib.drs_tick_commit_insertion(self.handle, int(row), int(veh), int(i), int(j), float(T_now)), self.lib)
+
+    def fetch_plans(self):
+        """The plans as they are now: dict(c [n_veh], routes [list of (row, pod) per vehicle], Cld [rows], pwt [rows])."""
+        nv, M = self.n_veh, self.MAX_PLAN
+        c = np.zeros(nv, dtype=np.float64)
+        ln = np.zeros(nv, dtype=np.int32)
+        sreq = np.zeros((max(nv, 1), M), dtype=np.int32)
+        spod = np.zeros((max(nv, 1), M), dtype=np.int8)
+        cld = np.zeros(self.n_rows, dtype=np.float64)
+        pwt = np.zeros(self.n_rows, dtype=np.float64)
+        _lib.check(self.lib.drs_tick_fetch_plans(self.handle, _lib.ptr_f64(c), _lib.ptr_i32(ln), _lib.ptr_i32(sreq),
+                                                 spod.ctypes.data_as(_i8p), M, _lib.ptr_f64(cld), _lib.ptr_f64(pwt)), self.lib)
+        routes = [[(int(sreq[v, k]), int(spod[v, k])) for k in range(ln[v])] for v in range(nv)]
+        return {"c": c, "routes": routes, "Cld": cld, "pwt": pwt}
+
+    def last_ms(self):
+        ms = np.zeros(4, dtype=np.float64)
+        _lib.check(self.lib.drs_tick_last_ms(self.handle, _lib.ptr_f64(ms)), self.lib)
+        return {"scan": float(ms[2]), "fold": float(ms[3])}
 
     def close(self):
         if self.handle:
@@ -553,8 +616,12 @@ class InsertionHeuristics(object):
     (lib/Agents.py:1429-1490): holds ``vehs`` / ``reqs`` / ``queue`` / ``rejs`` like the legacy Model
     and assigns each queued request to the vehicle and (pickup, drop-off) slots the reference's
     scan would pick.  Vehicles are read through the reference's attribute surface (idle, route legs
-    with rid/pod/tlng/tlat, c, n, T, K, lng, lat); requests through id, olng, olat, dlng, dlat, Cep,
-    Clp, Cld, Ts, Tr, pwt."""
+    with rid/pod/tlng/tlat and steps[0].geo/t/et, c, n, T, K, lng, lat); requests through id, olng, olat,
+    dlng, dlat, Cep, Clp, Cld, Ts, Tr, pwt.
+
+    ``insertion_heuristics`` marshals the fleet ONCE per tick and runs the whole queue on the device
+    (drs_tick_insertion_queue: every request sees the plans the previous winners' build_route left
+    behind); the winners' ``build_route`` is then called on the host objects in queue order."""
 
     def __init__(self, vehs, reqs, params=None):
         from collections import deque
@@ -562,8 +629,9 @@ class InsertionHeuristics(object):
         self.queue = deque()
         self.rejs = []
         self.params = params
+        self._tick = None
 
-    def _marshal(self, router, extra_req):
+    def _marshal(self, router, new_reqs):
         G = router.G
         rows, table = {}, {k: [] for k in ("o", "d", "Cep", "Clp", "Cld", "Ts", "Tr", "pwt")}
 
@@ -577,48 +645,78 @@ class InsertionHeuristics(object):
             return rows[rq.id]
         vehs = []
         for veh in self.vehs:
+            keep = None
+            if len(veh.route) > 0:                             # what a later build_route keeps (lib/Agents.py:319-336)
+                st = veh.route[0].steps[0]
+                keep = (G.node_of_location(st.geo[1][0], st.geo[1][1]), float(st.t), float(getattr(st, "et", st.t)))
             try:                                               # lib/Agents.py:1508-1516
                 node = G.node_index(str((veh.lng, veh.lat)))
-                t0 = 0.0
+                t0, pos = 0.0, node
             except ValueError:
-                assert len(veh.route) > 0
-                geo = veh.route[0].steps[0].geo[1]
-                node = G.node_of_location(geo[0], geo[1])
-                t0 = float(veh.route[0].steps[0].t)
+                assert keep is not None
+                node, t0, pos = keep[0], keep[1], None
             route = []
             if not veh.idle:                                   # lib/Agents.py:1458-1461
                 for leg in veh.route:
                     route.append((row_of(self.reqs[leg.rid]), int(leg.pod), G.node_of_location(leg.tlng, leg.tlat)))
             vehs.append({"node": node, "t0": t0, "n": int(veh.n), "T": float(veh.T), "K": int(veh.K), "c": float(veh.c),
-                         "route": route})
-        new_row = row_of(extra_req)
-        return vehs, {k: np.asarray(v) for k, v in table.items()}, new_row
+                         "route": route, "keep": keep, "pos": pos})
+        new_rows = [row_of(rq) for rq in new_reqs]
+        return vehs, {k: np.asarray(v) for k, v in table.items()}, new_rows
 
-    def insert_heuristics(self, router, req, T):
-        """lib/Agents.py:1451-1490.  Returns True when the request was assigned."""
-        vehs, table, new_row = self._marshal(router, req)
-        tick = InsertionTick(router.G, vehs, table, self.params)
-        try:
-            bv, bi, bj, dc, _ = tick.evaluate([new_row])
-        finally:
-            tick.close()
-        if bv[0] < 0:
-            return False
-        veh = self.vehs[int(bv[0])]
+    def _load(self, router, new_reqs):
+        vehs, table, new_rows = self._marshal(router, new_reqs)
+        if self._tick is None or self._tick.G is not router.G or not self._tick.handle:
+            self._tick = InsertionTick(router.G, vehs, table, self.params)
+        else:
+            self._tick.set_plans(vehs, table, self.params)
+        return new_rows
+
+    def _assign(self, router, req, veh, i, j, T):
         route = []
         if not veh.idle:
             route = [(leg.rid, leg.pod, leg.tlng, leg.tlat) for leg in veh.route]
-        route.insert(int(bi[0]), (req.id, 1, req.olng, req.olat))
-        route.insert(int(bj[0]), (req.id, -1, req.dlng, req.dlat))
-        self.last_choice = (veh, route, float(dc[0]))
+        elif getattr(veh, "_drs_route", None):
+            route = list(veh._drs_route)                       # test doubles without build_route
+        route.insert(int(i), (req.id, 1, req.olng, req.olat))
+        route.insert(int(j), (req.id, -1, req.dlng, req.dlat))
         if hasattr(veh, "build_route"):
             veh.build_route(router, route, self.reqs, T, None)
+        else:
+            veh._drs_route = list(route)
+        return route
+
+    def insert_heuristics(self, router, req, T):
+        """lib/Agents.py:1451-1490.  Returns True when the request was assigned."""
+        new_rows = self._load(router, [req])
+        bv, bi, bj, dc, _ = self._tick.evaluate(new_rows)
+        if bv[0] < 0:
+            return False
+        veh = self.vehs[int(bv[0])]
+        route = self._assign(router, req, veh, bi[0], bj[0], T)
+        self.last_choice = (veh, route, float(dc[0]))
         return True
 
     def insertion_heuristics(self, router, T):
-        """lib/Agents.py:1429-1448 (DISTANCE_THRESHOLD = 0, lib/Constants.py:81)."""
-        for _ in range(len(self.queue)):
-            req = self.queue.popleft()
-            if not self.insert_heuristics(router, req, T):
+        """lib/Agents.py:1429-1448 (DISTANCE_THRESHOLD = 0, lib/Constants.py:81): the whole queue in one device call."""
+        reqs_q = [self.queue.popleft() for _ in range(len(self.queue))]
+        if not reqs_q:
+            return
+        new_rows = self._load(router, reqs_q)
+        bv, bi, bj, dc, _ = self._tick.queue(new_rows, T)
+        self.last_results = []
+        for k, req in enumerate(reqs_q):
+            if bv[k] < 0:
                 self.rejs.append(req)
+                self.last_results.append((req, None, None, float("inf")))
+            else:
+                veh = self.vehs[int(bv[k])]
+                route = self._assign(router, req, veh, bi[k], bj[k], T)
+                self.last_choice = (veh, route, float(dc[k]))
+                self.last_results.append((req, veh, route, float(dc[k])))
             req.assigned = True
+
+    def close(self):
+        if self._tick is not None:
+            self._tick.close()
+            self._tick = None

@@ -319,6 +319,16 @@ typedef struct {
   const int32_t* stop_node;    /* plan stops in route order (leg.tlng, leg.tlat) */
   const int32_t* stop_req;     /* row of the request table */
   const int8_t* stop_pod;
+  /* What a commit (Veh.build_route, lib/Agents.py:148-297) needs beyond the scan; each may be NULL.
+   * pos_node: vertex the vehicle stands on, -1 between vertices (NULL: start_node where start_delay == 0).
+   * keep_*:   the first step of the current route -- its end vertex, remaining time `t` and expected time `et` --
+   *           which clear_route_but_keep_next_node keeps in front of a new route (lib/Agents.py:319-336);
+   *           keep_node -1 = the vehicle has no route (NULL: start_node / start_delay for vehicles under way or
+   *           with a plan, none otherwise). */
+  const int32_t* pos_node;
+  const int32_t* keep_node;
+  const double* keep_t;
+  const double* keep_et;
 } drs_plan_batch;
 
 typedef struct {
@@ -350,16 +360,39 @@ int drs_tick_set_plans(drs_tick* t, const drs_plan_batch* plans, const drs_reque
 int drs_tick_insertion_eval(drs_tick* t, int32_t n_new, const int32_t* new_rows_host, int32_t* best_veh,
                             int32_t* best_i, int32_t* best_j, double* best_dc, int64_t* n_candidates);
 
+/* The queue of Model.insertion_heuristics (lib/Agents.py:1429-1448): the new requests are inserted ONE AFTER ANOTHER in
+ * the given order, each scan seeing the plans the previous winners' Veh.build_route left behind -- the route with the
+ * pickup at i and the drop-off at j, veh.c (lib/Agents.py:256-270) and the predicted waiting time pwt of the requests
+ * still to be picked up (lib/Agents.py:165-220).  T_now is the tick time handed to build_route.  All of it happens on
+ * the device: after a request is folded, its winner's plan is patched, that vehicle is re-prepared and its column is
+ * re-evaluated for the requests still queued.  Outputs as drs_tick_insertion_eval; the plans stay patched (fetch them
+ * with drs_tick_fetch_plans).  Plans hold at most DRS_INS_MAX_PLAN stops; a vehicle whose plan could not take two more
+ * is not insertable.  Not reproduced: the Req.Cld values test_constraints_get_cost leaves on requests it merely
+ * evaluated (lib/Agents.py:1550,1554) -- within a tick they are rewritten before every read; see INTEGRATION.md. */
+#define DRS_INS_MAX_PLAN 16
+int drs_tick_insertion_queue(drs_tick* t, int32_t n_new, const int32_t* new_rows_host, double T_now, int32_t* best_veh,
+                             int32_t* best_i, int32_t* best_j, double* best_dc, int64_t* n_candidates);
+/* One commit by hand (the building block of the queue): request row req_row joins vehicle veh with its pickup at route
+ * position i and its drop-off at j (lib/Agents.py:1468-1469), then Veh.build_route's bookkeeping as above. */
+int drs_tick_commit_insertion(drs_tick* t, int32_t req_row, int32_t veh, int32_t i, int32_t j, double T_now);
+/* The plans as they are now (host outputs, any may be NULL): veh_cost[n_veh] = veh.c, plan_len[n_veh], stop_req / stop_pod
+ * [n_veh x stops_per_vehicle] (stops_per_vehicle >= DRS_INS_MAX_PLAN), and per request-table row Cld and pwt. */
+int drs_tick_fetch_plans(drs_tick* t, double* veh_cost, int32_t* plan_len, int32_t* stop_req, int8_t* stop_pod,
+                         int32_t stops_per_vehicle, double* row_Cld, double* row_pwt);
+
 /* ---------------------------------------------------------- instrumentation --
  * The CUDA stream (cudaStream_t as void*) every call on this graph launches on:
  * lets the host time kernels with events on the launching stream. */
 int drs_graph_stream(const drs_graph* g, void** stream);
 /* Device time (ms, CUDA events on the graph's stream) of the last evaluation kernels of a tick:
- * ms[0] rv_filter, ms[1] rv_eval (drs_tick_rv_eval); ms[2] insertion_scan, ms[3] insertion_fold
- * (drs_tick_insertion_eval). */
+ * ms[0] rv_filter, ms[1] rv_eval (drs_tick_rv_eval); ms[2] insertion scan = plan prep + reach test + evaluation,
+ * ms[3] insertion fold (drs_tick_insertion_eval) or the whole fold / commit / re-scan loop (drs_tick_insertion_queue). */
 int drs_tick_last_ms(const drs_tick* t, double* ms);
 /* Number of kernels this library has launched in this process so far. */
 int64_t drs_launch_count(void);
+/* Number of device allocations (cudaMalloc) this library has made in this process so far: a steady-state tick or query
+ * makes none (tests/test_gpu_insertion.py, tests/test_gpu_routing.py). */
+int64_t drs_alloc_count(void);
 /* Device time of the last drs_apsp_build by phase, from CUDA events on the
  * graph's stream: ms[0] init (fill + edge scatter), ms[1] phase 1 + row part of
  * phase 2 (all rounds), ms[2] column part of phase 2 + phase 3 (all rounds),

@@ -196,3 +196,161 @@ def test_c4_full_size_tick_sampled_against_oracle():
         j = [x for x, s in enumerate(route) if s[0] == row and s[1] == -1][0]
         assert (int(bv[k]), int(bi[k]), int(bj[k])) == (vid, i, j) and dc[k] == odc
     G.close()
+
+
+# ------------------------------------------------------------------ fixtures produced by the reference's own lib/Agents.py
+LEGACY = ["g8_int_K4", "g20_int_K4", "g20_int_K1", "g8_int_K2_few", "g20_uniform_K4", "g12_float_K2"]
+
+
+def _golden_tick(G, rec):
+    """InsertionTick inputs of one golden insertion record (fleet and request table BEFORE the scan)."""
+    from conftest import unjf
+    vehs = []
+    for v in rec["vehs"]:
+        vehs.append({"node": v["node"], "t0": unjf(v["t0"]), "n": v["n"], "T": unjf(v["T"]), "K": v["K"], "c": unjf(v["c"]),
+                     "route": [] if v["idle"] else [(s[0], s[1], s[2]) for s in v["route"]],
+                     "keep": None if v["keep"] is None else (v["keep"]["node"], unjf(v["keep"]["t"]), unjf(v["keep"]["et"])),
+                     "pos": v["node"] if unjf(v["t0"]) == 0.0 else None})
+    reqs = rec["reqs"]
+    assert [r["rid"] for r in reqs] == list(range(len(reqs)))
+    table = {"o": np.array([r["o"] for r in reqs], dtype=np.int32), "d": np.array([r["d"] for r in reqs], dtype=np.int32)}
+    for k in ("Cep", "Clp", "Cld", "Ts", "Tr", "pwt"):
+        table[k] = np.array([unjf(r[k]) for r in reqs], dtype=np.float64)
+    return vehs, table
+
+
+@pytest.mark.parametrize("tag", LEGACY)
+def test_insertion_matches_the_references_own_scan(tag):
+    """Every insertion the reference's Model.insert_heuristics performed in the fixture (lib/Agents.py:1451-1572 run
+    unmodified, oracle/make_golden.py): same winning vehicle, same (i, j), same cost increase -- bit-exact on the
+    integer-weighted maps, 1e-5 relative on the float map (fp32 matrix)."""
+    from conftest import load_golden, unjf
+    from drs_abm_b200.dispatch import InsertionTick
+    from drs_abm_b200.gml import read_gml
+    from drs_abm_b200.routing import RoadGraph
+    gold = load_golden("legacy_%s.json" % tag)
+    G = RoadGraph(read_gml(golden_map_path(gold["map"])))
+    is_float = "float" in gold["map"]
+    assigned = 0
+    for rec in gold["insertions"]:
+        vehs, table = _golden_tick(G, rec)
+        tick = InsertionTick(G, vehs, table)
+        bv, bi, bj, dc, _ = tick.evaluate([rec["rid"]])
+        tick.close()
+        w = rec["winner"]
+        if w is None:
+            assert bv[0] == -1 and np.isinf(dc[0]), (tag, rec["rid"])
+            continue
+        assigned += 1
+        assert (int(bv[0]), int(bi[0]), int(bj[0])) == (w["vid"], w["i"], w["j"]), (tag, rec["rid"])
+        if is_float:
+            assert dc[0] == pytest.approx(unjf(w["dc"]), rel=1e-5)
+        else:
+            assert dc[0] == unjf(w["dc"])
+    assert assigned > 0
+    G.close()
+
+
+@pytest.mark.parametrize("tag", LEGACY)
+def test_insertion_queue_matches_the_references_own_ticks(tag):
+    """Model.insertion_heuristics tick by tick (lib/Agents.py:1429-1448 run unmodified, oracle/make_golden.py): ALL requests
+    of a tick go through drs_tick_insertion_queue from the state before the first of them; every winner, (i, j) and cost
+    increase must be the reference's -- later requests see the earlier winners' routes, veh.c and pwt -- and after the
+    tick veh.c, the routes and pwt on the device equal what the reference's build_route left behind."""
+    from conftest import load_golden, unjf
+    from drs_abm_b200.dispatch import InsertionTick
+    from drs_abm_b200.gml import read_gml
+    from drs_abm_b200.routing import RoadGraph
+    gold = load_golden("legacy_%s.json" % tag)
+    G = RoadGraph(read_gml(golden_map_path(gold["map"])))
+    is_float = "float" in gold["map"]
+    eq = (lambda a, b: a == pytest.approx(b, rel=1e-5, abs=1e-6)) if is_float else (lambda a, b: a == b)
+    ticks = {}
+    for rec in gold["insertions"]:
+        ticks.setdefault(rec["T"], []).append(rec)
+    tick = None
+    repeats = 0
+    for T, recs in ticks.items():
+        vehs, table = _golden_tick(G, recs[0])      # the tick's arrivals were all created before the queue ran
+        assert len(recs[0]["reqs"]) == len(recs[-1]["reqs"])
+        if tick is None:
+            tick = InsertionTick(G, vehs, table)
+        else:
+            tick.set_plans(vehs, table)
+        rids = [rec["rid"] for rec in recs]
+        bv, bi, bj, dc, ncand = tick.queue(rids, unjf(T))
+        winners = []
+        for k, rec in enumerate(recs):
+            w = rec["winner"]
+            if w is None:
+                assert bv[k] == -1 and np.isinf(dc[k]), (tag, rec["rid"])
+            else:
+                assert (int(bv[k]), int(bi[k]), int(bj[k])) == (w["vid"], w["i"], w["j"]), (tag, rec["rid"])
+                assert eq(dc[k], unjf(w["dc"])), (tag, rec["rid"])
+                winners.append(w["vid"])
+        repeats += len(winners) - len(set(winners))
+        # candidates: every request scans every plan as it is at its turn
+        want = sum(sum((len(v["route"]) + 1) * (len(v["route"]) + 2) // 2 if not v["idle"] else 1 for v in rec["vehs"]) for rec in recs)
+        assert ncand == want
+        state = tick.fetch_plans()
+        after = recs[-1]
+        for v, want_v in enumerate(after["after_vehs"]):
+            if want_v["idle"] and not want_v["route"]:
+                continue
+            if not want_v["idle"]:
+                assert eq(state["c"][v], unjf(want_v["c"])), (tag, T, v)
+                assert state["routes"][v] == [(s[0], s[1]) for s in want_v["route"]], (tag, T, v)
+        touched = set(r for v in set(winners) for (r, pod) in state["routes"][v] if pod == 1)
+        for r in touched:
+            assert eq(state["pwt"][r], unjf(after["after_pwt"][r])), (tag, T, r)
+    tick.close()
+    G.close()
+
+
+def test_insertion_queue_matches_oracle_queue_on_a_fleet():
+    """A 60-vehicle fleet with mixed plans and a queue of 40 requests: drs_tick_insertion_queue against the oracle's
+    restatement of the sequential loop (which tests/test_oracle_golden.py pins on the reference itself)."""
+    from drs_abm_b200 import synth
+    from drs_abm_b200.dispatch import InsertionTick
+    from drs_abm_b200.gml import read_gml
+    from drs_abm_b200.routing import RoadGraph
+    from oracle import dispatch_oracle as D
+    name = "g20_int"
+    data = read_gml(golden_map_path(name))
+    G = RoadGraph(data)
+    O = oracle_graph(name)
+    dist = G.dist_rows(0, G.n)
+    tt = lambda a, b: float(dist[a, b])
+    sc = synth.fleet_scenario(data, 60, 40, 600.0, 11, lambda s, t: dist[s, t], plan_stops=(0, 0, 2, 4, 6), capacity=4, radius=5)
+    vehs = []
+    for v in sc["vehs"]:
+        moving = v["t0"] != 0.0 or len(v["route"]) > 0
+        vehs.append(dict(v, keep=(v["node"], v["t0"], v["t0"]) if moving else None, pos=v["node"] if v["t0"] == 0.0 else None))
+    tick = InsertionTick(G, vehs, sc["table"])
+    bv, bi, bj, dc, _ = tick.queue(sc["new_rows"], 600.0)
+    state = tick.fetch_plans()
+    tick.close()
+    ovehs = [{"vid": k, "n": v["n"], "T": v["T"], "K": v["K"], "c": v["c"], "node": v["node"], "t0": v["t0"], "idle": len(v["route"]) == 0,
+              "route": list(v["route"]), "node_pos": v["pos"],
+              "keep": None if v["keep"] is None else {"node": v["keep"][0], "t": v["keep"][1], "et": v["keep"][2]}}
+             for k, v in enumerate(vehs)]
+    oreqs = _oracle_reqs(sc["table"])
+
+    def first_step(a, b):
+        path = O.epath(a, b)
+        if not path:
+            return (a, 0.0)
+        e = path[0]
+        other = int(O.dst[e]) if int(O.src[e]) == a else int(O.src[e])
+        return (other, float(O.tt[e]))
+    res = D.legacy_insertion_queue(tt, ovehs, oreqs, [int(r) for r in sc["new_rows"]], 600.0, first_step=first_step)
+    won = [r[1] for r in res if r[1] is not None]
+    assert len(won) >= 15 and len(won) > len(set(won))          # some vehicle wins twice: the carried state matters
+    for k, (rid, vid, i, j, odc) in enumerate(res):
+        assert (int(bv[k]), int(bi[k]), int(bj[k])) == ((vid, i, j) if vid is not None else (-1, -1, -1)), k
+        assert dc[k] == odc
+    for v, ov in enumerate(ovehs):
+        assert state["c"][v] == ov["c"] and state["routes"][v] == [(s[0], s[1]) for s in ov["route"]]
+    for r, rq in oreqs.items():
+        assert state["pwt"][r] == rq["pwt"]
+    G.close()
