@@ -19,6 +19,7 @@ APSP_FW, APSP_SSSP, APSP_AUTO = 0, 1, 2
 PRED_LAZY, PRED_MATRIX = 0, 1
 I32_INF = 0x3FFFFFFF
 
+QUEUE_TRACK_CLD = 1
 ERR_ARG, ERR_CUDA, ERR_STATE, ERR_NOMEM, ERR_RANGE, ERR_CAPACITY = -1, -2, -3, -4, -5, -6
 
 
@@ -96,6 +97,7 @@ SIGNATURES = {
     "drs_fw_wait_words": (C.c_int, [C.c_int32, C.POINTER(_vp), C.c_int32, C.c_int64, _vp, _vp]),
     "drs_pred_build": (C.c_int, [_vp, C.c_int32, _vp, C.c_int64, C.c_int32, C.c_int32, _vp, _vp]),
     "drs_query_pairs": (C.c_int, [_vp, C.c_int32, _i32p, _i32p, _f64p, _f64p, _i32p]),
+    "drs_query_pair": (C.c_int, [_vp, C.c_int32, C.c_int32, _f64p, _f64p, _i32p]),
     "drs_query_matrix": (C.c_int, [_vp, C.c_int32, _i32p, _i32p, _f64p]),
     "drs_path": (C.c_int, [_vp, C.c_int32, C.c_int32, _i32p, _i32p, _i32p]),
     "drs_alu_peak": (C.c_int, [C.c_int32, C.c_int32, _f64p]),
@@ -116,10 +118,11 @@ SIGNATURES = {
     "drs_tick_rv_fetch": (C.c_int, [_vp, C.c_int32, _i32p, _i32p, _f64p, _u8p, _i32p]),
     "drs_tick_set_plans": (C.c_int, [_vp, C.POINTER(PlanBatch), C.POINTER(RequestTable), C.POINTER(InsertionParams)]),
     "drs_tick_insertion_eval": (C.c_int, [_vp, C.c_int32, _i32p, _i32p, _i32p, _i32p, _f64p, _i64p]),
-    "drs_tick_insertion_queue": (C.c_int, [_vp, C.c_int32, _i32p, C.c_double, _i32p, _i32p, _i32p, _f64p, _i64p]),
+    "drs_tick_insertion_queue": (C.c_int, [_vp, C.c_int32, _i32p, C.c_double, C.c_int32, _i32p, _i32p, _i32p, _f64p, _i64p]),
     "drs_tick_commit_insertion": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double]),
     "drs_tick_fetch_plans": (C.c_int, [_vp, _f64p, _i32p, _i32p, _i8p, C.c_int32, _f64p, _f64p]),
     "drs_alloc_count": (C.c_int64, []),
+    "drs_tick_last_insertion_ms": (C.c_int, [_vp, _f64p]),
     "drs_tick_trip_eval": (C.c_int, [_vp, C.c_double, C.c_int32, C.c_int32, _i32p, _i32p, _i32p, _f64p, _u8p,
                                      _i32p]),
 }

@@ -62,6 +62,7 @@ template <int VAR> int run_variant(int iters, double* relax_per_s) {
   DRS_CUDA(cudaGetDevice(&dev));
   DRS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   float* d_out = nullptr;
+  drs_count_alloc();
   DRS_CUDA(cudaMalloc((void**)&d_out, 4));
   cudaEvent_t e0, e1;
   DRS_CUDA(cudaEventCreate(&e0));

@@ -515,7 +515,6 @@ __global__ void count_status_kernel(const int8_t* status, int64_t total, unsigne
   }
 }
 
-template <typename T> int upload(T** dptr, const T* h, size_t n, cudaStream_t st) { return drs_upload(dptr, h, n, st); }
 
 // stop counts from which a trip's searches are split by its first two / three stops, packed (split3 << 8) | split2
 // (DRS_EVAL_SPLIT2 / DRS_EVAL_SPLIT3 override: tuning knobs; the split never changes the result)
@@ -550,10 +549,7 @@ static_assert(sizeof(EvalShared<EV_TASKS, EV_THREADS>) <= 48 * 1024, "evaluation
 }  // namespace
 
 static void tick_free_results(drs_tick* t) {
-  void* ptrs[] = {t->d_status, t->d_surv_veh, t->d_surv_req, t->d_surv_count, t->d_cost, t->d_order, t->d_nstops,
-                  t->d_counters};
-  for (void* p : ptrs)
-    if (p) cudaFree(p);
+  t->a_rv.release(); t->a_rvres.release(); t->a_trip.release();
   t->d_status = nullptr; t->d_surv_veh = t->d_surv_req = nullptr; t->d_surv_count = nullptr; t->d_cost = nullptr;
   t->d_order = nullptr; t->d_nstops = nullptr; t->d_counters = nullptr;
   t->surv_capacity = 0; t->rv_pairs = 0; t->rv_nsurv = 0;
@@ -573,11 +569,7 @@ extern "C" int drs_tick_destroy(drs_tick* t) {
   DrsDeviceGuard guard(t->g->device);
   tick_free_results(t);
   drs_tick_free_plans(t);
-  TickDev& d = t->dev;
-  void* ptrs[] = {d.v_perm, d.v_node, d.v_cap, d.v_pax, d.v_off, d.v_delay, d.s_node, d.s_rid, d.s_pod, d.s_prev, d.s_lb, d.s_ub,
-                  d.r_rid, d.r_o, d.r_d, d.r_lbp, d.r_ubp, d.r_lbd, d.r_ubd};
-  for (void* p : ptrs)
-    if (p) cudaFree(p);
+  t->a_veh.release(); t->a_req.release();
   delete t;
   return DRS_OK;
 }
@@ -619,15 +611,26 @@ extern "C" int drs_tick_set_vehicles(drs_tick* t, const drs_vehicle_batch* b) {
     const int lx = b->stop_off[x + 1] - b->stop_off[x], ly = b->stop_off[y + 1] - b->stop_off[y];
     return lx != ly ? lx > ly : b->start_node[x] < b->start_node[y];
   });
-  if ((rc = upload(&d.v_perm, perm.data(), nv, st))) return rc;
   d.directed = t->g->directed;
-  if ((rc = upload(&d.v_node, b->start_node, nv, st)) || (rc = upload(&d.v_delay, b->start_delay, nv, st)) ||
-      (rc = upload(&d.v_cap, b->capacity, nv, st)) || (rc = upload(&d.v_pax, b->onboard, nv, st)) ||
-      (rc = upload(&d.v_off, b->stop_off, nv ? nv + 1 : 0, st)) || (rc = upload(&d.s_node, b->stop_node, nstops, st)) ||
-      (rc = upload(&d.s_rid, b->stop_rid, nstops, st)) || (rc = upload(&d.s_pod, b->stop_pod, nstops, st)) ||
-      (rc = upload(&d.s_prev, b->stop_prev, nstops, st)) || (rc = upload(&d.s_lb, b->stop_lb, nstops, st)) ||
-      (rc = upload(&d.s_ub, b->stop_ub, nstops, st)))
-    return rc;
+  // one host image, one copy (a steady-state tick allocates nothing)
+  DrsArenaLayout lay;
+  const size_t nvp = std::max(nv, 1), nsp = std::max(nstops, 1);
+  const size_t o_perm = lay.add(4 * nvp), o_node = lay.add(4 * nvp), o_delay = lay.add(8 * nvp), o_cap = lay.add(4 * nvp), o_pax = lay.add(4 * nvp),
+               o_off = lay.add(4 * (nvp + 1)), o_snode = lay.add(4 * nsp), o_srid = lay.add(4 * nsp), o_spod = lay.add(nsp), o_sprev = lay.add(nsp),
+               o_slb = lay.add(8 * nsp), o_sub = lay.add(8 * nsp);
+  if ((rc = t->a_veh.reserve(lay.total))) return rc;
+  std::vector<unsigned char>& img = t->a_veh.host;
+  img.assign(lay.total, 0);
+  auto put = [&](size_t o, const void* src, size_t bytes) { if (bytes) std::memcpy(img.data() + o, src, bytes); };
+  put(o_perm, perm.data(), 4 * (size_t)nv); put(o_node, b->start_node, 4 * (size_t)nv); put(o_delay, b->start_delay, 8 * (size_t)nv);
+  put(o_cap, b->capacity, 4 * (size_t)nv); put(o_pax, b->onboard, 4 * (size_t)nv); put(o_off, b->stop_off, nv ? 4 * (size_t)(nv + 1) : 0);
+  put(o_snode, b->stop_node, 4 * (size_t)nstops); put(o_srid, b->stop_rid, 4 * (size_t)nstops); put(o_spod, b->stop_pod, (size_t)nstops);
+  put(o_sprev, b->stop_prev, (size_t)nstops); put(o_slb, b->stop_lb, 8 * (size_t)nstops); put(o_sub, b->stop_ub, 8 * (size_t)nstops);
+  DRS_CUDA(cudaMemcpyAsync(t->a_veh.ptr, img.data(), lay.total, cudaMemcpyHostToDevice, st));
+  unsigned char* vb = (unsigned char*)t->a_veh.ptr;
+  d.v_perm = (int32_t*)(vb + o_perm); d.v_node = (int32_t*)(vb + o_node); d.v_delay = (double*)(vb + o_delay); d.v_cap = (int32_t*)(vb + o_cap);
+  d.v_pax = (int32_t*)(vb + o_pax); d.v_off = (int32_t*)(vb + o_off); d.s_node = (int32_t*)(vb + o_snode); d.s_rid = (int32_t*)(vb + o_srid);
+  d.s_pod = (int8_t*)(vb + o_spod); d.s_prev = (int8_t*)(vb + o_sprev); d.s_lb = (double*)(vb + o_slb); d.s_ub = (double*)(vb + o_sub);
   DRS_CUDA(cudaStreamSynchronize(st));
   d.n_veh = nv;
   d.n_stops = nstops;
@@ -647,11 +650,22 @@ extern "C" int drs_tick_set_requests(drs_tick* t, const drs_request_batch* b) {
   cudaStream_t st = t->g->stream;
   TickDev& d = t->dev;
   int rc;
-  if ((rc = upload(&d.r_rid, b->rid, nr, st)) || (rc = upload(&d.r_o, b->o_node, nr, st)) ||
-      (rc = upload(&d.r_d, b->d_node, nr, st)) || (rc = upload(&d.r_lbp, b->lb_p, nr, st)) ||
-      (rc = upload(&d.r_ubp, b->ub_p, nr, st)) || (rc = upload(&d.r_lbd, b->lb_d, nr, st)) ||
-      (rc = upload(&d.r_ubd, b->ub_d, nr, st)))
-    return rc;
+  {
+    DrsArenaLayout lay;
+    const size_t nrp = std::max(nr, 1);
+    const size_t o_rid = lay.add(4 * nrp), o_o = lay.add(4 * nrp), o_d = lay.add(4 * nrp), o_lbp = lay.add(8 * nrp), o_ubp = lay.add(8 * nrp),
+                 o_lbd = lay.add(8 * nrp), o_ubd = lay.add(8 * nrp);
+    if ((rc = t->a_req.reserve(lay.total))) return rc;
+    std::vector<unsigned char>& img = t->a_req.host;
+    img.assign(lay.total, 0);
+    auto put = [&](size_t o, const void* src, size_t bytes) { if (bytes) std::memcpy(img.data() + o, src, bytes); };
+    put(o_rid, b->rid, 4 * (size_t)nr); put(o_o, b->o_node, 4 * (size_t)nr); put(o_d, b->d_node, 4 * (size_t)nr); put(o_lbp, b->lb_p, 8 * (size_t)nr);
+    put(o_ubp, b->ub_p, 8 * (size_t)nr); put(o_lbd, b->lb_d, 8 * (size_t)nr); put(o_ubd, b->ub_d, 8 * (size_t)nr);
+    DRS_CUDA(cudaMemcpyAsync(t->a_req.ptr, img.data(), lay.total, cudaMemcpyHostToDevice, st));
+    unsigned char* rb = (unsigned char*)t->a_req.ptr;
+    d.r_rid = (int32_t*)(rb + o_rid); d.r_o = (int32_t*)(rb + o_o); d.r_d = (int32_t*)(rb + o_d); d.r_lbp = (double*)(rb + o_lbp);
+    d.r_ubp = (double*)(rb + o_ubp); d.r_lbd = (double*)(rb + o_lbd); d.r_ubd = (double*)(rb + o_ubd);
+  }
   DRS_CUDA(cudaStreamSynchronize(st));
   d.n_req = nr;
   return DRS_OK;
@@ -682,14 +696,14 @@ extern "C" int drs_tick_rv_eval(drs_tick* t, double T, int32_t flags, int32_t* n
   t->rv_pairs = total;
   t->rv_nsurv = 0;
   if (total == 0) return DRS_OK;
-  if (t->surv_capacity < total) {
-    tick_free_results(t);
-    t->rv_pairs = total;
-    DRS_CUDA(cudaMalloc((void**)&t->d_status, total));
-    DRS_CUDA(cudaMalloc((void**)&t->d_surv_veh, sizeof(int32_t) * total));
-    DRS_CUDA(cudaMalloc((void**)&t->d_surv_req, sizeof(int32_t) * total));
-    DRS_CUDA(cudaMalloc((void**)&t->d_surv_count, sizeof(int)));
-    DRS_CUDA(cudaMalloc((void**)&t->d_counters, 4 * sizeof(unsigned long long)));
+  {
+    DrsArenaLayout lay;
+    const size_t o_st = lay.add((size_t)total), o_sv = lay.add(sizeof(int32_t) * (size_t)total), o_sr = lay.add(sizeof(int32_t) * (size_t)total),
+                 o_cnt = lay.add(sizeof(int)), o_ctr = lay.add(4 * sizeof(unsigned long long));
+    if ((rc = t->a_rv.reserve(lay.total))) return rc;
+    unsigned char* rb = (unsigned char*)t->a_rv.ptr;
+    t->d_status = (int8_t*)(rb + o_st); t->d_surv_veh = (int32_t*)(rb + o_sv); t->d_surv_req = (int32_t*)(rb + o_sr);
+    t->d_surv_count = (int*)(rb + o_cnt); t->d_counters = (unsigned long long*)(rb + o_ctr);
     t->surv_capacity = total;
   }
   DistView dv{t->g->d_dist, t->g->ld, t->g->mode};
@@ -707,13 +721,17 @@ extern "C" int drs_tick_rv_eval(drs_tick* t, double T, int32_t flags, int32_t* n
   DRS_CUDA(cudaMemcpyAsync(&nsurv, t->d_surv_count, sizeof(int), cudaMemcpyDeviceToHost, st));
   DRS_CUDA(cudaStreamSynchronize(st));
   t->rv_nsurv = nsurv;
-  if (t->d_cost) { cudaFree(t->d_cost); cudaFree(t->d_order); cudaFree(t->d_nstops); t->d_cost = nullptr; t->d_order = nullptr; t->d_nstops = nullptr; }
-  DRS_CUDA(cudaMalloc((void**)&t->d_cost, sizeof(double) * std::max(nsurv, 1)));
-  DRS_CUDA(cudaMalloc((void**)&t->d_order, (size_t)MAXS * std::max(nsurv, 1)));
-  DRS_CUDA(cudaMalloc((void**)&t->d_nstops, sizeof(int32_t) * std::max(nsurv, 1)));
+  {
+    DrsArenaLayout lay;
+    const size_t ns1 = (size_t)std::max(nsurv, 1);
+    const size_t o_c = lay.add(sizeof(double) * ns1), o_o = lay.add((size_t)MAXS * ns1), o_n = lay.add(sizeof(int32_t) * ns1);
+    if ((rc = t->a_rvres.reserve(lay.total))) return rc;
+    unsigned char* rb = (unsigned char*)t->a_rvres.ptr;
+    t->d_cost = (double*)(rb + o_c); t->d_order = (uint8_t*)(rb + o_o); t->d_nstops = (int32_t*)(rb + o_n);
+  }
   tm_eval.start();
   if (nsurv > 0) {
-    int rc = launch_rv_eval(d, dv, T, flags, nsurv, t->d_surv_veh, t->d_surv_req, t->d_status, t->d_cost, t->d_order, t->d_nstops, st);
+    rc = launch_rv_eval(d, dv, T, flags, nsurv, t->d_surv_veh, t->d_surv_req, t->d_status, t->d_cost, t->d_order, t->d_nstops, st);
     if (rc) return rc;
   }
   tm_eval.stop();
@@ -790,19 +808,22 @@ extern "C" int drs_tick_trip_eval(drs_tick* t, double T, int32_t flags, int32_t 
   }
   DrsDeviceGuard guard(t->g->device);
   cudaStream_t st = t->g->stream;
-  int32_t *dv_ = nullptr, *dn = nullptr, *dr = nullptr, *dns = nullptr;
-  double* dc = nullptr;
-  uint8_t* dord = nullptr;
-  auto cleanup = [&]() { cudaFree(dv_); cudaFree(dn); cudaFree(dr); cudaFree(dns); cudaFree(dc); cudaFree(dord); };
-  if ((rc = upload(&dv_, task_veh, n_tasks, st)) || (rc = upload(&dn, task_nreq, n_tasks, st)) ||
-      (rc = upload(&dr, task_req, (size_t)n_tasks * MAXR, st))) { cleanup(); return rc; }
-  if (cudaMalloc((void**)&dc, sizeof(double) * n_tasks) != cudaSuccess ||
-      cudaMalloc((void**)&dord, (size_t)n_tasks * MAXS) != cudaSuccess ||
-      cudaMalloc((void**)&dns, sizeof(int32_t) * n_tasks) != cudaSuccess) {
-    cleanup();
-    drs_set_error("drs_tick_trip_eval: cudaMalloc failed");
-    return DRS_ERR_NOMEM;
-  }
+  DrsArenaLayout lay;
+  const size_t nt = (size_t)n_tasks;
+  const size_t o_v = lay.add(4 * nt), o_n = lay.add(4 * nt), o_r = lay.add(4 * nt * MAXR);
+  const size_t in_bytes = lay.total;
+  const size_t o_c = lay.add(8 * nt), o_ord = lay.add(nt * MAXS), o_ns = lay.add(4 * nt);
+  if ((rc = t->a_trip.reserve(lay.total))) return rc;
+  std::vector<unsigned char>& img = t->a_trip.host;
+  img.assign(in_bytes, 0);
+  std::memcpy(img.data() + o_v, task_veh, 4 * nt); std::memcpy(img.data() + o_n, task_nreq, 4 * nt);
+  std::memcpy(img.data() + o_r, task_req, 4 * nt * MAXR);
+  DRS_CUDA(cudaMemcpyAsync(t->a_trip.ptr, img.data(), in_bytes, cudaMemcpyHostToDevice, st));
+  unsigned char* tb = (unsigned char*)t->a_trip.ptr;
+  int32_t *dv_ = (int32_t*)(tb + o_v), *dn = (int32_t*)(tb + o_n), *dr = (int32_t*)(tb + o_r), *dns = (int32_t*)(tb + o_ns);
+  double* dc = (double*)(tb + o_c);
+  uint8_t* dord = (uint8_t*)(tb + o_ord);
+  auto cleanup = [&]() {};
   DistView dv{t->g->d_dist, t->g->ld, t->g->mode};
   TaskList tl{dv_, dn, dr};
   rc = launch_trip_eval(d, dv, T, flags, n_tasks, tl, dc, dord, dns, st);

@@ -121,6 +121,7 @@ extern "C" int drs_graph_create(int32_t n, int32_t m, int32_t directed, const in
   g->h_out_eid.assign(out_eid, out_eid + na);
   g->h_in_eid.assign(in_eid, in_eid + na);
   auto fail = [&](int code) { drs_graph_destroy(g); return code; };
+  drs_count_alloc();
   if (cudaMalloc(&g->d_arena, img.size()) != cudaSuccess) {
     cudaGetLastError();
     drs_set_error("drs_graph_create: cudaMalloc(%zu bytes) failed", img.size());
@@ -165,6 +166,8 @@ extern "C" int drs_graph_destroy(drs_graph* g) {
   if (g->sssp_queues) cudaFree(g->sssp_queues);
   if (g->sssp_arcs) cudaFree(g->sssp_arcs);
   if (g->sssp_sources) cudaFree(g->sssp_sources);
+  if (g->q_dev) cudaFree(g->q_dev);
+  if (g->q_pin) cudaFreeHost(g->q_pin);
   if (g->stream) cudaStreamDestroy(g->stream);
   delete g;
   return DRS_OK;
@@ -194,11 +197,15 @@ extern "C" int drs_apsp_build(drs_graph* g, int32_t mode) {
   const int64_t ld = g->npad;
   if (!g->owns_matrices || g->ld != ld) {
     free_matrices(g);
+    drs_count_alloc();
     DRS_CUDA(cudaMalloc(&g->d_dist, sizeof(float) * ld * ld));
     g->owns_matrices = true;
     g->ld = ld;
   }
-  if (g->pred_mode == DRS_PRED_MATRIX && !g->d_pred) DRS_CUDA(cudaMalloc((void**)&g->d_pred, sizeof(int32_t) * ld * ld));
+  if (g->pred_mode == DRS_PRED_MATRIX && !g->d_pred) {
+    drs_count_alloc();
+    DRS_CUDA(cudaMalloc((void**)&g->d_pred, sizeof(int32_t) * ld * ld));
+  }
   if (g->pred_mode == DRS_PRED_LAZY && g->d_pred) { cudaFree(g->d_pred); g->d_pred = nullptr; }
   g->apsp_valid = false;
   g->mode = mode;
@@ -299,50 +306,46 @@ extern "C" int drs_apsp_adopt(drs_graph* g, int32_t mode, void* dist_dev, int32_
 // ---------------------------------------------------------------------------- queries
 namespace {
 
-// hops[q] = number of edges on the canonical path (-1 unreachable / broken chain)
-__global__ void path_count_kernel(int npairs, const int32_t* s, const int32_t* t, PredSource ps, int n,
-                                  const int32_t* esrc, const int32_t* edst, int32_t* hops) {
+// One query = one thread: walks the canonical path s -> t BACKWARDS (the predecessor rule gives the last edge), keeping
+// the edge ids in the query's scratch segment, then forms the fp64 sums LEFT TO RIGHT in travel order, which is what
+// the reference's loops over the epath do (lib/RoutingEngine.py:199-203, 212-216) -- so get_duration is bit-identical to
+// the sum of the step durations get_routing reports (invariant lib/Agents.py:358, 999-1000).  A path longer than the
+// segment sets hops to its true length and status 1: the host repeats the query with a larger segment.
+struct PathAnswer { double tt, len; int32_t hops, status; };
+
+__global__ void path_query_kernel(int npairs, const int32_t* s, const int32_t* t, PredSource ps, int n, const int32_t* esrc,
+                                  const int32_t* edst, const double* tt64, const double* len64, int32_t* scratch, int seg,
+                                  PathAnswer* out, int32_t* path_out /* may be null: forward edge ids of query 0 */) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= npairs) return;
   const int src = s[q];
   int cur = t[q], h = 0;
+  int32_t* mine = scratch + (int64_t)q * seg;
+  bool broken = false;
   while (cur != src) {
     const int e = ps.last_edge(src, cur);
-    if (e < 0 || h >= n) { h = -1; break; }
+    if (e < 0 || h >= n) { broken = true; break; }
+    if (h < seg) mine[h] = e;
     cur = prev_node(e, cur, esrc, edst);
     ++h;
   }
-  hops[q] = h;
-}
-
-// writes the path of query q in travel order at path[offset[q] ..] and the fp64 left-to-right sums
-__global__ void path_fill_kernel(int npairs, const int32_t* s, const int32_t* t, PredSource ps,
-                                 const int32_t* esrc, const int32_t* edst, const int32_t* hops,
-                                 const int64_t* offset, int32_t* path, const double* tt64, const double* len64,
-                                 double* tt_out, double* len_out) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= npairs) return;
-  const int h = hops[q];
-  if (h < 0) {
-    if (tt_out) tt_out[q] = __longlong_as_double(0x7ff0000000000000LL);
-    if (len_out) len_out[q] = __longlong_as_double(0x7ff0000000000000LL);
-    return;
+  PathAnswer a;
+  a.status = 0;
+  if (broken) {
+    a.hops = -1; a.tt = a.len = __longlong_as_double(0x7ff0000000000000LL);
+  } else if (h > seg) {
+    a.hops = h; a.status = 1; a.tt = a.len = 0.0;
+  } else {
+    double tt = 0.0, len = 0.0;
+    for (int i = h - 1; i >= 0; --i) {
+      const int e = mine[i];
+      tt += tt64[e];
+      len += len64[e];
+      if (path_out) path_out[h - 1 - i] = e;
+    }
+    a.hops = h; a.tt = tt; a.len = len;
   }
-  const int src = s[q];
-  int cur = t[q];
-  int32_t* out = path + offset[q];
-  for (int i = h - 1; i >= 0; --i) {
-    const int e = ps.last_edge(src, cur);
-    out[i] = e;
-    cur = prev_node(e, cur, esrc, edst);
-  }
-  double tt = 0.0, len = 0.0;
-  for (int i = 0; i < h; ++i) {
-    tt += tt64[out[i]];
-    len += len64[out[i]];
-  }
-  if (tt_out) tt_out[q] = tt;
-  if (len_out) len_out[q] = len;
+  out[q] = a;
 }
 
 __device__ __forceinline__ double dist_to_double(float d) { return (double)d; }
@@ -370,16 +373,6 @@ __global__ void rows_to_double_kernel(const T* dist, int64_t ld, int row0, int n
 
 PredSource pred_source(const drs_graph* g) { return drs_pred_source(g); }
 
-struct DevBuf {
-  void* p = nullptr;
-  ~DevBuf() { if (p) cudaFree(p); }
-  int alloc(size_t bytes) {
-    DRS_CUDA(cudaMalloc(&p, std::max<size_t>(bytes, 16)));
-    return DRS_OK;
-  }
-  template <typename T> T* as() { return (T*)p; }
-};
-
 int check_pairs(const drs_graph* g, int npairs, const int32_t* s, const int32_t* t, const char* who) {
   DRS_REQUIRE(g, DRS_ERR_ARG, "%s: null graph", who);
   DRS_REQUIRE(g->apsp_valid, DRS_ERR_STATE, "%s: travel-time matrix not built (or invalidated by a weight update)", who);
@@ -387,6 +380,105 @@ int check_pairs(const drs_graph* g, int npairs, const int32_t* s, const int32_t*
   for (int q = 0; q < npairs; ++q)
     DRS_REQUIRE(s[q] >= 0 && s[q] < g->n && t[q] >= 0 && t[q] < g->n, DRS_ERR_RANGE,
                 "%s: pair %d (%d -> %d) out of range (n=%d)", who, q, s[q], t[q], g->n);
+  return DRS_OK;
+}
+
+// grow-only pools on the graph handle
+int pool_device(const drs_graph* gc, size_t bytes, void** out) {
+  drs_graph* g = const_cast<drs_graph*>(gc);
+  if (g->q_dev_cap < bytes) {
+    if (g->q_dev) cudaFree(g->q_dev);
+    g->q_dev = nullptr; g->q_dev_cap = 0;
+    const size_t want = std::max<size_t>(bytes + bytes / 2, 1 << 20);
+    drs_count_alloc();
+    if (cudaMalloc(&g->q_dev, want) != cudaSuccess) {
+      cudaGetLastError();
+      DRS_REQUIRE(false, DRS_ERR_NOMEM, "query scratch: cudaMalloc(%zu bytes) failed", want);
+    }
+    g->q_dev_cap = want;
+  }
+  *out = g->q_dev;
+  return DRS_OK;
+}
+
+int pool_pinned(const drs_graph* gc, size_t bytes, void** host, void** dev) {
+  drs_graph* g = const_cast<drs_graph*>(gc);
+  if (g->q_pin_cap < bytes) {
+    if (g->q_pin) cudaFreeHost(g->q_pin);
+    g->q_pin = g->q_pin_dev = nullptr; g->q_pin_cap = 0;
+    const size_t want = std::max<size_t>(bytes + bytes / 2, 1 << 16);
+    drs_count_alloc();
+    if (cudaHostAlloc(&g->q_pin, want, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer(&g->q_pin_dev, g->q_pin, 0) != cudaSuccess) {
+      cudaGetLastError();
+      DRS_REQUIRE(false, DRS_ERR_NOMEM, "query staging: cudaHostAlloc(%zu bytes) failed", want);
+    }
+    g->q_pin_cap = want;
+  }
+  *host = g->q_pin; *dev = g->q_pin_dev;
+  return DRS_OK;
+}
+
+constexpr int SMALL_QUERY = 2048;      // up to this many pairs a query is ONE kernel on mapped host memory (no copies)
+constexpr int PATH_SEG_SMALL = 1024;   // path edges kept per query on the first try
+
+// Path sums of npairs queries.  Small batches: the kernel reads the pairs from, and writes the answers to, pinned host
+// memory mapped into the device (one launch, one stream synchronisation, no copy).  Large batches: staged copies.
+int run_path_queries(const drs_graph* g, int npairs, const int32_t* s, const int32_t* t, double* tt_out, double* len_out,
+                     int32_t* hops_out, int32_t* path_out_host, int path_cap, int* path_len) {
+  cudaStream_t st = g->stream;
+  int seg = npairs <= SMALL_QUERY ? PATH_SEG_SMALL : 256;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    const size_t in_bytes = sizeof(int32_t) * 2 * (size_t)npairs, ans_bytes = sizeof(PathAnswer) * (size_t)npairs;
+    const size_t path_bytes = path_out_host ? sizeof(int32_t) * (size_t)seg : 0;
+    const size_t ans_off = (in_bytes + 15) & ~(size_t)15, path_off = (ans_off + ans_bytes + 15) & ~(size_t)15;
+    void *hp, *hd, *dscratch;
+    int rc;
+    if ((rc = pool_pinned(g, path_off + path_bytes, &hp, &hd))) return rc;
+    const bool small = npairs <= SMALL_QUERY;
+    const size_t scratch_bytes = sizeof(int32_t) * (size_t)seg * npairs;
+    const size_t dev_in_off = (scratch_bytes + 255) & ~(size_t)255, dev_ans_off = (dev_in_off + in_bytes + 255) & ~(size_t)255;
+    if ((rc = pool_device(g, small ? scratch_bytes : dev_ans_off + ans_bytes, &dscratch))) return rc;
+    int32_t* h_in = (int32_t*)hp;
+    std::memcpy(h_in, s, sizeof(int32_t) * npairs);
+    std::memcpy(h_in + npairs, t, sizeof(int32_t) * npairs);
+    PathAnswer* h_ans = (PathAnswer*)((char*)hp + ans_off);
+    const int32_t *k_s, *k_t;
+    PathAnswer* k_ans;
+    int32_t* k_path = path_out_host ? (int32_t*)((char*)hd + path_off) : nullptr;
+    if (small) {
+      k_s = (const int32_t*)hd; k_t = k_s + npairs; k_ans = (PathAnswer*)((char*)hd + ans_off);
+    } else {
+      char* db = (char*)dscratch;
+      DRS_CUDA(cudaMemcpyAsync(db + dev_in_off, h_in, in_bytes, cudaMemcpyHostToDevice, st));
+      k_s = (const int32_t*)(db + dev_in_off); k_t = k_s + npairs; k_ans = (PathAnswer*)(db + dev_ans_off);
+    }
+    const int threads = npairs < 128 ? 32 : 128;
+    path_query_kernel<<<(npairs + threads - 1) / threads, threads, 0, st>>>(npairs, k_s, k_t, pred_source(g), g->n, g->d_esrc, g->d_edst,
+                                                                          g->d_tt64, g->d_len64, (int32_t*)dscratch, seg, k_ans, k_path);
+    drs_count_launch();
+    DRS_CUDA(cudaGetLastError());
+    if (!small) DRS_CUDA(cudaMemcpyAsync(h_ans, k_ans, ans_bytes, cudaMemcpyDeviceToHost, st));
+    DRS_CUDA(cudaStreamSynchronize(st));
+    int longest = 0;
+    for (int q = 0; q < npairs; ++q)
+      if (h_ans[q].status == 1) longest = std::max(longest, h_ans[q].hops);
+    if (longest == 0 || attempt == 1) {
+      DRS_REQUIRE(longest == 0, DRS_ERR_STATE, "path query: a path of %d edges did not fit the second attempt", longest);
+      for (int q = 0; q < npairs; ++q) {
+        if (tt_out) tt_out[q] = h_ans[q].tt;
+        if (len_out) len_out[q] = h_ans[q].len;
+        if (hops_out) hops_out[q] = h_ans[q].hops;
+      }
+      if (path_out_host) {
+        const int h = std::max(h_ans[0].hops, 0);
+        *path_len = h_ans[0].hops;
+        if (h <= path_cap) std::memcpy(path_out_host, (char*)hp + path_off, sizeof(int32_t) * h);
+      }
+      return DRS_OK;
+    }
+    seg = longest;   // at least one path outgrew its segment: once more with room for the longest
+  }
   return DRS_OK;
 }
 
@@ -398,37 +490,23 @@ extern "C" int drs_query_pairs(const drs_graph* g, int32_t npairs, const int32_t
   if (rc) return rc;
   if (npairs == 0) return DRS_OK;
   DrsDeviceGuard guard(g->device);
-  cudaStream_t st = g->stream;
-  DevBuf ds, dt, dh, doff, dpath, dtt, dlen;
-  if ((rc = ds.alloc(sizeof(int32_t) * npairs)) || (rc = dt.alloc(sizeof(int32_t) * npairs)) ||
-      (rc = dh.alloc(sizeof(int32_t) * npairs)) || (rc = doff.alloc(sizeof(int64_t) * npairs)) ||
-      (rc = dtt.alloc(sizeof(double) * npairs)) || (rc = dlen.alloc(sizeof(double) * npairs)))
-    return rc;
-  DRS_CUDA(cudaMemcpyAsync(ds.p, s, sizeof(int32_t) * npairs, cudaMemcpyHostToDevice, st));
-  DRS_CUDA(cudaMemcpyAsync(dt.p, t, sizeof(int32_t) * npairs, cudaMemcpyHostToDevice, st));
-  const int blocks = (npairs + 127) / 128;
-  path_count_kernel<<<blocks, 128, 0, st>>>(npairs, ds.as<int32_t>(), dt.as<int32_t>(), pred_source(g), g->n,
-                                            g->d_esrc, g->d_edst, dh.as<int32_t>());
-  drs_count_launch();
-  DRS_CUDA(cudaGetLastError());
-  std::vector<int32_t> hops(npairs);
-  DRS_CUDA(cudaMemcpyAsync(hops.data(), dh.p, sizeof(int32_t) * npairs, cudaMemcpyDeviceToHost, st));
-  DRS_CUDA(cudaStreamSynchronize(st));
-  std::vector<int64_t> off(npairs);
-  int64_t total = 0;
-  for (int q = 0; q < npairs; ++q) { off[q] = total; total += std::max(hops[q], 0); }
-  if ((rc = dpath.alloc(sizeof(int32_t) * (size_t)total))) return rc;
-  DRS_CUDA(cudaMemcpyAsync(doff.p, off.data(), sizeof(int64_t) * npairs, cudaMemcpyHostToDevice, st));
-  path_fill_kernel<<<blocks, 128, 0, st>>>(npairs, ds.as<int32_t>(), dt.as<int32_t>(), pred_source(g), g->d_esrc,
-                                           g->d_edst, dh.as<int32_t>(), doff.as<int64_t>(), dpath.as<int32_t>(),
-                                           g->d_tt64, g->d_len64, dtt.as<double>(), dlen.as<double>());
-  drs_count_launch();
-  DRS_CUDA(cudaGetLastError());
-  if (tt_out) DRS_CUDA(cudaMemcpyAsync(tt_out, dtt.p, sizeof(double) * npairs, cudaMemcpyDeviceToHost, st));
-  if (len_out) DRS_CUDA(cudaMemcpyAsync(len_out, dlen.p, sizeof(double) * npairs, cudaMemcpyDeviceToHost, st));
-  DRS_CUDA(cudaStreamSynchronize(st));
-  if (hops_out) std::memcpy(hops_out, hops.data(), sizeof(int32_t) * npairs);
+  const int chunk = 1 << 18;   // 256 MB of path scratch at most
+  for (int q0 = 0; q0 < npairs; q0 += chunk) {
+    const int cnt = std::min(chunk, npairs - q0);
+    rc = run_path_queries(g, cnt, s + q0, t + q0, tt_out ? tt_out + q0 : nullptr, len_out ? len_out + q0 : nullptr,
+                          hops_out ? hops_out + q0 : nullptr, nullptr, 0, nullptr);
+    if (rc) return rc;
+  }
   return DRS_OK;
+}
+
+// Scalar form of drs_query_pairs (RoutingEngine.get_duration / get_distance are called one pair at a time,
+// lib/Agents.py:898-923, 756, 1073): one kernel, answer written straight into mapped host memory.
+extern "C" int drs_query_pair(const drs_graph* g, int32_t s, int32_t t, double* tt_out, double* len_out, int32_t* hops_out) {
+  int rc = check_pairs(g, 1, &s, &t, "drs_query_pair");
+  if (rc) return rc;
+  DrsDeviceGuard guard(g->device);
+  return run_path_queries(g, 1, &s, &t, tt_out, len_out, hops_out, nullptr, 0, nullptr);
 }
 
 extern "C" int drs_query_matrix(const drs_graph* g, int32_t npairs, const int32_t* s, const int32_t* t,
@@ -439,23 +517,34 @@ extern "C" int drs_query_matrix(const drs_graph* g, int32_t npairs, const int32_
   if (npairs == 0) return DRS_OK;
   DrsDeviceGuard guard(g->device);
   cudaStream_t st = g->stream;
-  DevBuf ds, dt, dout;
-  if ((rc = ds.alloc(sizeof(int32_t) * npairs)) || (rc = dt.alloc(sizeof(int32_t) * npairs)) ||
-      (rc = dout.alloc(sizeof(double) * npairs)))
-    return rc;
-  DRS_CUDA(cudaMemcpyAsync(ds.p, s, sizeof(int32_t) * npairs, cudaMemcpyHostToDevice, st));
-  DRS_CUDA(cudaMemcpyAsync(dt.p, t, sizeof(int32_t) * npairs, cudaMemcpyHostToDevice, st));
-  const int blocks = (npairs + 127) / 128;
+  const size_t in_bytes = sizeof(int32_t) * 2 * (size_t)npairs, out_bytes = sizeof(double) * (size_t)npairs;
+  const size_t out_off = (in_bytes + 15) & ~(size_t)15;
+  void *hp, *hd;
+  if ((rc = pool_pinned(g, out_off + out_bytes, &hp, &hd))) return rc;
+  int32_t* h_in = (int32_t*)hp;
+  std::memcpy(h_in, s, sizeof(int32_t) * npairs);
+  std::memcpy(h_in + npairs, t, sizeof(int32_t) * npairs);
+  const bool small = npairs <= SMALL_QUERY;
+  const int32_t *k_s, *k_t;
+  double* k_out;
+  if (small) {
+    k_s = (const int32_t*)hd; k_t = k_s + npairs; k_out = (double*)((char*)hd + out_off);
+  } else {
+    void* db;
+    if ((rc = pool_device(g, out_off + out_bytes, &db))) return rc;
+    DRS_CUDA(cudaMemcpyAsync(db, h_in, in_bytes, cudaMemcpyHostToDevice, st));
+    k_s = (const int32_t*)db; k_t = k_s + npairs; k_out = (double*)((char*)db + out_off);
+  }
+  const int threads = npairs < 128 ? 32 : 128, blocks = (npairs + threads - 1) / threads;
   if (g->mode == DRS_MODE_F32)
-    matrix_gather_kernel<float><<<blocks, 128, 0, st>>>(npairs, ds.as<int32_t>(), dt.as<int32_t>(),
-                                                        (const float*)g->d_dist, g->ld, dout.as<double>());
+    matrix_gather_kernel<float><<<blocks, threads, 0, st>>>(npairs, k_s, k_t, (const float*)g->d_dist, g->ld, k_out);
   else
-    matrix_gather_kernel<int><<<blocks, 128, 0, st>>>(npairs, ds.as<int32_t>(), dt.as<int32_t>(),
-                                                      (const int*)g->d_dist, g->ld, dout.as<double>());
+    matrix_gather_kernel<int><<<blocks, threads, 0, st>>>(npairs, k_s, k_t, (const int*)g->d_dist, g->ld, k_out);
   drs_count_launch();
   DRS_CUDA(cudaGetLastError());
-  DRS_CUDA(cudaMemcpyAsync(tt_out, dout.p, sizeof(double) * npairs, cudaMemcpyDeviceToHost, st));
+  if (!small) DRS_CUDA(cudaMemcpyAsync((char*)hp + out_off, k_out, out_bytes, cudaMemcpyDeviceToHost, st));
   DRS_CUDA(cudaStreamSynchronize(st));
+  std::memcpy(tt_out, (char*)hp + out_off, out_bytes);
   return DRS_OK;
 }
 
@@ -466,20 +555,23 @@ extern "C" int drs_apsp_rows_to_host(const drs_graph* g, int32_t row0, int32_t n
               "drs_apsp_rows_to_host: rows [%d, %d) out of range (n=%d)", row0, row0 + nrows, g->n);
   if (nrows == 0) return DRS_OK;
   DrsDeviceGuard guard(g->device);
-  DevBuf tmp;
   int rc;
-  const size_t bytes = sizeof(double) * (size_t)nrows * g->n;
-  if ((rc = tmp.alloc(bytes))) return rc;
-  if (g->mode == DRS_MODE_F32)
-    rows_to_double_kernel<float><<<148 * 4, 256, 0, g->stream>>>((const float*)g->d_dist, g->ld, row0, nrows, g->n,
-                                                                  tmp.as<double>());
-  else
-    rows_to_double_kernel<int><<<148 * 4, 256, 0, g->stream>>>((const int*)g->d_dist, g->ld, row0, nrows, g->n,
-                                                                tmp.as<double>());
-  drs_count_launch();
-  DRS_CUDA(cudaGetLastError());
-  DRS_CUDA(cudaMemcpyAsync(out, tmp.p, bytes, cudaMemcpyDeviceToHost, g->stream));
-  DRS_CUDA(cudaStreamSynchronize(g->stream));
+  // at most 256 MB of converted rows at a time through the pooled scratch
+  const int chunk = (int)std::max<int64_t>(1, std::min<int64_t>(nrows, ((int64_t)256 << 20) / (8 * (int64_t)g->n)));
+  void* tmp;
+  if ((rc = pool_device(g, sizeof(double) * (size_t)chunk * g->n, &tmp))) return rc;
+  for (int r = 0; r < nrows; r += chunk) {
+    const int cnt = std::min(chunk, nrows - r);
+    const size_t bytes = sizeof(double) * (size_t)cnt * g->n;
+    if (g->mode == DRS_MODE_F32)
+      rows_to_double_kernel<float><<<148 * 4, 256, 0, g->stream>>>((const float*)g->d_dist, g->ld, row0 + r, cnt, g->n, (double*)tmp);
+    else
+      rows_to_double_kernel<int><<<148 * 4, 256, 0, g->stream>>>((const int*)g->d_dist, g->ld, row0 + r, cnt, g->n, (double*)tmp);
+    drs_count_launch();
+    DRS_CUDA(cudaGetLastError());
+    DRS_CUDA(cudaMemcpyAsync(out + (size_t)r * g->n, tmp, bytes, cudaMemcpyDeviceToHost, g->stream));
+    DRS_CUDA(cudaStreamSynchronize(g->stream));
+  }
   return DRS_OK;
 }
 
@@ -490,31 +582,15 @@ extern "C" int drs_path(const drs_graph* g, int32_t s, int32_t t, int32_t* edge_
   if (rc) return rc;
   const int cap = *nedges;
   DrsDeviceGuard guard(g->device);
-  cudaStream_t st = g->stream;
-  DevBuf dq, dh, doff, dpath;
-  if ((rc = dq.alloc(sizeof(int32_t) * 2)) || (rc = dh.alloc(sizeof(int32_t))) || (rc = doff.alloc(sizeof(int64_t))))
-    return rc;
-  const int32_t q[2] = {s, t};
-  DRS_CUDA(cudaMemcpyAsync(dq.p, q, sizeof(q), cudaMemcpyHostToDevice, st));
-  path_count_kernel<<<1, 32, 0, st>>>(1, dq.as<int32_t>(), dq.as<int32_t>() + 1, pred_source(g), g->n, g->d_esrc,
-                                      g->d_edst, dh.as<int32_t>());
-  drs_count_launch();
-  DRS_CUDA(cudaGetLastError());
-  int32_t h = 0;
-  DRS_CUDA(cudaMemcpyAsync(&h, dh.p, sizeof(h), cudaMemcpyDeviceToHost, st));
-  DRS_CUDA(cudaStreamSynchronize(st));
+  // one kernel: the path's edge ids land in mapped host memory in travel order
+  std::vector<int32_t> dummy;
+  int32_t one = 0;
+  int32_t* dst = (edge_ids && cap > 0) ? edge_ids : &one;
+  int h = 0;
+  if ((rc = run_path_queries(g, 1, &s, &t, nullptr, nullptr, nullptr, dst, (edge_ids && cap > 0) ? cap : 0, &h))) return rc;
   if (reachable) *reachable = (h >= 0) ? 1 : 0;
   if (h <= 0) { *nedges = 0; return DRS_OK; }
   *nedges = h;
   DRS_REQUIRE(edge_ids && cap >= h, DRS_ERR_CAPACITY, "drs_path: path has %d edges, buffer holds %d", h, cap);
-  if ((rc = dpath.alloc(sizeof(int32_t) * h))) return rc;
-  DRS_CUDA(cudaMemsetAsync(doff.p, 0, sizeof(int64_t), st));
-  path_fill_kernel<<<1, 32, 0, st>>>(1, dq.as<int32_t>(), dq.as<int32_t>() + 1, pred_source(g), g->d_esrc, g->d_edst,
-                                     dh.as<int32_t>(), doff.as<int64_t>(), dpath.as<int32_t>(), g->d_tt64, g->d_len64,
-                                     nullptr, nullptr);
-  drs_count_launch();
-  DRS_CUDA(cudaGetLastError());
-  DRS_CUDA(cudaMemcpyAsync(edge_ids, dpath.p, sizeof(int32_t) * h, cudaMemcpyDeviceToHost, st));
-  DRS_CUDA(cudaStreamSynchronize(st));
   return DRS_OK;
 }

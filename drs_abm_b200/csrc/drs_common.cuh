@@ -83,6 +83,14 @@ struct drs_graph {
   int32_t* sssp_sources = nullptr;   // nsrc source ids followed by the overflow flag
   int sssp_sources_cap = 0;
 
+  // query pool (drs_api.cu): grow-only device scratch and pinned, device-mapped host staging, so that a steady-state
+  // query allocates nothing and a scalar query is ONE kernel that writes its answer straight into host memory
+  void* q_dev = nullptr;
+  size_t q_dev_cap = 0;
+  void* q_pin = nullptr;       // cudaHostAlloc(mapped)
+  void* q_pin_dev = nullptr;   // its device alias
+  size_t q_pin_cap = 0;
+
   double prof_ms[4] = {0, 0, 0, 0};   // last build, by phase (drs_apsp_last_profile)
   int prof_rounds = 0;
 };

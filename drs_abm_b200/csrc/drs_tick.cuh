@@ -2,6 +2,41 @@
 #pragma once
 #include "drs_common.cuh"
 
+// Grow-only device allocation with a host staging image: a tick's arrays are slices of a few of these, filled by one
+// copy each, so that a steady-state tick allocates nothing (drs_alloc_count() counts every cudaMalloc of the library).
+struct DrsArenaLayout {
+  size_t total = 0;
+  size_t add(size_t bytes) {
+    const size_t o = total;
+    total = (total + (bytes > 0 ? bytes : 1) + 255) & ~(size_t)255;
+    return o;
+  }
+};
+struct DrsArena {
+  void* ptr = nullptr;
+  size_t cap = 0;
+  std::vector<unsigned char> host;
+  int reserve(size_t bytes) {
+    if (ptr && bytes <= cap) return DRS_OK;
+    release();
+    const size_t want = bytes + bytes / 4 + 4096;
+    drs_count_alloc();
+    if (cudaMalloc(&ptr, want) != cudaSuccess) {
+      cudaGetLastError();
+      ptr = nullptr;
+      drs_set_error("device allocation of %zu bytes failed", want);
+      return DRS_ERR_NOMEM;
+    }
+    cap = want;
+    return DRS_OK;
+  }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+  }
+};
+
 struct TickDev {
   // vehicles
   int n_veh = 0, n_stops = 0;
@@ -46,54 +81,12 @@ struct drs_tick {
   unsigned long long* d_counters = nullptr;
   int64_t surv_capacity = 0;
   LegacyDev* legacy = nullptr;   // plans + request table of the insertion heuristic
+  DrsArena a_veh, a_req, a_rv, a_rvres, a_trip;   // vehicles, requests, RV survivors, RV results, trip-evaluation buffers
   double last_ms[4] = {0, 0, 0, 0};
 };
 
 
 void drs_tick_free_plans(drs_tick* t);
-
-// Grow-only device allocation with a host staging image: a tick's arrays are slices of a few of these, filled by one
-// copy each, so that a steady-state tick allocates nothing (drs_alloc_count() counts every cudaMalloc of the library).
-struct DrsArenaLayout {
-  size_t total = 0;
-  size_t add(size_t bytes) {
-    const size_t o = total;
-    total = (total + (bytes > 0 ? bytes : 1) + 255) & ~(size_t)255;
-    return o;
-  }
-};
-struct DrsArena {
-  void* ptr = nullptr;
-  size_t cap = 0;
-  std::vector<unsigned char> host;
-  int reserve(size_t bytes) {
-    if (ptr && bytes <= cap) return DRS_OK;
-    release();
-    const size_t want = bytes + bytes / 4 + 4096;
-    drs_count_alloc();
-    if (cudaMalloc(&ptr, want) != cudaSuccess) {
-      cudaGetLastError();
-      ptr = nullptr;
-      drs_set_error("device allocation of %zu bytes failed", want);
-      return DRS_ERR_NOMEM;
-    }
-    cap = want;
-    return DRS_OK;
-  }
-  void release() {
-    if (ptr) cudaFree(ptr);
-    ptr = nullptr;
-    cap = 0;
-  }
-};
-
-template <typename T> inline int drs_upload(T** dptr, const T* h, size_t n, cudaStream_t st) {
-  if (*dptr) { cudaFree(*dptr); *dptr = nullptr; }
-  drs_count_alloc();
-  DRS_CUDA(cudaMalloc((void**)dptr, (n > 0 ? n : 1) * sizeof(T)));
-  if (n) DRS_CUDA(cudaMemcpyAsync(*dptr, h, n * sizeof(T), cudaMemcpyHostToDevice, st));
-  return DRS_OK;
-}
 
 // CUDA-event stopwatch on one stream
 struct DrsTimer {

@@ -511,6 +511,7 @@ __global__ void wait_words_kernel(WordList wl, int value, long long timeout_cycl
 extern "C" int drs_p2p_alloc(int64_t bytes, void** dev_ptr, unsigned char* handle) {
   DRS_REQUIRE(bytes > 0 && dev_ptr && handle, DRS_ERR_ARG, "drs_p2p_alloc: bad argument");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  drs_count_alloc();
   DRS_CUDA(cudaMalloc(dev_ptr, (size_t)bytes));
   DRS_CUDA(cudaMemset(*dev_ptr, 0, (size_t)bytes));
   cudaIpcMemHandle_t h;

@@ -126,7 +126,17 @@ __device__ void load_pair(Pair& p, const PlanView& pv, const DistView& dv, int v
 // test_constraints_get_cost (lib/Agents.py:1493-1572) for the candidate "pickup after a
 // planned stops, drop-off after b planned stops" (a <= b), i.e. (i, j) = (a, b + 1).
 // Returns viol (-1 = success) and the total cost through *c_out.
-__device__ int eval_candidate(const Pair& p, const PlanView& pv, int a, int b, double C, double* c_out) {
+// FX: also record the Req.Cld values the walk assigns at every pickup it processes (lib/Agents.py:1550,1554 mutate the
+// request objects while a candidate is merely evaluated): fx_cld[k] for planned stop k, fx_cld[L] for the new request,
+// bit k / L of *fx_mask set.  A walk that fails later keeps what it wrote before, like the reference.
+// mpre_out (with C = +inf): the largest running cost after any stop walked BEFORE the stop that violates (all stops if
+// none does).  Under a finite bound C the reference's walk returns 0 at the first stop whose running cost exceeds C, and
+// a violation is tested before the cost of its own stop, so: result(C) = 1 if over capacity, else 0 if mpre > C, else
+// the unbounded result -- which lets the lanes of a warp walk the candidates of a vehicle in parallel, without the
+// bound, and one pass over their (viol, mpre, cost) triples replay the sequential scan exactly (scan_vehicle_warp).
+template <bool FX>
+__device__ int eval_candidate(const Pair& p, const PlanView& pv, int a, int b, double C, double* c_out, double* fx_cld = nullptr,
+                              uint32_t* fx_mask = nullptr, double* mpre_out = nullptr) {
   // capacity pre-check over the whole candidate route (:1518-1521)
   {
     int n = p.n0;
@@ -181,6 +191,7 @@ __device__ int eval_candidate(const Pair& p, const PlanView& pv, int a, int b, d
         cld = T + t + pv.prm.max_detour * pv.q_ts[rq];
       }
       if (kind == 1) cld_new = cld; else cld_local[k] = cld;
+      if (FX) { const int at = kind == 1 ? p.L : k; fx_cld[at] = cld; *fx_mask |= 1u << at; }
     } else if (pod == -1) {
       double cld;
       if (kind == 2) cld = cld_new;
@@ -195,10 +206,45 @@ __device__ int eval_candidate(const Pair& p, const PlanView& pv, int a, int b, d
       else c += t * pv.prm.coef_wait;
     }
     if (c > C) return 0;             // over the incumbent bound (:1568-1569)
+    if (mpre_out) *mpre_out = fmax(*mpre_out, c);
     last = (kind == 0) ? k : (kind == 1 ? p.L : p.L + 1);
   }
   *c_out = c;
   return -1;
+}
+
+// The reference's scan of ONE vehicle (lib/Agents.py:1466-1482) by a whole warp: lanes walk the (i, j) candidates in
+// parallel without the bound, then every lane replays the sequential decisions from the triples (identically, so the
+// warp stays converged).  dc / wi / wj are updated like dc_, route_ in the reference; returns true if the vehicle won.
+__device__ bool scan_vehicle_warp(const Pair& p, const PlanView& pv, double& dc, int& wi, int& wj) {
+  const int lane = threadIdx.x & 31;
+  const int ncand = (p.L + 1) * (p.L + 2) / 2;
+  const double c0 = p.c0;
+  bool won = false, over = false;
+  int skip_i = -1;                       // the j-loop of this i was left (viol > 0)
+  for (int base = 0; base < ncand && !over; base += 32) {
+    const int k = base + lane;
+    int ci = 0, cj = 1, viol = 1;
+    double F = 0.0, mpre = -d_inf();
+    if (k < ncand) {
+      int rem = k;                       // k-th candidate in scan order: i = 0..L, j = i+1..L+1
+      while (rem >= p.L + 1 - ci) { rem -= p.L + 1 - ci; ++ci; }
+      cj = ci + 1 + rem;
+      viol = eval_candidate<false>(p, pv, ci, cj - 1, d_inf(), &F, nullptr, nullptr, &mpre);
+    }
+    const int nb = min(32, ncand - base);
+    for (int q = 0; q < nb && !over; ++q) {
+      const int qi = __shfl_sync(0xffffffffu, ci, q), qj = __shfl_sync(0xffffffffu, cj, q);
+      const int qv = __shfl_sync(0xffffffffu, viol, q);
+      const double qF = __shfl_sync(0xffffffffu, F, q), qM = __shfl_sync(0xffffffffu, mpre, q);
+      if (qi == skip_i) continue;
+      const int res = (qv == 1) ? 1 : ((qM > c0 + dc) ? 0 : qv);
+      if (res < 0) { dc = qF - c0; wi = qi; wj = qj; won = true; }
+      if (res > 0) skip_i = qi;
+      if (res == 2) over = true;
+    }
+  }
+  return won;
 }
 
 // One stop of test_constraints_get_cost's walk (lib/Agents.py:1523-1567) without the bound test.
@@ -375,11 +421,12 @@ __global__ void __launch_bounds__(1024, 1) insertion_reach_kernel(PlanView pv, D
 //     further stops served" is advanced incrementally over b, and only the tail after the drop-off is re-walked per
 //     candidate.  Arithmetic and operation order per candidate are those of eval_candidate; only successes matter
 //     here, so no viol codes.
-__device__ double pair_cmin(const PlanView& pv, const DistView& dv, int rq, int vs) {
+__device__ double pair_cmin(const PlanView& pv, const DistView& dv, int rq, int vs, bool* reach_out = nullptr) {
   const int nv = pv.n_veh;
   const double inf = d_inf();
   const int L = pv.len[vs];
   double cmin = inf;
+  if (reach_out) *reach_out = false;
   const int bviol = pv.m_base_viol[vs];
   if (bviol < 0) return inf;
   const int o = pv.q_o[rq], d = pv.q_d[rq];
@@ -404,6 +451,7 @@ __device__ double pair_cmin(const PlanView& pv, const DistView& dv, int rq, int 
     }
   }
   if (!reachable) return inf;
+  if (reach_out) *reach_out = true;
   to_d[0] = tt_into(dv, pv.directed, d, start);
   for (int k = 0; k < L; ++k) {
     const int nd = pv.m_node[k * nv + vs];
@@ -463,8 +511,12 @@ __global__ void __launch_bounds__(128) insertion_eval_kernel(PlanView pv, DistVi
 // One WARP per request.  Lanes read the smallest costs of 32 consecutive vehicles IN THE CALLER'S ORDER (eight chunks
 // ahead: the walk is a chain of dependent decisions, the loads are not); only flagged vehicles are re-scanned (by
 // their lane) with the running bound.  r_first / r_count select the requests (the sequential queue folds one at a time).
+struct FoldEvent { int v; int pad; double dc; };   // after the exact re-scan of vehicle v the incumbent cost increase is dc
+constexpr int FOLD_EVENT_CAP = 8192;
+
 __global__ void insertion_fold_kernel(PlanView pv, DistView dv, int r_first, int r_count, const int32_t* new_rows, const uint32_t* mask,
-                                      int words, const double* cmin, int32_t* best_veh, int32_t* best_i, int32_t* best_j, double* best_dc) {
+                                      int words, const double* cmin, int32_t* best_veh, int32_t* best_i, int32_t* best_j, double* best_dc,
+                                      FoldEvent* events /* may be null; single-request folds only */, int* n_events) {
   const int rr = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (rr >= r_count) return;
@@ -472,6 +524,7 @@ __global__ void insertion_fold_kernel(PlanView pv, DistView dv, int r_first, int
   const double inf = d_inf();
   double dc = inf;                   // dc_ = np.inf (:1452)
   int wv = -1, wi = -1, wj = -1;
+  int n_ev = 0;
   const uint32_t* mrow = mask + (size_t)r * words;
   constexpr int AHEAD = 8;
   for (int base0 = 0; base0 < pv.n_veh; base0 += 32 * AHEAD) {
@@ -503,7 +556,7 @@ __global__ void insertion_fold_kernel(PlanView pv, DistView dv, int r_first, int
           for (int i = 0; i <= p.L; ++i) {                         // (:1466-1482)
             for (int j = i + 1; j <= p.L + 1; ++j) {
               double c;
-              viol = eval_candidate(p, pv, i, j - 1, c0 + ndc, &c);
+              viol = eval_candidate<false>(p, pv, i, j - 1, c0 + ndc, &c);
               if (viol < 0) { ndc = c - c0; nv = v; ni = i; nj = j; }
               if (viol > 0) break;
             }
@@ -512,10 +565,49 @@ __global__ void insertion_fold_kernel(PlanView pv, DistView dv, int r_first, int
         }
         dc = __shfl_sync(0xffffffffu, ndc, l); wv = __shfl_sync(0xffffffffu, nv, l);
         wi = __shfl_sync(0xffffffffu, ni, l); wj = __shfl_sync(0xffffffffu, nj, l);
+        if (events && lane == 0) {
+          if (n_ev < FOLD_EVENT_CAP) events[n_ev] = FoldEvent{base0 + 32 * u + l, 0, dc};
+          ++n_ev;
+        }
       }
     }
   }
-  if (lane == 0) { best_veh[r] = wv; best_i[r] = wi; best_j[r] = wj; best_dc[r] = dc; }
+  if (lane == 0) { best_veh[r] = wv; best_i[r] = wi; best_j[r] = wj; best_dc[r] = dc; if (events) *n_events = n_ev; }
+}
+
+// Side effects of one request's scan on Req.Cld (lib/Agents.py:1550,1554), exactly: every vehicle whose pickup position 0
+// can be reached (bit set in the request's mask; for all others the very first walk ends at the late pickup, viol 2, and
+// the scan of that vehicle is over) repeats the reference's bounded scan -- the bound it starts with is the incumbent the
+// fold had when it passed that vehicle (events) -- and the LAST value each pickup received wins: per planned pickup within
+// its vehicle, for the new request across vehicles in the caller's order (fx_new / fx_last_v, applied by the commit).
+__global__ void insertion_sidefx_kernel(PlanView pv, DistView dv, const int32_t* new_rows, int r, const uint32_t* mask, int words,
+                                        const FoldEvent* events, const int* n_events, double* fx_new, int* fx_last_v, int* err) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= pv.n_veh) return;
+  const int vs = pv.inv[v];
+  if (!((mask[(size_t)r * words + (vs >> 5)] >> (vs & 31)) & 1u)) return;
+  const int ne = *n_events;
+  if (ne > FOLD_EVENT_CAP) { *err = 4; return; }
+  double dc = d_inf();
+  for (int e = 0; e < ne && events[e].v < v; ++e) dc = events[e].dc;
+  Pair p;
+  load_pair(p, pv, dv, vs, new_rows[r]);
+  double fx_cld[INS_MAXL + 1];
+  uint32_t fx_mask = 0;
+  const double c0 = p.c0;
+  int viol = -1;
+  for (int i = 0; i <= p.L; ++i) {
+    for (int j = i + 1; j <= p.L + 1; ++j) {
+      double c;
+      viol = eval_candidate<true>(p, pv, i, j - 1, c0 + dc, &c, fx_cld, &fx_mask);
+      if (viol < 0) dc = c - c0;
+      if (viol > 0) break;
+    }
+    if (viol == 2) break;
+  }
+  for (int k = 0; k < p.L; ++k)
+    if ((fx_mask >> k) & 1u) pv.q_cld[p.req[k]] = fx_cld[k];
+  if ((fx_mask >> p.L) & 1u) { fx_new[vs] = fx_cld[p.L]; atomicMax(fx_last_v, v); }
 }
 
 // ------------------------------------------------------------------------------------------------ commit
@@ -596,8 +688,12 @@ __device__ void commit_one(const PlanView& pv, const DistView& dv, const PredSou
 
 __global__ void insertion_commit_kernel(PlanView pv, DistView dv, PredSource ps, const int32_t* esrc, const int32_t* edst, const double* tt64,
                                         const int32_t* new_rows, int r, const int32_t* best_veh, const int32_t* best_i,
-                                        const int32_t* best_j, double T_now, int* err) {
+                                        const int32_t* best_j, double T_now, int* err, const double* fx_new, int* fx_last_v) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  if (fx_new) {                      // the last walk that picked the new request up left its Cld (side-effect pass)
+    if (*fx_last_v >= 0) pv.q_cld[new_rows[r]] = fx_new[pv.inv[*fx_last_v]];
+    *fx_last_v = -1;
+  }
   const int v = best_veh[r];
   if (v < 0) return;
   commit_one(pv, dv, ps, esrc, edst, tt64, new_rows[r], v, best_i[r], best_j[r], T_now, err);
@@ -616,10 +712,141 @@ __global__ void insertion_rescan_kernel(PlanView pv, DistView dv, int n_new, con
   if (v < 0) return;
   const int vs = pv.inv[v];
   for (int r2 = r + 1 + blockIdx.x * blockDim.x + threadIdx.x; r2 < n_new; r2 += gridDim.x * blockDim.x) {
-    const double cm = pair_cmin(pv, dv, new_rows[r2], vs);
+    bool reach;
+    const double cm = pair_cmin(pv, dv, new_rows[r2], vs, &reach);
     uint32_t* w = mask + (size_t)r2 * words + (vs >> 5);
-    if (cm != d_inf()) { cmin[(int64_t)r2 * pv.n_veh + vs] = cm; atomicOr(w, 1u << (vs & 31)); }
+    // the bit means "some pickup position can be reached in time" (the fold reads the cost only where it is set; the
+    // side-effect pass repeats the reference's scan only there), whether or not any candidate succeeds
+    if (reach) { cmin[(int64_t)r2 * pv.n_veh + vs] = cm; atomicOr(w, 1u << (vs & 31)); }
     else atomicAnd(w, ~(1u << (vs & 31)));
+  }
+}
+
+
+// The whole queue in ONE launch: a single persistent CTA walks the requests in order (the chain of dependent decisions
+// leaves nothing for a second CTA to do); per request
+//   A  all threads: the vehicles whose bit is set in the request's mask, with their smallest cost, ordered by the
+//      caller's vehicle index (rank by counting in shared memory),
+//   B  warp 0: the fold over that short list -- a vehicle is re-scanned (scan_vehicle_warp) only if its smallest cost
+//      can meet the incumbent bound -- recording the incumbent after every re-scan,
+//   C  (DRS_QUEUE_TRACK_CLD) one thread per listed vehicle: the reference's bounded scan again, for the Req.Cld values
+//      it leaves behind,
+//   D  thread 0: commit (build_route's route, veh.c, pwt) and re-preparation of the winner,
+//   E  all threads: the winner's column for the requests still queued.
+constexpr int QUEUE_THREADS = 1024;
+constexpr int QUEUE_MAXC = 3072;          // vehicles in reach of one request that the shared-memory list holds
+
+struct QueueShared {
+  int vs[QUEUE_MAXC];
+  int v[QUEUE_MAXC];
+  double cm[QUEUE_MAXC];
+  int order[QUEUE_MAXC];                  // order[rank] = list position, ascending caller's vehicle index
+  int ev_v[QUEUE_MAXC];                   // fold events: after the re-scan of vehicle ev_v the incumbent is ev_dc
+  double ev_dc[QUEUE_MAXC];
+  double fx_new[QUEUE_MAXC];              // Cld the scan of the k-th listed vehicle left on the new request
+  int count, n_ev, win_v, win_i, win_j, last_fx;
+  double win_dc;
+};
+
+__global__ void __launch_bounds__(QUEUE_THREADS, 1) insertion_queue_kernel(
+    PlanView pv, DistView dv, PredSource ps, const int32_t* esrc, const int32_t* edst, const double* tt64, int n_new,
+    const int32_t* new_rows, uint32_t* mask, int words, double* cmin, int32_t* best_veh, int32_t* best_i, int32_t* best_j,
+    double* best_dc, double T_now, int track_cld, int* err) {
+  extern __shared__ __align__(16) unsigned char queue_smem[];
+  QueueShared& sh = *reinterpret_cast<QueueShared*>(queue_smem);
+  const int tid = threadIdx.x, lane = tid & 31, nv = pv.n_veh;
+  const double inf = d_inf();
+  for (int r = 0; r < n_new; ++r) {
+    const int rq = new_rows[r];
+    if (tid == 0) { sh.count = 0; sh.n_ev = 0; sh.last_fx = -1; }
+    __syncthreads();
+    // ---- A: list of the vehicles in reach
+    const uint32_t* mrow = mask + (size_t)r * words;
+    for (int w = tid; w < words; w += QUEUE_THREADS) {
+      uint32_t m = mrow[w];
+      while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        const int vs = w * 32 + b;
+        const int pos = atomicAdd(&sh.count, 1);
+        if (pos < QUEUE_MAXC) { sh.vs[pos] = vs; sh.v[pos] = pv.perm[vs]; sh.cm[pos] = cmin[(int64_t)r * nv + vs]; }
+      }
+    }
+    __syncthreads();
+    const int cnt = sh.count;
+    if (cnt > QUEUE_MAXC) { if (tid == 0) *err = 5; return; }
+    for (int k = tid; k < cnt; k += QUEUE_THREADS) {
+      const int mine = sh.v[k];
+      int rank = 0;
+      for (int m = 0; m < cnt; ++m) rank += sh.v[m] < mine;
+      sh.order[rank] = k;
+    }
+    __syncthreads();
+    // ---- B: fold (warp 0)
+    if (tid < 32) {
+      double dc = inf;
+      int wv = -1, wi = -1, wj = -1, n_ev = 0;
+      for (int k = 0; k < cnt; ++k) {
+        const int at = sh.order[k];
+        const double cm = sh.cm[at];
+        const int vs = sh.vs[at];
+        const double c0 = pv.cost[vs];
+        if (cm == inf || cm > c0 + dc) continue;
+        Pair p;
+        load_pair(p, pv, dv, vs, rq);
+        if (scan_vehicle_warp(p, pv, dc, wi, wj)) wv = sh.v[at];
+        if (lane == 0) { sh.ev_v[n_ev] = sh.v[at]; sh.ev_dc[n_ev] = dc; }
+        ++n_ev;
+      }
+      if (lane == 0) {
+        sh.win_v = wv; sh.win_i = wi; sh.win_j = wj; sh.win_dc = dc; sh.n_ev = n_ev;
+        best_veh[r] = wv; best_i[r] = wi; best_j[r] = wj; best_dc[r] = dc;
+      }
+    }
+    __syncthreads();
+    // ---- C: Req.Cld side effects of this scan (lib/Agents.py:1550,1554)
+    if (track_cld) {
+      for (int k = tid; k < cnt; k += QUEUE_THREADS) {
+        const int at = sh.order[k];
+        const int v = sh.v[at], vs = sh.vs[at];
+        double dc = inf;
+        for (int e = 0; e < sh.n_ev && sh.ev_v[e] < v; ++e) dc = sh.ev_dc[e];
+        Pair p;
+        load_pair(p, pv, dv, vs, rq);
+        double fx_cld[INS_MAXL + 1];
+        uint32_t fx_mask = 0;
+        int viol = -1;
+        for (int i = 0; i <= p.L; ++i) {
+          for (int j = i + 1; j <= p.L + 1; ++j) {
+            double c;
+            viol = eval_candidate<true>(p, pv, i, j - 1, p.c0 + dc, &c, fx_cld, &fx_mask);
+            if (viol < 0) dc = c - p.c0;
+            if (viol > 0) break;
+          }
+          if (viol == 2) break;
+        }
+        for (int s2 = 0; s2 < p.L; ++s2)
+          if ((fx_mask >> s2) & 1u) pv.q_cld[p.req[s2]] = fx_cld[s2];
+        if ((fx_mask >> p.L) & 1u) { sh.fx_new[k] = fx_cld[p.L]; atomicMax(&sh.last_fx, k); }
+      }
+      __syncthreads();
+      if (tid == 0 && sh.last_fx >= 0) pv.q_cld[rq] = sh.fx_new[sh.last_fx];   // the last vehicle in the caller's order wins
+    }
+    // ---- D: commit
+    if (tid == 0 && sh.win_v >= 0) commit_one(pv, dv, ps, esrc, edst, tt64, rq, sh.win_v, sh.win_i, sh.win_j, T_now, err);
+    __syncthreads();
+    // ---- E: the winner's column for the requests still queued
+    if (sh.win_v >= 0) {
+      const int vs = pv.inv[sh.win_v];
+      for (int r2 = r + 1 + tid; r2 < n_new; r2 += QUEUE_THREADS) {
+        bool reach;
+        const double cm = pair_cmin(pv, dv, new_rows[r2], vs, &reach);
+        uint32_t* w = mask + (size_t)r2 * words + (vs >> 5);
+        if (reach) { cmin[(int64_t)r2 * nv + vs] = cm; atomicOr(w, 1u << (vs & 31)); }
+        else atomicAnd(w, ~(1u << (vs & 31)));
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -637,9 +864,12 @@ struct LegacyDev {
   double *d_dc = nullptr, *d_cmin = nullptr;
   uint32_t* d_mask = nullptr;
   int2* d_list = nullptr;
-  int* d_counters = nullptr;         // [0] list fill, [1] next request, [2] commit error
+  int* d_counters = nullptr;         // [0] list fill, [1] next request, [2] commit error, [3] fold events, [4] last vehicle that set the new request's Cld
+  FoldEvent* d_events = nullptr;
+  double* d_fx_new = nullptr;        // [vs] Cld the vehicle's scan left on the new request
   int64_t base_candidates = 0;       // sum over vehicles of (L+1)(L+2)/2 for the plans as they are now
   bool prepared = false, full_list = false, list_is_full = false;
+  double detail_ms[6] = {0, 0, 0, 0, 0, 0};   // last call: plan prep, reach test, evaluation, fold, queue loop; [5] = surviving pairs
   std::vector<int32_t> h_rows;       // the new-request rows of the running call
 };
 
@@ -667,7 +897,8 @@ int ensure_eval_buffers(LegacyDev& d, int n_new) {
   d.list_is_full = d.full_list;
   DrsArenaLayout lay;
   const size_t o_rows = lay.add(sizeof(int32_t) * cap), o_bv = lay.add(sizeof(int32_t) * cap), o_bi = lay.add(sizeof(int32_t) * cap),
-               o_bj = lay.add(sizeof(int32_t) * cap), o_dc = lay.add(sizeof(double) * cap), o_cnt = lay.add(sizeof(int) * 4),
+               o_bj = lay.add(sizeof(int32_t) * cap), o_dc = lay.add(sizeof(double) * cap), o_cnt = lay.add(sizeof(int) * 8), o_ev = lay.add(sizeof(FoldEvent) * FOLD_EVENT_CAP),
+               o_fx = lay.add(sizeof(double) * nv),
                o_mask = lay.add(sizeof(uint32_t) * (size_t)cap * words), o_list = lay.add(sizeof(int2) * (size_t)list_cap),
                o_cmin = lay.add(sizeof(double) * (size_t)pairs);
   int rc = d.res.reserve(lay.total);
@@ -675,7 +906,7 @@ int ensure_eval_buffers(LegacyDev& d, int n_new) {
   unsigned char* b = (unsigned char*)d.res.ptr;
   d.d_rows = (int32_t*)(b + o_rows); d.d_bv = (int32_t*)(b + o_bv); d.d_bi = (int32_t*)(b + o_bi); d.d_bj = (int32_t*)(b + o_bj);
   d.d_dc = (double*)(b + o_dc); d.d_counters = (int*)(b + o_cnt); d.d_mask = (uint32_t*)(b + o_mask); d.d_list = (int2*)(b + o_list);
-  d.d_cmin = (double*)(b + o_cmin);
+  d.d_cmin = (double*)(b + o_cmin); d.d_events = (FoldEvent*)(b + o_ev); d.d_fx_new = (double*)(b + o_fx);
   d.cap_new = cap; d.words = words; d.list_cap = list_cap;
   return DRS_OK;
 }
@@ -684,18 +915,22 @@ int ensure_eval_buffers(LegacyDev& d, int n_new) {
 int scan_all(drs_tick* t, LegacyDev& d, int n_new, cudaStream_t st) {
   const drs_graph* g = t->g;
   DistView dv{g->d_dist, g->ld, g->mode};
+  DrsTimer tm_prep(st), tm_reach(st), tm_eval(st);
+  tm_prep.start();
   if (!d.prepared) {
     plan_prep_kernel<<<(d.n_veh + 127) / 128, 128, 0, st>>>(d.pv, dv);
     drs_count_launch();
     d.prepared = true;
   }
+  tm_prep.stop();
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g->device);
   const size_t row_bytes = (size_t)g->ld * 4;
   const char* env = getenv("DRS_INS_STAGED");
   const bool staged = !g->directed && row_bytes <= 220 * 1024 && row_bytes % 16 == 0 && !(env && env[0] == '0');
   for (int attempt = 0; attempt < 2; ++attempt) {
-    DRS_CUDA(cudaMemsetAsync(d.d_counters, 0, sizeof(int) * 4, st));
+    DRS_CUDA(cudaMemsetAsync(d.d_counters, 0, sizeof(int) * 8, st));
+    tm_reach.start();
     const int grid = std::max(1, std::min(n_new, sms));
     if (staged) {
       DRS_CUDA(cudaFuncSetAttribute(insertion_reach_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_bytes));
@@ -704,6 +939,7 @@ int scan_all(drs_tick* t, LegacyDev& d, int n_new, cudaStream_t st) {
       insertion_reach_kernel<false><<<grid, 1024, 0, st>>>(d.pv, dv, n_new, d.d_rows, d.d_mask, d.words, d.d_list, d.list_cap, d.d_counters);
     }
     drs_count_launch();
+    tm_reach.stop();
     DRS_CUDA(cudaGetLastError());
     const int64_t pairs = (int64_t)n_new * d.n_veh;
     if (d.list_cap >= pairs) break;                    // the list cannot overflow
@@ -718,9 +954,15 @@ int scan_all(drs_tick* t, LegacyDev& d, int n_new, cudaStream_t st) {
     DRS_CUDA(cudaMemcpyAsync(d.d_rows, d.h_rows.data(), sizeof(int32_t) * n_new, cudaMemcpyHostToDevice, st));
   }
   const int eval_blocks = std::max(1, std::min(sms * 8, (d.list_cap + 127) / 128));
+  tm_eval.start();
   insertion_eval_kernel<<<eval_blocks, 128, 0, st>>>(d.pv, dv, d.d_rows, d.d_list, d.d_counters, d.list_cap, d.d_cmin);
   drs_count_launch();
+  tm_eval.stop();
   DRS_CUDA(cudaGetLastError());
+  int fill = 0;
+  DRS_CUDA(cudaMemcpyAsync(&fill, d.d_counters, sizeof(int), cudaMemcpyDeviceToHost, st));
+  DRS_CUDA(cudaStreamSynchronize(st));
+  d.detail_ms[0] = tm_prep.ms(); d.detail_ms[1] = tm_reach.ms(); d.detail_ms[2] = tm_eval.ms(); d.detail_ms[5] = (double)fill;
   return DRS_OK;
 }
 
@@ -885,19 +1127,20 @@ extern "C" int drs_tick_insertion_eval(drs_tick* t, int32_t n_new, const int32_t
   tm_scan.stop();
   tm_fold.start();
   insertion_fold_kernel<<<(n_new * 32 + 127) / 128, 128, 0, st>>>(d.pv, dv, 0, n_new, d.d_rows, d.d_mask, d.words, d.d_cmin, d.d_bv, d.d_bi,
-                                                                    d.d_bj, d.d_dc);
+                                                                    d.d_bj, d.d_dc, nullptr, nullptr);
   drs_count_launch();
   tm_fold.stop();
   DRS_CUDA(cudaGetLastError());
   if ((rc = fetch_results(d, n_new, best_veh, best_i, best_j, best_dc, st))) return rc;
   t->last_ms[2] = tm_scan.ms(); t->last_ms[3] = tm_fold.ms();
+  d.detail_ms[3] = t->last_ms[3]; d.detail_ms[4] = 0;
   if (n_candidates) *n_candidates = d.base_candidates * n_new;
   return DRS_OK;
 }
 
 // Sequential queue (lib/Agents.py:1429-1448): the requests are inserted one after another, each scan seeing the routes,
 // costs and predicted waiting times the previous winners' build_route left behind.
-extern "C" int drs_tick_insertion_queue(drs_tick* t, int32_t n_new, const int32_t* new_rows, double T_now, int32_t* best_veh,
+extern "C" int drs_tick_insertion_queue(drs_tick* t, int32_t n_new, const int32_t* new_rows, double T_now, int32_t flags, int32_t* best_veh,
                                         int32_t* best_i, int32_t* best_j, double* best_dc, int64_t* n_candidates) {
   int rc = check_new_rows("drs_tick_insertion_queue", t, n_new, new_rows, best_veh, best_i, best_j, best_dc);
   if (rc) return rc;
@@ -919,12 +1162,40 @@ extern "C" int drs_tick_insertion_queue(drs_tick* t, int32_t n_new, const int32_
   tm_queue.start();
   int* d_err = d.d_counters + 2;
   const int rescan_blocks = std::max(1, std::min(148, (n_new + 127) / 128));
-  for (int r = 0; r < n_new; ++r) {
-    insertion_fold_kernel<<<1, 32, 0, st>>>(d.pv, dv, r, 1, d.d_rows, d.d_mask, d.words, d.d_cmin, d.d_bv, d.d_bi, d.d_bj, d.d_dc);
-    insertion_commit_kernel<<<1, 32, 0, st>>>(d.pv, dv, ps, g->d_esrc, g->d_edst, g->d_tt64, d.d_rows, r, d.d_bv, d.d_bi, d.d_bj, T_now, d_err);
+  const bool track_cld = (flags & DRS_QUEUE_TRACK_CLD) != 0;
+  const char* unfused_env = getenv("DRS_INS_QUEUE_UNFUSED");
+  bool fused = !(unfused_env && unfused_env[0] == '1') && d.n_veh > 0;
+  if (fused) {
+    // one persistent CTA walks the whole queue (insertion_queue_kernel)
+    DRS_CUDA(cudaFuncSetAttribute(insertion_queue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QueueShared)));
+    insertion_queue_kernel<<<1, QUEUE_THREADS, sizeof(QueueShared), st>>>(d.pv, dv, ps, g->d_esrc, g->d_edst, g->d_tt64, n_new, d.d_rows, d.d_mask,
+                                                                           d.words, d.d_cmin, d.d_bv, d.d_bi, d.d_bj, d.d_dc, T_now, track_cld ? 1 : 0,
+                                                                           d_err);
+    drs_count_launch();
+    DRS_CUDA(cudaGetLastError());
+    int err5 = 0;
+    DRS_CUDA(cudaMemcpyAsync(&err5, d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    DRS_CUDA(cudaStreamSynchronize(st));
+    DRS_REQUIRE(err5 != 5, DRS_ERR_CAPACITY, "drs_tick_insertion_queue: more than %d vehicles in reach of one request; "
+                "set DRS_INS_QUEUE_UNFUSED=1 for the kernel-per-step form", QUEUE_MAXC);
+  }
+  int* d_nev = d.d_counters + 3;
+  int* d_last_v = d.d_counters + 4;
+  if (track_cld) {
+    const int minus_one = -1;
+    DRS_CUDA(cudaMemcpyAsync(d_last_v, &minus_one, sizeof(int), cudaMemcpyHostToDevice, st));
+  }
+  for (int r = 0; r < n_new && !fused; ++r) {
+    insertion_fold_kernel<<<1, 32, 0, st>>>(d.pv, dv, r, 1, d.d_rows, d.d_mask, d.words, d.d_cmin, d.d_bv, d.d_bi, d.d_bj, d.d_dc,
+                                            track_cld ? d.d_events : nullptr, d_nev);
+    if (track_cld)
+      insertion_sidefx_kernel<<<(d.n_veh + 127) / 128, 128, 0, st>>>(d.pv, dv, d.d_rows, r, d.d_mask, d.words, d.d_events, d_nev, d.d_fx_new,
+                                                                      d_last_v, d_err);
+    insertion_commit_kernel<<<1, 32, 0, st>>>(d.pv, dv, ps, g->d_esrc, g->d_edst, g->d_tt64, d.d_rows, r, d.d_bv, d.d_bi, d.d_bj, T_now, d_err,
+                                              track_cld ? d.d_fx_new : nullptr, d_last_v);
     if (r + 1 < n_new)
       insertion_rescan_kernel<<<rescan_blocks, 128, 0, st>>>(d.pv, dv, n_new, d.d_rows, r, d.d_bv, d.d_mask, d.words, d.d_cmin);
-    drs_count_launch(r + 1 < n_new ? 3 : 2);
+    drs_count_launch(2 + (track_cld ? 1 : 0) + (r + 1 < n_new ? 1 : 0));
   }
   tm_queue.stop();
   DRS_CUDA(cudaGetLastError());
@@ -932,6 +1203,7 @@ extern "C" int drs_tick_insertion_queue(drs_tick* t, int32_t n_new, const int32_
   DRS_CUDA(cudaMemcpyAsync(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
   if ((rc = fetch_results(d, n_new, best_veh, best_i, best_j, best_dc, st))) return rc;
   t->last_ms[2] = tm_scan.ms(); t->last_ms[3] = tm_queue.ms();
+  d.detail_ms[3] = 0; d.detail_ms[4] = t->last_ms[3];
   DRS_REQUIRE(err == 0, DRS_ERR_STATE, "drs_tick_insertion_queue: a winner's plan could not be patched (code %d)", err);
   if (n_candidates) {
     // every request scans every vehicle's plan as it is at its turn;
@@ -1020,5 +1292,14 @@ extern "C" int drs_tick_fetch_plans(drs_tick* t, double* veh_cost, int32_t* plan
         if (stop_pod) stop_pod[(size_t)v * stops_per_vehicle + k] = mpod[(size_t)k * nv + vs];
       }
   }
+  return DRS_OK;
+}
+
+// Device times of the last insertion call by kernel (ms): [0] plan prep, [1] reach test, [2] evaluation of the surviving
+// pairs, [3] fold (drs_tick_insertion_eval), [4] fold / commit / re-scan loop (drs_tick_insertion_queue); [5] = number of
+// (request, vehicle) pairs that survived the reach test.
+extern "C" int drs_tick_last_insertion_ms(const drs_tick* t, double* ms) {
+  DRS_REQUIRE(t && t->legacy && ms, DRS_ERR_ARG, "drs_tick_last_insertion_ms: no insertion call on this tick yet");
+  for (int i = 0; i < 6; ++i) ms[i] = t->legacy->detail_ms[i];
   return DRS_OK;
 }

@@ -611,6 +611,7 @@ extern "C" int drs_sssp_batch_dev(const drs_graph* g, int32_t mode, int32_t nsrc
     grid = mode == DRS_MODE_F32 ? sssp_grid<float>(sms, nsrc) : sssp_grid<int>(sms, nsrc);
   }
   // packed arcs (narcs records) followed by the ELL records (4 per vertex)
+  if (!gm->sssp_arcs) drs_count_alloc();
   if (!gm->sssp_arcs) DRS_CUDA(cudaMalloc(&gm->sssp_arcs, sizeof(int2) * ((size_t)std::max(g->narcs, 1) + 4 + (size_t)SSSP_D * g->n)));
   int2* d_ell = (int2*)gm->sssp_arcs + ((std::max(g->narcs, 1) + 3) & ~3);   // 32-byte aligned: records are read with one 256-bit load
   if (!gm->sssp_arcs_valid) {
@@ -623,6 +624,7 @@ extern "C" int drs_sssp_batch_dev(const drs_graph* g, int32_t mode, int32_t nsrc
   if (gm->sssp_sources_cap < nsrc) {
     if (gm->sssp_sources) cudaFree(gm->sssp_sources);
     gm->sssp_sources = nullptr; gm->sssp_sources_cap = 0;
+    drs_count_alloc();
     DRS_CUDA(cudaMalloc((void**)&gm->sssp_sources, sizeof(int32_t) * (size_t)nsrc + 2 * sizeof(int)));
     gm->sssp_sources_cap = nsrc;
   }
@@ -636,6 +638,7 @@ extern "C" int drs_sssp_batch_dev(const drs_graph* g, int32_t mode, int32_t nsrc
     if (gm->sssp_queue_bytes < need) {
       if (gm->sssp_queues) cudaFree(gm->sssp_queues);
       gm->sssp_queues = nullptr; gm->sssp_queue_bytes = 0;
+      drs_count_alloc();
       if (cudaMalloc(&gm->sssp_queues, need) != cudaSuccess) {
         DRS_REQUIRE(false, DRS_ERR_NOMEM, "drs_sssp_batch_dev: cannot allocate %zu bytes of work queues", need);
       }
@@ -685,6 +688,7 @@ extern "C" int drs_sssp_batch(const drs_graph* g, int32_t mode, int32_t nsrc, co
   DrsDeviceGuard guard(g->device);
   const int64_t ld = g->npad;
   void* d = nullptr;
+  drs_count_alloc();
   DRS_CUDA(cudaMalloc(&d, sizeof(float) * ld * nsrc));
   int rc = drs_sssp_batch_dev(g, mode, nsrc, sources_host, d, ld, 0.0, g->stream);
   if (rc == DRS_OK) {

@@ -572,10 +572,12 @@ class InsertionTick(object):
         Returns (best_veh, best_i, best_j, best_dc, n_candidates) for the new-request rows."""
         return self._run(self.lib.drs_tick_insertion_eval, new_rows)
 
-    def queue(self, new_rows, T_now):
+    def queue(self, new_rows, T_now, track_cld=True):
         """Model.insertion_heuristics (lib/Agents.py:1429-1448): the requests one after another, each seeing the plans
-        the previous winners' build_route left behind; the plans stay patched on the device."""
-        return self._run(self.lib.drs_tick_insertion_queue, new_rows, C.c_double(float(T_now)))
+        the previous winners' build_route left behind; the plans stay patched on the device.  track_cld also leaves in
+        the request table (fetch_plans()["Cld"]) the Req.Cld values the reference's scans assign as a side effect."""
+        return self._run(self.lib.drs_tick_insertion_queue, new_rows, C.c_double(float(T_now)),
+                         C.c_int32(_lib.QUEUE_TRACK_CLD if track_cld else 0))
 
     def commit(self, row, veh, i, j, T_now):
         _lib.check(self.lib.drs_tick_commit_insertion(self.handle, int(row), int(veh), int(i), int(j), float(T_now)), self.lib)
@@ -595,9 +597,11 @@ class InsertionTick(object):
         return {"c": c, "routes": routes, "Cld": cld, "pwt": pwt}
 
     def last_ms(self):
-        ms = np.zeros(4, dtype=np.float64)
-        _lib.check(self.lib.drs_tick_last_ms(self.handle, _lib.ptr_f64(ms)), self.lib)
-        return {"scan": float(ms[2]), "fold": float(ms[3])}
+        """Device times (ms) of the last evaluate() / queue() by kernel, and the pairs that survived the reach test."""
+        ms = np.zeros(6, dtype=np.float64)
+        _lib.check(self.lib.drs_tick_last_insertion_ms(self.handle, _lib.ptr_f64(ms)), self.lib)
+        return {"prep": float(ms[0]), "reach": float(ms[1]), "eval": float(ms[2]), "fold": float(ms[3]), "queue": float(ms[4]),
+                "scan": float(ms[0] + ms[1] + ms[2]), "survivors": int(ms[5])}
 
     def close(self):
         if self.handle:
@@ -634,10 +638,12 @@ class InsertionHeuristics(object):
     def _marshal(self, router, new_reqs):
         G = router.G
         rows, table = {}, {k: [] for k in ("o", "d", "Cep", "Clp", "Cld", "Ts", "Tr", "pwt")}
+        self._row_reqs = []                                    # request object of every table row (Cld write-back)
 
         def row_of(rq):
             if rq.id not in rows:
                 rows[rq.id] = len(table["o"])
+                self._row_reqs.append(rq)
                 table["o"].append(G.node_of_location(rq.olng, rq.olat))
                 table["d"].append(G.node_of_location(rq.dlng, rq.dlat))
                 for k in ("Cep", "Clp", "Cld", "Ts", "Tr", "pwt"):
@@ -686,10 +692,19 @@ class InsertionHeuristics(object):
             veh._drs_route = list(route)
         return route
 
+    def _run_queue(self, router, reqs_q, T):
+        new_rows = self._load(router, reqs_q)
+        bv, bi, bj, dc, _ = self._tick.queue(new_rows, T, track_cld=True)
+        # Req.Cld as the reference's scans leave it (lib/Agents.py:1550,1554): on-board riders of later ticks are checked
+        # against it (lib/Agents.py:1555)
+        cld = self._tick.fetch_plans()["Cld"]
+        for row, rq in enumerate(self._row_reqs):
+            rq.Cld = float(cld[row])
+        return bv, bi, bj, dc
+
     def insert_heuristics(self, router, req, T):
         """lib/Agents.py:1451-1490.  Returns True when the request was assigned."""
-        new_rows = self._load(router, [req])
-        bv, bi, bj, dc, _ = self._tick.evaluate(new_rows)
+        bv, bi, bj, dc = self._run_queue(router, [req], T)
         if bv[0] < 0:
             return False
         veh = self.vehs[int(bv[0])]
@@ -702,8 +717,7 @@ class InsertionHeuristics(object):
         reqs_q = [self.queue.popleft() for _ in range(len(self.queue))]
         if not reqs_q:
             return
-        new_rows = self._load(router, reqs_q)
-        bv, bi, bj, dc, _ = self._tick.queue(new_rows, T)
+        bv, bi, bj, dc = self._run_queue(router, reqs_q, T)
         self.last_results = []
         for k, req in enumerate(reqs_q):
             if bv[k] < 0:

@@ -367,6 +367,8 @@ class RoadGraph(object):
     def _ensure(self, weights, build=True):
         """Device graph exists, carries `weights`, and (build=True) the APSP matrix is valid."""
         attr = weights if weights is not None else (self._weight_attr or "ttmedian")
+        if self._valid and attr == self._weight_attr and not self._weights_dirty and self._lib is not None:
+            return self._lib                                  # the common case of every query: nothing to do
         if not isinstance(attr, str):
             raise ValueError("weights must name an edge attribute")
         if attr not in self._eattrs:
@@ -455,20 +457,42 @@ class RoadGraph(object):
                                        _lib.ptr_f64(ln), _lib.ptr_i32(hops)), lib)
         return tt, ln, hops
 
+    def pair_sums(self, s, t, weights=None):
+        """Scalar form of path_sums for one (s, t): (duration, length, hops).  One kernel launch whose answer lands in
+        mapped host memory (drs_query_pair); the reference asks one pair at a time (lib/Agents.py:898-923, 756, 1073)."""
+        lib = self._ensure(weights)
+        if not (0 <= s < self.n and 0 <= t < self.n):
+            raise ValueError("vertex index out of range (n=%d)" % self.n)
+        if self._new_of_old is not None:
+            s, t = int(self._new_of_old[s]), int(self._new_of_old[t])
+        out = self._scalar_out
+        if out is None:
+            out = self._scalar_out = (C.c_double(), C.c_double(), C.c_int32())
+        _lib.check(lib.drs_query_pair(self._handle, s, t, C.byref(out[0]), C.byref(out[1]), C.byref(out[2])), lib)
+        return out[0].value, out[1].value, out[2].value
+
+    _scalar_out = None
+
     def epath(self, s, t, weights=None):
         lib = self._ensure(weights)
-        s, t = (int(x) for x in self.dev_ids([s, t]))
-        cap = 256
+        if not (0 <= s < self.n and 0 <= t < self.n):
+            raise ValueError("vertex index out of range (n=%d)" % self.n)
+        if self._new_of_old is not None:
+            s, t = int(self._new_of_old[s]), int(self._new_of_old[t])
+        buf = self._path_buf
+        if buf is None:
+            buf = self._path_buf = np.empty(1024, dtype=np.int32)
         while True:
-            buf = np.empty(cap, dtype=np.int32)
-            n = C.c_int32(cap)
+            n = C.c_int32(len(buf))
             reach = C.c_int32(0)
             rc = lib.drs_path(self._handle, int(s), int(t), _lib.ptr_i32(buf), C.byref(n), C.byref(reach))
             if rc == _lib.ERR_CAPACITY:
-                cap = max(n.value, cap * 2)
+                buf = self._path_buf = np.empty(max(n.value, 2 * len(buf)), dtype=np.int32)
                 continue
             _lib.check(rc, lib)
-            return [int(e) for e in buf[:n.value]]
+            return buf[:n.value].tolist()
+
+    _path_buf = None
 
     def sssp(self, sources, weights=None):
         """Distances from the given sources WITHOUT the N x N matrix (batched delta-stepping SSSP);
@@ -606,8 +630,7 @@ class RoutingEngine(object):
     def _sums(self, olng, olat, dlng, dlat):
         o = self.G.node_index(str((olng, olat)))
         d = self.G.node_index(str((dlng, dlat)))
-        tt, ln, hops = self.G.path_sums([o], [d], self.ttweight)
-        return float(tt[0]), float(ln[0]), int(hops[0])
+        return self.G.pair_sums(o, d, self.ttweight)
 
     def get_distance(self, olng, olat, dlng, dlat):
         """lib/RoutingEngine.py:195-205: length along the TIME-shortest path (int 0 for an empty path)."""

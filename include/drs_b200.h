@@ -189,6 +189,10 @@ int drs_query_pairs(const drs_graph* g, int32_t npairs, const int32_t* s_host,
                     const int32_t* t_host, double* tt_out_host, double* len_out_host,
                     int32_t* hops_out_host);
 
+/* Scalar form of drs_query_pairs -- the reference asks one pair at a time (lib/Agents.py:898-923, 756, 1073): ONE kernel
+ * that reads the pair from, and writes the answer to, pinned host memory mapped into the device; no allocation, no copy. */
+int drs_query_pair(const drs_graph* g, int32_t s, int32_t t, double* tt_out, double* len_out, int32_t* hops_out);
+
 /* Matrix look-up only (no path walk): dist[s,t] as double, inf if unreachable.
  * Replaces shortestPathTime (lib/optimUtils.py:656-664). */
 int drs_query_matrix(const drs_graph* g, int32_t npairs, const int32_t* s_host,
@@ -367,11 +371,16 @@ int drs_tick_insertion_eval(drs_tick* t, int32_t n_new, const int32_t* new_rows_
  * the device: after a request is folded, its winner's plan is patched, that vehicle is re-prepared and its column is
  * re-evaluated for the requests still queued.  Outputs as drs_tick_insertion_eval; the plans stay patched (fetch them
  * with drs_tick_fetch_plans).  Plans hold at most DRS_INS_MAX_PLAN stops; a vehicle whose plan could not take two more
- * is not insertable.  Not reproduced: the Req.Cld values test_constraints_get_cost leaves on requests it merely
- * evaluated (lib/Agents.py:1550,1554) -- within a tick they are rewritten before every read; see INTEGRATION.md. */
+ * cannot be patched (the call fails instead of picking another vehicle).
+ * flags: DRS_QUEUE_TRACK_CLD also reproduces the side effect of lib/Agents.py:1550,1554 -- test_constraints_get_cost
+ * assigns Req.Cld at every pickup of every candidate it walks, so after a scan each waiting request carries the value
+ * of the LAST walk that reached its pickup; one extra kernel per request repeats the bounded scan of the vehicles in
+ * reach and leaves those values in the request table (drs_tick_fetch_plans row_Cld).  Within a tick the values are
+ * rewritten before every read, so winners do not depend on the flag; it matters for on-board riders of later ticks. */
+#define DRS_QUEUE_TRACK_CLD 1
 #define DRS_INS_MAX_PLAN 16
-int drs_tick_insertion_queue(drs_tick* t, int32_t n_new, const int32_t* new_rows_host, double T_now, int32_t* best_veh,
-                             int32_t* best_i, int32_t* best_j, double* best_dc, int64_t* n_candidates);
+int drs_tick_insertion_queue(drs_tick* t, int32_t n_new, const int32_t* new_rows_host, double T_now, int32_t flags,
+                             int32_t* best_veh, int32_t* best_i, int32_t* best_j, double* best_dc, int64_t* n_candidates);
 /* One commit by hand (the building block of the queue): request row req_row joins vehicle veh with its pickup at route
  * position i and its drop-off at j (lib/Agents.py:1468-1469), then Veh.build_route's bookkeeping as above. */
 int drs_tick_commit_insertion(drs_tick* t, int32_t req_row, int32_t veh, int32_t i, int32_t j, double T_now);
@@ -388,6 +397,10 @@ int drs_graph_stream(const drs_graph* g, void** stream);
  * ms[0] rv_filter, ms[1] rv_eval (drs_tick_rv_eval); ms[2] insertion scan = plan prep + reach test + evaluation,
  * ms[3] insertion fold (drs_tick_insertion_eval) or the whole fold / commit / re-scan loop (drs_tick_insertion_queue). */
 int drs_tick_last_ms(const drs_tick* t, double* ms);
+/* Device times of the last insertion call by kernel (ms): [0] plan prep, [1] reach test, [2] evaluation of the surviving
+ * pairs, [3] fold (drs_tick_insertion_eval), [4] fold / commit / re-scan loop (drs_tick_insertion_queue); ms[5] = number
+ * of (request, vehicle) pairs that survived the reach test. */
+int drs_tick_last_insertion_ms(const drs_tick* t, double* ms);
 /* Number of kernels this library has launched in this process so far. */
 int64_t drs_launch_count(void);
 /* Number of device allocations (cudaMalloc) this library has made in this process so far: a steady-state tick or query

@@ -303,6 +303,9 @@ def test_insertion_queue_matches_the_references_own_ticks(tag):
         touched = set(r for v in set(winners) for (r, pod) in state["routes"][v] if pod == 1)
         for r in touched:
             assert eq(state["pwt"][r], unjf(after["after_pwt"][r])), (tag, T, r)
+        # Req.Cld of EVERY request as the reference's scans left it (side effect of lib/Agents.py:1550,1554)
+        for r, want_cld in enumerate(after["after_Cld"]):
+            assert eq(state["Cld"][r], unjf(want_cld)), (tag, T, r)
     tick.close()
     G.close()
 
@@ -353,4 +356,34 @@ def test_insertion_queue_matches_oracle_queue_on_a_fleet():
         assert state["c"][v] == ov["c"] and state["routes"][v] == [(s[0], s[1]) for s in ov["route"]]
     for r, rq in oreqs.items():
         assert state["pwt"][r] == rq["pwt"]
+    G.close()
+
+
+@pytest.mark.parametrize("tag", ["g8_int_K4", "g20_int_K4", "g20_uniform_K4"])
+def test_single_scans_leave_the_references_cld(tag):
+    """One request at a time (the granularity of Model.insert_heuristics): winner and the Req.Cld value of EVERY request
+    after the scan -- candidates that were merely evaluated leave their mark too (lib/Agents.py:1550,1554)."""
+    from conftest import load_golden, unjf
+    from drs_abm_b200.dispatch import InsertionTick
+    from drs_abm_b200.gml import read_gml
+    from drs_abm_b200.routing import RoadGraph
+    gold = load_golden("legacy_%s.json" % tag)
+    G = RoadGraph(read_gml(golden_map_path(gold["map"])))
+    tick = None
+    changed = 0
+    for rec in gold["insertions"]:
+        vehs, table = _golden_tick(G, rec)
+        if tick is None:
+            tick = InsertionTick(G, vehs, table)
+        else:
+            tick.set_plans(vehs, table)
+        bv, bi, bj, dc, _ = tick.queue([rec["rid"]], unjf(rec["T"]), track_cld=True)
+        w = rec["winner"]
+        assert (int(bv[0]), int(bi[0]), int(bj[0])) == ((w["vid"], w["i"], w["j"]) if w else (-1, -1, -1))
+        cld = tick.fetch_plans()["Cld"]
+        want = np.array([unjf(x) for x in rec["after_Cld"]])
+        assert np.array_equal(cld, want), (tag, rec["rid"], np.flatnonzero(cld != want))
+        changed += int(np.sum(want != table["Cld"]))
+    assert changed > 0
+    tick.close()
     G.close()
