@@ -642,28 +642,36 @@ __device__ void commit_one(const PlanView& pv, const DistView& dv, const PredSou
   }
   pv.len[vs] = L2;
   const bool merge = pv.keep_node[vs] >= 0;              // len(self.route) > 0 (:156-160)
-  for (int k = 0; k < L2; ++k)
-    if (pod[k] > 0) pv.q_pwt[req[k]] = merge ? 0.0 + pv.keep_et[vs] : 0.0;
   int cur = merge ? pv.keep_node[vs] : pv.pos_node[vs];
   if (cur < 0) { *err = 2; return; }                     // a vehicle without a route must stand on a vertex
   const int first_from = cur;
-  double vt = merge ? 0.0 + pv.keep_t[vs] : 0.0;
+  // all leg times and pickup windows first (independent loads in flight together), then the dependent arithmetic
+  double pred[INS_MAXL], cep[INS_MAXL], pwt[INS_MAXL];
+  for (int k = 0; k < L2; ++k) {
+    pred[k] = (cur == node[k]) ? 0.0 : dv.at(cur, node[k]);
+    cep[k] = pod[k] > 0 ? pv.q_cep[req[k]] : 0.0;
+    cur = node[k];
+  }
+  const double keep_t = merge ? pv.keep_t[vs] : 0.0, keep_et = merge ? pv.keep_et[vs] : 0.0;
+  for (int k = 0; k < L2; ++k) pwt[k] = merge ? 0.0 + keep_et : 0.0;      // pwt = 0 (+ the kept step's expected time) (:186-193)
+  double vt = merge ? 0.0 + keep_t : 0.0;
   double c = 0.0, t = 0.0;
   int n = pv.onboard[vs];
   for (int k = 0; k < L2; ++k) {
-    const double pred_t = (cur == node[k]) ? 0.0 : dv.at(cur, node[k]);
+    const double pred_t = pred[k];
     double t_leg = pred_t;
-    if (pod[k] > 0 && T_now + vt + t_leg < pv.q_cep[req[k]]) t_leg += pv.q_cep[req[k]] - (T_now + vt + t_leg);   // add_leg waits (:363-367)
+    if (pod[k] > 0 && T_now + vt + t_leg < cep[k]) t_leg += cep[k] - (T_now + vt + t_leg);   // add_leg waits (:363-367)
     vt += t_leg;
     for (int m = k; m < L2; ++m)
-      if (pod[m] > 0) pv.q_pwt[req[m]] += pred_t;        // every request not yet picked up, this one included (:214-220)
-    const double leg_t = (k == 0 && merge) ? pv.keep_t[vs] + t_leg : t_leg;   // the kept step joins the first leg (:222-240)
+      if (pod[m] > 0) pwt[m] += pred_t;                  // every request not yet picked up, this one included (:214-220)
+    const double leg_t = (k == 0 && merge) ? keep_t + t_leg : t_leg;   // the kept step joins the first leg (:222-240)
     t += leg_t;
     c += n * leg_t * pv.prm.coef_inveh;
     n += pod[k];
     if (pod[k] > 0) c += t * pv.prm.coef_wait;
-    cur = node[k];
   }
+  for (int k = 0; k < L2; ++k)
+    if (pod[k] > 0) pv.q_pwt[req[k]] = pwt[k];
   pv.cost[vs] = c;
   if (!merge) {
     // first step of the leg first_from -> node[0] along the canonical path: walk the predecessor chain back from the stop
@@ -751,8 +759,11 @@ struct QueueShared {
 __global__ void __launch_bounds__(QUEUE_THREADS, 1) insertion_queue_kernel(
     PlanView pv, DistView dv, PredSource ps, const int32_t* esrc, const int32_t* edst, const double* tt64, int n_new,
     const int32_t* new_rows, uint32_t* mask, int words, double* cmin, int32_t* best_veh, int32_t* best_i, int32_t* best_j,
-    double* best_dc, double T_now, int track_cld, int* err) {
+    double* best_dc, double T_now, int track_cld, int* err, unsigned long long* prof /* cycles of thread 0 by phase A..E, [5] listed vehicles, [6] re-scans */) {
   extern __shared__ __align__(16) unsigned char queue_smem[];
+  unsigned long long pacc[7] = {0, 0, 0, 0, 0, 0, 0};
+  long long pt = clock64();
+  auto lap = [&](int i) { const long long now = clock64(); pacc[i] += (unsigned long long)(now - pt); pt = now; };
   QueueShared& sh = *reinterpret_cast<QueueShared*>(queue_smem);
   const int tid = threadIdx.x, lane = tid & 31, nv = pv.n_veh;
   const double inf = d_inf();
@@ -782,6 +793,8 @@ __global__ void __launch_bounds__(QUEUE_THREADS, 1) insertion_queue_kernel(
       sh.order[rank] = k;
     }
     __syncthreads();
+    lap(0);
+    pacc[5] += cnt;
     // ---- B: fold (warp 0)
     if (tid < 32) {
       double dc = inf;
@@ -804,6 +817,8 @@ __global__ void __launch_bounds__(QUEUE_THREADS, 1) insertion_queue_kernel(
       }
     }
     __syncthreads();
+    lap(1);
+    pacc[6] += sh.n_ev;
     // ---- C: Req.Cld side effects of this scan (lib/Agents.py:1550,1554)
     if (track_cld) {
       for (int k = tid; k < cnt; k += QUEUE_THREADS) {
@@ -832,9 +847,11 @@ __global__ void __launch_bounds__(QUEUE_THREADS, 1) insertion_queue_kernel(
       __syncthreads();
       if (tid == 0 && sh.last_fx >= 0) pv.q_cld[rq] = sh.fx_new[sh.last_fx];   // the last vehicle in the caller's order wins
     }
+    lap(2);
     // ---- D: commit
     if (tid == 0 && sh.win_v >= 0) commit_one(pv, dv, ps, esrc, edst, tt64, rq, sh.win_v, sh.win_i, sh.win_j, T_now, err);
     __syncthreads();
+    lap(3);
     // ---- E: the winner's column for the requests still queued
     if (sh.win_v >= 0) {
       const int vs = pv.inv[sh.win_v];
@@ -847,7 +864,10 @@ __global__ void __launch_bounds__(QUEUE_THREADS, 1) insertion_queue_kernel(
       }
     }
     __syncthreads();
+    lap(4);
   }
+  if (tid == 0 && prof)
+    for (int i = 0; i < 7; ++i) prof[i] = pacc[i];
 }
 
 }  // namespace
@@ -866,6 +886,7 @@ struct LegacyDev {
   int2* d_list = nullptr;
   int* d_counters = nullptr;         // [0] list fill, [1] next request, [2] commit error, [3] fold events, [4] last vehicle that set the new request's Cld
   FoldEvent* d_events = nullptr;
+  unsigned long long* d_prof = nullptr;
   double* d_fx_new = nullptr;        // [vs] Cld the vehicle's scan left on the new request
   int64_t base_candidates = 0;       // sum over vehicles of (L+1)(L+2)/2 for the plans as they are now
   bool prepared = false, full_list = false, list_is_full = false;
@@ -897,7 +918,7 @@ int ensure_eval_buffers(LegacyDev& d, int n_new) {
   d.list_is_full = d.full_list;
   DrsArenaLayout lay;
   const size_t o_rows = lay.add(sizeof(int32_t) * cap), o_bv = lay.add(sizeof(int32_t) * cap), o_bi = lay.add(sizeof(int32_t) * cap),
-               o_bj = lay.add(sizeof(int32_t) * cap), o_dc = lay.add(sizeof(double) * cap), o_cnt = lay.add(sizeof(int) * 8), o_ev = lay.add(sizeof(FoldEvent) * FOLD_EVENT_CAP),
+               o_bj = lay.add(sizeof(int32_t) * cap), o_dc = lay.add(sizeof(double) * cap), o_cnt = lay.add(sizeof(int) * 8), o_prof = lay.add(64), o_ev = lay.add(sizeof(FoldEvent) * FOLD_EVENT_CAP),
                o_fx = lay.add(sizeof(double) * nv),
                o_mask = lay.add(sizeof(uint32_t) * (size_t)cap * words), o_list = lay.add(sizeof(int2) * (size_t)list_cap),
                o_cmin = lay.add(sizeof(double) * (size_t)pairs);
@@ -906,6 +927,7 @@ int ensure_eval_buffers(LegacyDev& d, int n_new) {
   unsigned char* b = (unsigned char*)d.res.ptr;
   d.d_rows = (int32_t*)(b + o_rows); d.d_bv = (int32_t*)(b + o_bv); d.d_bi = (int32_t*)(b + o_bi); d.d_bj = (int32_t*)(b + o_bj);
   d.d_dc = (double*)(b + o_dc); d.d_counters = (int*)(b + o_cnt); d.d_mask = (uint32_t*)(b + o_mask); d.d_list = (int2*)(b + o_list);
+  d.d_prof = (unsigned long long*)(b + o_prof);
   d.d_cmin = (double*)(b + o_cmin); d.d_events = (FoldEvent*)(b + o_ev); d.d_fx_new = (double*)(b + o_fx);
   d.cap_new = cap; d.words = words; d.list_cap = list_cap;
   return DRS_OK;
@@ -1170,12 +1192,19 @@ extern "C" int drs_tick_insertion_queue(drs_tick* t, int32_t n_new, const int32_
     DRS_CUDA(cudaFuncSetAttribute(insertion_queue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QueueShared)));
     insertion_queue_kernel<<<1, QUEUE_THREADS, sizeof(QueueShared), st>>>(d.pv, dv, ps, g->d_esrc, g->d_edst, g->d_tt64, n_new, d.d_rows, d.d_mask,
                                                                            d.words, d.d_cmin, d.d_bv, d.d_bi, d.d_bj, d.d_dc, T_now, track_cld ? 1 : 0,
-                                                                           d_err);
+                                                                           d_err, d.d_prof);
     drs_count_launch();
     DRS_CUDA(cudaGetLastError());
     int err5 = 0;
     DRS_CUDA(cudaMemcpyAsync(&err5, d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
     DRS_CUDA(cudaStreamSynchronize(st));
+    if (getenv("DRS_INS_QUEUE_PROF")) {
+      unsigned long long pr[8];
+      cudaMemcpy(pr, d.d_prof, sizeof(pr), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[queue prof] %d requests: cycles/request list %.0f fold %.0f sidefx %.0f commit %.0f rescan %.0f | listed vehicles/request %.1f "
+              "re-scans/request %.2f\n", n_new, (double)pr[0] / n_new, (double)pr[1] / n_new, (double)pr[2] / n_new, (double)pr[3] / n_new,
+              (double)pr[4] / n_new, (double)pr[5] / n_new, (double)pr[6] / n_new);
+    }
     DRS_REQUIRE(err5 != 5, DRS_ERR_CAPACITY, "drs_tick_insertion_queue: more than %d vehicles in reach of one request; "
                 "set DRS_INS_QUEUE_UNFUSED=1 for the kernel-per-step form", QUEUE_MAXC);
   }
