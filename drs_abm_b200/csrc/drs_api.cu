@@ -44,6 +44,19 @@ void free_matrices(drs_graph* g) {
 
 }  // namespace
 
+static void classify_weights(drs_graph* g) {
+  g->weights_integral = true;
+  for (double w : g->h_tt)
+    if (!(w == std::floor(w) && w < 1e6)) { g->weights_integral = false; break; }
+}
+
+int drs_check_mode(const drs_graph* g, int mode, const char* who) {
+  DRS_REQUIRE(mode == DRS_MODE_F32 || mode == DRS_MODE_I32, DRS_ERR_ARG, "%s: unknown mode %d", who, mode);
+  DRS_REQUIRE(mode != DRS_MODE_I32 || g->weights_integral, DRS_ERR_ARG,
+              "%s: DRS_MODE_I32 needs integer travel times below 1e6 (this map has others; use DRS_MODE_F32)", who);
+  return DRS_OK;
+}
+
 // (Re)builds the float weight arrays of both CSRs from h_tt (drs_graph_set_weights; creation fills them in the arena copy).
 int drs_graph_upload_weights(drs_graph* g) {
   std::vector<float> out_w(g->narcs), in_w(g->narcs);
@@ -77,6 +90,7 @@ extern "C" int drs_graph_create(int32_t n, int32_t m, int32_t directed, const in
   g->npad = (n + DRS_FW_TILE - 1) / DRS_FW_TILE * DRS_FW_TILE;
   g->h_src.assign(src, src + m); g->h_dst.assign(dst, dst + m);
   g->h_tt.assign(tt, tt + m); g->h_len.assign(length, length + m);
+  classify_weights(g);
 
   // arcs: (u, v, eid); undirected edges contribute both directions.  Adjacency
   // order = edge id order (igraph incidence-list order).
@@ -153,6 +167,7 @@ extern "C" int drs_graph_set_weights(drs_graph* g, const double* tt) {
                 "drs_graph_set_weights: edge %d travel time must be finite and > 0 (got %g)", e, tt[e]);
   DrsDeviceGuard guard(g->device);
   g->h_tt.assign(tt, tt + g->m);
+  classify_weights(g);
   g->apsp_valid = false;
   g->sssp_arcs_valid = false;
   return drs_graph_upload_weights(g);
@@ -187,12 +202,7 @@ extern "C" int drs_graph_info(const drs_graph* g, int32_t* n, int32_t* m, int32_
 
 extern "C" int drs_apsp_build(drs_graph* g, int32_t mode) {
   DRS_REQUIRE(g, DRS_ERR_ARG, "drs_apsp_build: null graph");
-  DRS_REQUIRE(mode == DRS_MODE_F32 || mode == DRS_MODE_I32, DRS_ERR_ARG, "drs_apsp_build: unknown mode %d", mode);
-  if (mode == DRS_MODE_I32) {
-    for (int e = 0; e < g->m; ++e)
-      DRS_REQUIRE(g->h_tt[e] == std::floor(g->h_tt[e]) && g->h_tt[e] < 1e6, DRS_ERR_ARG,
-                  "drs_apsp_build: DRS_MODE_I32 needs integer travel times below 1e6 (edge %d = %g)", e, g->h_tt[e]);
-  }
+  { int rcm = drs_check_mode(g, mode, "drs_apsp_build"); if (rcm) return rcm; }
   DrsDeviceGuard guard(g->device);
   const int64_t ld = g->npad;
   if (!g->owns_matrices || g->ld != ld) {

@@ -40,6 +40,7 @@ struct drs_graph {
   // host copies of the edge list (edge id = position)
   std::vector<int32_t> h_src, h_dst;
   std::vector<double> h_tt, h_len;
+  bool weights_integral = false;   // every travel time is an integer below 1e6: what DRS_MODE_I32 requires
 
   // host copies of the arc -> edge id maps of both CSRs (weight refresh without a device round trip)
   std::vector<int32_t> h_out_eid, h_in_eid;
@@ -96,6 +97,8 @@ struct drs_graph {
 };
 
 int drs_graph_upload_weights(drs_graph* g);
+// DRS_MODE_F32 / DRS_MODE_I32 known, and I32 only on integer travel times below 1e6 (a float weight would be truncated)
+int drs_check_mode(const drs_graph* g, int mode, const char* who);
 
 // RAII device guard
 struct DrsDeviceGuard {

@@ -455,6 +455,7 @@ int update_impl(T* local, int64_t ld, int nrows, const T* panel, int kb, int ski
 extern "C" int drs_fw_init(const drs_graph* g, int32_t mode, void* local_dev, int64_t ld, int32_t row0,
                            int32_t nrows, void* stream) {
   DRS_REQUIRE(g && local_dev, DRS_ERR_ARG, "drs_fw_init: null argument");
+  { int rcm = drs_check_mode(g, mode, "drs_fw_init"); if (rcm) return rcm; }
   DRS_REQUIRE(ld == g->npad && row0 >= 0 && nrows >= 0 && row0 + nrows <= g->npad, DRS_ERR_ARG,
               "drs_fw_init: bad shard (ld=%lld row0=%d nrows=%d npad=%d)", (long long)ld, row0, nrows, g->npad);
   cudaStream_t st = (cudaStream_t)stream;

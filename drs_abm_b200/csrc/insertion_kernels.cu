@@ -340,7 +340,7 @@ __device__ __forceinline__ float reach_limit(const PlanView& pv, int rq) {
 
 // STAGED: the origin row of each request is copied into shared memory by the bulk-copy engine (one elected thread
 // issues cp.async.bulk in 32 KB pieces, all threads wait on the mbarrier); otherwise the same gathers go to L2.
-template <bool STAGED>
+template <bool STAGED, bool I32>
 __global__ void __launch_bounds__(1024, 1) insertion_reach_kernel(PlanView pv, DistView dv, int n_new, const int32_t* __restrict__ new_rows,
                                                                     uint32_t* __restrict__ mask, int words, int2* __restrict__ list,
                                                                     int list_cap, int* __restrict__ counters /* [0] list fill, [1] next request */) {
@@ -356,10 +356,9 @@ __global__ void __launch_bounds__(1024, 1) insertion_reach_kernel(PlanView pv, D
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   unsigned phase = 0;
+  if (tid == 0) s_req = atomicAdd(&counters[1], 1);
   while (true) {
-    __syncthreads();                                   // every lane is done with the previous row
-    if (tid == 0) s_req = atomicAdd(&counters[1], 1);
-    __syncthreads();
+    __syncthreads();                                   // every lane is done with the previous row (and sees s_req)
     const int r = s_req;
     if (r >= n_new) break;
     const int rq = new_rows[r];
@@ -381,23 +380,55 @@ __global__ void __launch_bounds__(1024, 1) insertion_reach_kernel(PlanView pv, D
                      : "=r"(landed) : "r"(smem_u32(&bar)), "r"(phase) : "memory");
       phase ^= 1;
     }
+    __syncthreads();                                   // everybody has read s_req
+    if (tid == 0) {
+      // claim the next request now and pull its row towards L2 while this one is being tested
+      const int nxt = atomicAdd(&counters[1], 1);
+      s_req = nxt;
+      if (STAGED && nxt < n_new) {
+        const char* src = reinterpret_cast<const char*>(dv.dist) + (size_t)pv.q_o[new_rows[nxt]] * row_bytes;
+        for (size_t off = 0; off < row_bytes; off += 32768) {
+          const uint32_t bytes = (uint32_t)min((size_t)32768, row_bytes - off);
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + off), "r"(bytes) : "memory");
+        }
+      }
+    }
     const float limit = reach_limit(pv, rq);
     uint32_t* mrow = mask + (size_t)r * words;
     for (int vs0 = tid - lane; vs0 < nv; vs0 += 1024) {
       const int vs = vs0 + lane;
       bool reach = false;
-      if (vs < nv) {
-        const int ns = pv.m_nslots[vs];
-        for (int a = 0; a < ns; ++a) {
-          const int x = a == 0 ? pv.node[vs] : pv.m_node[(a - 1) * nv + vs];
-          float w;
-          if (STAGED) {
-            w = dv.mode == DRS_MODE_F32 ? frow[x] : (irow[x] >= DRS_I32_INF ? __int_as_float(0x7f800000) : __int2float_rd(irow[x]));
-          } else {
-            const double wd = tt_into(dv, pv.directed, o, x);
-            w = __double2float_rd(wd);
+      {
+        const int ns = vs < nv ? pv.m_nslots[vs] : 0;
+        // the vehicle's bounds and vertices for ALL its positions first (independent loads in flight together: the
+        // kernel was bound by one L2 round trip per position), then the gathers and the compares.  Fully predicated on
+        // purpose: a warp-uniform branch per position (skip what lies beyond the warp's longest plan) measured 13 %
+        // SLOWER -- the branches keep the compiler from issuing the loads together.
+        constexpr int U = 9;                              // positions handled in registers (plans up to 8 stops); the rest in the loop below
+        float lb[U];
+        int xs[U];
+#pragma unroll
+        for (int a = 0; a < U; ++a) {
+          lb[a] = __int_as_float(0x7f800000);
+          xs[a] = 0;
+          if (a < ns) {
+            lb[a] = pv.m_lb[a * nv + vs];
+            xs[a] = a == 0 ? pv.node[vs] : pv.m_node[(a - 1) * nv + vs];
           }
-          if (pv.m_lb[a * nv + vs] + w <= limit) { reach = true; break; }
+        }
+#pragma unroll
+        for (int a = 0; a < U; ++a) {
+          float w;
+          if (STAGED) w = I32 ? (irow[xs[a]] >= DRS_I32_INF ? __int_as_float(0x7f800000) : __int2float_rd(irow[xs[a]])) : frow[xs[a]];
+          else w = a < ns ? __double2float_rd(tt_into(dv, pv.directed, o, xs[a])) : 0.f;
+          reach = reach || (lb[a] + w <= limit);          // lb = +inf past the usable positions
+        }
+        for (int a = U; a < ns && !reach; ++a) {
+          const int x = pv.m_node[(a - 1) * nv + vs];
+          float w;
+          if (STAGED) w = I32 ? (irow[x] >= DRS_I32_INF ? __int_as_float(0x7f800000) : __int2float_rd(irow[x])) : frow[x];
+          else w = __double2float_rd(tt_into(dv, pv.directed, o, x));
+          reach = pv.m_lb[a * nv + vs] + w <= limit;
         }
       }
       const unsigned m = __ballot_sync(0xffffffffu, reach);
@@ -497,6 +528,8 @@ __device__ double pair_cmin(const PlanView& pv, const DistView& dv, int rq, int 
   return cmin;
 }
 
+// One thread per surviving pair.  (Eight lanes per pair, one pickup position each through pair_cmin_at and a shuffle
+// minimum, measured 18 % slower on the C4 tick: every lane rebuilds the prefix state and repeats the shared gathers.)
 __global__ void __launch_bounds__(128) insertion_eval_kernel(PlanView pv, DistView dv, const int32_t* __restrict__ new_rows,
                                                              const int2* __restrict__ list, const int* __restrict__ counters, int list_cap,
                                                              double* __restrict__ cmin_out) {
@@ -514,7 +547,7 @@ __global__ void __launch_bounds__(128) insertion_eval_kernel(PlanView pv, DistVi
 struct FoldEvent { int v; int pad; double dc; };   // after the exact re-scan of vehicle v the incumbent cost increase is dc
 constexpr int FOLD_EVENT_CAP = 8192;
 
-__global__ void insertion_fold_kernel(PlanView pv, DistView dv, int r_first, int r_count, const int32_t* new_rows, const uint32_t* mask,
+__global__ void insertion_fold_dense_kernel(PlanView pv, DistView dv, int r_first, int r_count, const int32_t* new_rows, const uint32_t* mask,
                                       int words, const double* cmin, int32_t* best_veh, int32_t* best_i, int32_t* best_j, double* best_dc,
                                       FoldEvent* events /* may be null; single-request folds only */, int* n_events) {
   const int rr = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -573,6 +606,68 @@ __global__ void insertion_fold_kernel(PlanView pv, DistView dv, int r_first, int
     }
   }
   if (lane == 0) { best_veh[r] = wv; best_i[r] = wi; best_j[r] = wj; best_dc[r] = dc; if (events) *n_events = n_ev; }
+}
+
+// Fold of the frozen-plan evaluation: one CTA per request.  The request's mask (n_veh bits) is scanned by all threads,
+// the vehicles in reach (~1 %) go to a shared-memory list with their smallest cost, the list is ordered by the caller's
+// vehicle index (rank by counting), and warp 0 walks it the way the reference walks the fleet: a vehicle is re-scanned
+// (scan_vehicle_warp: candidates in parallel, decisions replayed in order) only if its smallest cost can meet the
+// incumbent bound.  A request with more vehicles in reach than the list holds is flagged for the dense kernel.
+constexpr int FOLD_THREADS = 128;
+constexpr int FOLD_MAXC = 1024;
+
+__global__ void __launch_bounds__(FOLD_THREADS) insertion_fold_kernel(PlanView pv, DistView dv, int n_new, const int32_t* __restrict__ new_rows,
+                                                                       const uint32_t* __restrict__ mask, int words, const double* __restrict__ cmin,
+                                                                       int32_t* best_veh, int32_t* best_i, int32_t* best_j, double* best_dc,
+                                                                       int* n_overflow) {
+  __shared__ int s_vs[FOLD_MAXC], s_v[FOLD_MAXC], s_order[FOLD_MAXC];
+  __shared__ double s_cm[FOLD_MAXC];
+  __shared__ int s_count;
+  const int r = blockIdx.x, tid = threadIdx.x, nv = pv.n_veh;
+  if (r >= n_new) return;
+  const double inf = d_inf();
+  if (tid == 0) s_count = 0;
+  __syncthreads();
+  const uint32_t* mrow = mask + (size_t)r * words;
+  for (int w = tid; w < words; w += FOLD_THREADS) {
+    uint32_t m = mrow[w];
+    while (m) {
+      const int b = __ffs(m) - 1;
+      m &= m - 1;
+      const int vs = w * 32 + b;
+      const double cm = cmin[(int64_t)r * nv + vs];
+      if (cm == inf) continue;                           // in reach, but no candidate succeeds
+      const int pos = atomicAdd(&s_count, 1);
+      if (pos < FOLD_MAXC) { s_vs[pos] = vs; s_v[pos] = pv.perm[vs]; s_cm[pos] = cm; }
+    }
+  }
+  __syncthreads();
+  const int cnt = s_count;
+  if (cnt > FOLD_MAXC) {
+    if (tid == 0) { best_veh[r] = -2; atomicAdd(n_overflow, 1); }
+    return;
+  }
+  for (int k = tid; k < cnt; k += FOLD_THREADS) {
+    const int mine = s_v[k];
+    int rank = 0;
+    for (int m = 0; m < cnt; ++m) rank += s_v[m] < mine;
+    s_order[rank] = k;
+  }
+  __syncthreads();
+  if (tid >= 32) return;
+  double dc = inf;                   // dc_ = np.inf (:1452)
+  int wv = -1, wi = -1, wj = -1;
+  const int rq = new_rows[r];
+  for (int k = 0; k < cnt; ++k) {
+    const int at = s_order[k];
+    const int vs = s_vs[at];
+    const double c0 = pv.cost[vs];
+    if (s_cm[at] > c0 + dc) continue;
+    Pair p;
+    load_pair(p, pv, dv, vs, rq);
+    if (scan_vehicle_warp(p, pv, dc, wi, wj)) wv = s_v[at];
+  }
+  if (tid == 0) { best_veh[r] = wv; best_i[r] = wi; best_j[r] = wj; best_dc[r] = dc; }
 }
 
 // Side effects of one request's scan on Req.Cld (lib/Agents.py:1550,1554), exactly: every vehicle whose pickup position 0
@@ -954,11 +1049,14 @@ int scan_all(drs_tick* t, LegacyDev& d, int n_new, cudaStream_t st) {
     DRS_CUDA(cudaMemsetAsync(d.d_counters, 0, sizeof(int) * 8, st));
     tm_reach.start();
     const int grid = std::max(1, std::min(n_new, sms));
-    if (staged) {
-      DRS_CUDA(cudaFuncSetAttribute(insertion_reach_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_bytes));
-      insertion_reach_kernel<true><<<grid, 1024, row_bytes, st>>>(d.pv, dv, n_new, d.d_rows, d.d_mask, d.words, d.d_list, d.list_cap, d.d_counters);
+    if (staged && g->mode == DRS_MODE_I32) {
+      DRS_CUDA(cudaFuncSetAttribute(insertion_reach_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_bytes));
+      insertion_reach_kernel<true, true><<<grid, 1024, row_bytes, st>>>(d.pv, dv, n_new, d.d_rows, d.d_mask, d.words, d.d_list, d.list_cap, d.d_counters);
+    } else if (staged) {
+      DRS_CUDA(cudaFuncSetAttribute(insertion_reach_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_bytes));
+      insertion_reach_kernel<true, false><<<grid, 1024, row_bytes, st>>>(d.pv, dv, n_new, d.d_rows, d.d_mask, d.words, d.d_list, d.list_cap, d.d_counters);
     } else {
-      insertion_reach_kernel<false><<<grid, 1024, 0, st>>>(d.pv, dv, n_new, d.d_rows, d.d_mask, d.words, d.d_list, d.list_cap, d.d_counters);
+      insertion_reach_kernel<false, false><<<grid, 1024, 0, st>>>(d.pv, dv, n_new, d.d_rows, d.d_mask, d.words, d.d_list, d.list_cap, d.d_counters);
     }
     drs_count_launch();
     tm_reach.stop();
@@ -1148,12 +1246,25 @@ extern "C" int drs_tick_insertion_eval(drs_tick* t, int32_t n_new, const int32_t
   if (d.n_veh > 0 && (rc = scan_all(t, d, n_new, st))) return rc;
   tm_scan.stop();
   tm_fold.start();
-  insertion_fold_kernel<<<(n_new * 32 + 127) / 128, 128, 0, st>>>(d.pv, dv, 0, n_new, d.d_rows, d.d_mask, d.words, d.d_cmin, d.d_bv, d.d_bi,
-                                                                    d.d_bj, d.d_dc, nullptr, nullptr);
+  int* d_novf = d.d_counters + 5;
+  DRS_CUDA(cudaMemsetAsync(d_novf, 0, sizeof(int), st));
+  insertion_fold_kernel<<<n_new, FOLD_THREADS, 0, st>>>(d.pv, dv, n_new, d.d_rows, d.d_mask, d.words, d.d_cmin, d.d_bv, d.d_bi, d.d_bj, d.d_dc, d_novf);
   drs_count_launch();
   tm_fold.stop();
   DRS_CUDA(cudaGetLastError());
   if ((rc = fetch_results(d, n_new, best_veh, best_i, best_j, best_dc, st))) return rc;
+  int novf = 0;
+  DRS_CUDA(cudaMemcpy(&novf, d_novf, sizeof(int), cudaMemcpyDeviceToHost));
+  if (novf > 0) {   // requests with more than FOLD_MAXC vehicles in reach: the dense walk over the whole fleet
+    for (int r = 0; r < n_new; ++r)
+      if (best_veh[r] == -2) {
+        insertion_fold_dense_kernel<<<1, 32, 0, st>>>(d.pv, dv, r, 1, d.d_rows, d.d_mask, d.words, d.d_cmin, d.d_bv, d.d_bi, d.d_bj, d.d_dc,
+                                                      nullptr, nullptr);
+        drs_count_launch();
+      }
+    DRS_CUDA(cudaGetLastError());
+    if ((rc = fetch_results(d, n_new, best_veh, best_i, best_j, best_dc, st))) return rc;
+  }
   t->last_ms[2] = tm_scan.ms(); t->last_ms[3] = tm_fold.ms();
   d.detail_ms[3] = t->last_ms[3]; d.detail_ms[4] = 0;
   if (n_candidates) *n_candidates = d.base_candidates * n_new;
@@ -1215,8 +1326,8 @@ extern "C" int drs_tick_insertion_queue(drs_tick* t, int32_t n_new, const int32_
     DRS_CUDA(cudaMemcpyAsync(d_last_v, &minus_one, sizeof(int), cudaMemcpyHostToDevice, st));
   }
   for (int r = 0; r < n_new && !fused; ++r) {
-    insertion_fold_kernel<<<1, 32, 0, st>>>(d.pv, dv, r, 1, d.d_rows, d.d_mask, d.words, d.d_cmin, d.d_bv, d.d_bi, d.d_bj, d.d_dc,
-                                            track_cld ? d.d_events : nullptr, d_nev);
+    insertion_fold_dense_kernel<<<1, 32, 0, st>>>(d.pv, dv, r, 1, d.d_rows, d.d_mask, d.words, d.d_cmin, d.d_bv, d.d_bi, d.d_bj, d.d_dc,
+                                                  track_cld ? d.d_events : nullptr, d_nev);
     if (track_cld)
       insertion_sidefx_kernel<<<(d.n_veh + 127) / 128, 128, 0, st>>>(d.pv, dv, d.d_rows, r, d.d_mask, d.words, d.d_events, d_nev, d.d_fx_new,
                                                                       d_last_v, d_err);

@@ -567,7 +567,7 @@ extern "C" int drs_sssp_batch_dev(const drs_graph* g, int32_t mode, int32_t nsrc
   DRS_REQUIRE(g && dist_dev && (nsrc == 0 || sources_host), DRS_ERR_ARG, "drs_sssp_batch_dev: null argument");
   DRS_REQUIRE(ld >= g->n && nsrc >= 0, DRS_ERR_ARG, "drs_sssp_batch_dev: ld (%lld) must be >= n (%d)", (long long)ld, g->n);
   DRS_REQUIRE(g->n <= VERTEX_MASK, DRS_ERR_ARG, "drs_sssp_batch_dev: at most %d vertices (queue entries pack the source slot above bit 24)", VERTEX_MASK);
-  DRS_REQUIRE(mode == DRS_MODE_F32 || mode == DRS_MODE_I32, DRS_ERR_ARG, "drs_sssp_batch_dev: unknown mode %d", mode);
+  { int rcm = drs_check_mode(g, mode, "drs_sssp_batch_dev"); if (rcm) return rcm; }
   for (int k = 0; k < nsrc; ++k)
     DRS_REQUIRE(sources_host[k] >= 0 && sources_host[k] < g->n, DRS_ERR_RANGE, "drs_sssp_batch_dev: source %d out of range", sources_host[k]);
   if (nsrc == 0) return DRS_OK;

@@ -340,6 +340,7 @@ class RoadGraph(object):
             self._eattrs[key][index] = value
         if key == self._weight_attr:
             self._weights_dirty = True
+        self._exact_key = None
 
     _weights_dirty = False
 
@@ -456,6 +457,35 @@ class RoadGraph(object):
         _lib.check(lib.drs_query_pairs(self._handle, n, _lib.ptr_i32(s), _lib.ptr_i32(t), _lib.ptr_f64(tt),
                                        _lib.ptr_f64(ln), _lib.ptr_i32(hops)), lib)
         return tt, ln, hops
+
+    def sums_equal_matrix(self, weights=None):
+        """True when the fp64 left-to-right sum along ANY shortest path equals the fp32 / int32 matrix entry bit for bit:
+        every weight an integer and (n - 1) * max weight below 2^24 (sums of integers are exact in both)."""
+        attr = weights if weights is not None else (self._weight_attr or "ttmedian")
+        key = (attr, id(self._eattrs.get(attr)))
+        if self._exact_key != key or self._weights_dirty:
+            w = np.asarray(self._eattrs[attr], dtype=np.float64)
+            self._exact = bool(w.size == 0 or (np.all(w == np.floor(w)) and float(w.max()) * max(self.n - 1, 1) < 2.0 ** 24))
+            self._exact_key = key
+        return self._exact
+
+    _exact_key, _exact = None, False
+
+    def pair_time(self, s, t, weights=None):
+        """dist[s, t] as a Python float (inf = unreachable): one gather kernel on mapped host memory."""
+        lib = self._ensure(weights)
+        if not (0 <= s < self.n and 0 <= t < self.n):
+            raise ValueError("vertex index out of range (n=%d)" % self.n)
+        if self._new_of_old is not None:
+            s, t = int(self._new_of_old[s]), int(self._new_of_old[t])
+        io = self._scalar_io
+        if io is None:
+            io = self._scalar_io = (C.c_int32(), C.c_int32(), C.c_double())
+        io[0].value, io[1].value = s, t
+        _lib.check(lib.drs_query_matrix(self._handle, 1, C.byref(io[0]), C.byref(io[1]), C.byref(io[2])), lib)
+        return io[2].value
+
+    _scalar_io = None
 
     def pair_sums(self, s, t, weights=None):
         """Scalar form of path_sums for one (s, t): (duration, length, hops).  One kernel launch whose answer lands in
@@ -639,7 +669,16 @@ class RoutingEngine(object):
 
     def get_duration(self, olng, olat, dlng, dlat):
         """lib/RoutingEngine.py:209-218: left-to-right fp64 sum of the path's weights (int 0 for an empty path;
-        igraph returns an empty path for an unreachable target)."""
+        igraph returns an empty path for an unreachable target).  Where every weight is an integer (and n * max weight
+        < 2^24) that sum is exact and equals the matrix entry, so the path need not be walked: one gather."""
+        G = self.G
+        if G.sums_equal_matrix(self.ttweight):
+            o = G.node_index(str((olng, olat)))
+            d = G.node_index(str((dlng, dlat)))
+            if o == d:
+                return 0
+            tt = G.pair_time(o, d, self.ttweight)
+            return tt if tt != float("inf") else 0
         tt, _, hops = self._sums(olng, olat, dlng, dlat)
         return tt if hops > 0 else 0
 

@@ -72,12 +72,13 @@ int drs_graph_info(const drs_graph* g, int32_t* n, int32_t* m, int32_t* npad, in
                    int32_t* apsp_valid, int32_t* device);
 
 /* ------------------------------------------------------------------- APSP --
- * Builds the all-pairs travel-time matrix with the blocked min-plus
- * Floyd-Warshall and then the canonical predecessor-edge matrix.  Replaces
- * every per-query Dijkstra the reference issues
+ * Builds the all-pairs travel-time matrix with the algorithm selected by drs_apsp_set_algorithm (default AUTO: N batched
+ * delta-stepping searches when arcs/vertex <= 16, the blocked min-plus Floyd-Warshall otherwise), and -- only in
+ * DRS_PRED_MATRIX mode -- the canonical predecessor-edge matrix; by default predecessors are evaluated lazily by the
+ * path queries.  Replaces every per-query Dijkstra the reference issues
  * (lib/RoutingEngine.py:87,199,212; lib/optimUtils.py:528,531,659).
- * Single GPU; the multi-GPU build drives the drs_fw_* entry points below from
- * one process per GPU.  Blocks until the matrices are complete.
+ * Single GPU; the multi-GPU build drives the drs_apsp_rows_sssp / drs_fw_* entry points below from
+ * one process per GPU.  Blocks until the matrix is complete.
  */
 int drs_apsp_build(drs_graph* g, int32_t mode);
 
@@ -118,8 +119,9 @@ int drs_apsp_set_pred_mode(drs_graph* g, int32_t pred_mode);
  * Distances from nsrc sources (delta-stepping, one CTA per source).  Replaces the same
  * igraph Dijkstra calls when the N x N matrix does not fit in HBM (BASELINE config C5).
  * _dev: row k of dist_dev (float or int32 per mode, leading dimension ld >= n) receives
- * the distances from sources_host[k]; delta <= 0 selects the default bucket width (twice
- * the mean arc weight).  The host variant returns nsrc x n doubles (inf = unreachable). */
+ * the distances from sources_host[k]; delta <= 0 selects the default bucket width (six
+ * times the mean arc weight, the measured sweet spot on grid cities; DRS_SSSP_DELTA_MULT overrides).
+ * mode DRS_MODE_I32 requires integer travel times below 1e6 (checked by every entry point that takes a mode).  The host variant returns nsrc x n doubles (inf = unreachable). */
 int drs_sssp_batch_dev(const drs_graph* g, int32_t mode, int32_t nsrc, const int32_t* sources_host,
                        void* dist_dev, int64_t ld, double delta, void* stream);
 int drs_sssp_batch(const drs_graph* g, int32_t mode, int32_t nsrc, const int32_t* sources_host,

@@ -387,3 +387,32 @@ def test_single_scans_leave_the_references_cld(tag):
     assert changed > 0
     tick.close()
     G.close()
+
+
+def test_steady_state_ticks_allocate_nothing():
+    """A tick handle reloaded with a fleet of the same size (set_plans) and evaluated again -- frozen plans and the
+    sequential queue -- makes no device allocation after the first round (drs_alloc_count)."""
+    from drs_abm_b200 import _lib, synth
+    from drs_abm_b200.dispatch import InsertionTick
+    from drs_abm_b200.gml import read_gml
+    from drs_abm_b200.routing import RoadGraph
+    data = read_gml(golden_map_path("g20_int"))
+    G = RoadGraph(data)
+    dist = G.dist_rows(0, G.n)
+    lib = _lib.load()
+    tick = None
+    first = None
+    for rnd in range(4):
+        sc = synth.fleet_scenario(data, 50, 30, 600.0, 20 + rnd, lambda s, t: dist[s, t], plan_stops=(0, 2, 4), radius=5)
+        if tick is None:
+            tick = InsertionTick(G, sc["vehs"], sc["table"])
+        else:
+            tick.set_plans(sc["vehs"], sc["table"])
+        tick.evaluate(sc["new_rows"])
+        tick.queue(sc["new_rows"], 600.0)
+        tick.fetch_plans()
+        if rnd == 0:
+            first = lib.drs_alloc_count()
+    assert lib.drs_alloc_count() == first, "a steady-state tick allocated device memory"
+    tick.close()
+    G.close()

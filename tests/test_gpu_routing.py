@@ -373,3 +373,55 @@ def test_device_numbering_does_not_change_any_answer():
             assert np.array_equal(got[4], ref[4]) and np.array_equal(got[5], ref[5])
         G.close()
     assert np.array_equal(ref[1], ref[0][37:40]) and np.array_equal(ref[4], ref[0][[0, 123, 399]])
+
+
+def test_steady_state_queries_allocate_nothing_and_scalar_equals_batch():
+    """RoutingEngine is asked one pair at a time (lib/Agents.py:898-923, 756, 1073): after the first call of each kind the
+    library must not allocate device or pinned memory again (drs_alloc_count), a scalar query is one kernel launch
+    (drs_launch_count), and the scalar answers equal the batched ones bit for bit."""
+    from drs_abm_b200 import _lib
+    from drs_abm_b200.routing import RoutingEngine
+    router = RoutingEngine(graph_loc=golden_map_path("g20_int"), cst_speed=9, seed=3)
+    G = router.G
+    lib = _lib.load()
+    rs = np.random.RandomState(5)
+    o, d = rs.randint(0, G.n, 64), rs.randint(0, G.n, 64)
+    tt, ln, hops = G.path_sums(o, d)
+    loc = lambda i: (G.vs[int(i)]["lng"], G.vs[int(i)]["lat"])
+    # warm every path once
+    router.get_duration(*loc(o[0]), *loc(d[0])); router.get_routing(*loc(o[0]), *loc(d[0])); G.shortest_paths(int(o[0]), int(d[0]), weights="ttmedian")
+    a0, l0 = lib.drs_alloc_count(), lib.drs_launch_count()
+    for k in range(64):
+        want_t, want_l = (float(tt[k]), float(ln[k])) if hops[k] > 0 else (0, 0)
+        assert router.get_duration(*loc(o[k]), *loc(d[k])) == want_t
+        assert router.get_distance(*loc(o[k]), *loc(d[k])) == want_l
+        assert router.get_distance_duration(*loc(o[k]), *loc(d[k])) == (want_l, want_t)
+    assert lib.drs_launch_count() - l0 == 3 * 64          # one kernel per scalar call
+    for k in range(16):
+        r = router.get_routing(*loc(o[k]), *loc(d[k]))
+        assert r["duration"] == (float(tt[k]) if hops[k] > 0 else 0)
+        assert G.shortest_paths(int(o[k]), int(d[k]), weights="ttmedian")[0][0] == G.matrix_lookup([o[k]], [d[k]])[0]
+    assert lib.drs_alloc_count() == a0, "a steady-state query allocated memory"
+    G.close()
+
+
+def test_i32_mode_is_refused_on_float_weights_by_every_entry_point():
+    """DRS_MODE_I32 would truncate non-integer travel times: every entry point that takes a mode refuses it."""
+    import ctypes as C
+    import torch
+    from drs_abm_b200 import _lib
+    from drs_abm_b200.gml import read_gml
+    from drs_abm_b200.routing import RoadGraph
+    G = RoadGraph(read_gml(golden_map_path("g12_float")), mode=_lib.MODE_I32)
+    with pytest.raises(ValueError):
+        G.build()
+    h = G.upload()
+    lib = _lib.load()
+    npad = (G.n + 127) // 128 * 128
+    buf = torch.empty((npad, npad), dtype=torch.int32, device="cuda")
+    src = _lib.as_i32([0, 1])
+    for rc in (lib.drs_sssp_batch_dev(h, _lib.MODE_I32, 2, _lib.ptr_i32(src), C.c_void_p(buf.data_ptr()), npad, 0.0, None),
+               lib.drs_apsp_rows_sssp(h, _lib.MODE_I32, C.c_void_p(buf.data_ptr()), npad, 0, npad, 0.0, None),
+               lib.drs_fw_init(h, _lib.MODE_I32, C.c_void_p(buf.data_ptr()), npad, 0, npad, None)):
+        assert rc == _lib.ERR_ARG and b"integer travel times" in lib.drs_last_error()
+    G.close()
