@@ -40,6 +40,7 @@ constexpr int MAXR = DRS_MAX_TRIP_REQS;
 struct Trip {
   double lb[MAXS], ub[MAXS];
   double t_start;         // T + veh["t"]  (or T without a vehicle)
+  double snap;            // TickDev::snap
   double cap;             // capacity (1e6 when unconstrained, lib/optimUtils.py:432)
   int tt[(MAXS + 1) * (MAXS + 1)];   // raw matrix entries (float bits or int32) among the trip's vertices
   int node[MAXS + 1];
@@ -117,6 +118,11 @@ __device__ __forceinline__ void dfs_begin(Dfs& s, DfsStack& k, const Trip* tr, u
   k.psum[0] = 0.0; k.cost[0] = 0.0;
 }
 
+// lb <= arr <= ub, an arrival within the relative slack `snap` of a bound counting as on it (snap = 0: the exact test)
+__device__ __forceinline__ bool in_window(double arr, double lb, double ub, double snap) {
+  return arr >= lb - snap * fmax(1.0, fabs(lb)) && arr <= ub + snap * fmax(1.0, fabs(ub));
+}
+
 __device__ __forceinline__ void dfs_step(Dfs& s, DfsStack& k, int mode) {
   const Trip& tr = *s.tr;
   if ((++s.visited & (kChargeEvery - 1)) == 0 && atomicAdd(s.steps, kChargeEvery) > kSearchBudget) {
@@ -150,9 +156,13 @@ __device__ __forceinline__ void dfs_step(Dfs& s, DfsStack& k, int mode) {
     const int cur = d == 0 ? 0 : ord_at(s.ord, d - 1) + 1;
     np = k.psum[d] + decode_tt(tr.tt[cur * (MAXS + 1) + i + 1], mode);
     const double arr = tr.t_start + np;
-    if (!(arr >= tr.lb[i] && arr <= tr.ub[i])) return;
+    if (!in_window(arr, tr.lb[i], tr.ub[i], tr.snap)) return;
     nc = k.cost[d];
-    if (tr.pod[i] < 0) nc += arr - tr.lb[i];
+    if (tr.pod[i] < 0) {
+      double late = arr - tr.lb[i];
+      if (tr.snap > 0.0 && fabs(late) <= tr.snap * fmax(1.0, fabs(tr.lb[i]))) late = 0.0;   // on the bound: the reference's delay is exactly 0
+      nc += late;
+    }
     if (!(nc < s.best)) return;   // cost is non-decreasing along an ordering: exact pruning
     if (s.shared_best && nc > __longlong_as_double((long long)*((volatile unsigned long long*)s.shared_best))) return;
   }
@@ -194,12 +204,14 @@ __device__ void fill_trip(Trip& tr, const TickDev& tk, double T, int v, int nreq
       tr.has_start = 1;
       tr.node[0] = tk.v_node[v];
       tr.t_start = T + tk.v_delay[v];           // lib/optimUtils.py:117
+      tr.snap = tk.snap;
       tr.cap = (double)tk.v_cap[v];
       tr.pax0 = tk.v_pax[v];
     } else {
       tr.has_start = 0;
       tr.node[0] = tk.r_o[reqs[0]];             // the first stop is the start (lib/optimUtils.py:160)
       tr.t_start = T;
+      tr.snap = tk.snap;
       tr.cap = 1e6;
       tr.pax0 = 0;
     }
@@ -466,7 +478,7 @@ __global__ void rv_filter_kernel(TickDev tk, DistView dv, double T, int8_t* stat
     const int vn = tk.v_node[v], o = tk.r_o[r];
     const double tvo = (vn == o) ? 0.0 : (tk.directed ? dv.at(vn, o) : dv.at(o, vn));
     int st;
-    if (T + tvo > tk.r_ubp[r]) {               // lib/Optimization.py:183-186
+    if (T + tvo > tk.r_ubp[r] + tk.snap * fmax(1.0, fabs(tk.r_ubp[r]))) {   // lib/Optimization.py:183-186
       st = DRS_RV_SKIPPED;
     } else {
       st = -1;
@@ -475,11 +487,11 @@ __global__ void rv_filter_kernel(TickDev tk, DistView dv, double T, int8_t* stat
         bool ok = 1 <= tk.v_cap[v];
         const double p1 = 0.0 + tvo;
         const double a1 = t0 + p1;
-        ok = ok && a1 >= tk.r_lbp[r] && a1 <= tk.r_ubp[r];
+        ok = ok && in_window(a1, tk.r_lbp[r], tk.r_ubp[r], tk.snap);
         const int dn = tk.r_d[r];
         const double p2 = p1 + ((o == dn) ? 0.0 : dv.at(o, dn));
         const double a2 = t0 + p2;
-        ok = ok && a2 >= tk.r_lbd[r] && a2 <= tk.r_ubd[r];
+        ok = ok && in_window(a2, tk.r_lbd[r], tk.r_ubd[r], tk.snap);
         ok = ok && ((a2 - tk.r_lbd[r]) < DRS_INF_ROUTE_COST);
         if (!ok) st = DRS_RV_SAVED;
       }
@@ -612,6 +624,7 @@ extern "C" int drs_tick_set_vehicles(drs_tick* t, const drs_vehicle_batch* b) {
     return lx != ly ? lx > ly : b->start_node[x] < b->start_node[y];
   });
   d.directed = t->g->directed;
+  d.snap = t->g->weights_integral ? 0.0 : 1e-5;   // float-weighted map: fp32 matrix entries vs the fp64 sums the windows were built from
   // one host image, one copy (a steady-state tick allocates nothing)
   DrsArenaLayout lay;
   const size_t nvp = std::max(nv, 1), nsp = std::max(nstops, 1);

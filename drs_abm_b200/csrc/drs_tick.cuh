@@ -47,6 +47,11 @@ struct TickDev {
   double *s_lb = nullptr, *s_ub = nullptr;
   int32_t* v_perm = nullptr;   // vehicles sorted by number of planned stops (uniform work per warp)
   int directed = 0;
+  // Window comparisons on a float-weighted map: the reference builds a request's windows from the same fp64 path sums it
+  // later compares arrivals with (Ced = Cep + Ts, lib/Agents.py:768), so a direct trip arrives EXACTLY at Ced; an fp32
+  // matrix entry differs from that sum by rounding, which would flip such a boundary case.  `snap` (relative, 0 on
+  // exact-integer maps) is the slack within which an arrival counts as being on the bound.
+  double snap = 0.0;
   // requests
   int n_req = 0;
   int32_t *r_rid = nullptr, *r_o = nullptr, *r_d = nullptr;

@@ -40,6 +40,7 @@ def grid_city(n_side, seed, keep=1.0, weights="int"):
     weights: "int"   ttmedian = randint(20, 61) s, length = 10 * ttmedian m
              "float" length = 100 * lognormal(0, 0.25) m, ttmedian = length / 9.0 s
              "uniform" every ttmedian = 30 s, length = 300 m (tie-stress case)
+             "dfloat" like "float" but DIRECTED: two one-way arcs per street with independent lengths
     """
     rs = np.random.RandomState(seed)
     idx = np.arange(n_side * n_side, dtype=np.int64).reshape(n_side, n_side)  # k = i*n_side + j
@@ -79,6 +80,13 @@ def grid_city(n_side, seed, keep=1.0, weights="int"):
     elif weights == "uniform":
         tt = np.full(m, 30.0)
         length = np.full(m, 300.0)
+    elif weights == "dfloat":
+        # DIRECTED float map: every street is two one-way arcs with independent lengths (a -> b, then b -> a)
+        allE = np.concatenate([allE, allE[:, ::-1]], 0)
+        allE = allE[np.argsort(allE[:, 0], kind="stable")]   # arcs grouped by their tail vertex, like the other maps' edges
+        m = allE.shape[0]
+        length = 100.0 * rs.lognormal(0.0, 0.25, size=m)
+        tt = length / 9.0
     else:
         raise ValueError("unknown weights %r" % (weights,))
     ii, jj = old_ids // n_side, old_ids % n_side
@@ -91,7 +99,7 @@ def grid_city(n_side, seed, keep=1.0, weights="int"):
     slnmean = np.log(0.5 * tt)
     slnsd = np.full(m, 0.2)
     eattrs = {"length": length, "ttmedian": tt, "slnshift": slnshift, "slnmean": slnmean, "slnsd": slnsd}
-    return RoadGraphData(n, False, allE[:, 0], allE[:, 1], vattrs, eattrs)
+    return RoadGraphData(n, weights == "dfloat", allE[:, 0], allE[:, 1], vattrs, eattrs)
 
 
 def config_graph(name):

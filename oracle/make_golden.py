@@ -44,6 +44,7 @@ MAPS = {
     "g12_float": (12, 0.9, 12, "float"),
     "g20_int": (20, 1.0, 20, "int"),         # BASELINE config C1
     "g20_uniform": (20, 1.0, 20, "uniform"),  # tie stress
+    "g10_dfloat": (10, 1.0, 10, "dfloat"),    # directed, float-weighted
 }
 
 
@@ -189,7 +190,7 @@ def cost_golden(name, ncases, seed):
     return cases
 
 
-def sim_golden(name, n_veh, n_ticks, req_per_tick, capacity, seed):
+def sim_golden(name, n_veh, n_ticks, req_per_tick, capacity, seed, boundary=False, suffix=""):
     """A few assignment ticks driven through the reference's own Veh / Req / AlonsoMora
     ("enumerate") classes: the corrected-unpack version of Fleet.dispatch_at_time /
     Fleet.optimal_assignment (lib/Agents.py:964-1096; unpack convention of
@@ -219,11 +220,18 @@ def sim_golden(name, n_veh, n_ticks, req_per_tick, capacity, seed):
                     reqs[rid].Td = t
             if len(veh.route) == 0:
                 veh.build_route(router, [])
-        for _ in range(req_per_tick):                       # new requests of this tick
+        for k in range(req_per_tick):                       # new requests of this tick
             o, d = int(rs.randint(n)), int(rs.randint(n))
+            Tr = T - float(rs.randint(0, RC.INT_ASSIGN))
+            if boundary and k == 0:
+                # the exact-Ced boundary: a request made NOW at the vertex an idle vehicle stands on, so that the direct
+                # trip arrives at Cep + Ts == Ced to the last bit in the reference (same fp64 sums on both sides)
+                idle = [v for v in vehs if len(v.route) == 0 and (v.lng, v.lat) in node_of]
+                if idle:
+                    o = node_of[(idle[tick % len(idle)].lng, idle[tick % len(idle)].lat)]
+                    Tr = float(T)
             while d == o:
                 d = int(rs.randint(n))
-            Tr = T - float(rs.randint(0, RC.INT_ASSIGN))
             reqs.append(Req(router, len(reqs), Tr, G.vs[o]["lng"], G.vs[o]["lat"], G.vs[d]["lng"], G.vs[d]["lat"]))
         # snapshot of what the optimizer sees
         snap_v = []
@@ -268,7 +276,7 @@ def sim_golden(name, n_veh, n_ticks, req_per_tick, capacity, seed):
                     vehs[vid].build_route(router, route, reqs, T)
                 for rid in rejected:
                     reqs[rid].assigned = True
-    with open(os.path.join(GOLD, "sim_%s_K%d.json" % (name, capacity)), "w") as fh:
+    with open(os.path.join(GOLD, "sim_%s_K%d%s.json" % (name, capacity, suffix)), "w") as fh:
         json.dump({"map": name, "capacity": capacity, "ticks": ticks}, fh)
     return ticks
 
@@ -420,4 +428,7 @@ if __name__ == "__main__":
                                ("g12_float", 5, 4, 4, 2)]:
         t = sim_golden(nm, nv, nt, rpt, K, seed=9)
         print("sim", nm, K, [len(x["rv_edges"]) for x in t], [len(x["veh_routes"]) for x in t])
+    for nm, nv, nt, rpt, K in [("g12_float", 6, 5, 3, 2), ("g10_dfloat", 5, 5, 3, 2)]:
+        t = sim_golden(nm, nv, nt, rpt, K, seed=13, boundary=True, suffix="b")
+        print("sim (boundary)", nm, K, [len(x["rv_edges"]) for x in t], [len(x["veh_routes"]) for x in t])
     legacy_all()

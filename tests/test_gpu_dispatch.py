@@ -67,7 +67,9 @@ def test_trip_costing_matches_reference_golden(name):
         veh["pax_reqs"] = [[r for r in veh["pax_reqs"] if r["rid"] == k][0] for k in pax_rids]
         veh["wait_reqs"] = [[r for r in veh["wait_reqs"] if r["rid"] == k][0] for k in wait_rids]
         ocost, oroute, oorder = D.find_optimal_routing([D.request_vertex(new, T)], tt, veh, T)
-        assert cost == ocost
+        # (float map: an arrival within 1e-5 of a window bound counts as on it in the kernel -- TickDev::snap -- so a
+        #  delay term can be snapped to 0; exact equality holds on the integer maps)
+        assert cost == pytest.approx(ocost, **tol)
         assert (order is None) == (oorder is None)
         if order is not None:
             assert order == list(oorder)
@@ -76,7 +78,7 @@ def test_trip_costing_matches_reference_golden(name):
             if case["route_unique"] and "float" not in name:
                 assert [[r[0], r[1]] for r in route] == case["route"]
         orr, _, orr_order = D.find_optimal_routing((D.request_vertex(new, T), D.request_vertex(other, T)), tt, None, T)
-        assert rr_cost == orr and (rr_order is None) == (orr_order is None)
+        assert rr_cost == pytest.approx(orr, **tol) and (rr_order is None) == (orr_order is None)
         if rr_order is not None:
             assert rr_order == list(orr_order)
         tick.close()
@@ -84,7 +86,8 @@ def test_trip_costing_matches_reference_golden(name):
 
 
 @pytest.mark.parametrize("fname,name", [("sim_g8_int_K4.json", "g8_int"), ("sim_g20_int_K4.json", "g20_int"),
-                                        ("sim_g20_int_K1.json", "g20_int"), ("sim_g12_float_K2.json", "g12_float")])
+                                        ("sim_g20_int_K1.json", "g20_int"), ("sim_g12_float_K2.json", "g12_float"),
+                                        ("sim_g12_float_K2b.json", "g12_float"), ("sim_g10_dfloat_K2b.json", "g10_dfloat")])
 def test_alonso_mora_matches_reference_golden(fname, name):
     """AlonsoMora("enumerate").optimizeAssignment on the ticks the reference's own classes produced."""
     from drs_abm_b200.dispatch import AlonsoMora

@@ -7,7 +7,7 @@ from conftest import golden_map_path, load_golden, oracle_graph, oracle_graph_fr
 
 pytestmark = pytest.mark.gpu
 
-MAPS = ["g8_int", "g12_float", "g20_int", "g20_uniform"]
+MAPS = ["g8_int", "g12_float", "g20_int", "g20_uniform", "g10_dfloat"]
 
 
 def _engine(name, **kw):

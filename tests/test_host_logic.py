@@ -198,3 +198,37 @@ def test_locality_numbering_is_a_permutation_with_fallback():
     assert np.array_equal(Gi.dev_ids(ids), ids) and np.array_equal(Gi.host_cols(rows), rows[:, :data.n])
     with pytest.raises(ValueError):
         RoadGraph(data, numbering="sorted")
+
+
+def test_rr_prefilter_equals_the_references_double_loop():
+    """The vectorised crow-flies pre-filter of the R x R stage against the reference's pair-by-pair expression
+    (lib/Optimization.py:148-151), including pairs placed exactly on the threshold."""
+    import math
+    from drs_abm_b200 import dispatch
+
+    class R(object):
+        pass
+    rs = np.random.RandomState(3)
+    reqs = []
+    for k in range(120):
+        r = R()
+        r.olat, r.olng = 42.3 + 0.05 * rs.rand(), -71.1 + 0.05 * rs.rand()
+        r.Clp = 600.0 + 400.0 * rs.rand()
+        reqs.append(r)
+    T = 300.0
+    # put a few pairs exactly on the boundary: Clp := T + d / CST_SPEED
+    for a, b in ((0, 1), (5, 9), (17, 80)):
+        d = dispatch.great_circle_distance(reqs[a].olat, reqs[a].olng, reqs[b].olat, reqs[b].olng)
+        reqs[a].Clp = T + d / dispatch.CST_SPEED
+        reqs[b].Clp = reqs[a].Clp + 50.0
+    want = []
+    for a in range(len(reqs)):
+        for b in range(a + 1, len(reqs)):
+            t = T + dispatch.great_circle_distance(reqs[a].olat, reqs[a].olng, reqs[b].olat, reqs[b].olng) / dispatch.CST_SPEED
+            if t > reqs[a].Clp or t > reqs[b].Clp:
+                continue
+            want.append((a, b))
+    got = dispatch.rr_prefilter(reqs, T)
+    assert got == want and 0 < len(want) < 120 * 119 // 2
+    assert (0, 1) in got and (5, 9) in got and (17, 80) in got
+    assert dispatch.rr_prefilter(reqs[:1], T) == []

@@ -8,7 +8,7 @@ from conftest import load_golden, oracle_graph, unjf
 from oracle import dispatch_oracle as D
 from oracle.routing_oracle import OracleRoutingEngine
 
-MAPS = ["g8_int", "g12_float", "g20_int", "g20_uniform"]
+MAPS = ["g8_int", "g12_float", "g20_int", "g20_uniform", "g10_dfloat"]
 
 
 @pytest.mark.parametrize("name", MAPS)
@@ -135,7 +135,8 @@ def route_cost(G, tt, tick, vid, route):
 
 
 @pytest.mark.parametrize("fname,name", [("sim_g8_int_K4.json", "g8_int"), ("sim_g20_int_K4.json", "g20_int"),
-                                        ("sim_g20_int_K1.json", "g20_int"), ("sim_g12_float_K2.json", "g12_float")])
+                                        ("sim_g20_int_K1.json", "g20_int"), ("sim_g12_float_K2.json", "g12_float"),
+                                        ("sim_g12_float_K2b.json", "g12_float"), ("sim_g10_dfloat_K2b.json", "g10_dfloat")])
 def test_assignment_ticks_match_reference(fname, name):
     gold = load_golden(fname)
     G = oracle_graph(name)
