@@ -692,9 +692,14 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the routing core has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    # stdout carries exactly ONE JSON line: everything native code prints meanwhile (NCCL's version banner comes from C, on
+    # file descriptor 1, from every rank) goes to stderr; rank 0 gets the descriptor back for the line
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line (NCCL's version banner)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = _lib.load()
     peaks, peaks_src = measured_peaks()
@@ -908,6 +913,8 @@ def main():
             line.update(sim_section(G2, data, args.config))
         if c5 is not None:
             line.update(c5)
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
     if comm[0] is not None:
         comm[0].close()

@@ -78,6 +78,7 @@ SIGNATURES = {
     "drs_version": (C.c_int, []),
     "drs_graph_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _i32p, _i32p, _f64p, _f64p, C.POINTER(_vp)]),
     "drs_graph_set_weights": (C.c_int, [_vp, _f64p]),
+    "drs_locality_order": (C.c_int, [C.c_int32, _f64p, _f64p, _i32p]),
     "drs_graph_destroy": (C.c_int, [_vp]),
     "drs_graph_info": (C.c_int, [_vp, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p]),
     "drs_apsp_build": (C.c_int, [_vp, C.c_int32]),

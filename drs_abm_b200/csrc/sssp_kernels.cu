@@ -631,7 +631,8 @@ extern "C" int drs_sssp_batch_dev(const drs_graph* g, int32_t mode, int32_t nsrc
   int32_t* d_sources = gm->sssp_sources;
   int* d_overflow = reinterpret_cast<int*>(d_sources + gm->sssp_sources_cap);
   // queue capacity per CTA: frontiers of road networks are a few thousand entries; overflow is detected and retried
-  int cap = std::max(4096, std::min(g->narcs + 1, 65536)) * sssp_slots();
+  // (an eighth of the vertices: the FAR pile of a grid city peaks at a few thousand entries; 4 * cap * 8 B per CTA, ~1 300 CTAs)
+  int cap = std::max(4096, std::min(g->n / 8 + 1, 65536)) * sssp_slots();
   int rc = DRS_OK;
   for (int attempt = 0; attempt < 3 && rc == DRS_OK; ++attempt) {
     const size_t need = sizeof(Entry) * 4 * (size_t)cap * grid;

@@ -159,7 +159,7 @@ def _spread16(v):
     return v
 
 
-def locality_order(n, src, dst, lng=None, lat=None):
+def locality_order(n, src, dst, lng=None, lat=None, native=False):
     """Vertex ids in the order of the DEVICE numbering: order[k] = caller's id of device vertex k.
 
     The kernels index distance rows by vertex id, so neighbouring vertices should have neighbouring ids (the same
@@ -167,8 +167,17 @@ def locality_order(n, src, dst, lng=None, lat=None):
     profiles/r01_sssp_numbering_probe.jsonl).  With usable coordinates: Morton (Z-order) curve over (lng, lat)
     ranked to at most 16 bits each; otherwise reverse Cuthill-McKee over the adjacency."""
     try:
-        x, y = np.asarray(lng, dtype=np.float64), np.asarray(lat, dtype=np.float64)
-        if x.shape != (n,) or y.shape != (n,) or not (np.isfinite(x).all() and np.isfinite(y).all()):
+        x, y = np.ascontiguousarray(lng, dtype=np.float64), np.ascontiguousarray(lat, dtype=np.float64)
+        if x.shape != (n,) or y.shape != (n,):
+            raise ValueError
+        if native:                                   # the same order from the library's C++ helper (for bindings without numpy;
+                                                     # numpy's vectorised sorts are the faster of the two here)
+            lib = _lib.load()
+            order = np.empty(n, dtype=np.int32)
+            if lib.drs_locality_order(n, _lib.ptr_f64(x), _lib.ptr_f64(y), _lib.ptr_i32(order)) == 0:
+                return order
+            raise ValueError
+        if not (np.isfinite(x).all() and np.isfinite(y).all()):
             raise ValueError
         ux, qx = np.unique(x, return_inverse=True)      # rank of each coordinate among the distinct values: a regular
         uy, qy = np.unique(y, return_inverse=True)      # grid gets its exact Z-curve, an irregular map a density-equalised one

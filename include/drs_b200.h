@@ -67,6 +67,13 @@ int drs_graph_set_weights(drs_graph* g, const double* tt_host);
 
 int drs_graph_destroy(drs_graph* g);
 
+/* Host-side helper of the bindings: vertex ids in the order of a locality-preserving DEVICE numbering (order_out[k] =
+ * caller's id of device vertex k; Morton curve over the ranks of the lng / lat values).  The kernels index distance rows by
+ * vertex id; a caller that numbers its vertices this way before drs_graph_create (and translates ids at the boundary, as
+ * routing.RoadGraph does) gets ~10 % faster builds than with row-major ids and ~40 % faster than with random ones.
+ * DRS_ERR_ARG: coordinates unusable (non-finite or all equal). */
+int drs_locality_order(int32_t n, const double* lng_host, const double* lat_host, int32_t* order_out_host);
+
 /* n, m, npad (matrix leading dimension), mode, apsp_valid, device */
 int drs_graph_info(const drs_graph* g, int32_t* n, int32_t* m, int32_t* npad, int32_t* mode,
                    int32_t* apsp_valid, int32_t* device);

@@ -232,3 +232,16 @@ def test_rr_prefilter_equals_the_references_double_loop():
     assert got == want and 0 < len(want) < 120 * 119 // 2
     assert (0, 1) in got and (5, 9) in got and (17, 80) in got
     assert dispatch.rr_prefilter(reqs[:1], T) == []
+
+
+def test_native_locality_order_equals_the_numpy_one():
+    """drs_locality_order (the C++ helper other bindings would call) gives the numbering routing.RoadGraph computes with numpy."""
+    from drs_abm_b200 import synth
+    from drs_abm_b200.routing import locality_order
+    data = synth.config_graph("C2")
+    a = locality_order(data.n, data.src, data.dst, data.vattrs["lng"], data.vattrs["lat"], native=True)
+    b = locality_order(data.n, data.src, data.dst, data.vattrs["lng"], data.vattrs["lat"], native=False)
+    assert np.array_equal(a, b) and sorted(a.tolist()) == list(range(data.n))
+    rs = np.random.RandomState(0)
+    x, y = rs.rand(3000).round(2), rs.rand(3000).round(2)          # irregular coordinates with many duplicates
+    assert np.array_equal(locality_order(3000, [], [], x, y, native=True), locality_order(3000, [], [], x, y, native=False))
