@@ -61,6 +61,12 @@ constexpr int VERTEX_MASK = (1 << SLOT_SHIFT) - 1;
 #ifndef DRS_SSSP_DEFAULT_SMEM
 #define DRS_SSSP_DEFAULT_SMEM 0   // which variant drs_sssp_batch_dev picks when DRS_SSSP_IMPL is unset
 #endif
+#ifndef DRS_SSSP_DEFAULT_ARC
+#define DRS_SSSP_DEFAULT_ARC 0    // 1: the lane-per-arc kernel with the row in L2 is the default
+#endif
+#ifndef DRS_SSSP_ARC_SHAPE
+#define DRS_SSSP_ARC_SHAPE 12812  // CTA size * 100 + CTAs per SM
+#endif
 #ifndef DRS_SSSP_SMEM_DELTA_MULT
 #define DRS_SSSP_SMEM_DELTA_MULT 24.0
 #endif
@@ -237,14 +243,19 @@ __device__ unsigned long long g_sssp_prof[16];
 
 // FAR = false compiles the one-bucket form (Bellman-Ford-Moore wavefronts: every improved vertex goes to the next
 // NEAR queue, no FAR pile, no theta), which is what an "infinite" bucket width selects.
-template <typename T, int THREADS, bool FAR>
-__global__ void __launch_bounds__(THREADS, 1) sssp_smem_kernel(
+// SROW = false is the same search with the row left in the output matrix (global memory, L2), i.e. the structure of
+// sssp_batch_kernel rebuilt on this kernel's leaner step -- one lane per (entry, arc), one barrier per step, one counter
+// atomic per warp -- so that MORE searches fit an SM (MINB CTAs of THREADS): the measured lever of this workload is the
+// number of independent searches in flight per SM (profiles/r02_sssp_step_profile.md).
+template <typename T, int THREADS, bool FAR, bool SROW, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) sssp_smem_kernel(
     int n, const int32_t* __restrict__ out_ptr, const int2* __restrict__ arcs, const int4* __restrict__ ell, T* dist, int64_t ld,
     int64_t row_stride, const int32_t* __restrict__ sources, int nsrc, Entry* queues, int cap, T delta, int* overflow, int qn) {
   extern __shared__ __align__(16) unsigned char sssp_smem[];
   T* row = reinterpret_cast<T*>(sssp_smem);
   int* irow = reinterpret_cast<int*>(sssp_smem);
-  Entry* s_q = reinterpret_cast<Entry*>(sssp_smem + sizeof(T) * ld);   // two NEAR buffers of qn entries
+  Entry* s_q = reinterpret_cast<Entry*>(sssp_smem + (SROW ? sizeof(T) * ld : 0));   // two NEAR buffers of qn entries
+  auto rd = [&](int x) { return SROW ? irow[x] : __ldcg(irow + x); };   // L2 read when the row is global: the atomics live there
   __shared__ int s_cnt[3], s_far, s_keep, s_min, s_group;
   int* next_group = overflow + 1;
   Entry* gq = queues + (int64_t)blockIdx.x * 4 * cap;                  // their overflow: two buffers of cap entries
@@ -264,13 +275,20 @@ __global__ void __launch_bounds__(THREADS, 1) sssp_smem_kernel(
   const long long prof_t0 = clock64();
 #endif
   // the row starts as +inf everywhere; after every search it is written out and reset in the same sweep
-  for (int64_t t = tid; t < ld; t += THREADS) row[t] = inf;
+  if (SROW)
+    for (int64_t t = tid; t < ld; t += THREADS) row[t] = inf;
   while (true) {
     __syncthreads();
     if (tid == 0) s_group = atomicAdd(next_group, 1);
     __syncthreads();
     const int k = s_group;
     if (k >= nsrc) break;
+    if (!SROW) {
+      row = dist + (int64_t)k * row_stride;
+      irow = reinterpret_cast<int*>(row);
+      for (int64_t t = tid; t < ld; t += THREADS) row[t] = inf;
+      __syncthreads();
+    }
     if (tid == 0) {
       const int src = sources[k];
       row[src] = (T)0;
@@ -302,7 +320,7 @@ __global__ void __launch_bounds__(THREADS, 1) sssp_smem_kernel(
           bool live = false;
           if (e < nn) {
             arc = __ldg(&ell2[4 * (int64_t)en.v + j]);
-            live = irow[en.v] == en.key;                 // stale otherwise: a shorter distance arrived later
+            live = rd(en.v) == en.key;                   // stale otherwise: a shorter distance arrived later
           }
 #ifdef DRS_SSSP_PROFILE
           if (arc.x == -12345 && live) prof[9] += 1;   // consume the loads before the time stamp
@@ -310,7 +328,7 @@ __global__ void __launch_bounds__(THREADS, 1) sssp_smem_kernel(
           SSSP_PROF_T(p1);
           SSSP_PROF_ADD(3, p1 - p0);
           const int nk = Dist<T>::key(Dist<T>::unkey(en.key) + Dist<T>::weight(arc.y));
-          bool push = live && arc.x >= 0 && nk < irow[max(arc.x, 0)];
+          bool push = live && arc.x >= 0 && nk < rd(max(arc.x, 0));
 #ifdef DRS_SSSP_PROFILE
           if (push && nk == -12345) prof[9] += 1;
 #endif
@@ -349,7 +367,7 @@ __global__ void __launch_bounds__(THREADS, 1) sssp_smem_kernel(
             for (int a = arc.y; a < a1; ++a) {
               const int2 ar = arcs[a];
               const int k2 = Dist<T>::key(Dist<T>::unkey(en.key) + Dist<T>::weight(ar.y));
-              if (k2 < irow[ar.x] && k2 < atomicMin(irow + ar.x, k2)) {
+              if (k2 < rd(ar.x) && k2 < atomicMin(irow + ar.x, k2)) {
                 const Entry ne{ar.x, k2};
                 if (!FAR || Dist<T>::unkey(k2) < theta) {
                   q_put(buf ^ 1, atomicAdd(&s_cnt[c_wr], 1), ne);
@@ -378,7 +396,7 @@ __global__ void __launch_bounds__(THREADS, 1) sssp_smem_kernel(
       int lmin = 0x7fffffff;
       for (int e = tid; e < nf; e += THREADS) {
         const Entry en = far[e];
-        if (irow[en.v] == en.key) lmin = min(lmin, en.key);
+        if (rd(en.v) == en.key) lmin = min(lmin, en.key);
       }
       for (int off = 16; off > 0; off >>= 1) lmin = min(lmin, __shfl_down_sync(0xffffffffu, lmin, off));
       if (lane == 0 && lmin != 0x7fffffff) atomicMin(&s_min, lmin);
@@ -388,7 +406,7 @@ __global__ void __launch_bounds__(THREADS, 1) sssp_smem_kernel(
       theta = Dist<T>::next_theta(Dist<T>::unkey(kmin), delta);
       for (int e = tid; e < nf; e += THREADS) {
         const Entry en = far[e];
-        if (irow[en.v] != en.key) continue;
+        if (rd(en.v) != en.key) continue;
         if (Dist<T>::unkey(en.key) < theta) q_put(buf, atomicAdd(&s_cnt[c_rd], 1), en);
         else far2[atomicAdd(&s_keep, 1)] = en;
       }
@@ -401,7 +419,7 @@ __global__ void __launch_bounds__(THREADS, 1) sssp_smem_kernel(
     // ---- the row is final: one coalesced sweep writes it out and resets the shared copy
     SSSP_PROF_T(pw0);
     __syncthreads();
-    {
+    if (SROW) {
       T* out = dist + (int64_t)k * row_stride;
       const int4 inf4 = make_int4(Dist<T>::key(inf), Dist<T>::key(inf), Dist<T>::key(inf), Dist<T>::key(inf));
       int4* r4 = reinterpret_cast<int4*>(row);
@@ -533,11 +551,11 @@ int sssp_smem_threads(int n) {
   return n <= 2048 ? 128 : (n <= 16384 ? 256 : 1024);
 }
 
-template <typename T, int TH, bool FAR>
+template <typename T, int TH, bool FAR, bool SROW, int MINB>
 int sssp_smem_go(int sms, cudaStream_t st, int n, const int32_t* out_ptr, const int2* arcs, const int4* ell, T* dist, int64_t ld,
                  int64_t row_stride, const int32_t* sources, int nsrc, Entry* queues, int cap, T delta, int* overflow, int qn, int* grid_out) {
-  const size_t smem = sizeof(T) * (size_t)ld + 2 * (size_t)qn * sizeof(Entry);
-  auto kern = sssp_smem_kernel<T, TH, FAR>;
+  const size_t smem = (SROW ? sizeof(T) * (size_t)ld : 0) + 2 * (size_t)qn * sizeof(Entry);
+  auto kern = sssp_smem_kernel<T, TH, FAR, SROW, MINB>;
   DRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
   DRS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TH, smem));
@@ -551,12 +569,26 @@ int sssp_smem_go(int sms, cudaStream_t st, int n, const int32_t* out_ptr, const 
 
 template <typename T, typename... A>
 int sssp_smem_dispatch(int threads, bool use_far, A... args) {
-#define DRS_SMEM_CASE(TH) case TH: return use_far ? sssp_smem_go<T, TH, true>(args...) : sssp_smem_go<T, TH, false>(args...);
+#define DRS_SMEM_CASE(TH) case TH: return use_far ? sssp_smem_go<T, TH, true, true, 1>(args...) : sssp_smem_go<T, TH, false, true, 1>(args...);
   switch (threads) {
     DRS_SMEM_CASE(128) DRS_SMEM_CASE(256) DRS_SMEM_CASE(512)
-    default: return use_far ? sssp_smem_go<T, 1024, true>(args...) : sssp_smem_go<T, 1024, false>(args...);
+    default: return use_far ? sssp_smem_go<T, 1024, true, true, 1>(args...) : sssp_smem_go<T, 1024, false, true, 1>(args...);
   }
 #undef DRS_SMEM_CASE
+}
+
+// the row-in-L2 form of the same kernel: `shape` = CTA size * 100 + CTAs per SM the register allocation must allow
+template <typename T, typename... A>
+int sssp_arc_dispatch(int shape, A... args) {
+  switch (shape) {
+    case 6432: return sssp_smem_go<T, 64, true, false, 32>(args...);
+    case 6424: return sssp_smem_go<T, 64, true, false, 24>(args...);
+    case 12816: return sssp_smem_go<T, 128, true, false, 16>(args...);
+    case 12812: return sssp_smem_go<T, 128, true, false, 12>(args...);
+    case 12809: return sssp_smem_go<T, 128, true, false, 9>(args...);
+    case 25608: return sssp_smem_go<T, 256, true, false, 8>(args...);
+    default: return sssp_smem_go<T, 128, true, false, 12>(args...);
+  }
 }
 
 }  // namespace
@@ -581,6 +613,9 @@ extern "C" int drs_sssp_batch_dev(const drs_graph* g, int32_t mode, int32_t nsrc
   const int qn = sssp_smem_qn(ld, sizeof(float));
   // default by measurement (profiles/r02_sssp_step_profile.md): DRS_SSSP_DEFAULT_SMEM
   const bool want_smem = impl_env ? !strcmp(impl_env, "smem") : (DRS_SSSP_DEFAULT_SMEM != 0);
+  const bool want_arc = impl_env ? !strcmp(impl_env, "arc") : (DRS_SSSP_DEFAULT_ARC != 0);
+  const int arc_shape = sssp_env_int("DRS_SSSP_ARC_SHAPE", DRS_SSSP_ARC_SHAPE);
+  const int arc_qn = 256;
   bool use_smem = want_smem && qn > 0 && ld % 4 == 0 && ((uintptr_t)dist_dev & 15) == 0;
   DRS_REQUIRE(use_smem || !(impl_env && !strcmp(impl_env, "smem")), DRS_ERR_ARG,
               "drs_sssp_batch_dev: DRS_SSSP_IMPL=smem but a row of %lld elements does not fit in shared memory", (long long)ld);
@@ -606,6 +641,15 @@ extern "C" int drs_sssp_batch_dev(const drs_graph* g, int32_t mode, int32_t nsrc
                   : sssp_smem_dispatch<int>(smem_threads, true, sms, (cudaStream_t) nullptr, 0, (const int32_t*)nullptr, (const int2*)nullptr,
                                             (const int4*)nullptr, (int*)nullptr, ld, ld, (const int32_t*)nullptr, nsrc, (Entry*)nullptr, 0, 0,
                                             (int*)nullptr, qn, &grid);
+    if (rc0) return rc0;
+  } else if (want_arc) {
+    int rc0 = mode == DRS_MODE_F32
+                  ? sssp_arc_dispatch<float>(arc_shape, sms, (cudaStream_t) nullptr, 0, (const int32_t*)nullptr, (const int2*)nullptr,
+                                             (const int4*)nullptr, (float*)nullptr, ld, ld, (const int32_t*)nullptr, nsrc, (Entry*)nullptr, 0,
+                                             0.0f, (int*)nullptr, arc_qn, &grid)
+                  : sssp_arc_dispatch<int>(arc_shape, sms, (cudaStream_t) nullptr, 0, (const int32_t*)nullptr, (const int2*)nullptr,
+                                           (const int4*)nullptr, (int*)nullptr, ld, ld, (const int32_t*)nullptr, nsrc, (Entry*)nullptr, 0, 0,
+                                           (int*)nullptr, arc_qn, &grid);
     if (rc0) return rc0;
   } else {
     grid = mode == DRS_MODE_F32 ? sssp_grid<float>(sms, nsrc) : sssp_grid<int>(sms, nsrc);
@@ -655,6 +699,14 @@ extern "C" int drs_sssp_batch_dev(const drs_graph* g, int32_t mode, int32_t nsrc
       rc = sssp_smem_dispatch<int>(smem_threads, use_far, sms, st, g->n, (const int32_t*)g->d_out_ptr, (const int2*)gm->sssp_arcs, (const int4*)d_ell,
                                    (int*)dist_dev, ld, ld, (const int32_t*)d_sources, nsrc, (Entry*)gm->sssp_queues, cap,
                                    (int)std::max(1.0, std::min<double>(delta, (double)DRS_I32_INF)), d_overflow, qn, (int*)nullptr);
+    else if (want_arc && mode == DRS_MODE_F32)
+      rc = sssp_arc_dispatch<float>(arc_shape, sms, st, g->n, (const int32_t*)g->d_out_ptr, (const int2*)gm->sssp_arcs, (const int4*)d_ell,
+                                    (float*)dist_dev, ld, ld, (const int32_t*)d_sources, nsrc, (Entry*)gm->sssp_queues, cap,
+                                    (float)std::min<double>(delta, big_f), d_overflow, arc_qn, (int*)nullptr);
+    else if (want_arc)
+      rc = sssp_arc_dispatch<int>(arc_shape, sms, st, g->n, (const int32_t*)g->d_out_ptr, (const int2*)gm->sssp_arcs, (const int4*)d_ell,
+                                  (int*)dist_dev, ld, ld, (const int32_t*)d_sources, nsrc, (Entry*)gm->sssp_queues, cap,
+                                  (int)std::max(1.0, std::min<double>(delta, (double)DRS_I32_INF)), d_overflow, arc_qn, (int*)nullptr);
     else if (mode == DRS_MODE_F32)
       rc = sssp_run<float>(g, nsrc, d_sources, (float*)dist_dev, ld, ld, delta, st, (const int2*)gm->sssp_arcs, (const int4*)d_ell,
                            (Entry*)gm->sssp_queues, cap, grid, d_overflow);

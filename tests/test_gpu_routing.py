@@ -425,3 +425,21 @@ def test_i32_mode_is_refused_on_float_weights_by_every_entry_point():
                lib.drs_fw_init(h, _lib.MODE_I32, C.c_void_p(buf.data_ptr()), npad, 0, npad, None)):
         assert rc == _lib.ERR_ARG and b"integer travel times" in lib.drs_last_error()
     G.close()
+
+
+@pytest.mark.parametrize("impl", ["smem", "arc"])
+def test_alternative_sssp_kernels_give_the_same_matrix(impl, monkeypatch):
+    """The two measured alternatives to the default SSSP kernel (profiles/r02_sssp_step_profile.md) -- the distance row in
+    shared memory, and one lane per arc with the row in L2 at full occupancy -- stay selectable and bit-identical."""
+    from drs_abm_b200 import _lib, synth
+    from drs_abm_b200.routing import RoadGraph
+    for data in (synth.config_graph("C1"), synth.config_graph("C2"), synth.config_graph("C2_float")):
+        monkeypatch.delenv("DRS_SSSP_IMPL", raising=False)
+        G = RoadGraph(data, algorithm=_lib.APSP_SSSP)
+        want = G.dist_rows(0, G.n)
+        G.close()
+        monkeypatch.setenv("DRS_SSSP_IMPL", impl)
+        G = RoadGraph(data, algorithm=_lib.APSP_SSSP)
+        got = G.dist_rows(0, G.n)
+        G.close()
+        assert np.array_equal(got, want)

@@ -44,7 +44,12 @@ settings = [(th, mult) for th in (1024, 512, 256) for mult in (6, 12, 24, 48, 0)
 if len(sys.argv) > 2:
     settings = [tuple(int(x) for x in s.split(":")) for s in sys.argv[2].split(",")]
 for th, mult in settings:
-    os.environ["DRS_SSSP_SMEM_THREADS"] = str(th)
+    if th > 2000:                       # a shape of the row-in-L2 lane-per-arc kernel: CTA size * 100 + CTAs per SM
+        os.environ["DRS_SSSP_IMPL"] = "arc"
+        os.environ["DRS_SSSP_ARC_SHAPE"] = str(th)
+    else:
+        os.environ["DRS_SSSP_IMPL"] = "smem"
+        os.environ["DRS_SSSP_SMEM_THREADS"] = str(th)
     os.environ["DRS_SSSP_DELTA_MULT"] = str(mult)
     buf.fill_(-1.0)
     try:
@@ -53,5 +58,5 @@ for th, mult in settings:
     except Exception as ex:  # noqa: BLE001
         print(json.dumps({"impl": "smem", "threads": th, "delta_mult": mult, "error": str(ex)}), flush=True)
         continue
-    print(json.dumps({"config": cfg, "impl": "smem", "threads": th, "delta_mult": mult, "ms": round(ms, 3), "bit_equal_to_l2": same}), flush=True)
+    print(json.dumps({"config": cfg, "impl": os.environ["DRS_SSSP_IMPL"], "threads_or_shape": th, "delta_mult": mult, "ms": round(ms, 3), "bit_equal_to_l2": same}), flush=True)
 G.close()
