@@ -36,8 +36,9 @@ sys.path.insert(0, ROOT)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (C3 map, one
 # B200, f32); reported as roofline.traffic only for the configuration the capture was taken on
 NCU_TRAFFIC = {
-    "sssp_batch_kernel": (10.41e9 + 25.70e9, "profiles/r01_sssp_ncu_full_final2.txt"),
-    "insertion_reach_kernel": (None, "profiles/r02_ins_reach_ncu_full.txt"),
+    "sssp_batch_kernel": (9.401e9 + 22.049e9, "profiles/r02_kernels_ncu.md"),
+    "insertion_reach_kernel": (0.403e9 + 0.007e9, "profiles/r02_kernels_ncu.md"),
+    "rv_filter_kernel": (0.404e9 + 0.022e9, "profiles/r02_kernels_ncu.md"),
 }
 
 WORKLOADS = {
@@ -293,7 +294,8 @@ def insertion_section(G, data, config, peaks, cpu_seconds=8.0):
                        "infeasible": int(counters[3]), "host_marshal_s": t_marshal,
                        "roofline": {"bound": "hbm", "achieved": pairs * 12.0 / (f_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
                                     "unit": "GB/s", "frac": pairs * 12.0 / (f_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                                    "traffic": None, "kernel": "rv_filter_kernel",
+                                    "traffic": NCU_TRAFFIC["rv_filter_kernel"][0] if config == "C3" else None,
+                                    "traffic_source": NCU_TRAFFIC["rv_filter_kernel"][1], "kernel": "rv_filter_kernel",
                                     "algorithmic_bytes_per_launch": pairs * 12.0}}
     return out
 
@@ -839,10 +841,11 @@ def main():
                     "traffic": NCU_TRAFFIC["sssp_batch_kernel"][0] if (args.config == "C3" and world == 1 and args.mode == "f32") else None,
                     "traffic_source": NCU_TRAFFIC["sssp_batch_kernel"][1],
                     "kernel": "sssp_batch_kernel", "algorithmic_bytes_per_launch": sssp_bytes,
-                    "note": "(16 E_dir + 8 N) bytes per source, served mostly by L1/L2: ncu shows L1/TEX at 75 % and L2 at "
-                            "64 % of peak throughput, DRAM 36 GB per build (3.8x the matrix: the ~1300 rows in flight exceed "
-                            "the 126 MB L2) -- bound by L1/L2 transactions and dependent round trips per bucket, not by HBM "
-                            "bandwidth"}
+                    "note": "(16 E_dir + 8 N) bytes per source, served mostly by L1/L2: ncu shows L1/TEX at 70 % and L2 at 59 % of peak "
+                            "throughput, DRAM 31 GB per build (3.3x the matrix: the ~1300 rows in flight exceed the 126 MB L2) -- bound by "
+                            "the number of searches an SM can keep in flight (each a chain of ~500 dependent wavefront steps), not by HBM "
+                            "bandwidth; the row-in-shared-memory and the full-occupancy lane-per-arc kernels were built and measured: "
+                            "profiles/r02_sssp_step_profile.md"}
         line = {"metric": "apsp_build_seconds", "value": sec, "unit": "s", "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": False, "scaling": "strong",
                 "vs_baseline": None, "dtype": args.mode, "data": "synthetic",

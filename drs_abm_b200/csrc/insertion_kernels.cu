@@ -51,6 +51,8 @@ struct PlanView {
   const int32_t* pos_node;             // vertex of the vehicle's position, -1 between vertices
   int32_t* keep_node;                  // -1: the vehicle has no route
   double *keep_t, *keep_et;
+  int32_t* keep_pend;                  // >= 0: the vehicle got its first route in this tick; its kept step is the first step of the
+                                       //       leg pos_node -> keep_pend, found (a path walk) only if the vehicle wins again
   // request table (Cld and pwt are updated by commits)
   const int32_t *q_o, *q_d;
   const double *q_cep, *q_clp, *q_ts, *q_tr;
@@ -314,6 +316,70 @@ __device__ void plan_prep(const PlanView& pv, const DistView& dv, int vs) {
     float lb = __int_as_float(0x7f800000);
     if (k < ns) {
       lb = __double2float_rd(T + pv.m_base_t[k * nv + vs]);
+      lb = (lb > 0.f) ? __int_as_float(__float_as_int(lb) - 1) : ((lb < 0.f) ? __int_as_float(__float_as_int(lb) + 1) : -1.0e-30f);
+    }
+    pv.m_lb[k * nv + vs] = lb;
+  }
+}
+
+// plan_prep for ONE vehicle whose plan the caller holds in local arrays (the commit): everything it needs from memory is
+// gathered up front (independent loads), the walk then runs in registers, the results are stored at the end -- the same
+// values as plan_prep, without a memory round trip per stop on the queue kernel's critical path.
+__device__ void plan_prep_local(const PlanView& pv, const DistView& dv, int vs, int L, const int* node, const int* req, const int8_t* pod,
+                                const int8_t* partner) {
+  const int nv = pv.n_veh;
+  double seg[INS_MAXL], cep[INS_MAXL], clp[INS_MAXL], ts[INS_MAXL], tr[INS_MAXL], pwt[INS_MAXL], cldq[INS_MAXL];
+  int prev = pv.node[vs];
+  for (int k = 0; k < L; ++k) {
+    seg[k] = (prev == node[k]) ? 0.0 : dv.at(prev, node[k]);
+    prev = node[k];
+    const int rq = req[k];
+    cep[k] = pv.q_cep[rq]; clp[k] = pv.q_clp[rq]; ts[k] = pv.q_ts[rq]; tr[k] = pv.q_tr[rq]; pwt[k] = pv.q_pwt[rq]; cldq[k] = pv.q_cld[rq];
+  }
+  const int onboard = pv.onboard[vs], cap = pv.cap[vs];
+  const double T = pv.clock[vs];
+  int occ = onboard, viol_at = L;
+  bool over = occ > cap;
+  for (int k = 0; k < L; ++k) { occ += pod[k]; if (occ > cap) over = true; }
+  double base_t[INS_MAXL + 1], base_c[INS_MAXL + 1], base_cld[INS_MAXL];
+  Walk w{0.0 + pv.delay[vs], 0.0, onboard};
+  for (int k = 0; k <= L; ++k) {
+    base_t[k] = w.t; base_c[k] = w.c;
+    if (k == L || viol_at < L) continue;
+    // one stop of the walk (walk_stop with the request's fields already in registers)
+    double dt = seg[k], cld_set = 0.0;
+    bool bad = false;
+    w.t += dt;
+    if (pod[k] == 1) {
+      if (T + w.t < cep[k]) { dt += cep[k] - T - w.t; w.t += cep[k] - T - w.t; cld_set = cep[k] + pv.prm.max_detour * ts[k]; }
+      else if (T + w.t > clp[k]) bad = true;
+      else cld_set = T + w.t + pv.prm.max_detour * ts[k];
+    } else if (pod[k] == -1) {
+      const double cld_drop = partner[k] >= 0 ? base_cld[partner[k]] : cldq[k];
+      if (T + w.t > cld_drop) bad = true;
+    }
+    if (bad) {
+      viol_at = k;
+    } else {
+      w.c += w.n * dt * pv.prm.coef_inveh;
+      w.n += pod[k];
+      if (pod[k] == 1) {
+        if (pwt[k] > 0) w.c += (T + w.t - tr[k] - pwt[k]) * pv.prm.coef_extra_wait;
+        else w.c += w.t * pv.prm.coef_wait;
+      }
+    }
+    base_cld[k] = cld_set;
+  }
+  const int bviol = (over || L > INS_SCAN_MAXL) ? -1 : viol_at;
+  const int ns = bviol < 0 ? 0 : min(L, bviol) + 1;
+  for (int k = 0; k < L; ++k) { pv.m_seg[k * nv + vs] = seg[k]; pv.m_base_cld[k * nv + vs] = base_cld[k]; }
+  for (int k = 0; k <= L; ++k) { pv.m_base_t[k * nv + vs] = base_t[k]; pv.m_base_c[k * nv + vs] = base_c[k]; }
+  pv.m_base_viol[vs] = bviol;
+  pv.m_nslots[vs] = (uint8_t)ns;
+  for (int k = 0; k <= INS_MAXL; ++k) {
+    float lb = __int_as_float(0x7f800000);
+    if (k < ns) {
+      lb = __double2float_rd(T + base_t[k]);
       lb = (lb > 0.f) ? __int_as_float(__float_as_int(lb) - 1) : ((lb < 0.f) ? __int_as_float(__float_as_int(lb) + 1) : -1.0e-30f);
     }
     pv.m_lb[k * nv + vs] = lb;
@@ -728,14 +794,35 @@ __device__ void commit_one(const PlanView& pv, const DistView& dv, const PredSou
     node[j] = pv.q_d[rq]; req[j] = rq; pod[j] = -1;
   }
   const int L2 = L + 2;
+  int8_t partners[INS_MAXL];
   for (int k = 0; k < L2; ++k) {
     int8_t partner = -1;
     if (pod[k] < 0)
       for (int m = 0; m < k; ++m)
         if (req[m] == req[k] && pod[m] > 0) partner = (int8_t)m;
+    partners[k] = partner;
     pv.m_node[k * nv + vs] = node[k]; pv.m_req[k * nv + vs] = req[k]; pv.m_pod[k * nv + vs] = pod[k]; pv.m_partner[k * nv + vs] = partner;
   }
   pv.len[vs] = L2;
+  if (pv.keep_pend[vs] >= 0) {
+    // second win of a vehicle that had no route at the start of the tick: NOW its kept step is needed -- the first step of
+    // the leg it was given at its first win, along the canonical path (walk the predecessor chain back from that stop)
+    const int from = pv.pos_node[vs], to = pv.keep_pend[vs];
+    int hop_to = from;                                   // zero-length leg: the dummy stay-in-place step (lib/RoutingEngine.py:173-189)
+    double hop_t = 0.0;
+    if (from != to) {
+      int x = to, guard = 0;
+      while (x != from && guard++ < (1 << 22)) {
+        const int e = ps.last_edge(from, x);
+        if (e < 0) { *err = 3; break; }
+        const int y = prev_node(e, x, esrc, edst);
+        if (y == from) { hop_to = x; hop_t = tt64[e]; }
+        x = y;
+      }
+    }
+    pv.keep_node[vs] = hop_to; pv.keep_t[vs] = hop_t; pv.keep_et[vs] = hop_t;
+    pv.keep_pend[vs] = -1;
+  }
   const bool merge = pv.keep_node[vs] >= 0;              // len(self.route) > 0 (:156-160)
   int cur = merge ? pv.keep_node[vs] : pv.pos_node[vs];
   if (cur < 0) { *err = 2; return; }                     // a vehicle without a route must stand on a vertex
@@ -768,25 +855,9 @@ __device__ void commit_one(const PlanView& pv, const DistView& dv, const PredSou
   for (int k = 0; k < L2; ++k)
     if (pod[k] > 0) pv.q_pwt[req[k]] = pwt[k];
   pv.cost[vs] = c;
-  if (!merge) {
-    // first step of the leg first_from -> node[0] along the canonical path: walk the predecessor chain back from the stop
-    int hop_to = node[0];
-    double hop_t = 0.0;
-    if (first_from != node[0]) {
-      int x = node[0], guard = 0;
-      while (x != first_from && guard++ < (1 << 22)) {
-        const int e = ps.last_edge(first_from, x);
-        if (e < 0) { *err = 3; break; }
-        const int y = prev_node(e, x, esrc, edst);
-        if (y == first_from) { hop_to = x; hop_t = tt64[e]; }
-        x = y;
-      }
-    } else {
-      hop_to = first_from;                               // zero-length leg: the dummy stay-in-place step (lib/RoutingEngine.py:173-189)
-    }
-    pv.keep_node[vs] = hop_to; pv.keep_t[vs] = hop_t; pv.keep_et[vs] = hop_t;
-  }
-  plan_prep(pv, dv, vs);
+  if (!merge) pv.keep_pend[vs] = node[0];                // the kept step of this new route is looked up only if it is ever needed
+  (void)first_from;
+  plan_prep_local(pv, dv, vs, L2, node, req, pod, partners);
 }
 
 __global__ void insertion_commit_kernel(PlanView pv, DistView dv, PredSource ps, const int32_t* esrc, const int32_t* edst, const double* tt64,
@@ -843,6 +914,7 @@ struct QueueShared {
   int vs[QUEUE_MAXC];
   int v[QUEUE_MAXC];
   double cm[QUEUE_MAXC];
+  double c0[QUEUE_MAXC];                  // veh.c of the listed vehicle
   int order[QUEUE_MAXC];                  // order[rank] = list position, ascending caller's vehicle index
   int ev_v[QUEUE_MAXC];                   // fold events: after the re-scan of vehicle ev_v the incumbent is ev_dc
   double ev_dc[QUEUE_MAXC];
@@ -854,7 +926,8 @@ struct QueueShared {
 __global__ void __launch_bounds__(QUEUE_THREADS, 1) insertion_queue_kernel(
     PlanView pv, DistView dv, PredSource ps, const int32_t* esrc, const int32_t* edst, const double* tt64, int n_new,
     const int32_t* new_rows, uint32_t* mask, int words, double* cmin, int32_t* best_veh, int32_t* best_i, int32_t* best_j,
-    double* best_dc, double T_now, int track_cld, int* err, unsigned long long* prof /* cycles of thread 0 by phase A..E, [5] listed vehicles, [6] re-scans */) {
+    double* best_dc, double T_now, int track_cld, int* err,
+    unsigned long long* prof /* cycles of thread 0 by phase A..E, [5] listed vehicles, [6] re-scans */) {
   extern __shared__ __align__(16) unsigned char queue_smem[];
   unsigned long long pacc[7] = {0, 0, 0, 0, 0, 0, 0};
   long long pt = clock64();
@@ -875,7 +948,7 @@ __global__ void __launch_bounds__(QUEUE_THREADS, 1) insertion_queue_kernel(
         m &= m - 1;
         const int vs = w * 32 + b;
         const int pos = atomicAdd(&sh.count, 1);
-        if (pos < QUEUE_MAXC) { sh.vs[pos] = vs; sh.v[pos] = pv.perm[vs]; sh.cm[pos] = cmin[(int64_t)r * nv + vs]; }
+        if (pos < QUEUE_MAXC) { sh.vs[pos] = vs; sh.v[pos] = pv.perm[vs]; sh.cm[pos] = cmin[(int64_t)r * nv + vs]; sh.c0[pos] = pv.cost[vs]; }
       }
     }
     __syncthreads();
@@ -898,11 +971,12 @@ __global__ void __launch_bounds__(QUEUE_THREADS, 1) insertion_queue_kernel(
         const int at = sh.order[k];
         const double cm = sh.cm[at];
         const int vs = sh.vs[at];
-        const double c0 = pv.cost[vs];
+        const double c0 = sh.c0[at];                     // veh.c, fetched with the list (a global load here would sit on the chain)
         if (cm == inf || cm > c0 + dc) continue;
         Pair p;
         load_pair(p, pv, dv, vs, rq);
-        if (scan_vehicle_warp(p, pv, dc, wi, wj)) wv = sh.v[at];
+        const bool won = scan_vehicle_warp(p, pv, dc, wi, wj);
+        if (won) wv = sh.v[at];
         if (lane == 0) { sh.ev_v[n_ev] = sh.v[at]; sh.ev_dc[n_ev] = dc; }
         ++n_ev;
       }
@@ -1130,7 +1204,7 @@ extern "C" int drs_tick_set_plans(drs_tick* t, const drs_plan_batch* b, const dr
   const size_t slots = (size_t)INS_MAXL * nvp, slots1 = (size_t)(INS_MAXL + 1) * nvp;
   const size_t o_perm = lv.add(4 * nvp), o_inv = lv.add(4 * nvp), o_node = lv.add(4 * nvp), o_onb = lv.add(4 * nvp), o_cap = lv.add(4 * nvp),
                o_len = lv.add(4 * nvp), o_delay = lv.add(8 * nvp), o_clock = lv.add(8 * nvp), o_cost = lv.add(8 * nvp), o_pos = lv.add(4 * nvp),
-               o_kn = lv.add(4 * nvp), o_kt = lv.add(8 * nvp), o_ke = lv.add(8 * nvp), o_mnode = lv.add(4 * slots), o_mreq = lv.add(4 * slots),
+               o_kn = lv.add(4 * nvp), o_kp = lv.add(4 * nvp), o_kt = lv.add(8 * nvp), o_ke = lv.add(8 * nvp), o_mnode = lv.add(4 * slots), o_mreq = lv.add(4 * slots),
                o_mpod = lv.add(slots), o_mpar = lv.add(slots);
   const size_t upload_bytes = lv.total;
   const size_t o_seg = lv.add(8 * slots), o_bt = lv.add(8 * slots1), o_bc = lv.add(8 * slots1), o_bcld = lv.add(8 * slots), o_bv = lv.add(4 * nvp),
@@ -1152,7 +1226,7 @@ extern "C" int drs_tick_set_plans(drs_tick* t, const drs_plan_batch* b, const dr
     // defaults: a vehicle with no delay stands on its start vertex; one under way keeps the step it is on
     const int pos = b->pos_node ? b->pos_node[v] : (b->start_delay[v] == 0.0 ? b->start_node[v] : -1);
     int kn = b->keep_node ? b->keep_node[v] : (b->start_delay[v] != 0.0 || L > 0 ? b->start_node[v] : -1);
-    I32(o_pos)[vs] = pos; I32(o_kn)[vs] = kn;
+    I32(o_pos)[vs] = pos; I32(o_kn)[vs] = kn; I32(o_kp)[vs] = -1;
     F64(o_kt)[vs] = b->keep_t ? b->keep_t[v] : b->start_delay[v];
     F64(o_ke)[vs] = b->keep_et ? b->keep_et[v] : F64(o_kt)[vs];
     d.h_len[vs] = L;
@@ -1189,7 +1263,7 @@ extern "C" int drs_tick_set_plans(drs_tick* t, const drs_plan_batch* b, const dr
   pv.n_veh = nv;
   pv.perm = (int32_t*)(vb + o_perm); pv.inv = (int32_t*)(vb + o_inv); pv.node = (int32_t*)(vb + o_node); pv.onboard = (int32_t*)(vb + o_onb);
   pv.cap = (int32_t*)(vb + o_cap); pv.len = (int32_t*)(vb + o_len); pv.delay = (double*)(vb + o_delay); pv.clock = (double*)(vb + o_clock);
-  pv.cost = (double*)(vb + o_cost); pv.pos_node = (int32_t*)(vb + o_pos); pv.keep_node = (int32_t*)(vb + o_kn); pv.keep_t = (double*)(vb + o_kt);
+  pv.cost = (double*)(vb + o_cost); pv.pos_node = (int32_t*)(vb + o_pos); pv.keep_node = (int32_t*)(vb + o_kn); pv.keep_pend = (int32_t*)(vb + o_kp); pv.keep_t = (double*)(vb + o_kt);
   pv.keep_et = (double*)(vb + o_ke); pv.m_node = (int32_t*)(vb + o_mnode); pv.m_req = (int32_t*)(vb + o_mreq); pv.m_pod = (int8_t*)(vb + o_mpod);
   pv.m_partner = (int8_t*)(vb + o_mpar); pv.m_seg = (double*)(vb + o_seg); pv.m_base_t = (double*)(vb + o_bt); pv.m_base_c = (double*)(vb + o_bc);
   pv.m_base_cld = (double*)(vb + o_bcld); pv.m_base_viol = (int32_t*)(vb + o_bv); pv.m_lb = (float*)(vb + o_lb); pv.m_nslots = (uint8_t*)(vb + o_ns);
