@@ -44,7 +44,8 @@ def test_our_arm_line_on_c1():
     assert d["insertion"]["value"] > 0 and d["insertion"]["roofline"]["bound"] == "hbm"
 
 
-@pytest.mark.parametrize("fname", ["r01_bench_c3_n1.json", "r01_bench_c3_n2.json", "r01_bench_c3_n4.json", "r01_bench_c3_n8.json"])
+@pytest.mark.parametrize("fname", ["r02_bench_c3_n1.json", "r02_bench_c3_n2.json", "r02_bench_c3_n4.json", "r02_bench_c3_n8.json",
+                                   "r01_bench_c3_n1.json", "r01_bench_c3_n2.json", "r01_bench_c3_n4.json", "r01_bench_c3_n8.json"])
 def test_committed_bench_lines_keep_the_contract(fname):
     """The bench lines committed under profiles/ (measured on B200s) carry the contract's keys and are self-consistent."""
     d = json.load(open(os.path.join(ROOT, "profiles", fname)))
@@ -59,3 +60,12 @@ def test_committed_bench_lines_keep_the_contract(fname):
     assert d["fw"]["same_matrix_as_headline"] is True and d["checksum"] == 12082473595208.0
     if d["n_gpus"] == 1:
         assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"]) and r["traffic"] > 0
+    if fname.startswith("r02"):
+        # round 2: config C5 at every N, sources sharded; at N = 1 the query latencies, the sequential queue and the CPU legs
+        assert d["sssp_c5"]["n_gpus"] == d["n_gpus"] and d["sssp_c5"]["matches_scipy_dijkstra"] is True
+        if d["n_gpus"] == 1:
+            assert d["query_latency"]["device_allocations_during_the_calls"] == 0
+            assert d["insertion"]["roofline"]["frac"] >= 0.6
+            q = d["insertion"]["sequential_queue"]
+            assert q["with_cld_side_effects"]["assigned"] == q["winners_only"]["assigned"] > 0
+            assert d["sim"]["cpu_baseline"]["same_objective_on_every_compared_tick"] is True
