@@ -36,6 +36,7 @@ _vp = C.c_void_p
 _i8p = C.POINTER(C.c_int8)
 _u8p = C.POINTER(C.c_uint8)
 _i64p = C.POINTER(C.c_int64)
+_u64p = C.POINTER(C.c_uint64)
 
 
 class VehicleBatch(C.Structure):
@@ -126,6 +127,8 @@ SIGNATURES = {
     "drs_tick_last_insertion_ms": (C.c_int, [_vp, _f64p]),
     "drs_tick_trip_eval": (C.c_int, [_vp, C.c_double, C.c_int32, C.c_int32, _i32p, _i32p, _i32p, _f64p, _u8p,
                                      _i32p]),
+    "drs_rtv_level": (C.c_int, [C.c_int32, C.c_int32, _i32p, _i32p, _u8p, C.c_int32, _u64p, C.c_int64, _i32p, _i32p,
+                                _i64p, _i64p]),
 }
 
 

@@ -62,9 +62,9 @@ def great_circle_distance(olat, olng, dlat, dlng):
         (math.cos((olat + dlat) * math.pi / 360) * (olng - dlng)) ** 2 + (olat - dlat) ** 2))
 
 
-def rr_prefilter(new_reqs, T):
+def rr_prefilter_pairs(new_reqs, T):
     """Pairs (a < b) of new requests that pass the crow-flies pre-filter of lib/Optimization.py:148-151:
-    ``T + greatCircleDistance(o1, o2) / CST_SPEED <= Clp`` of BOTH requests.
+    ``T + greatCircleDistance(o1, o2) / CST_SPEED <= Clp`` of BOTH requests, as an int32 array [m, 2] in lexicographic order.
 
     The reference evaluates the formula pair by pair in Python floats; here all R^2 pairs are screened at once with numpy
     and only the pairs within a relative 1e-9 of the threshold (where a last-bit difference between numpy's and libm's
@@ -72,11 +72,11 @@ def rr_prefilter(new_reqs, T):
     (2*10^6 calls at BASELINE config C4)."""
     nr = len(new_reqs)
     if nr < 2:
-        return []
+        return np.zeros((0, 2), dtype=np.int32)
     olat = np.array([float(r.olat) for r in new_reqs], dtype=np.float64)
     olng = np.array([float(r.olng) for r in new_reqs], dtype=np.float64)
     clp = np.array([float(r.Clp) for r in new_reqs], dtype=np.float64)
-    out = []
+    out_a, out_b = [], []
     step = max(1, (1 << 22) // nr)                          # ~4M pairs per block
     for a0 in range(0, nr, step):
         a1 = min(nr, a0 + step)
@@ -90,15 +90,26 @@ def rr_prefilter(new_reqs, T):
         sure = (margin <= -1e-9 * np.maximum(1.0, np.abs(lim))) & upper
         close = (np.abs(margin) < 1e-9 * np.maximum(1.0, np.abs(lim))) & upper
         aa, bb = np.nonzero(sure)
-        keep = list(zip((aa + a0).tolist(), bb.tolist()))
+        out_a.append(aa + a0)
+        out_b.append(bb)
+        ca, cb = [], []
         for a, b in zip(*np.nonzero(close)):
             r1, r2 = new_reqs[a + a0], new_reqs[b]
             t = T + great_circle_distance(r1.olat, r1.olng, r2.olat, r2.olng) / CST_SPEED
             if not (t > r1.Clp or t > r2.Clp):
-                keep.append((int(a + a0), int(b)))
-        out.extend(keep)
-    out.sort()
-    return out
+                ca.append(int(a + a0))
+                cb.append(int(b))
+        out_a.append(np.array(ca, dtype=np.int64))
+        out_b.append(np.array(cb, dtype=np.int64))
+    a = np.concatenate(out_a)
+    b = np.concatenate(out_b)
+    o = np.lexsort((b, a))
+    return np.stack([a[o], b[o]], axis=1).astype(np.int32)
+
+
+def rr_prefilter(new_reqs, T):
+    """rr_prefilter_pairs as a list of (a, b) tuples."""
+    return [(int(a), int(b)) for a, b in rr_prefilter_pairs(new_reqs, T)]
 
 
 class Tick(object):
@@ -195,8 +206,9 @@ class Tick(object):
             pass
 
     # ------------------------------------------------------------------ kernels
-    def rv_eval(self):
-        """RV stage.  Returns (edges, counters): edges = list of (veh_index, req_index, cost, order)."""
+    def rv_eval_arrays(self):
+        """RV stage.  Returns (veh_idx, req_idx, cost, order [n, MAX_STOPS], n_stops, counters): the feasible
+        (vehicle, request) edges as arrays, sorted by (request, vehicle)."""
         n_edges = C.c_int32(0)
         counters = np.zeros(4, dtype=np.int64)
         _lib.check(self.lib.drs_tick_rv_eval(self.handle, float(self.T), self.flags, C.byref(n_edges),
@@ -208,9 +220,37 @@ class Tick(object):
         ns = np.empty(ne, dtype=np.int32)
         _lib.check(self.lib.drs_tick_rv_fetch(self.handle, ne, _lib.ptr_i32(vi), _lib.ptr_i32(ri), _lib.ptr_f64(cost),
                                               order.ctypes.data_as(_u8p), _lib.ptr_i32(ns)), self.lib)
-        edges = [(int(vi[e]), int(ri[e]), float(cost[e]), [int(x) for x in order[e, :ns[e]]]) for e in range(ne)]
-        return edges, {"feasible": int(counters[0]), "skipped": int(counters[1]), "saved": int(counters[2]),
-                       "infeasible": int(counters[3])}
+        return vi, ri, cost, order, ns, {"feasible": int(counters[0]), "skipped": int(counters[1]),
+                                         "saved": int(counters[2]), "infeasible": int(counters[3])}
+
+    def rv_eval(self):
+        """RV stage.  Returns (edges, counters): edges = list of (veh_index, req_index, cost, order)."""
+        vi, ri, cost, order, ns, counters = self.rv_eval_arrays()
+        edges = [(int(vi[e]), int(ri[e]), float(cost[e]), [int(x) for x in order[e, :ns[e]]]) for e in range(len(vi))]
+        return edges, counters
+
+    def trip_eval_arrays(self, task_veh, task_req):
+        """task_veh [n] (vehicle index or -1), task_req [n, k] (request indices; k <= MAX_TRIP_REQS, every task of one
+        size).  Returns (cost [n], order [n, MAX_STOPS] uint8, n_stops [n]); cost == INF_ROUTE_COST: infeasible."""
+        tv = _lib.as_i32(task_veh)
+        nt = len(tv)
+        members = np.asarray(task_req, dtype=np.int32)
+        members = members.reshape(nt, -1) if nt else members.reshape(0, members.shape[1] if members.ndim == 2 else 1)
+        k = members.shape[1]
+        if k > MAX_TRIP_REQS:
+            raise ValueError("a trip holds at most %d new requests" % MAX_TRIP_REQS)
+        cost = np.empty(nt, dtype=np.float64)
+        order = np.empty((nt, MAX_STOPS), dtype=np.uint8)
+        ns = np.empty(nt, dtype=np.int32)
+        if nt == 0:
+            return cost, order, ns
+        tr = np.zeros((nt, MAX_TRIP_REQS), dtype=np.int32)
+        tr[:, :k] = members
+        tn = np.full(nt, k, dtype=np.int32)
+        _lib.check(self.lib.drs_tick_trip_eval(self.handle, float(self.T), self.flags, nt, _lib.ptr_i32(tv),
+                                               _lib.ptr_i32(tn), _lib.ptr_i32(tr), _lib.ptr_f64(cost),
+                                               order.ctypes.data_as(_u8p), _lib.ptr_i32(ns)), self.lib)
+        return cost, order, ns
 
     def trip_eval(self, tasks):
         """tasks: list of (veh_index or -1, [request indices]).  Returns list of (cost, order or None)."""
@@ -252,11 +292,98 @@ class Tick(object):
         return [stops[i] for i in order]
 
 
-class _Listing(object):
-    """len()-able stand-in for the igraph graphs the reference passes between stages."""
+class _Sized(object):
+    """len()-able stand-in for an igraph vertex / edge sequence that nobody iterates."""
 
-    def __init__(self, vs, es):
-        self.vs, self.es = vs, es
+    def __init__(self, n):
+        self.n = int(n)
+
+    def __len__(self):
+        return self.n
+
+
+class _Trips(object):
+    """Feasible trips of one size as arrays: veh [n] (vehicle index, -1 for request-request edges), members [n, k]
+    (request indices, ascending), cost [n], order [n, MAX_STOPS] / ns [n] (the optimal stop sequence in the kernel's
+    numbering, see Tick.route_of)."""
+
+    def __init__(self, veh, members, cost, order, ns):
+        self.veh, self.members, self.cost, self.order, self.ns = veh, members, cost, order, ns
+        self.k = members.shape[1]
+
+    def __len__(self):
+        return len(self.veh)
+
+    def take(self, sel):
+        return _Trips(self.veh[sel], self.members[sel], self.cost[sel], self.order[sel], self.ns[sel])
+
+    def route(self, tick, e):
+        return tick.route_of(int(self.veh[e]), [int(x) for x in self.members[e]], [int(x) for x in self.order[e, :self.ns[e]]])
+
+
+class _RVGraph(object):
+    """What generatePairwiseGraph hands to generateRTVGraph (an igraph Graph in the reference): .vs / .es for len(),
+    the edges as arrays (rr_edges, rv_edges) and, built on first use, as the dicts .rr {(a, b): (cost, route)} and
+    .rv {(veh index, request index): (cost, route)}."""
+
+    def __init__(self, tick, rr_edges, rv_edges, counters):
+        self.tick, self.rr_edges, self.rv_edges, self.counters = tick, rr_edges, rv_edges, counters
+        self.vs = _Sized(len(tick.new_reqs) + len(tick.vehs))
+        self.es = _Sized(len(rr_edges) + len(rv_edges))
+        nr = len(tick.new_reqs)
+        self.rr_ok = np.zeros((nr, nr), dtype=bool)
+        if len(rr_edges):
+            a, b = rr_edges.members[:, 0], rr_edges.members[:, 1]
+            self.rr_ok[a, b] = True
+            self.rr_ok[b, a] = True
+        self._rr = self._rv = None
+
+    @property
+    def rr(self):
+        if self._rr is None:
+            E = self.rr_edges
+            self._rr = {(int(E.members[e, 0]), int(E.members[e, 1])): (float(E.cost[e]), E.route(self.tick, e)) for e in range(len(E))}
+        return self._rr
+
+    @property
+    def rv(self):
+        if self._rv is None:
+            E = self.rv_edges
+            self._rv = {(int(E.veh[e]), int(E.members[e, 0])): (float(E.cost[e]), E.route(self.tick, e)) for e in range(len(E))}
+        return self._rv
+
+
+class _RTVGraph(object):
+    """What generateRTVGraph hands to assignFromRTVGraph: the feasible (vehicle, trip) edges level by level (size 1, 2,
+    ...), each level ordered by vehicle and, within a vehicle, in the order the reference creates the trips."""
+
+    def __init__(self, rv_graph, levels):
+        self.tick, self.levels, self.objective = rv_graph.tick, levels, None
+        nr = len(self.tick.new_reqs)
+        n_trips = 0
+        for L in levels:                                     # distinct request sets = the reference's trip vertices
+            if len(L) == 0:
+                continue
+            if nr < 65536:
+                key = np.zeros(len(L), dtype=np.int64)
+                for i in range(L.k):
+                    key |= L.members[:, i].astype(np.int64) << (16 * i)
+                n_trips += len(np.unique(key))
+            else:
+                n_trips += len(np.unique(L.members, axis=0))
+        self.vs = _Sized(len(rv_graph.vs) + n_trips)
+        self.es = _Sized(sum(len(L) for L in levels))
+        self._veh_trips = None
+
+    @property
+    def veh_trips(self):
+        """{(veh index, trip tuple): (cost, route)} (built on first use; the assignment works on the arrays)."""
+        if self._veh_trips is None:
+            self._veh_trips = {}
+            for L in self.levels:
+                for e in range(len(L)):
+                    self._veh_trips[(int(L.veh[e]), tuple(int(x) for x in L.members[e]))] = (float(L.cost[e]), L.route(self.tick, e))
+        return self._veh_trips
 
 
 class AssignmentMethod():
@@ -332,137 +459,112 @@ class AlonsoMora(VehReqMatchingAssignment):
     # ------------------------------------------------------------------ RV graph
     def generatePairwiseGraph(self, vehs, reqs, G, T=0):
         """lib/Optimization.py:104-225.  Returns an object with .vs / .es (for len()) carrying the
-        request-request and request-vehicle edges."""
+        request-request and request-vehicle edges (arrays; dict views .rr / .rv on demand)."""
         tick = Tick(G, vehs, reqs, T, pairwise_checks=(self.parameters["routing_method"] == "enumerate"))
-        nr = len(tick.new_reqs)
         # ---- R x R (lib/Optimization.py:142-165): crow-flies pre-filter on the host, costing on the GPU
-        rr_tasks = [(-1, [int(a), int(b)]) for a, b in rr_prefilter(tick.new_reqs, T)]
-        rr = {}
-        feas = inf = 0
-        for (task, (cost, order)) in zip(rr_tasks, tick.trip_eval(rr_tasks)):
-            if order is not None:
-                a, b = task[1]
-                rr[(a, b)] = (cost, tick.route_of(-1, [a, b], order))
-                feas += 1
-            else:
-                inf += 1
-        self._print("    Feasible pairings found amongst requests: {}".format(feas))
-        self._print("    Infeasible pairings evaluated: {}".format(inf))
+        pairs = rr_prefilter_pairs(tick.new_reqs, T)
+        cost, order, ns = tick.trip_eval_arrays(np.full(len(pairs), -1, dtype=np.int32), pairs)
+        ok = cost < INF_ROUTE_COST
+        rr_edges = _Trips(np.full(int(ok.sum()), -1, dtype=np.int32), pairs[ok], cost[ok], order[ok], ns[ok])
+        self._print("    Feasible pairings found amongst requests: {}".format(int(ok.sum())))
+        self._print("    Infeasible pairings evaluated: {}".format(int(len(ok) - ok.sum())))
         # ---- R x V (lib/Optimization.py:176-218)
-        edges, counters = tick.rv_eval()
-        rv = {}
-        for (vi, ri, cost, order) in edges:
-            rv[(vi, ri)] = (cost, tick.route_of(vi, [ri], order))
+        vi, ri, cost, order, ns, counters = tick.rv_eval_arrays()
+        rv_edges = _Trips(vi, ri.reshape(-1, 1), cost, order, ns)
         self._print("    Feasible pairings found between requests and vehicles: {}".format(counters["feasible"]))
         self._print("    Infeasible pairings evaluated: {}".format(counters["infeasible"]))
         self._print("    Infeasible pairings skipped via dummy evaluation: {}".format(counters["saved"]))
         self._print("    Pairings skipped because vehicle was too far away: {}".format(counters["skipped"]))
-        g = _Listing(vs=list(tick.new_reqs) + list(tick.vehs), es=list(rr) + list(rv))
-        g.tick, g.rr, g.rv, g.counters = tick, rr, rv, counters
-        return g
+        return _RVGraph(tick, rr_edges, rv_edges, counters)
 
     # ------------------------------------------------------------------ RTV graph
+    def _next_level(self, tick, prev, k, veh_on, rr_bits):
+        """Candidate trips of size k for every vehicle (drs_rtv_level: lib/Optimization.py:265-347 on the host, native)."""
+        nv, nr = len(tick.vehs), len(tick.new_reqs)
+        key_off = np.zeros(nv + 1, dtype=np.int32)
+        np.cumsum(np.bincount(prev.veh, minlength=nv), out=key_off[1:])
+        key_req = np.ascontiguousarray(prev.members, dtype=np.int32)
+        on = None if veh_on is None else np.ascontiguousarray(veh_on, dtype=np.uint8)
+        cap = max(1024, 4 * len(prev))
+        while True:
+            tv = np.empty(cap, dtype=np.int32)
+            tr = np.empty((cap, k), dtype=np.int32)
+            n_tasks, n_saved = C.c_int64(0), C.c_int64(0)
+            _lib.check(tick.lib.drs_rtv_level(nv, k, _lib.ptr_i32(key_off), _lib.ptr_i32(key_req),
+                                              None if on is None else on.ctypes.data_as(_u8p), nr,
+                                              rr_bits.ctypes.data_as(_lib._u64p), cap, _lib.ptr_i32(tv), _lib.ptr_i32(tr),
+                                              C.byref(n_tasks), C.byref(n_saved)), tick.lib)
+            if n_tasks.value <= cap:
+                return tv[:n_tasks.value], tr[:n_tasks.value], n_saved.value
+            cap = n_tasks.value
+
     def generateRTVGraph(self, rvGraph, G, T=0):
-        """lib/Optimization.py:227-357.  Trips are keyed by tuples of request indices in RV-vertex
-        order; each level's candidates (all vehicles) are costed in one kernel launch."""
-        tick, rr, rv = rvGraph.tick, rvGraph.rr, rvGraph.rv
-        nv = len(tick.vehs)
-        veh_trips = {}                                        # (vi, trip tuple) -> (cost, route)
-        level = {}                                            # vi -> ordered list of trip tuples of the current size
-        for vi in range(nv):
-            level[vi] = []
-        for (vi, ri) in sorted(rv, key=lambda k: (k[0], k[1])):   # veh.neighbors(): ascending vertex id (:243-262)
-            veh_trips[(vi, (ri,))] = rv[(vi, ri)]
-            level[vi].append((ri,))
+        """lib/Optimization.py:227-357.  A level = the feasible trips of one size for the whole fleet: its candidates
+        come from one native enumeration pass (drs_rtv_level) and are costed in one kernel launch."""
+        tick = rvGraph.tick
+        nr = len(tick.new_reqs)
+        rv = rvGraph.rv_edges
+        # veh.neighbors(): ascending vertex id (:243-262)
+        levels = [rv.take(np.lexsort((rv.members[:, 0], rv.veh)))]
+        cap = tick._v["cap"]
+        max_size = cap if self.max_trip_size is None else np.minimum(cap, int(self.max_trip_size))
+        words = (nr + 63) // 64
+        padded = np.zeros((nr, words * 64), dtype=bool)
+        padded[:, :nr] = rvGraph.rr_ok
+        rr_bits = np.ascontiguousarray(np.packbits(padded, axis=1, bitorder="little")).view(np.uint64)
         feas = inf = saved = 0
-
-        def has_rr(a, b):
-            return ((a, b) if a < b else (b, a)) in rr
-
-        # trips of size two (:265-288)
-        tasks = []
-        for vi in range(nv):
-            if self.max_trip_size is not None and int(self.max_trip_size) < 2:
-                continue
-            singles = [t[0] for t in level[vi]]
-            for x in range(len(singles)):
-                for y in range(x + 1, len(singles)):
-                    if has_rr(singles[x], singles[y]):
-                        tasks.append((vi, [singles[x], singles[y]]))
-                    else:
-                        saved += 1
-        prev_level = level
-        level = {vi: [] for vi in range(nv)}
-        for (task, (cost, order)) in zip(tasks, tick.trip_eval(tasks)):
-            vi, members = task
-            if order is not None:
-                veh_trips[(vi, tuple(members))] = (cost, tick.route_of(vi, members, order))
-                level[vi].append(tuple(members))
-                feas += 1
-            else:
-                inf += 1
-        # trips of size three and more (:291-347)
-        k = 3
-        while any(level[vi] for vi in range(nv)):
-            tasks = []
-            for vi in range(nv):
-                if self._max_size(tick, vi) < k or not level[vi]:
-                    continue
-                keys = level[vi]
-                keysets = [frozenset(t) for t in keys]
-                tested = []
-                for t1 in keys:
-                    for t2 in keys:
-                        trip = frozenset(t1) | frozenset(t2)
-                        if len(trip) == k and trip not in tested:
-                            tested.append(trip)
-                            subsets_ok = all(sum(1 for ks in keysets if (trip - {r}) <= ks) == 1 for r in trip)
-                            if not subsets_ok:
-                                saved += 1
-                                break                          # the reference leaves the t2 loop here (:325-327)
-                            members = sorted(trip)
-                            if all(has_rr(a, b) for i, a in enumerate(members) for b in members[i + 1:]):
-                                tasks.append((vi, members))
-                            else:
-                                saved += 1
-            level = {vi: [] for vi in range(nv)}
-            for (task, (cost, order)) in zip(tasks, tick.trip_eval(tasks)):
-                vi, members = task
-                if order is not None:
-                    veh_trips[(vi, tuple(members))] = (cost, tick.route_of(vi, members, order))
-                    level[vi].append(tuple(members))
-                    feas += 1
-                else:
-                    inf += 1
+        k = 2
+        while len(levels[-1]):
+            prev = levels[-1]
+            if k == 2:                                        # trips of size two (:265-288)
+                if self.max_trip_size is not None and int(self.max_trip_size) < 2:
+                    break
+                veh_on = None
+            else:                                             # trips of size three and more (:291-347)
+                veh_on = max_size >= k
+                if not veh_on[prev.veh].any():
+                    break
+            tv, tr, sv = self._next_level(tick, prev, k, veh_on, rr_bits)
+            saved += sv
+            cost, order, ns = tick.trip_eval_arrays(tv, tr)
+            ok = cost < INF_ROUTE_COST
+            feas += int(ok.sum())
+            inf += int(len(ok) - ok.sum())
+            levels.append(_Trips(tv[ok], tr[ok], cost[ok], order[ok], ns[ok]))
             k += 1
         self._print("    Feasible trip assignments evaluated: {}".format(feas))
         self._print("    Infeasible trip assignments evaluated: {}".format(inf))
         self._print("    Infeasible trip evaluations skipped via incomplete subgraphs / previous trip length checks: {}".format(saved))
-        trips = sorted(set(t for (_, t) in veh_trips))
-        g = _Listing(vs=list(rvGraph.vs) + trips, es=list(veh_trips))
-        g.tick, g.veh_trips, g.objective = tick, veh_trips, None
-        return g
-
-    def _max_size(self, tick, vi):
-        cap = int(tick.vehs[vi].K)
-        return cap if self.max_trip_size is None else min(cap, int(self.max_trip_size))
+        return _RTVGraph(rvGraph, [L for L in levels if len(L)])
 
     # ------------------------------------------------------------------ assignment
     def assignFromRTVGraph(self, rtvGraph):
         """lib/Optimization.py:359-408: min sum cost*e + 1e6*sum x; one trip per vehicle; every request in
         exactly one chosen trip or ignored.  Returns (veh_routes {vid: route}, rejected {rid})."""
         tick = rtvGraph.tick
-        keys = sorted(rtvGraph.veh_trips, key=lambda k: (k[0], len(k[1]), k[1]))
         nreq = len(tick.new_reqs)
-        costs = np.array([rtvGraph.veh_trips[k][0] for k in keys], dtype=np.float64)
-        chosen, ignored, objective = solve_set_packing(len(tick.vehs), nreq, [(k[0], k[1]) for k in keys], costs)
+        L = rtvGraph.levels
+        veh = np.concatenate([l.veh for l in L]) if L else np.zeros(0, dtype=np.int32)
+        size = np.concatenate([np.full(len(l), l.k, dtype=np.int32) for l in L]) if L else np.zeros(0, dtype=np.int32)
+        members = np.full((len(veh), MAX_TRIP_REQS), -1, dtype=np.int32)
+        level_of = np.concatenate([np.full(len(l), i, dtype=np.int32) for i, l in enumerate(L)]) if L else np.zeros(0, dtype=np.int32)
+        pos_in = np.concatenate([np.arange(len(l), dtype=np.int64) for l in L]) if L else np.zeros(0, dtype=np.int64)
+        at = 0
+        for l in L:
+            members[at:at + len(l), :l.k] = l.members
+            at += len(l)
+        costs = np.concatenate([l.cost for l in L]) if L else np.zeros(0)
+        # the column order of the reference's model: by vehicle, then trip size, then members
+        o = np.lexsort(tuple(members[:, i] for i in range(MAX_TRIP_REQS - 1, -1, -1)) + (size, veh))
+        chosen, ignored, objective = _solve_packing_arrays(len(tick.vehs), nreq, veh[o], size[o], members[o], costs[o])
         if chosen is None:
             return None, None                                 # lib/Optimization.py:405-406
         rtvGraph.objective = objective
         veh_routes = dict()
         for idx in chosen:
-            vi, trip = keys[idx]
-            veh_routes[tick.vehs[vi].id] = rtvGraph.veh_trips[keys[idx]][1]
+            e = o[idx]
+            lv = L[level_of[e]]
+            veh_routes[tick.vehs[int(veh[e])].id] = lv.route(tick, int(pos_in[e]))
         rejected = set(int(tick.new_reqs[ri].id) for ri in ignored)
         return veh_routes, rejected
 
@@ -471,27 +573,41 @@ def solve_set_packing(nveh, nreq, trips, costs):
     """The ILP of lib/Optimization.py:359-408.  trips: list of (veh_index, tuple of request
     indices).  Returns (chosen trip indices, ignored request indices, objective)."""
     nt = len(trips)
+    veh = np.array([t[0] for t in trips], dtype=np.int32)
+    size = np.array([len(t[1]) for t in trips], dtype=np.int32)
+    members = np.full((nt, max([1] + [len(t[1]) for t in trips])), -1, dtype=np.int32)
+    for k, t in enumerate(trips):
+        members[k, :len(t[1])] = t[1]
+    return _solve_packing_arrays(nveh, nreq, veh, size, members, np.asarray(costs, dtype=np.float64))
+
+
+def _solve_packing_arrays(nveh, nreq, veh, size, members, costs):
+    """solve_set_packing on arrays: veh [nt], size [nt], members [nt, kmax] (-1 padded), costs [nt]."""
+    nt = len(veh)
     if nt == 0:
         return [], list(range(nreq)), COST_IGNORED * nreq
-    if all(len(t[1]) == 1 for t in trips):
+    if (size == 1).all():
         # rectangular assignment: serve request r by vehicle v at cost c, or ignore it at 1e6
         from scipy.optimize import linear_sum_assignment
         big = 4.0 * COST_IGNORED
         M = np.full((nreq, nveh + nreq), big)
         tid = -np.ones((nreq, nveh), dtype=np.int64)
-        for k, (vi, tr) in enumerate(trips):
-            if costs[k] < M[tr[0], vi]:
-                M[tr[0], vi] = costs[k]
-                tid[tr[0], vi] = k
-        for r in range(nreq):
-            M[r, nveh + r] = COST_IGNORED
+        r = members[:, 0]
+        first = np.lexsort((np.arange(nt), costs, veh, r))   # of several trips for one (r, v): the cheapest, then the first
+        keep = np.ones(nt, dtype=bool)
+        keep[1:] = (r[first][1:] != r[first][:-1]) | (veh[first][1:] != veh[first][:-1])
+        sel = first[keep]
+        sel = sel[costs[sel] < big]
+        M[r[sel], veh[sel]] = costs[sel]
+        tid[r[sel], veh[sel]] = sel
+        M[np.arange(nreq), nveh + np.arange(nreq)] = COST_IGNORED
         rows, cols = linear_sum_assignment(M)
         chosen, ignored = [], []
-        for r, c in zip(rows, cols):
-            if c < nveh and tid[r, c] >= 0:
-                chosen.append(int(tid[r, c]))
+        for rr_, c in zip(rows, cols):
+            if c < nveh and tid[rr_, c] >= 0:
+                chosen.append(int(tid[rr_, c]))
             else:
-                ignored.append(int(r))
+                ignored.append(int(rr_))
         obj = float(sum(costs[k] for k in chosen) + COST_IGNORED * len(ignored))
         return sorted(chosen), sorted(ignored), obj
     from scipy.optimize import milp, LinearConstraint, Bounds
@@ -501,15 +617,16 @@ def solve_set_packing(nveh, nreq, trips, costs):
     lo = np.concatenate([np.full(nveh, -np.inf), np.ones(nreq)])
     hi = np.ones(nveh + nreq)
     # rows 0..nveh-1: one trip per vehicle; rows nveh..: each request in exactly one chosen trip or ignored
-    rows = [t[0] for t in trips] + [nveh + r for t in trips for r in t[1]] + [nveh + r for r in range(nreq)]
-    cols = list(range(nt)) + [k for k, t in enumerate(trips) for _ in t[1]] + [nt + r for r in range(nreq)]
+    tk, mk = np.nonzero(members >= 0)
+    rows = np.concatenate([veh.astype(np.int64), nveh + members[tk, mk].astype(np.int64), nveh + np.arange(nreq, dtype=np.int64)])
+    cols = np.concatenate([np.arange(nt, dtype=np.int64), tk.astype(np.int64), nt + np.arange(nreq, dtype=np.int64)])
     A = csr_matrix((np.ones(len(rows)), (rows, cols)), shape=(nveh + nreq, nvar))
     res = milp(c, constraints=LinearConstraint(A, lo, hi), integrality=np.ones(nvar), bounds=Bounds(0, 1))
     if res.status != 0:
         return None, None, None
     x = np.round(res.x).astype(np.int64)
-    chosen = [k for k in range(nt) if x[k] > 0]
-    ignored = [r for r in range(nreq) if x[nt + r] > 0]
+    chosen = [int(k) for k in np.nonzero(x[:nt] > 0)[0]]
+    ignored = [int(r) for r in np.nonzero(x[nt:] > 0)[0]]
     return chosen, ignored, float(res.fun)
 
 

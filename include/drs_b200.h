@@ -308,6 +308,21 @@ int drs_tick_trip_eval(drs_tick* t, double T, int32_t flags, int32_t n_tasks, co
                        const int32_t* task_nreq, const int32_t* task_req, double* cost_host,
                        uint8_t* order_host, int32_t* n_stops_host);
 
+/* One level of the RTV trip enumeration for the whole fleet, on the HOST (set logic only; the candidates are then costed
+ * by drs_tick_trip_eval).  Replaces the per-vehicle loops of AlonsoMora.generateRTVGraph, lib/Optimization.py:265-288
+ * (k = 2) and :291-347 (k >= 3), including the order in which candidates appear and the reference's early exit from the
+ * inner loop when a (k-1)-subset of a union is not a trip of the vehicle (:325-327).
+ *   key_off[n_veh + 1], key_req[n_keys * (k-1)]: every vehicle's feasible trips of size k-1 in the order the reference
+ *     holds them (members ascending within a trip); veh_on[n_veh] (may be NULL = all): vehicles to enumerate for;
+ *   rr_bits: the request-request graph as n_req rows of ceil(n_req / 64) 64-bit words (bit b of row a: a and b share
+ *     an edge; symmetric).
+ * Writes the first cap_tasks candidates (vehicle index, k members ascending) and always returns the full count in
+ * *n_tasks (call again with a larger buffer if it exceeds cap_tasks); *n_saved = candidates the reference counts as
+ * "skipped via incomplete subgraphs / previous trip length checks". */
+int drs_rtv_level(int32_t n_veh, int32_t k, const int32_t* key_off, const int32_t* key_req, const uint8_t* veh_on,
+                  int32_t n_req, const uint64_t* rr_bits, int64_t cap_tasks, int32_t* task_veh, int32_t* task_req,
+                  int64_t* n_tasks, int64_t* n_saved);
+
 /* ------------------------------------------------------ legacy insertion --
  * The (vehicle, pickup slot, drop-off slot) insertion heuristic: replaces
  * Model.insert_heuristics / test_constraints_get_cost (lib/Agents.py:1451-1572;

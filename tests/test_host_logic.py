@@ -245,3 +245,94 @@ def test_native_locality_order_equals_the_numpy_one():
     rs = np.random.RandomState(0)
     x, y = rs.rand(3000).round(2), rs.rand(3000).round(2)          # irregular coordinates with many duplicates
     assert np.array_equal(locality_order(3000, [], [], x, y, native=True), locality_order(3000, [], [], x, y, native=False))
+
+
+def _reference_rtv_level(keys_by_veh, k, rr, on):
+    """The loops of lib/Optimization.py:265-288 (k = 2) and :291-347 (k >= 3), restated literally for one level."""
+    tasks, saved = [], 0
+
+    def has_rr(a, b):
+        return ((a, b) if a < b else (b, a)) in rr
+    for vi, keys in enumerate(keys_by_veh):
+        if not keys or not on[vi]:
+            continue
+        if k == 2:
+            singles = [t[0] for t in keys]
+            for x in range(len(singles)):
+                for y in range(x + 1, len(singles)):
+                    if has_rr(singles[x], singles[y]):
+                        tasks.append((vi, (singles[x], singles[y])))
+                    else:
+                        saved += 1
+            continue
+        keysets = [frozenset(t) for t in keys]
+        tested = []
+        for t1 in keys:
+            for t2 in keys:
+                trip = frozenset(t1) | frozenset(t2)
+                if len(trip) == k and trip not in tested:
+                    tested.append(trip)
+                    if not all(sum(1 for ks in keysets if (trip - {r}) <= ks) == 1 for r in trip):
+                        saved += 1
+                        break
+                    members = sorted(trip)
+                    if all(has_rr(a, b) for i, a in enumerate(members) for b in members[i + 1:]):
+                        tasks.append((vi, tuple(members)))
+                    else:
+                        saved += 1
+    return tasks, saved
+
+
+@pytest.mark.parametrize("k", [2, 3, 4])
+def test_native_rtv_level_equals_the_references_loops(k):
+    """drs_rtv_level (host-only entry point of the library) against the reference's per-vehicle set loops, including the
+    order of the candidates and the early exit of the inner loop (lib/Optimization.py:325-327)."""
+    import ctypes as C
+    import itertools
+    from drs_abm_b200 import _lib
+    lib = _lib.load()
+    rs = np.random.RandomState(100 + k)
+    for trial in range(12):
+        nr, nv = int(rs.randint(3, 70)), int(rs.randint(1, 9))
+        dense = rs.rand() < 0.5
+        rr = set()
+        for a in range(nr):
+            for b in range(a + 1, nr):
+                if rs.rand() < (0.8 if dense else 0.3):
+                    rr.add((a, b))
+        keys_by_veh = []
+        for v in range(nv):
+            pool = sorted(rs.choice(nr, size=min(nr, int(rs.randint(0, 9))), replace=False).tolist())
+            combos = [c for c in itertools.combinations(pool, k - 1)]
+            if k > 2:
+                combos = [c for c in combos if rs.rand() < 0.75]
+                order = rs.permutation(len(combos))          # higher levels are NOT held in sorted order by the reference
+                combos = [combos[i] for i in order]
+            keys_by_veh.append(combos)
+        on = rs.rand(nv) < 0.85
+        want, want_saved = _reference_rtv_level(keys_by_veh, k, rr, on)
+        key_off = np.zeros(nv + 1, dtype=np.int32)
+        key_off[1:] = np.cumsum([len(x) for x in keys_by_veh])
+        key_req = np.array([m for keys in keys_by_veh for t in keys for m in t], dtype=np.int32).reshape(-1, k - 1)
+        words = (nr + 63) // 64
+        bits = np.zeros((nr, words * 64), dtype=bool)
+        for a, b in rr:
+            bits[a, b] = bits[b, a] = True
+        rr_bits = np.ascontiguousarray(np.packbits(bits, axis=1, bitorder="little")).view(np.uint64)
+        on8 = on.astype(np.uint8)
+        for cap in (0, max(1, len(want) // 2), len(want) + 3):
+            tv = np.full(max(cap, 1), -7, dtype=np.int32)
+            tr = np.full((max(cap, 1), k), -7, dtype=np.int32)
+            n_tasks, n_saved = C.c_int64(-1), C.c_int64(-1)
+            rc = lib.drs_rtv_level(nv, k, _lib.ptr_i32(key_off), _lib.ptr_i32(key_req), on8.ctypes.data_as(_lib._u8p), nr,
+                                   rr_bits.ctypes.data_as(_lib._u64p), cap, _lib.ptr_i32(tv), _lib.ptr_i32(tr),
+                                   C.byref(n_tasks), C.byref(n_saved))
+            assert rc == 0
+            assert n_tasks.value == len(want) and n_saved.value == want_saved
+            got = [(int(tv[i]), tuple(int(x) for x in tr[i])) for i in range(min(cap, len(want)))]
+            assert got == want[:min(cap, len(want))]
+    # more members than a trip may hold
+    n_tasks, n_saved = C.c_int64(0), C.c_int64(0)
+    z = np.zeros(2, dtype=np.int32)
+    assert lib.drs_rtv_level(1, 5, _lib.ptr_i32(z), _lib.ptr_i32(z), None, 0, None, 0, None, None,
+                             C.byref(n_tasks), C.byref(n_saved)) == _lib.ERR_CAPACITY
