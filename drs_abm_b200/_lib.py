@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("DRS_B200_LIB") or os.path.join(_HERE, "libdrs_b200.so
 MODE_F32 = 0
 MODE_I32 = 1
 FW_TILE = 128
-APSP_FW, APSP_SSSP, APSP_AUTO = 0, 1, 2
+APSP_FW, APSP_SSSP, APSP_AUTO, APSP_SEP = 0, 1, 2, 3
 PRED_LAZY, PRED_MATRIX = 0, 1
 I32_INF = 0x3FFFFFFF
 
@@ -109,6 +109,11 @@ SIGNATURES = {
     "drs_sssp_batch_dev": (C.c_int, [_vp, C.c_int32, C.c_int32, _i32p, _vp, C.c_int64, C.c_double, _vp]),
     "drs_sssp_batch": (C.c_int, [_vp, C.c_int32, C.c_int32, _i32p, _f64p]),
     "drs_apsp_rows_sssp": (C.c_int, [_vp, C.c_int32, _vp, C.c_int64, C.c_int32, C.c_int32, C.c_double, _vp]),
+    "drs_partition_order": (C.c_int, [C.c_int32, C.c_int32, _i32p, _i32p, _f64p, _f64p, C.c_int32, _i32p, _i32p, C.c_int32, _i32p]),
+    "drs_graph_set_partition": (C.c_int, [_vp, C.c_int32, _i32p]),
+    "drs_sep_info": (C.c_int, [_vp, _i32p, _i32p, _i32p, _i32p, _i32p]),
+    "drs_apsp_rows_sep": (C.c_int, [_vp, C.c_int32, _vp, C.c_int64, C.c_int32, C.c_int32, _vp]),
+    "drs_apsp_sep_profile": (C.c_int, [_vp, _f64p]),
     "drs_launch_count": (C.c_int64, []),
     "drs_tick_last_ms": (C.c_int, [_vp, _f64p]),
     "drs_apsp_last_profile": (C.c_int, [_vp, _f64p, _i32p]),

@@ -82,6 +82,10 @@ class CudaTiles(object):
         _lib.check(self.lib.drs_apsp_rows_sssp(self.g, self.mode, C.c_void_p(local.data_ptr()), local.shape[1], row0,
                                                local.shape[0], 0.0, self._stream()), self.lib)
 
+    def sep_rows(self, local, row0):
+        _lib.check(self.lib.drs_apsp_rows_sep(self.g, self.mode, C.c_void_p(local.data_ptr()), local.shape[1], row0,
+                                              local.shape[0], self._stream()), self.lib)
+
     def pred(self, local, row0, out):
         _lib.check(self.lib.drs_pred_build(self.g, self.mode, C.c_void_p(local.data_ptr()), local.shape[1], row0,
                                            local.shape[0], C.c_void_p(out.data_ptr()), self._stream()), self.lib)
@@ -246,6 +250,8 @@ def build_sharded(tiles, npad, rank=0, world=1, dist=None, lookahead=True, with_
     algorithm "fw": blocked Floyd-Warshall with pivot-panel broadcasts (below).
     algorithm "sssp": every rank runs the delta-stepping searches of its own source rows;
     sources are independent, so there is no collective at all.
+    algorithm "sep": the separator-partitioned build (csrc/sep_apsp.cu): every rank closes the parts and the separator
+    graph (a few ms, replicated) and expands its own rows; no collective either.
 
     Returns (local, pred_local, row0): this rank's rows of the distance and
     predecessor matrices and the global index of its first row.
@@ -255,8 +261,11 @@ def build_sharded(tiles, npad, rank=0, world=1, dist=None, lookahead=True, with_
     b0, b1 = starts[rank], starts[rank + 1]
     row0 = b0 * TILE
     local = tiles.empty((b1 - b0) * TILE, npad)
-    if algorithm == "sssp":
-        tiles.sssp_rows(local, row0)
+    if algorithm in ("sssp", "sep"):
+        if algorithm == "sep":
+            tiles.sep_rows(local, row0)
+        else:
+            tiles.sssp_rows(local, row0)
         pred_local = None
         if with_pred:
             pred_local = tiles.empty_pred((b1 - b0) * TILE, npad)

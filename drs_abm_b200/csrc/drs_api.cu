@@ -221,6 +221,7 @@ extern "C" int drs_graph_destroy(drs_graph* g) {
   if (!g) return DRS_OK;
   DrsDeviceGuard guard(g->device);
   free_matrices(g);
+  drs_sep_free(g);
   if (g->d_arena) cudaFree(g->d_arena);
   if (g->sssp_queues) cudaFree(g->sssp_queues);
   if (g->sssp_arcs) cudaFree(g->sssp_arcs);
@@ -267,10 +268,14 @@ extern "C" int drs_apsp_build(drs_graph* g, int32_t mode) {
   const int nb = g->npad / DRS_FW_TILE;
   cudaStream_t st = g->stream;
   int algo = g->algorithm;
-  if (algo == DRS_APSP_AUTO) algo = (g->narcs <= 16 * (int64_t)g->n) ? DRS_APSP_SSSP : DRS_APSP_FW;
+  if (algo == DRS_APSP_AUTO)
+    algo = drs_sep_usable(g) ? DRS_APSP_SEP : (g->narcs <= 16 * (int64_t)g->n) ? DRS_APSP_SSSP : DRS_APSP_FW;
+  if (algo == DRS_APSP_SEP)
+    DRS_REQUIRE(g->sep && g->weights_integral, DRS_ERR_STATE,
+                "drs_apsp_build: DRS_APSP_SEP needs a partition (drs_graph_set_partition) and integer travel times below 1e6");
   // events: [0] start, [1] after init, then per round (after pivot row, after update), last after pred;
   // the SSSP build is one "round" booked under "update"
-  const int ner = (algo == DRS_APSP_SSSP) ? 1 : nb;
+  const int ner = (algo == DRS_APSP_SSSP || algo == DRS_APSP_SEP) ? 1 : nb;
   std::vector<cudaEvent_t> ev(3 + 2 * ner);
   for (auto& e : ev) DRS_CUDA(cudaEventCreate(&e));
   auto release = [&]() { for (auto& e : ev) cudaEventDestroy(e); };
@@ -279,6 +284,11 @@ extern "C" int drs_apsp_build(drs_graph* g, int32_t mode) {
     DRS_CUDA(cudaEventRecord(ev[1], st));
     DRS_CUDA(cudaEventRecord(ev[2], st));
     if ((rc = drs_apsp_rows_sssp(g, mode, g->d_dist, ld, 0, g->npad, 0.0, st))) { release(); return rc; }
+    DRS_CUDA(cudaEventRecord(ev[3], st));
+  } else if (algo == DRS_APSP_SEP) {
+    DRS_CUDA(cudaEventRecord(ev[1], st));
+    DRS_CUDA(cudaEventRecord(ev[2], st));
+    if ((rc = drs_apsp_rows_sep(g, mode, g->d_dist, ld, 0, g->npad, st))) { release(); return rc; }
     DRS_CUDA(cudaEventRecord(ev[3], st));
   } else {
   if ((rc = drs_fw_init(g, mode, g->d_dist, ld, 0, g->npad, st))) { release(); return rc; }
@@ -310,7 +320,7 @@ extern "C" int drs_apsp_build(drs_graph* g, int32_t mode) {
 
 extern "C" int drs_apsp_set_algorithm(drs_graph* g, int32_t algorithm) {
   DRS_REQUIRE(g, DRS_ERR_ARG, "drs_apsp_set_algorithm: null graph");
-  DRS_REQUIRE(algorithm == DRS_APSP_FW || algorithm == DRS_APSP_SSSP || algorithm == DRS_APSP_AUTO, DRS_ERR_ARG,
+  DRS_REQUIRE(algorithm == DRS_APSP_FW || algorithm == DRS_APSP_SSSP || algorithm == DRS_APSP_AUTO || algorithm == DRS_APSP_SEP, DRS_ERR_ARG,
               "drs_apsp_set_algorithm: unknown algorithm %d", algorithm);
   g->algorithm = algorithm;
   return DRS_OK;

@@ -30,6 +30,8 @@ void drs_count_alloc(int n = 1);   // every cudaMalloc of the library (drs_alloc
     }                                   \
   } while (0)
 
+struct drs_sep_plan;   // sep_apsp.cu: the part / separator tables and work arrays of the partitioned build
+
 // Host-side graph handle.  Device arrays live on `device`.
 struct drs_graph {
   int device = 0;
@@ -92,11 +94,15 @@ struct drs_graph {
   void* q_pin_dev = nullptr;   // its device alias
   size_t q_pin_cap = 0;
 
+  drs_sep_plan* sep = nullptr;   // set by drs_graph_set_partition
+
   double prof_ms[4] = {0, 0, 0, 0};   // last build, by phase (drs_apsp_last_profile)
   int prof_rounds = 0;
 };
 
 int drs_graph_upload_weights(drs_graph* g);
+void drs_sep_free(drs_graph* g);
+bool drs_sep_usable(const drs_graph* g);   // partition present, exact arithmetic, separators a small part of the map
 // DRS_MODE_F32 / DRS_MODE_I32 known, and I32 only on integer travel times below 1e6 (a float weight would be truncated)
 int drs_check_mode(const drs_graph* g, int mode, const char* who);
 

@@ -1,0 +1,244 @@
+// Min-plus 128x128 register-tile product shared by the blocked Floyd-Warshall (fw_kernels.cu) and the
+// separator-partitioned build (sep_apsp.cu).
+//
+// One CTA = 256 threads, an 8x8 accumulator tile per thread, A (128 x K) and B (K x 128) streamed through a 3-stage
+// cp.async ring in 32-wide k chunks.  fp32 runs on packed adds: one FADD2 + one 3-input FMNMX3 per two relaxations;
+// int32 on the DPX add-min (VIADDMNMX).  The work is ALU-bound (kernel K1).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "drs_b200.h"
+
+namespace mp {
+
+constexpr int TILE = DRS_FW_TILE;  // 128
+constexpr int KC = 32;             // k chunk streamed per pipeline stage
+constexpr int STAGES = 3;
+constexpr int APAD = KC + 4;       // padded row of the A chunk (keeps 16 B alignment)
+constexpr int NTHREADS = 256;
+
+template <typename T> struct Semiring;
+template <> struct Semiring<float> {
+  static constexpr bool packed = true;    // sm_100 packed fp32x2 add (FADD2) in the tile kernel
+  static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
+  // acc = min(acc, a0+b0, a1+b1): two FADD + one 3-input FMNMX3 (sm_100+)
+  static __device__ __forceinline__ float relax2(float acc, float a0, float b0, float a1, float b1) {
+    float d;
+    float s0 = a0 + b0, s1 = a1 + b1;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(acc), "f"(s0), "f"(s1));
+    return d;
+  }
+  static __device__ __forceinline__ float relax1(float acc, float a, float b) { return fminf(acc, a + b); }
+};
+template <> struct Semiring<int> {
+  static constexpr bool packed = false;
+  static __device__ __forceinline__ int inf() { return DRS_I32_INF; }
+  // VIADDMNMX: add and min in one DPX instruction
+  static __device__ __forceinline__ int relax2(int acc, int a0, int b0, int a1, int b1) {
+    return __viaddmin_s32(a1, b1, __viaddmin_s32(a0, b0, acc));
+  }
+  static __device__ __forceinline__ int relax1(int acc, int a, int b) { return __viaddmin_s32(a, b, acc); }
+};
+
+template <typename T> struct Vec4;
+template <> struct Vec4<float> { using type = float4; };
+template <> struct Vec4<int> { using type = int4; };
+template <typename T> struct Vec2;
+template <> struct Vec2<float> { using type = float2; };
+template <> struct Vec2<int> { using type = int2; };
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N));
+}
+
+constexpr size_t kTileSmemBytes = sizeof(float) * STAGES * (TILE * APAD + KC * TILE);
+
+// Tile coordinates of accumulator element acc[r][c] of thread (tx = tid & 15, ty = tid >> 4).
+// fp32 (packed): rows ty + 16 r, the four column pairs 32 j + 2 tx (keeps the k-pair-interleaved B loads conflict-free);
+// int32: rows ty + 16 r, columns 4 tx .. and 64 + 4 tx ..
+template <typename T> __device__ __forceinline__ int acc_row(int r, int ty) { return ty + 16 * r; }
+template <typename T> __device__ __forceinline__ int acc_col(int c, int tx) {
+  if (Semiring<T>::packed) return 32 * (c >> 1) + 2 * tx + (c & 1);
+  return (c < 4) ? tx * 4 + c : 64 + tx * 4 + (c - 4);
+}
+
+template <typename T> __device__ __forceinline__ void acc_fill(T (&acc)[8][8], T v) {
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[r][c] = v;
+}
+
+// Whole 128x128 tile at C (16-byte aligned, ldc a multiple of 4) into the accumulators.
+template <typename T> __device__ __forceinline__ void acc_load(T (&acc)[8][8], const T* C, int64_t ldc, int tid) {
+  using V4 = typename Vec4<T>::type;
+  using V2 = typename Vec2<T>::type;
+  const int tx = tid & 15, ty = tid >> 4;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const T* crow = C + (int64_t)(ty + 16 * r) * ldc;
+    if (Semiring<T>::packed) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const V2 v = *reinterpret_cast<const V2*>(crow + 32 * j + tx * 2);
+        acc[r][2 * j] = v.x; acc[r][2 * j + 1] = v.y;
+      }
+    } else {
+      V4 lo = *reinterpret_cast<const V4*>(crow + tx * 4);
+      V4 hi = *reinterpret_cast<const V4*>(crow + 64 + tx * 4);
+      acc[r][0] = lo.x; acc[r][1] = lo.y; acc[r][2] = lo.z; acc[r][3] = lo.w;
+      acc[r][4] = hi.x; acc[r][5] = hi.y; acc[r][6] = hi.z; acc[r][7] = hi.w;
+    }
+  }
+}
+
+// Accumulators to the tile at C; rows >= rows or columns >= cols are not written (edge tiles store element-wise).
+template <typename T> __device__ __forceinline__ void acc_store(const T (&acc)[8][8], T* C, int64_t ldc, int rows, int cols, int tid) {
+  using V4 = typename Vec4<T>::type;
+  using V2 = typename Vec2<T>::type;
+  const int tx = tid & 15, ty = tid >> 4;
+  if (rows >= TILE && cols >= TILE) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      T* crow = C + (int64_t)(ty + 16 * r) * ldc;
+      if (Semiring<T>::packed) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          V2 v; v.x = acc[r][2 * j]; v.y = acc[r][2 * j + 1];
+          *reinterpret_cast<V2*>(crow + 32 * j + tx * 2) = v;
+        }
+      } else {
+        V4 lo, hi;
+        lo.x = acc[r][0]; lo.y = acc[r][1]; lo.z = acc[r][2]; lo.w = acc[r][3];
+        hi.x = acc[r][4]; hi.y = acc[r][5]; hi.z = acc[r][6]; hi.w = acc[r][7];
+        *reinterpret_cast<V4*>(crow + tx * 4) = lo;
+        *reinterpret_cast<V4*>(crow + 64 + tx * 4) = hi;
+      }
+    }
+    return;
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int row = ty + 16 * r;
+    if (row >= rows) continue;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int col = acc_col<T>(c, tx);
+      if (col < cols) C[(int64_t)row * ldc + col] = acc[r][c];
+    }
+  }
+}
+
+// acc = min(acc, A (x) B) over nchunk 32-wide k chunks.  A: 128 rows x 32 nchunk (16-byte aligned rows), B: 32 nchunk rows
+// x 128 columns (16-byte aligned rows for int32, 4-byte for fp32).  smem_raw: kTileSmemBytes of dynamic shared memory.
+// Returns with every copy drained and every thread past its last shared-memory read, so the ring can be refilled at once
+// (the multi-pass tiles of the separator build call it once per pass).
+template <typename T>
+__device__ __forceinline__ void tile_accumulate(T (&acc)[8][8], const T* __restrict__ A, int64_t lda, const T* __restrict__ B,
+                                                int64_t ldb, int nchunk, unsigned char* smem_raw, int tid) {
+  using V4 = typename Vec4<T>::type;
+  using V2 = typename Vec2<T>::type;
+  T(*As)[TILE][APAD] = reinterpret_cast<T(*)[TILE][APAD]>(smem_raw);
+  T(*Bs)[KC][TILE] = reinterpret_cast<T(*)[KC][TILE]>(smem_raw + sizeof(T) * STAGES * TILE * APAD);
+  const int tx = tid & 15, ty = tid >> 4;
+  constexpr bool kPacked = Semiring<T>::packed;
+  if (nchunk <= 0) return;
+
+  auto load_chunk = [&](int kc, int stage) {
+    const int k0 = kc * KC;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {   // A chunk: 128 rows x 32 k
+      const int v = tid + NTHREADS * q;
+      const int row = v >> 3, cv = v & 7;
+      cp_async16(&As[stage][row][cv * 4], A + (int64_t)row * lda + k0 + cv * 4);
+    }
+    if (kPacked) {
+      // fp32: B is stored k-pair interleaved, Bs2[k/2][column] = (b[k][column], b[k+1][column]), so that one
+      // 8-byte shared load yields the operand pair of a packed add (FADD2) -- 4-byte cp.async, coalesced per row
+      float* Bf = reinterpret_cast<float*>(&Bs[stage][0][0]);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const int e = tid + NTHREADS * q;
+        const int row = e >> 7, col = e & 127;
+        cp_async4(Bf + ((row >> 1) * TILE + col) * 2 + (row & 1), B + (int64_t)(k0 + row) * ldb + col);
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {   // B chunk: 32 k x 128 columns
+        const int v = tid + NTHREADS * q;
+        const int row = v >> 5, cv = v & 31;
+        cp_async16(&Bs[stage][row][cv * 4], B + (int64_t)(k0 + row) * ldb + cv * 4);
+      }
+    }
+  };
+
+  load_chunk(0, 0);
+  cp_async_commit();
+  if (nchunk > 1) load_chunk(1, 1);
+  cp_async_commit();
+
+#pragma unroll 1
+  for (int kc = 0; kc < nchunk; ++kc) {
+    const int stage = kc % STAGES;
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    if (kc + STAGES - 1 < nchunk) load_chunk(kc + STAGES - 1, (kc + STAGES - 1) % STAGES);
+    cp_async_commit();
+
+    if (kPacked) {
+      const float2* Bp = reinterpret_cast<const float2*>(&Bs[stage][0][0]);
+#pragma unroll
+      for (int kk = 0; kk < KC; kk += 2) {
+        float2 a[8], b[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) a[r] = *reinterpret_cast<const float2*>(&As[stage][ty + 16 * r][kk]);
+        const float2* brow = Bp + (kk >> 1) * TILE;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {   // columns 32j + 2tx, +1: 16 lanes x 16 B contiguous per load
+          const float4 q = *reinterpret_cast<const float4*>(brow + 32 * j + tx * 2);
+          b[2 * j] = make_float2(q.x, q.y); b[2 * j + 1] = make_float2(q.z, q.w);
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float2 sum = __fadd2_rn(a[r], b[c]);
+            float d;
+            asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"((float)acc[r][c]), "f"(sum.x), "f"(sum.y));
+            acc[r][c] = (T)d;
+          }
+      }
+    } else {
+#pragma unroll
+      for (int kk = 0; kk < KC; kk += 2) {   // two k per step: acc = min3(acc, a0+b0, a1+b1)
+        V2 a[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) a[r] = *reinterpret_cast<const V2*>(&As[stage][ty + 16 * r][kk]);
+        const V4 b0l = *reinterpret_cast<const V4*>(&Bs[stage][kk][tx * 4]);
+        const V4 b0h = *reinterpret_cast<const V4*>(&Bs[stage][kk][64 + tx * 4]);
+        const V4 b1l = *reinterpret_cast<const V4*>(&Bs[stage][kk + 1][tx * 4]);
+        const V4 b1h = *reinterpret_cast<const V4*>(&Bs[stage][kk + 1][64 + tx * 4]);
+        const T b0[8] = {b0l.x, b0l.y, b0l.z, b0l.w, b0h.x, b0h.y, b0h.z, b0h.w};
+        const T b1[8] = {b1l.x, b1l.y, b1l.z, b1l.w, b1h.x, b1h.y, b1h.z, b1h.w};
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[r][c] = Semiring<T>::relax2(acc[r][c], a[r].x, b0[c], a[r].y, b1[c]);
+      }
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+}
+
+}  // namespace mp

@@ -1,0 +1,762 @@
+// Separator-partitioned min-plus all-pairs build (DRS_APSP_SEP): the blocked Floyd-Warshall of fw_kernels.cu run in
+// nested-dissection order, so that a road network's small vertex separators bound the pivots every output tile sees.
+//
+// Replaces, like the other builders, the per-query Dijkstra of the reference (lib/RoutingEngine.py:87,199,212;
+// lib/optimUtils.py:528,531,659) by one resident travel-time matrix; the matrix it writes is the one the SSSP and the plain
+// Floyd-Warshall builders write (bit-identical on exact-arithmetic maps, which is where the library selects it).
+//
+// The vertices are numbered part-major (drs_partition_order): the interiors of the parts first, one contiguous id range
+// each, and the separator vertices S last.  No arc joins the interiors of two different parts.  With S_j = the separators
+// adjacent to part j and Q_j = P_j + S_j (the "closed part"):
+//   S1  M_j = closure of the subgraph induced by Q_j             batched blocked FW, one small dense matrix per part
+//   S2  dS  = closure of the separator graph (arcs inside S and, per part, the S_j x S_j block of M_j): the true
+//             distances between separators                        blocked FW on |S| x |S| (fw_kernels.cu)
+//   S3  D[u, (j,k)] = min_{s in S_i} M_i[u, s] + dS[s, S_j[k]]   u in P_i: distance from every vertex to every part's
+//             separators, stored per part as a contiguous k range ("D_all", n x sum_j |S_j|)
+//   S4  C[u, v] = min( M_j[u, v] if u in P_j,  min_k D[u, (j,k)] + M_j[S_j[k], v] )     v in P_j: the output tiles,
+//             each a 128 x 128 x |S_j| min-plus product written exactly once
+//   S4x C[u, s] = D[u, (j,k)] for one (j,k) with S_j[k] = s      the separator columns are a gather
+// Every stage is the 128x128 register-tile product of minplus.cuh (FADD2 + FMNMX3 / VIADDMNMX): ALU-bound; the matrix
+// leaves the SMs once.  Work: n^2 * mean|S_j| relaxations for S4 against n^2 * (arcs/n) * (re-relaxation factor) dependent
+// L2 round trips for the SSSP builder.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+#include <queue>
+
+#include "drs_common.cuh"
+#include "minplus.cuh"
+
+using namespace mp;
+
+struct drs_sep_plan {
+  int nparts = 0, sep0 = 0, nsep = 0, spad = 0, ktot = 0, kmax = 0, maxnb = 0, max_rowtiles = 0, ncoltiles = 0, maxq = 0;
+  std::vector<int32_t> pstart, pend, sj, kpad, koff, qpad, cbase, wpad, sall, sepcol, ct_pass_ptr, ct_pass_part;
+  std::vector<int64_t> moff, apoff;
+  int64_t m_elems = 0, ap_elems = 0;
+  // device: one arena for the tables, one for the work arrays
+  void* d_tables = nullptr;
+  void* d_work = nullptr;
+  size_t work_bytes = 0;
+  const int32_t *d_pstart = nullptr, *d_pend = nullptr, *d_sj = nullptr, *d_kpad = nullptr, *d_koff = nullptr, *d_qpad = nullptr,
+                *d_cbase = nullptr, *d_wpad = nullptr, *d_sall = nullptr, *d_sepcol = nullptr, *d_ct_pass_ptr = nullptr,
+                *d_ct_pass_part = nullptr;
+  const int64_t *d_moff = nullptr, *d_apoff = nullptr;
+  void *d_M = nullptr, *d_dS = nullptr, *d_Dall = nullptr, *d_dSS = nullptr, *d_Aprime = nullptr, *d_Apad = nullptr;
+  double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+namespace {
+
+struct SepTab {
+  int nparts, sep0, nsep, n, npad, spad, ktot, kmax;
+  const int32_t *pstart, *pend, *sj, *kpad, *koff, *qpad, *cbase, *wpad;
+  const int64_t *moff, *apoff;
+  const int32_t *sall, *sepcol, *ct_pass_ptr, *ct_pass_part;
+};
+
+template <typename T> __device__ __forceinline__ void atomic_min_nonneg(T* addr, T v);
+template <> __device__ __forceinline__ void atomic_min_nonneg<float>(float* addr, float v) {
+  atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));   // non-negative floats (and +inf) order like their bits
+}
+template <> __device__ __forceinline__ void atomic_min_nonneg<int>(int* addr, int v) { atomicMin(addr, v); }
+
+// ------------------------------------------------------------------------------------------------ S1: closed parts
+template <typename T>
+__global__ void sep_fill_parts_kernel(T* M, SepTab t) {
+  const int j = blockIdx.y;
+  const int64_t ld = t.qpad[j], total = ld * ld;
+  T* Mj = M + t.moff[j];
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = idx / ld, c = idx - i * ld;
+    Mj[idx] = (i == c) ? (T)0 : Semiring<T>::inf();
+  }
+}
+
+// local index of vertex y in Q_j (interior first, then S_j in list order), -1 when y is outside the closed part
+__device__ __forceinline__ int local_of(const SepTab& t, int j, int y) {
+  const int ps = t.pstart[j], pe = t.pend[j];
+  if (y >= ps && y < pe) return y - ps;
+  if (y < t.sep0) return -1;
+  const int key = y - t.sep0;
+  const int32_t* lst = t.sall + t.koff[j];
+  int lo = 0, hi = t.sj[j];
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (lst[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  return (lo < t.sj[j] && lst[lo] == key) ? (pe - ps) + lo : -1;
+}
+
+template <typename T>
+__global__ void sep_scatter_parts_kernel(T* M, SepTab t, const int32_t* __restrict__ out_ptr, const int32_t* __restrict__ out_col,
+                                         const float* __restrict__ out_w) {
+  const int j = blockIdx.y;
+  const int li = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nj = t.pend[j] - t.pstart[j];
+  if (li >= nj + t.sj[j]) return;
+  const int x = li < nj ? t.pstart[j] + li : t.sep0 + t.sall[t.koff[j] + (li - nj)];
+  const int64_t ld = t.qpad[j];
+  T* row = M + t.moff[j] + (int64_t)li * ld;
+  for (int a = out_ptr[x]; a < out_ptr[x + 1]; ++a) {
+    const int y = out_col[a];
+    if (y == x) continue;
+    const int ly = local_of(t, j, y);
+    if (ly < 0) continue;
+    const T w = (T)out_w[a];
+    if (w < row[ly]) row[ly] = w;   // one thread per row: no race; multi-edges keep the minimum
+  }
+}
+
+constexpr int P1PAD = TILE + 4;
+constexpr size_t kDiagSmemBytes = sizeof(float) * TILE * P1PAD;
+
+// round r of every part's blocked FW, phase 1: close the diagonal tile (r, r) in shared memory
+template <typename T>
+__global__ void __launch_bounds__(1024, 1) sep_fw_diag_kernel(T* M, SepTab t, int r) {
+  using V4 = typename Vec4<T>::type;
+  const int j = blockIdx.x;
+  const int64_t ld = t.qpad[j];
+  if ((int64_t)r * TILE >= ld) return;
+  T* D = M + t.moff[j] + (int64_t)r * TILE * (ld + 1);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T(*s)[P1PAD] = reinterpret_cast<T(*)[P1PAD]>(smem_raw);
+  const int tid = threadIdx.x;
+  const int tx = tid & 31, ty = tid >> 5;  // thread owns rows ty*4..+3, columns tx*4..+3
+  V4 c[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    c[q] = *reinterpret_cast<const V4*>(D + (int64_t)(ty * 4 + q) * ld + tx * 4);
+    *reinterpret_cast<V4*>(&s[ty * 4 + q][tx * 4]) = c[q];
+  }
+  __syncthreads();
+  for (int k = 0; k < TILE; ++k) {
+    const V4 bk = *reinterpret_cast<const V4*>(&s[k][tx * 4]);
+    T a[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) a[q] = s[ty * 4 + q][k];
+    __syncthreads();   // all reads of iteration k done before anyone overwrites
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      c[q].x = Semiring<T>::relax1(c[q].x, a[q], bk.x);
+      c[q].y = Semiring<T>::relax1(c[q].y, a[q], bk.y);
+      c[q].z = Semiring<T>::relax1(c[q].z, a[q], bk.z);
+      c[q].w = Semiring<T>::relax1(c[q].w, a[q], bk.w);
+      *reinterpret_cast<V4*>(&s[ty * 4 + q][tx * 4]) = c[q];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) *reinterpret_cast<V4*>(D + (int64_t)(ty * 4 + q) * ld + tx * 4) = c[q];
+}
+
+// phases 2 (pivot row / column panels: grid (maxnb, 2, nparts)) and 3 (every other tile: grid (maxnb, maxnb, nparts))
+template <typename T>
+__global__ void __launch_bounds__(NTHREADS, 2) sep_fw_tile_kernel(T* M, SepTab t, int r, int phase) {
+  const int j = blockIdx.z;
+  const int64_t ld = t.qpad[j];
+  const int nb = (int)(ld / TILE);
+  if (r >= nb) return;
+  T* Mj = M + t.moff[j];
+  const int bx = blockIdx.x, by = blockIdx.y;
+  const T *A, *B;
+  T* C;
+  if (phase == 2) {
+    if (bx >= nb || bx == r) return;
+    const T* diag = Mj + (int64_t)r * TILE * (ld + 1);
+    if (by == 0) { C = Mj + (int64_t)r * TILE * ld + (int64_t)bx * TILE; A = diag; B = C; }
+    else { C = Mj + (int64_t)bx * TILE * ld + (int64_t)r * TILE; A = C; B = diag; }
+  } else {
+    if (bx >= nb || by >= nb || bx == r || by == r) return;
+    C = Mj + (int64_t)by * TILE * ld + (int64_t)bx * TILE;
+    A = Mj + (int64_t)by * TILE * ld + (int64_t)r * TILE;
+    B = Mj + (int64_t)r * TILE * ld + (int64_t)bx * TILE;
+  }
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x;
+  T acc[8][8];
+  acc_load<T>(acc, C, ld, tid);
+  tile_accumulate<T>(acc, A, ld, B, ld, TILE / KC, smem_raw, tid);
+  acc_store<T>(acc, C, ld, TILE, TILE, tid);
+}
+
+// S1x: what the later stages read from the closed parts.  blockIdx.z: 0 = A' rows (interior -> own separators),
+// 1 = padded A_j panels (own separators -> interior, columns on the global 128-column grid), 2 = S_j x S_j into dS
+template <typename T>
+__global__ void sep_extract_kernel(const T* __restrict__ M, SepTab t, T* __restrict__ Aprime, T* __restrict__ Apad, T* dS) {
+  const int j = blockIdx.y;
+  const int ps = t.pstart[j], nj = t.pend[j] - ps, sj = t.sj[j], kp = t.kpad[j];
+  const int64_t ld = t.qpad[j];
+  const T* Mj = M + t.moff[j];
+  const int64_t g0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gs = (int64_t)gridDim.x * blockDim.x;
+  if (blockIdx.z == 0) {
+    const int64_t total = (int64_t)nj * t.kmax;
+    for (int64_t idx = g0; idx < total; idx += gs) {
+      const int li = (int)(idx / t.kmax), k = (int)(idx - (int64_t)li * t.kmax);
+      Aprime[(int64_t)(ps + li) * t.kmax + k] = k < sj ? Mj[(int64_t)li * ld + nj + k] : Semiring<T>::inf();
+    }
+  } else if (blockIdx.z == 1) {
+    const int wp = t.wpad[j], cb = t.cbase[j];
+    T* Aj = Apad + t.apoff[j];
+    const int64_t total = (int64_t)kp * wp;
+    for (int64_t idx = g0; idx < total; idx += gs) {
+      const int k = (int)(idx / wp), c = (int)(idx - (int64_t)k * wp);
+      const int lv = cb + c - ps;
+      Aj[idx] = (k < sj && lv >= 0 && lv < nj) ? Mj[(int64_t)(nj + k) * ld + lv] : Semiring<T>::inf();
+    }
+  } else {
+    const int32_t* lst = t.sall + t.koff[j];
+    const int64_t total = (int64_t)sj * sj;
+    for (int64_t idx = g0; idx < total; idx += gs) {
+      const int ka = (int)(idx / sj), kb = (int)(idx - (int64_t)ka * sj);
+      const T v = Mj[(int64_t)(nj + ka) * ld + nj + kb];
+      if (v < Semiring<T>::inf()) atomic_min_nonneg<T>(dS + (int64_t)lst[ka] * t.spad + lst[kb], v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ S2: separator graph
+template <typename T>
+__global__ void sep_fill_identity_kernel(T* M, int64_t ld, int64_t rows) {
+  const int64_t total = rows * ld;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = idx / ld, c = idx - i * ld;
+    M[idx] = (i == c) ? (T)0 : Semiring<T>::inf();
+  }
+}
+
+template <typename T>
+__global__ void sep_arcs_kernel(T* dS, SepTab t, const int32_t* __restrict__ out_ptr, const int32_t* __restrict__ out_col,
+                                const float* __restrict__ out_w) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= t.nsep) return;
+  const int x = t.sep0 + r;
+  for (int a = out_ptr[x]; a < out_ptr[x + 1]; ++a) {
+    const int y = out_col[a];
+    if (y < t.sep0 || y == x) continue;
+    atomic_min_nonneg<T>(dS + (int64_t)r * t.spad + (y - t.sep0), (T)out_w[a]);
+  }
+}
+
+// S2x: rows [sep0, npad) of D_all: D_all[sep0 + r][c] = dS[r][sall[c]]; padding columns and rows = inf
+template <typename T>
+__global__ void sep_gather_rows_kernel(const T* __restrict__ dS, SepTab t, T* __restrict__ Dall) {
+  const int64_t total = (int64_t)(t.npad - t.sep0) * t.ktot;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(idx / t.ktot), c = (int)(idx - (int64_t)r * t.ktot);
+    const int s = t.sall[c];
+    Dall[(int64_t)(t.sep0 + r) * t.ktot + c] = (r < t.nsep && s >= 0) ? dS[(int64_t)r * t.spad + s] : Semiring<T>::inf();
+  }
+}
+
+// dSS[c'][c] = dS[sall[c']][sall[c]] = the separator row of D_all
+template <typename T>
+__global__ void sep_gather_dss_kernel(const T* __restrict__ Dall, SepTab t, T* __restrict__ dSS) {
+  const int64_t total = (int64_t)t.ktot * t.ktot;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int cp = (int)(idx / t.ktot), c = (int)(idx - (int64_t)cp * t.ktot);
+    const int s = t.sall[cp];
+    dSS[idx] = s >= 0 ? Dall[(int64_t)(t.sep0 + s) * t.ktot + c] : Semiring<T>::inf();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ S3: vertex -> separators
+// grid (ktot / 128, max row tiles of a part, nparts).  Row tiles start at the part's first vertex; rows past its last one
+// are computed from the next part's A' rows and not stored.
+template <typename T>
+__global__ void __launch_bounds__(NTHREADS, 2) sep_expand_rows_kernel(const T* __restrict__ Aprime, const T* __restrict__ dSS,
+                                                                        T* __restrict__ Dall, SepTab t, int row_lo, int row_hi) {
+  const int i = blockIdx.z;
+  const int row0 = t.pstart[i] + blockIdx.y * TILE, pe = t.pend[i];
+  if (row0 >= pe || row0 >= row_hi || min(row0 + TILE, pe) <= row_lo) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x;
+  T acc[8][8];
+  acc_fill<T>(acc, Semiring<T>::inf());
+  tile_accumulate<T>(acc, Aprime + (int64_t)row0 * t.kmax, t.kmax, dSS + (int64_t)t.koff[i] * t.ktot + (int64_t)blockIdx.x * TILE,
+                     t.ktot, t.kpad[i] / KC, smem_raw, tid);
+  acc_store<T>(acc, Dall + (int64_t)row0 * t.ktot + (int64_t)blockIdx.x * TILE, t.ktot, pe - row0, TILE, tid);
+}
+
+// ------------------------------------------------------------------------------------------------ S4: the output tiles
+// grid (column tiles of [0, sep0), row tiles of the shard).  One pass per part the 128 columns intersect (one or two;
+// a part's padded A_j panel is +inf outside its own columns, so the passes do not disturb each other).
+template <typename T>
+__global__ void __launch_bounds__(NTHREADS, 2) sep_expand_kernel(const T* __restrict__ Dall, const T* __restrict__ Apad,
+                                                                   const T* __restrict__ M, T* __restrict__ C, int64_t ldc, SepTab t,
+                                                                   int row_lo) {
+  const int ct = blockIdx.x;
+  const int R0 = row_lo + blockIdx.y * TILE, C0 = ct * TILE;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  T acc[8][8];
+  acc_fill<T>(acc, Semiring<T>::inf());
+  for (int p = t.ct_pass_ptr[ct]; p < t.ct_pass_ptr[ct + 1]; ++p) {
+    const int j = t.ct_pass_part[p];
+    const int ps = t.pstart[j], pe = t.pend[j];
+    if (R0 < pe && R0 + TILE > ps) {   // rows of this tile lie in part j: paths that stay inside the closed part
+      const int64_t ld = t.qpad[j];
+      const T* Mj = M + t.moff[j];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int u = R0 + acc_row<T>(r, ty);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const int v = C0 + acc_col<T>(c, tx);
+          if (u >= ps && u < pe && v >= ps && v < pe) acc[r][c] = Mj[(int64_t)(u - ps) * ld + (v - ps)];
+        }
+      }
+    }
+    tile_accumulate<T>(acc, Dall + (int64_t)R0 * t.ktot + t.koff[j], t.ktot, Apad + t.apoff[j] + (C0 - t.cbase[j]), t.wpad[j],
+                       t.kpad[j] / KC, smem_raw, tid);
+  }
+  acc_store<T>(acc, C + (int64_t)(R0 - row_lo) * ldc + C0, ldc, TILE, min(TILE, t.sep0 - C0), tid);
+}
+
+// S4x: columns [sep0, npad) of the shard: separator columns gathered from D_all, padding as the other builders leave it
+// (0 on the diagonal of the padding rows, +inf elsewhere)
+template <typename T>
+__global__ void sep_cols_kernel(const T* __restrict__ Dall, T* __restrict__ C, int64_t ldc, SepTab t, int row_lo, int nrows) {
+  const int w = t.npad - t.sep0;
+  const int64_t total = (int64_t)nrows * w;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int lr = (int)(idx / w), cc = (int)(idx - (int64_t)lr * w);
+    const int u = row_lo + lr, c = t.sep0 + cc;
+    T v;
+    if (u >= t.n || c >= t.n) v = (u == c) ? (T)0 : Semiring<T>::inf();
+    else v = Dall[(int64_t)u * t.ktot + t.sepcol[cc]];
+    C[(int64_t)lr * ldc + c] = v;
+  }
+}
+
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+SepTab device_tab(const drs_graph* g) {
+  const drs_sep_plan* p = g->sep;
+  SepTab t{};
+  t.nparts = p->nparts; t.sep0 = p->sep0; t.nsep = p->nsep; t.n = g->n; t.npad = g->npad; t.spad = p->spad; t.ktot = p->ktot;
+  t.kmax = p->kmax;
+  t.pstart = p->d_pstart; t.pend = p->d_pend; t.sj = p->d_sj; t.kpad = p->d_kpad; t.koff = p->d_koff; t.qpad = p->d_qpad;
+  t.cbase = p->d_cbase; t.wpad = p->d_wpad; t.moff = p->d_moff; t.apoff = p->d_apoff; t.sall = p->d_sall; t.sepcol = p->d_sepcol;
+  t.ct_pass_ptr = p->d_ct_pass_ptr; t.ct_pass_part = p->d_ct_pass_part;
+  return t;
+}
+
+template <typename T>
+int configure_kernels() {
+  static bool configured[64] = {};
+  int dev = 0;
+  DRS_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && configured[dev]) return DRS_OK;
+  DRS_CUDA(cudaFuncSetAttribute(sep_fw_tile_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
+  DRS_CUDA(cudaFuncSetAttribute(sep_expand_rows_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
+  DRS_CUDA(cudaFuncSetAttribute(sep_expand_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
+  DRS_CUDA(cudaFuncSetAttribute(sep_fw_diag_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDiagSmemBytes));
+  if (dev >= 0 && dev < 64) configured[dev] = true;
+  return DRS_OK;
+}
+
+int ensure_work(drs_graph* g) {
+  drs_sep_plan* p = g->sep;
+  auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t b_M = al(4 * (size_t)p->m_elems), b_dS = al(4 * (size_t)p->spad * p->spad);
+  const size_t b_Dall = al(4 * (size_t)g->npad * p->ktot), b_dSS = al(4 * (size_t)p->ktot * p->ktot);
+  const size_t b_Apr = al(4 * (size_t)(g->npad + TILE) * p->kmax), b_Apad = al(4 * (size_t)std::max<int64_t>(p->ap_elems, 1));
+  const size_t total = b_M + b_dS + b_Dall + b_dSS + b_Apr + b_Apad;
+  if (!p->d_work || p->work_bytes < total) {
+    if (p->d_work) cudaFree(p->d_work);
+    p->d_work = nullptr; p->work_bytes = 0;
+    drs_count_alloc();
+    if (cudaMalloc(&p->d_work, total) != cudaSuccess) {
+      cudaGetLastError();
+      DRS_REQUIRE(false, DRS_ERR_NOMEM, "separator build: cudaMalloc(%zu bytes) of work arrays failed", total);
+    }
+    p->work_bytes = total;
+    // rows of A' past the last interior vertex are read (never used) by the last row tile of a part
+    DRS_CUDA(cudaMemset(p->d_work, 0x7f, total));
+  }
+  char* b = (char*)p->d_work;
+  p->d_M = b; b += b_M; p->d_dS = b; b += b_dS; p->d_Dall = b; b += b_Dall; p->d_dSS = b; b += b_dSS;
+  p->d_Aprime = b; b += b_Apr; p->d_Apad = b;
+  return DRS_OK;
+}
+
+template <typename T>
+int build_rows(drs_graph* g, int mode, T* local, int64_t ld, int row0, int nrows, cudaStream_t st) {
+  drs_sep_plan* p = g->sep;
+  int rc;
+  if ((rc = configure_kernels<T>())) return rc;
+  if ((rc = ensure_work(g))) return rc;
+  const SepTab t = device_tab(g);
+  T *M = (T*)p->d_M, *dS = (T*)p->d_dS, *Dall = (T*)p->d_Dall, *dSS = (T*)p->d_dSS, *Apr = (T*)p->d_Aprime, *Apad = (T*)p->d_Apad;
+  cudaEvent_t ev[9];
+  for (auto& e : ev) DRS_CUDA(cudaEventCreate(&e));
+  auto release = [&]() { for (auto& e : ev) cudaEventDestroy(e); };
+  auto fail = [&](int code) { release(); return code; };
+#define SEP_CHECK() do { if (cudaGetLastError() != cudaSuccess) { drs_set_error("separator build: kernel launch failed (%s:%d)", __FILE__, __LINE__); return fail(DRS_ERR_CUDA); } } while (0)
+  cudaEventRecord(ev[0], st);
+  // S1: closed parts
+  sep_fill_parts_kernel<T><<<dim3(64, p->nparts), 256, 0, st>>>(M, t);
+  sep_scatter_parts_kernel<T><<<dim3((p->maxq + 127) / 128, p->nparts), 128, 0, st>>>(M, t, g->d_out_ptr, g->d_out_col, g->d_out_w);
+  drs_count_launch(2);
+  SEP_CHECK();
+  cudaEventRecord(ev[1], st);
+  for (int r = 0; r < p->maxnb; ++r) {
+    sep_fw_diag_kernel<T><<<p->nparts, 1024, kDiagSmemBytes, st>>>(M, t, r);
+    drs_count_launch();
+    if (p->maxnb > 1) {
+      sep_fw_tile_kernel<T><<<dim3(p->maxnb, 2, p->nparts), NTHREADS, kTileSmemBytes, st>>>(M, t, r, 2);
+      sep_fw_tile_kernel<T><<<dim3(p->maxnb, p->maxnb, p->nparts), NTHREADS, kTileSmemBytes, st>>>(M, t, r, 3);
+      drs_count_launch(2);
+    }
+    SEP_CHECK();
+  }
+  cudaEventRecord(ev[2], st);
+  // S1x + S2
+  sep_fill_identity_kernel<T><<<148 * 4, 256, 0, st>>>(dS, p->spad, p->spad);
+  sep_extract_kernel<T><<<dim3(32, p->nparts, 3), 256, 0, st>>>(M, t, Apr, Apad, dS);
+  drs_count_launch(2);
+  if (p->nsep > 0) {
+    sep_arcs_kernel<T><<<(p->nsep + 127) / 128, 128, 0, st>>>(dS, t, g->d_out_ptr, g->d_out_col, g->d_out_w);
+    drs_count_launch();
+  }
+  SEP_CHECK();
+  cudaEventRecord(ev[3], st);
+  if (p->nsep > 0) {
+    const int nbs = p->spad / TILE;
+    for (int kb = 0; kb < nbs; ++kb) {
+      char* panel = (char*)dS + sizeof(T) * (int64_t)kb * TILE * p->spad;
+      if ((rc = drs_fw_pivot_row(mode, panel, p->spad, kb, st))) return fail(rc);
+      if ((rc = drs_fw_update(mode, dS, p->spad, p->spad, panel, kb, kb, 0, nbs, st))) return fail(rc);
+    }
+  }
+  cudaEventRecord(ev[4], st);
+  // S2x
+  sep_gather_rows_kernel<T><<<148 * 8, 256, 0, st>>>(dS, t, Dall);
+  sep_gather_dss_kernel<T><<<148 * 8, 256, 0, st>>>(Dall, t, dSS);
+  drs_count_launch(2);
+  SEP_CHECK();
+  cudaEventRecord(ev[5], st);
+  // S3
+  sep_expand_rows_kernel<T><<<dim3(p->ktot / TILE, p->max_rowtiles, p->nparts), NTHREADS, kTileSmemBytes, st>>>(Apr, dSS, Dall, t, row0,
+                                                                                                              row0 + nrows);
+  drs_count_launch();
+  SEP_CHECK();
+  cudaEventRecord(ev[6], st);
+  // S4
+  if (p->ncoltiles > 0) {
+    sep_expand_kernel<T><<<dim3(p->ncoltiles, nrows / TILE), NTHREADS, kTileSmemBytes, st>>>(Dall, Apad, M, local, ld, t, row0);
+    drs_count_launch();
+  }
+  SEP_CHECK();
+  cudaEventRecord(ev[7], st);
+  sep_cols_kernel<T><<<148 * 8, 256, 0, st>>>(Dall, local, ld, t, row0, nrows);
+  drs_count_launch();
+  SEP_CHECK();
+  cudaEventRecord(ev[8], st);
+#undef SEP_CHECK
+  if (cudaStreamSynchronize(st) != cudaSuccess) {
+    drs_set_error("separator build: %s", cudaGetErrorString(cudaGetLastError()));
+    return fail(DRS_ERR_CUDA);
+  }
+  for (int i = 0; i < 8; ++i) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+    p->prof_ms[i] = ms;
+  }
+  release();
+  return DRS_OK;
+}
+
+}  // namespace
+
+void drs_sep_free(drs_graph* g) {
+  if (!g->sep) return;
+  if (g->sep->d_tables) cudaFree(g->sep->d_tables);
+  if (g->sep->d_work) cudaFree(g->sep->d_work);
+  delete g->sep;
+  g->sep = nullptr;
+}
+
+bool drs_sep_usable(const drs_graph* g) {
+  // exact arithmetic (any association of the sums gives the same bits) and separators that are a small part of the map
+  return g->sep && g->weights_integral && (int64_t)g->sep->nsep * 3 <= g->n && (int64_t)g->sep->ktot * 2 <= g->npad + 256;
+}
+
+extern "C" int drs_graph_set_partition(drs_graph* g, int32_t nparts, const int32_t* part_ptr) {
+  DRS_REQUIRE(g, DRS_ERR_ARG, "drs_graph_set_partition: null graph");
+  DrsDeviceGuard guard(g->device);
+  drs_sep_free(g);
+  if (nparts <= 0) return DRS_OK;   // partition removed
+  DRS_REQUIRE(part_ptr && part_ptr[0] == 0, DRS_ERR_ARG, "drs_graph_set_partition: part_ptr must start at 0");
+  for (int j = 0; j < nparts; ++j)
+    DRS_REQUIRE(part_ptr[j + 1] > part_ptr[j], DRS_ERR_ARG, "drs_graph_set_partition: part %d is empty or out of order", j);
+  const int n = g->n, sep0 = part_ptr[nparts];
+  DRS_REQUIRE(sep0 <= n, DRS_ERR_RANGE, "drs_graph_set_partition: parts cover %d vertices, the graph has %d", sep0, n);
+  std::vector<int32_t> part_of(n, -1);
+  for (int j = 0; j < nparts; ++j)
+    for (int v = part_ptr[j]; v < part_ptr[j + 1]; ++v) part_of[v] = j;
+  std::vector<std::vector<int32_t>> S(nparts);
+  for (int e = 0; e < g->m; ++e) {
+    const int a = g->h_src[e], b = g->h_dst[e];
+    const int pa = part_of[a], pb = part_of[b];
+    if (pa >= 0 && pb >= 0) {
+      DRS_REQUIRE(pa == pb, DRS_ERR_ARG, "drs_graph_set_partition: edge %d (%d - %d) joins the interiors of parts %d and %d", e, a, b,
+                  pa, pb);
+    } else if (pa >= 0) S[pa].push_back(b - sep0);
+    else if (pb >= 0) S[pb].push_back(a - sep0);
+  }
+  const int nsep = n - sep0;
+  std::vector<char> listed(std::max(nsep, 1), 0);
+  for (auto& s : S) {
+    std::sort(s.begin(), s.end());
+    s.erase(std::unique(s.begin(), s.end()), s.end());
+    for (int r : s) listed[r] = 1;
+  }
+  for (int r = 0; r < nsep; ++r)
+    if (!listed[r]) {   // a separator with separator neighbours only: any closed part may carry it
+      int best = 0;
+      for (int j = 1; j < nparts; ++j)
+        if (S[j].size() < S[best].size()) best = j;
+      S[best].insert(std::lower_bound(S[best].begin(), S[best].end(), r), r);
+    }
+  drs_sep_plan* p = new (std::nothrow) drs_sep_plan();
+  DRS_REQUIRE(p, DRS_ERR_NOMEM, "drs_graph_set_partition: out of host memory");
+  p->nparts = nparts; p->sep0 = sep0; p->nsep = nsep;
+  p->spad = std::max(TILE, round_up(nsep, TILE));
+  p->pstart.assign(part_ptr, part_ptr + nparts); p->pend.assign(part_ptr + 1, part_ptr + nparts + 1);
+  p->sj.resize(nparts); p->kpad.resize(nparts); p->koff.resize(nparts); p->qpad.resize(nparts); p->cbase.resize(nparts);
+  p->wpad.resize(nparts); p->moff.resize(nparts); p->apoff.resize(nparts);
+  int ksum = 0;
+  int64_t melems = 0, apelems = 0;
+  p->kmax = KC;
+  for (int j = 0; j < nparts; ++j) {
+    const int nj = p->pend[j] - p->pstart[j], sj = (int)S[j].size();
+    p->sj[j] = sj; p->kpad[j] = round_up(sj, KC); p->koff[j] = ksum; ksum += p->kpad[j];
+    p->kmax = std::max(p->kmax, p->kpad[j]);
+    p->qpad[j] = round_up(nj + sj, TILE); p->moff[j] = melems; melems += (int64_t)p->qpad[j] * p->qpad[j];
+    p->maxq = std::max(p->maxq, nj + sj);
+    p->maxnb = std::max(p->maxnb, p->qpad[j] / TILE);
+    p->max_rowtiles = std::max(p->max_rowtiles, (nj + TILE - 1) / TILE);
+    p->cbase[j] = p->pstart[j] / TILE * TILE; p->wpad[j] = round_up(p->pend[j], TILE) - p->cbase[j];
+    p->apoff[j] = apelems; apelems += (int64_t)p->kpad[j] * p->wpad[j];
+  }
+  p->ktot = std::max(TILE, round_up(ksum, TILE));
+  p->m_elems = melems; p->ap_elems = apelems;
+  p->sall.assign(p->ktot, -1);
+  p->sepcol.assign(std::max(g->npad - sep0, 1), 0);
+  std::vector<char> have(std::max(nsep, 1), 0);
+  for (int j = 0; j < nparts; ++j)
+    for (int k = 0; k < (int)S[j].size(); ++k) {
+      const int r = S[j][k];
+      p->sall[p->koff[j] + k] = r;
+      if (!have[r]) { have[r] = 1; p->sepcol[r] = p->koff[j] + k; }
+    }
+  p->ncoltiles = (sep0 + TILE - 1) / TILE;
+  p->ct_pass_ptr.assign(p->ncoltiles + 1, 0);
+  {
+    int j = 0;
+    for (int ct = 0; ct < p->ncoltiles; ++ct) {
+      const int c0 = ct * TILE, c1 = std::min(c0 + TILE, sep0);
+      while (j < nparts && p->pend[j] <= c0) ++j;
+      for (int q = j; q < nparts && p->pstart[q] < c1; ++q) p->ct_pass_part.push_back(q);
+      p->ct_pass_ptr[ct + 1] = (int)p->ct_pass_part.size();
+    }
+  }
+  if (p->ct_pass_part.empty()) p->ct_pass_part.push_back(0);
+  // one device arena for the tables
+  struct Slice { const void* src; size_t bytes; size_t off; };
+  std::vector<Slice> sl;
+  size_t off = 0;
+  auto add = [&](const void* src, size_t bytes) { sl.push_back({src, bytes, off}); const size_t o = off; off = (off + std::max<size_t>(bytes, 4) + 255) & ~(size_t)255; return o; };
+  const size_t o_ps = add(p->pstart.data(), 4 * nparts), o_pe = add(p->pend.data(), 4 * nparts), o_sj = add(p->sj.data(), 4 * nparts);
+  const size_t o_kp = add(p->kpad.data(), 4 * nparts), o_ko = add(p->koff.data(), 4 * nparts), o_qp = add(p->qpad.data(), 4 * nparts);
+  const size_t o_cb = add(p->cbase.data(), 4 * nparts), o_wp = add(p->wpad.data(), 4 * nparts);
+  const size_t o_mo = add(p->moff.data(), 8 * nparts), o_ao = add(p->apoff.data(), 8 * nparts);
+  const size_t o_sa = add(p->sall.data(), 4 * p->sall.size()), o_sc = add(p->sepcol.data(), 4 * p->sepcol.size());
+  const size_t o_cp = add(p->ct_pass_ptr.data(), 4 * p->ct_pass_ptr.size()), o_cq = add(p->ct_pass_part.data(), 4 * p->ct_pass_part.size());
+  std::vector<unsigned char> img(off, 0);
+  for (const Slice& s : sl) std::memcpy(img.data() + s.off, s.src, s.bytes);
+  drs_count_alloc();
+  if (cudaMalloc(&p->d_tables, img.size()) != cudaSuccess ||
+      cudaMemcpy(p->d_tables, img.data(), img.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaGetLastError();
+    if (p->d_tables) cudaFree(p->d_tables);
+    delete p;
+    DRS_REQUIRE(false, DRS_ERR_CUDA, "drs_graph_set_partition: device tables (%zu bytes) could not be created", img.size());
+  }
+  const char* b = (const char*)p->d_tables;
+  p->d_pstart = (const int32_t*)(b + o_ps); p->d_pend = (const int32_t*)(b + o_pe); p->d_sj = (const int32_t*)(b + o_sj);
+  p->d_kpad = (const int32_t*)(b + o_kp); p->d_koff = (const int32_t*)(b + o_ko); p->d_qpad = (const int32_t*)(b + o_qp);
+  p->d_cbase = (const int32_t*)(b + o_cb); p->d_wpad = (const int32_t*)(b + o_wp);
+  p->d_moff = (const int64_t*)(b + o_mo); p->d_apoff = (const int64_t*)(b + o_ao);
+  p->d_sall = (const int32_t*)(b + o_sa); p->d_sepcol = (const int32_t*)(b + o_sc);
+  p->d_ct_pass_ptr = (const int32_t*)(b + o_cp); p->d_ct_pass_part = (const int32_t*)(b + o_cq);
+  g->sep = p;
+  return DRS_OK;
+}
+
+extern "C" int drs_sep_info(const drs_graph* g, int32_t* nparts, int32_t* nsep, int32_t* ktot, int32_t* kmax, int32_t* usable) {
+  DRS_REQUIRE(g, DRS_ERR_ARG, "drs_sep_info: null graph");
+  const drs_sep_plan* p = g->sep;
+  if (nparts) *nparts = p ? p->nparts : 0;
+  if (nsep) *nsep = p ? p->nsep : 0;
+  if (ktot) *ktot = p ? p->ktot : 0;
+  if (kmax) *kmax = p ? p->kmax : 0;
+  if (usable) *usable = drs_sep_usable(g) ? 1 : 0;
+  return DRS_OK;
+}
+
+extern "C" int drs_apsp_sep_profile(const drs_graph* g, double* ms8) {
+  DRS_REQUIRE(g && ms8, DRS_ERR_ARG, "drs_apsp_sep_profile: null argument");
+  DRS_REQUIRE(g->sep, DRS_ERR_STATE, "drs_apsp_sep_profile: the graph has no partition");
+  for (int i = 0; i < 8; ++i) ms8[i] = g->sep->prof_ms[i];
+  return DRS_OK;
+}
+
+extern "C" int drs_apsp_rows_sep(const drs_graph* gc, int32_t mode, void* local_dev, int64_t ld, int32_t row0, int32_t nrows,
+                                 void* stream) {
+  DRS_REQUIRE(gc && local_dev, DRS_ERR_ARG, "drs_apsp_rows_sep: null argument");
+  drs_graph* g = const_cast<drs_graph*>(gc);
+  { int rcm = drs_check_mode(g, mode, "drs_apsp_rows_sep"); if (rcm) return rcm; }
+  DRS_REQUIRE(g->sep, DRS_ERR_STATE, "drs_apsp_rows_sep: the graph has no partition (drs_graph_set_partition)");
+  DRS_REQUIRE(g->weights_integral, DRS_ERR_ARG,
+              "drs_apsp_rows_sep: needs integer travel times below 1e6 (the build re-associates sums; use the SSSP builder)");
+  DRS_REQUIRE(ld == g->npad && row0 >= 0 && nrows >= 0 && row0 + nrows <= g->npad && row0 % TILE == 0 && nrows % TILE == 0,
+              DRS_ERR_ARG, "drs_apsp_rows_sep: bad shard (ld=%lld row0=%d nrows=%d npad=%d; rows in multiples of %d)", (long long)ld,
+              row0, nrows, g->npad, TILE);
+  if (nrows == 0) return DRS_OK;
+  DrsDeviceGuard guard(g->device);
+  if (mode == DRS_MODE_F32) return build_rows<float>(g, mode, (float*)local_dev, ld, row0, nrows, (cudaStream_t)stream);
+  return build_rows<int>(g, mode, (int*)local_dev, ld, row0, nrows, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------ host: the partition
+namespace {
+
+struct Bisector {
+  int n, target;
+  const double *x, *y;           // null: no usable coordinates
+  std::vector<int32_t> adj_ptr, adj;   // undirected adjacency (for the coordinate-free split)
+  std::vector<int32_t> idx;
+  std::vector<std::pair<int, int>> leaves;
+  std::vector<int32_t> stamp_in, stamp_seen;
+  int stamp = 0, seen_ctr = 0;
+
+  void bfs_order(int lo, int hi) {
+    // level-structure order of the subgraph induced by idx[lo, hi), started from a pseudo-peripheral vertex
+    ++stamp;
+    for (int i = lo; i < hi; ++i) stamp_in[idx[i]] = stamp;
+    std::vector<int32_t> order;
+    order.reserve(hi - lo);
+    auto sweep = [&](int start, int seen_stamp, std::vector<int32_t>& out) {
+      size_t head = out.size();
+      out.push_back(start);
+      stamp_seen[start] = seen_stamp;
+      while (head < out.size()) {
+        const int u = out[head++];
+        for (int a = adj_ptr[u]; a < adj_ptr[u + 1]; ++a) {
+          const int v = adj[a];
+          if (stamp_in[v] == stamp && stamp_seen[v] != seen_stamp) { stamp_seen[v] = seen_stamp; out.push_back(v); }
+        }
+      }
+    };
+    std::vector<int32_t> probe;
+    sweep(idx[lo], ++seen_ctr, probe);
+    const int far = probe.back();
+    const int seen2 = ++seen_ctr;
+    sweep(far, seen2, order);
+    for (int i = lo; i < hi; ++i)
+      if (stamp_seen[idx[i]] != seen2) sweep(idx[i], seen2, order);   // further components
+    std::copy(order.begin(), order.end(), idx.begin() + lo);
+  }
+
+  void split(int lo, int hi) {
+    const int c = hi - lo;
+    if (c <= target) { if (c > 0) leaves.push_back({lo, hi}); return; }
+    const int L = (c + target - 1) / target, Ll = L / 2;
+    const int mid = lo + (int)((int64_t)c * Ll / L);
+    if (x) {
+      double x0 = x[idx[lo]], x1 = x0, y0 = y[idx[lo]], y1 = y0;
+      for (int i = lo; i < hi; ++i) {
+        x0 = std::min(x0, x[idx[i]]); x1 = std::max(x1, x[idx[i]]);
+        y0 = std::min(y0, y[idx[i]]); y1 = std::max(y1, y[idx[i]]);
+      }
+      const double* k = (x1 - x0 >= y1 - y0) ? x : y;
+      std::nth_element(idx.begin() + lo, idx.begin() + mid, idx.begin() + hi,
+                       [k](int a, int b) { return k[a] < k[b] || (k[a] == k[b] && a < b); });
+    } else {
+      bfs_order(lo, hi);
+    }
+    split(lo, mid);
+    split(mid, hi);
+  }
+};
+
+}  // namespace
+
+// Part-major device numbering for the separator build (and a locality numbering for everything else: parts follow the
+// bisection tree, so neighbouring vertices keep neighbouring ids).  order_out[k] = caller's id of device vertex k;
+// part_ptr_out[0..nparts] = id ranges of the part interiors, part_ptr_out[nparts] = first separator id.
+// Parts: recursive coordinate bisection (median cuts along the wider axis) when lng/lat are usable, otherwise recursive
+// bisection of breadth-first level structures.  Separators: a greedy vertex cover of the cut edges.
+extern "C" int drs_partition_order(int32_t n, int32_t m, const int32_t* src, const int32_t* dst, const double* lng, const double* lat,
+                                   int32_t target, int32_t* order_out, int32_t* part_ptr_out, int32_t max_parts, int32_t* nparts_out) {
+  DRS_REQUIRE(n > 0 && m >= 0 && (m == 0 || (src && dst)) && order_out && part_ptr_out && nparts_out && target > 0 && max_parts > 0,
+              DRS_ERR_ARG, "drs_partition_order: bad argument");
+  for (int e = 0; e < m; ++e)
+    DRS_REQUIRE(src[e] >= 0 && src[e] < n && dst[e] >= 0 && dst[e] < n, DRS_ERR_RANGE, "drs_partition_order: edge %d endpoint out of range", e);
+  Bisector b;
+  b.n = n; b.target = target; b.x = b.y = nullptr;
+  if (lng && lat) {
+    bool ok = true, varied = false;
+    for (int i = 0; i < n && ok; ++i) {
+      ok = std::isfinite(lng[i]) && std::isfinite(lat[i]);
+      varied = varied || lng[i] != lng[0] || lat[i] != lat[0];
+    }
+    if (ok && varied) { b.x = lng; b.y = lat; }
+  }
+  b.idx.resize(n);
+  std::iota(b.idx.begin(), b.idx.end(), 0);
+  if (!b.x) {
+    b.adj_ptr.assign(n + 1, 0);
+    for (int e = 0; e < m; ++e) if (src[e] != dst[e]) { b.adj_ptr[src[e] + 1]++; b.adj_ptr[dst[e] + 1]++; }
+    std::partial_sum(b.adj_ptr.begin(), b.adj_ptr.end(), b.adj_ptr.begin());
+    b.adj.resize(b.adj_ptr[n]);
+    std::vector<int32_t> pos(b.adj_ptr.begin(), b.adj_ptr.end() - 1);
+    for (int e = 0; e < m; ++e) if (src[e] != dst[e]) { b.adj[pos[src[e]]++] = dst[e]; b.adj[pos[dst[e]]++] = src[e]; }
+    b.stamp_in.assign(n, 0); b.stamp_seen.assign(n, 0);
+  }
+  b.split(0, n);
+  std::vector<int32_t> part(n);
+  for (int j = 0; j < (int)b.leaves.size(); ++j)
+    for (int i = b.leaves[j].first; i < b.leaves[j].second; ++i) part[b.idx[i]] = j;
+  std::vector<int32_t> cutdeg(n, 0);
+  for (int e = 0; e < m; ++e)
+    if (part[src[e]] != part[dst[e]]) { cutdeg[src[e]]++; cutdeg[dst[e]]++; }
+  std::vector<char> sep(n, 0);
+  for (int e = 0; e < m; ++e) {
+    const int u = src[e], v = dst[e];
+    if (part[u] == part[v] || sep[u] || sep[v]) continue;
+    const int pick = cutdeg[u] > cutdeg[v] ? u : cutdeg[v] > cutdeg[u] ? v : (part[u] < part[v] ? u : v);
+    sep[pick] = 1;
+  }
+  int k = 0, np = 0;
+  part_ptr_out[0] = 0;
+  for (const auto& lf : b.leaves) {
+    const int k0 = k;
+    for (int i = lf.first; i < lf.second; ++i)
+      if (!sep[b.idx[i]]) order_out[k++] = b.idx[i];
+    if (k > k0) {
+      DRS_REQUIRE(np < max_parts, DRS_ERR_CAPACITY, "drs_partition_order: more than %d parts (raise max_parts or the target size)", max_parts);
+      part_ptr_out[++np] = k;
+    }
+  }
+  for (const auto& lf : b.leaves)
+    for (int i = lf.first; i < lf.second; ++i)
+      if (sep[b.idx[i]]) order_out[k++] = b.idx[i];
+  *nparts_out = np;
+  return DRS_OK;
+}

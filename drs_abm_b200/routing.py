@@ -197,6 +197,35 @@ def locality_order(n, src, dst, lng=None, lat=None, native=False):
         return np.asarray(reverse_cuthill_mckee(A, symmetric_mode=True), dtype=np.int32)
 
 
+def default_part_target(n):
+    """Vertices per part of the separator partition: the expansion stage costs n^2 x (separators around a part, which
+    grow like the square root of the part) and the separator closure (number of separators)^3, which shrinks with
+    larger parts; on grid-like road maps the two balance near n / 100 (measured on the 50k-node city: DESIGN.md)."""
+    return int(min(2048, max(192, n // 96)))
+
+
+def partition_order(n, src, dst, lng=None, lat=None, target=None):
+    """(order, part_ptr) of the part-major device numbering (include/drs_b200.h: drs_partition_order)."""
+    lib = _lib.load()
+    target = int(target or default_part_target(n))
+    src, dst = _lib.as_i32(src), _lib.as_i32(dst)
+    x = y = None
+    try:
+        x, y = np.ascontiguousarray(lng, dtype=np.float64), np.ascontiguousarray(lat, dtype=np.float64)
+        if x.shape != (n,) or y.shape != (n,):
+            x = y = None
+    except (TypeError, ValueError):
+        x = y = None
+    order = np.empty(n, dtype=np.int32)
+    max_parts = max(4, 4 * (n // target + 1))
+    part_ptr = np.zeros(max_parts + 1, dtype=np.int32)
+    nparts = C.c_int32(0)
+    _lib.check(lib.drs_partition_order(n, len(src), _lib.ptr_i32(src), _lib.ptr_i32(dst),
+                                       _lib.ptr_f64(x) if x is not None else None, _lib.ptr_f64(y) if y is not None else None,
+                                       target, _lib.ptr_i32(order), _lib.ptr_i32(part_ptr), max_parts, C.byref(nparts)), lib)
+    return order, part_ptr[:nparts.value + 1].copy()
+
+
 class RoadGraph(object):
     """The object callers know as ``router.G``: igraph look-alike backed by a device
     CSR graph and the resident travel-time / predecessor matrices.
@@ -206,7 +235,8 @@ class RoadGraph(object):
     ``ttmedian`` after load).
     """
 
-    def __init__(self, data, mode=_lib.MODE_F32, algorithm=_lib.APSP_AUTO, pred=_lib.PRED_LAZY, numbering="locality"):
+    def __init__(self, data, mode=_lib.MODE_F32, algorithm=_lib.APSP_AUTO, pred=_lib.PRED_LAZY, numbering="partition",
+                 part_target=None):
         if not isinstance(data, RoadGraphData):
             raise TypeError("RoadGraph needs RoadGraphData (use RoadGraph.Read_GML)")
         self.n, self.m = data.n, data.m
@@ -225,9 +255,15 @@ class RoadGraph(object):
         # Device numbering of the vertices: "locality" = along a space-filling curve (locality_order), "input" = the
         # caller's.  Vertex ids are translated at every call into the library (dev_ids / host_cols); edge ids, and
         # with them adjacency order, canonical predecessors and paths, do not depend on it.
-        if numbering not in ("locality", "input"):
-            raise ValueError("numbering must be 'locality' or 'input'")
+        # "partition" (the default) = part-major numbering over a vertex-separator partition (partition_order): the
+        # interiors of the parts first, the separators last; parts follow the bisection tree, so it is a locality
+        # numbering too, and it is what the separator-partitioned build (APSP_SEP) works on.  "locality" = the plain
+        # space-filling curve of round 1.
+        if numbering not in ("partition", "locality", "input"):
+            raise ValueError("numbering must be 'partition', 'locality' or 'input'")
         self.numbering = numbering
+        self.part_target = int(os.environ.get("DRS_SEP_TARGET", part_target or 0)) or None
+        self._part_ptr = None
         self._new_of_old = self._old_of_new = None
 
     # ------------------------------------------------------------------ igraph surface
@@ -354,8 +390,13 @@ class RoadGraph(object):
     _weights_dirty = False
 
     def _number(self):
-        if self.numbering == "locality" and self._new_of_old is None:
-            order = locality_order(self.n, self._src, self._dst, self._vattrs.get("lng"), self._vattrs.get("lat"))
+        if self.numbering in ("locality", "partition") and self._new_of_old is None:
+            order = None
+            if self.numbering == "partition":
+                order, self._part_ptr = partition_order(self.n, self._src, self._dst, self._vattrs.get("lng"),
+                                                        self._vattrs.get("lat"), self.part_target)
+            else:
+                order = locality_order(self.n, self._src, self._dst, self._vattrs.get("lng"), self._vattrs.get("lat"))
             self._old_of_new = np.ascontiguousarray(order, dtype=np.int32)
             self._new_of_old = np.empty(self.n, dtype=np.int32)
             self._new_of_old[order] = np.arange(self.n, dtype=np.int32)
@@ -393,6 +434,9 @@ class RoadGraph(object):
             _lib.check(lib.drs_graph_create(self.n, self.m, 1 if self.directed else 0, _lib.ptr_i32(src),
                                             _lib.ptr_i32(dst), _lib.ptr_f64(tt), _lib.ptr_f64(length), C.byref(h)), lib)
             self._handle = h
+            if self._part_ptr is not None:
+                pp = _lib.as_i32(self._part_ptr)
+                _lib.check(lib.drs_graph_set_partition(h, len(pp) - 1, _lib.ptr_i32(pp)), lib)
             self._weight_attr = attr
             self._weights_dirty = False
             self._valid = False

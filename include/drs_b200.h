@@ -109,11 +109,43 @@ int drs_apsp_rows_to_host(const drs_graph* g, int32_t row0, int32_t nrows, doubl
 /* Algorithm used by drs_apsp_build.  FW: blocked min-plus Floyd-Warshall (N^3 work, ALU
  * bound, independent of sparsity).  SSSP: N delta-stepping searches over the CSR (about
  * N*E work, memory-latency bound; far less work on sparse road networks).  Both give the
- * same matrix bit for bit on integer weights.  AUTO picks SSSP when arcs/vertex <= 16. */
+ * same matrix bit for bit on integer weights.  SEP: the blocked Floyd-Warshall in nested-dissection
+ * order over a vertex-separator partition of the map (drs_graph_set_partition): about N^2 * |S_j|
+ * relaxations, |S_j| = separators around a part, ALU bound, the matrix written once; it re-associates the
+ * sums, so it is offered on integer travel times only, where it gives the same matrix bit for bit.
+ * AUTO picks SEP when the graph has a partition with small separators and integer travel times, else
+ * SSSP when arcs/vertex <= 16, else FW. */
 #define DRS_APSP_FW 0
 #define DRS_APSP_SSSP 1
 #define DRS_APSP_AUTO 2
+#define DRS_APSP_SEP 3
 int drs_apsp_set_algorithm(drs_graph* g, int32_t algorithm);
+
+/* ------------------------------------------------- separator partition --
+ * Host-side helper of the bindings (no device work): a part-major device numbering of the vertices.
+ * order_out[k] = caller's id of device vertex k; device ids [part_ptr_out[j], part_ptr_out[j+1]) are the
+ * interior of part j (j < *nparts_out), ids [part_ptr_out[*nparts_out], n) the separator vertices; no edge
+ * joins the interiors of two parts.  Parts hold about `target` vertices: recursive coordinate bisection
+ * when lng/lat are usable (they may be NULL), else bisection of breadth-first level structures;
+ * separators = a greedy vertex cover of the cut edges.  Parts follow the bisection tree, so the numbering
+ * also serves as the locality numbering of drs_locality_order.  Replaces nothing in the reference (vertex
+ * ids are igraph's load order there, lib/RoutingEngine.py:48-60); the bindings translate ids at every call. */
+int drs_partition_order(int32_t n, int32_t m, const int32_t* src, const int32_t* dst, const double* lng,
+                        const double* lat, int32_t target, int32_t* order_out, int32_t* part_ptr_out,
+                        int32_t max_parts, int32_t* nparts_out);
+/* Declares the partition of a graph created in that numbering (part_ptr as above, nparts + 1 entries; nparts = 0
+ * removes it).  DRS_ERR_ARG if an edge joins two interiors.  Builds the device tables of the SEP build. */
+int drs_graph_set_partition(drs_graph* g, int32_t nparts, const int32_t* part_ptr);
+/* parts, separator vertices, sum and maximum of the per-part separator counts (padded), and whether AUTO would use it */
+int drs_sep_info(const drs_graph* g, int32_t* nparts, int32_t* nsep, int32_t* ktot, int32_t* kmax, int32_t* usable);
+/* Rows [row0, row0 + nrows) (multiples of DRS_FW_TILE) of the matrix by the SEP build into local_dev (nrows x ld, ld = npad):
+ * the sharded form used by the multi-GPU build (every rank closes the parts and the separator graph, then expands
+ * its own rows; no collective).  Same role as drs_apsp_rows_sssp. */
+int drs_apsp_rows_sep(const drs_graph* g, int32_t mode, void* local_dev, int64_t ld, int32_t row0, int32_t nrows,
+                      void* stream);
+/* milliseconds of the last SEP build by stage: fill+scatter, part closures, extraction, separator closure,
+ * gathers, vertex->separator rows, output tiles, separator columns */
+int drs_apsp_sep_profile(const drs_graph* g, double* ms8);
 
 /* Predecessors.  LAZY (default): no predecessor matrix; path queries evaluate the canonical rule on the
  * spot from the distance row and the target's in-arcs (a handful of extra gathers per hop, half the HBM
