@@ -102,12 +102,14 @@ template <typename T> __device__ __forceinline__ void acc_load(T (&acc)[8][8], c
   }
 }
 
-// Accumulators to the tile at C; rows >= rows or columns >= cols are not written (edge tiles store element-wise).
-template <typename T> __device__ __forceinline__ void acc_store(const T (&acc)[8][8], T* C, int64_t ldc, int rows, int cols, int tid) {
+// Accumulators to the tile at C; rows >= rows and columns outside [col_lo, cols) are not written (edge tiles store
+// element-wise).
+template <typename T> __device__ __forceinline__ void acc_store(const T (&acc)[8][8], T* C, int64_t ldc, int rows, int cols, int tid,
+                                                               int col_lo = 0) {
   using V4 = typename Vec4<T>::type;
   using V2 = typename Vec2<T>::type;
   const int tx = tid & 15, ty = tid >> 4;
-  if (rows >= TILE && cols >= TILE) {
+  if (rows >= TILE && cols >= TILE && col_lo <= 0) {
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       T* crow = C + (int64_t)(ty + 16 * r) * ldc;
@@ -134,25 +136,53 @@ template <typename T> __device__ __forceinline__ void acc_store(const T (&acc)[8
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       const int col = acc_col<T>(c, tx);
-      if (col < cols) C[(int64_t)row * ldc + col] = acc[r][c];
+      if (col < cols && col >= col_lo) C[(int64_t)row * ldc + col] = acc[r][c];
     }
   }
 }
 
-// acc = min(acc, A (x) B) over nchunk 32-wide k chunks.  A: 128 rows x 32 nchunk (16-byte aligned rows), B: 32 nchunk rows
-// x 128 columns (16-byte aligned rows for int32, 4-byte for fp32).  smem_raw: kTileSmemBytes of dynamic shared memory.
+// The transposed tile: element (row, col) of the accumulators goes to Ct[col * ldc + row] for col in [col_lo, col_hi) and
+// row < rows, staged through shared memory (TILE x (TILE + 1) elements of smem_raw, free once tile_accumulate has
+// returned) so that the global stores run along rows of Ct.
+constexpr int TPITCH = TILE + 1;
+template <typename T> __device__ __forceinline__ void acc_store_transposed(const T (&acc)[8][8], unsigned char* smem_raw, T* Ct, int64_t ldc,
+                                                                          int col_lo, int col_hi, int rows, int tid) {
+  T* s = reinterpret_cast<T*>(smem_raw);
+  const int tx = tid & 15, ty = tid >> 4;
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) s[acc_col<T>(c, tx) * TPITCH + acc_row<T>(r, ty)] = acc[r][c];
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int v = warp; v < TILE; v += NTHREADS / 32) {
+    if (v < col_lo || v >= col_hi) continue;
+    T* crow = Ct + (int64_t)v * ldc;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int u = lane + 32 * q;
+      if (u < rows) crow[u] = s[v * TPITCH + u];
+    }
+  }
+}
+
+// acc = min(acc, A (x) B) over kcols inner indices (a multiple of 16), streamed in 32-wide chunks; a last half chunk is
+// loaded whole (the 16 extra k columns of A / rows of B must be readable) and half of it used.  A: 128 rows x kcols
+// (16-byte aligned rows), B: kcols rows x 128 columns (16-byte aligned rows for int32, 4-byte for fp32).  smem_raw: kTileSmemBytes of dynamic shared memory.
 // Returns with every copy drained and every thread past its last shared-memory read, so the ring can be refilled at once
 // (the multi-pass tiles of the separator build call it once per pass).
 template <typename T>
 __device__ __forceinline__ void tile_accumulate(T (&acc)[8][8], const T* __restrict__ A, int64_t lda, const T* __restrict__ B,
-                                                int64_t ldb, int nchunk, unsigned char* smem_raw, int tid) {
+                                                int64_t ldb, int kcols, unsigned char* smem_raw, int tid) {
   using V4 = typename Vec4<T>::type;
   using V2 = typename Vec2<T>::type;
   T(*As)[TILE][APAD] = reinterpret_cast<T(*)[TILE][APAD]>(smem_raw);
   T(*Bs)[KC][TILE] = reinterpret_cast<T(*)[KC][TILE]>(smem_raw + sizeof(T) * STAGES * TILE * APAD);
   const int tx = tid & 15, ty = tid >> 4;
   constexpr bool kPacked = Semiring<T>::packed;
-  if (nchunk <= 0) return;
+  if (kcols <= 0) return;
+  const int nchunk = (kcols + KC - 1) / KC;
+  const bool half_tail = (kcols & (KC - 1)) != 0;
 
   auto load_chunk = [&](int kc, int stage) {
     const int k0 = kc * KC;
@@ -195,10 +225,12 @@ __device__ __forceinline__ void tile_accumulate(T (&acc)[8][8], const T* __restr
     if (kc + STAGES - 1 < nchunk) load_chunk(kc + STAGES - 1, (kc + STAGES - 1) % STAGES);
     cp_async_commit();
 
+    const bool full = !(half_tail && kc == nchunk - 1);
     if (kPacked) {
       const float2* Bp = reinterpret_cast<const float2*>(&Bs[stage][0][0]);
 #pragma unroll
       for (int kk = 0; kk < KC; kk += 2) {
+        if (kk == KC / 2 && !full) break;
         float2 a[8], b[8];
 #pragma unroll
         for (int r = 0; r < 8; ++r) a[r] = *reinterpret_cast<const float2*>(&As[stage][ty + 16 * r][kk]);
@@ -221,6 +253,7 @@ __device__ __forceinline__ void tile_accumulate(T (&acc)[8][8], const T* __restr
     } else {
 #pragma unroll
       for (int kk = 0; kk < KC; kk += 2) {   // two k per step: acc = min3(acc, a0+b0, a1+b1)
+        if (kk == KC / 2 && !full) break;
         V2 a[8];
 #pragma unroll
         for (int r = 0; r < 8; ++r) a[r] = *reinterpret_cast<const V2*>(&As[stage][ty + 16 * r][kk]);

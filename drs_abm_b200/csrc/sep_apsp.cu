@@ -21,6 +21,7 @@
 // L2 round trips for the SSSP builder.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <queue>
@@ -32,7 +33,7 @@ using namespace mp;
 
 struct drs_sep_plan {
   int nparts = 0, sep0 = 0, nsep = 0, spad = 0, ktot = 0, kmax = 0, maxnb = 0, max_rowtiles = 0, ncoltiles = 0, maxq = 0;
-  std::vector<int32_t> pstart, pend, sj, kpad, koff, qpad, cbase, wpad, sall, sepcol, ct_pass_ptr, ct_pass_part;
+  std::vector<int32_t> pstart, pend, sj, kpad, koff, qpad, cbase, wpad, sall, sepcol, ct_part, ct_col0;
   std::vector<int64_t> moff, apoff;
   int64_t m_elems = 0, ap_elems = 0;
   // device: one arena for the tables, one for the work arrays
@@ -40,11 +41,14 @@ struct drs_sep_plan {
   void* d_work = nullptr;
   size_t work_bytes = 0;
   const int32_t *d_pstart = nullptr, *d_pend = nullptr, *d_sj = nullptr, *d_kpad = nullptr, *d_koff = nullptr, *d_qpad = nullptr,
-                *d_cbase = nullptr, *d_wpad = nullptr, *d_sall = nullptr, *d_sepcol = nullptr, *d_ct_pass_ptr = nullptr,
-                *d_ct_pass_part = nullptr;
+                *d_cbase = nullptr, *d_wpad = nullptr, *d_sall = nullptr, *d_sepcol = nullptr, *d_ct_part = nullptr,
+                *d_ct_col0 = nullptr;
   const int64_t *d_moff = nullptr, *d_apoff = nullptr;
   void *d_M = nullptr, *d_dS = nullptr, *d_Dall = nullptr, *d_dSS = nullptr, *d_Aprime = nullptr, *d_Apad = nullptr;
   double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  bool no_mirror = false;   // DRS_SEP_NO_MIRROR=1: compute every output tile (measurement knob)
+  int n = 0, npad = 0;      // vertices of this level and their padded count (the leading dimension of its matrix)
+  drs_sep_plan* child = nullptr;   // level 2: the same build on this level's separator graph
 };
 
 namespace {
@@ -53,7 +57,7 @@ struct SepTab {
   int nparts, sep0, nsep, n, npad, spad, ktot, kmax;
   const int32_t *pstart, *pend, *sj, *kpad, *koff, *qpad, *cbase, *wpad;
   const int64_t *moff, *apoff;
-  const int32_t *sall, *sepcol, *ct_pass_ptr, *ct_pass_part;
+  const int32_t *sall, *sepcol, *ct_part, *ct_col0;
 };
 
 template <typename T> __device__ __forceinline__ void atomic_min_nonneg(T* addr, T v);
@@ -177,7 +181,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) sep_fw_tile_kernel(T* M, SepTab t
   const int tid = threadIdx.x;
   T acc[8][8];
   acc_load<T>(acc, C, ld, tid);
-  tile_accumulate<T>(acc, A, ld, B, ld, TILE / KC, smem_raw, tid);
+  tile_accumulate<T>(acc, A, ld, B, ld, TILE, smem_raw, tid);
   acc_store<T>(acc, C, ld, TILE, TILE, tid);
 }
 
@@ -199,7 +203,7 @@ __global__ void sep_extract_kernel(const T* __restrict__ M, SepTab t, T* __restr
   } else if (blockIdx.z == 1) {
     const int wp = t.wpad[j], cb = t.cbase[j];
     T* Aj = Apad + t.apoff[j];
-    const int64_t total = (int64_t)kp * wp;
+    const int64_t total = (int64_t)((kp + KC - 1) / KC * KC) * wp;
     for (int64_t idx = g0; idx < total; idx += gs) {
       const int k = (int)(idx / wp), c = (int)(idx - (int64_t)k * wp);
       const int lv = cb + c - ps;
@@ -275,44 +279,49 @@ __global__ void __launch_bounds__(NTHREADS, 2) sep_expand_rows_kernel(const T* _
   T acc[8][8];
   acc_fill<T>(acc, Semiring<T>::inf());
   tile_accumulate<T>(acc, Aprime + (int64_t)row0 * t.kmax, t.kmax, dSS + (int64_t)t.koff[i] * t.ktot + (int64_t)blockIdx.x * TILE,
-                     t.ktot, t.kpad[i] / KC, smem_raw, tid);
+                     t.ktot, t.kpad[i], smem_raw, tid);
   acc_store<T>(acc, Dall + (int64_t)row0 * t.ktot + (int64_t)blockIdx.x * TILE, t.ktot, pe - row0, TILE, tid);
 }
 
 // ------------------------------------------------------------------------------------------------ S4: the output tiles
-// grid (column tiles of [0, sep0), row tiles of the shard).  One pass per part the 128 columns intersect (one or two;
-// a part's padded A_j panel is +inf outside its own columns, so the passes do not disturb each other).
-template <typename T>
+// grid (column tiles, row tiles of the shard).  Column tiles are laid out per part: tile t of part j covers the columns
+// cbase_j + 128 t .. of the part (cbase_j = the part's first vertex rounded down to 4, so vector stores stay aligned); a
+// part's padded A_j panel is +inf outside its own columns and the store is clipped to them, so every element of the
+// matrix is written by exactly one tile.  MIRROR (undirected maps, whole-matrix builds): only the tiles that reach the
+// diagonal or lie above it are computed, and each also writes its transpose -- the matrix is symmetric.
+template <typename T, bool MIRROR>
 __global__ void __launch_bounds__(NTHREADS, 2) sep_expand_kernel(const T* __restrict__ Dall, const T* __restrict__ Apad,
                                                                    const T* __restrict__ M, T* __restrict__ C, int64_t ldc, SepTab t,
                                                                    int row_lo) {
   const int ct = blockIdx.x;
-  const int R0 = row_lo + blockIdx.y * TILE, C0 = ct * TILE;
+  const int j = t.ct_part[ct], C0 = t.ct_col0[ct];
+  const int R0 = row_lo + blockIdx.y * TILE;
+  const int ps = t.pstart[j], pe = t.pend[j];
+  const int col_lo = max(ps - C0, 0), col_hi = min(pe - C0, TILE);
+  if (MIRROR && !(C0 + col_hi > R0 || R0 + TILE > t.sep0)) return;   // strictly below the diagonal, interior rows: mirrored
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   T acc[8][8];
   acc_fill<T>(acc, Semiring<T>::inf());
-  for (int p = t.ct_pass_ptr[ct]; p < t.ct_pass_ptr[ct + 1]; ++p) {
-    const int j = t.ct_pass_part[p];
-    const int ps = t.pstart[j], pe = t.pend[j];
-    if (R0 < pe && R0 + TILE > ps) {   // rows of this tile lie in part j: paths that stay inside the closed part
-      const int64_t ld = t.qpad[j];
-      const T* Mj = M + t.moff[j];
+  if (R0 < pe && R0 + TILE > ps) {   // rows of this tile lie in part j: paths that stay inside the closed part
+    const int64_t ld = t.qpad[j];
+    const T* Mj = M + t.moff[j];
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const int u = R0 + acc_row<T>(r, ty);
+    for (int r = 0; r < 8; ++r) {
+      const int u = R0 + acc_row<T>(r, ty);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const int v = C0 + acc_col<T>(c, tx);
-          if (u >= ps && u < pe && v >= ps && v < pe) acc[r][c] = Mj[(int64_t)(u - ps) * ld + (v - ps)];
-        }
+      for (int c = 0; c < 8; ++c) {
+        const int v = C0 + acc_col<T>(c, tx);
+        if (u >= ps && u < pe && v >= ps && v < pe) acc[r][c] = Mj[(int64_t)(u - ps) * ld + (v - ps)];
       }
     }
-    tile_accumulate<T>(acc, Dall + (int64_t)R0 * t.ktot + t.koff[j], t.ktot, Apad + t.apoff[j] + (C0 - t.cbase[j]), t.wpad[j],
-                       t.kpad[j] / KC, smem_raw, tid);
   }
-  acc_store<T>(acc, C + (int64_t)(R0 - row_lo) * ldc + C0, ldc, TILE, min(TILE, t.sep0 - C0), tid);
+  tile_accumulate<T>(acc, Dall + (int64_t)R0 * t.ktot + t.koff[j], t.ktot, Apad + t.apoff[j] + (C0 - t.cbase[j]), t.wpad[j],
+                     t.kpad[j], smem_raw, tid);
+  acc_store<T>(acc, C + (int64_t)(R0 - row_lo) * ldc + C0, ldc, TILE, col_hi, tid, col_lo);
+  if (MIRROR && R0 < t.sep0)   // C[v][u] = C[u][v]; columns u are interior vertices only (separator columns: S4x)
+    acc_store_transposed<T>(acc, smem_raw, C + (int64_t)C0 * ldc + R0, ldc, col_lo, col_hi, min(TILE, t.sep0 - R0), tid);
 }
 
 // S4x: columns [sep0, npad) of the shard: separator columns gathered from D_all, padding as the other builders leave it
@@ -333,14 +342,44 @@ __global__ void sep_cols_kernel(const T* __restrict__ Dall, T* __restrict__ C, i
 
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
-SepTab device_tab(const drs_graph* g) {
-  const drs_sep_plan* p = g->sep;
+// Level 2 (the separator graph of level 1 handled by the same build): the closed parts and the top separator graph
+// start from a dense matrix W (the level-1 separator graph: arcs inside S and the S_j x S_j blocks) instead of a CSR
+template <typename T>
+__global__ void sep_gather_parts_kernel(T* M, SepTab t, const T* __restrict__ W, int64_t ldw) {
+  const int j = blockIdx.y;
+  const int ps = t.pstart[j], nj = t.pend[j] - ps, q = nj + t.sj[j];
+  const int64_t ld = t.qpad[j], total = ld * ld;
+  const int32_t* lst = t.sall + t.koff[j];
+  T* Mj = M + t.moff[j];
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int li = (int)(idx / ld), lj = (int)(idx - (int64_t)li * ld);
+    T v = (li == lj) ? (T)0 : Semiring<T>::inf();
+    if (li < q && lj < q && li != lj) {
+      const int x = li < nj ? ps + li : t.sep0 + lst[li - nj], y = lj < nj ? ps + lj : t.sep0 + lst[lj - nj];
+      v = W[(int64_t)x * ldw + y];
+    }
+    Mj[idx] = v;
+  }
+}
+
+template <typename T>
+__global__ void sep_gather_top_kernel(T* dS, SepTab t, const T* __restrict__ W, int64_t ldw) {
+  const int64_t total = (int64_t)t.spad * t.spad;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int a = (int)(idx / t.spad), b = (int)(idx - (int64_t)a * t.spad);
+    T v = (a == b) ? (T)0 : Semiring<T>::inf();
+    if (a < t.nsep && b < t.nsep && a != b) v = W[(int64_t)(t.sep0 + a) * ldw + (t.sep0 + b)];
+    dS[idx] = v;
+  }
+}
+
+SepTab device_tab(const drs_sep_plan* p) {
   SepTab t{};
-  t.nparts = p->nparts; t.sep0 = p->sep0; t.nsep = p->nsep; t.n = g->n; t.npad = g->npad; t.spad = p->spad; t.ktot = p->ktot;
+  t.nparts = p->nparts; t.sep0 = p->sep0; t.nsep = p->nsep; t.n = p->n; t.npad = p->npad; t.spad = p->spad; t.ktot = p->ktot;
   t.kmax = p->kmax;
   t.pstart = p->d_pstart; t.pend = p->d_pend; t.sj = p->d_sj; t.kpad = p->d_kpad; t.koff = p->d_koff; t.qpad = p->d_qpad;
   t.cbase = p->d_cbase; t.wpad = p->d_wpad; t.moff = p->d_moff; t.apoff = p->d_apoff; t.sall = p->d_sall; t.sepcol = p->d_sepcol;
-  t.ct_pass_ptr = p->d_ct_pass_ptr; t.ct_pass_part = p->d_ct_pass_part;
+  t.ct_part = p->d_ct_part; t.ct_col0 = p->d_ct_col0;
   return t;
 }
 
@@ -352,18 +391,18 @@ int configure_kernels() {
   if (dev >= 0 && dev < 64 && configured[dev]) return DRS_OK;
   DRS_CUDA(cudaFuncSetAttribute(sep_fw_tile_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
   DRS_CUDA(cudaFuncSetAttribute(sep_expand_rows_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
-  DRS_CUDA(cudaFuncSetAttribute(sep_expand_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
+  DRS_CUDA(cudaFuncSetAttribute(sep_expand_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
+  DRS_CUDA(cudaFuncSetAttribute(sep_expand_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
   DRS_CUDA(cudaFuncSetAttribute(sep_fw_diag_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDiagSmemBytes));
   if (dev >= 0 && dev < 64) configured[dev] = true;
   return DRS_OK;
 }
 
-int ensure_work(drs_graph* g) {
-  drs_sep_plan* p = g->sep;
+int ensure_work(drs_sep_plan* p) {
   auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
   const size_t b_M = al(4 * (size_t)p->m_elems), b_dS = al(4 * (size_t)p->spad * p->spad);
-  const size_t b_Dall = al(4 * (size_t)g->npad * p->ktot), b_dSS = al(4 * (size_t)p->ktot * p->ktot);
-  const size_t b_Apr = al(4 * (size_t)(g->npad + TILE) * p->kmax), b_Apad = al(4 * (size_t)std::max<int64_t>(p->ap_elems, 1));
+  const size_t b_Dall = al(4 * (size_t)p->npad * p->ktot), b_dSS = al(4 * (size_t)p->ktot * p->ktot);
+  const size_t b_Apr = al(4 * (size_t)(p->npad + TILE) * p->kmax), b_Apad = al(4 * (size_t)std::max<int64_t>(p->ap_elems, 1));
   const size_t total = b_M + b_dS + b_Dall + b_dSS + b_Apr + b_Apad;
   if (!p->d_work || p->work_bytes < total) {
     if (p->d_work) cudaFree(p->d_work);
@@ -383,26 +422,35 @@ int ensure_work(drs_graph* g) {
   return DRS_OK;
 }
 
+// where a level's arcs come from: the device CSR of the map (level 1) or a dense matrix (level 2)
+struct LevelInput {
+  const int32_t* out_ptr = nullptr; const int32_t* out_col = nullptr; const float* out_w = nullptr;
+  const void* W = nullptr; int64_t ldw = 0;
+};
+
+// Rows [row0, row0 + nrows) of the level's all-pairs matrix into C (nrows x ldc).  Launches only: the caller
+// synchronises.  ev (9 events, may be null) brackets the stages of this level.
 template <typename T>
-int build_rows(drs_graph* g, int mode, T* local, int64_t ld, int row0, int nrows, cudaStream_t st) {
-  drs_sep_plan* p = g->sep;
+int run_level(drs_sep_plan* p, const LevelInput& in, int mode, bool directed, T* C, int64_t ldc, int row0, int nrows, cudaStream_t st,
+              cudaEvent_t* ev) {
   int rc;
-  if ((rc = configure_kernels<T>())) return rc;
-  if ((rc = ensure_work(g))) return rc;
-  const SepTab t = device_tab(g);
+  if ((rc = ensure_work(p))) return rc;
+  const SepTab t = device_tab(p);
   T *M = (T*)p->d_M, *dS = (T*)p->d_dS, *Dall = (T*)p->d_Dall, *dSS = (T*)p->d_dSS, *Apr = (T*)p->d_Aprime, *Apad = (T*)p->d_Apad;
-  cudaEvent_t ev[9];
-  for (auto& e : ev) DRS_CUDA(cudaEventCreate(&e));
-  auto release = [&]() { for (auto& e : ev) cudaEventDestroy(e); };
-  auto fail = [&](int code) { release(); return code; };
-#define SEP_CHECK() do { if (cudaGetLastError() != cudaSuccess) { drs_set_error("separator build: kernel launch failed (%s:%d)", __FILE__, __LINE__); return fail(DRS_ERR_CUDA); } } while (0)
-  cudaEventRecord(ev[0], st);
+#define SEP_CHECK() DRS_REQUIRE(cudaGetLastError() == cudaSuccess, DRS_ERR_CUDA, "separator build: kernel launch failed (%s:%d)", __FILE__, __LINE__)
+#define SEP_EVENT(i) do { if (ev) cudaEventRecord(ev[i], st); } while (0)
+  SEP_EVENT(0);
   // S1: closed parts
-  sep_fill_parts_kernel<T><<<dim3(64, p->nparts), 256, 0, st>>>(M, t);
-  sep_scatter_parts_kernel<T><<<dim3((p->maxq + 127) / 128, p->nparts), 128, 0, st>>>(M, t, g->d_out_ptr, g->d_out_col, g->d_out_w);
-  drs_count_launch(2);
+  if (in.W) {
+    sep_gather_parts_kernel<T><<<dim3(64, p->nparts), 256, 0, st>>>(M, t, (const T*)in.W, in.ldw);
+    drs_count_launch();
+  } else {
+    sep_fill_parts_kernel<T><<<dim3(64, p->nparts), 256, 0, st>>>(M, t);
+    sep_scatter_parts_kernel<T><<<dim3((p->maxq + 127) / 128, p->nparts), 128, 0, st>>>(M, t, in.out_ptr, in.out_col, in.out_w);
+    drs_count_launch(2);
+  }
   SEP_CHECK();
-  cudaEventRecord(ev[1], st);
+  SEP_EVENT(1);
   for (int r = 0; r < p->maxnb; ++r) {
     sep_fw_diag_kernel<T><<<p->nparts, 1024, kDiagSmemBytes, st>>>(M, t, r);
     drs_count_launch();
@@ -413,94 +461,114 @@ int build_rows(drs_graph* g, int mode, T* local, int64_t ld, int row0, int nrows
     }
     SEP_CHECK();
   }
-  cudaEventRecord(ev[2], st);
-  // S1x + S2
-  sep_fill_identity_kernel<T><<<148 * 4, 256, 0, st>>>(dS, p->spad, p->spad);
+  SEP_EVENT(2);
+  // S1x: the separator graph's matrix, A' and the padded A_j panels
+  if (in.W) sep_gather_top_kernel<T><<<148 * 4, 256, 0, st>>>(dS, t, (const T*)in.W, in.ldw);
+  else sep_fill_identity_kernel<T><<<148 * 4, 256, 0, st>>>(dS, p->spad, p->spad);
   sep_extract_kernel<T><<<dim3(32, p->nparts, 3), 256, 0, st>>>(M, t, Apr, Apad, dS);
   drs_count_launch(2);
-  if (p->nsep > 0) {
-    sep_arcs_kernel<T><<<(p->nsep + 127) / 128, 128, 0, st>>>(dS, t, g->d_out_ptr, g->d_out_col, g->d_out_w);
+  if (p->nsep > 0 && !in.W) {
+    sep_arcs_kernel<T><<<(p->nsep + 127) / 128, 128, 0, st>>>(dS, t, in.out_ptr, in.out_col, in.out_w);
     drs_count_launch();
   }
   SEP_CHECK();
-  cudaEventRecord(ev[3], st);
+  SEP_EVENT(3);
+  // S2: closure of the separator graph -- by this same build one level up when the partition has a second level
   if (p->nsep > 0) {
-    const int nbs = p->spad / TILE;
-    for (int kb = 0; kb < nbs; ++kb) {
-      char* panel = (char*)dS + sizeof(T) * (int64_t)kb * TILE * p->spad;
-      if ((rc = drs_fw_pivot_row(mode, panel, p->spad, kb, st))) return fail(rc);
-      if ((rc = drs_fw_update(mode, dS, p->spad, p->spad, panel, kb, kb, 0, nbs, st))) return fail(rc);
+    if (p->child) {
+      LevelInput up;
+      up.W = dS; up.ldw = p->spad;
+      if ((rc = run_level<T>(p->child, up, mode, directed, dS, p->spad, 0, p->spad, st, nullptr))) return rc;   // in place
+    } else {
+      const int nbs = p->spad / TILE;
+      for (int kb = 0; kb < nbs; ++kb) {
+        char* panel = (char*)dS + sizeof(T) * (int64_t)kb * TILE * p->spad;
+        if ((rc = drs_fw_pivot_row(mode, panel, p->spad, kb, st))) return rc;
+        if ((rc = drs_fw_update(mode, dS, p->spad, p->spad, panel, kb, kb, 0, nbs, st))) return rc;
+      }
     }
   }
-  cudaEventRecord(ev[4], st);
+  SEP_EVENT(4);
   // S2x
   sep_gather_rows_kernel<T><<<148 * 8, 256, 0, st>>>(dS, t, Dall);
   sep_gather_dss_kernel<T><<<148 * 8, 256, 0, st>>>(Dall, t, dSS);
   drs_count_launch(2);
   SEP_CHECK();
-  cudaEventRecord(ev[5], st);
+  SEP_EVENT(5);
   // S3
   sep_expand_rows_kernel<T><<<dim3(p->ktot / TILE, p->max_rowtiles, p->nparts), NTHREADS, kTileSmemBytes, st>>>(Apr, dSS, Dall, t, row0,
                                                                                                               row0 + nrows);
   drs_count_launch();
   SEP_CHECK();
-  cudaEventRecord(ev[6], st);
+  SEP_EVENT(6);
   // S4
   if (p->ncoltiles > 0) {
-    sep_expand_kernel<T><<<dim3(p->ncoltiles, nrows / TILE), NTHREADS, kTileSmemBytes, st>>>(Dall, Apad, M, local, ld, t, row0);
+    const dim3 grid(p->ncoltiles, nrows / TILE);
+    const bool mirror = !directed && row0 == 0 && nrows == p->npad && !p->no_mirror;
+    if (mirror) sep_expand_kernel<T, true><<<grid, NTHREADS, kTileSmemBytes, st>>>(Dall, Apad, M, C, ldc, t, row0);
+    else sep_expand_kernel<T, false><<<grid, NTHREADS, kTileSmemBytes, st>>>(Dall, Apad, M, C, ldc, t, row0);
     drs_count_launch();
   }
   SEP_CHECK();
-  cudaEventRecord(ev[7], st);
-  sep_cols_kernel<T><<<148 * 8, 256, 0, st>>>(Dall, local, ld, t, row0, nrows);
+  SEP_EVENT(7);
+  sep_cols_kernel<T><<<148 * 8, 256, 0, st>>>(Dall, C, ldc, t, row0, nrows);
   drs_count_launch();
   SEP_CHECK();
-  cudaEventRecord(ev[8], st);
+  SEP_EVENT(8);
 #undef SEP_CHECK
-  if (cudaStreamSynchronize(st) != cudaSuccess) {
-    drs_set_error("separator build: %s", cudaGetErrorString(cudaGetLastError()));
-    return fail(DRS_ERR_CUDA);
-  }
-  for (int i = 0; i < 8; ++i) {
-    float ms = 0;
-    cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
-    p->prof_ms[i] = ms;
-  }
-  release();
+#undef SEP_EVENT
   return DRS_OK;
 }
 
-}  // namespace
-
-void drs_sep_free(drs_graph* g) {
-  if (!g->sep) return;
-  if (g->sep->d_tables) cudaFree(g->sep->d_tables);
-  if (g->sep->d_work) cudaFree(g->sep->d_work);
-  delete g->sep;
-  g->sep = nullptr;
+template <typename T>
+int build_rows(drs_graph* g, int mode, T* local, int64_t ld, int row0, int nrows, cudaStream_t st) {
+  drs_sep_plan* p = g->sep;
+  int rc;
+  if ((rc = configure_kernels<T>())) return rc;
+  cudaEvent_t ev[9];
+  for (auto& e : ev) DRS_CUDA(cudaEventCreate(&e));
+  LevelInput in;
+  in.out_ptr = g->d_out_ptr; in.out_col = g->d_out_col; in.out_w = g->d_out_w;
+  rc = run_level<T>(p, in, mode, g->directed != 0, local, ld, row0, nrows, st, ev);
+  if (!rc && cudaStreamSynchronize(st) != cudaSuccess) {
+    drs_set_error("separator build: %s", cudaGetErrorString(cudaGetLastError()));
+    rc = DRS_ERR_CUDA;
+  }
+  if (!rc)
+    for (int i = 0; i < 8; ++i) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+      p->prof_ms[i] = ms;
+    }
+  for (auto& e : ev) cudaEventDestroy(e);
+  return rc;
 }
 
-bool drs_sep_usable(const drs_graph* g) {
-  // exact arithmetic (any association of the sums gives the same bits) and separators that are a small part of the map
-  return g->sep && g->weights_integral && (int64_t)g->sep->nsep * 3 <= g->n && (int64_t)g->sep->ktot * 2 <= g->npad + 256;
+void free_plan(drs_sep_plan* p) {
+  if (!p) return;
+  free_plan(p->child);
+  if (p->d_tables) cudaFree(p->d_tables);
+  if (p->d_work) cudaFree(p->d_work);
+  delete p;
 }
 
-extern "C" int drs_graph_set_partition(drs_graph* g, int32_t nparts, const int32_t* part_ptr) {
-  DRS_REQUIRE(g, DRS_ERR_ARG, "drs_graph_set_partition: null graph");
-  DrsDeviceGuard guard(g->device);
-  drs_sep_free(g);
-  if (nparts <= 0) return DRS_OK;   // partition removed
+// Tables of one level.  Vertices [part_ptr[j], part_ptr[j+1]) are the interior of part j, [part_ptr[nparts], n) the
+// separators; edges (src[e], dst[e]) in that numbering.  S_lists_out (optional): the sorted separator lists (separator-local
+// ids) of the parts, from which the next level's edges are formed.
+int make_plan(int n, int npad, int m, const int32_t* src, const int32_t* dst, int nparts, const int32_t* part_ptr, drs_sep_plan** out,
+              std::vector<std::vector<int32_t>>* S_lists_out) {
+  *out = nullptr;
   DRS_REQUIRE(part_ptr && part_ptr[0] == 0, DRS_ERR_ARG, "drs_graph_set_partition: part_ptr must start at 0");
   for (int j = 0; j < nparts; ++j)
     DRS_REQUIRE(part_ptr[j + 1] > part_ptr[j], DRS_ERR_ARG, "drs_graph_set_partition: part %d is empty or out of order", j);
-  const int n = g->n, sep0 = part_ptr[nparts];
+  const int sep0 = part_ptr[nparts];
   DRS_REQUIRE(sep0 <= n, DRS_ERR_RANGE, "drs_graph_set_partition: parts cover %d vertices, the graph has %d", sep0, n);
   std::vector<int32_t> part_of(n, -1);
   for (int j = 0; j < nparts; ++j)
     for (int v = part_ptr[j]; v < part_ptr[j + 1]; ++v) part_of[v] = j;
   std::vector<std::vector<int32_t>> S(nparts);
-  for (int e = 0; e < g->m; ++e) {
-    const int a = g->h_src[e], b = g->h_dst[e];
+  for (int e = 0; e < m; ++e) {
+    const int a = src[e], b = dst[e];
     const int pa = part_of[a], pb = part_of[b];
     if (pa >= 0 && pb >= 0) {
       DRS_REQUIRE(pa == pb, DRS_ERR_ARG, "drs_graph_set_partition: edge %d (%d - %d) joins the interiors of parts %d and %d", e, a, b,
@@ -524,6 +592,7 @@ extern "C" int drs_graph_set_partition(drs_graph* g, int32_t nparts, const int32
     }
   drs_sep_plan* p = new (std::nothrow) drs_sep_plan();
   DRS_REQUIRE(p, DRS_ERR_NOMEM, "drs_graph_set_partition: out of host memory");
+  p->n = n; p->npad = npad;
   p->nparts = nparts; p->sep0 = sep0; p->nsep = nsep;
   p->spad = std::max(TILE, round_up(nsep, TILE));
   p->pstart.assign(part_ptr, part_ptr + nparts); p->pend.assign(part_ptr + 1, part_ptr + nparts + 1);
@@ -534,19 +603,20 @@ extern "C" int drs_graph_set_partition(drs_graph* g, int32_t nparts, const int32
   p->kmax = KC;
   for (int j = 0; j < nparts; ++j) {
     const int nj = p->pend[j] - p->pstart[j], sj = (int)S[j].size();
-    p->sj[j] = sj; p->kpad[j] = round_up(sj, KC); p->koff[j] = ksum; ksum += p->kpad[j];
-    p->kmax = std::max(p->kmax, p->kpad[j]);
+    p->sj[j] = sj; p->kpad[j] = round_up(sj, KC / 2); p->koff[j] = ksum; ksum += p->kpad[j];
+    p->kmax = std::max(p->kmax, round_up(p->kpad[j], KC));
     p->qpad[j] = round_up(nj + sj, TILE); p->moff[j] = melems; melems += (int64_t)p->qpad[j] * p->qpad[j];
     p->maxq = std::max(p->maxq, nj + sj);
     p->maxnb = std::max(p->maxnb, p->qpad[j] / TILE);
     p->max_rowtiles = std::max(p->max_rowtiles, (nj + TILE - 1) / TILE);
-    p->cbase[j] = p->pstart[j] / TILE * TILE; p->wpad[j] = round_up(p->pend[j], TILE) - p->cbase[j];
-    p->apoff[j] = apelems; apelems += (int64_t)p->kpad[j] * p->wpad[j];
+    p->cbase[j] = p->pstart[j] / 4 * 4; p->wpad[j] = round_up(p->pend[j] - p->cbase[j], TILE);
+    p->apoff[j] = apelems; apelems += (int64_t)round_up(p->kpad[j], KC) * p->wpad[j];
+    for (int c0 = p->cbase[j]; c0 < p->pend[j]; c0 += TILE) { p->ct_part.push_back(j); p->ct_col0.push_back(c0); }
   }
-  p->ktot = std::max(TILE, round_up(ksum, TILE));
+  p->ktot = std::max(TILE, round_up(ksum + KC / 2, TILE));   // a half chunk is loaded whole: 16 readable columns past the last range
   p->m_elems = melems; p->ap_elems = apelems;
   p->sall.assign(p->ktot, -1);
-  p->sepcol.assign(std::max(g->npad - sep0, 1), 0);
+  p->sepcol.assign(std::max(npad - sep0, 1), 0);
   std::vector<char> have(std::max(nsep, 1), 0);
   for (int j = 0; j < nparts; ++j)
     for (int k = 0; k < (int)S[j].size(); ++k) {
@@ -554,31 +624,21 @@ extern "C" int drs_graph_set_partition(drs_graph* g, int32_t nparts, const int32
       p->sall[p->koff[j] + k] = r;
       if (!have[r]) { have[r] = 1; p->sepcol[r] = p->koff[j] + k; }
     }
-  p->ncoltiles = (sep0 + TILE - 1) / TILE;
-  p->ct_pass_ptr.assign(p->ncoltiles + 1, 0);
-  {
-    int j = 0;
-    for (int ct = 0; ct < p->ncoltiles; ++ct) {
-      const int c0 = ct * TILE, c1 = std::min(c0 + TILE, sep0);
-      while (j < nparts && p->pend[j] <= c0) ++j;
-      for (int q = j; q < nparts && p->pstart[q] < c1; ++q) p->ct_pass_part.push_back(q);
-      p->ct_pass_ptr[ct + 1] = (int)p->ct_pass_part.size();
-    }
-  }
-  if (p->ct_pass_part.empty()) p->ct_pass_part.push_back(0);
+  p->ncoltiles = (int)p->ct_part.size();
+  if (p->ct_part.empty()) { p->ct_part.push_back(0); p->ct_col0.push_back(0); }
   // one device arena for the tables
   struct Slice { const void* src; size_t bytes; size_t off; };
   std::vector<Slice> sl;
   size_t off = 0;
-  auto add = [&](const void* src, size_t bytes) { sl.push_back({src, bytes, off}); const size_t o = off; off = (off + std::max<size_t>(bytes, 4) + 255) & ~(size_t)255; return o; };
+  auto add = [&](const void* src_, size_t bytes) { sl.push_back({src_, bytes, off}); const size_t o = off; off = (off + std::max<size_t>(bytes, 4) + 255) & ~(size_t)255; return o; };
   const size_t o_ps = add(p->pstart.data(), 4 * nparts), o_pe = add(p->pend.data(), 4 * nparts), o_sj = add(p->sj.data(), 4 * nparts);
   const size_t o_kp = add(p->kpad.data(), 4 * nparts), o_ko = add(p->koff.data(), 4 * nparts), o_qp = add(p->qpad.data(), 4 * nparts);
   const size_t o_cb = add(p->cbase.data(), 4 * nparts), o_wp = add(p->wpad.data(), 4 * nparts);
   const size_t o_mo = add(p->moff.data(), 8 * nparts), o_ao = add(p->apoff.data(), 8 * nparts);
   const size_t o_sa = add(p->sall.data(), 4 * p->sall.size()), o_sc = add(p->sepcol.data(), 4 * p->sepcol.size());
-  const size_t o_cp = add(p->ct_pass_ptr.data(), 4 * p->ct_pass_ptr.size()), o_cq = add(p->ct_pass_part.data(), 4 * p->ct_pass_part.size());
+  const size_t o_cp = add(p->ct_part.data(), 4 * p->ct_part.size()), o_cq = add(p->ct_col0.data(), 4 * p->ct_col0.size());
   std::vector<unsigned char> img(off, 0);
-  for (const Slice& s : sl) std::memcpy(img.data() + s.off, s.src, s.bytes);
+  for (const Slice& x : sl) std::memcpy(img.data() + x.off, x.src, x.bytes);
   drs_count_alloc();
   if (cudaMalloc(&p->d_tables, img.size()) != cudaSuccess ||
       cudaMemcpy(p->d_tables, img.data(), img.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -593,7 +653,48 @@ extern "C" int drs_graph_set_partition(drs_graph* g, int32_t nparts, const int32
   p->d_cbase = (const int32_t*)(b + o_cb); p->d_wpad = (const int32_t*)(b + o_wp);
   p->d_moff = (const int64_t*)(b + o_mo); p->d_apoff = (const int64_t*)(b + o_ao);
   p->d_sall = (const int32_t*)(b + o_sa); p->d_sepcol = (const int32_t*)(b + o_sc);
-  p->d_ct_pass_ptr = (const int32_t*)(b + o_cp); p->d_ct_pass_part = (const int32_t*)(b + o_cq);
+  p->d_ct_part = (const int32_t*)(b + o_cp); p->d_ct_col0 = (const int32_t*)(b + o_cq);
+  { const char* e = getenv("DRS_SEP_NO_MIRROR"); p->no_mirror = e && e[0] == '1'; }
+  if (S_lists_out) *S_lists_out = std::move(S);
+  *out = p;
+  return DRS_OK;
+}
+
+}  // namespace
+
+void drs_sep_free(drs_graph* g) {
+  free_plan(g->sep);
+  g->sep = nullptr;
+}
+
+bool drs_sep_usable(const drs_graph* g) {
+  // exact arithmetic (any association of the sums gives the same bits) and separators that are a small part of the map
+  return g->sep && g->weights_integral && (int64_t)g->sep->nsep * 3 <= g->n && (int64_t)g->sep->ktot * 2 <= g->npad + 256;
+}
+
+extern "C" int drs_graph_set_partition(drs_graph* g, int32_t nparts, const int32_t* part_ptr, int32_t n_sep_parts,
+                                       const int32_t* sep_part_ptr) {
+  DRS_REQUIRE(g, DRS_ERR_ARG, "drs_graph_set_partition: null graph");
+  DrsDeviceGuard guard(g->device);
+  drs_sep_free(g);
+  if (nparts <= 0) return DRS_OK;   // partition removed
+  drs_sep_plan* p = nullptr;
+  std::vector<std::vector<int32_t>> S;
+  int rc = make_plan(g->n, g->npad, g->m, g->h_src.data(), g->h_dst.data(), nparts, part_ptr, &p, &S);
+  if (rc) return rc;
+  if (n_sep_parts > 0 && sep_part_ptr && p->nsep > 0) {
+    // level 2: the separator graph (separator-local ids): the map's edges inside S and a clique per S_j
+    std::vector<int32_t> s2, d2;
+    for (int e = 0; e < g->m; ++e)
+      if (g->h_src[e] >= p->sep0 && g->h_dst[e] >= p->sep0 && g->h_src[e] != g->h_dst[e]) {
+        s2.push_back(g->h_src[e] - p->sep0); d2.push_back(g->h_dst[e] - p->sep0);
+      }
+    for (const auto& lst : S)
+      for (size_t a = 0; a < lst.size(); ++a)
+        for (size_t b = a + 1; b < lst.size(); ++b) { s2.push_back(lst[a]); d2.push_back(lst[b]); }
+    rc = make_plan(p->nsep, p->spad, (int)s2.size(), s2.data(), d2.data(), n_sep_parts, sep_part_ptr, &p->child, nullptr);
+    if (rc) { free_plan(p); return rc; }
+  }
   g->sep = p;
   return DRS_OK;
 }
@@ -606,6 +707,14 @@ extern "C" int drs_sep_info(const drs_graph* g, int32_t* nparts, int32_t* nsep, 
   if (ktot) *ktot = p ? p->ktot : 0;
   if (kmax) *kmax = p ? p->kmax : 0;
   if (usable) *usable = drs_sep_usable(g) ? 1 : 0;
+  return DRS_OK;
+}
+
+extern "C" int drs_sep_info2(const drs_graph* g, int32_t* n_sep_parts, int32_t* n_top) {
+  DRS_REQUIRE(g, DRS_ERR_ARG, "drs_sep_info2: null graph");
+  const drs_sep_plan* c = g->sep ? g->sep->child : nullptr;
+  if (n_sep_parts) *n_sep_parts = c ? c->nparts : 0;
+  if (n_top) *n_top = c ? c->nsep : 0;
   return DRS_OK;
 }
 
@@ -642,6 +751,8 @@ struct Bisector {
   std::vector<int32_t> adj_ptr, adj;   // undirected adjacency (for the coordinate-free split)
   std::vector<int32_t> idx;
   std::vector<std::pair<int, int>> leaves;
+  std::vector<int32_t> leaf_super;     // group of each leaf at the second level: the subtree of <= leaves_per_super leaves it lies in
+  int leaves_per_super = 1, nsuper = 0;
   std::vector<int32_t> stamp_in, stamp_seen;
   int stamp = 0, seen_ctr = 0;
 
@@ -673,10 +784,11 @@ struct Bisector {
     std::copy(order.begin(), order.end(), idx.begin() + lo);
   }
 
-  void split(int lo, int hi) {
+  void split(int lo, int hi, int sup) {
     const int c = hi - lo;
-    if (c <= target) { if (c > 0) leaves.push_back({lo, hi}); return; }
     const int L = (c + target - 1) / target, Ll = L / 2;
+    if (sup < 0 && L <= leaves_per_super) sup = nsuper++;
+    if (c <= target) { if (c > 0) { leaves.push_back({lo, hi}); leaf_super.push_back(sup); } return; }
     const int mid = lo + (int)((int64_t)c * Ll / L);
     if (x) {
       double x0 = x[idx[lo]], x1 = x0, y0 = y[idx[lo]], y1 = y0;
@@ -690,8 +802,8 @@ struct Bisector {
     } else {
       bfs_order(lo, hi);
     }
-    split(lo, mid);
-    split(mid, hi);
+    split(lo, mid, sup);
+    split(mid, hi, sup);
   }
 };
 
@@ -703,7 +815,8 @@ struct Bisector {
 // Parts: recursive coordinate bisection (median cuts along the wider axis) when lng/lat are usable, otherwise recursive
 // bisection of breadth-first level structures.  Separators: a greedy vertex cover of the cut edges.
 extern "C" int drs_partition_order(int32_t n, int32_t m, const int32_t* src, const int32_t* dst, const double* lng, const double* lat,
-                                   int32_t target, int32_t* order_out, int32_t* part_ptr_out, int32_t max_parts, int32_t* nparts_out) {
+                                   int32_t target, int32_t* order_out, int32_t* part_ptr_out, int32_t max_parts, int32_t* nparts_out,
+                                   int32_t* sep_part_ptr_out, int32_t* n_sep_parts_out) {
   DRS_REQUIRE(n > 0 && m >= 0 && (m == 0 || (src && dst)) && order_out && part_ptr_out && nparts_out && target > 0 && max_parts > 0,
               DRS_ERR_ARG, "drs_partition_order: bad argument");
   for (int e = 0; e < m; ++e)
@@ -729,7 +842,12 @@ extern "C" int drs_partition_order(int32_t n, int32_t m, const int32_t* src, con
     for (int e = 0; e < m; ++e) if (src[e] != dst[e]) { b.adj[pos[src[e]]++] = dst[e]; b.adj[pos[dst[e]]++] = src[e]; }
     b.stamp_in.assign(n, 0); b.stamp_seen.assign(n, 0);
   }
-  b.split(0, n);
+  {
+    const int Ltot = (n + target - 1) / target;
+    const char* e = getenv("DRS_SEP_SUPER");
+    b.leaves_per_super = e ? std::max(1, atoi(e)) : std::max(2, (int)std::ceil(1.25 * std::sqrt((double)Ltot)));
+  }
+  b.split(0, n, -1);
   std::vector<int32_t> part(n);
   for (int j = 0; j < (int)b.leaves.size(); ++j)
     for (int i = b.leaves[j].first; i < b.leaves[j].second; ++i) part[b.idx[i]] = j;
@@ -754,9 +872,32 @@ extern "C" int drs_partition_order(int32_t n, int32_t m, const int32_t* src, con
       part_ptr_out[++np] = k;
     }
   }
+  *nparts_out = np;
+  // second level: a separator with a neighbour in another group of leaves belongs to the top separator set T; the others
+  // follow their own leaf's group.  Separators are numbered group by group, T last; in the separator graph (edges inside S
+  // and a clique per part's separator list) no edge joins two groups, so (groups, T) is a separator partition of it.
+  std::vector<char> top(n, 0);
+  for (int e = 0; e < m; ++e) {
+    const int u = src[e], v = dst[e];
+    if (b.leaf_super[part[u]] != b.leaf_super[part[v]]) { if (sep[u]) top[u] = 1; if (sep[v]) top[v] = 1; }
+  }
+  const int sep0 = k;
+  int nsp = 0;
+  std::vector<std::vector<int32_t>> group(std::max(b.nsuper, 1));
+  for (int j = 0; j < (int)b.leaves.size(); ++j)
+    for (int i = b.leaves[j].first; i < b.leaves[j].second; ++i) {
+      const int v = b.idx[i];
+      if (sep[v] && !top[v]) group[std::max(b.leaf_super[j], 0)].push_back(v);
+    }
+  if (sep_part_ptr_out) sep_part_ptr_out[0] = 0;
+  for (const auto& grp : group) {
+    if (grp.empty()) continue;
+    for (int v : grp) order_out[k++] = v;
+    if (sep_part_ptr_out && nsp < max_parts) sep_part_ptr_out[++nsp] = k - sep0;
+  }
   for (const auto& lf : b.leaves)
     for (int i = lf.first; i < lf.second; ++i)
-      if (sep[b.idx[i]]) order_out[k++] = b.idx[i];
-  *nparts_out = np;
+      if (sep[b.idx[i]] && top[b.idx[i]]) order_out[k++] = b.idx[i];
+  if (n_sep_parts_out) *n_sep_parts_out = sep_part_ptr_out ? nsp : 0;
   return DRS_OK;
 }

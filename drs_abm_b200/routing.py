@@ -197,6 +197,11 @@ def locality_order(n, src, dst, lng=None, lat=None, native=False):
         return np.asarray(reverse_cuthill_mckee(A, symmetric_mode=True), dtype=np.int32)
 
 
+# below this many separator vertices their graph is closed by the plain blocked Floyd-Warshall (a few rounds); above, by
+# the partitioned build itself one level up (DRS_SEP_LEVEL2_MIN overrides)
+SECOND_LEVEL_MIN_SEPARATORS = int(os.environ.get("DRS_SEP_LEVEL2_MIN", 1024))
+
+
 def default_part_target(n):
     """Vertices per part of the separator partition: the expansion stage costs n^2 x (separators around a part, which
     grow like the square root of the part) and the separator closure (number of separators)^3, which shrinks with
@@ -204,8 +209,9 @@ def default_part_target(n):
     return int(min(2048, max(192, n // 96)))
 
 
-def partition_order(n, src, dst, lng=None, lat=None, target=None):
-    """(order, part_ptr) of the part-major device numbering (include/drs_b200.h: drs_partition_order)."""
+def partition_order(n, src, dst, lng=None, lat=None, target=None, second_level=False):
+    """(order, part_ptr) of the part-major device numbering (include/drs_b200.h: drs_partition_order); with second_level
+    also the group boundaries of the separators (relative to the first separator id)."""
     lib = _lib.load()
     target = int(target or default_part_target(n))
     src, dst = _lib.as_i32(src), _lib.as_i32(dst)
@@ -219,10 +225,14 @@ def partition_order(n, src, dst, lng=None, lat=None, target=None):
     order = np.empty(n, dtype=np.int32)
     max_parts = max(4, 4 * (n // target + 1))
     part_ptr = np.zeros(max_parts + 1, dtype=np.int32)
-    nparts = C.c_int32(0)
+    nparts, nsp = C.c_int32(0), C.c_int32(0)
+    sep_ptr = np.zeros(max_parts + 1, dtype=np.int32)
     _lib.check(lib.drs_partition_order(n, len(src), _lib.ptr_i32(src), _lib.ptr_i32(dst),
                                        _lib.ptr_f64(x) if x is not None else None, _lib.ptr_f64(y) if y is not None else None,
-                                       target, _lib.ptr_i32(order), _lib.ptr_i32(part_ptr), max_parts, C.byref(nparts)), lib)
+                                       target, _lib.ptr_i32(order), _lib.ptr_i32(part_ptr), max_parts, C.byref(nparts),
+                                       _lib.ptr_i32(sep_ptr), C.byref(nsp)), lib)
+    if second_level:
+        return order, part_ptr[:nparts.value + 1].copy(), sep_ptr[:nsp.value + 1].copy()
     return order, part_ptr[:nparts.value + 1].copy()
 
 
@@ -236,7 +246,7 @@ class RoadGraph(object):
     """
 
     def __init__(self, data, mode=_lib.MODE_F32, algorithm=_lib.APSP_AUTO, pred=_lib.PRED_LAZY, numbering="partition",
-                 part_target=None):
+                 part_target=None, second_level_min=None):
         if not isinstance(data, RoadGraphData):
             raise TypeError("RoadGraph needs RoadGraphData (use RoadGraph.Read_GML)")
         self.n, self.m = data.n, data.m
@@ -263,7 +273,8 @@ class RoadGraph(object):
             raise ValueError("numbering must be 'partition', 'locality' or 'input'")
         self.numbering = numbering
         self.part_target = int(os.environ.get("DRS_SEP_TARGET", part_target or 0)) or None
-        self._part_ptr = None
+        self._part_ptr = self._sep_part_ptr = None
+        self.second_level_min = SECOND_LEVEL_MIN_SEPARATORS if second_level_min is None else int(second_level_min)
         self._new_of_old = self._old_of_new = None
 
     # ------------------------------------------------------------------ igraph surface
@@ -393,8 +404,8 @@ class RoadGraph(object):
         if self.numbering in ("locality", "partition") and self._new_of_old is None:
             order = None
             if self.numbering == "partition":
-                order, self._part_ptr = partition_order(self.n, self._src, self._dst, self._vattrs.get("lng"),
-                                                        self._vattrs.get("lat"), self.part_target)
+                order, self._part_ptr, self._sep_part_ptr = partition_order(self.n, self._src, self._dst, self._vattrs.get("lng"),
+                                                                            self._vattrs.get("lat"), self.part_target, True)
             else:
                 order = locality_order(self.n, self._src, self._dst, self._vattrs.get("lng"), self._vattrs.get("lat"))
             self._old_of_new = np.ascontiguousarray(order, dtype=np.int32)
@@ -435,8 +446,10 @@ class RoadGraph(object):
                                             _lib.ptr_i32(dst), _lib.ptr_f64(tt), _lib.ptr_f64(length), C.byref(h)), lib)
             self._handle = h
             if self._part_ptr is not None:
-                pp = _lib.as_i32(self._part_ptr)
-                _lib.check(lib.drs_graph_set_partition(h, len(pp) - 1, _lib.ptr_i32(pp)), lib)
+                pp, sp = _lib.as_i32(self._part_ptr), _lib.as_i32(self._sep_part_ptr)
+                two = len(sp) > 2 and int(self.n - pp[-1]) >= self.second_level_min
+                _lib.check(lib.drs_graph_set_partition(h, len(pp) - 1, _lib.ptr_i32(pp), len(sp) - 1 if two else 0,
+                                                       _lib.ptr_i32(sp) if two else None), lib)
             self._weight_attr = attr
             self._weights_dirty = False
             self._valid = False

@@ -132,10 +132,18 @@ int drs_apsp_set_algorithm(drs_graph* g, int32_t algorithm);
  * ids are igraph's load order there, lib/RoutingEngine.py:48-60); the bindings translate ids at every call. */
 int drs_partition_order(int32_t n, int32_t m, const int32_t* src, const int32_t* dst, const double* lng,
                         const double* lat, int32_t target, int32_t* order_out, int32_t* part_ptr_out,
-                        int32_t max_parts, int32_t* nparts_out);
+                        int32_t max_parts, int32_t* nparts_out, int32_t* sep_part_ptr_out, int32_t* n_sep_parts_out);
+/* Second level (sep_part_ptr_out may be NULL): the separator vertices themselves are numbered in groups that follow
+ * the upper levels of the bisection tree, the "top" separators (those with a neighbour in another group) last;
+ * sep_part_ptr_out[0..n_sep_parts] are the group boundaries relative to the first separator id.  (groups, top) is a
+ * separator partition of the separator graph, which lets the build close that graph the way it closes the map. */
 /* Declares the partition of a graph created in that numbering (part_ptr as above, nparts + 1 entries; nparts = 0
- * removes it).  DRS_ERR_ARG if an edge joins two interiors.  Builds the device tables of the SEP build. */
-int drs_graph_set_partition(drs_graph* g, int32_t nparts, const int32_t* part_ptr);
+ * removes it; n_sep_parts = 0 / sep_part_ptr = NULL: no second level).  DRS_ERR_ARG if an edge joins two interiors.
+ * Builds the device tables of the SEP build. */
+int drs_graph_set_partition(drs_graph* g, int32_t nparts, const int32_t* part_ptr, int32_t n_sep_parts,
+                            const int32_t* sep_part_ptr);
+/* groups and top separators of the second level (0, 0 without one) */
+int drs_sep_info2(const drs_graph* g, int32_t* n_sep_parts, int32_t* n_top);
 /* parts, separator vertices, sum and maximum of the per-part separator counts (padded), and whether AUTO would use it */
 int drs_sep_info(const drs_graph* g, int32_t* nparts, int32_t* nsep, int32_t* ktot, int32_t* kmax, int32_t* usable);
 /* Rows [row0, row0 + nrows) (multiples of DRS_FW_TILE) of the matrix by the SEP build into local_dev (nrows x ld, ld = npad):

@@ -1,0 +1,175 @@
+"""Separator-partitioned build (csrc/sep_apsp.cu, DRS_APSP_SEP) through the C-ABI: the matrix it writes is the matrix of
+the oracle (scipy-free restatement of the reference's igraph Dijkstra, oracle/routing_oracle.py) and of the SSSP build,
+bit for bit, on integer-weighted maps -- undirected, directed, disconnected, with and without coordinates, one part or
+many, in both element types, whole or by row shards.  Replaces lib/RoutingEngine.py:87,199,212 and
+lib/optimUtils.py:528,531,659 like the other builders."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import golden_map_path, oracle_graph, oracle_graph_from_data
+
+pytestmark = pytest.mark.gpu
+
+
+def _data(n, src, dst, tt, directed=False, coords=None):
+    from drs_abm_b200.gml import RoadGraphData
+    vattrs = {"name": [str(i) for i in range(n)]}
+    if coords is not None:
+        vattrs["lng"], vattrs["lat"] = [float(c) for c in coords[0]], [float(c) for c in coords[1]]
+    tt = np.asarray(tt, dtype=np.float64)
+    return RoadGraphData(n, directed, src, dst, vattrs, {"ttmedian": tt, "length": 10.0 * tt})
+
+
+def _random_planar(n_side, seed, directed=False, coords=True, drop=0.1, islands=1):
+    """Grid with random integer weights, a fraction of the edges dropped (components are kept: unreachable pairs are part
+    of the case), optionally several disjoint copies, optionally one-way arcs with independent weights."""
+    rs = np.random.RandomState(seed)
+    src, dst, xs, ys = [], [], [], []
+    for isl in range(islands):
+        base = isl * n_side * n_side
+        for i in range(n_side):
+            for j in range(n_side):
+                xs.append(j + isl * (n_side + 3)); ys.append(i)
+                if j + 1 < n_side and rs.rand() > drop:
+                    src.append(base + i * n_side + j); dst.append(base + i * n_side + j + 1)
+                if i + 1 < n_side and rs.rand() > drop:
+                    src.append(base + i * n_side + j); dst.append(base + (i + 1) * n_side + j)
+    src, dst = np.array(src), np.array(dst)
+    if directed:
+        back = rs.rand(len(src)) < 0.8
+        src, dst = np.concatenate([src, dst[back]]), np.concatenate([dst, src[back]])
+    tt = rs.randint(5, 90, size=len(src)).astype(np.float64)
+    n = islands * n_side * n_side
+    perm = rs.permutation(n)                     # the caller's numbering carries no locality
+    inv = np.empty(n, dtype=np.int64); inv[perm] = np.arange(n)
+    cs = (np.array(xs)[inv], np.array(ys)[inv]) if coords else None
+    return _data(n, perm[src], perm[dst], tt, directed, cs)
+
+
+def _matrices(data, target, mode, algorithms, levels=1):
+    from drs_abm_b200 import _lib
+    from drs_abm_b200.routing import RoadGraph
+    out = {}
+    for algo in algorithms:
+        G = RoadGraph(data, mode=mode, algorithm=algo, numbering="partition", part_target=target,
+                      second_level_min=1 if levels == 2 else 10 ** 9)
+        out[algo] = G.dist_rows(0, G.n)
+        if algo == _lib.APSP_SEP:
+            info = [C.c_int32(0) for _ in range(7)]
+            _lib.check(G._lib.drs_sep_info(G._handle, *[C.byref(x) for x in info[:5]]), G._lib)
+            _lib.check(G._lib.drs_sep_info2(G._handle, C.byref(info[5]), C.byref(info[6])), G._lib)
+            out["parts"], out["nsep"], out["groups"], out["top"] = info[0].value, info[1].value, info[5].value, info[6].value
+        G.close()
+    return out
+
+
+@pytest.mark.parametrize("name", ["g8_int", "g20_int", "g20_uniform"])
+@pytest.mark.parametrize("target", [16, 60, 4096])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_sep_matrix_equals_the_oracle_on_the_golden_maps(name, target, mode):
+    from drs_abm_b200 import _lib
+    from drs_abm_b200.gml import read_gml
+    got = _matrices(read_gml(golden_map_path(name)), target, mode, [_lib.APSP_SEP])
+    assert np.array_equal(got[_lib.APSP_SEP], oracle_graph(name).dist_matrix())
+    assert got["parts"] >= (1 if target == 4096 else 2)
+
+
+CASES = {
+    "undirected_24": dict(n_side=24, seed=3),
+    "directed_20": dict(n_side=20, seed=4, directed=True),
+    "no_coordinates_22": dict(n_side=22, seed=5, coords=False),
+    "islands_3x12": dict(n_side=12, seed=6, islands=3, drop=0.2),
+    "directed_islands_no_coordinates": dict(n_side=14, seed=7, islands=2, directed=True, coords=False, drop=0.25),
+}
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+@pytest.mark.parametrize("target", [24, 130])
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("levels", [1, 2])
+def test_sep_matrix_equals_oracle_and_sssp_on_irregular_maps(case, target, mode, levels):
+    from drs_abm_b200 import _lib
+    data = _random_planar(**CASES[case])
+    got = _matrices(data, target, mode, [_lib.APSP_SEP, _lib.APSP_SSSP], levels)
+    want = oracle_graph_from_data(data).dist_matrix()
+    assert np.array_equal(got[_lib.APSP_SSSP], want)
+    assert np.array_equal(got[_lib.APSP_SEP], want)              # +inf where unreachable, on both sides
+    assert got["parts"] >= 3 and got["nsep"] > 0
+    if levels == 2 and target == 24:
+        assert got["groups"] >= 2 and 0 < got["top"] < got["nsep"]   # the separator graph really went through level 2
+
+
+def test_sep_on_the_5k_city_equals_sssp_and_paths_follow():
+    """C2 (5 040 vertices, 27 parts): whole matrix on the device equal to the SSSP build's; path queries, which read the
+    matrix through the canonical predecessor rule, return the oracle's edge ids."""
+    import torch
+    from drs_abm_b200 import _lib, synth
+    from drs_abm_b200.apsp_dist import CudaTiles, build_sharded
+    from drs_abm_b200.routing import RoadGraph
+    data = synth.config_graph("C2")
+    G = RoadGraph(data, numbering="partition")
+    h = G.upload()
+    tiles = CudaTiles(h, _lib.MODE_F32)
+    npad = (data.n + 127) // 128 * 128
+    a, _, _ = build_sharded(tiles, npad, algorithm="sep", with_pred=False)
+    b, _, _ = build_sharded(tiles, npad, algorithm="sssp", with_pred=False)
+    assert torch.equal(a, b)
+    # two row shards of unequal size give the same rows as the whole build
+    top = torch.empty((1280, npad), dtype=torch.float32, device="cuda")
+    rest = torch.empty((npad - 1280, npad), dtype=torch.float32, device="cuda")
+    tiles.sep_rows(top, 0); tiles.sep_rows(rest, 1280); torch.cuda.synchronize()
+    assert torch.equal(torch.cat([top, rest]), a)
+    assert G.algorithm == _lib.APSP_AUTO
+    G.build()                                                   # AUTO picks the partitioned build on this map
+    prof = np.zeros(8)
+    _lib.check(G._lib.drs_apsp_sep_profile(h, _lib.ptr_f64(prof)), G._lib)
+    assert prof.sum() > 0
+    O = oracle_graph_from_data(data)
+    rs = np.random.RandomState(2)
+    for _ in range(40):
+        s, t = int(rs.randint(data.n)), int(rs.randint(data.n))
+        assert G.epath(s, t) == O.epath(s, t)
+    G.close()
+
+
+def test_sep_is_refused_on_float_travel_times_and_auto_avoids_it():
+    from drs_abm_b200 import _lib, synth
+    from drs_abm_b200.routing import RoadGraph
+    data = synth.config_graph("C1_float")
+    G = RoadGraph(data, algorithm=_lib.APSP_SEP, numbering="partition", part_target=64)
+    with pytest.raises(_lib.DrsError):
+        G.build()
+    G.close()
+    G = RoadGraph(data, numbering="partition", part_target=64)    # AUTO: SSSP on this map
+    G.build()
+    info = [C.c_int32(0) for _ in range(5)]
+    _lib.check(G._lib.drs_sep_info(G._handle, *[C.byref(x) for x in info]), G._lib)
+    assert info[0].value > 1 and info[4].value == 0
+    want = oracle_graph_from_data(data).dist_matrix()
+    got = G.dist_rows(0, G.n)
+    assert np.max(np.abs(got - want) / np.maximum(want, 1e-12)) < 1e-5
+    G.close()
+
+
+def test_partition_is_validated_and_follows_weight_updates():
+    from drs_abm_b200 import _lib, synth
+    from drs_abm_b200.routing import RoadGraph
+    data = synth.config_graph("C1")
+    G = RoadGraph(data, algorithm=_lib.APSP_SEP, numbering="partition", part_target=50)
+    h = G.upload()
+    lib = G._lib
+    bad = _lib.as_i32([0, 200, 400])                             # two "interiors" that are joined by edges
+    assert lib.drs_graph_set_partition(h, 2, _lib.ptr_i32(bad), 0, None) == _lib.ERR_ARG
+    assert b"joins the interiors" in lib.drs_last_error()
+    pp = _lib.as_i32(G._part_ptr)
+    _lib.check(lib.drs_graph_set_partition(h, len(pp) - 1, _lib.ptr_i32(pp), 0, None), lib)
+    first = G.dist_rows(0, G.n)
+    tt = np.array(G._eattrs["ttmedian"]); tt[::3] += 7.0
+    G.es["ttmedian"] = tt.tolist()                               # the igraph-style write invalidates the matrix
+    second = G.dist_rows(0, G.n)
+    from drs_abm_b200.gml import RoadGraphData
+    d2 = RoadGraphData(data.n, data.directed, data.src, data.dst, data.vattrs, dict(data.eattrs, ttmedian=tt))
+    assert np.array_equal(second, oracle_graph_from_data(d2).dist_matrix()) and not np.array_equal(first, second)
+    G.close()

@@ -336,3 +336,35 @@ def test_native_rtv_level_equals_the_references_loops(k):
     z = np.zeros(2, dtype=np.int32)
     assert lib.drs_rtv_level(1, 5, _lib.ptr_i32(z), _lib.ptr_i32(z), None, 0, None, 0, None, None,
                              C.byref(n_tasks), C.byref(n_saved)) == _lib.ERR_CAPACITY
+
+
+def test_partition_order_gives_a_valid_separator_partition():
+    """drs_partition_order (host code of the library, no GPU): a permutation; part interiors are contiguous id ranges; no edge
+    joins two interiors; separators are a small share of a grid city; works without coordinates (breadth-first bisection),
+    on disconnected maps, on maps smaller than one part and on edgeless ones."""
+    from drs_abm_b200 import synth
+    from drs_abm_b200.routing import default_part_target, partition_order
+
+    def check(n, src, dst, lng, lat, target):
+        order, pp = partition_order(n, src, dst, lng, lat, target)
+        assert sorted(order.tolist()) == list(range(n)) and pp[0] == 0 and np.all(np.diff(pp) > 0) and pp[-1] <= n
+        new_of_old = np.empty(n, dtype=np.int64); new_of_old[order] = np.arange(n)
+        part = np.searchsorted(pp, np.arange(n), side="right") - 1
+        part[pp[-1]:] = -1
+        ps, pt = part[new_of_old[np.asarray(src, dtype=np.int64)]], part[new_of_old[np.asarray(dst, dtype=np.int64)]]
+        assert not np.any((ps >= 0) & (pt >= 0) & (ps != pt))
+        assert np.diff(pp).max() <= target
+        return len(pp) - 1, n - int(pp[-1])
+
+    d = synth.config_graph("C2")
+    lng, lat = d.vattrs["lng"], d.vattrs["lat"]
+    parts, nsep = check(d.n, d.src, d.dst, lng, lat, 200)
+    assert parts >= 20 and nsep < d.n // 6
+    parts_b, nsep_b = check(d.n, d.src, d.dst, None, None, 200)          # no coordinates
+    assert parts_b >= 20 and nsep_b < d.n // 4
+    assert check(d.n, d.src, d.dst, lng, lat, 10 ** 6) == (1, 0)         # one part, no separator
+    two = np.concatenate([d.src, d.src + d.n]), np.concatenate([d.dst, d.dst + d.n])   # two disjoint copies
+    check(2 * d.n, two[0], two[1], None, None, 300)
+    check(2 * d.n, two[0], two[1], list(lng) * 2, list(lat) * 2, 300)    # coincident coordinates
+    assert check(5, [], [], None, None, 2)[1] == 0                       # no edges: no separators
+    assert 192 <= default_part_target(50171) <= 2048

@@ -35,6 +35,9 @@ for name in args.configs.split(","):
         npad = (data.n + 127) // 128 * 128
         out = {"config": name, "target": target, "n": data.n, "upload_s": round(t_up, 4), "parts": info[0].value, "nsep": info[1].value,
                "ktot": info[2].value, "kmax": info[3].value, "usable": info[4].value}
+        i2 = [C.c_int32(0), C.c_int32(0)]
+        _lib.check(lib.drs_sep_info2(h, C.byref(i2[0]), C.byref(i2[1])), lib)
+        out["groups"], out["top"] = i2[0].value, i2[1].value
         res = {}
         for algo in ("sep", "sssp"):
             ms = []
