@@ -674,7 +674,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C3", choices=sorted(WORKLOADS))
     ap.add_argument("--mode", default="f32", choices=["f32", "i32"])
-    ap.add_argument("--algorithm", default="auto", choices=["auto", "fw", "sssp"],
+    ap.add_argument("--algorithm", default="auto", choices=["auto", "fw", "sssp", "sep"],
                     help="APSP algorithm of the headline value; auto = the library default (SSSP on sparse road networks). "
                          "The blocked Floyd-Warshall is always measured too and reported under \"fw\".")
     ap.add_argument("--pred-matrix", action="store_true",
@@ -726,7 +726,12 @@ def main():
         torch.cuda.synchronize()
 
     sparse = 2 * data.m <= 16 * data.n                    # the library's AUTO rule (drs_apsp_build)
-    algo = args.algorithm if args.algorithm != "auto" else ("sssp" if sparse else "fw")
+    import ctypes as C
+    sep_info = [C.c_int32(0) for _ in range(7)]
+    _lib.check(lib.drs_sep_info(handle, *[C.byref(x) for x in sep_info[:5]]), lib)
+    _lib.check(lib.drs_sep_info2(handle, C.byref(sep_info[5]), C.byref(sep_info[6])), lib)
+    sep_usable = bool(sep_info[4].value)
+    algo = args.algorithm if args.algorithm != "auto" else ("sep" if sep_usable else "sssp" if sparse else "fw")
 
     comm = [None]
 
@@ -782,7 +787,7 @@ def main():
     sec, launches, checksum = timed_builds(algo, args.warmup, args.steps)
     clocks = sampler.stop(args.gpus) if rank == 0 else None
     # the other algorithm, for the record (the blocked FW is the north-star path; SSSP the sparse-graph default)
-    other = "fw" if algo == "sssp" else ("sssp" if sparse else None)
+    other = "fw" if algo in ("sssp", "sep") else ("sssp" if sparse else None)
     other_res = None
     if other is not None:
         sampler2 = ClockSampler()
@@ -790,6 +795,7 @@ def main():
             sampler2.start()
         other_res = timed_builds(other, 3 if other == "sssp" else 1, max(1, min(args.steps, 2)))
         other_clocks = sampler2.stop(args.gpus) if rank == 0 else None
+    sssp_beside = timed_builds("sssp", 2, max(1, min(args.steps, 3))) if algo == "sep" else None
     p2p_res = None
     if world > 1 and not args.no_p2p:
         p2p_res = timed_builds("fw_p2p", 1, max(1, min(args.steps, 2)))
@@ -803,7 +809,7 @@ def main():
         torch.cuda.empty_cache()
         barrier()
         t0 = time.time()
-        G2 = RoadGraph(data, mode=mode, algorithm={"fw": _lib.APSP_FW, "sssp": _lib.APSP_SSSP}[algo],
+        G2 = RoadGraph(data, mode=mode, algorithm={"fw": _lib.APSP_FW, "sssp": _lib.APSP_SSSP, "sep": _lib.APSP_SEP}[algo],
                        pred=_lib.PRED_MATRIX if args.pred_matrix else _lib.PRED_LAZY)
         h2 = G2.upload()
         o, d = synth.random_od_pairs(data.n, 4096, 3)
@@ -859,14 +865,27 @@ def main():
                 "config": {"workload": WORKLOADS[args.config], "n_nodes": data.n, "n_edges": data.m, "npad": npad,
                            "predecessors": "matrix built inside the timed step" if args.pred_matrix else
                                            "lazy (canonical rule evaluated per hop by the path queries; no predecessor matrix)",
-                           "apsp_algorithm": {"sssp": "batched delta-stepping SSSP, one CTA per source (library default on sparse graphs)",
-                                              "fw": "blocked min-plus Floyd-Warshall"}[algo],
-                           "l2": "inputs larger than L2: the %d MB matrix is written (SSSP) / streamed once per round (FW); L2 is 126 MB" % (npad * npad * 4 >> 20),
+                           "apsp_algorithm": {"sssp": "batched delta-stepping SSSP, one CTA per source (library default on sparse graphs with non-integer travel times)",
+                                              "fw": "blocked min-plus Floyd-Warshall",
+                                              "sep": "blocked min-plus Floyd-Warshall in nested-dissection order over a vertex-separator partition "
+                                                     "(%d parts, %d separator vertices, second level: %d groups + %d top separators): part closures, separator-graph "
+                                                     "closure, then every output tile as ONE 128x128x|S_j| min-plus product, written once; mirrored tiles on "
+                                                     "undirected maps at N = 1 (library default on integer-weighted maps: bit-identical to SSSP / FW)"
+                                                     % (sep_info[0].value, sep_info[1].value, sep_info[5].value, sep_info[6].value)}[algo],
+                           "l2": "inputs larger than L2: the %d MB matrix is written once (SEP, SSSP) / streamed once per round (FW); L2 is 126 MB" % (npad * npad * 4 >> 20),
                            "parallelism": ("source rows sharded x%d, no collective" % world) if algo == "sssp" else
+                                          ("part and separator closures replicated on every rank, output row blocks sharded x%d, no collective" % world) if algo == "sep" else
                                           "row-block shards x%d, NCCL pivot-panel broadcast%s" % (world, "" if args.no_lookahead else " with look-ahead")},
                 "gpu_launches": launches, "clocks": clocks, "checksum": checksum, "alu_peak_relax_per_s": alu,
                 "peaks": peaks_src}
-        prof_fw = prof_sssp = None
+        prof_fw = prof_sssp = prof_sep = None
+        if world == 1 and algo == "sep":
+            Gp = RoadGraph(data, mode=mode, algorithm=_lib.APSP_SEP)
+            Gp.build(); Gp._valid = False; Gp.build()
+            prof_sep, work_sep = np.zeros(8), np.zeros(5)
+            _lib.check(lib.drs_apsp_sep_profile(Gp._handle, _lib.ptr_f64(prof_sep)), lib)
+            _lib.check(lib.drs_sep_work(Gp._handle, _lib.ptr_f64(work_sep)), lib)
+            Gp.close()
         if world == 1:
             # per-kernel device times from the library's own CUDA events (public single-GPU build)
             def profile(algorithm):
@@ -879,7 +898,29 @@ def main():
             if algo == "sssp" or other == "sssp":
                 prof_sssp = profile(_lib.APSP_SSSP)
             prof_fw = profile(_lib.APSP_FW)
-        if algo == "sssp":
+        if algo == "sep":
+            line["phase_ms"] = dict(zip(["fill_scatter", "part_closures", "extract", "separator_closure", "gathers",
+                                         "vertex_to_separator_rows", "output_tiles", "separator_columns"], [float(x) for x in prof_sep])) \
+                if prof_sep is not None else None
+            if prof_sep is not None:
+                t_k = prof_sep[6] * 1e-3
+                tile_stages_ms = float(prof_sep[1] + prof_sep[3] + prof_sep[5] + prof_sep[6])
+                line["roofline"] = {
+                    "bound": "alu", "achieved": 2 * work_sep[4] / t_k / 1e12, "peak": 2 * best_alu / 1e12, "unit": "Tlaneop/s",
+                    "frac": (work_sep[4] / t_k) / best_alu, "executed_frac": (work_sep[3] / t_k) / best_alu,
+                    "kernel": "sep_expand_kernel", "kernel_ms": float(prof_sep[6]), "share_of_step": float(prof_sep[6]) / float(prof_sep.sum()),
+                    "algorithmic_relaxations_per_launch": float(work_sep[4]), "executed_relaxations_per_launch": float(work_sep[3]),
+                    "traffic": NCU_TRAFFIC.get("sep_expand_kernel", (None, None))[0] if (args.config == "C3" and args.mode == "f32") else None,
+                    "traffic_source": NCU_TRAFFIC.get("sep_expand_kernel", (None, None))[1],
+                    "hbm": {"compulsory_bytes": 4.0 * npad * npad, "GBps_over_the_whole_build": 4.0 * npad * npad / sec / 1e9,
+                            "frac_of_peak": 4.0 * npad * npad / sec / 1e9 / peaks["hbm_gbs"]},
+                    "all_tile_stages": {"relaxations": float(work_sep[0] + work_sep[1] + work_sep[2] + work_sep[3]), "ms": tile_stages_ms,
+                                        "frac": float(work_sep[0] + work_sep[1] + work_sep[2] + work_sep[3]) / (tile_stages_ms * 1e-3) / best_alu},
+                    "note": "min-plus is not a tensor-core operation (north_star): the bound is the add+min issue rate of the SMs.  2 lane-ops "
+                            "per relaxation; algorithmic relaxations of the dominant kernel = n * sum_j n_j * |S_j| (halved: mirrored tiles on the "
+                            "undirected map), executed = the same with |S_j| padded to 16 and part widths to 128-column tiles; peak = best "
+                            "register-resident add+min stream measured in this run (drs_alu_peak)"}
+        elif algo == "sssp":
             t_k = prof_sssp[2] * 1e-3 if prof_sssp is not None else sec * world
             line["roofline"] = sssp_roofline(t_k)
             if prof_sssp is not None:
@@ -903,6 +944,11 @@ def main():
                 t_k = prof_sssp[2] * 1e-3 if prof_sssp is not None else osec * world
                 sub["roofline"] = sssp_roofline(t_k)
                 line["sssp"] = sub
+        if sssp_beside is not None:
+            ssec, slaunch, scs = sssp_beside
+            line["sssp"] = {"value": ssec, "unit": "s", "gpu_launches": slaunch, "checksum": scs, "same_matrix_as_headline": bool(scs == checksum),
+                            "roofline": sssp_roofline(ssec * world),
+                            "note": "round 1's headline builder on the same device graph (it keeps float-weighted maps and C5)"}
         if p2p_res is not None:
             psec, plaunch, pcs = p2p_res
             line["fw_p2p"] = {"value": psec, "unit": "s", "gpu_launches": plaunch, "checksum": pcs,

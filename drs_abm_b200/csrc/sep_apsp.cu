@@ -692,8 +692,9 @@ extern "C" int drs_graph_set_partition(drs_graph* g, int32_t nparts, const int32
     for (const auto& lst : S)
       for (size_t a = 0; a < lst.size(); ++a)
         for (size_t b = a + 1; b < lst.size(); ++b) { s2.push_back(lst[a]); d2.push_back(lst[b]); }
-    rc = make_plan(p->nsep, p->spad, (int)s2.size(), s2.data(), d2.data(), n_sep_parts, sep_part_ptr, &p->child, nullptr);
-    if (rc) { free_plan(p); return rc; }
+    // a grouping that is not a separator partition of this graph (a caller's own partition may be one) is not used:
+    // the separator graph is then closed by the plain blocked Floyd-Warshall
+    if (make_plan(p->nsep, p->spad, (int)s2.size(), s2.data(), d2.data(), n_sep_parts, sep_part_ptr, &p->child, nullptr)) p->child = nullptr;
   }
   g->sep = p;
   return DRS_OK;
@@ -715,6 +716,44 @@ extern "C" int drs_sep_info2(const drs_graph* g, int32_t* n_sep_parts, int32_t* 
   const drs_sep_plan* c = g->sep ? g->sep->child : nullptr;
   if (n_sep_parts) *n_sep_parts = c ? c->nparts : 0;
   if (n_top) *n_top = c ? c->nsep : 0;
+  return DRS_OK;
+}
+
+namespace {
+// relaxations (one add + one min) the stages of a level execute: [0] part closures, [1] separator closure, [2] vertex ->
+// separator rows, [3] output tiles as launched, [4] output tiles without padding (n * sum_j n_j * s_j, halved when mirrored)
+void level_work(const drs_sep_plan* p, bool directed, double* w) {
+  w[0] = w[1] = w[2] = w[3] = w[4] = 0;
+  for (int j = 0; j < p->nparts; ++j) {
+    const double q = p->qpad[j];
+    w[0] += q * q * q;
+    w[2] += (double)round_up(p->pend[j] - p->pstart[j], TILE) * p->ktot * p->kpad[j];
+    w[4] += (double)p->n * (p->pend[j] - p->pstart[j]) * p->sj[j];
+  }
+  if (p->nsep > 0) {
+    if (p->child) {
+      double c[5];
+      level_work(p->child, directed, c);
+      w[1] = c[0] + c[1] + c[2] + c[3];
+    } else {
+      w[1] = (double)p->spad * p->spad * p->spad;
+    }
+  }
+  const bool mirror = !directed && !p->no_mirror;
+  for (int ct = 0; ct < p->ncoltiles; ++ct) {
+    const int j = p->ct_part[ct], c0 = p->ct_col0[ct];
+    const int c1 = c0 + std::min(p->pend[j] - c0, TILE);
+    for (int r0 = 0; r0 < p->npad; r0 += TILE)
+      if (!mirror || c1 > r0 || r0 + TILE > p->sep0) w[3] += (double)TILE * TILE * p->kpad[j];
+  }
+  if (mirror) w[4] *= 0.5;
+}
+}  // namespace
+
+extern "C" int drs_sep_work(const drs_graph* g, double* relax5) {
+  DRS_REQUIRE(g && relax5, DRS_ERR_ARG, "drs_sep_work: null argument");
+  DRS_REQUIRE(g->sep, DRS_ERR_STATE, "drs_sep_work: the graph has no partition");
+  level_work(g->sep, g->directed != 0, relax5);
   return DRS_OK;
 }
 
@@ -860,6 +899,20 @@ extern "C" int drs_partition_order(int32_t n, int32_t m, const int32_t* src, con
     if (part[u] == part[v] || sep[u] || sep[v]) continue;
     const int pick = cutdeg[u] > cutdeg[v] ? u : cutdeg[v] > cutdeg[u] ? v : (part[u] < part[v] ? u : v);
     sep[pick] = 1;
+  }
+  {
+    // a cover vertex whose neighbours are all cover vertices covers nothing on its own: back to its part's interior
+    std::vector<int32_t> nbr_ptr(n + 1, 0);
+    for (int e = 0; e < m; ++e) if (src[e] != dst[e]) { nbr_ptr[src[e] + 1]++; nbr_ptr[dst[e] + 1]++; }
+    std::partial_sum(nbr_ptr.begin(), nbr_ptr.end(), nbr_ptr.begin());
+    std::vector<int32_t> nbr(nbr_ptr[n]), pos(nbr_ptr.begin(), nbr_ptr.end() - 1);
+    for (int e = 0; e < m; ++e) if (src[e] != dst[e]) { nbr[pos[src[e]]++] = dst[e]; nbr[pos[dst[e]]++] = src[e]; }
+    for (int v = 0; v < n; ++v) {
+      if (!sep[v]) continue;
+      bool all_sep = true;
+      for (int a = nbr_ptr[v]; a < nbr_ptr[v + 1] && all_sep; ++a) all_sep = sep[nbr[a]] != 0;
+      if (all_sep) sep[v] = 0;
+    }
   }
   int k = 0, np = 0;
   part_ptr_out[0] = 0;

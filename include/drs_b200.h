@@ -151,6 +151,10 @@ int drs_sep_info(const drs_graph* g, int32_t* nparts, int32_t* nsep, int32_t* kt
  * its own rows; no collective).  Same role as drs_apsp_rows_sssp. */
 int drs_apsp_rows_sep(const drs_graph* g, int32_t mode, void* local_dev, int64_t ld, int32_t row0, int32_t nrows,
                       void* stream);
+/* relaxations (one add + one min each) a whole-matrix SEP build executes: [0] part closures, [1] separator closure,
+ * [2] vertex->separator rows, [3] output tiles as launched (padded), [4] output tiles without padding = the
+ * algorithmic work of the dominant kernel: n * sum_j n_j * |S_j|, halved on undirected maps (mirrored tiles) */
+int drs_sep_work(const drs_graph* g, double* relax5);
 /* milliseconds of the last SEP build by stage: fill+scatter, part closures, extraction, separator closure,
  * gathers, vertex->separator rows, output tiles, separator columns */
 int drs_apsp_sep_profile(const drs_graph* g, double* ms8);

@@ -44,7 +44,8 @@ def oracle_graph_from_data(data):
     from oracle.routing_oracle import OracleGraph
     extra = {k: np.asarray(data.eattrs[k]) for k in ("slnshift", "slnmean", "slnsd") if k in data.eattrs}
     return OracleGraph(data.n, data.src, data.dst, data.eattrs["ttmedian"], data.eattrs["length"],
-                       data.vattrs["name"], data.vattrs["lng"], data.vattrs["lat"], directed=data.directed,
+                       data.vattrs["name"], data.vattrs.get("lng", [0.0] * data.n), data.vattrs.get("lat", [0.0] * data.n),
+                       directed=data.directed,
                        extra_eattrs=extra)
 
 
