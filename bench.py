@@ -7,10 +7,12 @@
 
 A step is one all-pairs travel-time-matrix build of the synthetic city named by --config (default C3, the 50k-node
 map the metric's 1/2/4/8-GPU scaling is quoted on; it fits one GPU) with the CSR graph already resident in HBM.
-The headline algorithm is the library default for sparse road networks, N batched delta-stepping searches (source
-rows sharded over the ranks, no collective); the blocked min-plus Floyd-Warshall the north star names is timed in
-the same run and reported under "fw" (N > 1: row-block shards, pivot panels broadcast with NCCL, and the fused
-P2P-store pivot step under "fw_p2p").  Predecessors are lazy by default (--pred-matrix adds the predecessor pass to
+The headline algorithm is the library default on integer-weighted road networks: the blocked min-plus Floyd-Warshall
+run in nested-dissection order over a vertex-separator partition of the map (csrc/sep_apsp.cu, "sep": part closures,
+separator-graph closure, every output tile one 128x128x|S_j| min-plus product written once; output rows sharded over
+the ranks, no collective).  Round 1's headline, N batched delta-stepping searches, is timed beside it under "sssp",
+and the plain blocked Floyd-Warshall the north star names under "fw" (N > 1: row-block shards, pivot panels
+broadcast with NCCL, and the fused P2P-store pivot step under "fw_p2p"); all three write the same matrix.  Predecessors are lazy by default (--pred-matrix adds the predecessor pass to
 the timed step; it is reported under phase_ms otherwise).  At N == 1 the same run also measures: scalar query
 latencies through the drop-in, one insertion-stress tick (BASELINE config C4: 10k vehicles x 2k pending requests on
 the same map: the (vehicle, pickup slot, drop-off slot) kernels with frozen plans AND the reference's sequential

@@ -44,7 +44,7 @@ struct drs_sep_plan {
                 *d_cbase = nullptr, *d_wpad = nullptr, *d_sall = nullptr, *d_sepcol = nullptr, *d_ct_part = nullptr,
                 *d_ct_col0 = nullptr;
   const int64_t *d_moff = nullptr, *d_apoff = nullptr;
-  void *d_M = nullptr, *d_dS = nullptr, *d_Dall = nullptr, *d_dSS = nullptr, *d_Aprime = nullptr, *d_Apad = nullptr;
+  void *d_M = nullptr, *d_dS = nullptr, *d_Dall = nullptr, *d_dSr = nullptr, *d_Duni = nullptr, *d_Aprime = nullptr, *d_Apad = nullptr;
   double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   bool no_mirror = false;   // DRS_SEP_NO_MIRROR=1: compute every output tile (measurement knob)
   int n = 0, npad = 0;      // vertices of this level and their padded count (the leading dimension of its matrix)
@@ -243,34 +243,31 @@ __global__ void sep_arcs_kernel(T* dS, SepTab t, const int32_t* __restrict__ out
   }
 }
 
-// S2x: rows [sep0, npad) of D_all: D_all[sep0 + r][c] = dS[r][sall[c]]; padding columns and rows = inf
+// S2x: the rows of dS in the order of the concatenated separator lists (the B operand of S3), and the separator rows of
+// D_uni (a separator's distances to the separators are its dS row); padding rows = +inf
 template <typename T>
-__global__ void sep_gather_rows_kernel(const T* __restrict__ dS, SepTab t, T* __restrict__ Dall) {
-  const int64_t total = (int64_t)(t.npad - t.sep0) * t.ktot;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(idx / t.ktot), c = (int)(idx - (int64_t)r * t.ktot);
-    const int s = t.sall[c];
-    Dall[(int64_t)(t.sep0 + r) * t.ktot + c] = (r < t.nsep && s >= 0) ? dS[(int64_t)r * t.spad + s] : Semiring<T>::inf();
-  }
-}
-
-// dSS[c'][c] = dS[sall[c']][sall[c]] = the separator row of D_all
-template <typename T>
-__global__ void sep_gather_dss_kernel(const T* __restrict__ Dall, SepTab t, T* __restrict__ dSS) {
-  const int64_t total = (int64_t)t.ktot * t.ktot;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int cp = (int)(idx / t.ktot), c = (int)(idx - (int64_t)cp * t.ktot);
-    const int s = t.sall[cp];
-    dSS[idx] = s >= 0 ? Dall[(int64_t)(t.sep0 + s) * t.ktot + c] : Semiring<T>::inf();
+__global__ void sep_gather_dsr_kernel(const T* __restrict__ dS, SepTab t, T* __restrict__ dSr, T* __restrict__ Duni) {
+  const int64_t n1 = (int64_t)t.ktot * t.spad, n2 = (int64_t)(t.npad - t.sep0) * t.spad;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n1 + n2; idx += (int64_t)gridDim.x * blockDim.x) {
+    if (idx < n1) {
+      const int cp = (int)(idx / t.spad), c = (int)(idx - (int64_t)cp * t.spad);
+      const int s = t.sall[cp];
+      dSr[idx] = s >= 0 ? dS[(int64_t)s * t.spad + c] : Semiring<T>::inf();
+    } else {
+      const int64_t k = idx - n1;
+      const int r = (int)(k / t.spad), c = (int)(k - (int64_t)r * t.spad);
+      Duni[(int64_t)(t.sep0 + r) * t.spad + c] = r < t.nsep ? dS[(int64_t)r * t.spad + c] : Semiring<T>::inf();
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------------ S3: vertex -> separators
-// grid (ktot / 128, max row tiles of a part, nparts).  Row tiles start at the part's first vertex; rows past its last one
-// are computed from the next part's A' rows and not stored.
+// D_uni[u, s] = min_k A'[u, k] + dS[S_i[k], s] for the interior vertices u of part i: grid (spad / 128, max row tiles of a
+// part, nparts).  Row tiles start at the part's first vertex; rows past its last one are computed from the next part's A'
+// rows and not stored.
 template <typename T>
-__global__ void __launch_bounds__(NTHREADS, 2) sep_expand_rows_kernel(const T* __restrict__ Aprime, const T* __restrict__ dSS,
-                                                                        T* __restrict__ Dall, SepTab t, int row_lo, int row_hi) {
+__global__ void __launch_bounds__(NTHREADS, 2) sep_expand_rows_kernel(const T* __restrict__ Aprime, const T* __restrict__ dSr,
+                                                                        T* __restrict__ Duni, SepTab t, int row_lo, int row_hi) {
   const int i = blockIdx.z;
   const int row0 = t.pstart[i] + blockIdx.y * TILE, pe = t.pend[i];
   if (row0 >= pe || row0 >= row_hi || min(row0 + TILE, pe) <= row_lo) return;
@@ -278,9 +275,36 @@ __global__ void __launch_bounds__(NTHREADS, 2) sep_expand_rows_kernel(const T* _
   const int tid = threadIdx.x;
   T acc[8][8];
   acc_fill<T>(acc, Semiring<T>::inf());
-  tile_accumulate<T>(acc, Aprime + (int64_t)row0 * t.kmax, t.kmax, dSS + (int64_t)t.koff[i] * t.ktot + (int64_t)blockIdx.x * TILE,
-                     t.ktot, t.kpad[i], smem_raw, tid);
-  acc_store<T>(acc, Dall + (int64_t)row0 * t.ktot + (int64_t)blockIdx.x * TILE, t.ktot, pe - row0, TILE, tid);
+  tile_accumulate<T>(acc, Aprime + (int64_t)row0 * t.kmax, t.kmax, dSr + (int64_t)t.koff[i] * t.spad + (int64_t)blockIdx.x * TILE,
+                     t.spad, t.kpad[i], smem_raw, tid);
+  acc_store<T>(acc, Duni + (int64_t)row0 * t.spad + (int64_t)blockIdx.x * TILE, t.spad, pe - row0, TILE, tid);
+}
+
+// S3x: SPREAD_ROWS rows of the shard per CTA: the rows of D_uni spread over the per-part k ranges (D_all, the A operand
+// of S4) and copied into the separator columns of the output; padding as the other builders leave it (0 on the diagonal
+// of the padding rows, +inf elsewhere)
+constexpr int SPREAD_ROWS = 8;
+template <typename T>
+__global__ void sep_spread_kernel(const T* __restrict__ Duni, T* __restrict__ Dall, T* __restrict__ C, int64_t ldc, SepTab t, int row_lo) {
+  const int lr0 = blockIdx.x * SPREAD_ROWS, u0 = row_lo + lr0;
+  for (int c = threadIdx.x; c < t.ktot; c += blockDim.x) {
+    const int s = t.sall[c];
+#pragma unroll
+    for (int r = 0; r < SPREAD_ROWS; ++r) {
+      const int u = u0 + r;
+      Dall[(int64_t)u * t.ktot + c] = (s >= 0 && u < t.n) ? Duni[(int64_t)u * t.spad + s] : Semiring<T>::inf();
+    }
+  }
+  for (int c = t.sep0 + threadIdx.x; c < t.npad; c += blockDim.x) {
+#pragma unroll
+    for (int r = 0; r < SPREAD_ROWS; ++r) {
+      const int u = u0 + r;
+      T v;
+      if (u >= t.n || c >= t.n) v = (u == c) ? (T)0 : Semiring<T>::inf();
+      else v = Duni[(int64_t)u * t.spad + (c - t.sep0)];
+      C[(int64_t)(lr0 + r) * ldc + c] = v;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ S4: the output tiles
@@ -322,22 +346,6 @@ __global__ void __launch_bounds__(NTHREADS, 2) sep_expand_kernel(const T* __rest
   acc_store<T>(acc, C + (int64_t)(R0 - row_lo) * ldc + C0, ldc, TILE, col_hi, tid, col_lo);
   if (MIRROR && R0 < t.sep0)   // C[v][u] = C[u][v]; columns u are interior vertices only (separator columns: S4x)
     acc_store_transposed<T>(acc, smem_raw, C + (int64_t)C0 * ldc + R0, ldc, col_lo, col_hi, min(TILE, t.sep0 - R0), tid);
-}
-
-// S4x: columns [sep0, npad) of the shard: separator columns gathered from D_all, padding as the other builders leave it
-// (0 on the diagonal of the padding rows, +inf elsewhere)
-template <typename T>
-__global__ void sep_cols_kernel(const T* __restrict__ Dall, T* __restrict__ C, int64_t ldc, SepTab t, int row_lo, int nrows) {
-  const int w = t.npad - t.sep0;
-  const int64_t total = (int64_t)nrows * w;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int lr = (int)(idx / w), cc = (int)(idx - (int64_t)lr * w);
-    const int u = row_lo + lr, c = t.sep0 + cc;
-    T v;
-    if (u >= t.n || c >= t.n) v = (u == c) ? (T)0 : Semiring<T>::inf();
-    else v = Dall[(int64_t)u * t.ktot + t.sepcol[cc]];
-    C[(int64_t)lr * ldc + c] = v;
-  }
 }
 
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -401,9 +409,10 @@ int configure_kernels() {
 int ensure_work(drs_sep_plan* p) {
   auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
   const size_t b_M = al(4 * (size_t)p->m_elems), b_dS = al(4 * (size_t)p->spad * p->spad);
-  const size_t b_Dall = al(4 * (size_t)p->npad * p->ktot), b_dSS = al(4 * (size_t)p->ktot * p->ktot);
+  const size_t b_Dall = al(4 * (size_t)p->npad * p->ktot), b_dSr = al(4 * (size_t)p->ktot * p->spad);
+  const size_t b_Duni = al(4 * (size_t)p->npad * p->spad);
   const size_t b_Apr = al(4 * (size_t)(p->npad + TILE) * p->kmax), b_Apad = al(4 * (size_t)std::max<int64_t>(p->ap_elems, 1));
-  const size_t total = b_M + b_dS + b_Dall + b_dSS + b_Apr + b_Apad;
+  const size_t total = b_M + b_dS + b_Dall + b_dSr + b_Duni + b_Apr + b_Apad;
   if (!p->d_work || p->work_bytes < total) {
     if (p->d_work) cudaFree(p->d_work);
     p->d_work = nullptr; p->work_bytes = 0;
@@ -417,7 +426,7 @@ int ensure_work(drs_sep_plan* p) {
     DRS_CUDA(cudaMemset(p->d_work, 0x7f, total));
   }
   char* b = (char*)p->d_work;
-  p->d_M = b; b += b_M; p->d_dS = b; b += b_dS; p->d_Dall = b; b += b_Dall; p->d_dSS = b; b += b_dSS;
+  p->d_M = b; b += b_M; p->d_dS = b; b += b_dS; p->d_Dall = b; b += b_Dall; p->d_dSr = b; b += b_dSr; p->d_Duni = b; b += b_Duni;
   p->d_Aprime = b; b += b_Apr; p->d_Apad = b;
   return DRS_OK;
 }
@@ -436,7 +445,8 @@ int run_level(drs_sep_plan* p, const LevelInput& in, int mode, bool directed, T*
   int rc;
   if ((rc = ensure_work(p))) return rc;
   const SepTab t = device_tab(p);
-  T *M = (T*)p->d_M, *dS = (T*)p->d_dS, *Dall = (T*)p->d_Dall, *dSS = (T*)p->d_dSS, *Apr = (T*)p->d_Aprime, *Apad = (T*)p->d_Apad;
+  T *M = (T*)p->d_M, *dS = (T*)p->d_dS, *Dall = (T*)p->d_Dall, *dSr = (T*)p->d_dSr, *Duni = (T*)p->d_Duni, *Apr = (T*)p->d_Aprime,
+    *Apad = (T*)p->d_Apad;
 #define SEP_CHECK() DRS_REQUIRE(cudaGetLastError() == cudaSuccess, DRS_ERR_CUDA, "separator build: kernel launch failed (%s:%d)", __FILE__, __LINE__)
 #define SEP_EVENT(i) do { if (ev) cudaEventRecord(ev[i], st); } while (0)
   SEP_EVENT(0);
@@ -490,15 +500,15 @@ int run_level(drs_sep_plan* p, const LevelInput& in, int mode, bool directed, T*
   }
   SEP_EVENT(4);
   // S2x
-  sep_gather_rows_kernel<T><<<148 * 8, 256, 0, st>>>(dS, t, Dall);
-  sep_gather_dss_kernel<T><<<148 * 8, 256, 0, st>>>(Dall, t, dSS);
-  drs_count_launch(2);
+  sep_gather_dsr_kernel<T><<<148 * 8, 256, 0, st>>>(dS, t, dSr, Duni);
+  drs_count_launch();
   SEP_CHECK();
   SEP_EVENT(5);
-  // S3
-  sep_expand_rows_kernel<T><<<dim3(p->ktot / TILE, p->max_rowtiles, p->nparts), NTHREADS, kTileSmemBytes, st>>>(Apr, dSS, Dall, t, row0,
+  // S3 + S3x
+  sep_expand_rows_kernel<T><<<dim3(p->spad / TILE, p->max_rowtiles, p->nparts), NTHREADS, kTileSmemBytes, st>>>(Apr, dSr, Duni, t, row0,
                                                                                                               row0 + nrows);
-  drs_count_launch();
+  sep_spread_kernel<T><<<nrows / SPREAD_ROWS, 256, 0, st>>>(Duni, Dall, C, ldc, t, row0);
+  drs_count_launch(2);
   SEP_CHECK();
   SEP_EVENT(6);
   // S4
@@ -511,9 +521,6 @@ int run_level(drs_sep_plan* p, const LevelInput& in, int mode, bool directed, T*
   }
   SEP_CHECK();
   SEP_EVENT(7);
-  sep_cols_kernel<T><<<148 * 8, 256, 0, st>>>(Dall, C, ldc, t, row0, nrows);
-  drs_count_launch();
-  SEP_CHECK();
   SEP_EVENT(8);
 #undef SEP_CHECK
 #undef SEP_EVENT
@@ -727,7 +734,7 @@ void level_work(const drs_sep_plan* p, bool directed, double* w) {
   for (int j = 0; j < p->nparts; ++j) {
     const double q = p->qpad[j];
     w[0] += q * q * q;
-    w[2] += (double)round_up(p->pend[j] - p->pstart[j], TILE) * p->ktot * p->kpad[j];
+    w[2] += (double)round_up(p->pend[j] - p->pstart[j], TILE) * p->spad * p->kpad[j];
     w[4] += (double)p->n * (p->pend[j] - p->pstart[j]) * p->sj[j];
   }
   if (p->nsep > 0) {

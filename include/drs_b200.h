@@ -79,12 +79,13 @@ int drs_graph_info(const drs_graph* g, int32_t* n, int32_t* m, int32_t* npad, in
                    int32_t* apsp_valid, int32_t* device);
 
 /* ------------------------------------------------------------------- APSP --
- * Builds the all-pairs travel-time matrix with the algorithm selected by drs_apsp_set_algorithm (default AUTO: N batched
- * delta-stepping searches when arcs/vertex <= 16, the blocked min-plus Floyd-Warshall otherwise), and -- only in
+ * Builds the all-pairs travel-time matrix with the algorithm selected by drs_apsp_set_algorithm (default AUTO: the
+ * separator-partitioned min-plus build when the graph carries a partition with small separators and integer travel
+ * times, else N batched delta-stepping searches when arcs/vertex <= 16, else the blocked min-plus Floyd-Warshall), and -- only in
  * DRS_PRED_MATRIX mode -- the canonical predecessor-edge matrix; by default predecessors are evaluated lazily by the
  * path queries.  Replaces every per-query Dijkstra the reference issues
  * (lib/RoutingEngine.py:87,199,212; lib/optimUtils.py:528,531,659).
- * Single GPU; the multi-GPU build drives the drs_apsp_rows_sssp / drs_fw_* entry points below from
+ * Single GPU; the multi-GPU build drives the drs_apsp_rows_sep / drs_apsp_rows_sssp / drs_fw_* entry points below from
  * one process per GPU.  Blocks until the matrix is complete.
  */
 int drs_apsp_build(drs_graph* g, int32_t mode);
