@@ -76,6 +76,7 @@ extern "C" int drs_graph_create(int32_t n, int32_t m, int32_t directed, const in
   *out = nullptr;
   DRS_REQUIRE(n > 0 && m >= 0, DRS_ERR_ARG, "drs_graph_create: need n > 0 and m >= 0 (n=%d m=%d)", n, m);
   DRS_REQUIRE(m == 0 || (src && dst && tt && length), DRS_ERR_ARG, "drs_graph_create: null edge array");
+  DrsHostTimer tm("drs_graph_create");
   for (int e = 0; e < m; ++e) {
     DRS_REQUIRE(src[e] >= 0 && src[e] < n && dst[e] >= 0 && dst[e] < n, DRS_ERR_RANGE,
                 "drs_graph_create: edge %d endpoint out of range (%d -> %d, n=%d)", e, src[e], dst[e], n);
@@ -83,6 +84,7 @@ extern "C" int drs_graph_create(int32_t n, int32_t m, int32_t directed, const in
                 "drs_graph_create: edge %d travel time must be finite and > 0 (got %g)", e, tt[e]);
     DRS_REQUIRE(std::isfinite(length[e]), DRS_ERR_ARG, "drs_graph_create: edge %d length not finite", e);
   }
+  tm.lap("validate");
   drs_graph* g = new (std::nothrow) drs_graph();
   DRS_REQUIRE(g, DRS_ERR_NOMEM, "drs_graph_create: out of host memory");
   DRS_CUDA(cudaGetDevice(&g->device));
@@ -92,19 +94,17 @@ extern "C" int drs_graph_create(int32_t n, int32_t m, int32_t directed, const in
   g->h_tt.assign(tt, tt + m); g->h_len.assign(length, length + m);
   classify_weights(g);
 
-  // arcs: (u, v, eid); undirected edges contribute both directions.  Adjacency
-  // order = edge id order (igraph incidence-list order).
-  struct Arc { int u, v, e; };
-  std::vector<Arc> arcs;
-  arcs.reserve((size_t)m * (directed ? 1 : 2));
-  for (int e = 0; e < m; ++e) {
-    arcs.push_back({src[e], dst[e], e});
-    if (!directed && src[e] != dst[e]) arcs.push_back({dst[e], src[e], e});
-  }
-  g->narcs = (int)arcs.size();
+  // arcs u -> v of edge e; undirected edges contribute both directions.  Adjacency order = edge id order (igraph
+  // incidence-list order): two passes over the edge list, no intermediate arc array.
   // pad to n+1 .. npad+1 so that padded vertices have empty adjacency
   std::vector<int32_t> out_ptr(g->npad + 1, 0), in_ptr(g->npad + 1, 0);
-  for (const Arc& a : arcs) { out_ptr[a.u + 1]++; in_ptr[a.v + 1]++; }
+  int narcs = 0;
+  for (int e = 0; e < m; ++e) {
+    const int u = src[e], v = dst[e];
+    out_ptr[u + 1]++; in_ptr[v + 1]++; ++narcs;
+    if (!directed && u != v) { out_ptr[v + 1]++; in_ptr[u + 1]++; ++narcs; }
+  }
+  g->narcs = narcs;
   std::partial_sum(out_ptr.begin(), out_ptr.end(), out_ptr.begin());
   std::partial_sum(in_ptr.begin(), in_ptr.end(), in_ptr.begin());
   // one host image of every device array (256-byte aligned slices), one allocation, one copy
@@ -114,7 +114,7 @@ extern "C" int drs_graph_create(int32_t n, int32_t m, int32_t directed, const in
   const size_t o_tt = slice(me * 8), o_len = slice(me * 8), o_esrc = slice(me * 4), o_edst = slice(me * 4);
   const size_t o_optr = slice(np1 * 4), o_ocol = slice(na * 4), o_oeid = slice(na * 4), o_ow = slice(na * 4);
   const size_t o_iptr = slice(np1 * 4), o_isrc = slice(na * 4), o_ieid = slice(na * 4), o_iw = slice(na * 4);
-  std::vector<unsigned char> img(off, 0);
+  std::vector<unsigned char> img(off);
   auto at = [&](size_t o) { return img.data() + o; };
   if (m) {
     std::memcpy(at(o_tt), tt, me * 8); std::memcpy(at(o_len), length, me * 8);
@@ -124,17 +124,22 @@ extern "C" int drs_graph_create(int32_t n, int32_t m, int32_t directed, const in
   int32_t* out_col = (int32_t*)at(o_ocol); int32_t* out_eid = (int32_t*)at(o_oeid); float* out_w = (float*)at(o_ow);
   int32_t* in_src = (int32_t*)at(o_isrc); int32_t* in_eid = (int32_t*)at(o_ieid); float* in_w = (float*)at(o_iw);
   {
-    // arcs were generated in edge-id order, so a single pass keeps every adjacency list in edge-id order
+    // edges are visited in id order, so every adjacency list comes out in edge-id order
     std::vector<int32_t> op(out_ptr.begin(), out_ptr.end() - 1), ip(in_ptr.begin(), in_ptr.end() - 1);
-    for (const Arc& a : arcs) {
-      const float w = (float)tt[a.e];
-      out_col[op[a.u]] = a.v; out_eid[op[a.u]] = a.e; out_w[op[a.u]] = w; op[a.u]++;
-      in_src[ip[a.v]] = a.u; in_eid[ip[a.v]] = a.e; in_w[ip[a.v]] = w; ip[a.v]++;
+    auto put = [&](int u, int v, int e, float w) {
+      out_col[op[u]] = v; out_eid[op[u]] = e; out_w[op[u]] = w; op[u]++;
+      in_src[ip[v]] = u; in_eid[ip[v]] = e; in_w[ip[v]] = w; ip[v]++;
+    };
+    for (int e = 0; e < m; ++e) {
+      const float w = (float)tt[e];
+      put(src[e], dst[e], e, w);
+      if (!directed && src[e] != dst[e]) put(dst[e], src[e], e, w);
     }
   }
   g->h_out_eid.assign(out_eid, out_eid + na);
   g->h_in_eid.assign(in_eid, in_eid + na);
   auto fail = [&](int code) { drs_graph_destroy(g); return code; };
+  tm.lap("host image");
   drs_count_alloc();
   if (cudaMalloc(&g->d_arena, img.size()) != cudaSuccess) {
     cudaGetLastError();
@@ -156,6 +161,7 @@ extern "C" int drs_graph_create(int32_t n, int32_t m, int32_t directed, const in
     drs_set_error("drs_graph_create: cudaStreamCreate failed");
     return fail(DRS_ERR_CUDA);
   }
+  tm.lap("malloc + copy + stream");
   *out = g;
   return DRS_OK;
 }
@@ -250,6 +256,7 @@ extern "C" int drs_apsp_build(drs_graph* g, int32_t mode) {
   { int rcm = drs_check_mode(g, mode, "drs_apsp_build"); if (rcm) return rcm; }
   DrsDeviceGuard guard(g->device);
   const int64_t ld = g->npad;
+  DrsHostTimer tm("drs_apsp_build");
   if (!g->owns_matrices || g->ld != ld) {
     free_matrices(g);
     drs_count_alloc();
@@ -257,6 +264,7 @@ extern "C" int drs_apsp_build(drs_graph* g, int32_t mode) {
     g->owns_matrices = true;
     g->ld = ld;
   }
+  tm.lap("matrix malloc");
   if (g->pred_mode == DRS_PRED_MATRIX && !g->d_pred) {
     drs_count_alloc();
     DRS_CUDA(cudaMalloc((void**)&g->d_pred, sizeof(int32_t) * ld * ld));
@@ -314,6 +322,7 @@ extern "C" int drs_apsp_build(drs_graph* g, int32_t mode) {
   cudaEventElapsedTime(&ms, ev[1 + 2 * ner], ev[2 + 2 * ner]); g->prof_ms[3] = ms;
   g->prof_rounds = nb;
   release();
+  tm.lap("build");
   g->apsp_valid = true;
   return DRS_OK;
 }

@@ -106,6 +106,26 @@ bool drs_sep_usable(const drs_graph* g);   // partition present, exact arithmeti
 // DRS_MODE_F32 / DRS_MODE_I32 known, and I32 only on integer travel times below 1e6 (a float weight would be truncated)
 int drs_check_mode(const drs_graph* g, int mode, const char* who);
 
+// DRS_TRACE_HOST=1: host-side phase times of the heavier entry points on stderr (development aid)
+#include <chrono>
+#include <cstdlib>
+struct DrsHostTimer {
+  const char* who;
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  explicit DrsHostTimer(const char* w) : who(w) {
+    const char* e = getenv("DRS_TRACE_HOST");
+    on = e && e[0] == '1';
+    t0 = std::chrono::steady_clock::now();
+  }
+  void lap(const char* what) {
+    if (!on) return;
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[drs host] %s: %s %.3f ms\n", who, what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+
 // RAII device guard
 struct DrsDeviceGuard {
   int prev = -1;

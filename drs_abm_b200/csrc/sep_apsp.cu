@@ -25,6 +25,7 @@
 #include <cstring>
 #include <numeric>
 #include <queue>
+#include <thread>
 
 #include "drs_common.cuh"
 #include "minplus.cuh"
@@ -406,14 +407,15 @@ int configure_kernels() {
   return DRS_OK;
 }
 
-int ensure_work(drs_sep_plan* p) {
+int ensure_work(drs_sep_plan* p, cudaStream_t st) {
   auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
   const size_t b_M = al(4 * (size_t)p->m_elems), b_dS = al(4 * (size_t)p->spad * p->spad);
   const size_t b_Dall = al(4 * (size_t)p->npad * p->ktot), b_dSr = al(4 * (size_t)p->ktot * p->spad);
   const size_t b_Duni = al(4 * (size_t)p->npad * p->spad);
   const size_t b_Apr = al(4 * (size_t)(p->npad + TILE) * p->kmax), b_Apad = al(4 * (size_t)std::max<int64_t>(p->ap_elems, 1));
   const size_t total = b_M + b_dS + b_Dall + b_dSr + b_Duni + b_Apr + b_Apad;
-  if (!p->d_work || p->work_bytes < total) {
+  const bool fresh = !p->d_work || p->work_bytes < total;
+  if (fresh) {
     if (p->d_work) cudaFree(p->d_work);
     p->d_work = nullptr; p->work_bytes = 0;
     drs_count_alloc();
@@ -422,12 +424,13 @@ int ensure_work(drs_sep_plan* p) {
       DRS_REQUIRE(false, DRS_ERR_NOMEM, "separator build: cudaMalloc(%zu bytes) of work arrays failed", total);
     }
     p->work_bytes = total;
-    // rows of A' past the last interior vertex are read (never used) by the last row tile of a part
-    DRS_CUDA(cudaMemset(p->d_work, 0x7f, total));
   }
   char* b = (char*)p->d_work;
   p->d_M = b; b += b_M; p->d_dS = b; b += b_dS; p->d_Dall = b; b += b_Dall; p->d_dSr = b; b += b_dSr; p->d_Duni = b; b += b_Duni;
   p->d_Aprime = b; b += b_Apr; p->d_Apad = b;
+  // rows of A' past the last interior vertex are read by the last row tile of a part; what is computed from them is never
+  // stored, but they should hold numbers that stay numbers
+  if (fresh) DRS_CUDA(cudaMemsetAsync(p->d_Aprime, 0x7f, b_Apr, st));
   return DRS_OK;
 }
 
@@ -443,7 +446,9 @@ template <typename T>
 int run_level(drs_sep_plan* p, const LevelInput& in, int mode, bool directed, T* C, int64_t ldc, int row0, int nrows, cudaStream_t st,
               cudaEvent_t* ev) {
   int rc;
-  if ((rc = ensure_work(p))) return rc;
+  DrsHostTimer tm("sep run_level");
+  if ((rc = ensure_work(p, st))) return rc;
+  tm.lap("work arrays");
   const SepTab t = device_tab(p);
   T *M = (T*)p->d_M, *dS = (T*)p->d_dS, *Dall = (T*)p->d_Dall, *dSr = (T*)p->d_dSr, *Duni = (T*)p->d_Duni, *Apr = (T*)p->d_Aprime,
     *Apad = (T*)p->d_Apad;
@@ -685,10 +690,12 @@ extern "C" int drs_graph_set_partition(drs_graph* g, int32_t nparts, const int32
   DrsDeviceGuard guard(g->device);
   drs_sep_free(g);
   if (nparts <= 0) return DRS_OK;   // partition removed
+  DrsHostTimer tm("drs_graph_set_partition");
   drs_sep_plan* p = nullptr;
   std::vector<std::vector<int32_t>> S;
   int rc = make_plan(g->n, g->npad, g->m, g->h_src.data(), g->h_dst.data(), nparts, part_ptr, &p, &S);
   if (rc) return rc;
+  tm.lap("level 1 tables");
   if (n_sep_parts > 0 && sep_part_ptr && p->nsep > 0) {
     // level 2: the separator graph (separator-local ids): the map's edges inside S and a clique per S_j
     std::vector<int32_t> s2, d2;
@@ -696,12 +703,19 @@ extern "C" int drs_graph_set_partition(drs_graph* g, int32_t nparts, const int32
       if (g->h_src[e] >= p->sep0 && g->h_dst[e] >= p->sep0 && g->h_src[e] != g->h_dst[e]) {
         s2.push_back(g->h_src[e] - p->sep0); d2.push_back(g->h_dst[e] - p->sep0);
       }
-    for (const auto& lst : S)
-      for (size_t a = 0; a < lst.size(); ++a)
-        for (size_t b = a + 1; b < lst.size(); ++b) { s2.push_back(lst[a]); d2.push_back(lst[b]); }
-    // a grouping that is not a separator partition of this graph (a caller's own partition may be one) is not used:
-    // the separator graph is then closed by the plain blocked Floyd-Warshall
+    // a part's separator list is a clique of that graph; for the tables a star is enough (same components, and the
+    // separator lists of the groups only need the group-to-top adjacencies): centre = the first member that is not a top
+    // separator (a list made of top separators only joins no group to anything)
+    const int top0 = sep_part_ptr[n_sep_parts];
+    for (const auto& lst : S) {
+      int centre = -1;
+      for (int r : lst) if (r < top0) { centre = r; break; }
+      if (centre < 0) continue;
+      for (int r : lst) if (r != centre) { s2.push_back(centre); d2.push_back(r); }
+    }
+    tm.lap("level 2 edges");
     if (make_plan(p->nsep, p->spad, (int)s2.size(), s2.data(), d2.data(), n_sep_parts, sep_part_ptr, &p->child, nullptr)) p->child = nullptr;
+    tm.lap("level 2 tables");
   }
   g->sep = p;
   return DRS_OK;
@@ -830,24 +844,42 @@ struct Bisector {
     std::copy(order.begin(), order.end(), idx.begin() + lo);
   }
 
+  // where a range of c vertices is cut: L = leaves it still has to yield, the left child takes floor(L/2) of them
+  int cut(int lo, int hi) const {
+    const int c = hi - lo, L = (c + target - 1) / target;
+    return lo + (int)((int64_t)c * (L / 2) / L);
+  }
+
+  // pass 1 (coordinates): median cuts along the wider axis; subtrees are independent, the upper levels run on threads
+  void arrange(int lo, int hi, int depth) {
+    if (hi - lo <= target) return;
+    const int mid = cut(lo, hi);
+    double x0 = x[idx[lo]], x1 = x0, y0 = y[idx[lo]], y1 = y0;
+    for (int i = lo; i < hi; ++i) {
+      x0 = std::min(x0, x[idx[i]]); x1 = std::max(x1, x[idx[i]]);
+      y0 = std::min(y0, y[idx[i]]); y1 = std::max(y1, y[idx[i]]);
+    }
+    const double* k = (x1 - x0 >= y1 - y0) ? x : y;
+    std::nth_element(idx.begin() + lo, idx.begin() + mid, idx.begin() + hi,
+                     [k](int a, int b) { return k[a] < k[b] || (k[a] == k[b] && a < b); });
+    if (depth < 3 && hi - lo > 8192) {
+      std::thread left([this, lo, mid, depth]() { arrange(lo, mid, depth + 1); });
+      arrange(mid, hi, depth + 1);
+      left.join();
+    } else {
+      arrange(lo, mid, depth + 1);
+      arrange(mid, hi, depth + 1);
+    }
+  }
+
+  // pass 2: the leaves in tree order, and the second-level group of each
   void split(int lo, int hi, int sup) {
     const int c = hi - lo;
-    const int L = (c + target - 1) / target, Ll = L / 2;
+    const int L = (c + target - 1) / target;
     if (sup < 0 && L <= leaves_per_super) sup = nsuper++;
     if (c <= target) { if (c > 0) { leaves.push_back({lo, hi}); leaf_super.push_back(sup); } return; }
-    const int mid = lo + (int)((int64_t)c * Ll / L);
-    if (x) {
-      double x0 = x[idx[lo]], x1 = x0, y0 = y[idx[lo]], y1 = y0;
-      for (int i = lo; i < hi; ++i) {
-        x0 = std::min(x0, x[idx[i]]); x1 = std::max(x1, x[idx[i]]);
-        y0 = std::min(y0, y[idx[i]]); y1 = std::max(y1, y[idx[i]]);
-      }
-      const double* k = (x1 - x0 >= y1 - y0) ? x : y;
-      std::nth_element(idx.begin() + lo, idx.begin() + mid, idx.begin() + hi,
-                       [k](int a, int b) { return k[a] < k[b] || (k[a] == k[b] && a < b); });
-    } else {
-      bfs_order(lo, hi);
-    }
+    const int mid = cut(lo, hi);
+    if (!x) bfs_order(lo, hi);
     split(lo, mid, sup);
     split(mid, hi, sup);
   }
@@ -867,6 +899,7 @@ extern "C" int drs_partition_order(int32_t n, int32_t m, const int32_t* src, con
               DRS_ERR_ARG, "drs_partition_order: bad argument");
   for (int e = 0; e < m; ++e)
     DRS_REQUIRE(src[e] >= 0 && src[e] < n && dst[e] >= 0 && dst[e] < n, DRS_ERR_RANGE, "drs_partition_order: edge %d endpoint out of range", e);
+  DrsHostTimer tm("drs_partition_order");
   Bisector b;
   b.n = n; b.target = target; b.x = b.y = nullptr;
   if (lng && lat) {
@@ -893,7 +926,10 @@ extern "C" int drs_partition_order(int32_t n, int32_t m, const int32_t* src, con
     const char* e = getenv("DRS_SEP_SUPER");
     b.leaves_per_super = e ? std::max(1, atoi(e)) : std::max(2, (int)std::ceil(1.25 * std::sqrt((double)Ltot)));
   }
+  tm.lap("setup");
+  if (b.x) b.arrange(0, n, 0);
   b.split(0, n, -1);
+  tm.lap("bisection");
   std::vector<int32_t> part(n);
   for (int j = 0; j < (int)b.leaves.size(); ++j)
     for (int i = b.leaves[j].first; i < b.leaves[j].second; ++i) part[b.idx[i]] = j;
@@ -921,6 +957,7 @@ extern "C" int drs_partition_order(int32_t n, int32_t m, const int32_t* src, con
       if (all_sep) sep[v] = 0;
     }
   }
+  tm.lap("vertex cover");
   int k = 0, np = 0;
   part_ptr_out[0] = 0;
   for (const auto& lf : b.leaves) {
@@ -959,5 +996,6 @@ extern "C" int drs_partition_order(int32_t n, int32_t m, const int32_t* src, con
     for (int i = lf.first; i < lf.second; ++i)
       if (sep[b.idx[i]] && top[b.idx[i]]) order_out[k++] = b.idx[i];
   if (n_sep_parts_out) *n_sep_parts_out = sep_part_ptr_out ? nsp : 0;
+  tm.lap("ordering");
   return DRS_OK;
 }

@@ -8,6 +8,8 @@ Python floats and strings as str; vertex order is file order and ``source`` /
 """
 import re
 
+import array
+
 import numpy as np
 
 _TOKEN = re.compile(r'"([^"]*)"|(\[)|(\])|([^\s\[\]"]+)')
@@ -28,6 +30,16 @@ class RoadGraphData(object):
         self.m = int(self.src.shape[0])
         self.vattrs = vattrs
         self.eattrs = eattrs
+        # numeric (lng, lat) arrays beside the attribute lists, converted once at load time: the device numbering of every
+        # RoadGraph made from this map reads them (None when the map has no usable coordinates)
+        self.coords = None
+        try:
+            x = np.frombuffer(array.array("d", vattrs["lng"]), dtype=np.float64)
+            y = np.frombuffer(array.array("d", vattrs["lat"]), dtype=np.float64)
+            if x.shape == (self.n,) and y.shape == (self.n,):
+                self.coords = (x, y)
+        except (KeyError, TypeError, ValueError):
+            pass
 
 
 def _convert(tok_str, tok_num):

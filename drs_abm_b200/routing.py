@@ -254,6 +254,7 @@ class RoadGraph(object):
         self.directed = data.directed
         self._src, self._dst = data.src, data.dst
         self._vattrs = {k: list(v) for k, v in data.vattrs.items()}
+        self._coords = getattr(data, "coords", None)
         self._eattrs = {k: (np.array(v, dtype=np.float64) if isinstance(v, np.ndarray) else list(v))
                         for k, v in data.eattrs.items()}
         self.mode = mode
@@ -405,8 +406,9 @@ class RoadGraph(object):
         if self.numbering in ("locality", "partition") and self._new_of_old is None:
             order = None
             if self.numbering == "partition":
-                order, self._part_ptr, self._sep_part_ptr = partition_order(self.n, self._src, self._dst, self._vattrs.get("lng"),
-                                                                            self._vattrs.get("lat"), self.part_target, True)
+                lng, lat = self._coords if self._coords is not None else (self._vattrs.get("lng"), self._vattrs.get("lat"))
+                order, self._part_ptr, self._sep_part_ptr = partition_order(self.n, self._src, self._dst, lng, lat,
+                                                                            self.part_target, True)
             else:
                 order = locality_order(self.n, self._src, self._dst, self._vattrs.get("lng"), self._vattrs.get("lat"))
             self._old_of_new = np.ascontiguousarray(order, dtype=np.int32)

@@ -16,7 +16,7 @@ out = []
 for rep in range(4):
     torch.cuda.synchronize()
     t = [time.time()]
-    G = RoadGraph(data, mode=_lib.MODE_F32, algorithm=_lib.APSP_SSSP); t.append(time.time())
+    G = RoadGraph(data, mode=_lib.MODE_F32); G._number(); t.append(time.time())
     G.upload(); torch.cuda.synchronize(); t.append(time.time())
     o, d = synth.random_od_pairs(data.n, 4096, 3); t.append(time.time())
     G.build(); torch.cuda.synchronize(); t.append(time.time())
@@ -26,6 +26,6 @@ for rep in range(4):
     prof = [round(float(x), 3) for x in pm]
     tt, ln, hops = G.path_sums(o, d); t.append(time.time())
     G.close(); torch.cuda.synchronize(); t.append(time.time())
-    names = ["ctor", "upload", "od_pairs", "build", "path_sums", "close"]
+    names = ["ctor_and_numbering", "upload_create_set_partition", "od_pairs", "build", "path_sums", "close"]
     out.append({n: round((b - a) * 1e3, 3) for n, a, b in zip(names, t[:-1], t[1:])} | {"profile": prof})
 print(json.dumps(out, indent=1))
