@@ -19,6 +19,7 @@
 #include <cstring>
 
 #include "drs_common.cuh"
+#include "minplus.cuh"
 
 namespace {
 
@@ -28,48 +29,7 @@ constexpr int STAGES = 3;
 constexpr int APAD = KC + 4;       // padded row of the A chunk (keeps 16 B alignment)
 constexpr int NTHREADS = 256;
 
-template <typename T> struct Semiring;
-template <> struct Semiring<float> {
-  static constexpr bool packed = true;    // sm_100 packed fp32x2 add (FADD2) in the tile kernel
-  static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
-  // acc = min(acc, a0+b0, a1+b1): two FADD + one 3-input FMNMX3 (sm_100+)
-  static __device__ __forceinline__ float relax2(float acc, float a0, float b0, float a1, float b1) {
-    float d;
-    float s0 = a0 + b0, s1 = a1 + b1;
-    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(acc), "f"(s0), "f"(s1));
-    return d;
-  }
-  static __device__ __forceinline__ float relax1(float acc, float a, float b) { return fminf(acc, a + b); }
-};
-template <> struct Semiring<int> {
-  static constexpr bool packed = false;
-  static __device__ __forceinline__ int inf() { return DRS_I32_INF; }
-  // VIADDMNMX: add and min in one DPX instruction
-  static __device__ __forceinline__ int relax2(int acc, int a0, int b0, int a1, int b1) {
-    return __viaddmin_s32(a1, b1, __viaddmin_s32(a0, b0, acc));
-  }
-  static __device__ __forceinline__ int relax1(int acc, int a, int b) { return __viaddmin_s32(a, b, acc); }
-};
-
-template <typename T> struct Vec4;
-template <> struct Vec4<float> { using type = float4; };
-template <> struct Vec4<int> { using type = int4; };
-template <typename T> struct Vec2;
-template <> struct Vec2<float> { using type = float2; };
-template <> struct Vec2<int> { using type = int2; };
-
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
-  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N));
-}
+using mp::Semiring; using mp::Vec4; using mp::Vec2; using mp::cp_async16; using mp::cp_async4; using mp::cp_async_commit; using mp::cp_async_wait;
 
 // Tile operands are addressed as base + i*si + j*sj (element strides), i = blockIdx.y
 // (+ i_off), j = blockIdx.x.
@@ -240,48 +200,20 @@ __global__ void __launch_bounds__(NTHREADS, 2) fw_minplus_tile_kernel(TileArgs<T
 
 constexpr size_t kTileSmemBytes = sizeof(float) * STAGES * (TILE * APAD + KC * TILE);
 
-// Phase 1: close the 128x128 diagonal tile in shared memory (classic FW, one CTA).
-constexpr int P1PAD = TILE + 4;
+// Phase 1: close the 128x128 diagonal tile (one CTA; the tile in registers, pivot row / column through shared memory:
+// minplus.cuh, fw_close_diag_tile).
 template <typename T> struct PeerList { int n; T* ptr[DRS_MAX_PEERS]; };
 
 template <typename T>
-__global__ void __launch_bounds__(1024, 1) fw_diag_kernel(T* D, int64_t ld, PeerList<T> peers) {
+__global__ void __launch_bounds__(mp::DIAG_THREADS) fw_diag_kernel(T* D, int64_t ld, PeerList<T> peers) {
   using V4 = typename Vec4<T>::type;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  T(*s)[P1PAD] = reinterpret_cast<T(*)[P1PAD]>(smem_raw);
-  const int tid = threadIdx.x;
-  const int tx = tid & 31, ty = tid >> 5;  // thread owns rows ty*4..+3, columns tx*4..+3
-  V4 c[4];
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    c[r] = *reinterpret_cast<const V4*>(D + (int64_t)(ty * 4 + r) * ld + tx * 4);
-    *reinterpret_cast<V4*>(&s[ty * 4 + r][tx * 4]) = c[r];
-  }
-  __syncthreads();
-  for (int k = 0; k < TILE; ++k) {
-    const V4 bk = *reinterpret_cast<const V4*>(&s[k][tx * 4]);
-    T a[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) a[r] = s[ty * 4 + r][k];
-    __syncthreads();   // all reads of iteration k done before anyone overwrites
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      c[r].x = Semiring<T>::relax1(c[r].x, a[r], bk.x);
-      c[r].y = Semiring<T>::relax1(c[r].y, a[r], bk.y);
-      c[r].z = Semiring<T>::relax1(c[r].z, a[r], bk.z);
-      c[r].w = Semiring<T>::relax1(c[r].w, a[r], bk.w);
-      *reinterpret_cast<V4*>(&s[ty * 4 + r][tx * 4]) = c[r];
+  mp::fw_close_diag_tile<T>(D, ld, threadIdx.x, [&](int64_t off, V4 lo, V4 hi) {
+    for (int pr = 0; pr < peers.n; ++pr) {
+      *reinterpret_cast<V4*>(peers.ptr[pr] + off) = lo;
+      *reinterpret_cast<V4*>(peers.ptr[pr] + off + 4) = hi;
     }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    *reinterpret_cast<V4*>(D + (int64_t)(ty * 4 + r) * ld + tx * 4) = c[r];
-    for (int pr = 0; pr < peers.n; ++pr)
-      *reinterpret_cast<V4*>(peers.ptr[pr] + (int64_t)(ty * 4 + r) * ld + tx * 4) = c[r];
-  }
+  });
 }
-constexpr size_t kDiagSmemBytes = sizeof(float) * TILE * P1PAD;
 
 // dist[i][j] = (row0+i == j) ? 0 : inf
 template <typename T>
@@ -392,8 +324,6 @@ int launch_tile(const TileArgs<T>& p, dim3 grid, cudaStream_t st) {
   if (dev < 0 || dev >= 64 || !configured[dev]) {
     DRS_CUDA(cudaFuncSetAttribute(fw_minplus_tile_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)kTileSmemBytes));
-    DRS_CUDA(cudaFuncSetAttribute(fw_diag_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)kDiagSmemBytes));
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   if (grid.x == 0 || grid.y == 0) return DRS_OK;
@@ -421,7 +351,7 @@ int pivot_row_impl(T* panel, int64_t ld, int kb, cudaStream_t st, int n_peers = 
   p.i_off = 0; p.skip_i = -1; p.skip_j = kb;
   int rc = launch_tile<T>(p, dim3(0, 0), st);   // configure only
   if (rc) return rc;
-  fw_diag_kernel<T><<<1, 1024, kDiagSmemBytes, st>>>(diag, ld, pl);
+  fw_diag_kernel<T><<<1, mp::DIAG_THREADS, 0, st>>>(diag, ld, pl);
   drs_count_launch();
   DRS_CUDA(cudaGetLastError());
   return launch_tile<T>(p, dim3(nb, 1), st);

@@ -166,6 +166,80 @@ template <typename T> __device__ __forceinline__ void acc_store_transposed(const
   }
 }
 
+// Phase 1 of the blocked Floyd-Warshall: closes one 128x128 diagonal tile D (row-major, leading dimension ld, 16-byte
+// aligned) in place.  One CTA of DIAG_THREADS threads; the tile lives in registers (4x8 per thread: rows 4 ty .., columns
+// 8 tx ..) and only the pivot row and the pivot column of the next step pass through shared memory (double-buffered: one
+// barrier per step).  Row k and column k do not change in step k (the diagonal is 0 and the weights are positive), so
+// publishing them one step ahead is exact.  The step loop is unrolled by 8 so that the published register is a
+// compile-time choice.  `store_peers(offset, lo, hi)`: the closed tile also goes to the peers' buffers (fused broadcast
+// of the pivot step).
+constexpr int DIAG_THREADS = 512;
+template <typename T, typename PeerFn>
+__device__ __forceinline__ void fw_close_diag_tile(T* D, int64_t ld, int tid, PeerFn store_peers) {
+  using V4 = typename Vec4<T>::type;
+  __shared__ __align__(16) T rowb[2][TILE];
+  __shared__ __align__(16) T colb[2][TILE];
+  const int tx = tid & 15, ty = tid >> 4;   // ty in [0, 32)
+  T c[4][8];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const V4 lo = *reinterpret_cast<const V4*>(D + (int64_t)(ty * 4 + r) * ld + tx * 8);
+    const V4 hi = *reinterpret_cast<const V4*>(D + (int64_t)(ty * 4 + r) * ld + tx * 8 + 4);
+    c[r][0] = lo.x; c[r][1] = lo.y; c[r][2] = lo.z; c[r][3] = lo.w;
+    c[r][4] = hi.x; c[r][5] = hi.y; c[r][6] = hi.z; c[r][7] = hi.w;
+  }
+  if (ty == 0) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) rowb[0][tx * 8 + q] = c[0][q];
+  }
+  if (tx == 0) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) colb[0][ty * 4 + r] = c[r][0];
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int kb = 0; kb < TILE / 8; ++kb) {
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      const int k = kb * 8 + kk, cur = kk & 1;
+      T bk[8], a[4];
+      {
+        const V4 b0 = *reinterpret_cast<const V4*>(&rowb[cur][tx * 8]), b1 = *reinterpret_cast<const V4*>(&rowb[cur][tx * 8 + 4]);
+        const V4 a0 = *reinterpret_cast<const V4*>(&colb[cur][ty * 4]);
+        bk[0] = b0.x; bk[1] = b0.y; bk[2] = b0.z; bk[3] = b0.w; bk[4] = b1.x; bk[5] = b1.y; bk[6] = b1.z; bk[7] = b1.w;
+        a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) c[r][q] = Semiring<T>::relax1(c[r][q], a[r], bk[q]);
+      // publish row k + 1 and column k + 1 (static register choice: (kk + 1) & 3 and (kk + 1) & 7)
+      const int kn = k + 1;
+      if (kn < TILE) {
+        if ((kn >> 2) == ty) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) rowb[cur ^ 1][tx * 8 + q] = c[(kk + 1) & 3][q];
+        }
+        if ((kn >> 3) == tx) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) colb[cur ^ 1][ty * 4 + r] = c[r][(kk + 1) & 7];
+        }
+      }
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    V4 lo, hi;
+    lo.x = c[r][0]; lo.y = c[r][1]; lo.z = c[r][2]; lo.w = c[r][3];
+    hi.x = c[r][4]; hi.y = c[r][5]; hi.z = c[r][6]; hi.w = c[r][7];
+    const int64_t off = (int64_t)(ty * 4 + r) * ld + tx * 8;
+    *reinterpret_cast<V4*>(D + off) = lo;
+    *reinterpret_cast<V4*>(D + off + 4) = hi;
+    store_peers(off, lo, hi);
+  }
+}
+
 // acc = min(acc, A (x) B) over kcols inner indices (a multiple of 16), streamed in 32-wide chunks; a last half chunk is
 // loaded whole (the 16 extra k columns of A / rows of B must be readable) and half of it used.  A: 128 rows x kcols
 // (16-byte aligned rows), B: kcols rows x 128 columns (16-byte aligned rows for int32, 4-byte for fp32).  smem_raw: kTileSmemBytes of dynamic shared memory.

@@ -44,7 +44,8 @@ struct drs_sep_plan {
   const int32_t *d_pstart = nullptr, *d_pend = nullptr, *d_sj = nullptr, *d_kpad = nullptr, *d_koff = nullptr, *d_qpad = nullptr,
                 *d_cbase = nullptr, *d_wpad = nullptr, *d_sall = nullptr, *d_sepcol = nullptr, *d_ct_part = nullptr,
                 *d_ct_col0 = nullptr;
-  const int64_t *d_moff = nullptr, *d_apoff = nullptr;
+  const int64_t *d_moff = nullptr, *d_apoff = nullptr, *d_top_moff = nullptr;
+  const int32_t* d_top_qpad = nullptr;   // the separator graph's matrix as a one-part table for the batched FW kernels
   void *d_M = nullptr, *d_dS = nullptr, *d_Dall = nullptr, *d_dSr = nullptr, *d_Duni = nullptr, *d_Aprime = nullptr, *d_Apad = nullptr;
   double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   bool no_mirror = false;   // DRS_SEP_NO_MIRROR=1: compute every output tile (measurement knob)
@@ -114,46 +115,14 @@ __global__ void sep_scatter_parts_kernel(T* M, SepTab t, const int32_t* __restri
   }
 }
 
-constexpr int P1PAD = TILE + 4;
-constexpr size_t kDiagSmemBytes = sizeof(float) * TILE * P1PAD;
-
-// round r of every part's blocked FW, phase 1: close the diagonal tile (r, r) in shared memory
+// round r of every part's blocked FW, phase 1: close the diagonal tile (r, r) (minplus.cuh: fw_close_diag_tile)
 template <typename T>
-__global__ void __launch_bounds__(1024, 1) sep_fw_diag_kernel(T* M, SepTab t, int r) {
+__global__ void __launch_bounds__(DIAG_THREADS) sep_fw_diag_kernel(T* M, SepTab t, int r) {
   using V4 = typename Vec4<T>::type;
   const int j = blockIdx.x;
   const int64_t ld = t.qpad[j];
   if ((int64_t)r * TILE >= ld) return;
-  T* D = M + t.moff[j] + (int64_t)r * TILE * (ld + 1);
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  T(*s)[P1PAD] = reinterpret_cast<T(*)[P1PAD]>(smem_raw);
-  const int tid = threadIdx.x;
-  const int tx = tid & 31, ty = tid >> 5;  // thread owns rows ty*4..+3, columns tx*4..+3
-  V4 c[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    c[q] = *reinterpret_cast<const V4*>(D + (int64_t)(ty * 4 + q) * ld + tx * 4);
-    *reinterpret_cast<V4*>(&s[ty * 4 + q][tx * 4]) = c[q];
-  }
-  __syncthreads();
-  for (int k = 0; k < TILE; ++k) {
-    const V4 bk = *reinterpret_cast<const V4*>(&s[k][tx * 4]);
-    T a[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) a[q] = s[ty * 4 + q][k];
-    __syncthreads();   // all reads of iteration k done before anyone overwrites
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      c[q].x = Semiring<T>::relax1(c[q].x, a[q], bk.x);
-      c[q].y = Semiring<T>::relax1(c[q].y, a[q], bk.y);
-      c[q].z = Semiring<T>::relax1(c[q].z, a[q], bk.z);
-      c[q].w = Semiring<T>::relax1(c[q].w, a[q], bk.w);
-      *reinterpret_cast<V4*>(&s[ty * 4 + q][tx * 4]) = c[q];
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int q = 0; q < 4; ++q) *reinterpret_cast<V4*>(D + (int64_t)(ty * 4 + q) * ld + tx * 4) = c[q];
+  fw_close_diag_tile<T>(M + t.moff[j] + (int64_t)r * TILE * (ld + 1), ld, threadIdx.x, [](int64_t, V4, V4) {});
 }
 
 // phases 2 (pivot row / column panels: grid (maxnb, 2, nparts)) and 3 (every other tile: grid (maxnb, maxnb, nparts))
@@ -402,7 +371,6 @@ int configure_kernels() {
   DRS_CUDA(cudaFuncSetAttribute(sep_expand_rows_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
   DRS_CUDA(cudaFuncSetAttribute(sep_expand_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
   DRS_CUDA(cudaFuncSetAttribute(sep_expand_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
-  DRS_CUDA(cudaFuncSetAttribute(sep_fw_diag_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDiagSmemBytes));
   if (dev >= 0 && dev < 64) configured[dev] = true;
   return DRS_OK;
 }
@@ -467,7 +435,7 @@ int run_level(drs_sep_plan* p, const LevelInput& in, int mode, bool directed, T*
   SEP_CHECK();
   SEP_EVENT(1);
   for (int r = 0; r < p->maxnb; ++r) {
-    sep_fw_diag_kernel<T><<<p->nparts, 1024, kDiagSmemBytes, st>>>(M, t, r);
+    sep_fw_diag_kernel<T><<<p->nparts, DIAG_THREADS, 0, st>>>(M, t, r);
     drs_count_launch();
     if (p->maxnb > 1) {
       sep_fw_tile_kernel<T><<<dim3(p->maxnb, 2, p->nparts), NTHREADS, kTileSmemBytes, st>>>(M, t, r, 2);
@@ -496,10 +464,17 @@ int run_level(drs_sep_plan* p, const LevelInput& in, int mode, bool directed, T*
       if ((rc = run_level<T>(p->child, up, mode, directed, dS, p->spad, 0, p->spad, st, nullptr))) return rc;   // in place
     } else {
       const int nbs = p->spad / TILE;
-      for (int kb = 0; kb < nbs; ++kb) {
-        char* panel = (char*)dS + sizeof(T) * (int64_t)kb * TILE * p->spad;
-        if ((rc = drs_fw_pivot_row(mode, panel, p->spad, kb, st))) return rc;
-        if ((rc = drs_fw_update(mode, dS, p->spad, p->spad, panel, kb, kb, 0, nbs, st))) return rc;
+      SepTab top = t;
+      top.moff = p->d_top_moff; top.qpad = p->d_top_qpad;
+      for (int r = 0; r < nbs; ++r) {
+        sep_fw_diag_kernel<T><<<1, DIAG_THREADS, 0, st>>>(dS, top, r);
+        drs_count_launch();
+        if (nbs > 1) {
+          sep_fw_tile_kernel<T><<<dim3(nbs, 2, 1), NTHREADS, kTileSmemBytes, st>>>(dS, top, r, 2);
+          sep_fw_tile_kernel<T><<<dim3(nbs, nbs, 1), NTHREADS, kTileSmemBytes, st>>>(dS, top, r, 3);
+          drs_count_launch(2);
+        }
+        SEP_CHECK();
       }
     }
   }
@@ -649,6 +624,9 @@ int make_plan(int n, int npad, int m, const int32_t* src, const int32_t* dst, in
   const size_t o_mo = add(p->moff.data(), 8 * nparts), o_ao = add(p->apoff.data(), 8 * nparts);
   const size_t o_sa = add(p->sall.data(), 4 * p->sall.size()), o_sc = add(p->sepcol.data(), 4 * p->sepcol.size());
   const size_t o_cp = add(p->ct_part.data(), 4 * p->ct_part.size()), o_cq = add(p->ct_col0.data(), 4 * p->ct_col0.size());
+  const int64_t top_moff = 0;
+  const int32_t top_qpad = p->spad;
+  const size_t o_tm = add(&top_moff, 8), o_tq = add(&top_qpad, 4);
   std::vector<unsigned char> img(off, 0);
   for (const Slice& x : sl) std::memcpy(img.data() + x.off, x.src, x.bytes);
   drs_count_alloc();
@@ -666,6 +644,7 @@ int make_plan(int n, int npad, int m, const int32_t* src, const int32_t* dst, in
   p->d_moff = (const int64_t*)(b + o_mo); p->d_apoff = (const int64_t*)(b + o_ao);
   p->d_sall = (const int32_t*)(b + o_sa); p->d_sepcol = (const int32_t*)(b + o_sc);
   p->d_ct_part = (const int32_t*)(b + o_cp); p->d_ct_col0 = (const int32_t*)(b + o_cq);
+  p->d_top_moff = (const int64_t*)(b + o_tm); p->d_top_qpad = (const int32_t*)(b + o_tq);
   { const char* e = getenv("DRS_SEP_NO_MIRROR"); p->no_mirror = e && e[0] == '1'; }
   if (S_lists_out) *S_lists_out = std::move(S);
   *out = p;

@@ -205,9 +205,9 @@ SECOND_LEVEL_MIN_SEPARATORS = int(os.environ.get("DRS_SEP_LEVEL2_MIN", 1024))
 def default_part_target(n):
     """Vertices per part of the separator partition: the expansion stage costs n^2 x (separators around a part, which
     grow like the square root of the part) and the separator closure (number of separators)^3, which shrinks with
-    larger parts; on grid-like road maps the two balance near n / 128 (measured on the 50k-node city, where 320 .. 520
-    vertices per part are within 3 % of each other: DESIGN.md)."""
-    return int(min(2048, max(192, n // 128)))
+    larger parts; on grid-like road maps the optimum is flat (measured on the 50k-node city: 128 .. 520 vertices per part
+    build within 4 % of each other); a power of two keeps the part interiors inside whole 128-column tiles."""
+    return int(min(2048, max(192, 1 << max(0, int(round(math.log2(max(n, 1) / 196.0)))))))
 
 
 def partition_order(n, src, dst, lng=None, lat=None, target=None, second_level=False):
