@@ -729,9 +729,9 @@ def main():
 
     sparse = 2 * data.m <= 16 * data.n                    # the library's AUTO rule (drs_apsp_build)
     import ctypes as C
-    sep_info = [C.c_int32(0) for _ in range(7)]
+    sep_info = [C.c_int32(0) for _ in range(8)]
     _lib.check(lib.drs_sep_info(handle, *[C.byref(x) for x in sep_info[:5]]), lib)
-    _lib.check(lib.drs_sep_info2(handle, C.byref(sep_info[5]), C.byref(sep_info[6])), lib)
+    _lib.check(lib.drs_sep_info2(handle, C.byref(sep_info[5]), C.byref(sep_info[6]), None), lib)
     sep_usable = bool(sep_info[4].value)
     algo = args.algorithm if args.algorithm != "auto" else ("sep" if sep_usable else "sssp" if sparse else "fw")
 

@@ -112,7 +112,7 @@ SIGNATURES = {
     "drs_partition_order": (C.c_int, [C.c_int32, C.c_int32, _i32p, _i32p, _f64p, _f64p, C.c_int32, _i32p, _i32p, C.c_int32, _i32p,
                                       _i32p, _i32p]),
     "drs_graph_set_partition": (C.c_int, [_vp, C.c_int32, _i32p, C.c_int32, _i32p]),
-    "drs_sep_info2": (C.c_int, [_vp, _i32p, _i32p]),
+    "drs_sep_info2": (C.c_int, [_vp, _i32p, _i32p, _i32p]),
     "drs_sep_work": (C.c_int, [_vp, _f64p]),
     "drs_sep_info": (C.c_int, [_vp, _i32p, _i32p, _i32p, _i32p, _i32p]),
     "drs_apsp_rows_sep": (C.c_int, [_vp, C.c_int32, _vp, C.c_int64, C.c_int32, C.c_int32, _vp]),

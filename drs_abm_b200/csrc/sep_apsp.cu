@@ -26,6 +26,7 @@
 #include <numeric>
 #include <queue>
 #include <thread>
+#include <type_traits>
 
 #include "drs_common.cuh"
 #include "minplus.cuh"
@@ -47,6 +48,10 @@ struct drs_sep_plan {
   const int64_t *d_moff = nullptr, *d_apoff = nullptr, *d_top_moff = nullptr;
   const int32_t* d_top_qpad = nullptr;   // the separator graph's matrix as a one-part table for the batched FW kernels
   void *d_M = nullptr, *d_dS = nullptr, *d_Dall = nullptr, *d_dSr = nullptr, *d_Duni = nullptr, *d_Aprime = nullptr, *d_Apad = nullptr;
+  void* d_Apad16 = nullptr;      // the A_j panels as 16-bit distances (the B operand of the 16-bit output tiles)
+  int32_t* d_flags = nullptr;    // [0] largest finite vertex->separator distance, [1] largest finite A_j / same-part entry (float bits)
+  bool used16 = false;           // the last build ran its output tiles on the 16-bit path
+  bool no16 = false;             // DRS_SEP_NO_U16=1 (measurement knob)
   double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   bool no_mirror = false;   // DRS_SEP_NO_MIRROR=1: compute every output tile (measurement knob)
   int n = 0, npad = 0;      // vertices of this level and their padded count (the leading dimension of its matrix)
@@ -157,8 +162,18 @@ __global__ void __launch_bounds__(NTHREADS, 2) sep_fw_tile_kernel(T* M, SepTab t
 
 // S1x: what the later stages read from the closed parts.  blockIdx.z: 0 = A' rows (interior -> own separators),
 // 1 = padded A_j panels (own separators -> interior, columns on the global 128-column grid), 2 = S_j x S_j into dS
+template <typename T> __device__ __forceinline__ int finite_bits(T v);   // ordering key of a finite distance, 0 for +inf
+template <> __device__ __forceinline__ int finite_bits<float>(float v) { return v < Semiring<float>::inf() ? __float_as_int(v) : 0; }
+template <> __device__ __forceinline__ int finite_bits<int>(int v) { return v < Semiring<int>::inf() ? __float_as_int((float)v) : 0; }
+__device__ __forceinline__ void flag_max(int32_t* flag, int key) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) key = max(key, __shfl_xor_sync(0xffffffffu, key, o));
+  if ((threadIdx.x & 31) == 0 && key > 0) atomicMax(flag, key);
+}
+
 template <typename T>
-__global__ void sep_extract_kernel(const T* __restrict__ M, SepTab t, T* __restrict__ Aprime, T* __restrict__ Apad, T* dS) {
+__global__ void sep_extract_kernel(const T* __restrict__ M, SepTab t, T* __restrict__ Aprime, T* __restrict__ Apad, T* dS,
+                                   uint16_t* __restrict__ Apad16, int32_t* flags) {
   const int j = blockIdx.y;
   const int ps = t.pstart[j], nj = t.pend[j] - ps, sj = t.sj[j], kp = t.kpad[j];
   const int64_t ld = t.qpad[j];
@@ -173,12 +188,24 @@ __global__ void sep_extract_kernel(const T* __restrict__ M, SepTab t, T* __restr
   } else if (blockIdx.z == 1) {
     const int wp = t.wpad[j], cb = t.cbase[j];
     T* Aj = Apad + t.apoff[j];
+    uint16_t* Aj16 = Apad16 + t.apoff[j];
     const int64_t total = (int64_t)((kp + KC - 1) / KC * KC) * wp;
+    int key = 0;
     for (int64_t idx = g0; idx < total; idx += gs) {
       const int k = (int)(idx / wp), c = (int)(idx - (int64_t)k * wp);
       const int lv = cb + c - ps;
-      Aj[idx] = (k < sj && lv >= 0 && lv < nj) ? Mj[(int64_t)(nj + k) * ld + lv] : Semiring<T>::inf();
+      const T v = (k < sj && lv >= 0 && lv < nj) ? Mj[(int64_t)(nj + k) * ld + lv] : Semiring<T>::inf();
+      Aj[idx] = v;
+      Aj16[idx] = (uint16_t)dist_to_u16((float)v);
+      key = max(key, finite_bits<T>(v));
     }
+    // distances inside the part (the other candidates of its diagonal tiles) count towards the same bound
+    const int64_t inner = (int64_t)nj * nj;
+    for (int64_t idx = g0; idx < inner; idx += gs) {
+      const int li = (int)(idx / nj), lj = (int)(idx - (int64_t)li * nj);
+      key = max(key, finite_bits<T>(Mj[(int64_t)li * ld + lj]));
+    }
+    flag_max(flags + 1, key);
   } else {
     const int32_t* lst = t.sall + t.koff[j];
     const int64_t total = (int64_t)sj * sj;
@@ -216,8 +243,9 @@ __global__ void sep_arcs_kernel(T* dS, SepTab t, const int32_t* __restrict__ out
 // S2x: the rows of dS in the order of the concatenated separator lists (the B operand of S3), and the separator rows of
 // D_uni (a separator's distances to the separators are its dS row); padding rows = +inf
 template <typename T>
-__global__ void sep_gather_dsr_kernel(const T* __restrict__ dS, SepTab t, T* __restrict__ dSr, T* __restrict__ Duni) {
+__global__ void sep_gather_dsr_kernel(const T* __restrict__ dS, SepTab t, T* __restrict__ dSr, T* __restrict__ Duni, int32_t* flags) {
   const int64_t n1 = (int64_t)t.ktot * t.spad, n2 = (int64_t)(t.npad - t.sep0) * t.spad;
+  int key = 0;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n1 + n2; idx += (int64_t)gridDim.x * blockDim.x) {
     if (idx < n1) {
       const int cp = (int)(idx / t.spad), c = (int)(idx - (int64_t)cp * t.spad);
@@ -226,9 +254,12 @@ __global__ void sep_gather_dsr_kernel(const T* __restrict__ dS, SepTab t, T* __r
     } else {
       const int64_t k = idx - n1;
       const int r = (int)(k / t.spad), c = (int)(k - (int64_t)r * t.spad);
-      Duni[(int64_t)(t.sep0 + r) * t.spad + c] = r < t.nsep ? dS[(int64_t)r * t.spad + c] : Semiring<T>::inf();
+      const T v = r < t.nsep ? dS[(int64_t)r * t.spad + c] : Semiring<T>::inf();
+      Duni[(int64_t)(t.sep0 + r) * t.spad + c] = v;
+      key = max(key, finite_bits<T>(v));
     }
   }
+  flag_max(flags, key);
 }
 
 // ------------------------------------------------------------------------------------------------ S3: vertex -> separators
@@ -237,7 +268,7 @@ __global__ void sep_gather_dsr_kernel(const T* __restrict__ dS, SepTab t, T* __r
 // rows and not stored.
 template <typename T>
 __global__ void __launch_bounds__(NTHREADS, 2) sep_expand_rows_kernel(const T* __restrict__ Aprime, const T* __restrict__ dSr,
-                                                                        T* __restrict__ Duni, SepTab t, int row_lo, int row_hi) {
+                                                                        T* __restrict__ Duni, SepTab t, int row_lo, int row_hi, int32_t* flags) {
   const int i = blockIdx.z;
   const int row0 = t.pstart[i] + blockIdx.y * TILE, pe = t.pend[i];
   if (row0 >= pe || row0 >= row_hi || min(row0 + TILE, pe) <= row_lo) return;
@@ -248,13 +279,21 @@ __global__ void __launch_bounds__(NTHREADS, 2) sep_expand_rows_kernel(const T* _
   tile_accumulate<T>(acc, Aprime + (int64_t)row0 * t.kmax, t.kmax, dSr + (int64_t)t.koff[i] * t.spad + (int64_t)blockIdx.x * TILE,
                      t.spad, t.kpad[i], smem_raw, tid);
   acc_store<T>(acc, Duni + (int64_t)row0 * t.spad + (int64_t)blockIdx.x * TILE, t.spad, pe - row0, TILE, tid);
+  int key = 0;
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+    if (acc_row<T>(r, tid >> 4) < pe - row0) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) key = max(key, finite_bits<T>(acc[r][c]));
+    }
+  flag_max(flags, key);
 }
 
 // S3x: SPREAD_ROWS rows of the shard per CTA: the rows of D_uni spread over the per-part k ranges (D_all, the A operand
 // of S4) and copied into the separator columns of the output; padding as the other builders leave it (0 on the diagonal
 // of the padding rows, +inf elsewhere)
 constexpr int SPREAD_ROWS = 8;
-template <typename T>
+template <typename T, bool U16>   // U16: D_all holds the 16-bit distance in both halves of a 32-bit word (A operand of the 16-bit tiles)
 __global__ void sep_spread_kernel(const T* __restrict__ Duni, T* __restrict__ Dall, T* __restrict__ C, int64_t ldc, SepTab t, int row_lo) {
   const int lr0 = blockIdx.x * SPREAD_ROWS, u0 = row_lo + lr0;
   for (int c = threadIdx.x; c < t.ktot; c += blockDim.x) {
@@ -262,7 +301,9 @@ __global__ void sep_spread_kernel(const T* __restrict__ Duni, T* __restrict__ Da
 #pragma unroll
     for (int r = 0; r < SPREAD_ROWS; ++r) {
       const int u = u0 + r;
-      Dall[(int64_t)u * t.ktot + c] = (s >= 0 && u < t.n) ? Duni[(int64_t)u * t.spad + s] : Semiring<T>::inf();
+      const T v = (s >= 0 && u < t.n) ? Duni[(int64_t)u * t.spad + s] : Semiring<T>::inf();
+      if (U16) reinterpret_cast<uint32_t*>(Dall)[(int64_t)u * t.ktot + c] = dist_to_u16((float)v) * 0x10001u;
+      else Dall[(int64_t)u * t.ktot + c] = v;
     }
   }
   for (int c = t.sep0 + threadIdx.x; c < t.npad; c += blockDim.x) {
@@ -318,6 +359,48 @@ __global__ void __launch_bounds__(NTHREADS, 2) sep_expand_kernel(const T* __rest
     acc_store_transposed<T>(acc, smem_raw, C + (int64_t)C0 * ldc + R0, ldc, col_lo, col_hi, min(TILE, t.sep0 - R0), tid);
 }
 
+// S4 on the 16-bit path (fp32 matrices of maps whose distances stay below 2^15): same tiles, VIADDMNMX.U16x2 inside
+template <bool MIRROR>
+__global__ void __launch_bounds__(NTHREADS, 3) sep_expand16_kernel(const uint32_t* __restrict__ Dall2, const uint16_t* __restrict__ Apad16,
+                                                                     const float* __restrict__ M, float* __restrict__ C, int64_t ldc, SepTab t,
+                                                                     int row_lo) {
+  const int ct = blockIdx.x;
+  const int j = t.ct_part[ct], C0 = t.ct_col0[ct];
+  const int R0 = row_lo + blockIdx.y * TILE;
+  const int ps = t.pstart[j], pe = t.pend[j];
+  const int col_lo = max(ps - C0, 0), col_hi = min(pe - C0, TILE);
+  if (MIRROR && !(C0 + col_hi > R0 || R0 + TILE > t.sep0)) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  uint32_t acc2[8][4];
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int p = 0; p < 4; ++p) acc2[r][p] = U16_INF * 0x10001u;
+  if (R0 < pe && R0 + TILE > ps) {
+    const int64_t ld = t.qpad[j];
+    const float* Mj = M + t.moff[j];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int u = R0 + ty + 16 * r;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int v = C0 + tx * 8 + q;
+        if (u >= ps && u < pe && v >= ps && v < pe) {
+          const unsigned d = dist_to_u16(Mj[(int64_t)(u - ps) * ld + (v - ps)]);
+          acc2[r][q >> 1] = (q & 1) ? ((acc2[r][q >> 1] & 0xffffu) | (d << 16)) : ((acc2[r][q >> 1] & 0xffff0000u) | d);
+        }
+      }
+    }
+  }
+  tile_accumulate_u16(acc2, Dall2 + (int64_t)R0 * t.ktot + t.koff[j], t.ktot, Apad16 + t.apoff[j] + (C0 - t.cbase[j]), t.wpad[j],
+                      t.kpad[j], smem_raw, tid);
+  acc16_store(acc2, C + (int64_t)(R0 - row_lo) * ldc + C0, ldc, TILE, col_hi, tid, col_lo);
+  if (MIRROR && R0 < t.sep0)
+    acc16_store_transposed(acc2, smem_raw, C + (int64_t)C0 * ldc + R0, ldc, col_lo, col_hi, min(TILE, t.sep0 - R0), tid);
+}
+
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 // Level 2 (the separator graph of level 1 handled by the same build): the closed parts and the top separator graph
@@ -371,6 +454,8 @@ int configure_kernels() {
   DRS_CUDA(cudaFuncSetAttribute(sep_expand_rows_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
   DRS_CUDA(cudaFuncSetAttribute(sep_expand_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
   DRS_CUDA(cudaFuncSetAttribute(sep_expand_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
+  DRS_CUDA(cudaFuncSetAttribute(sep_expand16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTile16SmemBytes));
+  DRS_CUDA(cudaFuncSetAttribute(sep_expand16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTile16SmemBytes));
   if (dev >= 0 && dev < 64) configured[dev] = true;
   return DRS_OK;
 }
@@ -381,7 +466,8 @@ int ensure_work(drs_sep_plan* p, cudaStream_t st) {
   const size_t b_Dall = al(4 * (size_t)p->npad * p->ktot), b_dSr = al(4 * (size_t)p->ktot * p->spad);
   const size_t b_Duni = al(4 * (size_t)p->npad * p->spad);
   const size_t b_Apr = al(4 * (size_t)(p->npad + TILE) * p->kmax), b_Apad = al(4 * (size_t)std::max<int64_t>(p->ap_elems, 1));
-  const size_t total = b_M + b_dS + b_Dall + b_dSr + b_Duni + b_Apr + b_Apad;
+  const size_t b_Apad16 = al(2 * (size_t)std::max<int64_t>(p->ap_elems, 1)), b_flags = 256;
+  const size_t total = b_M + b_dS + b_Dall + b_dSr + b_Duni + b_Apr + b_Apad + b_Apad16 + b_flags;
   const bool fresh = !p->d_work || p->work_bytes < total;
   if (fresh) {
     if (p->d_work) cudaFree(p->d_work);
@@ -395,7 +481,7 @@ int ensure_work(drs_sep_plan* p, cudaStream_t st) {
   }
   char* b = (char*)p->d_work;
   p->d_M = b; b += b_M; p->d_dS = b; b += b_dS; p->d_Dall = b; b += b_Dall; p->d_dSr = b; b += b_dSr; p->d_Duni = b; b += b_Duni;
-  p->d_Aprime = b; b += b_Apr; p->d_Apad = b;
+  p->d_Aprime = b; b += b_Apr; p->d_Apad = b; b += b_Apad; p->d_Apad16 = b; b += b_Apad16; p->d_flags = (int32_t*)b;
   // rows of A' past the last interior vertex are read by the last row tile of a part; what is computed from them is never
   // stored, but they should hold numbers that stay numbers
   if (fresh) DRS_CUDA(cudaMemsetAsync(p->d_Aprime, 0x7f, b_Apr, st));
@@ -412,7 +498,7 @@ struct LevelInput {
 // synchronises.  ev (9 events, may be null) brackets the stages of this level.
 template <typename T>
 int run_level(drs_sep_plan* p, const LevelInput& in, int mode, bool directed, T* C, int64_t ldc, int row0, int nrows, cudaStream_t st,
-              cudaEvent_t* ev) {
+              cudaEvent_t* ev, bool allow16) {
   int rc;
   DrsHostTimer tm("sep run_level");
   if ((rc = ensure_work(p, st))) return rc;
@@ -422,6 +508,7 @@ int run_level(drs_sep_plan* p, const LevelInput& in, int mode, bool directed, T*
     *Apad = (T*)p->d_Apad;
 #define SEP_CHECK() DRS_REQUIRE(cudaGetLastError() == cudaSuccess, DRS_ERR_CUDA, "separator build: kernel launch failed (%s:%d)", __FILE__, __LINE__)
 #define SEP_EVENT(i) do { if (ev) cudaEventRecord(ev[i], st); } while (0)
+  DRS_CUDA(cudaMemsetAsync(p->d_flags, 0, 8, st));
   SEP_EVENT(0);
   // S1: closed parts
   if (in.W) {
@@ -448,7 +535,7 @@ int run_level(drs_sep_plan* p, const LevelInput& in, int mode, bool directed, T*
   // S1x: the separator graph's matrix, A' and the padded A_j panels
   if (in.W) sep_gather_top_kernel<T><<<148 * 4, 256, 0, st>>>(dS, t, (const T*)in.W, in.ldw);
   else sep_fill_identity_kernel<T><<<148 * 4, 256, 0, st>>>(dS, p->spad, p->spad);
-  sep_extract_kernel<T><<<dim3(32, p->nparts, 3), 256, 0, st>>>(M, t, Apr, Apad, dS);
+  sep_extract_kernel<T><<<dim3(32, p->nparts, 3), 256, 0, st>>>(M, t, Apr, Apad, dS, (uint16_t*)p->d_Apad16, p->d_flags);
   drs_count_launch(2);
   if (p->nsep > 0 && !in.W) {
     sep_arcs_kernel<T><<<(p->nsep + 127) / 128, 128, 0, st>>>(dS, t, in.out_ptr, in.out_col, in.out_w);
@@ -461,7 +548,7 @@ int run_level(drs_sep_plan* p, const LevelInput& in, int mode, bool directed, T*
     if (p->child) {
       LevelInput up;
       up.W = dS; up.ldw = p->spad;
-      if ((rc = run_level<T>(p->child, up, mode, directed, dS, p->spad, 0, p->spad, st, nullptr))) return rc;   // in place
+      if ((rc = run_level<T>(p->child, up, mode, directed, dS, p->spad, 0, p->spad, st, nullptr, false))) return rc;   // in place
     } else {
       const int nbs = p->spad / TILE;
       SepTab top = t;
@@ -480,22 +567,40 @@ int run_level(drs_sep_plan* p, const LevelInput& in, int mode, bool directed, T*
   }
   SEP_EVENT(4);
   // S2x
-  sep_gather_dsr_kernel<T><<<148 * 8, 256, 0, st>>>(dS, t, dSr, Duni);
+  sep_gather_dsr_kernel<T><<<148 * 8, 256, 0, st>>>(dS, t, dSr, Duni, p->d_flags);
   drs_count_launch();
   SEP_CHECK();
   SEP_EVENT(5);
   // S3 + S3x
   sep_expand_rows_kernel<T><<<dim3(p->spad / TILE, p->max_rowtiles, p->nparts), NTHREADS, kTileSmemBytes, st>>>(Apr, dSr, Duni, t, row0,
-                                                                                                              row0 + nrows);
-  sep_spread_kernel<T><<<nrows / SPREAD_ROWS, 256, 0, st>>>(Duni, Dall, C, ldc, t, row0);
-  drs_count_launch(2);
+                                                                                                              row0 + nrows, p->d_flags);
+  drs_count_launch();
+  SEP_CHECK();
+  // 16-bit output tiles when every candidate sum stays below 2^15: (largest vertex->separator distance of this shard and
+  // of the separators) + (largest distance inside a closed part) bounds them all.  One 8-byte read-back decides.
+  bool use16 = false;
+  if (allow16 && std::is_same<T, float>::value && !p->no16) {
+    float h[2] = {0, 0};
+    DRS_CUDA(cudaMemcpyAsync(h, p->d_flags, 8, cudaMemcpyDeviceToHost, st));
+    DRS_CUDA(cudaStreamSynchronize(st));
+    use16 = h[0] + h[1] < (float)U16_INF;
+  }
+  p->used16 = use16;
+  if (use16) sep_spread_kernel<T, true><<<nrows / SPREAD_ROWS, 256, 0, st>>>(Duni, Dall, C, ldc, t, row0);
+  else sep_spread_kernel<T, false><<<nrows / SPREAD_ROWS, 256, 0, st>>>(Duni, Dall, C, ldc, t, row0);
+  drs_count_launch();
   SEP_CHECK();
   SEP_EVENT(6);
   // S4
   if (p->ncoltiles > 0) {
     const dim3 grid(p->ncoltiles, nrows / TILE);
     const bool mirror = !directed && row0 == 0 && nrows == p->npad && !p->no_mirror;
-    if (mirror) sep_expand_kernel<T, true><<<grid, NTHREADS, kTileSmemBytes, st>>>(Dall, Apad, M, C, ldc, t, row0);
+    if (use16) {
+      const uint32_t* D2 = (const uint32_t*)p->d_Dall;
+      const uint16_t* A16 = (const uint16_t*)p->d_Apad16;
+      if (mirror) sep_expand16_kernel<true><<<grid, NTHREADS, kTile16SmemBytes, st>>>(D2, A16, (const float*)p->d_M, (float*)C, ldc, t, row0);
+      else sep_expand16_kernel<false><<<grid, NTHREADS, kTile16SmemBytes, st>>>(D2, A16, (const float*)p->d_M, (float*)C, ldc, t, row0);
+    } else if (mirror) sep_expand_kernel<T, true><<<grid, NTHREADS, kTileSmemBytes, st>>>(Dall, Apad, M, C, ldc, t, row0);
     else sep_expand_kernel<T, false><<<grid, NTHREADS, kTileSmemBytes, st>>>(Dall, Apad, M, C, ldc, t, row0);
     drs_count_launch();
   }
@@ -516,7 +621,7 @@ int build_rows(drs_graph* g, int mode, T* local, int64_t ld, int row0, int nrows
   for (auto& e : ev) DRS_CUDA(cudaEventCreate(&e));
   LevelInput in;
   in.out_ptr = g->d_out_ptr; in.out_col = g->d_out_col; in.out_w = g->d_out_w;
-  rc = run_level<T>(p, in, mode, g->directed != 0, local, ld, row0, nrows, st, ev);
+  rc = run_level<T>(p, in, mode, g->directed != 0, local, ld, row0, nrows, st, ev, true);
   if (!rc && cudaStreamSynchronize(st) != cudaSuccess) {
     drs_set_error("separator build: %s", cudaGetErrorString(cudaGetLastError()));
     rc = DRS_ERR_CUDA;
@@ -646,6 +751,7 @@ int make_plan(int n, int npad, int m, const int32_t* src, const int32_t* dst, in
   p->d_ct_part = (const int32_t*)(b + o_cp); p->d_ct_col0 = (const int32_t*)(b + o_cq);
   p->d_top_moff = (const int64_t*)(b + o_tm); p->d_top_qpad = (const int32_t*)(b + o_tq);
   { const char* e = getenv("DRS_SEP_NO_MIRROR"); p->no_mirror = e && e[0] == '1'; }
+  { const char* e = getenv("DRS_SEP_NO_U16"); p->no16 = e && e[0] == '1'; }
   if (S_lists_out) *S_lists_out = std::move(S);
   *out = p;
   return DRS_OK;
@@ -711,11 +817,12 @@ extern "C" int drs_sep_info(const drs_graph* g, int32_t* nparts, int32_t* nsep, 
   return DRS_OK;
 }
 
-extern "C" int drs_sep_info2(const drs_graph* g, int32_t* n_sep_parts, int32_t* n_top) {
+extern "C" int drs_sep_info2(const drs_graph* g, int32_t* n_sep_parts, int32_t* n_top, int32_t* used16) {
   DRS_REQUIRE(g, DRS_ERR_ARG, "drs_sep_info2: null graph");
   const drs_sep_plan* c = g->sep ? g->sep->child : nullptr;
   if (n_sep_parts) *n_sep_parts = c ? c->nparts : 0;
   if (n_top) *n_top = c ? c->nsep : 0;
+  if (used16) *used16 = (g->sep && g->sep->used16) ? 1 : 0;
   return DRS_OK;
 }
 

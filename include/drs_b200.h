@@ -143,8 +143,10 @@ int drs_partition_order(int32_t n, int32_t m, const int32_t* src, const int32_t*
  * Builds the device tables of the SEP build. */
 int drs_graph_set_partition(drs_graph* g, int32_t nparts, const int32_t* part_ptr, int32_t n_sep_parts,
                             const int32_t* sep_part_ptr);
-/* groups and top separators of the second level (0, 0 without one) */
-int drs_sep_info2(const drs_graph* g, int32_t* n_sep_parts, int32_t* n_top);
+/* groups and top separators of the second level (0, 0 without one); whether the last build ran its output tiles on the
+ * 16-bit path (VIADDMNMX.U16x2: fp32 matrices of maps whose distances all stay below 2^15, decided per build from the
+ * largest vertex->separator and in-part distances; twice the relaxation rate, same matrix) */
+int drs_sep_info2(const drs_graph* g, int32_t* n_sep_parts, int32_t* n_top, int32_t* used16);
 /* parts, separator vertices, sum and maximum of the per-part separator counts (padded), and whether AUTO would use it */
 int drs_sep_info(const drs_graph* g, int32_t* nparts, int32_t* nsep, int32_t* ktot, int32_t* kmax, int32_t* usable);
 /* Rows [row0, row0 + nrows) (multiples of DRS_FW_TILE) of the matrix by the SEP build into local_dev (nrows x ld, ld = npad):

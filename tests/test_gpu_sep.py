@@ -22,7 +22,7 @@ def _data(n, src, dst, tt, directed=False, coords=None):
     return RoadGraphData(n, directed, src, dst, vattrs, {"ttmedian": tt, "length": 10.0 * tt})
 
 
-def _random_planar(n_side, seed, directed=False, coords=True, drop=0.1, islands=1):
+def _random_planar(n_side, seed, directed=False, coords=True, drop=0.1, islands=1, wmax=90):
     """Grid with random integer weights, a fraction of the edges dropped (components are kept: unreachable pairs are part
     of the case), optionally several disjoint copies, optionally one-way arcs with independent weights."""
     rs = np.random.RandomState(seed)
@@ -40,7 +40,7 @@ def _random_planar(n_side, seed, directed=False, coords=True, drop=0.1, islands=
     if directed:
         back = rs.rand(len(src)) < 0.8
         src, dst = np.concatenate([src, dst[back]]), np.concatenate([dst, src[back]])
-    tt = rs.randint(5, 90, size=len(src)).astype(np.float64)
+    tt = rs.randint(5, wmax, size=len(src)).astype(np.float64)
     n = islands * n_side * n_side
     perm = rs.permutation(n)                     # the caller's numbering carries no locality
     inv = np.empty(n, dtype=np.int64); inv[perm] = np.arange(n)
@@ -57,10 +57,10 @@ def _matrices(data, target, mode, algorithms, levels=1):
                       second_level_min=1 if levels == 2 else 10 ** 9)
         out[algo] = G.dist_rows(0, G.n)
         if algo == _lib.APSP_SEP:
-            info = [C.c_int32(0) for _ in range(7)]
+            info = [C.c_int32(0) for _ in range(8)]
             _lib.check(G._lib.drs_sep_info(G._handle, *[C.byref(x) for x in info[:5]]), G._lib)
-            _lib.check(G._lib.drs_sep_info2(G._handle, C.byref(info[5]), C.byref(info[6])), G._lib)
-            out["parts"], out["nsep"], out["groups"], out["top"] = info[0].value, info[1].value, info[5].value, info[6].value
+            _lib.check(G._lib.drs_sep_info2(G._handle, C.byref(info[5]), C.byref(info[6]), C.byref(info[7])), G._lib)
+            out["parts"], out["nsep"], out["groups"], out["top"], out["used16"] = info[0].value, info[1].value, info[5].value, info[6].value, info[7].value
         G.close()
     return out
 
@@ -82,6 +82,9 @@ CASES = {
     "no_coordinates_22": dict(n_side=22, seed=5, coords=False),
     "islands_3x12": dict(n_side=12, seed=6, islands=3, drop=0.2),
     "directed_islands_no_coordinates": dict(n_side=14, seed=7, islands=2, directed=True, coords=False, drop=0.25),
+    # distances beyond 15 bits: the output tiles stay on the 32-bit path; and right at the edge of the 16-bit range
+    "heavy_weights_24": dict(n_side=24, seed=8, wmax=9000),
+    "edge_of_16_bits_24": dict(n_side=24, seed=9, wmax=1200),
 }
 
 
@@ -99,6 +102,11 @@ def test_sep_matrix_equals_oracle_and_sssp_on_irregular_maps(case, target, mode,
     assert got["parts"] >= 3 and got["nsep"] > 0
     if levels == 2 and target == 24:
         assert got["groups"] >= 2 and 0 < got["top"] < got["nsep"]   # the separator graph really went through level 2
+    finite = want[np.isfinite(want)]
+    if mode == 1 or case == "heavy_weights_24":
+        assert got["used16"] == 0                                    # int32 matrices and long distances: 32-bit tiles
+    elif finite.max() < 16000:
+        assert got["used16"] == 1                                    # VIADDMNMX.U16x2 tiles, same matrix
 
 
 def test_sep_on_the_5k_city_equals_sssp_and_paths_follow():

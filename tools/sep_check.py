@@ -35,8 +35,8 @@ for name in args.configs.split(","):
         npad = (data.n + 127) // 128 * 128
         out = {"config": name, "target": target, "n": data.n, "upload_s": round(t_up, 4), "parts": info[0].value, "nsep": info[1].value,
                "ktot": info[2].value, "kmax": info[3].value, "usable": info[4].value}
-        i2 = [C.c_int32(0), C.c_int32(0)]
-        _lib.check(lib.drs_sep_info2(h, C.byref(i2[0]), C.byref(i2[1])), lib)
+        i2 = [C.c_int32(0), C.c_int32(0), C.c_int32(0)]
+        _lib.check(lib.drs_sep_info2(h, C.byref(i2[0]), C.byref(i2[1]), None), lib)
         out["groups"], out["top"] = i2[0].value, i2[1].value
         res = {}
         for algo in ("sep", "sssp"):
@@ -56,6 +56,8 @@ for name in args.configs.split(","):
                 prof = np.zeros(8)
                 _lib.check(lib.drs_apsp_sep_profile(h, _lib.ptr_f64(prof)), lib)
                 out["sep_stage_ms"] = [round(float(x), 3) for x in prof]
+                _lib.check(lib.drs_sep_info2(h, None, None, C.byref(i2[2])), lib)
+                out["used16"] = i2[2].value
         out["equal"] = bool(torch.equal(res["sep"], res["sssp"]))
         if not out["equal"]:
             diff = (res["sep"] != res["sssp"])
