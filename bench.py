@@ -41,6 +41,8 @@ NCU_TRAFFIC = {
     "sssp_batch_kernel": (9.401e9 + 22.049e9, "profiles/r02_kernels_ncu.md"),
     "insertion_reach_kernel": (0.403e9 + 0.007e9, "profiles/r02_kernels_ncu.md"),
     "rv_filter_kernel": (0.404e9 + 0.022e9, "profiles/r02_kernels_ncu.md"),
+    "sep_expand16_kernel": (1.518e9 + 8.954e9, "profiles/r02_sep_ncu.md"),
+    "sep_expand_kernel": (1.712e9 + 9.136e9, "profiles/r02_sep_ncu.md"),
 }
 
 WORKLOADS = {
@@ -750,7 +752,7 @@ def main():
     # ALU roofline denominator, measured live (rank 0): best add+min stream of the three instruction mixes
     alu = {}
     if rank == 0:
-        for v, name in ((0, "fadd_fadd_fmnmx3"), (1, "viaddmnmx_s32"), (2, "fadd2_fmnmx3")):
+        for v, name in ((0, "fadd_fadd_fmnmx3"), (1, "viaddmnmx_s32"), (2, "fadd2_fmnmx3"), (3, "viaddmnmx_u16x2")):
             r = __import__("ctypes").c_double()
             _lib.check(lib.drs_alu_peak(v, 8000, __import__("ctypes").byref(r)), lib)
             alu[name] = r.value
@@ -839,7 +841,7 @@ def main():
     if rank == 0:
         import ctypes as C
         relax = float(data.n) ** 3
-        best_alu = max(alu.values())
+        best_alu = max(v for k, v in alu.items() if k != "viaddmnmx_u16x2")    # 32-bit relaxations (FW tiles, 32-bit SEP tiles)
         narcs = 2 * data.m
         sssp_bytes = (16.0 * narcs + 8.0 * data.n) * data.n          # 16 E_dir + 8 N bytes per source
 
@@ -887,6 +889,9 @@ def main():
             prof_sep, work_sep = np.zeros(8), np.zeros(5)
             _lib.check(lib.drs_apsp_sep_profile(Gp._handle, _lib.ptr_f64(prof_sep)), lib)
             _lib.check(lib.drs_sep_work(Gp._handle, _lib.ptr_f64(work_sep)), lib)
+            u16 = C.c_int32(0)
+            _lib.check(lib.drs_sep_info2(Gp._handle, None, None, C.byref(u16)), lib)
+            sep_used16 = bool(u16.value)
             Gp.close()
         if world == 1:
             # per-kernel device times from the library's own CUDA events (public single-GPU build)
@@ -907,21 +912,28 @@ def main():
             if prof_sep is not None:
                 t_k = prof_sep[6] * 1e-3
                 tile_stages_ms = float(prof_sep[1] + prof_sep[3] + prof_sep[5] + prof_sep[6])
+                sep_kernel = "sep_expand16_kernel" if sep_used16 else "sep_expand_kernel"
+                sep_peak = alu["viaddmnmx_u16x2"] if sep_used16 else best_alu
                 line["roofline"] = {
-                    "bound": "alu", "achieved": 2 * work_sep[4] / t_k / 1e12, "peak": 2 * best_alu / 1e12, "unit": "Tlaneop/s",
-                    "frac": (work_sep[4] / t_k) / best_alu, "executed_frac": (work_sep[3] / t_k) / best_alu,
-                    "kernel": "sep_expand_kernel", "kernel_ms": float(prof_sep[6]), "share_of_step": float(prof_sep[6]) / float(prof_sep.sum()),
+                    "bound": "alu", "achieved": 2 * work_sep[4] / t_k / 1e12, "peak": 2 * sep_peak / 1e12, "unit": "Tlaneop/s",
+                    "frac": (work_sep[4] / t_k) / sep_peak, "executed_frac": (work_sep[3] / t_k) / sep_peak,
+                    "frac_of_the_32_bit_peak": (work_sep[4] / t_k) / best_alu,
+                    "kernel": sep_kernel, "kernel_ms": float(prof_sep[6]), "share_of_step": float(prof_sep[6]) / float(prof_sep.sum()),
+                    "second_bound": {"bound": "hbm", "what": "the kernel writes the whole matrix once", "bytes": 4.0 * npad * npad,
+                                     "achieved_GBps": 4.0 * npad * npad / t_k / 1e9, "frac": 4.0 * npad * npad / t_k / 1e9 / peaks["hbm_gbs"]},
                     "algorithmic_relaxations_per_launch": float(work_sep[4]), "executed_relaxations_per_launch": float(work_sep[3]),
-                    "traffic": NCU_TRAFFIC.get("sep_expand_kernel", (None, None))[0] if (args.config == "C3" and args.mode == "f32") else None,
-                    "traffic_source": NCU_TRAFFIC.get("sep_expand_kernel", (None, None))[1],
+                    "traffic": NCU_TRAFFIC.get(sep_kernel, (None, None))[0] if (args.config == "C3" and args.mode == "f32") else None,
+                    "traffic_source": NCU_TRAFFIC.get(sep_kernel, (None, None))[1],
                     "hbm": {"compulsory_bytes": 4.0 * npad * npad, "GBps_over_the_whole_build": 4.0 * npad * npad / sec / 1e9,
                             "frac_of_peak": 4.0 * npad * npad / sec / 1e9 / peaks["hbm_gbs"]},
                     "all_tile_stages": {"relaxations": float(work_sep[0] + work_sep[1] + work_sep[2] + work_sep[3]), "ms": tile_stages_ms,
                                         "frac": float(work_sep[0] + work_sep[1] + work_sep[2] + work_sep[3]) / (tile_stages_ms * 1e-3) / best_alu},
                     "note": "min-plus is not a tensor-core operation (north_star): the bound is the add+min issue rate of the SMs.  2 lane-ops "
                             "per relaxation; algorithmic relaxations of the dominant kernel = n * sum_j n_j * |S_j| (halved: mirrored tiles on the "
-                            "undirected map), executed = the same with |S_j| padded to 16 and part widths to 128-column tiles; peak = best "
-                            "register-resident add+min stream measured in this run (drs_alu_peak)"}
+                            "undirected map), executed = the same with |S_j| padded to 16 and part widths to 128-column tiles; peak = the "
+                            "register-resident add+min stream of the instruction the tiles use, measured in this run (drs_alu_peak: "
+                            "VIADDMNMX.U16x2 when the map's distances stay below 2^15 and the tiles run 16-bit, else the best 32-bit mix); "
+                            "at that rate the 10 GB matrix write becomes the next bound (second_bound)"}
         elif algo == "sssp":
             t_k = prof_sssp[2] * 1e-3 if prof_sssp is not None else sec * world
             line["roofline"] = sssp_roofline(t_k)
