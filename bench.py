@@ -883,16 +883,15 @@ def main():
                 "gpu_launches": launches, "clocks": clocks, "checksum": checksum, "alu_peak_relax_per_s": alu,
                 "peaks": peaks_src}
         prof_fw = prof_sssp = prof_sep = None
-        if world == 1 and algo == "sep":
-            Gp = RoadGraph(data, mode=mode, algorithm=_lib.APSP_SEP)
-            Gp.build(); Gp._valid = False; Gp.build()
+        if algo == "sep":
+            # stage times of rank 0's last timed build (the library's own CUDA events) and the relaxations its shard executes
             prof_sep, work_sep = np.zeros(8), np.zeros(5)
-            _lib.check(lib.drs_apsp_sep_profile(Gp._handle, _lib.ptr_f64(prof_sep)), lib)
-            _lib.check(lib.drs_sep_work(Gp._handle, _lib.ptr_f64(work_sep)), lib)
+            starts = apsp_dist.block_partition(npad // 128, world)
+            _lib.check(lib.drs_apsp_sep_profile(handle, _lib.ptr_f64(prof_sep)), lib)
+            _lib.check(lib.drs_sep_work(handle, starts[0] * 128, (starts[1] - starts[0]) * 128, _lib.ptr_f64(work_sep)), lib)
             u16 = C.c_int32(0)
-            _lib.check(lib.drs_sep_info2(Gp._handle, None, None, C.byref(u16)), lib)
+            _lib.check(lib.drs_sep_info2(handle, None, None, C.byref(u16)), lib)
             sep_used16 = bool(u16.value)
-            Gp.close()
         if world == 1:
             # per-kernel device times from the library's own CUDA events (public single-GPU build)
             def profile(algorithm):
@@ -919,15 +918,17 @@ def main():
                     "frac": (work_sep[4] / t_k) / sep_peak, "executed_frac": (work_sep[3] / t_k) / sep_peak,
                     "frac_of_the_32_bit_peak": (work_sep[4] / t_k) / best_alu,
                     "kernel": sep_kernel, "kernel_ms": float(prof_sep[6]), "share_of_step": float(prof_sep[6]) / float(prof_sep.sum()),
-                    "second_bound": {"bound": "hbm", "what": "the kernel writes the whole matrix once", "bytes": 4.0 * npad * npad,
-                                     "achieved_GBps": 4.0 * npad * npad / t_k / 1e9, "frac": 4.0 * npad * npad / t_k / 1e9 / peaks["hbm_gbs"]},
+                    "second_bound": {"bound": "hbm", "what": "the kernel writes its rows of the matrix once", "bytes": 4.0 * npad * npad / world,
+                                     "achieved_GBps": 4.0 * npad * npad / world / t_k / 1e9,
+                                     "frac": 4.0 * npad * npad / world / t_k / 1e9 / peaks["hbm_gbs"]},
                     "algorithmic_relaxations_per_launch": float(work_sep[4]), "executed_relaxations_per_launch": float(work_sep[3]),
-                    "traffic": NCU_TRAFFIC.get(sep_kernel, (None, None))[0] if (args.config == "C3" and args.mode == "f32") else None,
+                    "traffic": NCU_TRAFFIC.get(sep_kernel, (None, None))[0] if (args.config == "C3" and args.mode == "f32" and world == 1) else None,
                     "traffic_source": NCU_TRAFFIC.get(sep_kernel, (None, None))[1],
                     "hbm": {"compulsory_bytes": 4.0 * npad * npad, "GBps_over_the_whole_build": 4.0 * npad * npad / sec / 1e9,
                             "frac_of_peak": 4.0 * npad * npad / sec / 1e9 / peaks["hbm_gbs"]},
                     "all_tile_stages": {"relaxations": float(work_sep[0] + work_sep[1] + work_sep[2] + work_sep[3]), "ms": tile_stages_ms,
                                         "frac": float(work_sep[0] + work_sep[1] + work_sep[2] + work_sep[3]) / (tile_stages_ms * 1e-3) / best_alu},
+                    "rank": 0, "rows": int((starts[1] - starts[0]) * 128),
                     "note": "min-plus is not a tensor-core operation (north_star): the bound is the add+min issue rate of the SMs.  2 lane-ops "
                             "per relaxation; algorithmic relaxations of the dominant kernel = n * sum_j n_j * |S_j| (halved: mirrored tiles on the "
                             "undirected map), executed = the same with |S_j| padded to 16 and part widths to 128-column tiles; peak = the "

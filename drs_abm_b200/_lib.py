@@ -81,6 +81,7 @@ SIGNATURES = {
     "drs_graph_set_weights": (C.c_int, [_vp, _f64p]),
     "drs_locality_order": (C.c_int, [C.c_int32, _f64p, _f64p, _i32p]),
     "drs_graph_destroy": (C.c_int, [_vp]),
+    "drs_pool_trim": (C.c_int, []),
     "drs_graph_info": (C.c_int, [_vp, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p]),
     "drs_apsp_build": (C.c_int, [_vp, C.c_int32]),
     "drs_apsp_matrices": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_int64)]),
@@ -113,7 +114,7 @@ SIGNATURES = {
                                       _i32p, _i32p]),
     "drs_graph_set_partition": (C.c_int, [_vp, C.c_int32, _i32p, C.c_int32, _i32p]),
     "drs_sep_info2": (C.c_int, [_vp, _i32p, _i32p, _i32p]),
-    "drs_sep_work": (C.c_int, [_vp, _f64p]),
+    "drs_sep_work": (C.c_int, [_vp, C.c_int32, C.c_int32, _f64p]),
     "drs_sep_info": (C.c_int, [_vp, _i32p, _i32p, _i32p, _i32p, _i32p]),
     "drs_apsp_rows_sep": (C.c_int, [_vp, C.c_int32, _vp, C.c_int64, C.c_int32, C.c_int32, _vp]),
     "drs_apsp_sep_profile": (C.c_int, [_vp, _f64p]),

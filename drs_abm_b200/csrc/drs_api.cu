@@ -29,12 +29,76 @@ extern "C" int64_t drs_alloc_count(void) { return (int64_t)g_allocs.load(); }
 extern "C" const char* drs_last_error(void) { return g_err; }
 extern "C" int drs_version(void) { return 100; }
 
+// Process-wide cache of the large device blocks (travel-time / predecessor matrices, the work arrays of the separator
+// build): a simulation that reloads its map, or a benchmark that builds fresh graphs, gets the blocks of the graph it just
+// closed back instead of paying cudaFree + cudaMalloc of 10 GB each time (milliseconds, and a device-wide synchronisation).
+// At most 6 blocks are kept per process; drs_pool_trim() returns them to the driver.
+#include <mutex>
+namespace {
+struct BigBlock { void* p; size_t bytes; int dev; };
+std::mutex g_pool_mu;
+std::vector<BigBlock> g_pool;
+constexpr size_t kPoolMin = (size_t)32 << 20;
+}  // namespace
+
+int drs_big_alloc(void** out, size_t bytes) {
+  *out = nullptr;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (bytes >= kPoolMin) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    int best = -1;
+    for (int i = 0; i < (int)g_pool.size(); ++i)
+      if (g_pool[i].dev == dev && g_pool[i].bytes >= bytes && g_pool[i].bytes <= bytes + bytes / 4 &&
+          (best < 0 || g_pool[i].bytes < g_pool[best].bytes))
+        best = i;
+    if (best >= 0) {
+      *out = g_pool[best].p;
+      g_pool.erase(g_pool.begin() + best);
+      return DRS_OK;
+    }
+  }
+  drs_count_alloc();
+  if (cudaMalloc(out, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    drs_pool_trim();                       // the cache may be what is in the way
+    if (cudaMalloc(out, bytes) != cudaSuccess) {
+      cudaGetLastError();
+      *out = nullptr;
+      DRS_REQUIRE(false, DRS_ERR_NOMEM, "cudaMalloc(%zu bytes) failed", bytes);
+    }
+  }
+  return DRS_OK;
+}
+
+void drs_big_free(void* p, size_t bytes) {
+  if (!p) return;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (bytes >= kPoolMin) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (g_pool.size() < 6) { g_pool.push_back({p, bytes, dev}); return; }
+  }
+  cudaFree(p);
+}
+
+extern "C" int drs_pool_trim(void) {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (const BigBlock& b : g_pool) { cudaSetDevice(b.dev); cudaFree(b.p); }
+  cudaSetDevice(cur);
+  g_pool.clear();
+  return DRS_OK;
+}
+
 namespace {
 
 void free_matrices(drs_graph* g) {
   if (g->owns_matrices) {
-    if (g->d_dist) cudaFree(g->d_dist);
-    if (g->d_pred) cudaFree(g->d_pred);
+    const size_t bytes = sizeof(float) * (size_t)g->ld * (size_t)g->ld;
+    if (g->d_dist) drs_big_free(g->d_dist, bytes);
+    if (g->d_pred) drs_big_free(g->d_pred, bytes);
   }
   g->d_dist = nullptr;
   g->d_pred = nullptr;
@@ -259,17 +323,16 @@ extern "C" int drs_apsp_build(drs_graph* g, int32_t mode) {
   DrsHostTimer tm("drs_apsp_build");
   if (!g->owns_matrices || g->ld != ld) {
     free_matrices(g);
-    drs_count_alloc();
-    DRS_CUDA(cudaMalloc(&g->d_dist, sizeof(float) * ld * ld));
+    { int rca = drs_big_alloc(&g->d_dist, sizeof(float) * (size_t)ld * (size_t)ld); if (rca) return rca; }
     g->owns_matrices = true;
     g->ld = ld;
   }
   tm.lap("matrix malloc");
   if (g->pred_mode == DRS_PRED_MATRIX && !g->d_pred) {
-    drs_count_alloc();
-    DRS_CUDA(cudaMalloc((void**)&g->d_pred, sizeof(int32_t) * ld * ld));
+    int rca = drs_big_alloc((void**)&g->d_pred, sizeof(int32_t) * (size_t)ld * (size_t)ld);
+    if (rca) return rca;
   }
-  if (g->pred_mode == DRS_PRED_LAZY && g->d_pred) { cudaFree(g->d_pred); g->d_pred = nullptr; }
+  if (g->pred_mode == DRS_PRED_LAZY && g->d_pred) { drs_big_free(g->d_pred, sizeof(int32_t) * (size_t)ld * (size_t)ld); g->d_pred = nullptr; }
   g->apsp_valid = false;
   g->mode = mode;
   int rc;

@@ -101,6 +101,9 @@ struct drs_graph {
 };
 
 int drs_graph_upload_weights(drs_graph* g);
+// large device blocks through the process-wide cache (drs_api.cu); *out = nullptr and an error code on failure
+int drs_big_alloc(void** out, size_t bytes);
+void drs_big_free(void* p, size_t bytes);
 void drs_sep_free(drs_graph* g);
 bool drs_sep_usable(const drs_graph* g);   // partition present, exact arithmetic, separators a small part of the map
 // DRS_MODE_F32 / DRS_MODE_I32 known, and I32 only on integer travel times below 1e6 (a float weight would be truncated)

@@ -470,13 +470,9 @@ int ensure_work(drs_sep_plan* p, cudaStream_t st) {
   const size_t total = b_M + b_dS + b_Dall + b_dSr + b_Duni + b_Apr + b_Apad + b_Apad16 + b_flags;
   const bool fresh = !p->d_work || p->work_bytes < total;
   if (fresh) {
-    if (p->d_work) cudaFree(p->d_work);
+    if (p->d_work) drs_big_free(p->d_work, p->work_bytes);
     p->d_work = nullptr; p->work_bytes = 0;
-    drs_count_alloc();
-    if (cudaMalloc(&p->d_work, total) != cudaSuccess) {
-      cudaGetLastError();
-      DRS_REQUIRE(false, DRS_ERR_NOMEM, "separator build: cudaMalloc(%zu bytes) of work arrays failed", total);
-    }
+    { int rca = drs_big_alloc(&p->d_work, total); if (rca) return rca; }
     p->work_bytes = total;
   }
   char* b = (char*)p->d_work;
@@ -640,7 +636,7 @@ void free_plan(drs_sep_plan* p) {
   if (!p) return;
   free_plan(p->child);
   if (p->d_tables) cudaFree(p->d_tables);
-  if (p->d_work) cudaFree(p->d_work);
+  if (p->d_work) drs_big_free(p->d_work, p->work_bytes);
   delete p;
 }
 
@@ -829,38 +825,43 @@ extern "C" int drs_sep_info2(const drs_graph* g, int32_t* n_sep_parts, int32_t* 
 namespace {
 // relaxations (one add + one min) the stages of a level execute: [0] part closures, [1] separator closure, [2] vertex ->
 // separator rows, [3] output tiles as launched, [4] output tiles without padding (n * sum_j n_j * s_j, halved when mirrored)
-void level_work(const drs_sep_plan* p, bool directed, double* w) {
+void level_work(const drs_sep_plan* p, bool directed, int row0, int nrows, double* w) {
   w[0] = w[1] = w[2] = w[3] = w[4] = 0;
+  const bool whole = row0 == 0 && nrows == p->npad;
+  const int row1 = row0 + nrows;
   for (int j = 0; j < p->nparts; ++j) {
     const double q = p->qpad[j];
     w[0] += q * q * q;
-    w[2] += (double)round_up(p->pend[j] - p->pstart[j], TILE) * p->spad * p->kpad[j];
-    w[4] += (double)p->n * (p->pend[j] - p->pstart[j]) * p->sj[j];
+    const int rows = std::max(0, std::min(row1, p->pend[j]) - std::max(row0, p->pstart[j]));
+    w[2] += (double)round_up(rows, TILE) * p->spad * p->kpad[j];
+    w[4] += (double)std::max(0, std::min(row1, p->n) - row0) * (p->pend[j] - p->pstart[j]) * p->sj[j];
   }
   if (p->nsep > 0) {
     if (p->child) {
       double c[5];
-      level_work(p->child, directed, c);
+      level_work(p->child, directed, 0, p->child->npad, c);
       w[1] = c[0] + c[1] + c[2] + c[3];
     } else {
       w[1] = (double)p->spad * p->spad * p->spad;
     }
   }
-  const bool mirror = !directed && !p->no_mirror;
+  const bool mirror = !directed && !p->no_mirror && whole;
   for (int ct = 0; ct < p->ncoltiles; ++ct) {
     const int j = p->ct_part[ct], c0 = p->ct_col0[ct];
     const int c1 = c0 + std::min(p->pend[j] - c0, TILE);
-    for (int r0 = 0; r0 < p->npad; r0 += TILE)
+    for (int r0 = row0; r0 < row1; r0 += TILE)
       if (!mirror || c1 > r0 || r0 + TILE > p->sep0) w[3] += (double)TILE * TILE * p->kpad[j];
   }
   if (mirror) w[4] *= 0.5;
 }
 }  // namespace
 
-extern "C" int drs_sep_work(const drs_graph* g, double* relax5) {
+extern "C" int drs_sep_work(const drs_graph* g, int32_t row0, int32_t nrows, double* relax5) {
   DRS_REQUIRE(g && relax5, DRS_ERR_ARG, "drs_sep_work: null argument");
   DRS_REQUIRE(g->sep, DRS_ERR_STATE, "drs_sep_work: the graph has no partition");
-  level_work(g->sep, g->directed != 0, relax5);
+  if (nrows <= 0) { row0 = 0; nrows = g->npad; }
+  DRS_REQUIRE(row0 >= 0 && row0 + nrows <= g->npad && row0 % TILE == 0 && nrows % TILE == 0, DRS_ERR_ARG, "drs_sep_work: bad shard");
+  level_work(g->sep, g->directed != 0, row0, nrows, relax5);
   return DRS_OK;
 }
 

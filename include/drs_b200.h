@@ -67,6 +67,11 @@ int drs_graph_set_weights(drs_graph* g, const double* tt_host);
 
 int drs_graph_destroy(drs_graph* g);
 
+/* The library keeps up to six large device blocks (matrices, work arrays of the separator build) of destroyed graphs in a
+ * process-wide cache so that the next graph of similar size does not pay cudaFree + cudaMalloc of ~10 GB; this call
+ * returns them to the driver. */
+int drs_pool_trim(void);
+
 /* Host-side helper of the bindings: vertex ids in the order of a locality-preserving DEVICE numbering (order_out[k] =
  * caller's id of device vertex k; Morton curve over the ranks of the lng / lat values).  The kernels index distance rows by
  * vertex id; a caller that numbers its vertices this way before drs_graph_create (and translates ids at the boundary, as
@@ -154,10 +159,11 @@ int drs_sep_info(const drs_graph* g, int32_t* nparts, int32_t* nsep, int32_t* kt
  * its own rows; no collective).  Same role as drs_apsp_rows_sssp. */
 int drs_apsp_rows_sep(const drs_graph* g, int32_t mode, void* local_dev, int64_t ld, int32_t row0, int32_t nrows,
                       void* stream);
-/* relaxations (one add + one min each) a whole-matrix SEP build executes: [0] part closures, [1] separator closure,
- * [2] vertex->separator rows, [3] output tiles as launched (padded), [4] output tiles without padding = the
- * algorithmic work of the dominant kernel: n * sum_j n_j * |S_j|, halved on undirected maps (mirrored tiles) */
-int drs_sep_work(const drs_graph* g, double* relax5);
+/* relaxations (one add + one min each) a SEP build of rows [row0, row0 + nrows) executes (nrows = 0: the whole matrix):
+ * [0] part closures, [1] separator closure, [2] vertex->separator rows, [3] output tiles as launched (padded), [4] output
+ * tiles without padding = the algorithmic work of the dominant kernel: rows * sum_j n_j * |S_j|, halved for a whole
+ * undirected matrix (mirrored tiles) */
+int drs_sep_work(const drs_graph* g, int32_t row0, int32_t nrows, double* relax5);
 /* milliseconds of the last SEP build by stage: fill+scatter, part closures, extraction, separator closure,
  * gathers, vertex->separator rows, output tiles, separator columns */
 int drs_apsp_sep_profile(const drs_graph* g, double* ms8);

@@ -25,7 +25,7 @@ for _ in range(args.builds):
     G.build()
 prof, work = np.zeros(8), np.zeros(5)
 _lib.check(lib.drs_apsp_sep_profile(G._handle, _lib.ptr_f64(prof)), lib)
-_lib.check(lib.drs_sep_work(G._handle, _lib.ptr_f64(work)), lib)
+_lib.check(lib.drs_sep_work(G._handle, 0, 0, _lib.ptr_f64(work)), lib)
 print(json.dumps({"config": args.config, "stage_ms": [round(float(x), 3) for x in prof], "total_ms": round(float(prof.sum()), 3),
                   "relaxations": [float(x) for x in work], "launches": int(lib.drs_launch_count())}))
 G.close()
