@@ -32,13 +32,18 @@ extern "C" int drs_version(void) { return 100; }
 // Process-wide cache of the large device blocks (travel-time / predecessor matrices, the work arrays of the separator
 // build): a simulation that reloads its map, or a benchmark that builds fresh graphs, gets the blocks of the graph it just
 // closed back instead of paying cudaFree + cudaMalloc of 10 GB each time (milliseconds, and a device-wide synchronisation).
-// At most 6 blocks are kept per process; drs_pool_trim() returns them to the driver.
+// The small per-graph blocks (CSR arena, partition tables, query scratch, pinned staging) go through it too: a fresh graph
+// then costs no cudaMalloc / cudaHostAlloc at all.  At most 24 device blocks and 4 pinned ones are kept per process;
+// drs_pool_trim() returns them to the driver.
 #include <mutex>
 namespace {
 struct BigBlock { void* p; size_t bytes; int dev; };
+struct PinnedBlock { void* host; void* dev_alias; size_t bytes; int dev; };
 std::mutex g_pool_mu;
 std::vector<BigBlock> g_pool;
-constexpr size_t kPoolMin = (size_t)32 << 20;
+std::vector<PinnedBlock> g_pinned;
+constexpr size_t kPoolMin = (size_t)16 << 10;
+constexpr size_t kPoolSlots = 24;
 }  // namespace
 
 int drs_big_alloc(void** out, size_t bytes) {
@@ -49,7 +54,7 @@ int drs_big_alloc(void** out, size_t bytes) {
     std::lock_guard<std::mutex> lk(g_pool_mu);
     int best = -1;
     for (int i = 0; i < (int)g_pool.size(); ++i)
-      if (g_pool[i].dev == dev && g_pool[i].bytes >= bytes && g_pool[i].bytes <= bytes + bytes / 4 &&
+      if (g_pool[i].dev == dev && g_pool[i].bytes >= bytes && g_pool[i].bytes <= bytes + bytes / 4 + (1 << 16) &&
           (best < 0 || g_pool[i].bytes < g_pool[best].bytes))
         best = i;
     if (best >= 0) {
@@ -77,7 +82,7 @@ void drs_big_free(void* p, size_t bytes) {
   cudaGetDevice(&dev);
   if (bytes >= kPoolMin) {
     std::lock_guard<std::mutex> lk(g_pool_mu);
-    if (g_pool.size() < 6) { g_pool.push_back({p, bytes, dev}); return; }
+    if (g_pool.size() < kPoolSlots) { g_pool.push_back({p, bytes, dev}); return; }
   }
   cudaFree(p);
 }
@@ -87,9 +92,44 @@ extern "C" int drs_pool_trim(void) {
   int cur = 0;
   cudaGetDevice(&cur);
   for (const BigBlock& b : g_pool) { cudaSetDevice(b.dev); cudaFree(b.p); }
+  for (const PinnedBlock& b : g_pinned) { cudaSetDevice(b.dev); cudaFreeHost(b.host); }
   cudaSetDevice(cur);
   g_pool.clear();
+  g_pinned.clear();
   return DRS_OK;
+}
+
+// pinned, device-mapped staging of at least `bytes` (from the cache when one fits)
+static int pinned_alloc(size_t bytes, void** host, void** dev_alias, size_t* got) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    for (size_t i = 0; i < g_pinned.size(); ++i)
+      if (g_pinned[i].dev == dev && g_pinned[i].bytes >= bytes) {
+        *host = g_pinned[i].host; *dev_alias = g_pinned[i].dev_alias; *got = g_pinned[i].bytes;
+        g_pinned.erase(g_pinned.begin() + i);
+        return DRS_OK;
+      }
+  }
+  drs_count_alloc();
+  if (cudaHostAlloc(host, bytes, cudaHostAllocMapped) != cudaSuccess || cudaHostGetDevicePointer(dev_alias, *host, 0) != cudaSuccess) {
+    cudaGetLastError();
+    DRS_REQUIRE(false, DRS_ERR_NOMEM, "query staging: cudaHostAlloc(%zu bytes) failed", bytes);
+  }
+  *got = bytes;
+  return DRS_OK;
+}
+
+static void pinned_free(void* host, void* dev_alias, size_t bytes) {
+  if (!host) return;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (g_pinned.size() < 4) { g_pinned.push_back({host, dev_alias, bytes, dev}); return; }
+  }
+  cudaFreeHost(host);
 }
 
 namespace {
@@ -204,12 +244,8 @@ extern "C" int drs_graph_create(int32_t n, int32_t m, int32_t directed, const in
   g->h_in_eid.assign(in_eid, in_eid + na);
   auto fail = [&](int code) { drs_graph_destroy(g); return code; };
   tm.lap("host image");
-  drs_count_alloc();
-  if (cudaMalloc(&g->d_arena, img.size()) != cudaSuccess) {
-    cudaGetLastError();
-    drs_set_error("drs_graph_create: cudaMalloc(%zu bytes) failed", img.size());
-    return fail(DRS_ERR_NOMEM);
-  }
+  g->arena_bytes = img.size();
+  if (drs_big_alloc(&g->d_arena, img.size())) return fail(DRS_ERR_NOMEM);
   if (cudaMemcpy(g->d_arena, img.data(), img.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
     drs_set_error("drs_graph_create: host-to-device copy failed: %s", cudaGetErrorString(cudaGetLastError()));
     return fail(DRS_ERR_CUDA);
@@ -292,12 +328,12 @@ extern "C" int drs_graph_destroy(drs_graph* g) {
   DrsDeviceGuard guard(g->device);
   free_matrices(g);
   drs_sep_free(g);
-  if (g->d_arena) cudaFree(g->d_arena);
+  if (g->d_arena) drs_big_free(g->d_arena, g->arena_bytes);
   if (g->sssp_queues) cudaFree(g->sssp_queues);
   if (g->sssp_arcs) cudaFree(g->sssp_arcs);
   if (g->sssp_sources) cudaFree(g->sssp_sources);
-  if (g->q_dev) cudaFree(g->q_dev);
-  if (g->q_pin) cudaFreeHost(g->q_pin);
+  if (g->q_dev) drs_big_free(g->q_dev, g->q_dev_cap);
+  pinned_free(g->q_pin, g->q_pin_dev, g->q_pin_cap);
   if (g->stream) cudaStreamDestroy(g->stream);
   delete g;
   return DRS_OK;
@@ -523,14 +559,10 @@ int check_pairs(const drs_graph* g, int npairs, const int32_t* s, const int32_t*
 int pool_device(const drs_graph* gc, size_t bytes, void** out) {
   drs_graph* g = const_cast<drs_graph*>(gc);
   if (g->q_dev_cap < bytes) {
-    if (g->q_dev) cudaFree(g->q_dev);
+    if (g->q_dev) drs_big_free(g->q_dev, g->q_dev_cap);
     g->q_dev = nullptr; g->q_dev_cap = 0;
     const size_t want = std::max<size_t>(bytes + bytes / 2, 1 << 20);
-    drs_count_alloc();
-    if (cudaMalloc(&g->q_dev, want) != cudaSuccess) {
-      cudaGetLastError();
-      DRS_REQUIRE(false, DRS_ERR_NOMEM, "query scratch: cudaMalloc(%zu bytes) failed", want);
-    }
+    { int rca = drs_big_alloc(&g->q_dev, want); if (rca) return rca; }
     g->q_dev_cap = want;
   }
   *out = g->q_dev;
@@ -540,16 +572,12 @@ int pool_device(const drs_graph* gc, size_t bytes, void** out) {
 int pool_pinned(const drs_graph* gc, size_t bytes, void** host, void** dev) {
   drs_graph* g = const_cast<drs_graph*>(gc);
   if (g->q_pin_cap < bytes) {
-    if (g->q_pin) cudaFreeHost(g->q_pin);
+    pinned_free(g->q_pin, g->q_pin_dev, g->q_pin_cap);
     g->q_pin = g->q_pin_dev = nullptr; g->q_pin_cap = 0;
     const size_t want = std::max<size_t>(bytes + bytes / 2, 1 << 16);
-    drs_count_alloc();
-    if (cudaHostAlloc(&g->q_pin, want, cudaHostAllocMapped) != cudaSuccess ||
-        cudaHostGetDevicePointer(&g->q_pin_dev, g->q_pin, 0) != cudaSuccess) {
-      cudaGetLastError();
-      DRS_REQUIRE(false, DRS_ERR_NOMEM, "query staging: cudaHostAlloc(%zu bytes) failed", want);
-    }
-    g->q_pin_cap = want;
+    size_t got = 0;
+    { int rca = pinned_alloc(want, &g->q_pin, &g->q_pin_dev, &got); if (rca) return rca; }
+    g->q_pin_cap = got;
   }
   *host = g->q_pin; *dev = g->q_pin_dev;
   return DRS_OK;

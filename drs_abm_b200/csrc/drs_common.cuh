@@ -49,6 +49,7 @@ struct drs_graph {
 
   // every array below is a slice of ONE device allocation (d_arena), filled by ONE host-to-device copy
   void* d_arena = nullptr;
+  size_t arena_bytes = 0;
 
   // per-edge attributes on device, indexed by edge id
   int32_t* d_esrc = nullptr;

@@ -364,7 +364,8 @@ constexpr unsigned U16_INF = 0x7fffu;
 constexpr int BS16 = TILE / 2;   // 32-bit words per B row in shared memory
 constexpr int STAGES16 = 2;      // two chunks in flight: three CTAs of 256 threads fit an SM
 constexpr size_t kTile16RingBytes = sizeof(uint32_t) * STAGES16 * (TILE * APAD + KC * BS16);
-constexpr size_t kTile16StageBytes = sizeof(float) * TILE * (TILE + 1);   // the transposed tile staged for the mirrored store
+constexpr int TPITCH16 = TILE + 4;   // staged rows stay 16-byte aligned
+constexpr size_t kTile16StageBytes = sizeof(float) * TILE * TPITCH16;   // the transposed tile staged for the mirrored store
 constexpr size_t kTile16SmemBytes = kTile16RingBytes > kTile16StageBytes ? kTile16RingBytes : kTile16StageBytes;
 
 __device__ __forceinline__ void tile_accumulate_u16(uint32_t (&acc2)[8][4], const uint32_t* __restrict__ A, int64_t lda,
@@ -451,7 +452,9 @@ __device__ __forceinline__ void acc16_store(const uint32_t (&acc2)[8][4], float*
   }
 }
 
-// the transposed tile as fp32 (see acc_store_transposed)
+// the transposed tile as fp32 (see acc_store_transposed).  Staged row v is rotated by 4 (v / 8) elements: the 16 lanes of a
+// staging store then fall into 8 banks instead of 4, and a row segment of four is still one aligned 128-bit shared load
+// followed by one 128-bit global store (a warp writes a whole 512-byte row segment).
 __device__ __forceinline__ void acc16_store_transposed(const uint32_t (&acc2)[8][4], unsigned char* smem_raw, float* Ct, int64_t ldc,
                                                        int col_lo, int col_hi, int rows, int tid) {
   float* s = reinterpret_cast<float*>(smem_raw);
@@ -460,19 +463,17 @@ __device__ __forceinline__ void acc16_store_transposed(const uint32_t (&acc2)[8]
   for (int r = 0; r < 8; ++r)
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
-      // a row of the staged tile is rotated by v / 8 (= tx here): the 16 lanes of a store land in 16 different banks
-      s[(tx * 8 + 2 * p) * TPITCH + ((ty + 16 * r + tx) & (TILE - 1))] = u16_to_dist(acc2[r][p] & 0xffffu);
-      s[(tx * 8 + 2 * p + 1) * TPITCH + ((ty + 16 * r + tx) & (TILE - 1))] = u16_to_dist(acc2[r][p] >> 16);
+      const int pos = (ty + 16 * r + 4 * tx) & (TILE - 1);
+      s[(tx * 8 + 2 * p) * TPITCH16 + pos] = u16_to_dist(acc2[r][p] & 0xffffu);
+      s[(tx * 8 + 2 * p + 1) * TPITCH16 + pos] = u16_to_dist(acc2[r][p] >> 16);
     }
   __syncthreads();
   const int warp = tid >> 5, lane = tid & 31;
   for (int v = warp; v < TILE; v += NTHREADS / 32) {
     if (v < col_lo || v >= col_hi) continue;
     float* crow = Ct + (int64_t)v * ldc;
-    const float* srow = s + v * TPITCH;
-    const int rot = v >> 3, u = lane * 4;
-    const float4 q4 = make_float4(srow[(u + rot) & (TILE - 1)], srow[(u + 1 + rot) & (TILE - 1)], srow[(u + 2 + rot) & (TILE - 1)],
-                                  srow[(u + 3 + rot) & (TILE - 1)]);
+    const int u = lane * 4;
+    const float4 q4 = *reinterpret_cast<const float4*>(s + v * TPITCH16 + ((u + 4 * (v >> 3)) & (TILE - 1)));
     if (u + 3 < rows) *reinterpret_cast<float4*>(crow + u) = q4;     // one 512-byte row segment per warp instruction
     else {
       if (u < rows) crow[u] = q4.x;

@@ -40,6 +40,7 @@ struct drs_sep_plan {
   int64_t m_elems = 0, ap_elems = 0;
   // device: one arena for the tables, one for the work arrays
   void* d_tables = nullptr;
+  size_t tables_bytes = 0;
   void* d_work = nullptr;
   size_t work_bytes = 0;
   const int32_t *d_pstart = nullptr, *d_pend = nullptr, *d_sj = nullptr, *d_kpad = nullptr, *d_koff = nullptr, *d_qpad = nullptr,
@@ -77,12 +78,10 @@ template <> __device__ __forceinline__ void atomic_min_nonneg<int>(int* addr, in
 template <typename T>
 __global__ void sep_fill_parts_kernel(T* M, SepTab t) {
   const int j = blockIdx.y;
-  const int64_t ld = t.qpad[j], total = ld * ld;
+  const int ld = t.qpad[j];
   T* Mj = M + t.moff[j];
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t i = idx / ld, c = idx - i * ld;
-    Mj[idx] = (i == c) ? (T)0 : Semiring<T>::inf();
-  }
+  for (int i = blockIdx.x; i < ld; i += gridDim.x)
+    for (int c = threadIdx.x; c < ld; c += blockDim.x) Mj[(int64_t)i * ld + c] = (i == c) ? (T)0 : Semiring<T>::inf();
 }
 
 // local index of vertex y in Q_j (interior first, then S_j in list order), -1 when y is outside the closed part
@@ -178,21 +177,21 @@ __global__ void sep_extract_kernel(const T* __restrict__ M, SepTab t, T* __restr
   const int ps = t.pstart[j], nj = t.pend[j] - ps, sj = t.sj[j], kp = t.kpad[j];
   const int64_t ld = t.qpad[j];
   const T* Mj = M + t.moff[j];
-  const int64_t g0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gs = (int64_t)gridDim.x * blockDim.x;
+  const unsigned g0 = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x;   // every extent here is far below 2^31
   if (blockIdx.z == 0) {
-    const int64_t total = (int64_t)nj * t.kmax;
-    for (int64_t idx = g0; idx < total; idx += gs) {
-      const int li = (int)(idx / t.kmax), k = (int)(idx - (int64_t)li * t.kmax);
+    const unsigned total = (unsigned)nj * t.kmax, kmax = t.kmax;
+    for (unsigned idx = g0; idx < total; idx += gs) {
+      const int li = (int)(idx / kmax), k = (int)(idx - (unsigned)li * kmax);
       Aprime[(int64_t)(ps + li) * t.kmax + k] = k < sj ? Mj[(int64_t)li * ld + nj + k] : Semiring<T>::inf();
     }
   } else if (blockIdx.z == 1) {
     const int wp = t.wpad[j], cb = t.cbase[j];
     T* Aj = Apad + t.apoff[j];
     uint16_t* Aj16 = Apad16 + t.apoff[j];
-    const int64_t total = (int64_t)((kp + KC - 1) / KC * KC) * wp;
+    const unsigned total = (unsigned)((kp + KC - 1) / KC * KC) * wp;
     int key = 0;
-    for (int64_t idx = g0; idx < total; idx += gs) {
-      const int k = (int)(idx / wp), c = (int)(idx - (int64_t)k * wp);
+    for (unsigned idx = g0; idx < total; idx += gs) {
+      const int k = (int)(idx / (unsigned)wp), c = (int)(idx - (unsigned)k * wp);
       const int lv = cb + c - ps;
       const T v = (k < sj && lv >= 0 && lv < nj) ? Mj[(int64_t)(nj + k) * ld + lv] : Semiring<T>::inf();
       Aj[idx] = v;
@@ -200,17 +199,17 @@ __global__ void sep_extract_kernel(const T* __restrict__ M, SepTab t, T* __restr
       key = max(key, finite_bits<T>(v));
     }
     // distances inside the part (the other candidates of its diagonal tiles) count towards the same bound
-    const int64_t inner = (int64_t)nj * nj;
-    for (int64_t idx = g0; idx < inner; idx += gs) {
-      const int li = (int)(idx / nj), lj = (int)(idx - (int64_t)li * nj);
+    const unsigned inner = (unsigned)nj * nj;
+    for (unsigned idx = g0; idx < inner; idx += gs) {
+      const int li = (int)(idx / (unsigned)nj), lj = (int)(idx - (unsigned)li * nj);
       key = max(key, finite_bits<T>(Mj[(int64_t)li * ld + lj]));
     }
     flag_max(flags + 1, key);
   } else {
     const int32_t* lst = t.sall + t.koff[j];
-    const int64_t total = (int64_t)sj * sj;
-    for (int64_t idx = g0; idx < total; idx += gs) {
-      const int ka = (int)(idx / sj), kb = (int)(idx - (int64_t)ka * sj);
+    const unsigned total = (unsigned)sj * sj;
+    for (unsigned idx = g0; idx < total; idx += gs) {
+      const int ka = (int)(idx / (unsigned)sj), kb = (int)(idx - (unsigned)ka * sj);
       const T v = Mj[(int64_t)(nj + ka) * ld + nj + kb];
       if (v < Semiring<T>::inf()) atomic_min_nonneg<T>(dS + (int64_t)lst[ka] * t.spad + lst[kb], v);
     }
@@ -220,11 +219,8 @@ __global__ void sep_extract_kernel(const T* __restrict__ M, SepTab t, T* __restr
 // ------------------------------------------------------------------------------------------------ S2: separator graph
 template <typename T>
 __global__ void sep_fill_identity_kernel(T* M, int64_t ld, int64_t rows) {
-  const int64_t total = rows * ld;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t i = idx / ld, c = idx - i * ld;
-    M[idx] = (i == c) ? (T)0 : Semiring<T>::inf();
-  }
+  for (int i = blockIdx.x; i < rows; i += gridDim.x)
+    for (int c = threadIdx.x; c < ld; c += blockDim.x) M[(int64_t)i * ld + c] = (i == c) ? (T)0 : Semiring<T>::inf();
 }
 
 template <typename T>
@@ -244,19 +240,23 @@ __global__ void sep_arcs_kernel(T* dS, SepTab t, const int32_t* __restrict__ out
 // D_uni (a separator's distances to the separators are its dS row); padding rows = +inf
 template <typename T>
 __global__ void sep_gather_dsr_kernel(const T* __restrict__ dS, SepTab t, T* __restrict__ dSr, T* __restrict__ Duni, int32_t* flags) {
-  const int64_t n1 = (int64_t)t.ktot * t.spad, n2 = (int64_t)(t.npad - t.sep0) * t.spad;
+  const int rows1 = t.ktot, rows2 = t.npad - t.sep0;
   int key = 0;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n1 + n2; idx += (int64_t)gridDim.x * blockDim.x) {
-    if (idx < n1) {
-      const int cp = (int)(idx / t.spad), c = (int)(idx - (int64_t)cp * t.spad);
-      const int s = t.sall[cp];
-      dSr[idx] = s >= 0 ? dS[(int64_t)s * t.spad + c] : Semiring<T>::inf();
+  for (int row = blockIdx.x; row < rows1 + rows2; row += gridDim.x) {
+    if (row < rows1) {
+      const int s = t.sall[row];
+      const T* src = dS + (int64_t)max(s, 0) * t.spad;
+      T* dst = dSr + (int64_t)row * t.spad;
+      for (int c = threadIdx.x; c < t.spad; c += blockDim.x) dst[c] = s >= 0 ? src[c] : Semiring<T>::inf();
     } else {
-      const int64_t k = idx - n1;
-      const int r = (int)(k / t.spad), c = (int)(k - (int64_t)r * t.spad);
-      const T v = r < t.nsep ? dS[(int64_t)r * t.spad + c] : Semiring<T>::inf();
-      Duni[(int64_t)(t.sep0 + r) * t.spad + c] = v;
-      key = max(key, finite_bits<T>(v));
+      const int r = row - rows1;
+      const T* src = dS + (int64_t)min(r, t.spad - 1) * t.spad;
+      T* dst = Duni + (int64_t)(t.sep0 + r) * t.spad;
+      for (int c = threadIdx.x; c < t.spad; c += blockDim.x) {
+        const T v = r < t.nsep ? src[c] : Semiring<T>::inf();
+        dst[c] = v;
+        key = max(key, finite_bits<T>(v));
+      }
     }
   }
   flag_max(flags, key);
@@ -409,29 +409,30 @@ template <typename T>
 __global__ void sep_gather_parts_kernel(T* M, SepTab t, const T* __restrict__ W, int64_t ldw) {
   const int j = blockIdx.y;
   const int ps = t.pstart[j], nj = t.pend[j] - ps, q = nj + t.sj[j];
-  const int64_t ld = t.qpad[j], total = ld * ld;
+  const int ld = t.qpad[j];
   const int32_t* lst = t.sall + t.koff[j];
   T* Mj = M + t.moff[j];
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int li = (int)(idx / ld), lj = (int)(idx - (int64_t)li * ld);
-    T v = (li == lj) ? (T)0 : Semiring<T>::inf();
-    if (li < q && lj < q && li != lj) {
-      const int x = li < nj ? ps + li : t.sep0 + lst[li - nj], y = lj < nj ? ps + lj : t.sep0 + lst[lj - nj];
-      v = W[(int64_t)x * ldw + y];
+  for (int li = blockIdx.x; li < ld; li += gridDim.x) {
+    const int x = li < nj ? ps + li : (li < q ? t.sep0 + lst[li - nj] : 0);
+    for (int lj = threadIdx.x; lj < ld; lj += blockDim.x) {
+      T v = (li == lj) ? (T)0 : Semiring<T>::inf();
+      if (li < q && lj < q && li != lj) {
+        const int y = lj < nj ? ps + lj : t.sep0 + lst[lj - nj];
+        v = W[(int64_t)x * ldw + y];
+      }
+      Mj[(int64_t)li * ld + lj] = v;
     }
-    Mj[idx] = v;
   }
 }
 
 template <typename T>
 __global__ void sep_gather_top_kernel(T* dS, SepTab t, const T* __restrict__ W, int64_t ldw) {
-  const int64_t total = (int64_t)t.spad * t.spad;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int a = (int)(idx / t.spad), b = (int)(idx - (int64_t)a * t.spad);
-    T v = (a == b) ? (T)0 : Semiring<T>::inf();
-    if (a < t.nsep && b < t.nsep && a != b) v = W[(int64_t)(t.sep0 + a) * ldw + (t.sep0 + b)];
-    dS[idx] = v;
-  }
+  for (int a = blockIdx.x; a < t.spad; a += gridDim.x)
+    for (int b = threadIdx.x; b < t.spad; b += blockDim.x) {
+      T v = (a == b) ? (T)0 : Semiring<T>::inf();
+      if (a < t.nsep && b < t.nsep && a != b) v = W[(int64_t)(t.sep0 + a) * ldw + (t.sep0 + b)];
+      dS[(int64_t)a * t.spad + b] = v;
+    }
 }
 
 SepTab device_tab(const drs_sep_plan* p) {
@@ -529,8 +530,8 @@ int run_level(drs_sep_plan* p, const LevelInput& in, int mode, bool directed, T*
   }
   SEP_EVENT(2);
   // S1x: the separator graph's matrix, A' and the padded A_j panels
-  if (in.W) sep_gather_top_kernel<T><<<148 * 4, 256, 0, st>>>(dS, t, (const T*)in.W, in.ldw);
-  else sep_fill_identity_kernel<T><<<148 * 4, 256, 0, st>>>(dS, p->spad, p->spad);
+  if (in.W) sep_gather_top_kernel<T><<<148 * 8, 256, 0, st>>>(dS, t, (const T*)in.W, in.ldw);
+  else sep_fill_identity_kernel<T><<<148 * 8, 256, 0, st>>>(dS, p->spad, p->spad);
   sep_extract_kernel<T><<<dim3(32, p->nparts, 3), 256, 0, st>>>(M, t, Apr, Apad, dS, (uint16_t*)p->d_Apad16, p->d_flags);
   drs_count_launch(2);
   if (p->nsep > 0 && !in.W) {
@@ -635,7 +636,7 @@ int build_rows(drs_graph* g, int mode, T* local, int64_t ld, int row0, int nrows
 void free_plan(drs_sep_plan* p) {
   if (!p) return;
   free_plan(p->child);
-  if (p->d_tables) cudaFree(p->d_tables);
+  if (p->d_tables) drs_big_free(p->d_tables, p->tables_bytes);
   if (p->d_work) drs_big_free(p->d_work, p->work_bytes);
   delete p;
 }
@@ -730,11 +731,11 @@ int make_plan(int n, int npad, int m, const int32_t* src, const int32_t* dst, in
   const size_t o_tm = add(&top_moff, 8), o_tq = add(&top_qpad, 4);
   std::vector<unsigned char> img(off, 0);
   for (const Slice& x : sl) std::memcpy(img.data() + x.off, x.src, x.bytes);
-  drs_count_alloc();
-  if (cudaMalloc(&p->d_tables, img.size()) != cudaSuccess ||
+  p->tables_bytes = img.size();
+  if (drs_big_alloc(&p->d_tables, img.size()) ||
       cudaMemcpy(p->d_tables, img.data(), img.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
     cudaGetLastError();
-    if (p->d_tables) cudaFree(p->d_tables);
+    if (p->d_tables) drs_big_free(p->d_tables, p->tables_bytes);
     delete p;
     DRS_REQUIRE(false, DRS_ERR_CUDA, "drs_graph_set_partition: device tables (%zu bytes) could not be created", img.size());
   }

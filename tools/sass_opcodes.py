@@ -9,7 +9,9 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "drs_abm_b200", "libdrs_b200.so")
 out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
-FAMILIES = [("fw_", "Floyd-Warshall tiles (fw_kernels.cu)"), ("pred_kernel", "canonical predecessors"), ("sssp_batch", "SSSP, rows in L2 (default)"),
+FAMILIES = [("sep_expand16", "separator build, 16-bit output tiles (sep_apsp.cu)"), ("sep_expand", "separator build, 32-bit tiles: output + vertex->separator rows"),
+            ("sep_fw_", "separator build, batched part / separator closures"), ("sep_", "separator build, fills / gathers / spread"),
+            ("fw_", "Floyd-Warshall tiles (fw_kernels.cu)"), ("pred_kernel", "canonical predecessors"), ("sssp_batch", "SSSP, rows in L2 (default)"),
             ("sssp_smem", "SSSP, alternative kernels (row in shared memory / lane per arc)"), ("insertion_reach", "insertion reach test (bulk-copy staged)"),
             ("insertion_eval", "insertion pair evaluation"), ("insertion_fold", "insertion fold"), ("insertion_queue", "insertion sequential queue"),
             ("insertion_commit", "insertion commit"), ("plan_prep", "insertion plan prep"), ("rv_filter", "RV filter"), ("rv_eval", "RV evaluation"),
@@ -43,5 +45,6 @@ for key, title in FAMILIES:
     print("| %s | %d | %s |" % (title, total[key], " | ".join(cells)))
 print("\nBulk-copy engine: `UBLKCP.S.G` = `cp.async.bulk.shared::cluster.global` (the insertion reach test stages a matrix row per request),")
 print("`UBLKPF.L2` = `cp.async.bulk.prefetch.L2`, `SYNCS.*` = mbarrier arrive / try_wait.  `LDG.E.ENL2.256` = 256-bit global load (SSSP adjacency")
-print("records).  `FADD2` / `FMNMX3` / `VIADDMNMX` = packed fp32x2 add, 3-input min, DPX add+min (Floyd-Warshall tiles).  No `UTC*MMA` / `HMMA`:")
+print("records).  `FADD2` / `FMNMX3` / `VIADDMNMX` = packed fp32x2 add, 3-input min, DPX add+min (Floyd-Warshall and separator-build tiles;")
+print("`VIADDMNMX.U16x2`, two 16-bit relaxations per lane, in the 16-bit output tiles: %d static instances).  No `UTC*MMA` / `HMMA`:" % sum(v for k, v in hist["sep_expand16"].items() if k.startswith("VIADDMNMX.U16x2")))
 print("min-plus is not a GEMM.")
