@@ -106,6 +106,7 @@ int drs_graph_upload_weights(drs_graph* g);
 int drs_big_alloc(void** out, size_t bytes);
 void drs_big_free(void* p, size_t bytes);
 void drs_sep_free(drs_graph* g);
+bool drs_sep_allowed(const drs_graph* g);  // partition present and the travel times are ones the build accepts
 bool drs_sep_usable(const drs_graph* g);   // partition present, exact arithmetic, separators a small part of the map
 // DRS_MODE_F32 / DRS_MODE_I32 known, and I32 only on integer travel times below 1e6 (a float weight would be truncated)
 int drs_check_mode(const drs_graph* g, int mode, const char* who);

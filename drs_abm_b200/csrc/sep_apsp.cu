@@ -761,9 +761,18 @@ void drs_sep_free(drs_graph* g) {
   g->sep = nullptr;
 }
 
+static bool sep_float_ok() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DRS_SEP_FLOAT"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
+bool drs_sep_allowed(const drs_graph* g) { return g->sep && (g->weights_integral || sep_float_ok()); }
+
 bool drs_sep_usable(const drs_graph* g) {
   // exact arithmetic (any association of the sums gives the same bits) and separators that are a small part of the map
-  return g->sep && g->weights_integral && (int64_t)g->sep->nsep * 3 <= g->n && (int64_t)g->sep->ktot * 2 <= g->npad + 256;
+  return g->sep && (g->weights_integral || sep_float_ok()) && (int64_t)g->sep->nsep * 3 <= g->n &&
+         (int64_t)g->sep->ktot * 2 <= g->npad + 256;
 }
 
 extern "C" int drs_graph_set_partition(drs_graph* g, int32_t nparts, const int32_t* part_ptr, int32_t n_sep_parts,
@@ -879,7 +888,7 @@ extern "C" int drs_apsp_rows_sep(const drs_graph* gc, int32_t mode, void* local_
   drs_graph* g = const_cast<drs_graph*>(gc);
   { int rcm = drs_check_mode(g, mode, "drs_apsp_rows_sep"); if (rcm) return rcm; }
   DRS_REQUIRE(g->sep, DRS_ERR_STATE, "drs_apsp_rows_sep: the graph has no partition (drs_graph_set_partition)");
-  DRS_REQUIRE(g->weights_integral, DRS_ERR_ARG,
+  DRS_REQUIRE(g->weights_integral || sep_float_ok(), DRS_ERR_ARG,
               "drs_apsp_rows_sep: needs integer travel times below 1e6 (the build re-associates sums; use the SSSP builder)");
   DRS_REQUIRE(ld == g->npad && row0 >= 0 && nrows >= 0 && row0 + nrows <= g->npad && row0 % TILE == 0 && nrows % TILE == 0,
               DRS_ERR_ARG, "drs_apsp_rows_sep: bad shard (ld=%lld row0=%d nrows=%d npad=%d; rows in multiples of %d)", (long long)ld,
