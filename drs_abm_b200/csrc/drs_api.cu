@@ -379,7 +379,7 @@ extern "C" int drs_apsp_build(drs_graph* g, int32_t mode) {
     algo = drs_sep_usable(g) ? DRS_APSP_SEP : (g->narcs <= 16 * (int64_t)g->n) ? DRS_APSP_SSSP : DRS_APSP_FW;
   if (algo == DRS_APSP_SEP)
     DRS_REQUIRE(g->sep && drs_sep_allowed(g), DRS_ERR_STATE,
-                "drs_apsp_build: DRS_APSP_SEP needs a partition (drs_graph_set_partition) and integer travel times below 1e6");
+                "drs_apsp_build: DRS_APSP_SEP needs a partition (drs_graph_set_partition); with DRS_SEP_FLOAT=0 also integer travel times");
   // events: [0] start, [1] after init, then per round (after pivot row, after update), last after pred;
   // the SSSP build is one "round" booked under "update"
   const int ner = (algo == DRS_APSP_SSSP || algo == DRS_APSP_SEP) ? 1 : nb;

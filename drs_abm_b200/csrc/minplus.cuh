@@ -144,24 +144,31 @@ template <typename T> __device__ __forceinline__ void acc_store(const T (&acc)[8
 // The transposed tile: element (row, col) of the accumulators goes to Ct[col * ldc + row] for col in [col_lo, col_hi) and
 // row < rows, staged through shared memory (TILE x (TILE + 1) elements of smem_raw, free once tile_accumulate has
 // returned) so that the global stores run along rows of Ct.
-constexpr int TPITCH = TILE + 1;
+constexpr int TPITCH = TILE + 4;   // staged rows stay 16-byte aligned
+// staged row v is rotated by 4 tx(v) elements (tx = the lane that owns column v): the lanes of a staging store spread over
+// the banks, and a row segment of four stays one aligned 128-bit shared load
+template <typename T> __device__ __forceinline__ int stage_rot(int v) { return Semiring<T>::packed ? 4 * ((v >> 1) & 15) : 4 * ((v >> 2) & 15); }
 template <typename T> __device__ __forceinline__ void acc_store_transposed(const T (&acc)[8][8], unsigned char* smem_raw, T* Ct, int64_t ldc,
                                                                           int col_lo, int col_hi, int rows, int tid) {
+  using V4 = typename Vec4<T>::type;
   T* s = reinterpret_cast<T*>(smem_raw);
   const int tx = tid & 15, ty = tid >> 4;
 #pragma unroll
   for (int r = 0; r < 8; ++r)
 #pragma unroll
-    for (int c = 0; c < 8; ++c) s[acc_col<T>(c, tx) * TPITCH + acc_row<T>(r, ty)] = acc[r][c];
+    for (int c = 0; c < 8; ++c) s[acc_col<T>(c, tx) * TPITCH + ((acc_row<T>(r, ty) + 4 * tx) & (TILE - 1))] = acc[r][c];
   __syncthreads();
   const int warp = tid >> 5, lane = tid & 31;
   for (int v = warp; v < TILE; v += NTHREADS / 32) {
     if (v < col_lo || v >= col_hi) continue;
     T* crow = Ct + (int64_t)v * ldc;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int u = lane + 32 * q;
-      if (u < rows) crow[u] = s[v * TPITCH + u];
+    const int u = lane * 4;
+    const V4 q4 = *reinterpret_cast<const V4*>(s + v * TPITCH + ((u + stage_rot<T>(v)) & (TILE - 1)));
+    if (u + 3 < rows) *reinterpret_cast<V4*>(crow + u) = q4;     // one 512-byte row segment per warp instruction
+    else {
+      if (u < rows) crow[u] = q4.x;
+      if (u + 1 < rows) crow[u + 1] = q4.y;
+      if (u + 2 < rows) crow[u + 2] = q4.z;
     }
   }
 }
@@ -393,16 +400,18 @@ __device__ __forceinline__ void tile_accumulate_u16(uint32_t (&acc2)[8][4], cons
     }
   };
 
+  // both stages are free at entry: the first two chunks are requested at once (a tile has two or three chunks, and the
+  // latency of its first loads is what its CTA waits for)
   load_chunk(0, 0);
+  cp_async_commit();
+  if (nchunk > 1) load_chunk(1, 1);
   cp_async_commit();
 
 #pragma unroll 1
   for (int kc = 0; kc < nchunk; ++kc) {
     const int stage = kc % STAGES16;
-    cp_async_wait<STAGES16 - 2>();
+    cp_async_wait<1>();            // everything but the most recent group: chunk kc has landed
     __syncthreads();
-    if (kc + STAGES16 - 1 < nchunk) load_chunk(kc + STAGES16 - 1, (kc + STAGES16 - 1) % STAGES16);
-    cp_async_commit();
     const bool full = !(half_tail && kc == nchunk - 1);
 #pragma unroll
     for (int kk = 0; kk < KC; kk += 2) {
@@ -419,6 +428,11 @@ __device__ __forceinline__ void tile_accumulate_u16(uint32_t (&acc2)[8][4], cons
         for (int p = 0; p < 4; ++p)
           acc2[r][p] = __viaddmin_u16x2(a[r].y, bb1[p], __viaddmin_u16x2(a[r].x, bb0[p], acc2[r][p]));
     }
+    if (kc + STAGES16 < nchunk) {  // a third or later chunk reuses this stage once every thread is done reading it
+      __syncthreads();
+      load_chunk(kc + STAGES16, stage);
+    }
+    cp_async_commit();
   }
   cp_async_wait<0>();
   __syncthreads();

@@ -618,7 +618,7 @@ int build_rows(drs_graph* g, int mode, T* local, int64_t ld, int row0, int nrows
   for (auto& e : ev) DRS_CUDA(cudaEventCreate(&e));
   LevelInput in;
   in.out_ptr = g->d_out_ptr; in.out_col = g->d_out_col; in.out_w = g->d_out_w;
-  rc = run_level<T>(p, in, mode, g->directed != 0, local, ld, row0, nrows, st, ev, true);
+  rc = run_level<T>(p, in, mode, g->directed != 0, local, ld, row0, nrows, st, ev, /*allow16=*/g->weights_integral);
   if (!rc && cudaStreamSynchronize(st) != cudaSuccess) {
     drs_set_error("separator build: %s", cudaGetErrorString(cudaGetLastError()));
     rc = DRS_ERR_CUDA;
@@ -761,9 +761,12 @@ void drs_sep_free(drs_graph* g) {
   g->sep = nullptr;
 }
 
+// Non-integer travel times: the build re-associates the fp32 sums, so its matrix differs from the SSSP / FW one in the last
+// bits (relative 1e-7; the drop-in's tolerance on float maps is 1e-5 and its answers are fp64 sums along the path the matrix
+// selects).  On by default; DRS_SEP_FLOAT=0 keeps float maps on the SSSP builder.
 static bool sep_float_ok() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("DRS_SEP_FLOAT"); v = (e && e[0] == '1') ? 1 : 0; }
+  if (v < 0) { const char* e = getenv("DRS_SEP_FLOAT"); v = (e && e[0] == '0') ? 0 : 1; }
   return v == 1;
 }
 
@@ -889,7 +892,7 @@ extern "C" int drs_apsp_rows_sep(const drs_graph* gc, int32_t mode, void* local_
   { int rcm = drs_check_mode(g, mode, "drs_apsp_rows_sep"); if (rcm) return rcm; }
   DRS_REQUIRE(g->sep, DRS_ERR_STATE, "drs_apsp_rows_sep: the graph has no partition (drs_graph_set_partition)");
   DRS_REQUIRE(g->weights_integral || sep_float_ok(), DRS_ERR_ARG,
-              "drs_apsp_rows_sep: needs integer travel times below 1e6 (the build re-associates sums; use the SSSP builder)");
+              "drs_apsp_rows_sep: non-integer travel times and DRS_SEP_FLOAT=0 (the build re-associates sums; use the SSSP builder)");
   DRS_REQUIRE(ld == g->npad && row0 >= 0 && nrows >= 0 && row0 + nrows <= g->npad && row0 % TILE == 0 && nrows % TILE == 0,
               DRS_ERR_ARG, "drs_apsp_rows_sep: bad shard (ld=%lld row0=%d nrows=%d npad=%d; rows in multiples of %d)", (long long)ld,
               row0, nrows, g->npad, TILE);

@@ -202,6 +202,10 @@ def locality_order(n, src, dst, lng=None, lat=None, native=False):
 SECOND_LEVEL_MIN_SEPARATORS = int(os.environ.get("DRS_SEP_LEVEL2_MIN", 1024))
 
 
+# largest all-pairs matrix the bindings plan for (bytes): beyond it a map gets the plain locality numbering
+MATRIX_BYTES_LIMIT = 120e9
+
+
 def default_part_target(n):
     """Vertices per part of the separator partition: the expansion stage costs n^2 x (separators around a part, which
     grow like the square root of the part) and the separator closure (number of separators)^3, which shrinks with
@@ -246,7 +250,7 @@ class RoadGraph(object):
     ``ttmedian`` after load).
     """
 
-    def __init__(self, data, mode=_lib.MODE_F32, algorithm=_lib.APSP_AUTO, pred=_lib.PRED_LAZY, numbering="partition",
+    def __init__(self, data, mode=_lib.MODE_F32, algorithm=_lib.APSP_AUTO, pred=_lib.PRED_LAZY, numbering="auto",
                  part_target=None, second_level_min=None):
         if not isinstance(data, RoadGraphData):
             raise TypeError("RoadGraph needs RoadGraphData (use RoadGraph.Read_GML)")
@@ -271,8 +275,13 @@ class RoadGraph(object):
         # interiors of the parts first, the separators last; parts follow the bisection tree, so it is a locality
         # numbering too, and it is what the separator-partitioned build (APSP_SEP) works on.  "locality" = the plain
         # space-filling curve of round 1.
-        if numbering not in ("partition", "locality", "input"):
-            raise ValueError("numbering must be 'partition', 'locality' or 'input'")
+        # "auto": "partition" when an all-pairs matrix of this map fits a GPU (the partition exists for the matrix build), else
+        # "locality" (maps served by SSSP rows on demand, BASELINE config C5).
+        if numbering not in ("auto", "partition", "locality", "input"):
+            raise ValueError("numbering must be 'auto', 'partition', 'locality' or 'input'")
+        if numbering == "auto":
+            npad = (data.n + 127) // 128 * 128
+            numbering = "partition" if 4.0 * npad * npad <= MATRIX_BYTES_LIMIT else "locality"
         self.numbering = numbering
         self.part_target = int(os.environ.get("DRS_SEP_TARGET", part_target or 0)) or None
         self._part_ptr = self._sep_part_ptr = None

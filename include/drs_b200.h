@@ -118,9 +118,10 @@ int drs_apsp_rows_to_host(const drs_graph* g, int32_t row0, int32_t nrows, doubl
  * same matrix bit for bit on integer weights.  SEP: the blocked Floyd-Warshall in nested-dissection
  * order over a vertex-separator partition of the map (drs_graph_set_partition): about N^2 * |S_j|
  * relaxations, |S_j| = separators around a part, ALU bound, the matrix written once; it re-associates the
- * sums, so it is offered on integer travel times only, where it gives the same matrix bit for bit.
- * AUTO picks SEP when the graph has a partition with small separators and integer travel times, else
- * SSSP when arcs/vertex <= 16, else FW. */
+ * sums: the same matrix bit for bit on integer travel times, last-bit differences on float ones (within the
+ * 1e-5 float maps are held to; DRS_SEP_FLOAT=0 in the environment keeps float maps off it).
+ * AUTO picks SEP when the graph has a partition with small separators, else SSSP when arcs/vertex <= 16,
+ * else FW. */
 #define DRS_APSP_FW 0
 #define DRS_APSP_SSSP 1
 #define DRS_APSP_AUTO 2
