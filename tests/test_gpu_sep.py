@@ -200,3 +200,27 @@ def test_partition_is_validated_and_follows_weight_updates():
     d2 = RoadGraphData(data.n, data.directed, data.src, data.dst, data.vattrs, dict(data.eattrs, ttmedian=tt))
     assert np.array_equal(second, oracle_graph_from_data(d2).dist_matrix()) and not np.array_equal(first, second)
     G.close()
+
+
+def test_graph_without_small_separators_falls_back_and_explicit_sep_stays_exact():
+    """A random graph of average degree 16 has no small separators: the cover takes most of the vertices.  AUTO then leaves the
+    separator build alone (drs_sep_info: usable = 0) and uses another builder; forcing APSP_SEP is still exact -- the
+    construction does not depend on the separators being few, only its speed does."""
+    from drs_abm_b200 import _lib
+    from drs_abm_b200.routing import RoadGraph
+    rs = np.random.RandomState(11)
+    n, m = 500, 4000
+    src, dst = rs.randint(0, n, m), rs.randint(0, n, m)
+    keep = src != dst
+    data = _data(n, src[keep], dst[keep], rs.randint(1, 50, size=int(keep.sum())).astype(np.float64))
+    want = oracle_graph_from_data(data).dist_matrix()
+    G = RoadGraph(data, part_target=64)
+    G.build()
+    info = [C.c_int32(0) for _ in range(5)]
+    _lib.check(G._lib.drs_sep_info(G._handle, *[C.byref(x) for x in info]), G._lib)
+    assert info[1].value * 3 > n and info[4].value == 0           # separators are most of the graph: not usable
+    assert np.array_equal(G.dist_rows(0, n), want)
+    G.close()
+    G = RoadGraph(data, algorithm=_lib.APSP_SEP, part_target=64, second_level_min=1)
+    assert np.array_equal(G.dist_rows(0, n), want)
+    G.close()
