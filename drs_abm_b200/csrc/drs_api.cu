@@ -42,7 +42,7 @@ struct PinnedBlock { void* host; void* dev_alias; size_t bytes; int dev; };
 std::mutex g_pool_mu;
 std::vector<BigBlock> g_pool;
 std::vector<PinnedBlock> g_pinned;
-constexpr size_t kPoolMin = (size_t)16 << 10;
+constexpr size_t kPoolMin = 256;
 constexpr size_t kPoolSlots = 24;
 }  // namespace
 
@@ -82,7 +82,16 @@ void drs_big_free(void* p, size_t bytes) {
   cudaGetDevice(&dev);
   if (bytes >= kPoolMin) {
     std::lock_guard<std::mutex> lk(g_pool_mu);
-    if (g_pool.size() < kPoolSlots) { g_pool.push_back({p, bytes, dev}); return; }
+    void* evicted = nullptr;
+    if (g_pool.size() >= kPoolSlots) {      // full: the block that has waited longest goes back to the driver
+      evicted = g_pool.front().p;
+      if (g_pool.front().dev != dev) cudaSetDevice(g_pool.front().dev);
+      cudaFree(evicted);
+      if (g_pool.front().dev != dev) cudaSetDevice(dev);
+      g_pool.erase(g_pool.begin());
+    }
+    g_pool.push_back({p, bytes, dev});
+    return;
   }
   cudaFree(p);
 }

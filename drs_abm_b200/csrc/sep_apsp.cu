@@ -50,7 +50,9 @@ struct drs_sep_plan {
   const int32_t* d_top_qpad = nullptr;   // the separator graph's matrix as a one-part table for the batched FW kernels
   void *d_M = nullptr, *d_dS = nullptr, *d_Dall = nullptr, *d_dSr = nullptr, *d_Duni = nullptr, *d_Aprime = nullptr, *d_Apad = nullptr;
   void* d_Apad16 = nullptr;      // the A_j panels as 16-bit distances (the B operand of the 16-bit output tiles)
-  int32_t* d_flags = nullptr;    // [0] largest finite vertex->separator distance, [1] largest finite A_j / same-part entry (float bits)
+  void* d_Aprime16 = nullptr;    // A' with the 16-bit distance in both halves of a word (A operand of the 16-bit rows stage)
+  void* d_dSr16 = nullptr;       // the gathered separator rows as 16-bit distances (its B operand)
+  int32_t* d_flags = nullptr;    // [0] largest finite separator-to-separator distance, [1] largest finite distance inside a closed part (float bits)
   bool used16 = false;           // the last build ran its output tiles on the 16-bit path
   bool no16 = false;             // DRS_SEP_NO_U16=1 (measurement knob)
   double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -172,7 +174,7 @@ __device__ __forceinline__ void flag_max(int32_t* flag, int key) {
 
 template <typename T>
 __global__ void sep_extract_kernel(const T* __restrict__ M, SepTab t, T* __restrict__ Aprime, T* __restrict__ Apad, T* dS,
-                                   uint16_t* __restrict__ Apad16, int32_t* flags) {
+                                   uint16_t* __restrict__ Apad16, uint32_t* __restrict__ Aprime16, int32_t* flags) {
   const int j = blockIdx.y;
   const int ps = t.pstart[j], nj = t.pend[j] - ps, sj = t.sj[j], kp = t.kpad[j];
   const int64_t ld = t.qpad[j];
@@ -180,10 +182,15 @@ __global__ void sep_extract_kernel(const T* __restrict__ M, SepTab t, T* __restr
   const unsigned g0 = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x;   // every extent here is far below 2^31
   if (blockIdx.z == 0) {
     const unsigned total = (unsigned)nj * t.kmax, kmax = t.kmax;
+    int key = 0;
     for (unsigned idx = g0; idx < total; idx += gs) {
       const int li = (int)(idx / kmax), k = (int)(idx - (unsigned)li * kmax);
-      Aprime[(int64_t)(ps + li) * t.kmax + k] = k < sj ? Mj[(int64_t)li * ld + nj + k] : Semiring<T>::inf();
+      const T v = k < sj ? Mj[(int64_t)li * ld + nj + k] : Semiring<T>::inf();
+      Aprime[(int64_t)(ps + li) * t.kmax + k] = v;
+      Aprime16[(int64_t)(ps + li) * t.kmax + k] = dist_to_u16((float)v) * 0x10001u;
+      key = max(key, finite_bits<T>(v));
     }
+    flag_max(flags + 1, key);
   } else if (blockIdx.z == 1) {
     const int wp = t.wpad[j], cb = t.cbase[j];
     T* Aj = Apad + t.apoff[j];
@@ -239,7 +246,8 @@ __global__ void sep_arcs_kernel(T* dS, SepTab t, const int32_t* __restrict__ out
 // S2x: the rows of dS in the order of the concatenated separator lists (the B operand of S3), and the separator rows of
 // D_uni (a separator's distances to the separators are its dS row); padding rows = +inf
 template <typename T>
-__global__ void sep_gather_dsr_kernel(const T* __restrict__ dS, SepTab t, T* __restrict__ dSr, T* __restrict__ Duni, int32_t* flags) {
+__global__ void sep_gather_dsr_kernel(const T* __restrict__ dS, SepTab t, T* __restrict__ dSr, T* __restrict__ Duni,
+                                      uint16_t* __restrict__ dSr16, int32_t* flags) {
   const int rows1 = t.ktot, rows2 = t.npad - t.sep0;
   int key = 0;
   for (int row = blockIdx.x; row < rows1 + rows2; row += gridDim.x) {
@@ -247,7 +255,12 @@ __global__ void sep_gather_dsr_kernel(const T* __restrict__ dS, SepTab t, T* __r
       const int s = t.sall[row];
       const T* src = dS + (int64_t)max(s, 0) * t.spad;
       T* dst = dSr + (int64_t)row * t.spad;
-      for (int c = threadIdx.x; c < t.spad; c += blockDim.x) dst[c] = s >= 0 ? src[c] : Semiring<T>::inf();
+      uint16_t* dst16 = dSr16 + (int64_t)row * t.spad;
+      for (int c = threadIdx.x; c < t.spad; c += blockDim.x) {
+        const T v = s >= 0 ? src[c] : Semiring<T>::inf();
+        dst[c] = v;
+        dst16[c] = (uint16_t)dist_to_u16((float)v);
+      }
     } else {
       const int r = row - rows1;
       const T* src = dS + (int64_t)min(r, t.spad - 1) * t.spad;
@@ -268,7 +281,7 @@ __global__ void sep_gather_dsr_kernel(const T* __restrict__ dS, SepTab t, T* __r
 // rows and not stored.
 template <typename T>
 __global__ void __launch_bounds__(NTHREADS, 2) sep_expand_rows_kernel(const T* __restrict__ Aprime, const T* __restrict__ dSr,
-                                                                        T* __restrict__ Duni, SepTab t, int row_lo, int row_hi, int32_t* flags) {
+                                                                        T* __restrict__ Duni, SepTab t, int row_lo, int row_hi) {
   const int i = blockIdx.z;
   const int row0 = t.pstart[i] + blockIdx.y * TILE, pe = t.pend[i];
   if (row0 >= pe || row0 >= row_hi || min(row0 + TILE, pe) <= row_lo) return;
@@ -279,14 +292,24 @@ __global__ void __launch_bounds__(NTHREADS, 2) sep_expand_rows_kernel(const T* _
   tile_accumulate<T>(acc, Aprime + (int64_t)row0 * t.kmax, t.kmax, dSr + (int64_t)t.koff[i] * t.spad + (int64_t)blockIdx.x * TILE,
                      t.spad, t.kpad[i], smem_raw, tid);
   acc_store<T>(acc, Duni + (int64_t)row0 * t.spad + (int64_t)blockIdx.x * TILE, t.spad, pe - row0, TILE, tid);
-  int key = 0;
+}
+
+// the same tiles on the 16-bit path (fp32 D_uni out)
+__global__ void __launch_bounds__(NTHREADS, 3) sep_expand_rows16_kernel(const uint32_t* __restrict__ Aprime16, const uint16_t* __restrict__ dSr16,
+                                                                          float* __restrict__ Duni, SepTab t, int row_lo, int row_hi) {
+  const int i = blockIdx.z;
+  const int row0 = t.pstart[i] + blockIdx.y * TILE, pe = t.pend[i];
+  if (row0 >= pe || row0 >= row_hi || min(row0 + TILE, pe) <= row_lo) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x;
+  uint32_t acc2[8][4];
 #pragma unroll
   for (int r = 0; r < 8; ++r)
-    if (acc_row<T>(r, tid >> 4) < pe - row0) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) key = max(key, finite_bits<T>(acc[r][c]));
-    }
-  flag_max(flags, key);
+    for (int p = 0; p < 4; ++p) acc2[r][p] = U16_INF * 0x10001u;
+  tile_accumulate_u16(acc2, Aprime16 + (int64_t)row0 * t.kmax, t.kmax, dSr16 + (int64_t)t.koff[i] * t.spad + (int64_t)blockIdx.x * TILE,
+                      t.spad, t.kpad[i], smem_raw, tid);
+  acc16_store(acc2, Duni + (int64_t)row0 * t.spad + (int64_t)blockIdx.x * TILE, t.spad, pe - row0, TILE, tid, 0);
 }
 
 // S3x: SPREAD_ROWS rows of the shard per CTA: the rows of D_uni spread over the per-part k ranges (D_all, the A operand
@@ -455,6 +478,7 @@ int configure_kernels() {
   DRS_CUDA(cudaFuncSetAttribute(sep_expand_rows_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
   DRS_CUDA(cudaFuncSetAttribute(sep_expand_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
   DRS_CUDA(cudaFuncSetAttribute(sep_expand_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
+  DRS_CUDA(cudaFuncSetAttribute(sep_expand_rows16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTile16SmemBytes));
   DRS_CUDA(cudaFuncSetAttribute(sep_expand16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTile16SmemBytes));
   DRS_CUDA(cudaFuncSetAttribute(sep_expand16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTile16SmemBytes));
   if (dev >= 0 && dev < 64) configured[dev] = true;
@@ -468,7 +492,8 @@ int ensure_work(drs_sep_plan* p, cudaStream_t st) {
   const size_t b_Duni = al(4 * (size_t)p->npad * p->spad);
   const size_t b_Apr = al(4 * (size_t)(p->npad + TILE) * p->kmax), b_Apad = al(4 * (size_t)std::max<int64_t>(p->ap_elems, 1));
   const size_t b_Apad16 = al(2 * (size_t)std::max<int64_t>(p->ap_elems, 1)), b_flags = 256;
-  const size_t total = b_M + b_dS + b_Dall + b_dSr + b_Duni + b_Apr + b_Apad + b_Apad16 + b_flags;
+  const size_t b_dSr16 = al(2 * (size_t)p->ktot * p->spad);
+  const size_t total = b_M + b_dS + b_Dall + b_dSr + b_Duni + 2 * b_Apr + b_Apad + b_Apad16 + b_dSr16 + b_flags;
   const bool fresh = !p->d_work || p->work_bytes < total;
   if (fresh) {
     if (p->d_work) drs_big_free(p->d_work, p->work_bytes);
@@ -478,10 +503,11 @@ int ensure_work(drs_sep_plan* p, cudaStream_t st) {
   }
   char* b = (char*)p->d_work;
   p->d_M = b; b += b_M; p->d_dS = b; b += b_dS; p->d_Dall = b; b += b_Dall; p->d_dSr = b; b += b_dSr; p->d_Duni = b; b += b_Duni;
-  p->d_Aprime = b; b += b_Apr; p->d_Apad = b; b += b_Apad; p->d_Apad16 = b; b += b_Apad16; p->d_flags = (int32_t*)b;
+  p->d_Aprime = b; b += b_Apr; p->d_Aprime16 = b; b += b_Apr; p->d_Apad = b; b += b_Apad; p->d_Apad16 = b; b += b_Apad16;
+  p->d_dSr16 = b; b += b_dSr16; p->d_flags = (int32_t*)b;
   // rows of A' past the last interior vertex are read by the last row tile of a part; what is computed from them is never
   // stored, but they should hold numbers that stay numbers
-  if (fresh) DRS_CUDA(cudaMemsetAsync(p->d_Aprime, 0x7f, b_Apr, st));
+  if (fresh) DRS_CUDA(cudaMemsetAsync(p->d_Aprime, 0x7f, 2 * b_Apr, st));   // A' and its 16-bit twin are adjacent
   return DRS_OK;
 }
 
@@ -532,7 +558,7 @@ int run_level(drs_sep_plan* p, const LevelInput& in, int mode, bool directed, T*
   // S1x: the separator graph's matrix, A' and the padded A_j panels
   if (in.W) sep_gather_top_kernel<T><<<148 * 8, 256, 0, st>>>(dS, t, (const T*)in.W, in.ldw);
   else sep_fill_identity_kernel<T><<<148 * 8, 256, 0, st>>>(dS, p->spad, p->spad);
-  sep_extract_kernel<T><<<dim3(32, p->nparts, 3), 256, 0, st>>>(M, t, Apr, Apad, dS, (uint16_t*)p->d_Apad16, p->d_flags);
+  sep_extract_kernel<T><<<dim3(32, p->nparts, 3), 256, 0, st>>>(M, t, Apr, Apad, dS, (uint16_t*)p->d_Apad16, (uint32_t*)p->d_Aprime16, p->d_flags);
   drs_count_launch(2);
   if (p->nsep > 0 && !in.W) {
     sep_arcs_kernel<T><<<(p->nsep + 127) / 128, 128, 0, st>>>(dS, t, in.out_ptr, in.out_col, in.out_w);
@@ -564,24 +590,29 @@ int run_level(drs_sep_plan* p, const LevelInput& in, int mode, bool directed, T*
   }
   SEP_EVENT(4);
   // S2x
-  sep_gather_dsr_kernel<T><<<148 * 8, 256, 0, st>>>(dS, t, dSr, Duni, p->d_flags);
+  sep_gather_dsr_kernel<T><<<148 * 8, 256, 0, st>>>(dS, t, dSr, Duni, (uint16_t*)p->d_dSr16, p->d_flags);
   drs_count_launch();
   SEP_CHECK();
   SEP_EVENT(5);
-  // S3 + S3x
-  sep_expand_rows_kernel<T><<<dim3(p->spad / TILE, p->max_rowtiles, p->nparts), NTHREADS, kTileSmemBytes, st>>>(Apr, dSr, Duni, t, row0,
-                                                                                                              row0 + nrows, p->d_flags);
-  drs_count_launch();
-  SEP_CHECK();
-  // 16-bit output tiles when every candidate sum stays below 2^15: (largest vertex->separator distance of this shard and
-  // of the separators) + (largest distance inside a closed part) bounds them all.  One 8-byte read-back decides.
+  // S3 + S3x.  16-bit tiles for both remaining stages when every candidate sum stays below 2^15: a vertex->separator
+  // distance is at most (largest distance inside a closed part) + (largest separator-to-separator distance), and an output
+  // candidate adds one more in-part distance.  One 8-byte read-back decides.
   bool use16 = false;
   if (allow16 && std::is_same<T, float>::value && !p->no16) {
     float h[2] = {0, 0};
     DRS_CUDA(cudaMemcpyAsync(h, p->d_flags, 8, cudaMemcpyDeviceToHost, st));
     DRS_CUDA(cudaStreamSynchronize(st));
-    use16 = h[0] + h[1] < (float)U16_INF;
+    use16 = h[0] + 2.0f * h[1] < (float)U16_INF;
   }
+  {
+    const dim3 grid(p->spad / TILE, p->max_rowtiles, p->nparts);
+    if (use16)
+      sep_expand_rows16_kernel<<<grid, NTHREADS, kTile16SmemBytes, st>>>((const uint32_t*)p->d_Aprime16, (const uint16_t*)p->d_dSr16,
+                                                                         (float*)Duni, t, row0, row0 + nrows);
+    else sep_expand_rows_kernel<T><<<grid, NTHREADS, kTileSmemBytes, st>>>(Apr, dSr, Duni, t, row0, row0 + nrows);
+  }
+  drs_count_launch();
+  SEP_CHECK();
   p->used16 = use16;
   if (use16) sep_spread_kernel<T, true><<<nrows / SPREAD_ROWS, 256, 0, st>>>(Duni, Dall, C, ldc, t, row0);
   else sep_spread_kernel<T, false><<<nrows / SPREAD_ROWS, 256, 0, st>>>(Duni, Dall, C, ldc, t, row0);

@@ -224,3 +224,30 @@ def test_graph_without_small_separators_falls_back_and_explicit_sep_stays_exact(
     G = RoadGraph(data, algorithm=_lib.APSP_SEP, part_target=64, second_level_min=1)
     assert np.array_equal(G.dist_rows(0, n), want)
     G.close()
+
+
+def test_a_second_graph_reuses_the_blocks_of_the_first():
+    """Device and pinned blocks of a closed graph go to a process-wide cache (drs_api.cu): a second graph of the same map builds
+    and answers queries without a single cudaMalloc / cudaHostAlloc (drs_alloc_count), and drs_pool_trim gives the blocks back."""
+    from drs_abm_b200 import _lib, synth
+    from drs_abm_b200.routing import RoadGraph
+    data = synth.config_graph("C2")
+    lib = _lib.load()
+    o, d = synth.random_od_pairs(data.n, 512, 5)
+    _lib.check(lib.drs_pool_trim(), lib)                          # whatever earlier tests left behind
+    G = RoadGraph(data)
+    first = G.path_sums(o, d)[0]
+    G.matrix_lookup(o, d)
+    G.close()
+    a0 = lib.drs_alloc_count()
+    G = RoadGraph(data)
+    second = G.path_sums(o, d)[0]
+    G.matrix_lookup(o, d)
+    G.close()
+    assert lib.drs_alloc_count() == a0, "a fresh graph of the same size allocated device or pinned memory"
+    assert np.array_equal(first, second)
+    _lib.check(lib.drs_pool_trim(), lib)
+    G = RoadGraph(data)
+    G.build()
+    assert lib.drs_alloc_count() > a0                              # after a trim the blocks come from the driver again
+    G.close()
