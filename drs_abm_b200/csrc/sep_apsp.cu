@@ -3,22 +3,26 @@
 //
 // Replaces, like the other builders, the per-query Dijkstra of the reference (lib/RoutingEngine.py:87,199,212;
 // lib/optimUtils.py:528,531,659) by one resident travel-time matrix; the matrix it writes is the one the SSSP and the plain
-// Floyd-Warshall builders write (bit-identical on exact-arithmetic maps, which is where the library selects it).
+// Floyd-Warshall builders write: bit-identical on integer travel times, last-bit differences on float ones (the sums are
+// re-associated; DESIGN.md, kernel K0).
 //
-// The vertices are numbered part-major (drs_partition_order): the interiors of the parts first, one contiguous id range
-// each, and the separator vertices S last.  No arc joins the interiors of two different parts.  With S_j = the separators
-// adjacent to part j and Q_j = P_j + S_j (the "closed part"):
+// The vertices are numbered part-major (drs_partition_order, at the end of this file): the interiors of the parts first,
+// one contiguous id range each, and the separator vertices S last.  No arc joins the interiors of two different parts.
+// With S_j = the separators adjacent to part j and Q_j = P_j + S_j (the "closed part"):
 //   S1  M_j = closure of the subgraph induced by Q_j             batched blocked FW, one small dense matrix per part
 //   S2  dS  = closure of the separator graph (arcs inside S and, per part, the S_j x S_j block of M_j): the true
-//             distances between separators                        blocked FW on |S| x |S| (fw_kernels.cu)
-//   S3  D[u, (j,k)] = min_{s in S_i} M_i[u, s] + dS[s, S_j[k]]   u in P_i: distance from every vertex to every part's
-//             separators, stored per part as a contiguous k range ("D_all", n x sum_j |S_j|)
-//   S4  C[u, v] = min( M_j[u, v] if u in P_j,  min_k D[u, (j,k)] + M_j[S_j[k], v] )     v in P_j: the output tiles,
-//             each a 128 x 128 x |S_j| min-plus product written exactly once
-//   S4x C[u, s] = D[u, (j,k)] for one (j,k) with S_j[k] = s      the separator columns are a gather
-// Every stage is the 128x128 register-tile product of minplus.cuh (FADD2 + FMNMX3 / VIADDMNMX): ALU-bound; the matrix
-// leaves the SMs once.  Work: n^2 * mean|S_j| relaxations for S4 against n^2 * (arcs/n) * (re-relaxation factor) dependent
-// L2 round trips for the SSSP builder.
+//             distances between separators                        this same build on the separator graph (second level:
+//                                                                 run_level recursion on a dense input), batched FW at the top
+//   S3  D_uni[u, s] = min_k M_i[u, S_i[k]] + dS[S_i[k], s]        u in P_i: every vertex to every separator; then spread
+//             into the per-part k ranges (D_all[u, (j,k)] = D_uni[u, S_j[k]], the A operand of S4) and into the
+//             separator columns of the output
+//   S4  C[u, v] = min( M_j[u, v] if u in P_j,  min_k D_all[u, (j,k)] + M_j[S_j[k], v] )     v in P_j: the output tiles,
+//             each a 128 x 128 x |S_j| min-plus product written exactly once; on undirected maps only the tiles on or
+//             above the diagonal, each also stored transposed
+// Every tile stage is the 128x128 register-tile product of minplus.cuh: FADD2 + FMNMX3 / VIADDMNMX on 32-bit elements,
+// VIADDMNMX.U16x2 (two relaxations per lane) for S3 and S4 when the map's distances stay below 2^15.  Work: n^2 * mean|S_j|
+// relaxations for S4 against n^3 for the plain FW and n^2 * (arcs/n) * (re-relaxation factor) dependent L2 round trips for
+// the SSSP builder; the matrix leaves the SMs once.
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -53,7 +57,7 @@ struct drs_sep_plan {
   void* d_Aprime16 = nullptr;    // A' with the 16-bit distance in both halves of a word (A operand of the 16-bit rows stage)
   void* d_dSr16 = nullptr;       // the gathered separator rows as 16-bit distances (its B operand)
   int32_t* d_flags = nullptr;    // [0] largest finite separator-to-separator distance, [1] largest finite distance inside a closed part (float bits)
-  bool used16 = false;           // the last build ran its output tiles on the 16-bit path
+  bool used16 = false;           // the last build ran S3 and S4 on the 16-bit path
   bool no16 = false;             // DRS_SEP_NO_U16=1 (measurement knob)
   double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   bool no_mirror = false;   // DRS_SEP_NO_MIRROR=1: compute every output tile (measurement knob)
