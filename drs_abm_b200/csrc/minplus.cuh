@@ -369,16 +369,24 @@ namespace mp {
 
 constexpr unsigned U16_INF = 0x7fffu;
 constexpr int BS16 = TILE / 2;   // 32-bit words per B row in shared memory
-constexpr int STAGES16 = 2;      // two chunks in flight: three CTAs of 256 threads fit an SM
-constexpr size_t kTile16RingBytes = sizeof(uint32_t) * STAGES16 * (TILE * APAD + KC * BS16);
-constexpr int TPITCH16 = TILE + 4;   // staged rows stay 16-byte aligned
-constexpr size_t kTile16StageBytes = sizeof(float) * TILE * TPITCH16;   // the transposed tile staged for the mirrored store
-constexpr size_t kTile16SmemBytes = kTile16RingBytes > kTile16StageBytes ? kTile16RingBytes : kTile16StageBytes;
+constexpr int STAGES16 = 2;      // two chunks in flight
+// ROWS = rows of the output tile (128, or 64: half-height tiles, twice as many and half as large CTAs per SM, which overlap
+// each other's load, compute and store phases more finely); a tile is computed by 2 ROWS threads; thread (tx = tid & 15,
+// ty = tid >> 4) owns rows ty + (ROWS / 8) r and the eight columns 8 tx ..
+template <int ROWS> struct Tile16 {
+  static constexpr int NT = 2 * ROWS, RG = ROWS / 8, PITCH = ROWS + 4;
+  static constexpr size_t ring_bytes = sizeof(uint32_t) * STAGES16 * (ROWS * APAD + KC * BS16);
+  static constexpr size_t stage_bytes = sizeof(float) * TILE * PITCH;   // the transposed tile staged for the mirrored store
+  static constexpr size_t smem_bytes = ring_bytes > stage_bytes ? ring_bytes : stage_bytes;
+};
+constexpr size_t kTile16SmemBytes = Tile16<TILE>::smem_bytes;
 
+template <int ROWS>
 __device__ __forceinline__ void tile_accumulate_u16(uint32_t (&acc2)[8][4], const uint32_t* __restrict__ A, int64_t lda,
                                                     const uint16_t* __restrict__ B, int64_t ldb, int kcols, unsigned char* smem_raw, int tid) {
-  uint32_t(*As)[TILE][APAD] = reinterpret_cast<uint32_t(*)[TILE][APAD]>(smem_raw);
-  uint32_t(*Bs)[KC][BS16] = reinterpret_cast<uint32_t(*)[KC][BS16]>(smem_raw + sizeof(uint32_t) * STAGES16 * TILE * APAD);
+  constexpr int NT = Tile16<ROWS>::NT, RG = Tile16<ROWS>::RG;
+  uint32_t(*As)[ROWS][APAD] = reinterpret_cast<uint32_t(*)[ROWS][APAD]>(smem_raw);
+  uint32_t(*Bs)[KC][BS16] = reinterpret_cast<uint32_t(*)[KC][BS16]>(smem_raw + sizeof(uint32_t) * STAGES16 * ROWS * APAD);
   const int tx = tid & 15, ty = tid >> 4;
   if (kcols <= 0) return;
   const int nchunk = (kcols + KC - 1) / KC;
@@ -387,14 +395,14 @@ __device__ __forceinline__ void tile_accumulate_u16(uint32_t (&acc2)[8][4], cons
   auto load_chunk = [&](int kc, int stage) {
     const int k0 = kc * KC;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {   // A chunk: 128 rows x 32 k words
-      const int v = tid + NTHREADS * q;
+    for (int q = 0; q < ROWS * 8 / NT; ++q) {   // A chunk: ROWS rows x 32 k words
+      const int v = tid + NT * q;
       const int row = v >> 3, cv = v & 7;
       cp_async16(&As[stage][row][cv * 4], A + (int64_t)row * lda + k0 + cv * 4);
     }
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {   // B chunk: 32 k x 128 columns of 16 bits = 16 x 16 bytes per row
-      const int v = tid + NTHREADS * q;
+    for (int q = 0; q < KC * 16 / NT; ++q) {    // B chunk: 32 k x 128 columns of 16 bits = 16 x 16 bytes per row
+      const int v = tid + NT * q;
       const int row = v >> 4, cv = v & 15;
       cp_async16(&Bs[stage][row][cv * 4], B + (int64_t)(k0 + row) * ldb + cv * 8);
     }
@@ -418,7 +426,7 @@ __device__ __forceinline__ void tile_accumulate_u16(uint32_t (&acc2)[8][4], cons
       if (kk == KC / 2 && !full) break;
       uint2 a[8];
 #pragma unroll
-      for (int r = 0; r < 8; ++r) a[r] = *reinterpret_cast<const uint2*>(&As[stage][ty + 16 * r][kk]);
+      for (int r = 0; r < 8; ++r) a[r] = *reinterpret_cast<const uint2*>(&As[stage][ty + RG * r][kk]);
       const uint4 b0 = *reinterpret_cast<const uint4*>(&Bs[stage][kk][tx * 4]);
       const uint4 b1 = *reinterpret_cast<const uint4*>(&Bs[stage][kk + 1][tx * 4]);
       const uint32_t bb0[4] = {b0.x, b0.y, b0.z, b0.w}, bb1[4] = {b1.x, b1.y, b1.z, b1.w};
@@ -441,14 +449,14 @@ __device__ __forceinline__ void tile_accumulate_u16(uint32_t (&acc2)[8][4], cons
 __device__ __forceinline__ float u16_to_dist(unsigned v) { return v >= U16_INF ? __int_as_float(0x7f800000) : (float)v; }
 __device__ __forceinline__ unsigned dist_to_u16(float d) { return d < (float)U16_INF ? (unsigned)d : U16_INF; }
 
-// packed accumulators as fp32 distances into the tile at C (rows ty + 16 r, columns 8 tx ..): rows >= rows and columns
-// outside [col_lo, cols) are not written
+// packed accumulators as fp32 distances into the tile at C: rows >= rows and columns outside [col_lo, cols) are not written
+template <int ROWS>
 __device__ __forceinline__ void acc16_store(const uint32_t (&acc2)[8][4], float* C, int64_t ldc, int rows, int cols, int tid, int col_lo) {
   const int tx = tid & 15, ty = tid >> 4;
-  const bool whole = rows >= TILE && cols >= TILE && col_lo <= 0;
+  const bool whole = rows >= ROWS && cols >= TILE && col_lo <= 0;
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
-    const int row = ty + 16 * r;
+    const int row = ty + Tile16<ROWS>::RG * r;
     float v[8];
 #pragma unroll
     for (int p = 0; p < 4; ++p) { v[2 * p] = u16_to_dist(acc2[r][p] & 0xffffu); v[2 * p + 1] = u16_to_dist(acc2[r][p] >> 16); }
@@ -466,29 +474,32 @@ __device__ __forceinline__ void acc16_store(const uint32_t (&acc2)[8][4], float*
   }
 }
 
-// the transposed tile as fp32 (see acc_store_transposed).  Staged row v is rotated by 4 (v / 8) elements: the 16 lanes of a
-// staging store then fall into 8 banks instead of 4, and a row segment of four is still one aligned 128-bit shared load
-// followed by one 128-bit global store (a warp writes a whole 512-byte row segment).
+// the transposed tile as fp32 (see acc_store_transposed).  Staged row v (a column of the tile, ROWS values) is rotated by
+// 4 (v / 8) elements: the 16 lanes of a staging store then fall into 8 banks instead of 4, and a row segment of four is
+// still one aligned 128-bit shared load followed by one 128-bit global store.
+template <int ROWS>
 __device__ __forceinline__ void acc16_store_transposed(const uint32_t (&acc2)[8][4], unsigned char* smem_raw, float* Ct, int64_t ldc,
                                                        int col_lo, int col_hi, int rows, int tid) {
+  constexpr int NT = Tile16<ROWS>::NT, RG = Tile16<ROWS>::RG, PITCH = Tile16<ROWS>::PITCH;
+  constexpr int LPR = ROWS / 4, RPW = 32 / LPR;   // lanes per staged row, staged rows per warp instruction
   float* s = reinterpret_cast<float*>(smem_raw);
   const int tx = tid & 15, ty = tid >> 4;
 #pragma unroll
   for (int r = 0; r < 8; ++r)
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
-      const int pos = (ty + 16 * r + 4 * tx) & (TILE - 1);
-      s[(tx * 8 + 2 * p) * TPITCH16 + pos] = u16_to_dist(acc2[r][p] & 0xffffu);
-      s[(tx * 8 + 2 * p + 1) * TPITCH16 + pos] = u16_to_dist(acc2[r][p] >> 16);
+      const int pos = (ty + RG * r + 4 * tx) & (ROWS - 1);
+      s[(tx * 8 + 2 * p) * PITCH + pos] = u16_to_dist(acc2[r][p] & 0xffffu);
+      s[(tx * 8 + 2 * p + 1) * PITCH + pos] = u16_to_dist(acc2[r][p] >> 16);
     }
   __syncthreads();
   const int warp = tid >> 5, lane = tid & 31;
-  for (int v = warp; v < TILE; v += NTHREADS / 32) {
+  for (int v = warp * RPW + lane / LPR; v < TILE; v += (NT / 32) * RPW) {
     if (v < col_lo || v >= col_hi) continue;
     float* crow = Ct + (int64_t)v * ldc;
-    const int u = lane * 4;
-    const float4 q4 = *reinterpret_cast<const float4*>(s + v * TPITCH16 + ((u + 4 * (v >> 3)) & (TILE - 1)));
-    if (u + 3 < rows) *reinterpret_cast<float4*>(crow + u) = q4;     // one 512-byte row segment per warp instruction
+    const int u = (lane % LPR) * 4;
+    const float4 q4 = *reinterpret_cast<const float4*>(s + v * PITCH + ((u + 4 * (v >> 3)) & (ROWS - 1)));
+    if (u + 3 < rows) *reinterpret_cast<float4*>(crow + u) = q4;
     else {
       if (u < rows) crow[u] = q4.x;
       if (u + 1 < rows) crow[u + 1] = q4.y;

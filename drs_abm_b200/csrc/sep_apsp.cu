@@ -59,6 +59,7 @@ struct drs_sep_plan {
   int32_t* d_flags = nullptr;    // [0] largest finite separator-to-separator distance, [1] largest finite distance inside a closed part (float bits)
   bool used16 = false;           // the last build ran S3 and S4 on the 16-bit path
   bool no16 = false;             // DRS_SEP_NO_U16=1 (measurement knob)
+  bool tile64 = false;           // DRS_SEP_TILE64: 16-bit output tiles of 64 rows
   double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   bool no_mirror = false;   // DRS_SEP_NO_MIRROR=1: compute every output tile (measurement knob)
   int n = 0, npad = 0;      // vertices of this level and their padded count (the leading dimension of its matrix)
@@ -311,9 +312,9 @@ __global__ void __launch_bounds__(NTHREADS, 3) sep_expand_rows16_kernel(const ui
   for (int r = 0; r < 8; ++r)
 #pragma unroll
     for (int p = 0; p < 4; ++p) acc2[r][p] = U16_INF * 0x10001u;
-  tile_accumulate_u16(acc2, Aprime16 + (int64_t)row0 * t.kmax, t.kmax, dSr16 + (int64_t)t.koff[i] * t.spad + (int64_t)blockIdx.x * TILE,
+  tile_accumulate_u16<TILE>(acc2, Aprime16 + (int64_t)row0 * t.kmax, t.kmax, dSr16 + (int64_t)t.koff[i] * t.spad + (int64_t)blockIdx.x * TILE,
                       t.spad, t.kpad[i], smem_raw, tid);
-  acc16_store(acc2, Duni + (int64_t)row0 * t.spad + (int64_t)blockIdx.x * TILE, t.spad, pe - row0, TILE, tid, 0);
+  acc16_store<TILE>(acc2, Duni + (int64_t)row0 * t.spad + (int64_t)blockIdx.x * TILE, t.spad, pe - row0, TILE, tid, 0);
 }
 
 // S3x: SPREAD_ROWS rows of the shard per CTA: the rows of D_uni spread over the per-part k ranges (D_all, the A operand
@@ -386,17 +387,19 @@ __global__ void __launch_bounds__(NTHREADS, 2) sep_expand_kernel(const T* __rest
     acc_store_transposed<T>(acc, smem_raw, C + (int64_t)C0 * ldc + R0, ldc, col_lo, col_hi, min(TILE, t.sep0 - R0), tid);
 }
 
-// S4 on the 16-bit path (fp32 matrices of maps whose distances stay below 2^15): same tiles, VIADDMNMX.U16x2 inside
-template <bool MIRROR>
-__global__ void __launch_bounds__(NTHREADS, 3) sep_expand16_kernel(const uint32_t* __restrict__ Dall2, const uint16_t* __restrict__ Apad16,
-                                                                     const float* __restrict__ M, float* __restrict__ C, int64_t ldc, SepTab t,
-                                                                     int row_lo) {
+// S4 on the 16-bit path (fp32 matrices of maps whose distances stay below 2^15): same tiles, VIADDMNMX.U16x2 inside.
+// ROWS = 128 (three CTAs of 256 threads per SM) or 64 (six CTAs of 128 threads: minplus.cuh, Tile16)
+template <bool MIRROR, int ROWS>
+__global__ void __launch_bounds__(2 * ROWS, ROWS == TILE ? 3 : 6)
+sep_expand16_kernel(const uint32_t* __restrict__ Dall2, const uint16_t* __restrict__ Apad16, const float* __restrict__ M,
+                    float* __restrict__ C, int64_t ldc, SepTab t, int row_lo) {
+  constexpr int RG = Tile16<ROWS>::RG;
   const int ct = blockIdx.x;
   const int j = t.ct_part[ct], C0 = t.ct_col0[ct];
-  const int R0 = row_lo + blockIdx.y * TILE;
+  const int R0 = row_lo + blockIdx.y * ROWS;
   const int ps = t.pstart[j], pe = t.pend[j];
   const int col_lo = max(ps - C0, 0), col_hi = min(pe - C0, TILE);
-  if (MIRROR && !(C0 + col_hi > R0 || R0 + TILE > t.sep0)) return;
+  if (MIRROR && !(C0 + col_hi > R0 || R0 + ROWS > t.sep0)) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
@@ -405,12 +408,12 @@ __global__ void __launch_bounds__(NTHREADS, 3) sep_expand16_kernel(const uint32_
   for (int r = 0; r < 8; ++r)
 #pragma unroll
     for (int p = 0; p < 4; ++p) acc2[r][p] = U16_INF * 0x10001u;
-  if (R0 < pe && R0 + TILE > ps) {
+  if (R0 < pe && R0 + ROWS > ps) {
     const int64_t ld = t.qpad[j];
     const float* Mj = M + t.moff[j];
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-      const int u = R0 + ty + 16 * r;
+      const int u = R0 + ty + RG * r;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const int v = C0 + tx * 8 + q;
@@ -421,11 +424,11 @@ __global__ void __launch_bounds__(NTHREADS, 3) sep_expand16_kernel(const uint32_
       }
     }
   }
-  tile_accumulate_u16(acc2, Dall2 + (int64_t)R0 * t.ktot + t.koff[j], t.ktot, Apad16 + t.apoff[j] + (C0 - t.cbase[j]), t.wpad[j],
-                      t.kpad[j], smem_raw, tid);
-  acc16_store(acc2, C + (int64_t)(R0 - row_lo) * ldc + C0, ldc, TILE, col_hi, tid, col_lo);
+  tile_accumulate_u16<ROWS>(acc2, Dall2 + (int64_t)R0 * t.ktot + t.koff[j], t.ktot, Apad16 + t.apoff[j] + (C0 - t.cbase[j]), t.wpad[j],
+                            t.kpad[j], smem_raw, tid);
+  acc16_store<ROWS>(acc2, C + (int64_t)(R0 - row_lo) * ldc + C0, ldc, ROWS, col_hi, tid, col_lo);
   if (MIRROR && R0 < t.sep0)
-    acc16_store_transposed(acc2, smem_raw, C + (int64_t)C0 * ldc + R0, ldc, col_lo, col_hi, min(TILE, t.sep0 - R0), tid);
+    acc16_store_transposed<ROWS>(acc2, smem_raw, C + (int64_t)C0 * ldc + R0, ldc, col_lo, col_hi, min(ROWS, t.sep0 - R0), tid);
 }
 
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -483,8 +486,10 @@ int configure_kernels() {
   DRS_CUDA(cudaFuncSetAttribute(sep_expand_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
   DRS_CUDA(cudaFuncSetAttribute(sep_expand_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
   DRS_CUDA(cudaFuncSetAttribute(sep_expand_rows16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTile16SmemBytes));
-  DRS_CUDA(cudaFuncSetAttribute(sep_expand16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTile16SmemBytes));
-  DRS_CUDA(cudaFuncSetAttribute(sep_expand16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTile16SmemBytes));
+  DRS_CUDA(cudaFuncSetAttribute(sep_expand16_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tile16<128>::smem_bytes));
+  DRS_CUDA(cudaFuncSetAttribute(sep_expand16_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tile16<128>::smem_bytes));
+  DRS_CUDA(cudaFuncSetAttribute(sep_expand16_kernel<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tile16<64>::smem_bytes));
+  DRS_CUDA(cudaFuncSetAttribute(sep_expand16_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tile16<64>::smem_bytes));
   if (dev >= 0 && dev < 64) configured[dev] = true;
   return DRS_OK;
 }
@@ -630,8 +635,14 @@ int run_level(drs_sep_plan* p, const LevelInput& in, int mode, bool directed, T*
     if (use16) {
       const uint32_t* D2 = (const uint32_t*)p->d_Dall;
       const uint16_t* A16 = (const uint16_t*)p->d_Apad16;
-      if (mirror) sep_expand16_kernel<true><<<grid, NTHREADS, kTile16SmemBytes, st>>>(D2, A16, (const float*)p->d_M, (float*)C, ldc, t, row0);
-      else sep_expand16_kernel<false><<<grid, NTHREADS, kTile16SmemBytes, st>>>(D2, A16, (const float*)p->d_M, (float*)C, ldc, t, row0);
+      const float* Mf = (const float*)p->d_M;
+      float* Cf = (float*)C;
+      if (p->tile64) {
+        const dim3 g64(p->ncoltiles, nrows / 64);
+        if (mirror) sep_expand16_kernel<true, 64><<<g64, 128, Tile16<64>::smem_bytes, st>>>(D2, A16, Mf, Cf, ldc, t, row0);
+        else sep_expand16_kernel<false, 64><<<g64, 128, Tile16<64>::smem_bytes, st>>>(D2, A16, Mf, Cf, ldc, t, row0);
+      } else if (mirror) sep_expand16_kernel<true, 128><<<grid, NTHREADS, Tile16<128>::smem_bytes, st>>>(D2, A16, Mf, Cf, ldc, t, row0);
+      else sep_expand16_kernel<false, 128><<<grid, NTHREADS, Tile16<128>::smem_bytes, st>>>(D2, A16, Mf, Cf, ldc, t, row0);
     } else if (mirror) sep_expand_kernel<T, true><<<grid, NTHREADS, kTileSmemBytes, st>>>(Dall, Apad, M, C, ldc, t, row0);
     else sep_expand_kernel<T, false><<<grid, NTHREADS, kTileSmemBytes, st>>>(Dall, Apad, M, C, ldc, t, row0);
     drs_count_launch();
@@ -784,6 +795,7 @@ int make_plan(int n, int npad, int m, const int32_t* src, const int32_t* dst, in
   p->d_top_moff = (const int64_t*)(b + o_tm); p->d_top_qpad = (const int32_t*)(b + o_tq);
   { const char* e = getenv("DRS_SEP_NO_MIRROR"); p->no_mirror = e && e[0] == '1'; }
   { const char* e = getenv("DRS_SEP_NO_U16"); p->no16 = e && e[0] == '1'; }
+  { const char* e = getenv("DRS_SEP_TILE64"); p->tile64 = e && e[0] == '1'; }
   if (S_lists_out) *S_lists_out = std::move(S);
   *out = p;
   return DRS_OK;

@@ -251,3 +251,29 @@ def test_a_second_graph_reuses_the_blocks_of_the_first():
     G.build()
     assert lib.drs_alloc_count() > a0                              # after a trim the blocks come from the driver again
     G.close()
+
+
+@pytest.mark.parametrize("tile64", ["0", "1"])
+def test_both_heights_of_the_16_bit_output_tiles(tile64, monkeypatch):
+    """DRS_SEP_TILE64 selects 64-row output tiles (128 threads, six CTAs per SM) instead of 128-row ones on the 16-bit path:
+    same matrix either way, whole and by row shards, undirected (mirrored tiles) and directed."""
+    import torch
+    from drs_abm_b200 import _lib, synth
+    from drs_abm_b200.apsp_dist import CudaTiles, build_sharded
+    from drs_abm_b200.routing import RoadGraph
+    monkeypatch.setenv("DRS_SEP_TILE64", tile64)
+    for data in (synth.config_graph("C2"), _random_planar(n_side=30, seed=12, directed=True)):
+        G = RoadGraph(data, part_target=100, second_level_min=1)
+        h = G.upload()
+        tiles = CudaTiles(h, _lib.MODE_F32)
+        npad = (data.n + 127) // 128 * 128
+        a, _, _ = build_sharded(tiles, npad, algorithm="sep", with_pred=False)
+        used = C.c_int32(0)
+        _lib.check(G._lib.drs_sep_info2(h, None, None, C.byref(used)), G._lib)
+        assert used.value == 1
+        b, _, _ = build_sharded(tiles, npad, algorithm="sssp", with_pred=False)
+        assert torch.equal(a, b)
+        top = torch.empty((384, npad), dtype=torch.float32, device="cuda")
+        tiles.sep_rows(top, 256); torch.cuda.synchronize()
+        assert torch.equal(top, a[256:640])
+        G.close()
