@@ -59,7 +59,7 @@ struct drs_sep_plan {
   int32_t* d_flags = nullptr;    // [0] largest finite separator-to-separator distance, [1] largest finite distance inside a closed part (float bits)
   bool used16 = false;           // the last build ran S3 and S4 on the 16-bit path
   bool no16 = false;             // DRS_SEP_NO_U16=1 (measurement knob)
-  bool tile64 = false;           // DRS_SEP_TILE64: 16-bit output tiles of 64 rows
+  int tile_rows = 32;            // rows of a 16-bit output tile: 32 (default), DRS_SEP_TILE_ROWS=64 or 128
   double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   bool no_mirror = false;   // DRS_SEP_NO_MIRROR=1: compute every output tile (measurement knob)
   int n = 0, npad = 0;      // vertices of this level and their padded count (the leading dimension of its matrix)
@@ -299,12 +299,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) sep_expand_rows_kernel(const T* _
   acc_store<T>(acc, Duni + (int64_t)row0 * t.spad + (int64_t)blockIdx.x * TILE, t.spad, pe - row0, TILE, tid);
 }
 
-// the same tiles on the 16-bit path (fp32 D_uni out)
-__global__ void __launch_bounds__(NTHREADS, 3) sep_expand_rows16_kernel(const uint32_t* __restrict__ Aprime16, const uint16_t* __restrict__ dSr16,
-                                                                          float* __restrict__ Duni, SepTab t, int row_lo, int row_hi) {
+// the same tiles on the 16-bit path (fp32 D_uni out), ROWS rows high (grid.y = row tiles of that height)
+template <int ROWS>
+__global__ void __launch_bounds__(2 * ROWS, ROWS == TILE ? 3 : ROWS == 64 ? 6 : 8)
+sep_expand_rows16_kernel(const uint32_t* __restrict__ Aprime16, const uint16_t* __restrict__ dSr16, float* __restrict__ Duni, SepTab t,
+                         int row_lo, int row_hi) {
   const int i = blockIdx.z;
-  const int row0 = t.pstart[i] + blockIdx.y * TILE, pe = t.pend[i];
-  if (row0 >= pe || row0 >= row_hi || min(row0 + TILE, pe) <= row_lo) return;
+  const int row0 = t.pstart[i] + blockIdx.y * ROWS, pe = t.pend[i];
+  if (row0 >= pe || row0 >= row_hi || min(row0 + ROWS, pe) <= row_lo) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   uint32_t acc2[8][4];
@@ -312,9 +314,9 @@ __global__ void __launch_bounds__(NTHREADS, 3) sep_expand_rows16_kernel(const ui
   for (int r = 0; r < 8; ++r)
 #pragma unroll
     for (int p = 0; p < 4; ++p) acc2[r][p] = U16_INF * 0x10001u;
-  tile_accumulate_u16<TILE>(acc2, Aprime16 + (int64_t)row0 * t.kmax, t.kmax, dSr16 + (int64_t)t.koff[i] * t.spad + (int64_t)blockIdx.x * TILE,
-                      t.spad, t.kpad[i], smem_raw, tid);
-  acc16_store<TILE>(acc2, Duni + (int64_t)row0 * t.spad + (int64_t)blockIdx.x * TILE, t.spad, pe - row0, TILE, tid, 0);
+  tile_accumulate_u16<ROWS>(acc2, Aprime16 + (int64_t)row0 * t.kmax, t.kmax, dSr16 + (int64_t)t.koff[i] * t.spad + (int64_t)blockIdx.x * TILE,
+                            t.spad, t.kpad[i], smem_raw, tid);
+  acc16_store<ROWS>(acc2, Duni + (int64_t)row0 * t.spad + (int64_t)blockIdx.x * TILE, t.spad, pe - row0, TILE, tid, 0);
 }
 
 // S3x: SPREAD_ROWS rows of the shard per CTA: the rows of D_uni spread over the per-part k ranges (D_all, the A operand
@@ -390,7 +392,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) sep_expand_kernel(const T* __rest
 // S4 on the 16-bit path (fp32 matrices of maps whose distances stay below 2^15): same tiles, VIADDMNMX.U16x2 inside.
 // ROWS = 128 (three CTAs of 256 threads per SM) or 64 (six CTAs of 128 threads: minplus.cuh, Tile16)
 template <bool MIRROR, int ROWS>
-__global__ void __launch_bounds__(2 * ROWS, ROWS == TILE ? 3 : 6)
+__global__ void __launch_bounds__(2 * ROWS, ROWS == TILE ? 3 : ROWS == 64 ? 6 : 8)
 sep_expand16_kernel(const uint32_t* __restrict__ Dall2, const uint16_t* __restrict__ Apad16, const float* __restrict__ M,
                     float* __restrict__ C, int64_t ldc, SepTab t, int row_lo) {
   constexpr int RG = Tile16<ROWS>::RG;
@@ -485,11 +487,13 @@ int configure_kernels() {
   DRS_CUDA(cudaFuncSetAttribute(sep_expand_rows_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
   DRS_CUDA(cudaFuncSetAttribute(sep_expand_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
   DRS_CUDA(cudaFuncSetAttribute(sep_expand_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
-  DRS_CUDA(cudaFuncSetAttribute(sep_expand_rows16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTile16SmemBytes));
+  DRS_CUDA(cudaFuncSetAttribute(sep_expand_rows16_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tile16<64>::smem_bytes));
   DRS_CUDA(cudaFuncSetAttribute(sep_expand16_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tile16<128>::smem_bytes));
   DRS_CUDA(cudaFuncSetAttribute(sep_expand16_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tile16<128>::smem_bytes));
   DRS_CUDA(cudaFuncSetAttribute(sep_expand16_kernel<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tile16<64>::smem_bytes));
   DRS_CUDA(cudaFuncSetAttribute(sep_expand16_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tile16<64>::smem_bytes));
+  DRS_CUDA(cudaFuncSetAttribute(sep_expand16_kernel<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tile16<32>::smem_bytes));
+  DRS_CUDA(cudaFuncSetAttribute(sep_expand16_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tile16<32>::smem_bytes));
   if (dev >= 0 && dev < 64) configured[dev] = true;
   return DRS_OK;
 }
@@ -615,9 +619,11 @@ int run_level(drs_sep_plan* p, const LevelInput& in, int mode, bool directed, T*
   }
   {
     const dim3 grid(p->spad / TILE, p->max_rowtiles, p->nparts);
-    if (use16)
-      sep_expand_rows16_kernel<<<grid, NTHREADS, kTile16SmemBytes, st>>>((const uint32_t*)p->d_Aprime16, (const uint16_t*)p->d_dSr16,
-                                                                         (float*)Duni, t, row0, row0 + nrows);
+    if (use16) {
+      const dim3 g64(p->spad / TILE, p->max_rowtiles * 2, p->nparts);
+      sep_expand_rows16_kernel<64><<<g64, 128, Tile16<64>::smem_bytes, st>>>((const uint32_t*)p->d_Aprime16, (const uint16_t*)p->d_dSr16,
+                                                                             (float*)Duni, t, row0, row0 + nrows);
+    }
     else sep_expand_rows_kernel<T><<<grid, NTHREADS, kTileSmemBytes, st>>>(Apr, dSr, Duni, t, row0, row0 + nrows);
   }
   drs_count_launch();
@@ -637,10 +643,14 @@ int run_level(drs_sep_plan* p, const LevelInput& in, int mode, bool directed, T*
       const uint16_t* A16 = (const uint16_t*)p->d_Apad16;
       const float* Mf = (const float*)p->d_M;
       float* Cf = (float*)C;
-      if (p->tile64) {
+      if (p->tile_rows == 64) {
         const dim3 g64(p->ncoltiles, nrows / 64);
         if (mirror) sep_expand16_kernel<true, 64><<<g64, 128, Tile16<64>::smem_bytes, st>>>(D2, A16, Mf, Cf, ldc, t, row0);
         else sep_expand16_kernel<false, 64><<<g64, 128, Tile16<64>::smem_bytes, st>>>(D2, A16, Mf, Cf, ldc, t, row0);
+      } else if (p->tile_rows == 32) {
+        const dim3 g32(p->ncoltiles, nrows / 32);
+        if (mirror) sep_expand16_kernel<true, 32><<<g32, 64, Tile16<32>::smem_bytes, st>>>(D2, A16, Mf, Cf, ldc, t, row0);
+        else sep_expand16_kernel<false, 32><<<g32, 64, Tile16<32>::smem_bytes, st>>>(D2, A16, Mf, Cf, ldc, t, row0);
       } else if (mirror) sep_expand16_kernel<true, 128><<<grid, NTHREADS, Tile16<128>::smem_bytes, st>>>(D2, A16, Mf, Cf, ldc, t, row0);
       else sep_expand16_kernel<false, 128><<<grid, NTHREADS, Tile16<128>::smem_bytes, st>>>(D2, A16, Mf, Cf, ldc, t, row0);
     } else if (mirror) sep_expand_kernel<T, true><<<grid, NTHREADS, kTileSmemBytes, st>>>(Dall, Apad, M, C, ldc, t, row0);
@@ -795,7 +805,7 @@ int make_plan(int n, int npad, int m, const int32_t* src, const int32_t* dst, in
   p->d_top_moff = (const int64_t*)(b + o_tm); p->d_top_qpad = (const int32_t*)(b + o_tq);
   { const char* e = getenv("DRS_SEP_NO_MIRROR"); p->no_mirror = e && e[0] == '1'; }
   { const char* e = getenv("DRS_SEP_NO_U16"); p->no16 = e && e[0] == '1'; }
-  { const char* e = getenv("DRS_SEP_TILE64"); p->tile64 = e && e[0] == '1'; }
+  { const char* e = getenv("DRS_SEP_TILE_ROWS"); const int v = e ? atoi(e) : 32; p->tile_rows = (v == 128 || v == 64) ? v : 32; }
   if (S_lists_out) *S_lists_out = std::move(S);
   *out = p;
   return DRS_OK;

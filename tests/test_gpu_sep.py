@@ -253,15 +253,15 @@ def test_a_second_graph_reuses_the_blocks_of_the_first():
     G.close()
 
 
-@pytest.mark.parametrize("tile64", ["0", "1"])
-def test_both_heights_of_the_16_bit_output_tiles(tile64, monkeypatch):
-    """DRS_SEP_TILE64 selects 64-row output tiles (128 threads, six CTAs per SM) instead of 128-row ones on the 16-bit path:
-    same matrix either way, whole and by row shards, undirected (mirrored tiles) and directed."""
+@pytest.mark.parametrize("tile_rows", ["128", "64", "32"])
+def test_every_height_of_the_16_bit_output_tiles(tile_rows, monkeypatch):
+    """DRS_SEP_TILE_ROWS selects the height of the 16-bit output tiles (64 rows = 128 threads, six CTAs per SM, is the default):
+    same matrix at every height, whole and by row shards, undirected (mirrored tiles) and directed."""
     import torch
     from drs_abm_b200 import _lib, synth
     from drs_abm_b200.apsp_dist import CudaTiles, build_sharded
     from drs_abm_b200.routing import RoadGraph
-    monkeypatch.setenv("DRS_SEP_TILE64", tile64)
+    monkeypatch.setenv("DRS_SEP_TILE_ROWS", tile_rows)
     for data in (synth.config_graph("C2"), _random_planar(n_side=30, seed=12, directed=True)):
         G = RoadGraph(data, part_target=100, second_level_min=1)
         h = G.upload()
