@@ -66,7 +66,7 @@ constexpr size_t kTileSmemBytes = sizeof(float) * STAGES * (TILE * APAD + KC * T
 // Tile coordinates of accumulator element acc[r][c] of thread (tx = tid & 15, ty = tid >> 4).
 // fp32 (packed): rows ty + 16 r, the four column pairs 32 j + 2 tx (keeps the k-pair-interleaved B loads conflict-free);
 // int32: rows ty + 16 r, columns 4 tx .. and 64 + 4 tx ..
-template <typename T> __device__ __forceinline__ int acc_row(int r, int ty) { return ty + 16 * r; }
+template <typename T, int ROWS = TILE> __device__ __forceinline__ int acc_row(int r, int ty) { return ty + (ROWS / 8) * r; }
 template <typename T> __device__ __forceinline__ int acc_col(int c, int tx) {
   if (Semiring<T>::packed) return 32 * (c >> 1) + 2 * tx + (c & 1);
   return (c < 4) ? tx * 4 + c : 64 + tx * 4 + (c - 4);
@@ -104,15 +104,15 @@ template <typename T> __device__ __forceinline__ void acc_load(T (&acc)[8][8], c
 
 // Accumulators to the tile at C; rows >= rows and columns outside [col_lo, cols) are not written (edge tiles store
 // element-wise).
-template <typename T> __device__ __forceinline__ void acc_store(const T (&acc)[8][8], T* C, int64_t ldc, int rows, int cols, int tid,
-                                                               int col_lo = 0) {
+template <typename T, int ROWS = TILE>
+__device__ __forceinline__ void acc_store(const T (&acc)[8][8], T* C, int64_t ldc, int rows, int cols, int tid, int col_lo = 0) {
   using V4 = typename Vec4<T>::type;
   using V2 = typename Vec2<T>::type;
   const int tx = tid & 15, ty = tid >> 4;
-  if (rows >= TILE && cols >= TILE && col_lo <= 0) {
+  if (rows >= ROWS && cols >= TILE && col_lo <= 0) {
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-      T* crow = C + (int64_t)(ty + 16 * r) * ldc;
+      T* crow = C + (int64_t)(ty + (ROWS / 8) * r) * ldc;
       if (Semiring<T>::packed) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -131,7 +131,7 @@ template <typename T> __device__ __forceinline__ void acc_store(const T (&acc)[8
   }
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
-    const int row = ty + 16 * r;
+    const int row = ty + (ROWS / 8) * r;
     if (row >= rows) continue;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
@@ -144,27 +144,29 @@ template <typename T> __device__ __forceinline__ void acc_store(const T (&acc)[8
 // The transposed tile: element (row, col) of the accumulators goes to Ct[col * ldc + row] for col in [col_lo, col_hi) and
 // row < rows, staged through shared memory (TILE x (TILE + 1) elements of smem_raw, free once tile_accumulate has
 // returned) so that the global stores run along rows of Ct.
-constexpr int TPITCH = TILE + 4;   // staged rows stay 16-byte aligned
-// staged row v is rotated by 4 tx(v) elements (tx = the lane that owns column v): the lanes of a staging store spread over
-// the banks, and a row segment of four stays one aligned 128-bit shared load
+// staged row v (a column of the tile, ROWS values, pitch ROWS + 4 so that rows stay 16-byte aligned) is rotated by 4 tx(v)
+// elements (tx = the lane that owns column v): the lanes of a staging store spread over the banks, and a row segment of
+// four stays one aligned 128-bit shared load
 template <typename T> __device__ __forceinline__ int stage_rot(int v) { return Semiring<T>::packed ? 4 * ((v >> 1) & 15) : 4 * ((v >> 2) & 15); }
-template <typename T> __device__ __forceinline__ void acc_store_transposed(const T (&acc)[8][8], unsigned char* smem_raw, T* Ct, int64_t ldc,
-                                                                          int col_lo, int col_hi, int rows, int tid) {
+template <typename T, int ROWS = TILE>
+__device__ __forceinline__ void acc_store_transposed(const T (&acc)[8][8], unsigned char* smem_raw, T* Ct, int64_t ldc, int col_lo, int col_hi,
+                                                     int rows, int tid) {
   using V4 = typename Vec4<T>::type;
+  constexpr int NT = 2 * ROWS, PITCH = ROWS + 4, LPR = ROWS / 4, RPW = 32 / LPR;
   T* s = reinterpret_cast<T*>(smem_raw);
   const int tx = tid & 15, ty = tid >> 4;
 #pragma unroll
   for (int r = 0; r < 8; ++r)
 #pragma unroll
-    for (int c = 0; c < 8; ++c) s[acc_col<T>(c, tx) * TPITCH + ((acc_row<T>(r, ty) + 4 * tx) & (TILE - 1))] = acc[r][c];
+    for (int c = 0; c < 8; ++c) s[acc_col<T>(c, tx) * PITCH + ((acc_row<T, ROWS>(r, ty) + 4 * tx) & (ROWS - 1))] = acc[r][c];
   __syncthreads();
   const int warp = tid >> 5, lane = tid & 31;
-  for (int v = warp; v < TILE; v += NTHREADS / 32) {
+  for (int v = warp * RPW + lane / LPR; v < TILE; v += (NT / 32) * RPW) {
     if (v < col_lo || v >= col_hi) continue;
     T* crow = Ct + (int64_t)v * ldc;
-    const int u = lane * 4;
-    const V4 q4 = *reinterpret_cast<const V4*>(s + v * TPITCH + ((u + stage_rot<T>(v)) & (TILE - 1)));
-    if (u + 3 < rows) *reinterpret_cast<V4*>(crow + u) = q4;     // one 512-byte row segment per warp instruction
+    const int u = (lane % LPR) * 4;
+    const V4 q4 = *reinterpret_cast<const V4*>(s + v * PITCH + ((u + stage_rot<T>(v)) & (ROWS - 1)));
+    if (u + 3 < rows) *reinterpret_cast<V4*>(crow + u) = q4;     // whole 16-byte segments of a transposed row
     else {
       if (u < rows) crow[u] = q4.x;
       if (u + 1 < rows) crow[u + 1] = q4.y;
@@ -252,13 +254,22 @@ __device__ __forceinline__ void fw_close_diag_tile(T* D, int64_t ld, int tid, Pe
 // (16-byte aligned rows), B: kcols rows x 128 columns (16-byte aligned rows for int32, 4-byte for fp32).  smem_raw: kTileSmemBytes of dynamic shared memory.
 // Returns with every copy drained and every thread past its last shared-memory read, so the ring can be refilled at once
 // (the multi-pass tiles of the separator build call it once per pass).
-template <typename T>
+// ROWS = rows of the tile (128: 256 threads, or 64: 128 threads and half-height tiles, more and smaller CTAs per SM), NSTG =
+// stages of the ring (3, or 2 so that four 64-row CTAs fit an SM).
+template <int ROWS, int NSTG> struct TileCfg {
+  static constexpr int NT = 2 * ROWS;
+  static constexpr size_t ring_bytes = sizeof(float) * NSTG * (ROWS * APAD + KC * TILE);
+  static constexpr size_t stage_bytes = sizeof(float) * TILE * (ROWS + 4);   // acc_store_transposed
+  static constexpr size_t smem_bytes = ring_bytes > stage_bytes ? ring_bytes : stage_bytes;
+};
+template <typename T, int ROWS = TILE, int NSTG = STAGES>
 __device__ __forceinline__ void tile_accumulate(T (&acc)[8][8], const T* __restrict__ A, int64_t lda, const T* __restrict__ B,
                                                 int64_t ldb, int kcols, unsigned char* smem_raw, int tid) {
   using V4 = typename Vec4<T>::type;
   using V2 = typename Vec2<T>::type;
-  T(*As)[TILE][APAD] = reinterpret_cast<T(*)[TILE][APAD]>(smem_raw);
-  T(*Bs)[KC][TILE] = reinterpret_cast<T(*)[KC][TILE]>(smem_raw + sizeof(T) * STAGES * TILE * APAD);
+  constexpr int NT = 2 * ROWS, RG = ROWS / 8;
+  T(*As)[ROWS][APAD] = reinterpret_cast<T(*)[ROWS][APAD]>(smem_raw);
+  T(*Bs)[KC][TILE] = reinterpret_cast<T(*)[KC][TILE]>(smem_raw + sizeof(T) * NSTG * ROWS * APAD);
   const int tx = tid & 15, ty = tid >> 4;
   constexpr bool kPacked = Semiring<T>::packed;
   if (kcols <= 0) return;
@@ -268,8 +279,8 @@ __device__ __forceinline__ void tile_accumulate(T (&acc)[8][8], const T* __restr
   auto load_chunk = [&](int kc, int stage) {
     const int k0 = kc * KC;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {   // A chunk: 128 rows x 32 k
-      const int v = tid + NTHREADS * q;
+    for (int q = 0; q < ROWS * 8 / NT; ++q) {   // A chunk: ROWS rows x 32 k
+      const int v = tid + NT * q;
       const int row = v >> 3, cv = v & 7;
       cp_async16(&As[stage][row][cv * 4], A + (int64_t)row * lda + k0 + cv * 4);
     }
@@ -278,34 +289,40 @@ __device__ __forceinline__ void tile_accumulate(T (&acc)[8][8], const T* __restr
       // 8-byte shared load yields the operand pair of a packed add (FADD2) -- 4-byte cp.async, coalesced per row
       float* Bf = reinterpret_cast<float*>(&Bs[stage][0][0]);
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const int e = tid + NTHREADS * q;
+      for (int q = 0; q < KC * TILE / NT; ++q) {
+        const int e = tid + NT * q;
         const int row = e >> 7, col = e & 127;
         cp_async4(Bf + ((row >> 1) * TILE + col) * 2 + (row & 1), B + (int64_t)(k0 + row) * ldb + col);
       }
     } else {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {   // B chunk: 32 k x 128 columns
-        const int v = tid + NTHREADS * q;
+      for (int q = 0; q < KC * TILE / 4 / NT; ++q) {   // B chunk: 32 k x 128 columns
+        const int v = tid + NT * q;
         const int row = v >> 5, cv = v & 31;
         cp_async16(&Bs[stage][row][cv * 4], B + (int64_t)(k0 + row) * ldb + cv * 4);
       }
     }
   };
 
-  load_chunk(0, 0);
-  cp_async_commit();
-  if (nchunk > 1) load_chunk(1, 1);
-  cp_async_commit();
+  // NSTG == 3: two chunks in flight ahead of the one being used, the ring refilled without a second barrier (the FW tiles:
+  // four chunks).  NSTG == 2 (short tiles, two or three chunks): both stages are requested at entry -- the latency of the
+  // first loads is what the CTA waits for -- and a third chunk reuses its stage after a second barrier.
+  constexpr int AHEAD = NSTG == 2 ? 2 : NSTG - 1;
+#pragma unroll
+  for (int q = 0; q < AHEAD; ++q) {
+    if (q < nchunk) load_chunk(q, q);
+    cp_async_commit();
+  }
 
 #pragma unroll 1
   for (int kc = 0; kc < nchunk; ++kc) {
-    const int stage = kc % STAGES;
-    cp_async_wait<STAGES - 2>();
+    const int stage = kc % NSTG;
+    cp_async_wait<AHEAD - 1>();
     __syncthreads();
-    if (kc + STAGES - 1 < nchunk) load_chunk(kc + STAGES - 1, (kc + STAGES - 1) % STAGES);
-    cp_async_commit();
-
+    if (NSTG != 2) {
+      if (kc + NSTG - 1 < nchunk) load_chunk(kc + NSTG - 1, (kc + NSTG - 1) % NSTG);
+      cp_async_commit();
+    }
     const bool full = !(half_tail && kc == nchunk - 1);
     if (kPacked) {
       const float2* Bp = reinterpret_cast<const float2*>(&Bs[stage][0][0]);
@@ -314,7 +331,7 @@ __device__ __forceinline__ void tile_accumulate(T (&acc)[8][8], const T* __restr
         if (kk == KC / 2 && !full) break;
         float2 a[8], b[8];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) a[r] = *reinterpret_cast<const float2*>(&As[stage][ty + 16 * r][kk]);
+        for (int r = 0; r < 8; ++r) a[r] = *reinterpret_cast<const float2*>(&As[stage][ty + RG * r][kk]);
         const float2* brow = Bp + (kk >> 1) * TILE;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {   // columns 32j + 2tx, +1: 16 lanes x 16 B contiguous per load
@@ -337,7 +354,7 @@ __device__ __forceinline__ void tile_accumulate(T (&acc)[8][8], const T* __restr
         if (kk == KC / 2 && !full) break;
         V2 a[8];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) a[r] = *reinterpret_cast<const V2*>(&As[stage][ty + 16 * r][kk]);
+        for (int r = 0; r < 8; ++r) a[r] = *reinterpret_cast<const V2*>(&As[stage][ty + RG * r][kk]);
         const V4 b0l = *reinterpret_cast<const V4*>(&Bs[stage][kk][tx * 4]);
         const V4 b0h = *reinterpret_cast<const V4*>(&Bs[stage][kk][64 + tx * 4]);
         const V4 b1l = *reinterpret_cast<const V4*>(&Bs[stage][kk + 1][tx * 4]);
@@ -349,6 +366,13 @@ __device__ __forceinline__ void tile_accumulate(T (&acc)[8][8], const T* __restr
 #pragma unroll
           for (int c = 0; c < 8; ++c) acc[r][c] = Semiring<T>::relax2(acc[r][c], a[r].x, b0[c], a[r].y, b1[c]);
       }
+    }
+    if (NSTG == 2) {
+      if (kc + 2 < nchunk) {   // every thread is done reading this stage before it is refilled
+        __syncthreads();
+        load_chunk(kc + 2, stage);
+      }
+      cp_async_commit();
     }
   }
   cp_async_wait<0>();

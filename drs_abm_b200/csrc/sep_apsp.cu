@@ -284,19 +284,21 @@ __global__ void sep_gather_dsr_kernel(const T* __restrict__ dS, SepTab t, T* __r
 // D_uni[u, s] = min_k A'[u, k] + dS[S_i[k], s] for the interior vertices u of part i: grid (spad / 128, max row tiles of a
 // part, nparts).  Row tiles start at the part's first vertex; rows past its last one are computed from the next part's A'
 // rows and not stored.
+constexpr int XROWS = 64, XSTG = 2;   // 32-bit expansion tiles: 64 rows (128 threads), two-stage ring: four CTAs per SM
+using XCfg = TileCfg<XROWS, XSTG>;
 template <typename T>
-__global__ void __launch_bounds__(NTHREADS, 2) sep_expand_rows_kernel(const T* __restrict__ Aprime, const T* __restrict__ dSr,
+__global__ void __launch_bounds__(XCfg::NT, 4) sep_expand_rows_kernel(const T* __restrict__ Aprime, const T* __restrict__ dSr,
                                                                         T* __restrict__ Duni, SepTab t, int row_lo, int row_hi) {
   const int i = blockIdx.z;
-  const int row0 = t.pstart[i] + blockIdx.y * TILE, pe = t.pend[i];
-  if (row0 >= pe || row0 >= row_hi || min(row0 + TILE, pe) <= row_lo) return;
+  const int row0 = t.pstart[i] + blockIdx.y * XROWS, pe = t.pend[i];
+  if (row0 >= pe || row0 >= row_hi || min(row0 + XROWS, pe) <= row_lo) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   T acc[8][8];
   acc_fill<T>(acc, Semiring<T>::inf());
-  tile_accumulate<T>(acc, Aprime + (int64_t)row0 * t.kmax, t.kmax, dSr + (int64_t)t.koff[i] * t.spad + (int64_t)blockIdx.x * TILE,
-                     t.spad, t.kpad[i], smem_raw, tid);
-  acc_store<T>(acc, Duni + (int64_t)row0 * t.spad + (int64_t)blockIdx.x * TILE, t.spad, pe - row0, TILE, tid);
+  tile_accumulate<T, XROWS, XSTG>(acc, Aprime + (int64_t)row0 * t.kmax, t.kmax,
+                                  dSr + (int64_t)t.koff[i] * t.spad + (int64_t)blockIdx.x * TILE, t.spad, t.kpad[i], smem_raw, tid);
+  acc_store<T, XROWS>(acc, Duni + (int64_t)row0 * t.spad + (int64_t)blockIdx.x * TILE, t.spad, pe - row0, TILE, tid);
 }
 
 // the same tiles on the 16-bit path (fp32 D_uni out), ROWS rows high (grid.y = row tiles of that height)
@@ -355,26 +357,26 @@ __global__ void sep_spread_kernel(const T* __restrict__ Duni, T* __restrict__ Da
 // matrix is written by exactly one tile.  MIRROR (undirected maps, whole-matrix builds): only the tiles that reach the
 // diagonal or lie above it are computed, and each also writes its transpose -- the matrix is symmetric.
 template <typename T, bool MIRROR>
-__global__ void __launch_bounds__(NTHREADS, 2) sep_expand_kernel(const T* __restrict__ Dall, const T* __restrict__ Apad,
+__global__ void __launch_bounds__(XCfg::NT, 4) sep_expand_kernel(const T* __restrict__ Dall, const T* __restrict__ Apad,
                                                                    const T* __restrict__ M, T* __restrict__ C, int64_t ldc, SepTab t,
                                                                    int row_lo) {
   const int ct = blockIdx.x;
   const int j = t.ct_part[ct], C0 = t.ct_col0[ct];
-  const int R0 = row_lo + blockIdx.y * TILE;
+  const int R0 = row_lo + blockIdx.y * XROWS;
   const int ps = t.pstart[j], pe = t.pend[j];
   const int col_lo = max(ps - C0, 0), col_hi = min(pe - C0, TILE);
-  if (MIRROR && !(C0 + col_hi > R0 || R0 + TILE > t.sep0)) return;   // strictly below the diagonal, interior rows: mirrored
+  if (MIRROR && !(C0 + col_hi > R0 || R0 + XROWS > t.sep0)) return;   // strictly below the diagonal, interior rows: mirrored
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   T acc[8][8];
   acc_fill<T>(acc, Semiring<T>::inf());
-  if (R0 < pe && R0 + TILE > ps) {   // rows of this tile lie in part j: paths that stay inside the closed part
+  if (R0 < pe && R0 + XROWS > ps) {   // rows of this tile lie in part j: paths that stay inside the closed part
     const int64_t ld = t.qpad[j];
     const T* Mj = M + t.moff[j];
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-      const int u = R0 + acc_row<T>(r, ty);
+      const int u = R0 + acc_row<T, XROWS>(r, ty);
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         const int v = C0 + acc_col<T>(c, tx);
@@ -382,11 +384,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) sep_expand_kernel(const T* __rest
       }
     }
   }
-  tile_accumulate<T>(acc, Dall + (int64_t)R0 * t.ktot + t.koff[j], t.ktot, Apad + t.apoff[j] + (C0 - t.cbase[j]), t.wpad[j],
-                     t.kpad[j], smem_raw, tid);
-  acc_store<T>(acc, C + (int64_t)(R0 - row_lo) * ldc + C0, ldc, TILE, col_hi, tid, col_lo);
+  tile_accumulate<T, XROWS, XSTG>(acc, Dall + (int64_t)R0 * t.ktot + t.koff[j], t.ktot, Apad + t.apoff[j] + (C0 - t.cbase[j]), t.wpad[j],
+                                  t.kpad[j], smem_raw, tid);
+  acc_store<T, XROWS>(acc, C + (int64_t)(R0 - row_lo) * ldc + C0, ldc, XROWS, col_hi, tid, col_lo);
   if (MIRROR && R0 < t.sep0)   // C[v][u] = C[u][v]; columns u are interior vertices only (separator columns: S4x)
-    acc_store_transposed<T>(acc, smem_raw, C + (int64_t)C0 * ldc + R0, ldc, col_lo, col_hi, min(TILE, t.sep0 - R0), tid);
+    acc_store_transposed<T, XROWS>(acc, smem_raw, C + (int64_t)C0 * ldc + R0, ldc, col_lo, col_hi, min(XROWS, t.sep0 - R0), tid);
 }
 
 // S4 on the 16-bit path (fp32 matrices of maps whose distances stay below 2^15): same tiles, VIADDMNMX.U16x2 inside.
@@ -484,9 +486,9 @@ int configure_kernels() {
   DRS_CUDA(cudaGetDevice(&dev));
   if (dev >= 0 && dev < 64 && configured[dev]) return DRS_OK;
   DRS_CUDA(cudaFuncSetAttribute(sep_fw_tile_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
-  DRS_CUDA(cudaFuncSetAttribute(sep_expand_rows_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
-  DRS_CUDA(cudaFuncSetAttribute(sep_expand_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
-  DRS_CUDA(cudaFuncSetAttribute(sep_expand_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
+  DRS_CUDA(cudaFuncSetAttribute(sep_expand_rows_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XCfg::smem_bytes));
+  DRS_CUDA(cudaFuncSetAttribute(sep_expand_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XCfg::smem_bytes));
+  DRS_CUDA(cudaFuncSetAttribute(sep_expand_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XCfg::smem_bytes));
   DRS_CUDA(cudaFuncSetAttribute(sep_expand_rows16_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tile16<64>::smem_bytes));
   DRS_CUDA(cudaFuncSetAttribute(sep_expand16_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tile16<128>::smem_bytes));
   DRS_CUDA(cudaFuncSetAttribute(sep_expand16_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tile16<128>::smem_bytes));
@@ -624,7 +626,10 @@ int run_level(drs_sep_plan* p, const LevelInput& in, int mode, bool directed, T*
       sep_expand_rows16_kernel<64><<<g64, 128, Tile16<64>::smem_bytes, st>>>((const uint32_t*)p->d_Aprime16, (const uint16_t*)p->d_dSr16,
                                                                              (float*)Duni, t, row0, row0 + nrows);
     }
-    else sep_expand_rows_kernel<T><<<grid, NTHREADS, kTileSmemBytes, st>>>(Apr, dSr, Duni, t, row0, row0 + nrows);
+    else {
+      const dim3 gx(p->spad / TILE, p->max_rowtiles * (TILE / XROWS), p->nparts);
+      sep_expand_rows_kernel<T><<<gx, XCfg::NT, XCfg::smem_bytes, st>>>(Apr, dSr, Duni, t, row0, row0 + nrows);
+    }
   }
   drs_count_launch();
   SEP_CHECK();
@@ -653,8 +658,11 @@ int run_level(drs_sep_plan* p, const LevelInput& in, int mode, bool directed, T*
         else sep_expand16_kernel<false, 32><<<g32, 64, Tile16<32>::smem_bytes, st>>>(D2, A16, Mf, Cf, ldc, t, row0);
       } else if (mirror) sep_expand16_kernel<true, 128><<<grid, NTHREADS, Tile16<128>::smem_bytes, st>>>(D2, A16, Mf, Cf, ldc, t, row0);
       else sep_expand16_kernel<false, 128><<<grid, NTHREADS, Tile16<128>::smem_bytes, st>>>(D2, A16, Mf, Cf, ldc, t, row0);
-    } else if (mirror) sep_expand_kernel<T, true><<<grid, NTHREADS, kTileSmemBytes, st>>>(Dall, Apad, M, C, ldc, t, row0);
-    else sep_expand_kernel<T, false><<<grid, NTHREADS, kTileSmemBytes, st>>>(Dall, Apad, M, C, ldc, t, row0);
+    } else {
+      const dim3 gx(p->ncoltiles, nrows / XROWS);
+      if (mirror) sep_expand_kernel<T, true><<<gx, XCfg::NT, XCfg::smem_bytes, st>>>(Dall, Apad, M, C, ldc, t, row0);
+      else sep_expand_kernel<T, false><<<gx, XCfg::NT, XCfg::smem_bytes, st>>>(Dall, Apad, M, C, ldc, t, row0);
+    }
     drs_count_launch();
   }
   SEP_CHECK();
