@@ -41,7 +41,7 @@ NCU_TRAFFIC = {
     "sssp_batch_kernel": (9.401e9 + 22.049e9, "profiles/r02_kernels_ncu.md"),
     "insertion_reach_kernel": (0.403e9 + 0.007e9, "profiles/r02_kernels_ncu.md"),
     "rv_filter_kernel": (0.404e9 + 0.022e9, "profiles/r02_kernels_ncu.md"),
-    "sep_expand16_kernel": (1.539e9 + 9.255e9, "profiles/r02_sep_ncu.md"),
+    "sep_expand16_kernel": (1.413e9 + 8.926e9, "profiles/r02_sep_ncu.md"),
     "sep_expand_kernel": (1.712e9 + 9.136e9, "profiles/r02_sep_ncu.md"),
 }
 

@@ -927,8 +927,9 @@ void level_work(const drs_sep_plan* p, bool directed, int row0, int nrows, doubl
   for (int ct = 0; ct < p->ncoltiles; ++ct) {
     const int j = p->ct_part[ct], c0 = p->ct_col0[ct];
     const int c1 = c0 + std::min(p->pend[j] - c0, TILE);
-    for (int r0 = row0; r0 < row1; r0 += TILE)
-      if (!mirror || c1 > r0 || r0 + TILE > p->sep0) w[3] += (double)TILE * TILE * p->kpad[j];
+    const int th = p->used16 ? p->tile_rows : XROWS;   // height of the output tiles of the last build (16-bit or 32-bit path)
+    for (int r0 = row0; r0 < row1; r0 += th)
+      if (!mirror || c1 > r0 || r0 + th > p->sep0) w[3] += (double)th * TILE * p->kpad[j];
   }
   if (mirror) w[4] *= 0.5;
 }
