@@ -165,8 +165,10 @@ int drs_apsp_rows_sep(const drs_graph* g, int32_t mode, void* local_dev, int64_t
  * tiles without padding = the algorithmic work of the dominant kernel: rows * sum_j n_j * |S_j|, halved for a whole
  * undirected matrix (mirrored tiles) */
 int drs_sep_work(const drs_graph* g, int32_t row0, int32_t nrows, double* relax5);
-/* milliseconds of the last SEP build by stage: fill+scatter, part closures, extraction, separator closure,
- * gathers, vertex->separator rows, output tiles, separator columns */
+/* milliseconds of the last SEP build by stage (the library's own CUDA events): [0] fill + scatter of the closed parts,
+ * [1] part closures, [2] extraction (A', A_j, separator-graph blocks), [3] separator closure (second level included),
+ * [4] gathers, [5] vertex->separator rows + the spread into the per-part ranges and the separator columns, [6] output
+ * tiles, [7] unused (the separator columns are written by the spread) */
 int drs_apsp_sep_profile(const drs_graph* g, double* ms8);
 
 /* Predecessors.  LAZY (default): no predecessor matrix; path queries evaluate the canonical rule on the
