@@ -46,5 +46,5 @@ for key, title in FAMILIES:
 print("\nBulk-copy engine: `UBLKCP.S.G` = `cp.async.bulk.shared::cluster.global` (the insertion reach test stages a matrix row per request),")
 print("`UBLKPF.L2` = `cp.async.bulk.prefetch.L2`, `SYNCS.*` = mbarrier arrive / try_wait.  `LDG.E.ENL2.256` = 256-bit global load (SSSP adjacency")
 print("records).  `FADD2` / `FMNMX3` / `VIADDMNMX` = packed fp32x2 add, 3-input min, DPX add+min (Floyd-Warshall and separator-build tiles;")
-print("`VIADDMNMX.U16x2`, two 16-bit relaxations per lane, in the 16-bit output tiles: %d static instances).  No `UTC*MMA` / `HMMA`:" % sum(v for k, v in hist["sep_expand16"].items() if k.startswith("VIADDMNMX.U16x2")))
+print("`VIADDMNMX.U16x2`, two 16-bit relaxations per lane, in the 16-bit output tiles: %d static instances).  No `UTC*MMA` / `HMMA`:" % sum(v for k, v in hist["sep_expand16"].items() if k.startswith("VIADDMNMX.U16")))
 print("min-plus is not a GEMM.")
