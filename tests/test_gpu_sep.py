@@ -199,6 +199,18 @@ def test_partition_is_validated_and_follows_weight_updates():
     from drs_abm_b200.gml import RoadGraphData
     d2 = RoadGraphData(data.n, data.directed, data.src, data.dst, data.vattrs, dict(data.eattrs, ttmedian=tt))
     assert np.array_equal(second, oracle_graph_from_data(d2).dist_matrix()) and not np.array_equal(first, second)
+    # the same graph turned float-weighted: the next build leaves the 16-bit path and stays within the float tolerance
+    used = C.c_int32(0)
+    _lib.check(lib.drs_sep_info2(h, None, None, C.byref(used)), lib)
+    assert used.value == 1
+    tt2 = tt.copy(); tt2[::5] += 0.37
+    G.es["ttmedian"] = tt2.tolist()
+    third = G.dist_rows(0, G.n)
+    _lib.check(lib.drs_sep_info2(h, None, None, C.byref(used)), lib)
+    assert used.value == 0
+    d3 = RoadGraphData(data.n, data.directed, data.src, data.dst, data.vattrs, dict(data.eattrs, ttmedian=tt2))
+    want3 = oracle_graph_from_data(d3).dist_matrix()
+    assert np.max(np.abs(third - want3) / np.maximum(want3, 1e-12)) < 1e-5
     G.close()
 
 
