@@ -37,7 +37,7 @@ class Vertex(object):
         return self.graph._vattrs[key][self.index]
 
     def __setitem__(self, key, value):
-        self.graph._vattrs.setdefault(key, [None] * self.graph.n)[self.index] = value
+        self.graph._own_vattr(key)[self.index] = value
         if key in ("name", "lng", "lat"):
             self.graph._by_name = self.graph._by_coord = None
 
@@ -257,10 +257,12 @@ class RoadGraph(object):
         self.n, self.m = data.n, data.m
         self.directed = data.directed
         self._src, self._dst = data.src, data.dst
-        self._vattrs = {k: list(v) for k, v in data.vattrs.items()}
+        # attribute columns are shared with `data` until the first write through this graph (copy on write: a fresh graph of a
+        # 50k-vertex map would otherwise spend milliseconds copying lists it never changes)
+        self._vattrs = dict(data.vattrs)
         self._coords = getattr(data, "coords", None)
-        self._eattrs = {k: (np.array(v, dtype=np.float64) if isinstance(v, np.ndarray) else list(v))
-                        for k, v in data.eattrs.items()}
+        self._eattrs = {k: (np.asarray(v, dtype=np.float64) if isinstance(v, np.ndarray) else v) for k, v in data.eattrs.items()}
+        self._owned = set()
         self.mode = mode
         self.pred = pred              # _lib.PRED_LAZY (canonical rule evaluated per hop of a path query) | PRED_MATRIX
         self.algorithm = algorithm    # _lib.APSP_FW (blocked Floyd-Warshall) | APSP_SSSP (N delta-stepping searches) | APSP_AUTO
@@ -393,6 +395,16 @@ class RoadGraph(object):
         return i
 
     # ------------------------------------------------------------------ device state
+    def _own_vattr(self, key):
+        """The list of a vertex attribute, private to this graph from now on (created if absent)."""
+        if ("v", key) not in self._owned:
+            cur = self._vattrs.get(key)
+            self._vattrs[key] = list(cur) if cur is not None else [None] * self.n
+            self._owned.add(("v", key))
+            if key in ("lng", "lat"):
+                self._coords = None          # the numeric copies made at load time no longer describe this graph
+        return self._vattrs[key]
+
     def _set_edge_attr(self, key, index, value):
         if index is None:
             vals = np.asarray(value, dtype=np.float64) if not isinstance(value, str) else value
@@ -401,9 +413,15 @@ class RoadGraph(object):
             if len(vals) != self.m:
                 raise ValueError("attribute list length (%d) != edge count (%d)" % (len(vals), self.m))
             self._eattrs[key] = np.array(vals, dtype=np.float64)
+            self._owned.add(("e", key))
         else:
             if key not in self._eattrs:
                 self._eattrs[key] = np.zeros(self.m, dtype=np.float64)
+                self._owned.add(("e", key))
+            elif ("e", key) not in self._owned:
+                cur = self._eattrs[key]
+                self._eattrs[key] = np.array(cur, dtype=np.float64) if isinstance(cur, np.ndarray) else list(cur)
+                self._owned.add(("e", key))
             self._eattrs[key][index] = value
         if key == self._weight_attr:
             self._weights_dirty = True

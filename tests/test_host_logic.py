@@ -368,3 +368,23 @@ def test_partition_order_gives_a_valid_separator_partition():
     check(2 * d.n, two[0], two[1], list(lng) * 2, list(lat) * 2, 300)    # coincident coordinates
     assert check(5, [], [], None, None, 2)[1] == 0                       # no edges: no separators
     assert 192 <= default_part_target(50171) <= 2048
+
+
+def test_attribute_writes_stay_private_to_the_graph():
+    """Attribute columns are shared with the loaded map until the first write (copy on write): writes through one graph
+    change neither the RoadGraphData nor another graph made from it (igraph semantics: every Graph owns its attributes)."""
+    from drs_abm_b200 import synth
+    from drs_abm_b200.routing import RoadGraph
+    data = synth.config_graph("C1")
+    lng0, tt0 = data.vattrs["lng"][0], float(data.eattrs["ttmedian"][3])
+    G1, G2 = RoadGraph(data), RoadGraph(data)
+    assert G1._vattrs["lng"] is data.vattrs["lng"]                 # shared until written
+    G1.vs[0]["lng"] = 99.5
+    G1.es[3]["ttmedian"] = 123.0
+    G1.vs[1]["colour"] = "red"                                      # a new attribute
+    assert G1.vs[0]["lng"] == 99.5 and G1.es[3]["ttmedian"] == 123.0 and G1.vs[1]["colour"] == "red" and G1.vs[2]["colour"] is None
+    assert data.vattrs["lng"][0] == lng0 and float(data.eattrs["ttmedian"][3]) == tt0 and "colour" not in data.vattrs
+    assert G2.vs[0]["lng"] == lng0 and G2.es[3]["ttmedian"] == tt0
+    assert G1._coords is None and G2._coords is not None           # the numeric coordinates of the load no longer describe G1
+    G1.es["ttmedian"] = [7.0] * G1.m                               # whole-column assignment
+    assert G1.es[0]["ttmedian"] == 7.0 and float(data.eattrs["ttmedian"][0]) != 7.0 or tt0 == 7.0
